@@ -1,0 +1,1388 @@
+// kvg_api.cu — the C-ABI of libkvgpu.so (include/kvgpu.h): context, HBM layout, launch sequencing
+// and result marshalling around the kernels in kvg_parse.cuh / kvg_scan.cuh.
+//
+// HBM layout owned by a context (all cudaMalloc'd once and grown geometrically, never per call):
+//   text      pci.ids image(s), padded with '\n' to a tile multiple + 16 (TMA halo)
+//   tables    open-addressed u64 slots  key(vendor<<16|device)<<32 | line offset
+//   pool      sanitised names of the NVIDIA section, slot = line offset - section offset
+//   recs      record staging (host entry points only)
+//   surv      compacted survivors, Walk order
+//   sort      2 x (keys,vals) ping-pong per ordering (device-id ordering, iommu-group ordering)
+//   seg       distinct keys + offsets per ordering
+// No CPU fallback exists anywhere below: every compute entry point fails with KVG_ECUDA when the
+// CUDA runtime is unusable.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/kvgpu.h"
+#include "kvg_common.cuh"
+#include "kvg_parse.cuh"
+#include "kvg_scan.cuh"
+
+using namespace kvg;
+
+// ------------------------------------------------------------------------------------------------
+// minimal NCCL surface, resolved with dlopen so single-GPU users need no NCCL at all
+// ------------------------------------------------------------------------------------------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct {
+  char internal[128];
+} ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclUint8 = 1, ncclUint32 = 3, ncclUint64 = 5 };
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string* err) {
+    if (handle) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (handle) break;
+    }
+    if (!handle) {
+      *err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror();
+      return false;
+    }
+#define KVG_SYM(field, name)                                   \
+  *(void**)(&field) = dlsym(handle, name);                     \
+  if (!field) {                                                \
+    *err = std::string("NCCL symbol missing: ") + name;        \
+    return false;                                              \
+  }
+    KVG_SYM(GetUniqueId, "ncclGetUniqueId");
+    KVG_SYM(CommInitRank, "ncclCommInitRank");
+    KVG_SYM(CommDestroy, "ncclCommDestroy");
+    KVG_SYM(AllGather, "ncclAllGather");
+    KVG_SYM(Broadcast, "ncclBroadcast");
+    KVG_SYM(GroupStart, "ncclGroupStart");
+    KVG_SYM(GroupEnd, "ncclGroupEnd");
+    KVG_SYM(GetErrorString, "ncclGetErrorString");
+#undef KVG_SYM
+    return true;
+  }
+};
+static NcclApi g_nccl;
+static std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+};
+
+struct PinnedBlock {
+  void* p;
+  size_t size;
+};
+
+struct OrderBufs {  // one stable ordering (sorted (key, index) pairs + segment heads)
+  DevBuf<uint32_t> k0, v0, k1, v1;
+  DevBuf<uint32_t> seg_key, seg_off;
+  DevBuf<uint64_t> heads_state;
+};
+
+struct kvg_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  std::string err;
+  uint64_t launches = 0;
+  uint32_t epoch = 1;
+
+  // pci.ids
+  DevBuf<uint8_t> text;  // owned copy (host entry point)
+  const uint8_t* d_text = nullptr;
+  uint32_t text_len = 0;
+  DevBuf<uint64_t> tables;
+  uint32_t cap_log2 = 0;
+  DevBuf<PciIdsInfo> info;
+  DevBuf<uint32_t> tile_arrays;  // 3 x n_tiles
+  DevBuf<uint64_t> parse_state;
+  DevBuf<uint32_t> parse_ticket;
+  DevBuf<uint8_t> pool;
+  std::vector<uint8_t> h_pool;
+  PciIdsInfo h_info{};
+  bool table_ready = false;
+  int parse_grid = 0;
+
+  // scans
+  DevBuf<ScanCtrl> ctrl;
+  ScanCtrl* h_ctrl = nullptr;  // pinned
+  DevBuf<uint4> recs;          // staging for host entry points
+  DevBuf<uint4> surv;
+  DevBuf<uint64_t> classify_state;
+  OrderBufs ord_dev, ord_grp;
+  DevBuf<uint32_t> tile_hist;
+  size_t last_n = 0;     // records of the last enqueued scan
+  size_t last_total = 0; // survivors capacity used by the last scan (sharded: all ranks)
+  int last_kind = 0;     // 1 = pci, 2 = mdev
+  // mdev dictionary
+  DevBuf<uint8_t> type_raw, type_label;
+  DevBuf<uint32_t> type_off, type_label_len, type_match, type_name_len;
+  DevBuf<uint16_t> type_canon;
+  DevBuf<uint8_t> type_names;
+  uint32_t n_types = 0;
+  std::vector<uint32_t> h_type_off;
+  // health
+  DevBuf<uint8_t> alive_prev;
+  DevBuf<uint32_t> changed;
+  size_t health_n = 0;
+  // misc
+  DevBuf<uint4> flush;
+  DevBuf<uint16_t> nv_ids;
+  DevBuf<uint32_t> probe_slots;
+  DevBuf<uint8_t> keys_blob;
+  DevBuf<uint32_t> keys_off, match_off, match_len;
+  DevBuf<uint8_t> match_out;
+  std::vector<PinnedBlock> pinned_free;
+  void* h_stage = nullptr;
+  size_t h_stage_cap = 0;
+  // kernel timing
+  bool timing = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  std::vector<std::string> ev_names;
+  size_t ev_used = 0;
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  DevBuf<uint64_t> gather_counts;  // [nranks]
+  DevBuf<uint4> local_surv;
+  uint64_t* h_counts = nullptr;  // pinned [nranks]
+};
+
+#define CK(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess) {                                                                  \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                          \
+      return KVG_ECUDA;                                                                       \
+    }                                                                                         \
+  } while (0)
+
+template <class T>
+static int ensure(kvg_ctx* ctx, DevBuf<T>& b, size_t n) {
+  if (n <= b.cap && b.p) return KVG_OK;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  size_t cap = n + n / 4 + 64;
+  cudaError_t e = cudaMalloc((void**)&b.p, cap * sizeof(T));
+  if (e != cudaSuccess) {
+    b.cap = 0;
+    ctx->err = std::string("cudaMalloc: ") + cudaGetErrorString(e);
+    return e == cudaErrorMemoryAllocation ? KVG_ENOMEM : KVG_ECUDA;
+  }
+  b.cap = cap;
+  return KVG_OK;
+}
+#define ENSURE(buf, n)                      \
+  do {                                      \
+    int rc_ = ensure(ctx, buf, n);          \
+    if (rc_) return rc_;                    \
+  } while (0)
+
+template <class T>
+static void release(DevBuf<T>& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+// launch bookkeeping: count + optional CUDA-event bracket on the context stream
+struct LaunchScope {
+  kvg_ctx* ctx;
+  size_t idx = (size_t)-1;
+  LaunchScope(kvg_ctx* c, const char* name) : ctx(c) {
+    ctx->launches++;
+    if (ctx->timing) {
+      if (ctx->ev_used == ctx->ev.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        ctx->ev.push_back({a, b});
+        ctx->ev_names.push_back("");
+      }
+      idx = ctx->ev_used++;
+      ctx->ev_names[idx] = name;
+      cudaEventRecord(ctx->ev[idx].first, ctx->stream);
+    }
+  }
+  ~LaunchScope() {
+    if (idx != (size_t)-1) cudaEventRecord(ctx->ev[idx].second, ctx->stream);
+  }
+};
+#define LAUNCH(name, kernel, grid, block, smem, ...)              \
+  do {                                                            \
+    LaunchScope ls_(ctx, name);                                   \
+    kernel<<<grid, block, smem, ctx->stream>>>(__VA_ARGS__);      \
+  } while (0)
+
+static int check_launch(kvg_ctx* ctx, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    ctx->err = std::string(what) + ": " + cudaGetErrorString(e);
+    return KVG_ECUDA;
+  }
+  return KVG_OK;
+}
+
+static void* pinned_alloc(kvg_ctx* ctx, size_t size) {
+  for (size_t i = 0; i < ctx->pinned_free.size(); i++) {
+    if (ctx->pinned_free[i].size >= size + 64) {
+      void* p = ctx->pinned_free[i].p;
+      ctx->pinned_free.erase(ctx->pinned_free.begin() + i);
+      return p;
+    }
+  }
+  void* p = nullptr;
+  size_t cap = size + size / 4 + 4096;
+  if (cudaMallocHost(&p, cap + 64) != cudaSuccess) return nullptr;
+  // header: owning ctx + capacity, so kvg_result_free can recycle without a ctx argument
+  ((uint64_t*)p)[0] = (uint64_t)(uintptr_t)ctx;
+  ((uint64_t*)p)[1] = cap;
+  return p;
+}
+static inline uint8_t* pinned_payload(void* blk) { return (uint8_t*)blk + 64; }
+
+extern "C" {
+
+int kvg_abi_version(void) { return KVG_ABI_VERSION; }
+
+int kvg_ctx_create(int cuda_device, kvg_ctx** out) {
+  if (!out) return KVG_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    g_create_error = std::string("no usable CUDA device: ") +
+                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    return KVG_ECUDA;
+  }
+  if (cuda_device < 0 || cuda_device >= n) {
+    g_create_error = "cuda_device out of range";
+    return KVG_EINVAL;
+  }
+  kvg_ctx* ctx = new kvg_ctx();
+  ctx->device = cuda_device;
+  if ((e = cudaSetDevice(cuda_device)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_error = std::string("cuda init: ") + cudaGetErrorString(e);
+    delete ctx;
+    return KVG_ECUDA;
+  }
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, cuda_device);
+  cudaFuncSetAttribute(k_pciids_parse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       (int)(P_STAGES * P_STAGE));
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pciids_parse, KVG_BLOCK, P_STAGES * P_STAGE);
+  if (occ < 1) occ = 1;
+  ctx->parse_grid = ctx->sm_count * occ;
+  if (ensure(ctx, ctx->ctrl, 1) != KVG_OK || cudaMallocHost((void**)&ctx->h_ctrl, sizeof(ScanCtrl)) != cudaSuccess) {
+    g_create_error = "control block allocation failed: " + ctx->err;
+    kvg_ctx_destroy(ctx);
+    return KVG_ENOMEM;
+  }
+  *out = ctx;
+  return KVG_OK;
+}
+
+void kvg_ctx_destroy(kvg_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+  release(ctx->text); release(ctx->tables); release(ctx->info); release(ctx->tile_arrays);
+  release(ctx->parse_state); release(ctx->parse_ticket); release(ctx->pool); release(ctx->ctrl);
+  release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist);
+  for (OrderBufs* o : {&ctx->ord_dev, &ctx->ord_grp}) {
+    release(o->k0); release(o->v0); release(o->k1); release(o->v1);
+    release(o->seg_key); release(o->seg_off); release(o->heads_state);
+  }
+  release(ctx->type_raw); release(ctx->type_label); release(ctx->type_off);
+  release(ctx->type_label_len); release(ctx->type_match); release(ctx->type_name_len);
+  release(ctx->type_canon); release(ctx->type_names); release(ctx->alive_prev);
+  release(ctx->changed); release(ctx->flush); release(ctx->nv_ids); release(ctx->probe_slots);
+  release(ctx->keys_blob); release(ctx->keys_off); release(ctx->match_off); release(ctx->match_len);
+  release(ctx->match_out); release(ctx->gather_counts); release(ctx->local_surv);
+  for (auto& b : ctx->pinned_free) cudaFreeHost(b.p);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
+  if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  for (auto& p : ctx->ev) {
+    cudaEventDestroy(p.first);
+    cudaEventDestroy(p.second);
+  }
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* kvg_last_error(kvg_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+uint64_t kvg_launch_count(kvg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* kvg_stream(kvg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+void kvg_result_free(void* result) {
+  if (!result) return;
+  void* blk = (uint8_t*)result - 64;
+  kvg_ctx* ctx = (kvg_ctx*)(uintptr_t)((uint64_t*)blk)[0];
+  size_t cap = ((uint64_t*)blk)[1];
+  // contexts outlive their results by contract (kvgpu.h); recycle the pinned block
+  if (ctx->pinned_free.size() < 8)
+    ctx->pinned_free.push_back({blk, cap});
+  else
+    cudaFreeHost(blk);
+}
+
+int kvg_set_kernel_timing(kvg_ctx* ctx, int enabled) {
+  if (!ctx) return KVG_EINVAL;
+  ctx->timing = enabled != 0;
+  ctx->ev_used = 0;
+  return KVG_OK;
+}
+
+int kvg_kernel_times(kvg_ctx* ctx, float* ms, char* names, size_t names_cap, int max_n) {
+  if (!ctx) return KVG_EINVAL;
+  CK(cudaStreamSynchronize(ctx->stream));
+  int n = 0;
+  size_t o = 0;
+  for (size_t i = 0; i < ctx->ev_used && n < max_n; i++) {
+    float t = 0;
+    cudaEventElapsedTime(&t, ctx->ev[i].first, ctx->ev[i].second);
+    ms[n] = t;
+    size_t l = ctx->ev_names[i].size() + 1;
+    if (names && o + l <= names_cap) {
+      memcpy(names + o, ctx->ev_names[i].c_str(), l);
+      o += l;
+    }
+    n++;
+  }
+  ctx->ev_used = 0;
+  return n;
+}
+
+// ================================================================================================
+// pci.ids
+// ================================================================================================
+size_t kvg_text_pad(size_t len) { return ((len + P_TILE - 1) / P_TILE) * P_TILE + P_HALO; }
+
+static uint32_t table_log2_for(size_t len) {
+  // ~1 device line per 77 bytes in pci.ids; keep the load factor under ~0.6
+  size_t want = len / 48 + 64;
+  uint32_t l = 10;
+  while (((size_t)1 << l) < want) l++;
+  return l;
+}
+
+static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t stride,
+                         uint32_t n_files) {
+  if (len == 0 || len >= 0xfffffff0ull) {
+    ctx->err = "pci.ids length out of range";
+    return KVG_EINVAL;
+  }
+  uint32_t tpf = (uint32_t)((len + P_TILE - 1) / P_TILE);
+  uint64_t n_tiles64 = (uint64_t)tpf * n_files;
+  if (n_tiles64 > 0x7fffffffull) {
+    ctx->err = "too many tiles";
+    return KVG_EINVAL;
+  }
+  uint32_t n_tiles = (uint32_t)n_tiles64;
+  ctx->cap_log2 = table_log2_for(len);
+  size_t cap = (size_t)1 << ctx->cap_log2;
+  ENSURE(ctx->tables, cap * n_files);
+  ENSURE(ctx->info, n_files);
+  ENSURE(ctx->tile_arrays, 3 * (size_t)n_tiles);
+  ENSURE(ctx->parse_state, n_tiles);
+  ENSURE(ctx->parse_ticket, 1);
+
+  ParseArgs A;
+  A.text = d_text;
+  A.stride = stride;
+  A.len = (uint32_t)len;
+  A.n_files = n_files;
+  A.tiles_per_file = tpf;
+  A.n_tiles = n_tiles;
+  A.tables = ctx->tables.p;
+  A.cap_mask = (uint32_t)cap - 1;
+  A.cap_shift = 32 - ctx->cap_log2;
+  A.info = ctx->info.p;
+  A.tile_first_hdr = ctx->tile_arrays.p;
+  A.tile_first_nl = ctx->tile_arrays.p + n_tiles;
+  A.tile_last_nl = ctx->tile_arrays.p + 2 * (size_t)n_tiles;
+  A.tile_state = ctx->parse_state.p;
+  A.epoch = ++ctx->epoch;
+  A.ticket = ctx->parse_ticket.p;
+
+  // table slots <- EMPTY, info <- {v_off = NONE, 0...}, ticket <- 0
+  {
+    size_t n64 = cap * n_files;
+    int grid = (int)((n64 / 4 + KVG_BLOCK - 1) / KVG_BLOCK);
+    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    if (grid < 1) grid = 1;
+    LAUNCH("table_clear", k_fill64, grid, KVG_BLOCK, 0, ctx->tables.p, n64, P_EMPTY);
+  }
+  CK(cudaMemsetAsync(ctx->info.p, 0, sizeof(PciIdsInfo) * n_files, ctx->stream));
+  CK(cudaMemset2DAsync(ctx->info.p, sizeof(PciIdsInfo), 0xff, sizeof(uint32_t), n_files, ctx->stream));
+  CK(cudaMemsetAsync(ctx->parse_ticket.p, 0, sizeof(uint32_t), ctx->stream));
+  int grid = ctx->parse_grid;
+  if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
+  LAUNCH("pciids_parse", k_pciids_parse, grid, KVG_BLOCK, P_STAGES * P_STAGE, A);
+  LAUNCH("pciids_finalize", k_pciids_finalize, n_files, KVG_BLOCK, 0, A);
+  return check_launch(ctx, "pciids parse");
+}
+
+// after the parse of image 0: sanitise the NVIDIA section into the pool and mirror it on the host
+static int table_publish(kvg_ctx* ctx, const uint8_t* d_text, size_t len) {
+  CK(cudaMemcpyAsync(&ctx->h_info, ctx->info.p, sizeof(PciIdsInfo), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->d_text = d_text;
+  ctx->text_len = (uint32_t)len;
+  ctx->h_pool.clear();
+  if (ctx->h_info.v_off != P_NONE) {
+    size_t sec = (size_t)ctx->h_info.sec_end - ctx->h_info.v_off;
+    ENSURE(ctx->pool, sec + 16);
+    CK(cudaMemsetAsync(ctx->pool.p, 0, sec + 16, ctx->stream));
+    int grid = (int)((sec + KVG_BLOCK - 1) / KVG_BLOCK);
+    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    if (grid < 1) grid = 1;
+    LAUNCH("pciids_sanitise", k_pciids_sanitise, grid, KVG_BLOCK, 0, d_text, (uint32_t)len,
+           ctx->info.p, ctx->pool.p);
+    int rc = check_launch(ctx, "pciids sanitise");
+    if (rc) return rc;
+    ctx->h_pool.resize(sec + 16);
+    CK(cudaMemcpyAsync(ctx->h_pool.data(), ctx->pool.p, sec + 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  } else {
+    ENSURE(ctx->pool, 16);
+  }
+  ctx->table_ready = true;
+  return KVG_OK;
+}
+
+int kvg_pciids_load(kvg_ctx* ctx, const uint8_t* text, size_t len) {
+  if (!ctx || (!text && len)) return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  ctx->table_ready = false;
+  if (len == 0) {  // an empty file: locateVendor fails, every lookup is "" (:382-385)
+    ENSURE(ctx->info, 1);
+    ENSURE(ctx->tables, 1024);
+    ctx->cap_log2 = 10;
+    LAUNCH("table_clear", k_fill64, 4, KVG_BLOCK, 0, ctx->tables.p, (size_t)1024, P_EMPTY);
+    PciIdsInfo z;
+    memset(&z, 0, sizeof z);
+    z.v_off = z.sec_end = P_NONE;
+    CK(cudaMemcpyAsync(ctx->info.p, &z, sizeof z, cudaMemcpyHostToDevice, ctx->stream));
+    ENSURE(ctx->text, 64);
+    return table_publish(ctx, ctx->text.p, 0);
+  }
+  size_t padded = kvg_text_pad(len);
+  ENSURE(ctx->text, padded);
+  CK(cudaMemsetAsync(ctx->text.p, '\n', padded, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->text.p, text, len, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = parse_enqueue(ctx, ctx->text.p, len, padded, 1);
+  if (rc) return rc;
+  return table_publish(ctx, ctx->text.p, len);
+}
+
+int kvg_dev_pciids_parse(kvg_ctx* ctx, const void* d_text, size_t len, size_t stride, uint32_t n_files) {
+  if (!ctx || !d_text || n_files == 0 || ((uintptr_t)d_text & 15) || (stride & 15) ||
+      (n_files > 1 && stride < kvg_text_pad(len)))
+    return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  int rc = parse_enqueue(ctx, (const uint8_t*)d_text, len, stride, n_files);
+  if (rc) return rc;
+  // bench path: sanitise on the stream without the host mirror round trip when the section
+  // bounds are already known to be the same image (first call publishes, later calls re-run K2)
+  if (!ctx->table_ready || ctx->d_text != d_text || ctx->text_len != len) return table_publish(ctx, (const uint8_t*)d_text, len);
+  size_t sec = ctx->h_pool.size();
+  if (sec > 16) {
+    int grid = (int)((sec + KVG_BLOCK - 1) / KVG_BLOCK);
+    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    LAUNCH("pciids_sanitise", k_pciids_sanitise, grid, KVG_BLOCK, 0, (const uint8_t*)d_text,
+           (uint32_t)len, ctx->info.p, ctx->pool.p);
+  }
+  return check_launch(ctx, "pciids sanitise");
+}
+
+int kvg_pciids_info(kvg_ctx* ctx, uint32_t* vendor_off, uint32_t* section_end, uint32_t* n_entries,
+                    uint32_t* n_lines) {
+  if (!ctx) return KVG_EINVAL;
+  if (!ctx->table_ready) {
+    ctx->err = "kvg_pciids_load has not been called";
+    return KVG_ESTATE;
+  }
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(&ctx->h_info, ctx->info.p, sizeof(PciIdsInfo), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (vendor_off) *vendor_off = ctx->h_info.v_off;
+  if (section_end) *section_end = ctx->h_info.sec_end;
+  if (n_entries) *n_entries = ctx->h_info.n_entries;
+  if (n_lines) *n_lines = ctx->h_info.n_lines;
+  return KVG_OK;
+}
+
+static bool canonical_key(const char* key, size_t keylen, uint32_t* val) {
+  if (keylen != 4) return false;
+  uint32_t v = 0;
+  for (int i = 0; i < 4; i++) {
+    char c = key[i];
+    uint32_t d;
+    if (c >= '0' && c <= '9') d = (uint32_t)(c - '0');
+    else if (c >= 'a' && c <= 'f') d = (uint32_t)(c - 'a' + 10);
+    else return false;
+    v = v * 16 + d;
+  }
+  *val = v;
+  return true;
+}
+
+// general path for n keys (arbitrary bytes); results land in ctx->match_len / match_out
+static int lookup_general(kvg_ctx* ctx, const uint8_t* d_keys, const uint32_t* d_key_off,
+                          uint32_t n_keys, uint32_t cap, uint8_t* d_out, uint32_t* d_out_len,
+                          uint32_t* d_match) {
+  if (n_keys == 0) return KVG_OK;
+  {
+    int grid = (int)((n_keys + KVG_BLOCK - 1) / KVG_BLOCK);
+    LAUNCH("match_clear", k_fill32, grid, KVG_BLOCK, 0, d_match, (size_t)n_keys, P_NONE);
+  }
+  size_t sec = ctx->h_info.v_off == P_NONE ? 0 : (size_t)ctx->h_info.sec_end - ctx->h_info.v_off;
+  if (sec) {
+    int gx = (int)((sec + KVG_BLOCK - 1) / KVG_BLOCK);
+    if (gx > 1024) gx = 1024;
+    for (uint32_t k0 = 0; k0 < n_keys; k0 += 65535) {
+      uint32_t nk = n_keys - k0 > 65535 ? 65535 : n_keys - k0;
+      dim3 grid(gx, nk);
+      LAUNCH("lookup_general", k_lookup_general, grid, KVG_BLOCK, 0, ctx->d_text, ctx->text_len,
+             ctx->info.p, d_keys, d_key_off + k0, d_match + k0);
+    }
+  }
+  int grid = (int)((n_keys + 63) / 64);
+  LAUNCH("sanitise_matches", k_sanitise_matches, grid, 64, 0, ctx->d_text, ctx->text_len, d_key_off,
+         d_match, n_keys, d_out, cap, d_out_len);
+  return check_launch(ctx, "lookup_general");
+}
+
+int kvg_name_lookup(kvg_ctx* ctx, const char* key, size_t keylen, char* out, size_t cap, size_t* outlen) {
+  if (!ctx || (!key && keylen) || !outlen) return KVG_EINVAL;
+  if (!ctx->table_ready) {
+    ctx->err = "kvg_pciids_load has not been called";
+    return KVG_ESTATE;
+  }
+  CK(cudaSetDevice(ctx->device));
+  *outlen = 0;
+  uint32_t v;
+  if (canonical_key(key, keylen, &v)) {  // hash path
+    ENSURE(ctx->probe_slots, 1);
+    LAUNCH("probe_keys", k_probe_keys, 1, 32, 0, ctx->tables.p, (1u << ctx->cap_log2) - 1,
+           32 - ctx->cap_log2, ctx->info.p, v, 1u, ctx->probe_slots.p);
+    uint32_t slot;
+    CK(cudaMemcpyAsync(&slot, ctx->probe_slots.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (slot == P_NONE) return KVG_OK;
+    size_t n = ctx->h_pool[slot] | ((size_t)ctx->h_pool[slot + 1] << 8);
+    if (n > cap) return KVG_ERANGE;
+    memcpy(out, &ctx->h_pool[slot + 2], n);
+    *outlen = n;
+    return KVG_OK;
+  }
+  // general path: prefix semantics on the GPU
+  uint32_t kcap = 4096;
+  for (;;) {
+    ENSURE(ctx->keys_blob, keylen + 16);
+    ENSURE(ctx->keys_off, 2);
+    ENSURE(ctx->match_off, 1);
+    ENSURE(ctx->match_len, 1);
+    ENSURE(ctx->match_out, kcap);
+    uint32_t off[2] = {0, (uint32_t)keylen};
+    if (keylen) CK(cudaMemcpyAsync(ctx->keys_blob.p, key, keylen, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->keys_off.p, off, sizeof off, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = lookup_general(ctx, ctx->keys_blob.p, ctx->keys_off.p, 1, kcap, ctx->match_out.p,
+                            ctx->match_len.p, ctx->match_off.p);
+    if (rc) return rc;
+    uint32_t n;
+    CK(cudaMemcpyAsync(&n, ctx->match_len.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (n > kcap) {  // name longer than the scratch: retry with the scanner's line limit
+      kcap = SCAN_TOKEN_MAX;
+      continue;
+    }
+    if (n > cap) return KVG_ERANGE;
+    if (n) CK(cudaMemcpy(out, ctx->match_out.p, n, cudaMemcpyDeviceToHost));
+    *outlen = n;
+    return KVG_OK;
+  }
+}
+
+int kvg_name_table(kvg_ctx* ctx, uint32_t first, uint32_t count, uint32_t* out_off, uint8_t* out_bytes, size_t cap) {
+  if (!ctx || !out_off || (!out_bytes && cap) || (uint64_t)first + count > 65536) return KVG_EINVAL;
+  if (!ctx->table_ready) {
+    ctx->err = "kvg_pciids_load has not been called";
+    return KVG_ESTATE;
+  }
+  CK(cudaSetDevice(ctx->device));
+  out_off[0] = 0;
+  if (count == 0) return KVG_OK;
+  ENSURE(ctx->probe_slots, count);
+  LAUNCH("probe_keys", k_probe_keys, (count + 255) / 256, 256, 0, ctx->tables.p,
+         (1u << ctx->cap_log2) - 1, 32 - ctx->cap_log2, ctx->info.p, first, count, ctx->probe_slots.p);
+  std::vector<uint32_t> slots(count);
+  CK(cudaMemcpyAsync(slots.data(), ctx->probe_slots.p, 4 * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  size_t o = 0;
+  for (uint32_t i = 0; i < count; i++) {
+    if (slots[i] != P_NONE) {
+      size_t n = ctx->h_pool[slots[i]] | ((size_t)ctx->h_pool[slots[i] + 1] << 8);
+      if (o + n > cap) return KVG_ERANGE;
+      memcpy(out_bytes + o, &ctx->h_pool[slots[i] + 2], n);
+      o += n;
+    }
+    out_off[i + 1] = (uint32_t)o;
+  }
+  return KVG_OK;
+}
+
+// ================================================================================================
+// scans
+// ================================================================================================
+static int compact_grid(kvg_ctx* ctx, size_t n_items) {
+  size_t tiles = (n_items + C_TILE - 1) / C_TILE;
+  size_t g = (size_t)ctx->sm_count * 6;  // 6 x 256 threads resident per SM
+  if (tiles < g) g = tiles;
+  return g < 1 ? 1 : (int)g;
+}
+
+static int ensure_order(kvg_ctx* ctx, OrderBufs& o, size_t cap) {
+  ENSURE(o.k0, cap); ENSURE(o.v0, cap); ENSURE(o.k1, cap); ENSURE(o.v1, cap);
+  ENSURE(o.seg_key, cap + 1); ENSURE(o.seg_off, cap + 2);
+  ENSURE(o.heads_state, (cap + C_TILE - 1) / C_TILE + 1);
+  return KVG_OK;
+}
+
+// stable LSD radix ordering of the survivors by one field + segment heads.
+//   sort_idx selects bin_total rows in ScanCtrl; npass_max bounds the passes launched.
+static int enqueue_order(kvg_ctx* ctx, OrderBufs& o, size_t cap, int src, int sort_idx,
+                         int npass_max, uint32_t* d_max_key, uint32_t* d_n_seg, uint32_t* ticket) {
+  size_t T = (cap + C_TILE - 1) / C_TILE;
+  if (T == 0) T = 1;
+  ENSURE(ctx->tile_hist, 256 * T);
+  uint32_t* kin = nullptr;
+  uint32_t* vin = nullptr;
+  for (int p = 0; p < npass_max; p++) {
+    RadixArgs a;
+    a.n_ptr = &ctx->ctrl.p->n_surv;
+    a.max_key = d_max_key;
+    a.src_records = ctx->surv.p;
+    a.keys_in = kin;
+    a.vals_in = vin;
+    a.keys_out = (p & 1) ? o.k1.p : o.k0.p;
+    a.vals_out = (p & 1) ? o.v1.p : o.v0.p;
+    a.tile_hist = ctx->tile_hist.p;
+    a.bin_total = ctx->ctrl.p->bin_total[sort_idx][p];
+    a.shift = 8 * p;
+    a.src = p == 0 ? src : SRC_PAIRS;
+    LAUNCH("radix_hist", k_radix_hist, (int)T, KVG_BLOCK, 0, a);
+    LAUNCH("radix_tilescan", k_radix_tilescan, 256, KVG_BLOCK, 0, a);
+    LAUNCH("radix_scatter", k_radix_scatter, (int)T, KVG_BLOCK, 0, a);
+    kin = a.keys_out;
+    vin = a.vals_out;
+  }
+  // heads of the final key array; the number of executed passes is device-side knowledge
+  // (max key), the heads kernel is launched once per possible final buffer and the wrong one
+  // exits immediately (its n_ptr reads 0 through the selector below)
+  (void)d_n_seg;
+  (void)ticket;
+  return check_launch(ctx, "radix order");
+}
+
+}  // extern "C"
+
+// heads kernel wrapper that picks the final ping-pong buffer from the device-side max key
+struct HeadsSelOp {
+  using Item = uint2;
+  const uint32_t* k0;
+  const uint32_t* k1;
+  const uint32_t* max_key;
+  int npass_max;
+  const uint32_t* n_ptr;
+  uint32_t* seg_key;
+  uint32_t* seg_off;
+  uint32_t* n_seg_out;
+  const uint32_t* keys;  // resolved in count()
+  __device__ __forceinline__ uint32_t count() {
+    uint32_t mk = *max_key;
+    int np = 1;
+    while (np < npass_max && (mk >> (8 * np)) != 0) np++;
+    keys = ((np - 1) & 1) ? k1 : k0;
+    return *n_ptr;
+  }
+  __device__ __forceinline__ Item load(uint32_t i, bool ok) const {
+    if (!ok) return make_uint2(0, 0);
+    return make_uint2(keys[i], i ? keys[i - 1] : 0);
+  }
+  __device__ __forceinline__ bool pred(const Item& v, uint32_t i) const { return i == 0 || v.x != v.y; }
+  __device__ __forceinline__ void emit(uint32_t pos, const Item& v, uint32_t i) {
+    seg_key[pos] = v.x;
+    seg_off[pos] = i;
+  }
+  __device__ __forceinline__ void tile_epilogue() {}
+  __device__ __forceinline__ void finish(uint32_t total) {
+    *n_seg_out = total;
+    seg_off[total] = *n_ptr;
+  }
+};
+
+static int active_passes(uint32_t max_key, int npass_max) {
+  int np = 1;
+  while (np < npass_max && (max_key >> (8 * np)) != 0) np++;
+  return np;
+}
+
+static int enqueue_heads(kvg_ctx* ctx, OrderBufs& o, size_t cap, int npass_max, uint32_t* d_max_key,
+                         uint32_t* d_n_seg, uint32_t* ticket) {
+  HeadsSelOp h;
+  h.k0 = o.k0.p;
+  h.k1 = o.k1.p;
+  h.max_key = d_max_key;
+  h.npass_max = npass_max;
+  h.n_ptr = &ctx->ctrl.p->n_surv;
+  h.seg_key = o.seg_key.p;
+  h.seg_off = o.seg_off.p;
+  h.n_seg_out = d_n_seg;
+  h.keys = nullptr;
+  LAUNCH("segment_heads", k_compact<HeadsSelOp>, compact_grid(ctx, cap), KVG_BLOCK, 0, h,
+         o.heads_state.p, ++ctx->epoch, ticket);
+  return check_launch(ctx, "segment heads");
+}
+
+// classify + both orderings of `n` device-resident PCI records (or of an already-gathered
+// survivor list when n_records == 0 and surv/ctrl were filled by the sharded path)
+static int enqueue_pci_orderings(kvg_ctx* ctx, size_t surv_cap) {
+  int rc = ensure_order(ctx, ctx->ord_dev, surv_cap);
+  if (rc) return rc;
+  rc = ensure_order(ctx, ctx->ord_grp, surv_cap);
+  if (rc) return rc;
+  ScanCtrl* c = ctx->ctrl.p;
+  rc = enqueue_order(ctx, ctx->ord_dev, surv_cap, SRC_PCI_DEVICE, 0, 2, &c->max_devkey, &c->n_dev_keys, &c->ticket[1]);
+  if (rc) return rc;
+  rc = enqueue_heads(ctx, ctx->ord_dev, surv_cap, 2, &c->max_devkey, &c->n_dev_keys, &c->ticket[1]);
+  if (rc) return rc;
+  rc = enqueue_order(ctx, ctx->ord_grp, surv_cap, SRC_PCI_GROUP, 1, 4, &c->max_group, &c->n_groups, &c->ticket[2]);
+  if (rc) return rc;
+  return enqueue_heads(ctx, ctx->ord_grp, surv_cap, 4, &c->max_group, &c->n_groups, &c->ticket[2]);
+}
+
+static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d_out) {
+  ENSURE(ctx->classify_state, (n + C_TILE - 1) / C_TILE + 1);
+  PciClassifyOp op;
+  op.recs = (const uint4*)d_recs;
+  op.n = (uint32_t)n;
+  op.out = (kvg_pci_surv*)d_out;
+  op.ctrl = ctx->ctrl.p;
+  op.table = ctx->tables.p;
+  op.cap_mask = (1u << ctx->cap_log2) - 1;
+  op.cap_shift = 32 - ctx->cap_log2;
+  op.info = ctx->info.p;
+  op.local_max_group = 0;
+  op.local_max_dev = 0;
+  LAUNCH("classify_compact", k_compact<PciClassifyOp>, compact_grid(ctx, n), KVG_BLOCK, 0, op,
+         ctx->classify_state.p, ++ctx->epoch, &ctx->ctrl.p->ticket[0]);
+  return check_launch(ctx, "classify");
+}
+
+extern "C" {
+
+int kvg_dev_scan_pci(kvg_ctx* ctx, const void* d_recs, size_t n) {
+  if (!ctx || (!d_recs && n) || n > 0xfffffff0ull || ((uintptr_t)d_recs & 15)) return KVG_EINVAL;
+  if (!ctx->table_ready) {
+    ctx->err = "kvg_pciids_load must precede a scan (the scan joins names)";
+    return KVG_ESTATE;
+  }
+  CK(cudaSetDevice(ctx->device));
+  ENSURE(ctx->surv, n + 1);
+  CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
+  int rc = enqueue_classify(ctx, d_recs, n, ctx->surv.p);
+  if (rc) return rc;
+  rc = enqueue_pci_orderings(ctx, n);
+  if (rc) return rc;
+  ctx->last_n = n;
+  ctx->last_total = n;
+  ctx->last_kind = 1;
+  return KVG_OK;
+}
+
+int kvg_dev_scan_pci_count(kvg_ctx* ctx, uint64_t* n_survivors, uint32_t* n_dev_keys, uint32_t* n_groups) {
+  if (!ctx || ctx->last_kind == 0) return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (n_survivors) *n_survivors = ctx->h_ctrl->n_surv;
+  if (n_dev_keys) *n_dev_keys = ctx->h_ctrl->n_dev_keys;
+  if (n_groups) *n_groups = ctx->h_ctrl->n_groups;
+  return KVG_OK;
+}
+
+static size_t align64(size_t x) { return (x + 63) & ~(size_t)63; }
+
+int kvg_dev_scan_pci_fetch(kvg_ctx* ctx, kvg_pci_result** res) {
+  if (!ctx || !res || ctx->last_kind != 1) return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t S = ctx->h_ctrl->n_surv, KD = ctx->h_ctrl->n_dev_keys, G = ctx->h_ctrl->n_groups;
+  const int np_dev = active_passes(ctx->h_ctrl->max_devkey, 2);
+  const int np_grp = active_passes(ctx->h_ctrl->max_group, 4);
+  const size_t pool_len = ctx->h_pool.size();
+  size_t o_hdr = 0, o = align64(sizeof(kvg_pci_result));
+  size_t o_surv = o; o += align64(S * 16);
+  size_t o_dkeys32 = o; o += align64(KD * 4);
+  size_t o_dkeys = o; o += align64(KD * 2);
+  size_t o_doff = o; o += align64((KD + 1) * 4);
+  size_t o_dperm = o; o += align64(S * 4);
+  size_t o_dname = o; o += align64(KD * 4);
+  size_t o_gkeys = o; o += align64(G * 4);
+  size_t o_goff = o; o += align64((G + 1) * 4);
+  size_t o_gperm = o; o += align64(S * 4);
+  size_t o_pool = o; o += align64(pool_len);
+  void* blk = pinned_alloc(ctx, o);
+  if (!blk) {
+    ctx->err = "cudaMallocHost failed for the result block";
+    return KVG_ENOMEM;
+  }
+  uint8_t* b = pinned_payload(blk);
+  (void)o_hdr;
+  auto D2H = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+    if (!bytes) return cudaSuccess;
+    return cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  };
+  OrderBufs& od = ctx->ord_dev;
+  OrderBufs& og = ctx->ord_grp;
+  CK(D2H(o_surv, ctx->surv.p, S * 16));
+  CK(D2H(o_dkeys32, od.seg_key.p, KD * 4));
+  CK(D2H(o_doff, od.seg_off.p, (KD + 1) * 4));
+  CK(D2H(o_dperm, ((np_dev - 1) & 1) ? od.v1.p : od.v0.p, S * 4));
+  CK(D2H(o_gkeys, og.seg_key.p, G * 4));
+  CK(D2H(o_goff, og.seg_off.p, (G + 1) * 4));
+  CK(D2H(o_gperm, ((np_grp - 1) & 1) ? og.v1.p : og.v0.p, S * 4));
+  CK(cudaStreamSynchronize(ctx->stream));
+  kvg_pci_result* r = (kvg_pci_result*)b;
+  memset(r, 0, sizeof *r);
+  r->n_records = ctx->last_n;
+  r->n_survivors = S;
+  r->survivors = (const kvg_pci_surv*)(b + o_surv);
+  r->n_dev_keys = (uint32_t)KD;
+  uint16_t* dk = (uint16_t*)(b + o_dkeys);
+  const uint32_t* dk32 = (const uint32_t*)(b + o_dkeys32);
+  uint32_t* dname = (uint32_t*)(b + o_dname);
+  const uint32_t* doff = (const uint32_t*)(b + o_doff);
+  const uint32_t* dperm = (const uint32_t*)(b + o_dperm);
+  if (S == 0) ((uint32_t*)(b + o_doff))[0] = 0, ((uint32_t*)(b + o_goff))[0] = 0;
+  for (size_t k = 0; k < KD; k++) {  // marshalling only: narrow the key, pick the joined slot
+    dk[k] = (uint16_t)dk32[k];
+    dname[k] = r->survivors[dperm[doff[k]]].name_slot;
+  }
+  r->dev_keys = dk;
+  r->dev_off = doff;
+  r->dev_perm = dperm;
+  r->dev_name_slot = dname;
+  r->n_groups = (uint32_t)G;
+  r->grp_keys = (const uint32_t*)(b + o_gkeys);
+  r->grp_off = (const uint32_t*)(b + o_goff);
+  r->grp_perm = (const uint32_t*)(b + o_gperm);
+  if (pool_len) memcpy(b + o_pool, ctx->h_pool.data(), pool_len);
+  r->name_pool = b + o_pool;
+  r->name_pool_len = pool_len;
+  *res = r;
+  return KVG_OK;
+}
+
+static int stage_h2d(kvg_ctx* ctx, const void* host, size_t bytes, void* dev) {
+  if (!bytes) return KVG_OK;
+  cudaPointerAttributes attr;
+  bool pinned = cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (!pinned) {  // the caller's memory may move or vanish after return (cgo rule): stage it
+    if (ctx->h_stage_cap < bytes) {
+      if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+      ctx->h_stage = nullptr;
+      ctx->h_stage_cap = 0;
+      size_t cap = bytes + bytes / 4 + 4096;
+      CK(cudaMallocHost(&ctx->h_stage, cap));
+      ctx->h_stage_cap = cap;
+    }
+    memcpy(ctx->h_stage, host, bytes);
+    host = ctx->h_stage;
+  }
+  CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return KVG_OK;
+}
+
+int kvg_scan_pci(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, kvg_pci_result** res) {
+  if (!ctx || !res || (!recs && n)) return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  ENSURE(ctx->recs, n + 1);
+  int rc = stage_h2d(ctx, recs, n * sizeof(kvg_pci_rec), ctx->recs.p);
+  if (rc) return rc;
+  rc = kvg_dev_scan_pci(ctx, ctx->recs.p, n);
+  if (rc) return rc;
+  return kvg_dev_scan_pci_fetch(ctx, res);
+}
+
+// ---- health -------------------------------------------------------------------------------------
+int kvg_health_reset(kvg_ctx* ctx) {
+  if (!ctx) return KVG_EINVAL;
+  ctx->health_n = 0;
+  return KVG_OK;
+}
+
+int kvg_health_rescan(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, kvg_health_delta** delta) {
+  if (!ctx || !delta || (!recs && n) || n > 0x7fffffffull) return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  ENSURE(ctx->recs, n + 1);
+  ENSURE(ctx->changed, n + 1);
+  ENSURE(ctx->classify_state, (n + C_TILE - 1) / C_TILE + 1);
+  if (ctx->health_n != n) {
+    ENSURE(ctx->alive_prev, n + 1);
+    CK(cudaMemsetAsync(ctx->alive_prev.p, 0, n + 1, ctx->stream));
+    ctx->health_n = n;
+  }
+  int rc = stage_h2d(ctx, recs, n * sizeof(kvg_pci_rec), ctx->recs.p);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(ctx->ctrl.p, 0, 64, ctx->stream));
+  HealthOp op;
+  op.recs = ctx->recs.p;
+  op.n = (uint32_t)n;
+  op.alive_prev = ctx->alive_prev.p;
+  op.changed = ctx->changed.p;
+  op.ctrl = ctx->ctrl.p;
+  op.local_alive = 0;
+  LAUNCH("health_diff", k_compact<HealthOp>, compact_grid(ctx, n), KVG_BLOCK, 0, op,
+         ctx->classify_state.p, ++ctx->epoch, &ctx->ctrl.p->ticket[0]);
+  rc = check_launch(ctx, "health");
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  size_t nc = ctx->h_ctrl->n_changed;
+  size_t o_list = align64(sizeof(kvg_health_delta));
+  void* blk = pinned_alloc(ctx, o_list + align64(nc * 4));
+  if (!blk) return KVG_ENOMEM;
+  uint8_t* b = pinned_payload(blk);
+  if (nc) {
+    CK(cudaMemcpyAsync(b + o_list, ctx->changed.p, nc * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  kvg_health_delta* d = (kvg_health_delta*)b;
+  d->n_records = (uint32_t)n;
+  d->n_alive = ctx->h_ctrl->n_alive;
+  d->n_changed = (uint32_t)nc;
+  d->changed = (const uint32_t*)(b + o_list);
+  *delta = d;
+  ctx->last_kind = 0;
+  return KVG_OK;
+}
+
+// ---- mdev ---------------------------------------------------------------------------------------
+static int load_type_dict(kvg_ctx* ctx, const kvg_type_dict* types) {
+  uint32_t nt = types->n_types;
+  if (nt > 65535) {
+    ctx->err = "more than 65535 mdev types";
+    return KVG_ERANGE;
+  }
+  size_t raw_len = nt ? types->off[nt] : 0;
+  ENSURE(ctx->type_raw, raw_len + 16);
+  ENSURE(ctx->type_label, raw_len + 16);
+  ENSURE(ctx->type_off, (size_t)nt + 2);
+  ENSURE(ctx->type_label_len, (size_t)nt + 1);
+  ENSURE(ctx->type_canon, (size_t)nt + 1);
+  ENSURE(ctx->type_match, (size_t)nt + 1);
+  ENSURE(ctx->type_name_len, (size_t)nt + 1);
+  ctx->n_types = nt;
+  ctx->h_type_off.assign(types->off, types->off + nt + 1);
+  if (nt == 0) return KVG_OK;
+  if (raw_len) CK(cudaMemcpyAsync(ctx->type_raw.p, types->bytes, raw_len, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->type_off.p, types->off, 4 * ((size_t)nt + 1), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));  // the caller's dictionary may be freed after return
+  int grid = (int)((nt + 63) / 64);
+  LAUNCH("mdev_labels", k_mdev_labels, grid, 64, 0, ctx->type_raw.p, ctx->type_off.p, nt,
+         ctx->type_label.p, ctx->type_label_len.p);
+  LAUNCH("mdev_canon", k_mdev_canon, grid, 64, 0, ctx->type_label.p, ctx->type_off.p,
+         ctx->type_label_len.p, nt, ctx->type_canon.p);
+  return check_launch(ctx, "mdev labels");
+}
+
+}  // extern "C"
+
+// label-keyed lookups need (offset,len) pairs rather than a prefix-offset array: a tiny kernel
+// compacts the labels into a contiguous key blob + offsets for k_lookup_general
+__global__ void k_pack_labels(const uint8_t* __restrict__ label, const uint32_t* __restrict__ raw_off,
+                              const uint32_t* __restrict__ label_len, uint32_t n_types,
+                              uint8_t* __restrict__ blob, uint32_t* __restrict__ blob_off) {
+  // single thread per type after a serial prefix by thread 0 (n_types <= 65535, tiny)
+  __shared__ uint32_t total;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    uint32_t o = 0;
+    for (uint32_t k = 0; k < n_types; k++) {
+      blob_off[k] = o;
+      o += label_len[k];
+    }
+    blob_off[n_types] = o;
+    total = o;
+  }
+  __syncthreads();
+  (void)total;
+  for (uint32_t k = threadIdx.x; k < n_types; k += blockDim.x) {
+    uint32_t o = blob_off[k];
+    for (uint32_t t = 0; t < label_len[k]; t++) blob[o + t] = label[raw_off[k] + t];
+  }
+}
+
+extern "C" {
+
+int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type_dict* types) {
+  if (!ctx || !types || (!d_recs && n) || n > 0xfffffff0ull || ((uintptr_t)d_recs & 15)) return KVG_EINVAL;
+  if (!ctx->table_ready) {
+    ctx->err = "kvg_pciids_load must precede a scan (the scan joins names)";
+    return KVG_ESTATE;
+  }
+  CK(cudaSetDevice(ctx->device));
+  int rc = load_type_dict(ctx, types);
+  if (rc) return rc;
+  const uint32_t nt = ctx->n_types;
+  // resource-name join for every label: getDeviceName(label) (:152) — exact prefix semantics
+  const uint32_t NAME_CAP = 256;
+  if (nt) {
+    ENSURE(ctx->keys_blob, (size_t)ctx->h_type_off[nt] + 16);
+    ENSURE(ctx->keys_off, (size_t)nt + 2);
+    ENSURE(ctx->type_names, (size_t)nt * NAME_CAP);
+    LAUNCH("pack_labels", k_pack_labels, 1, KVG_BLOCK, 0, ctx->type_label.p, ctx->type_off.p,
+           ctx->type_label_len.p, nt, ctx->keys_blob.p, ctx->keys_off.p);
+    rc = lookup_general(ctx, ctx->keys_blob.p, ctx->keys_off.p, nt, NAME_CAP, ctx->type_names.p,
+                        ctx->type_name_len.p, ctx->type_match.p);
+    if (rc) return rc;
+  }
+  ENSURE(ctx->surv, 2 * (n + 1));
+  ENSURE(ctx->classify_state, (n + C_TILE - 1) / C_TILE + 1);
+  CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
+  MdevClassifyOp op;
+  op.recs = (const uint4*)d_recs;
+  op.n = (uint32_t)n;
+  op.out = ctx->surv.p;
+  op.ctrl = ctx->ctrl.p;
+  op.type_canon = ctx->type_canon.p;
+  op.n_types = nt;
+  op.local_max_parent = 0;
+  op.local_max_type = 0;
+  LAUNCH("mdev_classify_compact", k_compact<MdevClassifyOp>, compact_grid(ctx, n), KVG_BLOCK, 0, op,
+         ctx->classify_state.p, ++ctx->epoch, &ctx->ctrl.p->ticket[0]);
+  rc = check_launch(ctx, "mdev classify");
+  if (rc) return rc;
+  rc = ensure_order(ctx, ctx->ord_dev, n);
+  if (rc) return rc;
+  rc = ensure_order(ctx, ctx->ord_grp, n);
+  if (rc) return rc;
+  ScanCtrl* c = ctx->ctrl.p;
+  rc = enqueue_order(ctx, ctx->ord_dev, n, SRC_MDEV_TYPE, 0, 2, &c->max_devkey, &c->n_dev_keys, &c->ticket[1]);
+  if (rc) return rc;
+  rc = enqueue_heads(ctx, ctx->ord_dev, n, 2, &c->max_devkey, &c->n_dev_keys, &c->ticket[1]);
+  if (rc) return rc;
+  rc = enqueue_order(ctx, ctx->ord_grp, n, SRC_MDEV_PARENT, 1, 4, &c->max_group, &c->n_groups, &c->ticket[2]);
+  if (rc) return rc;
+  rc = enqueue_heads(ctx, ctx->ord_grp, n, 4, &c->max_group, &c->n_groups, &c->ticket[2]);
+  if (rc) return rc;
+  ctx->last_n = n;
+  ctx->last_total = n;
+  ctx->last_kind = 2;
+  return KVG_OK;
+}
+
+int kvg_dev_scan_mdev_fetch(kvg_ctx* ctx, kvg_mdev_result** res) {
+  if (!ctx || !res || ctx->last_kind != 2) return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const size_t S = ctx->h_ctrl->n_surv, KT = ctx->h_ctrl->n_dev_keys, P = ctx->h_ctrl->n_groups;
+  const int np_t = active_passes(ctx->h_ctrl->max_devkey, 2);
+  const int np_p = active_passes(ctx->h_ctrl->max_group, 4);
+  const uint32_t nt = ctx->n_types;
+  const size_t raw_len = nt ? ctx->h_type_off[nt] : 0;
+  const uint32_t NAME_CAP = 256;
+  size_t o = align64(sizeof(kvg_mdev_result));
+  size_t o_surv = o; o += align64(S * 32);
+  size_t o_tk32 = o; o += align64(KT * 4);
+  size_t o_tk = o; o += align64(KT * 2);
+  size_t o_toff = o; o += align64((KT + 1) * 4);
+  size_t o_tperm = o; o += align64(S * 4);
+  size_t o_lraw = o; o += align64(raw_len + 16);
+  size_t o_llen = o; o += align64(((size_t)nt + 1) * 4);
+  size_t o_loff = o; o += align64(((size_t)nt + 1) * 4);
+  size_t o_lbytes = o; o += align64(raw_len + 16);
+  size_t o_canon = o; o += align64(((size_t)nt + 1) * 2);
+  size_t o_nraw = o; o += align64((size_t)nt * NAME_CAP + 16);
+  size_t o_nlen = o; o += align64(((size_t)nt + 1) * 4);
+  size_t o_noff = o; o += align64(((size_t)nt + 1) * 4);
+  size_t o_nbytes = o; o += align64((size_t)nt * NAME_CAP + 16);
+  size_t o_pk = o; o += align64(P * 4);
+  size_t o_poff = o; o += align64((P + 1) * 4);
+  size_t o_pperm = o; o += align64(S * 4);
+  void* blk = pinned_alloc(ctx, o);
+  if (!blk) return KVG_ENOMEM;
+  uint8_t* b = pinned_payload(blk);
+  auto D2H = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+    if (!bytes) return cudaSuccess;
+    return cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  };
+  OrderBufs& ot = ctx->ord_dev;
+  OrderBufs& op = ctx->ord_grp;
+  CK(D2H(o_surv, ctx->surv.p, S * 32));
+  CK(D2H(o_tk32, ot.seg_key.p, KT * 4));
+  CK(D2H(o_toff, ot.seg_off.p, (KT + 1) * 4));
+  CK(D2H(o_tperm, ((np_t - 1) & 1) ? ot.v1.p : ot.v0.p, S * 4));
+  CK(D2H(o_pk, op.seg_key.p, P * 4));
+  CK(D2H(o_poff, op.seg_off.p, (P + 1) * 4));
+  CK(D2H(o_pperm, ((np_p - 1) & 1) ? op.v1.p : op.v0.p, S * 4));
+  if (nt) {
+    CK(D2H(o_lraw, ctx->type_label.p, raw_len));
+    CK(D2H(o_llen, ctx->type_label_len.p, (size_t)nt * 4));
+    CK(D2H(o_canon, ctx->type_canon.p, (size_t)nt * 2));
+    CK(D2H(o_nraw, ctx->type_names.p, (size_t)nt * NAME_CAP));
+    CK(D2H(o_nlen, ctx->type_name_len.p, (size_t)nt * 4));
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  kvg_mdev_result* r = (kvg_mdev_result*)b;
+  memset(r, 0, sizeof *r);
+  if (S == 0) ((uint32_t*)(b + o_toff))[0] = 0, ((uint32_t*)(b + o_poff))[0] = 0;
+  r->n_records = ctx->last_n;
+  r->n_survivors = S;
+  r->survivors = (const kvg_mdev_surv*)(b + o_surv);
+  r->n_type_keys = (uint32_t)KT;
+  uint16_t* tk = (uint16_t*)(b + o_tk);
+  for (size_t k = 0; k < KT; k++) tk[k] = (uint16_t)((const uint32_t*)(b + o_tk32))[k];
+  r->type_keys = tk;
+  r->type_off = (const uint32_t*)(b + o_toff);
+  r->type_perm = (const uint32_t*)(b + o_tperm);
+  // repack labels / names contiguously (marshalling of GPU-produced bytes)
+  r->n_types = nt;
+  uint32_t* loff = (uint32_t*)(b + o_loff);
+  uint32_t* noff = (uint32_t*)(b + o_noff);
+  const uint32_t* llen = (const uint32_t*)(b + o_llen);
+  const uint32_t* nlen = (const uint32_t*)(b + o_nlen);
+  size_t lo = 0, no = 0;
+  for (uint32_t k = 0; k < nt; k++) {
+    loff[k] = (uint32_t)lo;
+    memcpy(b + o_lbytes + lo, b + o_lraw + ctx->h_type_off[k], llen[k]);
+    lo += llen[k];
+    noff[k] = (uint32_t)no;
+    uint32_t nl = nlen[k] > NAME_CAP ? NAME_CAP : nlen[k];
+    memcpy(b + o_nbytes + no, b + o_nraw + (size_t)k * NAME_CAP, nl);
+    no += nl;
+  }
+  loff[nt] = (uint32_t)lo;
+  noff[nt] = (uint32_t)no;
+  r->label_off = loff;
+  r->label_bytes = b + o_lbytes;
+  r->type_canon = (const uint16_t*)(b + o_canon);
+  r->type_name_off = noff;
+  r->type_name_bytes = b + o_nbytes;
+  r->n_parents = (uint32_t)P;
+  r->par_keys = (const uint32_t*)(b + o_pk);
+  r->par_off = (const uint32_t*)(b + o_poff);
+  r->par_perm = (const uint32_t*)(b + o_pperm);
+  *res = r;
+  return KVG_OK;
+}
+
+int kvg_scan_mdev(kvg_ctx* ctx, const kvg_mdev_rec* recs, size_t n, const kvg_type_dict* types,
+                  kvg_mdev_result** res) {
+  if (!ctx || !res || !types || (!recs && n)) return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  ENSURE(ctx->recs, 2 * (n + 1));
+  int rc = stage_h2d(ctx, recs, n * sizeof(kvg_mdev_rec), ctx->recs.p);
+  if (rc) return rc;
+  rc = kvg_dev_scan_mdev(ctx, ctx->recs.p, n, types);
+  if (rc) return rc;
+  return kvg_dev_scan_mdev_fetch(ctx, res);
+}
+
+// ---- generators, flush --------------------------------------------------------------------------
+int kvg_dev_gen_pci(kvg_ctx* ctx, void* d_recs, uint64_t first, size_t n, const uint16_t* nv_ids,
+                    uint32_t n_nv_ids, uint32_t group_bits) {
+  if (!ctx || (!d_recs && n) || n > 0xfffffff0ull) return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  ENSURE(ctx->nv_ids, (size_t)n_nv_ids + 1);
+  if (n_nv_ids) {
+    CK(cudaMemcpyAsync(ctx->nv_ids.p, nv_ids, 2 * (size_t)n_nv_ids, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (n == 0) return KVG_OK;
+  LAUNCH("gen_pci", k_gen_pci, ctx->sm_count * 8, KVG_BLOCK, 0, (uint4*)d_recs, first, (uint32_t)n,
+         ctx->nv_ids.p, n_nv_ids, group_bits);
+  return check_launch(ctx, "gen_pci");
+}
+int kvg_dev_gen_mdev(kvg_ctx* ctx, void* d_recs, uint64_t first, size_t n) {
+  if (!ctx || (!d_recs && n) || n > 0xfffffff0ull) return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  if (n == 0) return KVG_OK;
+  LAUNCH("gen_mdev", k_gen_mdev, ctx->sm_count * 8, KVG_BLOCK, 0, (uint4*)d_recs, first, (uint32_t)n);
+  return check_launch(ctx, "gen_mdev");
+}
+int kvg_dev_flush_l2(kvg_ctx* ctx) {
+  if (!ctx) return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n16 = (size_t)(192u << 20) / 16;  // 192 MiB > 126 MB L2
+  ENSURE(ctx->flush, n16);
+  kvg::k_fill<<<ctx->sm_count * 8, KVG_BLOCK, 0, ctx->stream>>>(ctx->flush.p, n16, ctx->epoch);
+  return check_launch(ctx, "flush");
+}
+
+// ================================================================================================
+// multi-GPU: range-sharded records, one allgatherv of survivors (BASELINE.json config 4)
+// ================================================================================================
+int kvg_comm_unique_id(void* out128) {
+  if (!out128) return KVG_EINVAL;
+  std::string err;
+  if (!g_nccl.load(&err)) {
+    g_create_error = err;
+    return KVG_ENCCL;
+  }
+  ncclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != 0) return KVG_ENCCL;
+  memcpy(out128, &id, KVG_UNIQUE_ID_BYTES);
+  return KVG_OK;
+}
+
+int kvg_comm_init(kvg_ctx* ctx, int rank, int nranks, const void* unique_id128) {
+  if (!ctx || !unique_id128 || nranks < 1 || rank < 0 || rank >= nranks) return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  if (!g_nccl.load(&ctx->err)) return KVG_ENCCL;
+  ncclUniqueId id;
+  memcpy(&id, unique_id128, KVG_UNIQUE_ID_BYTES);
+  ncclResult_t r = g_nccl.CommInitRank(&ctx->comm, nranks, id, rank);
+  if (r != 0) {
+    ctx->err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r);
+    return KVG_ENCCL;
+  }
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  ENSURE(ctx->gather_counts, (size_t)nranks + 1);
+  if (!ctx->h_counts) CK(cudaMallocHost((void**)&ctx->h_counts, sizeof(uint64_t) * ((size_t)nranks + 1)));
+  return KVG_OK;
+}
+
+int kvg_comm_destroy(kvg_ctx* ctx) {
+  if (!ctx) return KVG_EINVAL;
+  if (ctx->comm) {
+    cudaStreamSynchronize(ctx->stream);
+    g_nccl.CommDestroy(ctx->comm);
+    ctx->comm = nullptr;
+  }
+  ctx->nranks = 1;
+  ctx->rank = 0;
+  return KVG_OK;
+}
+
+}  // extern "C"
+
+// after the gather: n_surv <- total, maxima already all-reduced by construction (each rank
+// recomputes them from the gathered list)
+__global__ void k_gathered_maxima(const kvg_pci_surv* __restrict__ s, uint32_t n, ScanCtrl* ctrl) {
+  uint32_t mg = 0, md = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    mg = max(mg, s[i].iommu_group);
+    md = max(md, (uint32_t)s[i].device);
+  }
+  mg = warp_max(mg);
+  md = warp_max(md);
+  if (lane_id() == 0) {
+    if (mg) atomicMax(&ctrl->max_group, mg);
+    if (md) atomicMax(&ctrl->max_devkey, md);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) ctrl->n_surv = n;
+}
+
+extern "C" {
+
+int kvg_dev_scan_pci_sharded(kvg_ctx* ctx, const void* d_recs, size_t n_local) {
+  if (!ctx || (!d_recs && n_local) || n_local > 0xfffffff0ull) return KVG_EINVAL;
+  if (!ctx->comm) {
+    ctx->err = "kvg_comm_init has not been called";
+    return KVG_ESTATE;
+  }
+  if (!ctx->table_ready) {
+    ctx->err = "kvg_pciids_load must precede a scan";
+    return KVG_ESTATE;
+  }
+  CK(cudaSetDevice(ctx->device));
+  const int P = ctx->nranks;
+  ENSURE(ctx->local_surv, n_local + 1);
+  CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
+  int rc = enqueue_classify(ctx, d_recs, n_local, ctx->local_surv.p);
+  if (rc) return rc;
+  // counts: every rank learns every shard's survivor count (8 bytes per rank)
+  {
+    // widen the device-side u32 count to u64 in place of a dedicated kernel: copy via host pinned
+    CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->h_counts[P] = ctx->h_ctrl->n_surv;
+    CK(cudaMemcpyAsync(ctx->gather_counts.p + P, &ctx->h_counts[P], 8, cudaMemcpyHostToDevice, ctx->stream));
+    ncclResult_t r = g_nccl.AllGather(ctx->gather_counts.p + P, ctx->gather_counts.p, 1, ncclUint64,
+                                      ctx->comm, ctx->stream);
+    if (r != 0) {
+      ctx->err = std::string("ncclAllGather(counts): ") + g_nccl.GetErrorString(r);
+      return KVG_ENCCL;
+    }
+    CK(cudaMemcpyAsync(ctx->h_counts, ctx->gather_counts.p, 8 * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  size_t total = 0;
+  std::vector<size_t> displ((size_t)P);
+  for (int r = 0; r < P; r++) {
+    displ[(size_t)r] = total;
+    total += ctx->h_counts[r];
+  }
+  if (total > 0xfffffff0ull) {
+    ctx->err = "gathered survivor list exceeds 2^32 entries";
+    return KVG_ERANGE;
+  }
+  ENSURE(ctx->surv, total + 1);
+  // allgatherv = one grouped broadcast per root; rank order == Walk order of the shards
+  {
+    ncclResult_t r = g_nccl.GroupStart();
+    for (int root = 0; root < P && r == 0; root++) {
+      size_t cnt = ctx->h_counts[root];
+      if (cnt == 0) continue;
+      r = g_nccl.Broadcast(root == ctx->rank ? (const void*)ctx->local_surv.p : nullptr,
+                           ctx->surv.p + displ[(size_t)root], cnt * 16, ncclUint8, root, ctx->comm,
+                           ctx->stream);
+    }
+    ncclResult_t r2 = g_nccl.GroupEnd();
+    if (r != 0 || r2 != 0) {
+      ctx->err = std::string("ncclBroadcast group: ") + g_nccl.GetErrorString(r ? r : r2);
+      return KVG_ENCCL;
+    }
+  }
+  // the orderings are recomputed on every rank from the gathered list (replicated, cheap)
+  CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
+  LAUNCH("gathered_maxima", k_gathered_maxima, ctx->sm_count * 4, KVG_BLOCK, 0,
+         (const kvg_pci_surv*)ctx->surv.p, (uint32_t)total, ctx->ctrl.p);
+  rc = enqueue_pci_orderings(ctx, total);
+  if (rc) return rc;
+  ctx->last_n = n_local;
+  ctx->last_total = total;
+  ctx->last_kind = 1;
+  return KVG_OK;
+}
+
+}  // extern "C"

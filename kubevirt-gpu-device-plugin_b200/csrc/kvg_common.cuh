@@ -1,0 +1,240 @@
+// kvg_common.cuh — device-side building blocks shared by every kernel of libkvgpu.so (sm_100a).
+//
+//   * streaming global loads/stores (ld.global.nc.L1::no_allocate / st.global.L1::no_allocate)
+//   * mbarrier + 1-D TMA bulk copy (cp.async.bulk ... mbarrier::complete_tx::bytes -> SASS UBLKCP)
+//   * warp / block scans
+//   * epoch-tagged decoupled look-back (single-pass chained scan) used by the stable compactions
+//     and by the vendor-context carry of the pci.ids parser
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define KVG_BLOCK 256
+#define KVG_WARPS (KVG_BLOCK / 32)
+#define KVG_FULL 0xffffffffu
+
+namespace kvg {
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ uint32_t warp_id() { return threadIdx.x >> 5; }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// ---- streaming memory access --------------------------------------------------------------------
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+  uint64_t v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ---- mbarrier + TMA 1-D bulk copy ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+// global -> shared bulk copy through the TMA unit; bytes % 16 == 0, both addresses 16-B aligned
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---- scans --------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(KVG_FULL, v, d);
+    if (lane_id() >= (uint32_t)d) v += t;
+  }
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_incl_max(uint32_t v) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(KVG_FULL, v, d);
+    if (lane_id() >= (uint32_t)d) v = max(v, t);
+  }
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(KVG_FULL, v, d);
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_max(uint32_t v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(KVG_FULL, v, d));
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_min(uint32_t v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(KVG_FULL, v, d));
+  return v;
+}
+
+// Block-wide exclusive sum over KVG_BLOCK threads; *total receives the block sum.
+// `scratch` is KVG_WARPS+1 words of shared memory; contains two __syncthreads().
+__device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t* scratch, uint32_t* total) {
+  uint32_t incl = warp_incl_sum(v);
+  if (lane_id() == 31) scratch[warp_id()] = incl;
+  __syncthreads();
+  if (warp_id() == 0) {
+    uint32_t w = lane_id() < KVG_WARPS ? scratch[lane_id()] : 0;
+    uint32_t wi = warp_incl_sum(w);
+    if (lane_id() < KVG_WARPS) scratch[lane_id()] = wi - w;
+    if (lane_id() == KVG_WARPS - 1) scratch[KVG_WARPS] = wi;
+  }
+  __syncthreads();
+  uint32_t r = scratch[warp_id()] + incl - v;
+  *total = scratch[KVG_WARPS];
+  return r;
+}
+// Block-wide exclusive max (identity 0); *total receives the block max.  Two __syncthreads().
+__device__ __forceinline__ uint32_t block_excl_max(uint32_t v, uint32_t* scratch, uint32_t* total) {
+  uint32_t incl = warp_incl_max(v);
+  uint32_t excl_in_warp = __shfl_up_sync(KVG_FULL, incl, 1);
+  if (lane_id() == 0) excl_in_warp = 0;
+  if (lane_id() == 31) scratch[warp_id()] = incl;
+  __syncthreads();
+  if (warp_id() == 0) {
+    uint32_t w = lane_id() < KVG_WARPS ? scratch[lane_id()] : 0;
+    uint32_t wi = warp_incl_max(w);
+    uint32_t we = __shfl_up_sync(KVG_FULL, wi, 1);
+    if (lane_id() == 0) we = 0;
+    if (lane_id() < KVG_WARPS) scratch[lane_id()] = we;
+    if (lane_id() == KVG_WARPS - 1) scratch[KVG_WARPS] = wi;
+  }
+  __syncthreads();
+  uint32_t r = max(scratch[warp_id()], excl_in_warp);
+  *total = scratch[KVG_WARPS];
+  return r;
+}
+
+// ---- decoupled look-back ------------------------------------------------------------------------
+// One 64-bit word per tile: [63:34] launch epoch, [33:32] status, [31:0] value.  The epoch makes a
+// stale word from an earlier launch read as "not ready", so the array never needs clearing.
+enum : uint32_t { LB_INVALID = 0, LB_AGGREGATE = 1, LB_INCLUSIVE = 2 };
+__device__ __forceinline__ uint64_t lb_pack(uint32_t epoch, uint32_t status, uint32_t value) {
+  return ((uint64_t)(epoch & 0x3fffffffu) << 34) | ((uint64_t)status << 32) | value;
+}
+__device__ __forceinline__ uint32_t lb_status(uint64_t w, uint32_t epoch) {
+  return ((uint32_t)(w >> 34) == (epoch & 0x3fffffffu)) ? (uint32_t)((w >> 32) & 3) : LB_INVALID;
+}
+
+// Sum look-back, executed by one full warp.  Publishes this tile's aggregate, walks predecessors
+// 32 at a time and returns the exclusive prefix (valid in every lane); publishes the inclusive.
+// Tiles must be handed out in increasing order by an atomic ticket so a predecessor is always
+// owned by a resident CTA.
+__device__ __forceinline__ uint32_t lookback_sum(uint64_t* state, uint32_t tile, uint32_t aggregate,
+                                                 uint32_t epoch) {
+  const uint32_t lane = lane_id();
+  if (tile == 0) {
+    if (lane == 0) st_relaxed_u64(&state[0], lb_pack(epoch, LB_INCLUSIVE, aggregate));
+    return 0;
+  }
+  if (lane == 0) st_relaxed_u64(&state[tile], lb_pack(epoch, LB_AGGREGATE, aggregate));
+  uint32_t excl = 0;
+  int look = (int)tile - 1;
+  for (;;) {
+    int idx = look - (int)lane;
+    uint64_t w = idx >= 0 ? ld_relaxed_u64(&state[idx]) : lb_pack(epoch, LB_INCLUSIVE, 0);
+    uint32_t st = lb_status(w, epoch);
+    uint32_t incl_mask = __ballot_sync(KVG_FULL, st == LB_INCLUSIVE);
+    uint32_t inv_mask = __ballot_sync(KVG_FULL, st == LB_INVALID);
+    uint32_t first = incl_mask ? (uint32_t)__ffs(incl_mask) - 1 : 32;
+    uint32_t need = first >= 31 ? KVG_FULL : ((2u << first) - 1);  // lanes 0..first
+    if (inv_mask & need) continue;                                 // a needed predecessor not ready
+    excl += warp_sum(lane <= first ? (uint32_t)w : 0u);
+    if (first < 32) break;
+    look -= 32;
+  }
+  if (lane == 0) st_relaxed_u64(&state[tile], lb_pack(epoch, LB_INCLUSIVE, excl + aggregate));
+  return excl;
+}
+
+// "Last writer wins" look-back (used for the pci.ids vendor context): a tile either defines a new
+// value (publishes INCLUSIVE immediately, no dependence on predecessors) or passes its
+// predecessor's value through.  Returns the value carried INTO `tile`; one full warp executes it.
+__device__ __forceinline__ uint32_t lookback_last(uint64_t* state, uint32_t tile, bool first_of_chain,
+                                                  bool defines, uint32_t own_value, uint32_t epoch) {
+  const uint32_t lane = lane_id();
+  if (defines && lane == 0) st_relaxed_u64(&state[tile], lb_pack(epoch, LB_INCLUSIVE, own_value));
+  if (first_of_chain) {
+    if (!defines && lane == 0) st_relaxed_u64(&state[tile], lb_pack(epoch, LB_INCLUSIVE, 0));
+    return 0;
+  }
+  if (!defines && lane == 0) st_relaxed_u64(&state[tile], lb_pack(epoch, LB_AGGREGATE, 0));
+  uint32_t carry;
+  int look = (int)tile - 1;
+  for (;;) {
+    int idx = look - (int)lane;
+    // idx < 0 cannot be reached: the first tile of a chain always publishes INCLUSIVE
+    uint64_t w = idx >= 0 ? ld_relaxed_u64(&state[idx]) : lb_pack(epoch, LB_INCLUSIVE, 0);
+    uint32_t st = lb_status(w, epoch);
+    uint32_t incl_mask = __ballot_sync(KVG_FULL, st == LB_INCLUSIVE);
+    uint32_t inv_mask = __ballot_sync(KVG_FULL, st == LB_INVALID);
+    uint32_t first = incl_mask ? (uint32_t)__ffs(incl_mask) - 1 : 32;
+    uint32_t need = first >= 31 ? KVG_FULL : ((2u << first) - 1);
+    if (inv_mask & need) continue;
+    if (first < 32) {
+      carry = __shfl_sync(KVG_FULL, (uint32_t)w, first);
+      break;
+    }
+    look -= 32;
+  }
+  if (!defines && lane == 0) st_relaxed_u64(&state[tile], lb_pack(epoch, LB_INCLUSIVE, carry));
+  return carry;
+}
+
+}  // namespace kvg

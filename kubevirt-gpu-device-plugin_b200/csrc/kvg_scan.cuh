@@ -1,0 +1,579 @@
+// kvg_scan.cuh — record classification, stable compaction and stable bucketing.
+//
+//   k_compact<Op>      single-pass stable compaction: 2048-item tiles, 8 x 128-bit loads in flight
+//                      per thread, warp ballots, block scan, decoupled look-back on tile counts.
+//                      Instantiated for
+//        PciClassifyOp   K3: createIommuDeviceMap's filter (device_plugin.go:201-244) + name join
+//        MdevClassifyOp  K5: createVgpuIDMap's filter (:268-289)
+//        HeadsOp         segment heads of a sorted key array (distinct map keys + offsets)
+//        HealthOp        K6: alive-set diff against the previous scan
+//   k_radix_*          K4: stable LSD radix sort of (key, index) pairs, 8-bit digits:
+//                      per-tile histogram -> per-digit tile scan -> ranked scatter
+//   k_gen_*            counter-based synthetic snapshots (twins of oracle/kvg_oracle.c kvo_gen_*)
+#pragma once
+#include "../../include/kvgpu.h"
+#include "kvg_common.cuh"
+#include "kvg_parse.cuh"
+
+namespace kvg {
+
+constexpr uint32_t C_ROWS = 8;                      // items per thread
+constexpr uint32_t C_TILE = KVG_BLOCK * C_ROWS;     // 2048 items per tile
+constexpr uint32_t C_WARP_ITEMS = 32 * C_ROWS;      // 256 contiguous items per warp
+
+// device-resident control block of one scan (zeroed by one memset per step)
+struct ScanCtrl {
+  uint32_t ticket[8];     // tile tickets, one per compaction launch in a step
+  uint32_t n_surv;        // survivors of the classify kernel
+  uint32_t max_group;     // max iommu group / parent among survivors (radix pass count)
+  uint32_t max_devkey;    // max device / type key among survivors
+  uint32_t n_dev_keys;    // distinct keys found by the heads kernels
+  uint32_t n_groups;
+  uint32_t n_alive;       // health
+  uint32_t n_changed;
+  uint32_t pad0;
+  uint32_t bin_total[2][4][256];  // [sort][pass][digit]
+};
+
+// ------------------------------------------------------------------------------------------------
+// generic stable compaction
+//   Op::Item                        what a thread holds per input element
+//   uint32_t count()                number of input items (may read device memory)
+//   Item load(uint32_t i, bool ok)  ok == false -> any value that fails pred
+//   bool pred(const Item&, i)
+//   void emit(uint32_t pos, const Item&, i)
+//   void warp_epilogue(...)         optional per-warp reduction hook (called once per tile)
+//   void finish(uint32_t total)     called by one thread of the last tile
+// ------------------------------------------------------------------------------------------------
+template <class Op>
+__global__ void __launch_bounds__(KVG_BLOCK) k_compact(Op op, uint64_t* tile_state, uint32_t epoch,
+                                                       uint32_t* ticket) {
+  __shared__ uint32_t s_tile, s_base;
+  __shared__ uint32_t s_wtot[KVG_WARPS], s_woff[KVG_WARPS];
+  const uint32_t n = op.count();
+  const uint32_t n_tiles = (n + C_TILE - 1) / C_TILE;
+  const uint32_t lane = lane_id(), warp = warp_id();
+  if (n_tiles == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) op.finish(0);
+    return;
+  }
+  for (;;) {
+    __syncthreads();  // previous iteration fully consumed s_*
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= n_tiles) break;
+    const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
+
+    typename Op::Item item[C_ROWS];
+#pragma unroll
+    for (uint32_t k = 0; k < C_ROWS; k++) {
+      uint32_t i = base + k * 32 + lane;
+      item[k] = op.load(i, i < n);
+    }
+    uint32_t bal[C_ROWS];
+    uint32_t wtot = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < C_ROWS; k++) {
+      uint32_t i = base + k * 32 + lane;
+      bool p = i < n && op.pred(item[k], i);
+      bal[k] = __ballot_sync(KVG_FULL, p);
+      wtot += __popc(bal[k]);
+    }
+    if (lane == 0) s_wtot[warp] = wtot;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = lane < KVG_WARPS ? s_wtot[lane] : 0;
+      uint32_t wi = warp_incl_sum(w);
+      if (lane < KVG_WARPS) s_woff[lane] = wi - w;
+      uint32_t tile_total = __shfl_sync(KVG_FULL, wi, KVG_WARPS - 1);
+      uint32_t excl = lookback_sum(tile_state, tile, tile_total, epoch);
+      if (lane == 0) {
+        s_base = excl;
+        if (tile == n_tiles - 1) op.finish(excl + tile_total);
+      }
+    }
+    __syncthreads();
+    uint32_t off = s_base + s_woff[warp];
+#pragma unroll
+    for (uint32_t k = 0; k < C_ROWS; k++) {
+      uint32_t i = base + k * 32 + lane;
+      if ((bal[k] >> lane) & 1u) op.emit(off + __popc(bal[k] & lanemask_lt()), item[k], i);
+      off += __popc(bal[k]);
+    }
+    op.tile_epilogue();
+  }
+}
+
+// ---- K3: PCI classify ---------------------------------------------------------------------------
+struct PciClassifyOp {
+  using Item = uint4;
+  const uint4* recs;
+  uint32_t n;
+  kvg_pci_surv* out;
+  ScanCtrl* ctrl;
+  const uint64_t* table;
+  uint32_t cap_mask, cap_shift;
+  const PciIdsInfo* info;
+  uint32_t local_max_group, local_max_dev;  // per-thread running maxima (registers)
+
+  __device__ __forceinline__ uint32_t count() const { return n; }
+  __device__ __forceinline__ Item load(uint32_t i, bool ok) const {
+    return ok ? ld_stream(recs + i) : make_uint4(0, 0, 0, 0xff00u);
+  }
+  // record = {addr, vendor | device<<16, iommu_group, driver | flags<<8 | numa<<16}
+  // device_plugin.go:203-238: any of vendor/driver/iommu/device read errors drops the entry,
+  // vendor must be "10de" (:209), driver in supportedVfioDrivers (:217, :75-78)
+  __device__ __forceinline__ bool pred(const Item& r, uint32_t) const {
+    uint32_t vendor = r.y & 0xffffu;
+    uint32_t driver = r.w & 0xffu;
+    uint32_t flags = (r.w >> 8) & 0xffu;
+    const uint32_t drop = KVG_PF_VENDOR_ERR | KVG_PF_DRIVER_ERR | KVG_PF_IOMMU_ERR | KVG_PF_DEVICE_ERR;
+    return vendor == 0x10deu && (flags & drop) == 0 &&
+           (driver == KVG_DRV_VFIO_PCI || driver == KVG_DRV_NVGRACE);
+  }
+  __device__ __forceinline__ void emit(uint32_t pos, const Item& r, uint32_t) {
+    uint32_t device = r.y >> 16;
+    uint32_t flags = (r.w >> 8) & 0xffu;
+    int32_t numa = (int32_t)r.w >> 16;  // sign-extended int16
+    if ((flags & KVG_PF_NUMA_ERR) || numa < 0) numa = 0;  // :227-230, :316-318
+    uint4 s;
+    s.x = r.x;
+    s.y = r.z;
+    s.z = device | ((uint32_t)numa << 16);
+    s.w = probe_name_slot(table, cap_mask, cap_shift, info, device);
+    st_stream(reinterpret_cast<uint4*>(out) + pos, s);
+    local_max_group = max(local_max_group, r.z);
+    local_max_dev = max(local_max_dev, device);
+  }
+  __device__ __forceinline__ void tile_epilogue() {
+    uint32_t g = warp_max(local_max_group), d = warp_max(local_max_dev);
+    if (lane_id() == 0) {
+      if (g) atomicMax(&ctrl->max_group, g);
+      if (d) atomicMax(&ctrl->max_devkey, d);
+    }
+    local_max_group = 0;
+    local_max_dev = 0;
+  }
+  __device__ __forceinline__ void finish(uint32_t total) { ctrl->n_surv = total; }
+};
+
+// ---- K5: mdev classify --------------------------------------------------------------------------
+struct MdevItem {
+  uint4 lo, hi;
+};
+struct MdevClassifyOp {
+  using Item = MdevItem;
+  const uint4* recs;  // 2 x uint4 per record
+  uint32_t n;
+  uint4* out;
+  ScanCtrl* ctrl;
+  const uint16_t* type_canon;  // [n_types] canonical id per raw dictionary entry
+  uint32_t n_types;
+  uint32_t local_max_parent, local_max_type;
+
+  __device__ __forceinline__ uint32_t count() const { return n; }
+  __device__ __forceinline__ Item load(uint32_t i, bool ok) const {
+    Item it;
+    if (ok) {
+      it.lo = ld_stream(recs + 2 * (size_t)i);
+      it.hi = ld_stream(recs + 2 * (size_t)i + 1);
+    } else {
+      it.lo = make_uint4(0, 0, 0, 0);
+      it.hi = make_uint4(0, 0xffu << 16, 0, 0);
+    }
+    return it;
+  }
+  // hi = {parent, type_idx | flags<<16 | pad<<24, parent_numa | pad.., pad}
+  __device__ __forceinline__ bool pred(const Item& r, uint32_t) const {
+    uint32_t flags = (r.hi.y >> 16) & 0xffu;
+    uint32_t type_idx = r.hi.y & 0xffffu;
+    return (flags & (KVG_MF_TYPE_ERR | KVG_MF_PARENT_ERR)) == 0 && type_idx < n_types;
+  }
+  __device__ __forceinline__ void emit(uint32_t pos, const Item& r, uint32_t i) {
+    uint32_t flags = (r.hi.y >> 16) & 0xffu;
+    uint32_t type_idx = r.hi.y & 0xffffu;
+    int32_t numa = (int32_t)(int16_t)(r.hi.z & 0xffffu);
+    if ((flags & KVG_MF_NUMA_ERR) || numa < 0) numa = 0;  // :281-284, :316-318
+    uint32_t canon = type_canon[type_idx];
+    uint4 hi;
+    hi.x = r.hi.x;
+    hi.y = canon | ((uint32_t)numa << 16);
+    hi.z = i;
+    hi.w = 0;
+    st_stream(out + 2 * (size_t)pos, r.lo);
+    st_stream(out + 2 * (size_t)pos + 1, hi);
+    local_max_parent = max(local_max_parent, r.hi.x);
+    local_max_type = max(local_max_type, canon);
+  }
+  __device__ __forceinline__ void tile_epilogue() {
+    uint32_t g = warp_max(local_max_parent), d = warp_max(local_max_type);
+    if (lane_id() == 0) {
+      if (g) atomicMax(&ctrl->max_group, g);
+      if (d) atomicMax(&ctrl->max_devkey, d);
+    }
+    local_max_parent = 0;
+    local_max_type = 0;
+  }
+  __device__ __forceinline__ void finish(uint32_t total) { ctrl->n_surv = total; }
+};
+
+// ---- segment heads of a sorted key array --------------------------------------------------------
+struct HeadsOp {
+  using Item = uint2;  // {key[i], key[i-1]}
+  const uint32_t* keys;
+  const uint32_t* n_ptr;  // device-side element count
+  uint32_t* seg_key;
+  uint32_t* seg_off;      // [segments + 1]
+  uint32_t* n_seg_out;
+  __device__ __forceinline__ uint32_t count() const { return *n_ptr; }
+  __device__ __forceinline__ Item load(uint32_t i, bool ok) const {
+    if (!ok) return make_uint2(0, 0);
+    return make_uint2(keys[i], i ? keys[i - 1] : 0);
+  }
+  __device__ __forceinline__ bool pred(const Item& v, uint32_t i) const {
+    return i == 0 || v.x != v.y;
+  }
+  __device__ __forceinline__ void emit(uint32_t pos, const Item& v, uint32_t i) {
+    seg_key[pos] = v.x;
+    seg_off[pos] = i;
+  }
+  __device__ __forceinline__ void tile_epilogue() {}
+  __device__ __forceinline__ void finish(uint32_t total) {
+    *n_seg_out = total;
+    seg_off[total] = *n_ptr;
+  }
+};
+
+// ---- K6: health diff ----------------------------------------------------------------------------
+struct HealthOp {
+  using Item = uint4;
+  const uint4* recs;
+  uint32_t n;
+  uint8_t* alive_prev;  // one byte per record, updated in place
+  uint32_t* changed;
+  ScanCtrl* ctrl;
+  uint32_t local_alive;
+  __device__ __forceinline__ uint32_t count() const { return n; }
+  __device__ __forceinline__ Item load(uint32_t i, bool ok) const {
+    if (!ok) return make_uint4(0, 0, 0, 0);
+    uint4 r = ld_stream(recs + i);
+    PciClassifyOp c{};
+    uint32_t alive = c.pred(r, i) ? 1u : 0u;
+    r.x = alive | ((uint32_t)alive_prev[i] << 1);
+    return r;
+  }
+  __device__ __forceinline__ bool pred(const Item& r, uint32_t) {
+    local_alive += r.x & 1u;
+    return (r.x & 1u) != (r.x >> 1);
+  }
+  __device__ __forceinline__ void emit(uint32_t pos, const Item& r, uint32_t i) {
+    changed[pos] = (i << 1) | (r.x & 1u);
+    alive_prev[i] = (uint8_t)(r.x & 1u);
+  }
+  __device__ __forceinline__ void tile_epilogue() {
+    uint32_t a = warp_sum(local_alive);
+    if (lane_id() == 0 && a) atomicAdd(&ctrl->n_alive, a);
+    local_alive = 0;
+  }
+  __device__ __forceinline__ void finish(uint32_t total) { ctrl->n_changed = total; }
+};
+
+// ------------------------------------------------------------------------------------------------
+// K4: stable LSD radix sort, 8-bit digits, tiles of 2048 pairs
+// ------------------------------------------------------------------------------------------------
+enum : int { SRC_PAIRS = 0, SRC_PCI_GROUP = 1, SRC_PCI_DEVICE = 2, SRC_MDEV_PARENT = 3, SRC_MDEV_TYPE = 4 };
+
+struct RadixArgs {
+  const uint32_t* n_ptr;      // element count (device)
+  const uint32_t* max_key;    // largest key (device): passes at or above its bit width are skipped
+  const void* src_records;    // survivors (SRC_* != PAIRS)
+  const uint32_t* keys_in;
+  const uint32_t* vals_in;
+  uint32_t* keys_out;
+  uint32_t* vals_out;
+  uint32_t* tile_hist;        // [256][T]  (T = ceil(n / C_TILE)), digit-major
+  uint32_t* bin_total;        // [256] for this pass
+  uint32_t shift;
+  int src;                    // where pass-0 keys come from
+};
+
+__device__ __forceinline__ bool radix_pass_active(const RadixArgs& a) {
+  return a.shift == 0 || (*a.max_key >> a.shift) != 0;
+}
+__device__ __forceinline__ uint32_t radix_key(const RadixArgs& a, uint32_t i) {
+  switch (a.src) {
+    case SRC_PCI_GROUP: return reinterpret_cast<const kvg_pci_surv*>(a.src_records)[i].iommu_group;
+    case SRC_PCI_DEVICE: return reinterpret_cast<const kvg_pci_surv*>(a.src_records)[i].device;
+    case SRC_MDEV_PARENT: return reinterpret_cast<const kvg_mdev_surv*>(a.src_records)[i].parent;
+    case SRC_MDEV_TYPE: return reinterpret_cast<const kvg_mdev_surv*>(a.src_records)[i].type_key;
+    default: return a.keys_in[i];
+  }
+}
+
+__global__ void __launch_bounds__(KVG_BLOCK) k_radix_hist(RadixArgs a) {
+  const uint32_t n = *a.n_ptr;
+  const uint32_t T = (n + C_TILE - 1) / C_TILE;
+  const uint32_t tile = blockIdx.x;
+  if (tile >= T || !radix_pass_active(a)) return;
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = tile * C_TILE;
+#pragma unroll
+  for (uint32_t k = 0; k < C_ROWS; k++) {
+    uint32_t i = base + k * KVG_BLOCK + threadIdx.x;
+    if (i < n) atomicAdd(&h[(radix_key(a, i) >> a.shift) & 0xffu], 1u);
+  }
+  __syncthreads();
+  uint32_t c = h[threadIdx.x];
+  a.tile_hist[(size_t)threadIdx.x * T + tile] = c;
+  if (c) atomicAdd(&a.bin_total[threadIdx.x], c);
+}
+
+// one CTA per digit: exclusive scan of that digit's per-tile counts, in place
+__global__ void __launch_bounds__(KVG_BLOCK) k_radix_tilescan(RadixArgs a) {
+  const uint32_t n = *a.n_ptr;
+  const uint32_t T = (n + C_TILE - 1) / C_TILE;
+  if (T == 0 || !radix_pass_active(a)) return;
+  __shared__ uint32_t scratch[KVG_WARPS + 1];
+  uint32_t* row = a.tile_hist + (size_t)blockIdx.x * T;
+  uint32_t carry = 0;
+  for (uint32_t b = 0; b < T; b += KVG_BLOCK) {
+    uint32_t i = b + threadIdx.x;
+    uint32_t v = i < T ? row[i] : 0;
+    uint32_t total;
+    uint32_t e = block_excl_sum(v, scratch, &total);
+    if (i < T) row[i] = carry + e;
+    carry += total;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(KVG_BLOCK) k_radix_scatter(RadixArgs a) {
+  const uint32_t n = *a.n_ptr;
+  const uint32_t T = (n + C_TILE - 1) / C_TILE;
+  const uint32_t tile = blockIdx.x;
+  if (tile >= T) return;
+  const uint32_t lane = lane_id(), warp = warp_id();
+  const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
+  if (!radix_pass_active(a)) {
+    // skipped pass: keep the ping-pong parity by copying (only pass-0 sources never skip)
+#pragma unroll
+    for (uint32_t k = 0; k < C_ROWS; k++) {
+      uint32_t i = base + k * 32 + lane;
+      if (i < n) {
+        a.keys_out[i] = a.keys_in[i];
+        a.vals_out[i] = a.vals_in[i];
+      }
+    }
+    return;
+  }
+  __shared__ uint32_t s_cnt[KVG_WARPS][256];  // per-warp digit counts, then warp bases
+  __shared__ uint32_t s_bin[256];             // global base of each digit for this tile
+  __shared__ uint32_t scratch[KVG_WARPS + 1];
+#pragma unroll
+  for (uint32_t w = 0; w < KVG_WARPS; w++) s_cnt[w][threadIdx.x] = 0;
+  {
+    uint32_t total;
+    uint32_t e = block_excl_sum(a.bin_total[threadIdx.x], scratch, &total);  // syncs inside
+    s_bin[threadIdx.x] = e + a.tile_hist[(size_t)threadIdx.x * T + tile];
+  }
+  __syncthreads();
+
+  uint32_t key[C_ROWS], val[C_ROWS], rank[C_ROWS];
+#pragma unroll
+  for (uint32_t k = 0; k < C_ROWS; k++) {
+    uint32_t i = base + k * 32 + lane;
+    bool ok = i < n;
+    key[k] = ok ? radix_key(a, i) : 0;
+    val[k] = ok ? (a.src == SRC_PAIRS ? a.vals_in[i] : i) : 0;
+  }
+  // stable rank inside the warp: rows in order, lanes in order within a row
+#pragma unroll
+  for (uint32_t k = 0; k < C_ROWS; k++) {
+    uint32_t i = base + k * 32 + lane;
+    bool ok = i < n;
+    uint32_t d = ok ? ((key[k] >> a.shift) & 0xffu) : (0x100u + lane);  // inactive lanes: unique
+    uint32_t peers = __match_any_sync(KVG_FULL, d);
+    uint32_t leader = (uint32_t)__ffs(peers) - 1;
+    uint32_t before = 0;
+    if (ok && lane == leader) {
+      before = s_cnt[warp][d];
+      s_cnt[warp][d] = before + __popc(peers);
+    }
+    before = __shfl_sync(KVG_FULL, before, leader);
+    rank[k] = before + __popc(peers & lanemask_lt());
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // exclusive prefix over warps for digit == threadIdx.x
+    uint32_t run = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < KVG_WARPS; w++) {
+      uint32_t c = s_cnt[w][threadIdx.x];
+      s_cnt[w][threadIdx.x] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (uint32_t k = 0; k < C_ROWS; k++) {
+    uint32_t i = base + k * 32 + lane;
+    if (i < n) {
+      uint32_t d = (key[k] >> a.shift) & 0xffu;
+      uint32_t pos = s_bin[d] + s_cnt[warp][d] + rank[k];
+      a.keys_out[pos] = key[k];
+      a.vals_out[pos] = val[k];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// mdev type dictionary: label = Trim(raw, "\n") then \s+ -> "_"  (device_plugin.go:341-342);
+// canonical id = smallest raw index with an identical label (they are ONE vGpuMap key).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_mdev_labels(const uint8_t* __restrict__ raw, const uint32_t* __restrict__ raw_off,
+                              uint32_t n_types, uint8_t* __restrict__ label,
+                              uint32_t* __restrict__ label_len) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_types) return;
+  uint32_t a = raw_off[k], b = raw_off[k + 1];
+  while (a < b && raw[a] == '\n') a++;
+  while (b > a && raw[b - 1] == '\n') b--;
+  uint8_t* out = label + raw_off[k];  // sanitised text is never longer than the raw text
+  uint32_t o = 0;
+  for (uint32_t i = a; i < b;) {
+    if (d_re2_space(raw[i])) {
+      out[o++] = '_';
+      while (i < b && d_re2_space(raw[i])) i++;
+    } else {
+      out[o++] = raw[i++];
+    }
+  }
+  label_len[k] = o;
+}
+__global__ void k_mdev_canon(const uint8_t* __restrict__ label, const uint32_t* __restrict__ raw_off,
+                             const uint32_t* __restrict__ label_len, uint32_t n_types,
+                             uint16_t* __restrict__ canon) {
+  uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_types) return;
+  uint32_t len = label_len[k];
+  const uint8_t* mine = label + raw_off[k];
+  uint32_t c = k;
+  for (uint32_t j = 0; j < k; j++) {
+    if (label_len[j] != len) continue;
+    const uint8_t* other = label + raw_off[j];
+    bool eq = true;
+    for (uint32_t t = 0; t < len && eq; t++) eq = other[t] == mine[t];
+    if (eq) {
+      c = j;
+      break;
+    }
+  }
+  canon[k] = (uint16_t)c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic snapshots (splitmix64, counter based) — identical to kvo_gen_pci / kvo_gen_mdev
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__global__ void k_gen_pci(uint4* __restrict__ out, uint64_t first, uint32_t n,
+                          const uint16_t* __restrict__ nv_ids, uint32_t n_nv_ids,
+                          uint32_t group_bits) {
+  const uint64_t SEED = 0x10DE000020250711ull;
+  const uint16_t other[8] = {0x8086, 0x1002, 0x15b3, 0x1022, 0x144d, 0x14e4, 0x1af4, 0x10df};
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    uint64_t i = first + k;
+    uint64_t r0 = mix64(SEED + 2 * i), r1 = mix64(SEED + 2 * i + 1);
+    bool nvidia = (r0 & 0xFF) < 128;
+    uint32_t vendor = nvidia ? 0x10deu : other[(r0 >> 8) & 7];
+    uint32_t device;
+    if (nvidia && ((r0 >> 16) & 0xFF) < 230 && n_nv_ids)
+      device = nv_ids[(uint32_t)((r0 >> 24) & 0xFFFFFF) % n_nv_ids];
+    else
+      device = (uint32_t)((r0 >> 24) & 0xFFFF);
+    uint32_t d = (uint32_t)((r0 >> 48) & 0xFF);
+    uint32_t flags = 0, driver;
+    if (d < 154)
+      driver = KVG_DRV_VFIO_PCI;
+    else if (d < 179)
+      driver = KVG_DRV_NVGRACE;
+    else if (d < 218)
+      driver = 3;
+    else if (d < 231)
+      driver = 4;
+    else {
+      driver = KVG_DRV_NONE;
+      flags |= KVG_PF_DRIVER_ERR;
+    }
+    uint32_t g = (uint32_t)(i >> 1);
+    if (group_bits) {
+      uint32_t mask = group_bits >= 32 ? 0xFFFFFFFFu : ((1u << group_bits) - 1);
+      uint32_t hi = g & ~mask, lo = g & mask;
+      lo = (lo * 0x9E3779B1u) & mask;
+      lo ^= lo >> (group_bits / 2 + 1);
+      g = hi | (lo & mask);
+    }
+    int32_t numa = (int32_t)(r1 & 7) - 1;
+    if (((r1 >> 8) & 0xFF) == 0) flags |= KVG_PF_VENDOR_ERR;
+    if (((r1 >> 16) & 0xFF) == 0) flags |= KVG_PF_IOMMU_ERR;
+    if (((r1 >> 24) & 0xFF) == 0) flags |= KVG_PF_DEVICE_ERR;
+    if (((r1 >> 32) & 0xFF) == 0) flags |= KVG_PF_NUMA_ERR;
+    uint4 r;
+    r.x = (uint32_t)i;
+    r.y = vendor | (device << 16);
+    r.z = g;
+    r.w = driver | (flags << 8) | (((uint32_t)numa & 0xffffu) << 16);
+    out[k] = r;
+  }
+}
+__global__ void k_gen_mdev(uint4* __restrict__ out, uint64_t first, uint32_t n) {
+  const uint64_t SEED = 0x4D44455600010000ull;
+  for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    uint64_t j = first + k;
+    uint64_t r0 = mix64(SEED + 2 * j), r1 = mix64(SEED + 2 * j + 1);
+    // uuid = BE32(j) | BE64(r0) | BE32(r1 low 32)   (little-endian words hold big-endian bytes)
+    uint4 lo;
+    lo.x = __byte_perm((uint32_t)j, 0, 0x0123);
+    lo.y = __byte_perm((uint32_t)(r0 >> 32), 0, 0x0123);
+    lo.z = __byte_perm((uint32_t)r0, 0, 0x0123);
+    lo.w = __byte_perm((uint32_t)r1, 0, 0x0123);
+    uint32_t flags = 0;
+    if (((r1 >> 40) & 0xFF) == 0) flags |= KVG_MF_TYPE_ERR;
+    if (((r1 >> 48) & 0xFF) == 0) flags |= KVG_MF_PARENT_ERR;
+    if (((r1 >> 56) & 0xFF) == 0) flags |= KVG_MF_NUMA_ERR;
+    int32_t numa = (int32_t)((j >> 5) & 3) - 1;
+    uint4 hi;
+    hi.x = (uint32_t)(j >> 5);
+    hi.y = (uint32_t)(r0 >> 56) | (flags << 16);
+    hi.z = (uint32_t)numa & 0xffffu;
+    hi.w = 0;
+    out[2 * (size_t)k] = lo;
+    out[2 * (size_t)k + 1] = hi;
+  }
+}
+
+// L2 flush helper: stream zeros through a buffer larger than L2
+__global__ void k_fill(uint4* __restrict__ p, size_t n16, uint32_t v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16;
+       i += (size_t)gridDim.x * blockDim.x)
+    p[i] = make_uint4(v, v, v, v);
+}
+__global__ void k_fill64(uint64_t* __restrict__ p, size_t n, uint64_t v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+__global__ void k_fill32(uint32_t* __restrict__ p, size_t n, uint32_t v) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+}  // namespace kvg

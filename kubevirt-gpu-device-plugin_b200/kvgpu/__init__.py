@@ -1,0 +1,15 @@
+"""kvgpu — B200-native discovery-and-classification scan for the KubeVirt GPU device plugin.
+
+The compute lives in libkvgpu.so (hand-written sm_100a CUDA, C-ABI in include/kvgpu.h); this
+package is the host-side mirror of the reference's plugin interface for that path.
+"""
+from ._lib import (KVG_NO_NAME, MDEV_REC, MDEV_SURV, PCI_REC, PCI_SURV, KvgError, declared_symbols,
+                   load)
+from .context import Context, HealthDelta, MdevResult, PciResult
+from .plugin import (DiscoveryScan, Maps, MdevSnapshot, NvidiaGpuDevice, PciSnapshot, PluginSpec,
+                     ReferencePanic, canonical_dump, format_bdf, format_uuid,
+                     mdev_maps_from_result, parse_bdf, pci_maps_from_result, snapshot_mdev_tree,
+                     snapshot_pci_tree)
+from .parallel import shard_range, ShardedScan
+
+__all__ = [n for n in dir() if not n.startswith("_")]

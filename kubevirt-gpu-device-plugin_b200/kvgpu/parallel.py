@@ -1,0 +1,47 @@
+"""Multi-GPU sharding of the scan (BASELINE.json config 4): one process per GPU.
+
+Records are range-partitioned in Walk order, rank r owns [r*N/P, (r+1)*N/P).  Every rank
+classifies its shard; ONE exchange step — an allgatherv of the 16-byte survivor records over
+NCCL/NVLink, rank order == Walk order — rebuilds the global survivor list on every rank, which
+then runs the (replicated) bucketing.  The pci.ids table is parsed by every rank itself.
+
+`ShardedScan` needs only a byte-broadcast callable to distribute the 128-byte NCCL unique id, so
+the same class is driven by torch.distributed (bench.py) or by any other launcher.
+"""
+from __future__ import annotations
+
+from .context import Context, PciResult
+
+
+def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
+    """[lo, hi) of rank's contiguous shard; shards tile [0, n) exactly, sizes differ by <= 1."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank/world")
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def concat_in_rank_order(parts: list) -> list:
+    """The host-side statement of what the allgatherv does: shard outputs concatenated in rank
+    order are the global Walk-order list (used by the gloo CPU tests)."""
+    out = []
+    for p in parts:
+        out.extend(p)
+    return out
+
+
+class ShardedScan:
+    def __init__(self, ctx: Context, rank: int, world: int, broadcast_bytes):
+        """broadcast_bytes(b: bytes | None, src=0) -> bytes : collective byte broadcast."""
+        self.ctx, self.rank, self.world = ctx, rank, world
+        uid = ctx.comm_unique_id() if rank == 0 else None
+        uid = broadcast_bytes(uid, 0)
+        ctx.comm_init(rank, world, uid)
+
+    def scan_device_shard(self, d_recs: int, n_local: int):
+        self.ctx.dev_scan_pci_sharded(d_recs, n_local)
+
+    def fetch(self) -> PciResult:
+        return self.ctx.dev_scan_pci_fetch()
+
+    def close(self):
+        self.ctx.comm_destroy()

@@ -1,0 +1,136 @@
+"""CPU: the C-ABI library loads, exports every declared symbol and fails loudly without a GPU;
+host-side logic (snapshotter, map rebuild, dump, sharding) on CPU."""
+import os
+
+import numpy as np
+import pytest
+
+import conftest
+import util
+
+
+def test_library_exports_every_declared_symbol():
+    import kvgpu
+    lib = kvgpu.load()
+    syms = kvgpu.declared_symbols()
+    assert len(syms) >= 30
+    assert [s for s in syms if not hasattr(lib, s)] == []
+    assert lib.kvg_abi_version() == 1
+    assert lib.kvg_text_pad(1) == 16384 + 16
+    assert lib.kvg_text_pad(16384) == 16384 + 16 and lib.kvg_text_pad(16385) == 2 * 16384 + 16
+
+
+@pytest.mark.skipif(conftest.HAS_GPU, reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_without_gpu():
+    import kvgpu
+    with pytest.raises(kvgpu.KvgError) as e:
+        kvgpu.Context(0)
+    assert e.value.rc == -2  # KVG_ECUDA
+    with pytest.raises(kvgpu.KvgError):
+        kvgpu.DiscoveryScan("/nonexistent", "/nonexistent", "/nonexistent")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(conftest.PKG)
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".go")):
+                src = open(os.path.join(root, f), errors="replace").read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+                assert "kvg_oracle" not in src or f.endswith((".cuh", ".cu")) and "twin" in src, f
+
+
+def test_wire_format_sizes():
+    import kvgpu
+    assert kvgpu.PCI_REC.itemsize == 16 and kvgpu.PCI_SURV.itemsize == 16
+    assert kvgpu.MDEV_REC.itemsize == 32 and kvgpu.MDEV_SURV.itemsize == 32
+    from oracle import oracle as O
+    assert O.PCI_REC == kvgpu.PCI_REC and O.MDEV_REC == kvgpu.MDEV_REC
+
+
+def test_snapshot_pci_tree_config1(tmp_path):
+    import kvgpu
+    from oracle import oracle as O
+    base = util.make_pci_tree(str(tmp_path), util.c1_tree_entries())
+    snap = kvgpu.snapshot_pci_tree(base)
+    assert snap.packed_addr and snap.group_names is None
+    assert snap.names == sorted(util.c1_tree_entries())
+    by = {n: r for n, r in zip(snap.names, snap.recs)}
+    r = by["0000:04:00.0"]
+    assert (r["vendor"], r["device"], r["driver"], r["flags"], r["iommu_group"], r["numa"]) == (
+        0x10de, 0x1b38, 1, 0, 40, 0)
+    assert by["0000:04:00.1"]["numa"] == -1            # clamp happens on the GPU
+    assert by["0000:01:00.0"]["vendor"] == 0x8086       # only vendor is read for non-NVIDIA
+    assert by["0000:08:00.0"]["driver"] == 3            # "nvidia": unsupported
+    assert by["0000:09:00.0"]["flags"] == 2             # no driver link
+    assert by["0000:87:00.0"]["addr"] == kvgpu.parse_bdf("0000:87:00.0")
+    # the snapshot, run through the ORACLE's flat path, equals the oracle's tree walk
+    m1, m2 = O.Maps(), O.Maps()
+    m1.create_iommu_device_map_tree(base)
+    m2.create_iommu_device_map_flat(snap.recs)
+    assert m1.dump(None) == m2.dump(None)
+
+
+def test_snapshot_index_mode_and_interned_groups(tmp_path):
+    import kvgpu
+    G = util.ginkgo()["create_iommu_device_map"]
+    base = util.make_pci_tree(str(tmp_path), G["entries"])
+    snap = kvgpu.snapshot_pci_tree(base)
+    assert not snap.packed_addr and snap.group_names == ["io_1", "io_2", "io_3"]
+    assert snap.names == ["1", "2", "3", "4", "5", "6"]
+    assert list(snap.recs["flags"]) == [16, 16, 16 | 8, 2, 4, 1]   # numa_node absent everywhere
+    assert list(snap.recs["addr"]) == [0, 1, 2, 3, 4, 5]
+
+
+def test_snapshot_mdev_tree(tmp_path):
+    import kvgpu
+    spec = util.ginkgo()["create_vgpu_id_map"]
+    mdev, pci = util.make_mdev_tree(str(tmp_path), {spec["parent_dir"]: spec["parent_numa_content"]},
+                                    spec["entries"])
+    snap = kvgpu.snapshot_mdev_tree(mdev, pci)
+    assert snap.names == ["1", "2", "3", "4", "5"]
+    assert snap.raw_types == [b"vGPUId", b"vGPUId1"] and snap.parent_names == ["GpuId"]
+    assert list(snap.recs["flags"]) == [0, 0, 0, 1, 1]  # a real tree cannot make only the link fail
+    assert list(snap.recs["parent_numa"][:3]) == [2, 2, 2]
+
+
+def test_reference_panic_is_surfaced(tmp_path):
+    import kvgpu
+    ent = {"0000:01:00.0": dict(vendor="10de", device="1b38", driver="vfio-pci", iommu_group="1")}
+    base = util.make_pci_tree(str(tmp_path), ent)
+    with open(os.path.join(base, "0000:01:00.0", "device"), "w") as f:
+        f.write("0")
+    with pytest.raises(kvgpu.ReferencePanic):
+        kvgpu.snapshot_pci_tree(base)
+
+
+def test_maps_and_dump_from_flat_results_cpu():
+    """pci_maps_from_result + canonical_dump on a hand-built flat result (no GPU involved)."""
+    import kvgpu
+    surv = np.zeros(3, dtype=kvgpu.PCI_SURV)
+    surv["addr"] = [kvgpu.parse_bdf(b) for b in ("0000:04:00.0", "0000:04:00.1", "0000:05:00.0")]
+    surv["iommu_group"] = [40, 40, 9]
+    surv["device"] = [0x1b38, 0x10f0, 0x1b38]
+    surv["numa"] = [0, 0, 1]
+    pool = b"\x00" * 4 + bytes([3, 0]) + b"P40"
+    res = kvgpu.PciResult(3, surv, np.array([0x10f0, 0x1b38], np.uint16), np.array([0, 1, 3], np.uint32),
+                          np.array([1, 0, 2], np.uint32), np.array([0xFFFFFFFF, 4], np.uint32),
+                          np.array([9, 40], np.uint32), np.array([0, 1, 3], np.uint32),
+                          np.array([2, 0, 1], np.uint32), pool)
+    m = kvgpu.pci_maps_from_result(res)
+    assert kvgpu.canonical_dump(m) == (
+        b"D 10f0 - nvidia.com/10f0 1\n  0000:04:00.1 0\n"
+        b"D 1b38 P40 nvidia.com/P40 2\n  0000:04:00.0 0\n  0000:05:00.0 1\n"
+        b"I 40 2\n  0000:04:00.0 0\n  0000:04:00.1 0\nI 9 1\n  0000:05:00.0 1\n"
+        b"B 0000:04:00.0 40\nB 0000:04:00.1 40\nB 0000:05:00.0 9\n")
+
+
+def test_shard_ranges_tile_exactly():
+    import kvgpu
+    for n in (0, 1, 7, 100, 1_000_003):
+        for world in (1, 2, 3, 8):
+            edges = [kvgpu.shard_range(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,406 @@
+"""GPU parity: the CUDA path (through the C-ABI of libkvgpu.so) against the CPU oracle, bit for bit.
+
+Every test here needs a B200 (`-m gpu`).  The oracle is only ever the checker.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import util
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def kv():
+    import kvgpu
+    return kvgpu
+
+
+@pytest.fixture(scope="module")
+def ctx(kv):
+    c = kv.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def pciids():
+    return util.pciids_text()
+
+
+@pytest.fixture(scope="module")
+def loaded(ctx, pciids):
+    ctx.pciids_load(pciids)
+    return ctx
+
+
+# ------------------------------------------------------------------------------------------------
+# getDeviceName
+# ------------------------------------------------------------------------------------------------
+def test_ginkgo_get_device_name_kats(ctx):
+    G = util.ginkgo()["get_device_name"]
+    ctx.pciids_load(G["fixture"].encode())
+    for kat in G["kats"]:
+        if kat["missing_file"]:
+            continue
+        assert ctx.name_lookup(kat["key"]) == kat["want"], kat
+    # unreadable file -> "" for every key (device_plugin_test.go:405-409): an empty table
+    ctx.pciids_load(b"")
+    assert ctx.name_lookup("118c") == ""
+    assert ctx.name_lookup("") == ""
+
+
+def test_full_pciids_table_matches_golden(loaded, pciids):
+    d = util.pciids_names()
+    info = loaded.pciids_info()
+    assert info["vendor_off"] == pciids.index(b"\n10de  NVIDIA") + 1
+    assert info["n_lines"] == pciids.count(b"\n")
+    names = loaded.name_table(0, 65536)
+    got = {"%04x" % i: n for i, n in enumerate(names) if n}
+    assert got == {k: v for k, v in d["names"].items() if v}
+    table = "".join("%s %s\n" % (k, got.get(k, "")) for k in sorted(d["names"])).encode()
+    assert hashlib.sha256(table).hexdigest() == d["table_sha256"]
+    # hash path == oracle on hits, misses and other vendors' ids
+    rng = np.random.default_rng(7)
+    for k in list(rng.integers(0, 65536, 300)) + [0x2331, 0x2330, 0xffff, 0x0000, 0x10de]:
+        key = "%04x" % int(k)
+        assert loaded.name_lookup(key) == O.get_device_name(pciids, key), key
+
+
+def test_general_keys_prefix_semantics(loaded, pciids):
+    keys = ["", "1", "1b", "1b3", "1b38 ", "1b38  GP102GL", "\t1043", "1B38", "2901  ", "x", "10de",
+            "0008  NV1 [STG2000X-B Series]", "0008  NV1 [STG2000X-B Series]x", "#", "\n", "1b38\n",
+            "ffffff", "2f", "334", "3340  GB120", "é", "1b3\r"]
+    for k in keys:
+        assert loaded.name_lookup(k.encode("utf-8")) == O.get_device_name(pciids, k.encode("utf-8")), repr(k)
+
+
+def _random_pciids(rng, n_lines):
+    vend = ["10de", "8086", "10de", "1002", "ffff", "10dx", "C 03", "", "10de  dup", "abcd"]
+    alphabet = [b"a", b"B", b"7", b" ", b"  ", b"\t", b"/", b".", b"[", b"]", b"-", b"_", b"\r", b"\x0b",
+                b"\x0c", b"\xc4\xb1", b"\xc5\xbf", b"\xc3\xa9", b"\xc2\xa0", b"\xe2\x80\x80", b"\xff",
+                b"\xe3\x80\x80", b"(", b"x"]
+    out = []
+    for _ in range(n_lines):
+        r = rng.integers(0, 100)
+        if r < 6:
+            out.append(rng.choice(vend).encode() + b"  Vendor " + bytes(rng.integers(65, 91, 3).tolist()))
+        elif r < 12:
+            out.append(b"# comment " + bytes(rng.integers(97, 123, 4).tolist()))
+        elif r < 14:
+            out.append(b"")
+        elif r < 30:
+            out.append(b"\t\t" + b"%04x %04x  sub" % (rng.integers(0, 65536), rng.integers(0, 65536)))
+        else:
+            idv = b"%04x" % rng.integers(0, 40)
+            if r > 95:
+                idv = idv.upper() if rng.integers(0, 2) else idv[:3]
+            sep = [b"  ", b" ", b"\t", b"", b" \xc2\xa0 "][int(rng.integers(0, 5))]
+            body = b"".join(alphabet[int(i)] for i in rng.integers(0, len(alphabet), rng.integers(0, 12)))
+            out.append(b"\t" + idv + sep + body)
+    text = b"\n".join(out)
+    if rng.integers(0, 2):
+        text += b"\n"
+    if rng.integers(0, 4) == 0:
+        text = text.replace(b"\n", b"\r\n")
+    return text
+
+
+def test_random_grammar_fuzz(ctx):
+    rng = np.random.default_rng(20250711)
+    keys = ["%04x" % i for i in range(0, 40)] + ["", "0", "00", "000", "0001 ", "\t", "001\r", "0001\r"]
+    for it in range(60):
+        text = _random_pciids(rng, int(rng.integers(1, 400)))
+        ctx.pciids_load(text)
+        for k in keys:
+            want = O.get_device_name(text, k.encode())
+            got = ctx.name_lookup(k.encode())
+            assert got == want, (it, k, text[:200])
+
+
+def test_tile_boundaries_and_scanner_limit(ctx):
+    TILE = 16384
+    base = b"8086  Intel\n\t1234  wrong vendor\n"
+    # the 10de line, device lines and a section end placed on every offset around a tile edge
+    for delta in range(-8, 9):
+        pad_len = TILE - len(base) + delta - 2
+        text = base + b"#" + b"c" * pad_len + b"\n" + b"10de  NVIDIA\n\t1234  Edge [case]\n" + \
+            b"#" + b"d" * (TILE - 40) + b"\n\t5678  second tile\n10df  next\n\t9999  other\n"
+        ctx.pciids_load(text)
+        for k in ("1234", "5678", "9999", "abcd"):
+            assert ctx.name_lookup(k) == O.get_device_name(text, k.encode()), (delta, k)
+    # vendor context carried across many tiles without any header line
+    many = b"10de  NVIDIA\n" + b"".join(b"\t%04x  dev %d\n" % (i, i) for i in range(0, 9000)) + b"1000 x\n\t0001  y\n"
+    ctx.pciids_load(many)
+    for k in ("0000", "0100", "1fff", "2327", "2328", "0001"):
+        assert ctx.name_lookup(k) == O.get_device_name(many, k.encode()), k
+    # bufio.Scanner 64 KiB token limit
+    tail = b"10de  NVIDIA\n\t1234  name\n"
+    for n, _ in ((65535, "NAME"), (65536, ""), (70000, "")):
+        text = b"x" * n + b"\n" + tail
+        ctx.pciids_load(text)
+        assert ctx.name_lookup("1234") == O.get_device_name(text, b"1234"), n
+    text = b"10de\n\t1234  name\n\t" + b"y" * 65536
+    ctx.pciids_load(text)
+    assert ctx.name_lookup("1234") == "NAME"
+    text = b"10de\n\t" + b"y" * 65536 + b"\n\t1234  name\n"
+    ctx.pciids_load(text)
+    assert ctx.name_lookup("1234") == ""
+    assert ctx.name_lookup("yyyy") == O.get_device_name(text, b"yyyy") == ""
+
+
+# ------------------------------------------------------------------------------------------------
+# createIommuDeviceMap on flat snapshots
+# ------------------------------------------------------------------------------------------------
+def _pci_dump_gpu(kv, ctx, recs):
+    res = ctx.scan_pci(recs)
+    return kv.canonical_dump(kv.pci_maps_from_result(res)), res
+
+
+def _pci_dump_oracle(recs, pciids):
+    m = O.Maps()
+    m.create_iommu_device_map_flat(recs)
+    return m.dump(pciids)
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 255, 256, 257, 2047, 2048, 2049, 6000, 100_003])
+@pytest.mark.parametrize("group_bits", [0, 12])
+def test_scan_pci_matches_oracle(kv, loaded, pciids, n, group_bits):
+    ids = O.nv_ids(pciids)
+    recs = O.gen_pci(0, n, ids, group_bits)
+    got, res = _pci_dump_gpu(kv, loaded, recs)
+    want = _pci_dump_oracle(recs, pciids)
+    assert hashlib.sha256(got).hexdigest() == hashlib.sha256(want).hexdigest()
+    assert got == want
+    assert res.n_records == n
+
+
+def test_scan_pci_config2_one_million(kv, loaded, pciids):
+    """BASELINE.json config 2: full pci.ids + 1,000,000 synthetic PCI records."""
+    ids = O.nv_ids(pciids)
+    recs = O.gen_pci(0, 1_000_000, ids, 19)
+    got, res = _pci_dump_gpu(kv, loaded, recs)
+    want = _pci_dump_oracle(recs, pciids)
+    assert hashlib.sha256(got).hexdigest() == hashlib.sha256(want).hexdigest()
+    assert 330_000 < len(res.survivors) < 360_000
+
+
+def test_scan_pci_edge_populations(kv, loaded, pciids):
+    n = 5000
+    recs = np.zeros(n, dtype=kv.PCI_REC)
+    recs["addr"] = np.arange(n)
+    recs["vendor"], recs["device"], recs["driver"] = 0x10de, 0x1b38, 1
+    recs["iommu_group"] = 7          # one giant IOMMU group
+    recs["numa"] = -1
+    got, res = _pci_dump_gpu(kv, loaded, recs)
+    assert got == _pci_dump_oracle(recs, pciids)
+    assert len(res.survivors) == n and len(res.grp_keys) == 1 and len(res.dev_keys) == 1
+    recs["flags"] = 8                # device read fails everywhere -> nothing survives
+    got, res = _pci_dump_gpu(kv, loaded, recs)
+    assert got == b"" == _pci_dump_oracle(recs, pciids)
+    recs["flags"] = 16               # numa unreadable -> kept with numa 0
+    recs["numa"] = 5
+    recs["iommu_group"] = np.arange(n)[::-1] * 977 % 4099 + 0xFFFF0000  # 32-bit group keys
+    recs["device"] = np.arange(n) % 300 + 0x1b00
+    got, res = _pci_dump_gpu(kv, loaded, recs)
+    assert got == _pci_dump_oracle(recs, pciids)
+    assert (res.survivors["numa"] == 0).all()
+
+
+def test_scan_requires_table(kv):
+    c = kv.Context(0)
+    with pytest.raises(kv.KvgError) as e:
+        c.scan_pci(np.zeros(4, dtype=kv.PCI_REC))
+    assert e.value.rc == -5
+    c.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# createVgpuIDMap on flat snapshots (BASELINE.json config 3)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 100, 2049, 65536])
+def test_scan_mdev_matches_oracle(kv, loaded, pciids, n):
+    recs = O.gen_mdev(0, n)
+    types = O.gen_type_names(256)
+    res = loaded.scan_mdev(recs, types)
+    got = kv.canonical_dump(kv.mdev_maps_from_result(res))
+    m = O.Maps()
+    m.create_vgpu_id_map_flat(recs, types)
+    want = m.dump(pciids)
+    assert got == want
+    if n == 65536:
+        assert len(res.type_keys) == 128          # 256 raw names, pairs merge after sanitising
+        assert all(nm == "" for nm in res.type_names)  # vGPU labels never match pci.ids (:152-155)
+
+
+def test_scan_mdev_label_that_matches_pciids(kv, loaded, pciids):
+    """A type label that happens to be a device-line prefix DOES resolve (prefix semantics)."""
+    recs = O.gen_mdev(0, 64)
+    recs["type_idx"] = np.arange(64) % 3
+    types = [b"1b38\n", b"GRID  P100X-1B\n", b"\n\n0008  NV1\n"]
+    res = loaded.scan_mdev(recs, types)
+    got = kv.canonical_dump(kv.mdev_maps_from_result(res))
+    m = O.Maps()
+    m.create_vgpu_id_map_flat(recs, types)
+    assert got == m.dump(pciids)
+    assert res.type_names[0] == "GP102GL_TESLA_P40"
+    assert res.labels[1] == b"GRID_P100X-1B"
+
+
+# ------------------------------------------------------------------------------------------------
+# health re-scan (BASELINE.json config 5)
+# ------------------------------------------------------------------------------------------------
+def _alive(recs):
+    drop = 1 | 2 | 4 | 8
+    return (recs["vendor"] == 0x10de) & ((recs["flags"] & drop) == 0) & (
+        (recs["driver"] == 1) | (recs["driver"] == 2))
+
+
+def test_health_rescan_transitions(kv, loaded, pciids):
+    ids = O.nv_ids(pciids)
+    n = 10_000
+    recs = O.gen_pci(0, n, ids, 0)
+    loaded.health_reset()
+    prev = np.zeros(n, dtype=bool)
+    rng = np.random.default_rng(5)
+    for tick in range(6):
+        if tick:
+            flip = rng.integers(0, n, 10)
+            recs["driver"][flip] = rng.integers(0, 5, 10)
+            recs["flags"][flip] ^= rng.integers(0, 32, 10).astype(np.uint8)
+        d = loaded.health_rescan(recs)
+        now = _alive(recs)
+        idx = np.nonzero(now != prev)[0]
+        want = (idx.astype(np.uint32) << 1) | now[idx].astype(np.uint32)
+        assert d.n_alive == int(now.sum())
+        assert np.array_equal(d.changed, want)
+        prev = now
+
+
+# ------------------------------------------------------------------------------------------------
+# real directory trees through the plugin-shaped interface
+# ------------------------------------------------------------------------------------------------
+def test_discovery_scan_on_trees(kv, tmp_path, pciids):
+    G = util.ginkgo()
+    ids_path = tmp_path / "pci.ids"
+    ids_path.write_bytes(pciids)
+    # config 1: 8 Tesla P40 + decoys
+    base = util.make_pci_tree(str(tmp_path / "c1"), util.c1_tree_entries())
+    ds = kv.DiscoveryScan(str(ids_path), base, str(tmp_path / "nomdev"))
+    ds.create_iommu_device_map()
+    ds.create_vgpu_id_map()
+    m = O.Maps()
+    m.create_iommu_device_map_tree(base)
+    m.create_vgpu_id_map_tree(str(tmp_path / "nomdev"), base)
+    assert kv.canonical_dump(ds.maps) == m.dump(pciids)
+    specs = {s.key: s for s in ds.create_device_plugins()}
+    p40 = specs["1b38"]
+    assert p40.resource_name == "nvidia.com/GP102GL_TESLA_P40"
+    assert p40.socket_path == "/var/lib/kubelet/device-plugins/kubevirt-GP102GL_TESLA_P40.sock"
+    assert p40.env_key == "PCI_RESOURCE_NVIDIA_COM_GP102GL_TESLA_P40"
+    assert [d["ID"] for d in p40.devs] == ["0000:%s:00.0" % b for b in
+                                           ("04", "05", "06", "07", "84", "85", "86", "87")]
+    assert [d["Topology"]["Nodes"][0]["ID"] for d in p40.devs] == [0, 0, 0, 0, 1, 1, 1, 1]
+    assert ds.get_device_name("1b38") == "GP102GL_TESLA_P40"
+    # the Ginkgo createIommuDeviceMap fixture: non-BDF names, non-numeric groups (index mode)
+    base2 = util.make_pci_tree(str(tmp_path / "gk"), G["create_iommu_device_map"]["entries"])
+    ds.basePath = base2
+    ds.create_iommu_device_map()
+    assert ds.maps.iommuMap["io_1"][0].addr == "1"
+    assert ds.maps.deviceMap["1b80"][0].addr == "1"
+    assert ds.maps.deviceMap["1b81"][0].addr == "2"
+    assert ds.maps.bdfToIommuMap["1"] == "io_1"
+    assert set(ds.maps.deviceMap) == {"1b80", "1b81"}
+    # the Ginkgo createVgpuIDMap fixture
+    spec = G["create_vgpu_id_map"]
+    mdev, pci = util.make_mdev_tree(str(tmp_path / "vg"), {spec["parent_dir"]: spec["parent_numa_content"]},
+                                    spec["entries"])
+    ds.vGpuBasePath, ds.basePath = mdev, pci
+    ds.create_vgpu_id_map()
+    assert ds.maps.gpuVgpuMap["GpuId"][0] == "1"
+    assert ds.maps.vGpuMap["vGPUId"][0].addr == "1" and ds.maps.vGpuMap["vGPUId"][0].numaNode == 2
+    m2 = O.Maps()
+    m2.create_vgpu_id_map_tree(mdev, pci)
+    ds.maps.iommuMap, ds.maps.deviceMap, ds.maps.bdfToIommuMap = {}, {}, {}
+    assert kv.canonical_dump(ds.maps) == m2.dump(pciids)
+    ds.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# device-resident path, generators, batch parse, full-size properties
+# ------------------------------------------------------------------------------------------------
+def test_device_generators_match_oracle(kv, loaded, pciids):
+    import torch
+    ids = O.nv_ids(pciids)
+    n = 50_001
+    buf = torch.empty(n * 16, dtype=torch.uint8, device="cuda")
+    for bits in (0, 15):
+        loaded.dev_gen_pci(buf.data_ptr(), 1234567, n, ids, bits)
+        loaded.dev_scan_pci(buf.data_ptr(), 0)  # stream sync via fetch
+        loaded.dev_scan_pci_count()
+        got = np.frombuffer(buf.cpu().numpy().tobytes(), dtype=kv.PCI_REC)
+        assert np.array_equal(got, O.gen_pci(1234567, n, ids, bits))
+    mb = torch.empty(n * 32, dtype=torch.uint8, device="cuda")
+    loaded.dev_gen_mdev(mb.data_ptr(), 99, n)
+    loaded.dev_scan_pci_count()
+    got = np.frombuffer(mb.cpu().numpy().tobytes(), dtype=kv.MDEV_REC)
+    want = O.gen_mdev(99, n)
+    assert got.tobytes() == want.tobytes()
+
+
+def test_batch_parse_device_resident(kv, pciids):
+    import torch
+    c = kv.Context(0)
+    n_files = 5
+    stride = c.text_pad(len(pciids)) + 16
+    host = np.full(stride * n_files, 10, dtype=np.uint8)
+    for f in range(n_files):
+        host[f * stride:f * stride + len(pciids)] = np.frombuffer(pciids, dtype=np.uint8)
+    dev = torch.from_numpy(host).cuda()
+    torch.cuda.synchronize()
+    c.dev_pciids_parse(dev.data_ptr(), len(pciids), stride, n_files)
+    info = c.pciids_info()
+    assert info["n_lines"] == pciids.count(b"\n")
+    d = util.pciids_names()
+    names = c.name_table(0, 65536)
+    assert {"%04x" % i: n for i, n in enumerate(names) if n} == {k: v for k, v in d["names"].items() if v}
+    assert info["n_entries"] > 19000
+    c.dev_pciids_parse(dev.data_ptr(), len(pciids), stride, n_files)  # steady-state path
+    assert c.name_lookup("2901") == "GB100_B200"
+    c.close()
+
+
+def test_full_size_properties(kv, loaded, pciids):
+    """16,777,216 records (> L2): size-independent properties instead of the oracle."""
+    import torch
+    ids = O.nv_ids(pciids)
+    n = 1 << 24
+    buf = torch.empty(n * 16, dtype=torch.uint8, device="cuda")
+    loaded.dev_gen_pci(buf.data_ptr(), 0, n, ids, 23)
+    loaded.dev_scan_pci(buf.data_ptr(), n)
+    res = loaded.dev_scan_pci_fetch()
+    recs = np.frombuffer(buf.cpu().numpy().tobytes(), dtype=kv.PCI_REC)
+    alive = _alive(recs)
+    S = int(alive.sum())
+    assert len(res.survivors) == S
+    # stable compaction: survivors are exactly the alive records, in order
+    assert np.array_equal(res.survivors["addr"], recs["addr"][alive])
+    assert np.array_equal(res.survivors["iommu_group"], recs["iommu_group"][alive])
+    assert np.array_equal(res.survivors["device"], recs["device"][alive])
+    for keys, off, perm, field in ((res.dev_keys, res.dev_off, res.dev_perm, "device"),
+                                   (res.grp_keys, res.grp_off, res.grp_perm, "iommu_group")):
+        assert np.all(np.diff(keys.astype(np.int64)) > 0)            # distinct, ascending
+        assert off[0] == 0 and off[-1] == S and np.all(np.diff(off.astype(np.int64)) > 0)
+        assert np.array_equal(np.sort(perm), np.arange(S, dtype=np.uint32))  # a permutation
+        k_of = res.survivors[field][perm]
+        assert np.array_equal(k_of, np.repeat(keys, np.diff(off)))   # bucket k holds key k only
+        same = k_of[1:] == k_of[:-1]
+        assert np.all(perm[1:][same] > perm[:-1][same])              # stable inside a bucket
+    # the join: name slots agree with the table for every distinct device id
+    names = loaded.name_table(0, 65536)
+    for k in range(0, len(res.dev_keys), 97):
+        assert res.name_at(int(res.dev_name_slot[k])) == names[int(res.dev_keys[k])]
