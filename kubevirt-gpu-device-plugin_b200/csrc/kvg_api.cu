@@ -120,6 +120,7 @@ struct kvg_ctx {
   std::vector<uint8_t> h_pool;
   PciIdsInfo h_info{};
   bool table_ready = false;
+  uint32_t parsed_files = 0;
   int parse_grid = 0;
 
   // scans
@@ -389,7 +390,7 @@ static uint32_t table_log2_for(size_t len) {
 }
 
 static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t stride,
-                         uint32_t n_files) {
+                         uint32_t n_files, uint32_t cap_log2) {
   if (len == 0 || len >= 0xfffffff0ull) {
     ctx->err = "pci.ids length out of range";
     return KVG_EINVAL;
@@ -401,13 +402,12 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
     return KVG_EINVAL;
   }
   uint32_t n_tiles = (uint32_t)n_tiles64;
-  ctx->cap_log2 = table_log2_for(len);
+  ctx->cap_log2 = cap_log2;
   size_t cap = (size_t)1 << ctx->cap_log2;
   ENSURE(ctx->tables, cap * n_files);
   ENSURE(ctx->info, n_files);
   ENSURE(ctx->tile_arrays, 3 * (size_t)n_tiles);
   ENSURE(ctx->parse_state, n_tiles);
-  ENSURE(ctx->parse_ticket, 1);
 
   ParseArgs A;
   A.text = d_text;
@@ -425,7 +425,6 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
   A.tile_last_nl = ctx->tile_arrays.p + 2 * (size_t)n_tiles;
   A.tile_state = ctx->parse_state.p;
   A.epoch = ++ctx->epoch;
-  A.ticket = ctx->parse_ticket.p;
 
   // table slots <- EMPTY, info <- {v_off = NONE, 0...}, ticket <- 0
   {
@@ -437,7 +436,6 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
   }
   CK(cudaMemsetAsync(ctx->info.p, 0, sizeof(PciIdsInfo) * n_files, ctx->stream));
   CK(cudaMemset2DAsync(ctx->info.p, sizeof(PciIdsInfo), 0xff, sizeof(uint32_t), n_files, ctx->stream));
-  CK(cudaMemsetAsync(ctx->parse_ticket.p, 0, sizeof(uint32_t), ctx->stream));
   int grid = ctx->parse_grid;
   if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
   LAUNCH("pciids_parse", k_pciids_parse, grid, KVG_BLOCK, P_STAGES * P_STAGE, A);
@@ -473,6 +471,30 @@ static int table_publish(kvg_ctx* ctx, const uint8_t* d_text, size_t len) {
   return KVG_OK;
 }
 
+// The table is sized from the text length (pci.ids has ~1 device line per 77 bytes); an input with
+// denser device lines overflows it, which K1 reports instead of spinning: re-parse with a table
+// sized from the line count until the load factor is sane.
+static int parse_with_regrow(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t stride,
+                             uint32_t n_files) {
+  uint32_t cap_log2 = table_log2_for(len);
+  for (;;) {
+    int rc = parse_enqueue(ctx, d_text, len, stride, n_files, cap_log2);
+    if (rc) return rc;
+    rc = table_publish(ctx, d_text, len);
+    if (rc) return rc;
+    size_t cap = (size_t)1 << cap_log2;
+    bool crowded = (size_t)ctx->h_info.n_entries * 10 > cap * 7;
+    if (!ctx->h_info.overflow && !crowded) return KVG_OK;
+    ctx->table_ready = false;
+    if (cap_log2 >= 30) {
+      ctx->err = "pci.ids hash table cannot grow further";
+      return KVG_ENOMEM;
+    }
+    size_t want = ctx->h_info.overflow ? cap * 4 : (size_t)ctx->h_info.n_entries * 2;
+    while (((size_t)1 << cap_log2) < want) cap_log2++;
+  }
+}
+
 int kvg_pciids_load(kvg_ctx* ctx, const uint8_t* text, size_t len) {
   if (!ctx || (!text && len)) return KVG_EINVAL;
   CK(cudaSetDevice(ctx->device));
@@ -493,9 +515,7 @@ int kvg_pciids_load(kvg_ctx* ctx, const uint8_t* text, size_t len) {
   ENSURE(ctx->text, padded);
   CK(cudaMemsetAsync(ctx->text.p, '\n', padded, ctx->stream));
   CK(cudaMemcpyAsync(ctx->text.p, text, len, cudaMemcpyHostToDevice, ctx->stream));
-  int rc = parse_enqueue(ctx, ctx->text.p, len, padded, 1);
-  if (rc) return rc;
-  return table_publish(ctx, ctx->text.p, len);
+  return parse_with_regrow(ctx, ctx->text.p, len, padded, 1);
 }
 
 int kvg_dev_pciids_parse(kvg_ctx* ctx, const void* d_text, size_t len, size_t stride, uint32_t n_files) {
@@ -503,11 +523,15 @@ int kvg_dev_pciids_parse(kvg_ctx* ctx, const void* d_text, size_t len, size_t st
       (n_files > 1 && stride < kvg_text_pad(len)))
     return KVG_EINVAL;
   CK(cudaSetDevice(ctx->device));
-  int rc = parse_enqueue(ctx, (const uint8_t*)d_text, len, stride, n_files);
+  // first call on an image publishes (host mirror of the name pool, table sizing); later calls on
+  // the same image stay fully asynchronous: parse + finalize + sanitise enqueued, no host sync
+  if (!ctx->table_ready || ctx->d_text != d_text || ctx->text_len != len || ctx->parsed_files != n_files) {
+    int rc0 = parse_with_regrow(ctx, (const uint8_t*)d_text, len, stride, n_files);
+    if (rc0 == KVG_OK) ctx->parsed_files = n_files;
+    return rc0;
+  }
+  int rc = parse_enqueue(ctx, (const uint8_t*)d_text, len, stride, n_files, ctx->cap_log2);
   if (rc) return rc;
-  // bench path: sanitise on the stream without the host mirror round trip when the section
-  // bounds are already known to be the same image (first call publishes, later calls re-run K2)
-  if (!ctx->table_ready || ctx->d_text != d_text || ctx->text_len != len) return table_publish(ctx, (const uint8_t*)d_text, len);
   size_t sec = ctx->h_pool.size();
   if (sec > 16) {
     int grid = (int)((sec + KVG_BLOCK - 1) / KVG_BLOCK);
@@ -658,12 +682,22 @@ int kvg_name_table(kvg_ctx* ctx, uint32_t first, uint32_t count, uint32_t* out_o
 // ================================================================================================
 // scans
 // ================================================================================================
+}  // extern "C"
+// k_compact needs a CO-RESIDENT grid (static round-robin tiles + look-back): cap it at
+// occupancy x SMs of the instantiation, and at the tile count when the host knows it.
+template <class Op>
 static int compact_grid(kvg_ctx* ctx, size_t n_items) {
+  static int occ = 0;
+  if (!occ) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_compact<Op>, KVG_BLOCK, 0);
+    if (occ < 1) occ = 1;
+  }
   size_t tiles = (n_items + C_TILE - 1) / C_TILE;
-  size_t g = (size_t)ctx->sm_count * 6;  // 6 x 256 threads resident per SM
+  size_t g = (size_t)ctx->sm_count * (size_t)occ;
   if (tiles < g) g = tiles;
   return g < 1 ? 1 : (int)g;
 }
+extern "C" {
 
 static int ensure_order(kvg_ctx* ctx, OrderBufs& o, size_t cap) {
   ENSURE(o.k0, cap); ENSURE(o.v0, cap); ENSURE(o.k1, cap); ENSURE(o.v1, cap);
@@ -722,6 +756,8 @@ struct HeadsSelOp {
   uint32_t* seg_off;
   uint32_t* n_seg_out;
   const uint32_t* keys;  // resolved in count()
+  __device__ __forceinline__ void begin() {}
+  __device__ __forceinline__ uint32_t prepare(const Item&) const { return 0; }
   __device__ __forceinline__ uint32_t count() {
     uint32_t mk = *max_key;
     int np = 1;
@@ -734,7 +770,7 @@ struct HeadsSelOp {
     return make_uint2(keys[i], i ? keys[i - 1] : 0);
   }
   __device__ __forceinline__ bool pred(const Item& v, uint32_t i) const { return i == 0 || v.x != v.y; }
-  __device__ __forceinline__ void emit(uint32_t pos, const Item& v, uint32_t i) {
+  __device__ __forceinline__ void emit(uint32_t pos, const Item& v, uint32_t i, uint32_t) {
     seg_key[pos] = v.x;
     seg_off[pos] = i;
   }
@@ -763,8 +799,8 @@ static int enqueue_heads(kvg_ctx* ctx, OrderBufs& o, size_t cap, int npass_max, 
   h.seg_off = o.seg_off.p;
   h.n_seg_out = d_n_seg;
   h.keys = nullptr;
-  LAUNCH("segment_heads", k_compact<HeadsSelOp>, compact_grid(ctx, cap), KVG_BLOCK, 0, h,
-         o.heads_state.p, ++ctx->epoch, ticket);
+  LAUNCH("segment_heads", k_compact<HeadsSelOp>, compact_grid<HeadsSelOp>(ctx, cap), KVG_BLOCK, 0, h,
+         o.heads_state.p, ++ctx->epoch);
   return check_launch(ctx, "segment heads");
 }
 
@@ -798,8 +834,8 @@ static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d
   op.info = ctx->info.p;
   op.local_max_group = 0;
   op.local_max_dev = 0;
-  LAUNCH("classify_compact", k_compact<PciClassifyOp>, compact_grid(ctx, n), KVG_BLOCK, 0, op,
-         ctx->classify_state.p, ++ctx->epoch, &ctx->ctrl.p->ticket[0]);
+  LAUNCH("classify_compact", k_compact<PciClassifyOp>, compact_grid<PciClassifyOp>(ctx, n), KVG_BLOCK, 0, op,
+         ctx->classify_state.p, ++ctx->epoch);
   return check_launch(ctx, "classify");
 }
 
@@ -969,8 +1005,8 @@ int kvg_health_rescan(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, kvg_healt
   op.changed = ctx->changed.p;
   op.ctrl = ctx->ctrl.p;
   op.local_alive = 0;
-  LAUNCH("health_diff", k_compact<HealthOp>, compact_grid(ctx, n), KVG_BLOCK, 0, op,
-         ctx->classify_state.p, ++ctx->epoch, &ctx->ctrl.p->ticket[0]);
+  LAUNCH("health_diff", k_compact<HealthOp>, compact_grid<HealthOp>(ctx, n), KVG_BLOCK, 0, op,
+         ctx->classify_state.p, ++ctx->epoch);
   rc = check_launch(ctx, "health");
   if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1085,8 +1121,8 @@ int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type
   op.n_types = nt;
   op.local_max_parent = 0;
   op.local_max_type = 0;
-  LAUNCH("mdev_classify_compact", k_compact<MdevClassifyOp>, compact_grid(ctx, n), KVG_BLOCK, 0, op,
-         ctx->classify_state.p, ++ctx->epoch, &ctx->ctrl.p->ticket[0]);
+  LAUNCH("mdev_classify_compact", k_compact<MdevClassifyOp>, compact_grid<MdevClassifyOp>(ctx, n), KVG_BLOCK, 0, op,
+         ctx->classify_state.p, ++ctx->epoch);
   rc = check_launch(ctx, "mdev classify");
   if (rc) return rc;
   rc = ensure_order(ctx, ctx->ord_dev, n);

@@ -32,7 +32,8 @@ struct PciIdsInfo {
   uint32_t n_entries; // distinct (vendor,device) keys inserted
   uint32_t n_lines;
   uint32_t limit;     // start of the first line bufio.Scanner would reject (>= 64 KiB), or len
-  uint32_t pad[3];
+  uint32_t overflow;  // set when an insert found no free slot: the host re-parses with a larger table
+  uint32_t pad[2];
 };
 
 struct ParseArgs {
@@ -51,7 +52,6 @@ struct ParseArgs {
   uint32_t* tile_last_nl;
   uint64_t* tile_state;  // [n_tiles] vendor-context look-back
   uint32_t epoch;
-  uint32_t* ticket;
 };
 
 __device__ __forceinline__ uint32_t hash32(uint32_t key, uint32_t shift) {
@@ -84,12 +84,17 @@ __device__ __forceinline__ uint32_t parse_hex4(const uint8_t* p) {
   return bad ? 0u : (0x10000u | (h0 << 12) | (h1 << 8) | (h2 << 4) | h3);
 }
 
-// first line wins: slot = key<<32 | line offset, atomicMin on a matching key
+// first line wins: slot = key<<32 | line offset, atomicMin on a matching key.
+// Probing is bounded by the table size; a full table raises *overflow instead of spinning.
 __device__ __forceinline__ bool table_insert(uint64_t* table, uint32_t mask, uint32_t shift,
-                                             uint32_t key, uint32_t off) {
+                                             uint32_t key, uint32_t off, uint32_t* overflow) {
   uint64_t item = ((uint64_t)key << 32) | off;
   uint32_t h = hash32(key, shift) & mask;
-  for (;;) {
+  for (uint32_t probes = 0;; probes++) {
+    if (probes > mask) {
+      atomicExch(overflow, 1u);
+      return false;
+    }
     uint64_t old = atomicCAS((unsigned long long*)&table[h], (unsigned long long)P_EMPTY,
                              (unsigned long long)item);
     if (old == P_EMPTY) return true;
@@ -103,17 +108,19 @@ __device__ __forceinline__ bool table_insert(uint64_t* table, uint32_t mask, uin
 __device__ __forceinline__ uint32_t table_probe(const uint64_t* __restrict__ table, uint32_t mask,
                                                 uint32_t shift, uint32_t key) {
   uint32_t h = hash32(key, shift) & mask;
-  for (;;) {
+  for (uint32_t probes = 0; probes <= mask; probes++) {
     uint64_t s = __ldg((const unsigned long long*)&table[h]);
     if (s == P_EMPTY) return P_NONE;
     if ((uint32_t)(s >> 32) == key) return (uint32_t)s;
     h = (h + 1) & mask;
   }
+  return P_NONE;
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1.  Persistent CTAs, tiles handed out by an atomic ticket (so look-back predecessors are
-// always resident), 3-stage TMA ring.  A tile owns the lines that START in (a, a+TILE], plus the
+// K1.  Persistent co-resident CTAs (grid <= occupancy x SMs), tile = blockIdx + k*gridDim: a
+// look-back predecessor always belongs to a resident CTA that reaches it no later than we reach
+// ours, and consecutive tiles sit in different CTAs so their chains overlap.  3-stage TMA ring.  A tile owns the lines that START in (a, a+TILE], plus the
 // line at offset 0 for the first tile of an image; the 16 halo bytes let it classify a line that
 // starts on its last byte.
 // ------------------------------------------------------------------------------------------------
@@ -121,16 +128,14 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_parse(ParseArgs A) {
   extern __shared__ __align__(128) uint8_t p_smem[];
   uint8_t* stage_buf = p_smem;  // P_STAGES * P_STAGE
   __shared__ __align__(8) uint64_t full_bar[P_STAGES];
-  __shared__ uint32_t s_tile[P_STAGES];
   __shared__ uint32_t s_scratch[KVG_WARPS + 1];
   __shared__ uint32_t s_carry;
   __shared__ uint32_t s_first_hdr, s_first_nl, s_last_nl;
 
   const uint32_t tid = threadIdx.x;
 
-  auto issue = [&](uint32_t stage) {  // thread 0 only
-    uint32_t t = atomicAdd(A.ticket, 1u);
-    s_tile[stage] = t;
+  auto issue = [&](uint32_t stage, uint32_t it) {  // thread 0 only
+    uint32_t t = blockIdx.x + it * gridDim.x;
     if (t < A.n_tiles) {
       uint32_t f = t / A.tiles_per_file, j = t - f * A.tiles_per_file;
       const uint8_t* src = A.text + (uint64_t)f * A.stride + (uint64_t)j * P_TILE;
@@ -145,15 +150,14 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_parse(ParseArgs A) {
   }
   __syncthreads();
   if (tid == 0)
-    for (uint32_t s = 0; s < P_STAGES; s++) issue(s);
-  __syncthreads();
+    for (uint32_t s = 0; s < P_STAGES; s++) issue(s, s);
 
   uint32_t n_new = 0, n_lines = 0;  // per-thread tallies, flushed per tile
 
   for (uint32_t it = 0;; ++it) {
     const uint32_t stage = it % P_STAGES;
     const uint32_t parity = (it / P_STAGES) & 1;
-    const uint32_t tile = s_tile[stage];
+    const uint32_t tile = blockIdx.x + it * gridDim.x;
     if (tile >= A.n_tiles) break;
     const uint32_t f = tile / A.tiles_per_file, j = tile - f * A.tiles_per_file;
     const uint32_t a = j * P_TILE;  // file offset of the tile
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_parse(ParseArgs A) {
         uint32_t dv = parse_hex4(sm + p + 1);
         if ((dv & ctx) & 0x10000u)
           n_new += table_insert(table, A.cap_mask, A.cap_shift, ((ctx & 0xffffu) << 16) | (dv & 0xffffu),
-                                a + p);
+                                a + p, &A.info[f].overflow);
       };
       if (j == 0 && tid == 0) visit(0);
       for (uint64_t mm = mask; mm; mm &= mm - 1) visit(sp + (uint32_t)__ffsll((long long)mm));
@@ -253,7 +257,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_parse(ParseArgs A) {
       n_lines = 0;
     }
     __syncthreads();  // everyone is done with this stage
-    if (tid == 0) issue(stage);
+    if (tid == 0) issue(stage, it + P_STAGES);
   }
 }
 
@@ -265,25 +269,31 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_finalize(ParseArgs A) {
   const uint8_t* text = A.text + (uint64_t)f * A.stride;
   const uint32_t t0 = f * A.tiles_per_file;
   PciIdsInfo* info = &A.info[f];
-  __shared__ uint32_t s_end, s_limit;
+  __shared__ uint32_t s_end, s_limit, s_hdr_tile;
   if (threadIdx.x == 0) {
     s_end = A.len;
-    // bufio.Scanner: a line with no '\n' in its first 64 KiB ends the scan with ErrTooLong.
-    // Within one tile two newlines are < 16 KiB apart, so only gaps across tiles can be long.
-    uint32_t line_start = 0, limit = A.len;
-    bool hit = false;
-    for (uint32_t t = 0; t < A.tiles_per_file && !hit; t++) {
-      uint32_t fn = A.tile_first_nl[t0 + t];
+    s_limit = A.len;
+    s_hdr_tile = P_NONE;
+  }
+  __syncthreads();
+  // bufio.Scanner: a line with no '\n' in its first 64 KiB ends the scan with ErrTooLong.  Inside
+  // one tile two newlines are < 16 KiB apart, so only a gap that spans tiles can be long: thread
+  // per tile, gap = from the previous newline (scan back over newline-free tiles) to my first.
+  for (uint32_t t = threadIdx.x; t <= A.tiles_per_file; t += blockDim.x) {
+    uint32_t fn;  // first newline at or after tile t (the virtual last tile stands for EOF)
+    if (t == A.tiles_per_file) fn = A.len;
+    else {
+      fn = A.tile_first_nl[t0 + t];
       if (fn == P_NONE) continue;
-      if (fn - line_start >= SCAN_TOKEN_MAX) {
-        limit = line_start;
-        hit = true;
+    }
+    uint32_t line_start = 0;
+    for (int u = (int)t - 1; u >= 0; u--) {
+      if (A.tile_first_nl[t0 + u] != P_NONE) {
+        line_start = A.tile_last_nl[t0 + u] + 1;
         break;
       }
-      line_start = A.tile_last_nl[t0 + t] + 1;
     }
-    if (!hit && A.len - line_start >= SCAN_TOKEN_MAX && line_start < A.len) limit = line_start;
-    s_limit = limit;
+    if (line_start < A.len && fn - line_start >= SCAN_TOKEN_MAX) atomicMin(&s_limit, line_start);
   }
   __syncthreads();
   const uint32_t V = info->v_off;
@@ -305,18 +315,12 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_finalize(ParseArgs A) {
       if (b0 != '\t' && b0 != '#') atomicMin(&s_end, p);
     }
   }
+  for (uint32_t t = tv + 1 + threadIdx.x; t < A.tiles_per_file; t += blockDim.x)
+    if (A.tile_first_hdr[t0 + t] != P_NONE) atomicMin(&s_hdr_tile, t);
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t e = s_end;
-    if (e == A.len) {
-      for (uint32_t t = tv + 1; t < A.tiles_per_file; t++) {
-        uint32_t h = A.tile_first_hdr[t0 + t];
-        if (h != P_NONE) {
-          e = h;
-          break;
-        }
-      }
-    }
+    if (e == A.len && s_hdr_tile != P_NONE) e = A.tile_first_hdr[t0 + s_hdr_tile];
     info->sec_end = min(e, limit);
     info->limit = limit;
   }

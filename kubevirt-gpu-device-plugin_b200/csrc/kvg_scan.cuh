@@ -46,10 +46,10 @@ struct ScanCtrl {
 //   void finish(uint32_t total)     called by one thread of the last tile
 // ------------------------------------------------------------------------------------------------
 template <class Op>
-__global__ void __launch_bounds__(KVG_BLOCK) k_compact(Op op, uint64_t* tile_state, uint32_t epoch,
-                                                       uint32_t* ticket) {
-  __shared__ uint32_t s_tile, s_base;
+__global__ void __launch_bounds__(KVG_BLOCK) k_compact(Op op, uint64_t* tile_state, uint32_t epoch) {
+  __shared__ uint32_t s_base;
   __shared__ uint32_t s_wtot[KVG_WARPS], s_woff[KVG_WARPS];
+  op.begin();
   const uint32_t n = op.count();
   const uint32_t n_tiles = (n + C_TILE - 1) / C_TILE;
   const uint32_t lane = lane_id(), warp = warp_id();
@@ -57,21 +57,17 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_compact(Op op, uint64_t* tile_sta
     if (blockIdx.x == 0 && threadIdx.x == 0) op.finish(0);
     return;
   }
-  for (;;) {
-    __syncthreads();  // previous iteration fully consumed s_*
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    if (tile >= n_tiles) break;
+  // Persistent, co-resident grid; tile = blockIdx + k*gridDim.  A look-back predecessor is owned by
+  // a resident CTA that reaches it no later than this CTA reaches its own tile (no ticket needed).
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
-
     typename Op::Item item[C_ROWS];
 #pragma unroll
     for (uint32_t k = 0; k < C_ROWS; k++) {
       uint32_t i = base + k * 32 + lane;
       item[k] = op.load(i, i < n);
     }
-    uint32_t bal[C_ROWS];
+    uint32_t bal[C_ROWS], aux[C_ROWS];
     uint32_t wtot = 0;
 #pragma unroll
     for (uint32_t k = 0; k < C_ROWS; k++) {
@@ -79,6 +75,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_compact(Op op, uint64_t* tile_sta
       bool p = i < n && op.pred(item[k], i);
       bal[k] = __ballot_sync(KVG_FULL, p);
       wtot += __popc(bal[k]);
+      aux[k] = p ? op.prepare(item[k]) : 0u;  // dependent loads overlap the look-back below
     }
     if (lane == 0) s_wtot[warp] = wtot;
     __syncthreads();
@@ -98,7 +95,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_compact(Op op, uint64_t* tile_sta
 #pragma unroll
     for (uint32_t k = 0; k < C_ROWS; k++) {
       uint32_t i = base + k * 32 + lane;
-      if ((bal[k] >> lane) & 1u) op.emit(off + __popc(bal[k] & lanemask_lt()), item[k], i);
+      if ((bal[k] >> lane) & 1u) op.emit(off + __popc(bal[k] & lanemask_lt()), item[k], i, aux[k]);
       off += __popc(bal[k]);
     }
     op.tile_epilogue();
@@ -106,6 +103,17 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_compact(Op op, uint64_t* tile_sta
 }
 
 // ---- K3: PCI classify ---------------------------------------------------------------------------
+// record = {addr, vendor | device<<16, iommu_group, driver | flags<<8 | numa<<16}
+// device_plugin.go:203-238: any of the vendor/driver/iommu/device read errors drops the entry,
+// vendor must be "10de" (:209), driver must be in supportedVfioDrivers (:217, :75-78)
+__device__ __forceinline__ bool pci_record_alive(const uint4& r) {
+  uint32_t vendor = r.y & 0xffffu;
+  uint32_t driver = r.w & 0xffu;
+  uint32_t flags = (r.w >> 8) & 0xffu;
+  const uint32_t drop = KVG_PF_VENDOR_ERR | KVG_PF_DRIVER_ERR | KVG_PF_IOMMU_ERR | KVG_PF_DEVICE_ERR;
+  return vendor == 0x10deu && (flags & drop) == 0 &&
+         (driver == KVG_DRV_VFIO_PCI || driver == KVG_DRV_NVGRACE);
+}
 struct PciClassifyOp {
   using Item = uint4;
   const uint4* recs;
@@ -116,7 +124,17 @@ struct PciClassifyOp {
   uint32_t cap_mask, cap_shift;
   const PciIdsInfo* info;
   uint32_t local_max_group, local_max_dev;  // per-thread running maxima (registers)
+  uint32_t v_off, sec_end;                  // section bounds, read once per thread
 
+  __device__ __forceinline__ void begin() {
+    v_off = info ? info->v_off : P_NONE;
+    sec_end = info ? info->sec_end : 0;
+  }
+  // the name join: hash probe (vendor 10de, device) -> line offset -> pool slot
+  __device__ __forceinline__ uint32_t prepare(const Item& r) const {
+    uint32_t off = table_probe(table, cap_mask, cap_shift, (0x10deu << 16) | (r.y >> 16));
+    return (off != P_NONE && v_off != P_NONE && off > v_off && off < sec_end) ? off - v_off : P_NONE;
+  }
   __device__ __forceinline__ uint32_t count() const { return n; }
   __device__ __forceinline__ Item load(uint32_t i, bool ok) const {
     return ok ? ld_stream(recs + i) : make_uint4(0, 0, 0, 0xff00u);
@@ -124,15 +142,8 @@ struct PciClassifyOp {
   // record = {addr, vendor | device<<16, iommu_group, driver | flags<<8 | numa<<16}
   // device_plugin.go:203-238: any of vendor/driver/iommu/device read errors drops the entry,
   // vendor must be "10de" (:209), driver in supportedVfioDrivers (:217, :75-78)
-  __device__ __forceinline__ bool pred(const Item& r, uint32_t) const {
-    uint32_t vendor = r.y & 0xffffu;
-    uint32_t driver = r.w & 0xffu;
-    uint32_t flags = (r.w >> 8) & 0xffu;
-    const uint32_t drop = KVG_PF_VENDOR_ERR | KVG_PF_DRIVER_ERR | KVG_PF_IOMMU_ERR | KVG_PF_DEVICE_ERR;
-    return vendor == 0x10deu && (flags & drop) == 0 &&
-           (driver == KVG_DRV_VFIO_PCI || driver == KVG_DRV_NVGRACE);
-  }
-  __device__ __forceinline__ void emit(uint32_t pos, const Item& r, uint32_t) {
+  __device__ __forceinline__ bool pred(const Item& r, uint32_t) const { return pci_record_alive(r); }
+  __device__ __forceinline__ void emit(uint32_t pos, const Item& r, uint32_t, uint32_t name_slot) {
     uint32_t device = r.y >> 16;
     uint32_t flags = (r.w >> 8) & 0xffu;
     int32_t numa = (int32_t)r.w >> 16;  // sign-extended int16
@@ -141,7 +152,7 @@ struct PciClassifyOp {
     s.x = r.x;
     s.y = r.z;
     s.z = device | ((uint32_t)numa << 16);
-    s.w = probe_name_slot(table, cap_mask, cap_shift, info, device);
+    s.w = name_slot;
     st_stream(reinterpret_cast<uint4*>(out) + pos, s);
     local_max_group = max(local_max_group, r.z);
     local_max_dev = max(local_max_dev, device);
@@ -172,6 +183,8 @@ struct MdevClassifyOp {
   uint32_t n_types;
   uint32_t local_max_parent, local_max_type;
 
+  __device__ __forceinline__ void begin() {}
+  __device__ __forceinline__ uint32_t prepare(const Item& r) const { return type_canon[r.hi.y & 0xffffu]; }
   __device__ __forceinline__ uint32_t count() const { return n; }
   __device__ __forceinline__ Item load(uint32_t i, bool ok) const {
     Item it;
@@ -190,12 +203,10 @@ struct MdevClassifyOp {
     uint32_t type_idx = r.hi.y & 0xffffu;
     return (flags & (KVG_MF_TYPE_ERR | KVG_MF_PARENT_ERR)) == 0 && type_idx < n_types;
   }
-  __device__ __forceinline__ void emit(uint32_t pos, const Item& r, uint32_t i) {
+  __device__ __forceinline__ void emit(uint32_t pos, const Item& r, uint32_t i, uint32_t canon) {
     uint32_t flags = (r.hi.y >> 16) & 0xffu;
-    uint32_t type_idx = r.hi.y & 0xffffu;
     int32_t numa = (int32_t)(int16_t)(r.hi.z & 0xffffu);
     if ((flags & KVG_MF_NUMA_ERR) || numa < 0) numa = 0;  // :281-284, :316-318
-    uint32_t canon = type_canon[type_idx];
     uint4 hi;
     hi.x = r.hi.x;
     hi.y = canon | ((uint32_t)numa << 16);
@@ -218,33 +229,6 @@ struct MdevClassifyOp {
   __device__ __forceinline__ void finish(uint32_t total) { ctrl->n_surv = total; }
 };
 
-// ---- segment heads of a sorted key array --------------------------------------------------------
-struct HeadsOp {
-  using Item = uint2;  // {key[i], key[i-1]}
-  const uint32_t* keys;
-  const uint32_t* n_ptr;  // device-side element count
-  uint32_t* seg_key;
-  uint32_t* seg_off;      // [segments + 1]
-  uint32_t* n_seg_out;
-  __device__ __forceinline__ uint32_t count() const { return *n_ptr; }
-  __device__ __forceinline__ Item load(uint32_t i, bool ok) const {
-    if (!ok) return make_uint2(0, 0);
-    return make_uint2(keys[i], i ? keys[i - 1] : 0);
-  }
-  __device__ __forceinline__ bool pred(const Item& v, uint32_t i) const {
-    return i == 0 || v.x != v.y;
-  }
-  __device__ __forceinline__ void emit(uint32_t pos, const Item& v, uint32_t i) {
-    seg_key[pos] = v.x;
-    seg_off[pos] = i;
-  }
-  __device__ __forceinline__ void tile_epilogue() {}
-  __device__ __forceinline__ void finish(uint32_t total) {
-    *n_seg_out = total;
-    seg_off[total] = *n_ptr;
-  }
-};
-
 // ---- K6: health diff ----------------------------------------------------------------------------
 struct HealthOp {
   using Item = uint4;
@@ -254,12 +238,13 @@ struct HealthOp {
   uint32_t* changed;
   ScanCtrl* ctrl;
   uint32_t local_alive;
+  __device__ __forceinline__ void begin() {}
+  __device__ __forceinline__ uint32_t prepare(const Item&) const { return 0; }
   __device__ __forceinline__ uint32_t count() const { return n; }
   __device__ __forceinline__ Item load(uint32_t i, bool ok) const {
     if (!ok) return make_uint4(0, 0, 0, 0);
     uint4 r = ld_stream(recs + i);
-    PciClassifyOp c{};
-    uint32_t alive = c.pred(r, i) ? 1u : 0u;
+    uint32_t alive = pci_record_alive(r) ? 1u : 0u;
     r.x = alive | ((uint32_t)alive_prev[i] << 1);
     return r;
   }
@@ -267,7 +252,7 @@ struct HealthOp {
     local_alive += r.x & 1u;
     return (r.x & 1u) != (r.x >> 1);
   }
-  __device__ __forceinline__ void emit(uint32_t pos, const Item& r, uint32_t i) {
+  __device__ __forceinline__ void emit(uint32_t pos, const Item& r, uint32_t i, uint32_t) {
     changed[pos] = (i << 1) | (r.x & 1u);
     alive_prev[i] = (uint8_t)(r.x & 1u);
   }

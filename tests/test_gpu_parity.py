@@ -33,9 +33,12 @@ def pciids():
 
 
 @pytest.fixture(scope="module")
-def loaded(ctx, pciids):
-    ctx.pciids_load(pciids)
-    return ctx
+def loaded(kv, pciids):
+    """a context that keeps the shipped pci.ids table (scratch loads go to `ctx`)"""
+    c = kv.Context(0)
+    c.pciids_load(pciids)
+    yield c
+    c.close()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -55,6 +58,7 @@ def test_ginkgo_get_device_name_kats(ctx):
 
 
 def test_full_pciids_table_matches_golden(loaded, pciids):
+    assert loaded.name_lookup("1b38") == "GP102GL_TESLA_P40"
     d = util.pciids_names()
     info = loaded.pciids_info()
     assert info["vendor_off"] == pciids.index(b"\n10de  NVIDIA") + 1
