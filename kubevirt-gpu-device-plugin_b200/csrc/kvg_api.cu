@@ -261,6 +261,25 @@ static void* pinned_alloc(kvg_ctx* ctx, size_t size) {
 }
 static inline uint8_t* pinned_payload(void* blk) { return (uint8_t*)blk + 64; }
 
+// grid for the TMA-pipelined classify kernels: co-resident, capped by the tile count
+template <class Op, int ROWS, int STAGES>
+static int classify_grid(kvg_ctx* ctx, size_t n_items, size_t* smem_out) {
+  static int occ = 0;
+  const size_t smem = (size_t)STAGES * KVG_BLOCK * ROWS * Op::REC_BYTES;
+  if (!occ) {
+    cudaFuncSetAttribute(k_classify_tma<Op, ROWS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_classify_tma<Op, ROWS, STAGES>, KVG_BLOCK, smem);
+    if (occ < 1) occ = 1;
+  }
+  *smem_out = smem;
+  size_t tiles = (n_items + (size_t)KVG_BLOCK * ROWS - 1) / ((size_t)KVG_BLOCK * ROWS);
+  size_t g = (size_t)ctx->sm_count * (size_t)occ;
+  if (tiles < g) g = tiles;
+  return g < 1 ? 1 : (int)g;
+}
+constexpr int PCI_ROWS = 4, PCI_STAGES = 4;    // 16 KiB stages, 64 KiB ring -> 3 CTAs / SM
+constexpr int MDEV_ROWS = 2, MDEV_STAGES = 4;  // 16 KiB stages
+
 extern "C" {
 
 int kvg_abi_version(void) { return KVG_ABI_VERSION; }
@@ -288,10 +307,9 @@ int kvg_ctx_create(int cuda_device, kvg_ctx** out) {
     return KVG_ECUDA;
   }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, cuda_device);
-  cudaFuncSetAttribute(k_pciids_parse, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       (int)(P_STAGES * P_STAGE));
+  cudaFuncSetAttribute(k_pciids_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM);
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pciids_parse, KVG_BLOCK, P_STAGES * P_STAGE);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pciids_parse, KVG_BLOCK, P_SMEM);
   if (occ < 1) occ = 1;
   ctx->parse_grid = ctx->sm_count * occ;
   if (ensure(ctx, ctx->ctrl, 1) != KVG_OK || cudaMallocHost((void**)&ctx->h_ctrl, sizeof(ScanCtrl)) != cudaSuccess) {
@@ -438,7 +456,7 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
   CK(cudaMemset2DAsync(ctx->info.p, sizeof(PciIdsInfo), 0xff, sizeof(uint32_t), n_files, ctx->stream));
   int grid = ctx->parse_grid;
   if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
-  LAUNCH("pciids_parse", k_pciids_parse, grid, KVG_BLOCK, P_STAGES * P_STAGE, A);
+  LAUNCH("pciids_parse", k_pciids_parse, grid, KVG_BLOCK, P_SMEM, A);
   LAUNCH("pciids_finalize", k_pciids_finalize, n_files, KVG_BLOCK, 0, A);
   return check_launch(ctx, "pciids parse");
 }
@@ -822,7 +840,7 @@ static int enqueue_pci_orderings(kvg_ctx* ctx, size_t surv_cap) {
 }
 
 static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d_out) {
-  ENSURE(ctx->classify_state, (n + C_TILE - 1) / C_TILE + 1);
+  ENSURE(ctx->classify_state, (n + (size_t)KVG_BLOCK * PCI_ROWS - 1) / ((size_t)KVG_BLOCK * PCI_ROWS) + 1);
   PciClassifyOp op;
   op.recs = (const uint4*)d_recs;
   op.n = (uint32_t)n;
@@ -834,7 +852,9 @@ static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d
   op.info = ctx->info.p;
   op.local_max_group = 0;
   op.local_max_dev = 0;
-  LAUNCH("classify_compact", k_compact<PciClassifyOp>, compact_grid<PciClassifyOp>(ctx, n), KVG_BLOCK, 0, op,
+  size_t smem = 0;
+  int grid = classify_grid<PciClassifyOp, PCI_ROWS, PCI_STAGES>(ctx, n, &smem);
+  LAUNCH("classify_compact", (k_classify_tma<PciClassifyOp, PCI_ROWS, PCI_STAGES>), grid, KVG_BLOCK, smem, op,
          ctx->classify_state.p, ++ctx->epoch);
   return check_launch(ctx, "classify");
 }
@@ -1110,7 +1130,7 @@ int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type
     if (rc) return rc;
   }
   ENSURE(ctx->surv, 2 * (n + 1));
-  ENSURE(ctx->classify_state, (n + C_TILE - 1) / C_TILE + 1);
+  ENSURE(ctx->classify_state, (n + (size_t)KVG_BLOCK * MDEV_ROWS - 1) / ((size_t)KVG_BLOCK * MDEV_ROWS) + 1);
   CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
   MdevClassifyOp op;
   op.recs = (const uint4*)d_recs;
@@ -1121,7 +1141,9 @@ int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type
   op.n_types = nt;
   op.local_max_parent = 0;
   op.local_max_type = 0;
-  LAUNCH("mdev_classify_compact", k_compact<MdevClassifyOp>, compact_grid<MdevClassifyOp>(ctx, n), KVG_BLOCK, 0, op,
+  size_t msmem = 0;
+  int mgrid = classify_grid<MdevClassifyOp, MDEV_ROWS, MDEV_STAGES>(ctx, n, &msmem);
+  LAUNCH("mdev_classify_compact", (k_classify_tma<MdevClassifyOp, MDEV_ROWS, MDEV_STAGES>), mgrid, KVG_BLOCK, msmem, op,
          ctx->classify_state.p, ++ctx->epoch);
   rc = check_launch(ctx, "mdev classify");
   if (rc) return rc;

@@ -14,16 +14,20 @@
 
 namespace kvg {
 
-constexpr uint32_t P_TILE = 16384;            // text bytes owned by one tile
+constexpr uint32_t P_TILE = 8192;             // text bytes owned by one tile
 constexpr uint32_t P_HALO = 16;               // bytes after the tile needed to classify its last line
 constexpr uint32_t P_STAGE = P_TILE + P_HALO; // one TMA transaction
-constexpr uint32_t P_STAGES = 3;
-constexpr uint32_t P_SPAN = P_TILE / KVG_BLOCK;  // 64 text bytes per thread
+constexpr uint32_t P_STAGES = 4;
+constexpr uint32_t P_SPAN = P_TILE / KVG_BLOCK;  // 32 text bytes per thread
+constexpr uint32_t P_WSPAN = 32 * P_SPAN;        // 1 KiB of text per warp
+constexpr uint32_t P_WCAP = P_WSPAN + 8;         // worst case: every byte of the warp span is '\n'
+constexpr uint32_t P_SMEM = P_STAGES * P_STAGE + 2 * KVG_WARPS * P_WCAP * 2;  // ring + line lists
 constexpr uint32_t P_NONE = 0xffffffffu;
 constexpr uint64_t P_EMPTY = 0xffffffffffffffffull;
 constexpr uint32_t SCAN_TOKEN_MAX = 65536;  // bufio.MaxScanTokenSize
 
-static_assert(P_SPAN == 64, "one 64-bit newline mask per thread");
+static_assert(P_SPAN == 32, "one 32-bit newline mask per thread");
+static_assert(P_TILE + 1 < (1u << 15), "tile-relative line start + 1 must fit 15 bits");
 
 // per-image facts; v_off is filled by K1 (atomicMin), the rest by k_pciids_finalize
 struct PciIdsInfo {
@@ -118,146 +122,222 @@ __device__ __forceinline__ uint32_t table_probe(const uint64_t* __restrict__ tab
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1.  Persistent co-resident CTAs (grid <= occupancy x SMs), tile = blockIdx + k*gridDim: a
-// look-back predecessor always belongs to a resident CTA that reaches it no later than we reach
-// ours, and consecutive tiles sit in different CTAs so their chains overlap.  3-stage TMA ring.  A tile owns the lines that START in (a, a+TILE], plus the
-// line at offset 0 for the first tile of an image; the 16 halo bytes let it classify a line that
-// starts on its last byte.
+// K1.  Persistent co-resident CTAs (grid <= occupancy x SMs), tile = blockIdx + k*gridDim, 4-stage
+// TMA ring of 8 KiB text tiles.  A tile owns the lines that START in (a, a+TILE] (plus offset 0 for
+// the first tile of an image); 16 halo bytes let it classify a line starting on its last byte.
+//
+// Two phases per tile, phase 2 running ONE ITERATION LATE so the cross-tile vendor context
+// (look-back) is already published when it is needed:
+//   phase 1(i)  per thread: 32-byte span -> 32-bit newline mask -> line starts appended to the
+//               WARP's list (shuffle prefix); warp-dense pass over the list: first byte tells
+//               header-type lines (not '\t', not '#'), their 4-hex vendor is parsed, the warp's
+//               last header is reduced.  Warp 0 then scans the 8 warp summaries, publishes the
+//               tile's context state and the tile summaries used by k_pciids_finalize.
+//   phase 2(i-1) warp-dense over the saved list: 32 lines per round with all lanes converged —
+//               classify, intra-round header scan, and ONE batch of hash inserts per round.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_parse(ParseArgs A) {
   extern __shared__ __align__(128) uint8_t p_smem[];
-  uint8_t* stage_buf = p_smem;  // P_STAGES * P_STAGE
+  uint8_t* stage_buf = p_smem;                                                      // ring
+  uint16_t* lists = reinterpret_cast<uint16_t*>(p_smem + P_STAGES * P_STAGE);       // [2][8][P_WCAP]
   __shared__ __align__(8) uint64_t full_bar[P_STAGES];
-  __shared__ uint32_t s_scratch[KVG_WARPS + 1];
+  __shared__ uint32_t s_wcnt[2][KVG_WARPS], s_whdr[2][KVG_WARPS], s_wctx[2][KVG_WARPS];
   __shared__ uint32_t s_carry;
   __shared__ uint32_t s_first_hdr, s_first_nl, s_last_nl;
 
-  const uint32_t tid = threadIdx.x;
+  const uint32_t tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+  const uint32_t G = gridDim.x, b = blockIdx.x;
+  if (b >= A.n_tiles) return;
+  const uint32_t my_count = (A.n_tiles - b + G - 1) / G;
 
-  auto issue = [&](uint32_t stage, uint32_t it) {  // thread 0 only
-    uint32_t t = blockIdx.x + it * gridDim.x;
-    if (t < A.n_tiles) {
-      uint32_t f = t / A.tiles_per_file, j = t - f * A.tiles_per_file;
-      const uint8_t* src = A.text + (uint64_t)f * A.stride + (uint64_t)j * P_TILE;
-      mbar_arrive_expect_tx(&full_bar[stage], P_STAGE);
-      tma_load_1d(stage_buf + stage * P_STAGE, src, P_STAGE, &full_bar[stage]);
-    }
+  auto issue = [&](uint32_t i) {  // thread 0 only
+    if (i >= my_count) return;
+    uint32_t t = b + i * G;
+    uint32_t f = t / A.tiles_per_file, j = t - f * A.tiles_per_file;
+    const uint8_t* src = A.text + (uint64_t)f * A.stride + (uint64_t)j * P_TILE;
+    uint32_t st = i % P_STAGES;
+    mbar_arrive_expect_tx(&full_bar[st], P_STAGE);
+    tma_load_1d(stage_buf + st * P_STAGE, src, P_STAGE, &full_bar[st]);
   };
 
   if (tid == 0) {
     for (uint32_t s = 0; s < P_STAGES; s++) mbar_init(&full_bar[s], 1);
     mbar_fence_init();
+    s_first_hdr = P_NONE;
+    s_first_nl = P_NONE;
+    s_last_nl = 0;
   }
   __syncthreads();
   if (tid == 0)
-    for (uint32_t s = 0; s < P_STAGES; s++) issue(s, s);
+    for (uint32_t s = 0; s < P_STAGES; s++) issue(s);
 
-  uint32_t n_new = 0, n_lines = 0;  // per-thread tallies, flushed per tile
+  uint32_t n_new = 0;                   // per-thread tally of first-time inserts
+  bool prev_defines = false, prev_first = false;  // warp 0: facts about tile i-1
 
-  for (uint32_t it = 0;; ++it) {
-    const uint32_t stage = it % P_STAGES;
-    const uint32_t parity = (it / P_STAGES) & 1;
-    const uint32_t tile = blockIdx.x + it * gridDim.x;
-    if (tile >= A.n_tiles) break;
-    const uint32_t f = tile / A.tiles_per_file, j = tile - f * A.tiles_per_file;
-    const uint32_t a = j * P_TILE;  // file offset of the tile
-    const uint8_t* sm = stage_buf + stage * P_STAGE;
-    uint64_t* table = A.tables + (uint64_t)f * (A.cap_mask + 1);
-
-    if (tid == 0) {
-      s_first_hdr = P_NONE;
-      s_first_nl = P_NONE;
-      s_last_nl = 0;
+  for (uint32_t i = 0; i <= my_count; ++i) {
+    // ---- warp 0: prefetch the look-back window of tile i-1
+    const uint32_t ptile = b + (i - 1) * G;  // meaningful for i > 0
+    uint64_t lbw = 0;
+    if (i > 0 && warp == 0 && !prev_first) {
+      int idx = (int)ptile - 1 - (int)lane;
+      lbw = idx >= 0 ? ld_relaxed_u64(&A.tile_state[idx]) : lb_pack(A.epoch, LB_INCLUSIVE, 0);
     }
-    mbar_wait(&full_bar[stage], parity);
 
-    // ---- newline mask of this thread's 64-byte span (bank-conflict-free rotated chunk order)
-    const uint32_t sp = tid * P_SPAN;
-    uint64_t mask = 0;
-#pragma unroll
-    for (uint32_t k = 0; k < 4; k++) {
-      uint32_t c = (k + (tid >> 1)) & 3;
-      uint4 v = *reinterpret_cast<const uint4*>(sm + sp + c * 16);
-      mask |= (uint64_t)nl_mask16(v) << (16 * c);
-    }
-    // newlines at or beyond EOF are padding, not line terminators of real lines
-    if (a + sp + P_SPAN > A.len) {
-      uint32_t keep = A.len > a + sp ? A.len - (a + sp) : 0;  // bytes of the span inside the file
-      mask = keep >= 64 ? mask : (mask & ((1ull << keep) - 1));
-    }
-    __syncthreads();  // s_first_* initialised
+    // ---- phase 1 of tile i
+    if (i < my_count) {
+      const uint32_t tile = b + i * G;
+      const uint32_t f = tile / A.tiles_per_file, j = tile - f * A.tiles_per_file;
+      const uint32_t a = j * P_TILE;
+      const uint32_t st = i % P_STAGES;
+      mbar_wait(&full_bar[st], (i / P_STAGES) & 1);
+      const uint8_t* sm = stage_buf + st * P_STAGE;
+      uint16_t* L = lists + ((i & 1) * KVG_WARPS + warp) * P_WCAP;
 
-    // ---- pass A: header-type lines (first byte neither '\t' nor '#') -> context for later lines
-    uint32_t last_hdr = 0;  // ((p+1)<<17) | valid<<16 | vendor, 0 = none in this span
-    {
-      uint32_t my_first_hdr = P_NONE;
-      auto visit = [&](uint32_t p) {
-        if (a + p >= A.len) return;  // a line must start before EOF
+      const uint32_t sp = tid * P_SPAN;
+      uint32_t c0 = (tid >> 2) & 1;  // rotate the two 16-byte chunks: conflict-free LDS.128
+      uint4 va = *reinterpret_cast<const uint4*>(sm + sp + c0 * 16);
+      uint4 vb = *reinterpret_cast<const uint4*>(sm + sp + (c0 ^ 1) * 16);
+      uint32_t ma = nl_mask16(va), mb = nl_mask16(vb);
+      uint32_t mask = c0 ? (mb | (ma << 16)) : (ma | (mb << 16));  // bit q: byte sp+q is '\n'
+      // bytes at or beyond EOF are padding
+      uint32_t pos0 = a + sp;
+      uint32_t keep = A.len > pos0 ? A.len - pos0 : 0;  // span bytes inside the file
+      if (keep < 32) mask &= keep ? ((1u << keep) - 1) : 0u;
+      // a newline that is the last byte of the file starts no line
+      uint32_t ls_mask = mask;
+      if (keep >= 1 && keep <= 32) ls_mask &= ~(1u << (keep - 1));
+      {
+        uint32_t l2 = warp_sum((uint32_t)__popc(mask));
+        if (lane == 0 && l2) atomicAdd(&A.info[f].n_lines, l2);
+      }
+      uint32_t fn = mask ? pos0 + (uint32_t)__ffs(mask) - 1 : P_NONE;
+      uint32_t lnl = mask ? pos0 + 31 - (uint32_t)__clz(mask) : 0;
+      fn = warp_min(fn);
+      lnl = warp_max(lnl);
+
+      const uint32_t extra = (j == 0 && tid == 0 && A.len > 0) ? 1u : 0u;  // the line at offset 0
+      uint32_t cnt = (uint32_t)__popc(ls_mask) + extra;
+      uint32_t incl = warp_incl_sum(cnt);
+      uint32_t o = incl - cnt;
+      const uint32_t wcnt = __shfl_sync(KVG_FULL, incl, 31);
+      if (extra) L[o++] = 0;
+      for (uint32_t mm = ls_mask; mm; mm &= mm - 1) L[o++] = (uint16_t)(sp + (uint32_t)__ffs(mm));
+      __syncwarp();
+
+      uint32_t my_last = 0, my_first = P_NONE;
+      for (uint32_t e = lane; e < wcnt; e += 32) {
+        uint32_t p = L[e];
         uint32_t b0 = sm[p];
         if (b0 != '\t' && b0 != '#') {
           uint32_t hv = parse_hex4(sm + p);
-          last_hdr = ((p + 1) << 17) | hv;
-          my_first_hdr = min(my_first_hdr, a + p);
+          my_last = ((p + 1) << 17) | hv;  // e ascends per lane, so the last assignment wins
+          my_first = min(my_first, a + p);
           if (hv == (0x10000u | 0x10deu)) atomicMin(&A.info[f].v_off, a + p);
         }
-      };
-      if (j == 0 && tid == 0) visit(0);
-      for (uint64_t mm = mask; mm; mm &= mm - 1) visit(sp + (uint32_t)__ffsll((long long)mm));
-      if (my_first_hdr != P_NONE) atomicMin(&s_first_hdr, my_first_hdr);
-      if (mask) {
-        atomicMin(&s_first_nl, a + sp + (uint32_t)__ffsll((long long)mask) - 1);
-        atomicMax(&s_last_nl, a + sp + 63 - (uint32_t)__clzll((long long)mask));
-        n_lines += (uint32_t)__popcll(mask);
       }
-    }
-    uint32_t tile_hdr;
-    uint32_t ctx = block_excl_max(last_hdr, s_scratch, &tile_hdr);  // two __syncthreads inside
-
-    // ---- vendor context carried into the tile
-    if (warp_id() == 0) {
-      uint32_t carry = lookback_last(A.tile_state, tile, j == 0, tile_hdr != 0, tile_hdr & 0x1ffffu,
-                                     A.epoch);
-      if (lane_id() == 0) {
-        s_carry = carry;
-        A.tile_first_hdr[tile] = s_first_hdr;
-        A.tile_first_nl[tile] = s_first_nl;
-        A.tile_last_nl[tile] = s_last_nl;
-      }
-    }
-    __syncthreads();
-    ctx = ctx ? (ctx & 0x1ffffu) : s_carry;
-
-    // ---- pass B: device lines "\t" + 4 lower-hex under a valid vendor -> hash insert
-    {
-      auto visit = [&](uint32_t p) {
-        if (a + p >= A.len) return;
-        uint32_t b0 = sm[p];
-        if (b0 == '#') return;
-        if (b0 != '\t') {
-          ctx = parse_hex4(sm + p);
-          return;
+      my_last = warp_max(my_last);
+      my_first = warp_min(my_first);
+      if (lane == 0) {
+        s_wcnt[i & 1][warp] = wcnt;
+        s_whdr[i & 1][warp] = my_last;
+        if (my_first != P_NONE) atomicMin(&s_first_hdr, my_first);
+        if (fn != P_NONE) {
+          atomicMin(&s_first_nl, fn);
+          atomicMax(&s_last_nl, lnl);
         }
-        uint32_t dv = parse_hex4(sm + p + 1);
-        if ((dv & ctx) & 0x10000u)
-          n_new += table_insert(table, A.cap_mask, A.cap_shift, ((ctx & 0xffffu) << 16) | (dv & 0xffffu),
-                                a + p, &A.info[f].overflow);
-      };
-      if (j == 0 && tid == 0) visit(0);
-      for (uint64_t mm = mask; mm; mm &= mm - 1) visit(sp + (uint32_t)__ffsll((long long)mm));
-    }
-
-    // ---- flush tallies once per tile per warp
-    {
-      uint32_t e = warp_sum(n_new), l = warp_sum(n_lines);
-      if (lane_id() == 0) {
-        if (e) atomicAdd(&A.info[f].n_entries, e);
-        if (l) atomicAdd(&A.info[f].n_lines, l);
       }
-      n_new = 0;
-      n_lines = 0;
     }
-    __syncthreads();  // everyone is done with this stage
-    if (tid == 0) issue(stage, it + P_STAGES);
+    __syncthreads();  // A: warp summaries of tile i visible; phase 2 of tile i-2 finished
+    if (tid == 0 && i >= 2) issue(i - 2 + P_STAGES);
+
+    if (warp == 0) {
+      bool defines = false, first = false;
+      if (i < my_count) {
+        const uint32_t tile = b + i * G;
+        const uint32_t j = tile % A.tiles_per_file;
+        uint32_t h = lane < KVG_WARPS ? s_whdr[i & 1][lane] : 0;
+        uint32_t hi = warp_incl_max(h);
+        uint32_t he = __shfl_up_sync(KVG_FULL, hi, 1);
+        if (lane == 0) he = 0;
+        if (lane < KVG_WARPS) s_wctx[i & 1][lane] = he;
+        uint32_t tile_hdr = __shfl_sync(KVG_FULL, hi, KVG_WARPS - 1);
+        defines = tile_hdr != 0;
+        first = j == 0;
+        if (lane == 0) {
+          uint32_t status = (defines || first) ? LB_INCLUSIVE : LB_AGGREGATE;
+          st_relaxed_u64(&A.tile_state[tile], lb_pack(A.epoch, status, tile_hdr & 0x1ffffu));
+          A.tile_first_hdr[tile] = s_first_hdr;
+          A.tile_first_nl[tile] = s_first_nl;
+          A.tile_last_nl[tile] = s_last_nl;
+          s_first_hdr = P_NONE;
+          s_first_nl = P_NONE;
+          s_last_nl = 0;
+        }
+      }
+      if (i > 0) {  // vendor context carried into tile i-1
+        uint32_t carry = 0;
+        if (!prev_first) {
+          int look = (int)ptile - 1;
+          uint64_t w = lbw;
+          for (;;) {
+            uint32_t st = lb_status(w, A.epoch);
+            uint32_t incl_mask = __ballot_sync(KVG_FULL, st == LB_INCLUSIVE);
+            uint32_t inv_mask = __ballot_sync(KVG_FULL, st == LB_INVALID);
+            uint32_t fi = incl_mask ? (uint32_t)__ffs(incl_mask) - 1 : 32;
+            uint32_t need = fi >= 31 ? KVG_FULL : ((2u << fi) - 1);
+            if (!(inv_mask & need)) {
+              if (fi < 32) {
+                carry = __shfl_sync(KVG_FULL, (uint32_t)w, fi);
+                break;
+              }
+              look -= 32;
+            }
+            int idx = look - (int)lane;
+            w = idx >= 0 ? ld_relaxed_u64(&A.tile_state[idx]) : lb_pack(A.epoch, LB_INCLUSIVE, 0);
+          }
+          if (!prev_defines && lane == 0)  // pass-through tile: shorten later look-backs
+            st_relaxed_u64(&A.tile_state[ptile], lb_pack(A.epoch, LB_INCLUSIVE, carry));
+        }
+        if (lane == 0) s_carry = carry;
+      }
+      prev_defines = defines;
+      prev_first = first;
+    }
+    __syncthreads();  // B: s_wctx of tile i and the carry of tile i-1 visible
+
+    // ---- phase 2 of tile i-1: device lines "\t" + 4 lower-hex under a valid vendor -> hash
+    if (i > 0) {
+      const uint32_t f = ptile / A.tiles_per_file, j = ptile - f * A.tiles_per_file;
+      const uint32_t a = j * P_TILE;
+      const uint8_t* sm = stage_buf + ((i - 1) % P_STAGES) * P_STAGE;
+      const uint16_t* L = lists + (((i - 1) & 1) * KVG_WARPS + warp) * P_WCAP;
+      uint64_t* table = A.tables + (uint64_t)f * (A.cap_mask + 1);
+      const uint32_t cnt = s_wcnt[(i - 1) & 1][warp];
+      const uint32_t c0 = s_wctx[(i - 1) & 1][warp];
+      uint32_t running = c0 ? (c0 & 0x1ffffu) : s_carry;  // valid<<16 | vendor
+      for (uint32_t base = 0; base < cnt; base += 32) {
+        const uint32_t e = base + lane;
+        uint32_t hval = 0, dv = 0, p = 0;
+        if (e < cnt) {
+          p = L[e];
+          uint32_t b0 = sm[p];
+          if (b0 == '\t')
+            dv = parse_hex4(sm + p + 1);
+          else if (b0 != '#')
+            hval = ((e + 1) << 17) | parse_hex4(sm + p);
+        }
+        uint32_t sc = warp_incl_max(hval);  // last header at or before this line, this round
+        uint32_t ctx = sc ? (sc & 0x1ffffu) : running;
+        if ((dv & ctx) & 0x10000u)
+          n_new += table_insert(table, A.cap_mask, A.cap_shift,
+                                ((ctx & 0xffffu) << 16) | (dv & 0xffffu), a + p, &A.info[f].overflow);
+        uint32_t last = __shfl_sync(KVG_FULL, sc, 31);
+        if (last) running = last & 0x1ffffu;
+      }
+      uint32_t e2 = warp_sum(n_new);
+      if (lane == 0 && e2) atomicAdd(&A.info[f].n_entries, e2);
+      n_new = 0;
+    }
   }
 }
 

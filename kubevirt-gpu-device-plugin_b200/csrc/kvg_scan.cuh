@@ -102,6 +102,156 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_compact(Op op, uint64_t* tile_sta
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3/K5 hot form: the same stable compaction for fixed-size RECORDS, software-pipelined so HBM
+// loads never stop:
+//   * records arrive through a STAGES-deep ring of TMA bulk copies (cp.async.bulk -> UBLKCP), so
+//     bytes stay in flight while the CTA is in its barrier / look-back phases;
+//   * the look-back + write-out of tile i-1 run one iteration LATE, behind the ballots of tile i:
+//     by then every predecessor published its count, so the look-back resolves without spinning
+//     (its state words are even prefetched before the ballots).
+// Iteration i:  [prefetch look-back words of tile i-1] -> wait TMA(i) -> LDS, predicate, ballots,
+//   probes -> sync -> warp 0: publish count(i), resolve base(i-1) -> sync -> emit tile i-1.
+// ------------------------------------------------------------------------------------------------
+template <class Op, int ROWS, int STAGES>
+__global__ void __launch_bounds__(KVG_BLOCK) k_classify_tma(Op op, uint64_t* tile_state, uint32_t epoch) {
+  constexpr uint32_t TILE = KVG_BLOCK * ROWS;
+  constexpr uint32_t RB = Op::REC_BYTES;
+  constexpr uint32_t STAGE_BYTES = TILE * RB;
+  constexpr uint32_t WARP_ITEMS = 32 * ROWS;
+  extern __shared__ __align__(128) uint8_t c_smem[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ uint32_t s_wtot[KVG_WARPS];
+  __shared__ uint32_t s_woff[2][KVG_WARPS];
+  __shared__ uint32_t s_base;
+
+  op.begin();
+  const uint32_t n = op.count();
+  const uint32_t n_tiles = (n + TILE - 1) / TILE;
+  const uint32_t lane = lane_id(), warp = warp_id(), tid = threadIdx.x;
+  const uint32_t G = gridDim.x, b = blockIdx.x;
+  if (n_tiles == 0) {
+    if (b == 0 && tid == 0) op.finish(0);
+    return;
+  }
+  if (b >= n_tiles) return;
+  const uint32_t my_count = (n_tiles - b + G - 1) / G;  // tiles b, b+G, ...
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(op.src());
+
+  auto issue = [&](uint32_t i) {  // thread 0: TMA for my i-th tile into stage i % STAGES
+    if (i >= my_count) return;
+    uint32_t tile = b + i * G;
+    uint32_t items = min(TILE, n - tile * TILE);
+    uint32_t st = i % STAGES;
+    mbar_arrive_expect_tx(&full_bar[st], items * RB);
+    tma_load_1d(c_smem + st * STAGE_BYTES, src + (size_t)tile * STAGE_BYTES, items * RB, &full_bar[st]);
+  };
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) mbar_init(&full_bar[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int s = 0; s < STAGES; s++) issue((uint32_t)s);
+
+  uint32_t prev_bal[ROWS], prev_aux[ROWS];
+  uint32_t prev_total = 0;  // warp 0 only
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) prev_bal[k] = prev_aux[k] = 0;
+
+  for (uint32_t i = 0; i <= my_count; ++i) {
+    // -- warp 0: prefetch the look-back window of tile i-1 (consumed after the ballots)
+    uint64_t lbw = 0;
+    const uint32_t ptile = b + (i - 1) * G;  // valid when i > 0
+    if (i > 0 && warp == 0 && ptile > 0) {
+      int idx = (int)ptile - 1 - (int)lane;
+      lbw = idx >= 0 ? ld_relaxed_u64(&tile_state[idx]) : lb_pack(epoch, LB_INCLUSIVE, 0);
+    }
+    uint32_t bal[ROWS], aux[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) bal[k] = aux[k] = 0;
+    if (i < my_count) {
+      const uint32_t tile = b + i * G;
+      const uint32_t st = i % STAGES;
+      mbar_wait(&full_bar[st], (i / STAGES) & 1);
+      const uint8_t* stage = c_smem + st * STAGE_BYTES;
+      uint32_t wtot = 0;
+#pragma unroll
+      for (int k = 0; k < ROWS; k++) {
+        uint32_t j = warp * WARP_ITEMS + k * 32 + lane;  // item index inside the tile
+        bool ok = tile * TILE + j < n;
+        typename Op::Item it = op.from_smem(stage + (size_t)j * RB);
+        bool p = ok && op.pred(it, tile * TILE + j);
+        bal[k] = __ballot_sync(KVG_FULL, p);
+        wtot += __popc(bal[k]);
+        aux[k] = p ? op.prepare(it) : 0u;
+      }
+      if (lane == 0) s_wtot[warp] = wtot;
+    }
+    __syncthreads();  // A: counts of tile i visible; everyone finished emitting tile i-2
+    if (tid == 0 && i >= 2) issue(i - 2 + STAGES);  // stage (i-2) % STAGES is free again
+    if (warp == 0) {
+      uint32_t my_total = 0;
+      if (i < my_count) {
+        const uint32_t tile = b + i * G;
+        uint32_t w = lane < KVG_WARPS ? s_wtot[lane] : 0;
+        uint32_t wi = warp_incl_sum(w);
+        if (lane < KVG_WARPS) s_woff[i & 1][lane] = wi - w;
+        my_total = __shfl_sync(KVG_FULL, wi, KVG_WARPS - 1);
+        if (lane == 0)
+          st_relaxed_u64(&tile_state[tile], lb_pack(epoch, tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE, my_total));
+      }
+      if (i > 0) {
+        uint32_t excl = 0;
+        if (ptile > 0) {
+          int look = (int)ptile - 1;
+          uint64_t w = lbw;
+          for (;;) {
+            uint32_t st = lb_status(w, epoch);
+            uint32_t incl_mask = __ballot_sync(KVG_FULL, st == LB_INCLUSIVE);
+            uint32_t inv_mask = __ballot_sync(KVG_FULL, st == LB_INVALID);
+            uint32_t first = incl_mask ? (uint32_t)__ffs(incl_mask) - 1 : 32;
+            uint32_t need = first >= 31 ? KVG_FULL : ((2u << first) - 1);
+            if (!(inv_mask & need)) {
+              excl += warp_sum(lane <= first ? (uint32_t)w : 0u);
+              if (first < 32) break;
+              look -= 32;
+            }
+            int idx = look - (int)lane;
+            w = idx >= 0 ? ld_relaxed_u64(&tile_state[idx]) : lb_pack(epoch, LB_INCLUSIVE, 0);
+          }
+          if (lane == 0) st_relaxed_u64(&tile_state[ptile], lb_pack(epoch, LB_INCLUSIVE, excl + prev_total));
+        }
+        if (lane == 0) {
+          s_base = excl;
+          if (ptile == n_tiles - 1) op.finish(excl + prev_total);
+        }
+      }
+      prev_total = my_total;
+    }
+    __syncthreads();  // B: base of tile i-1 visible
+    if (i > 0) {
+      const uint8_t* stage = c_smem + ((i - 1) % STAGES) * STAGE_BYTES;
+      uint32_t off = s_base + s_woff[(i - 1) & 1][warp];
+#pragma unroll
+      for (int k = 0; k < ROWS; k++) {
+        if ((prev_bal[k] >> lane) & 1u) {
+          uint32_t j = warp * WARP_ITEMS + k * 32 + lane;
+          typename Op::Item it = op.from_smem(stage + (size_t)j * RB);
+          op.emit(off + __popc(prev_bal[k] & lanemask_lt()), it, ptile * TILE + j, prev_aux[k]);
+        }
+        off += __popc(prev_bal[k]);
+      }
+      op.tile_epilogue();
+    }
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) {
+      prev_bal[k] = bal[k];
+      prev_aux[k] = aux[k];
+    }
+  }
+}
+
 // ---- K3: PCI classify ---------------------------------------------------------------------------
 // record = {addr, vendor | device<<16, iommu_group, driver | flags<<8 | numa<<16}
 // device_plugin.go:203-238: any of the vendor/driver/iommu/device read errors drops the entry,
@@ -116,6 +266,11 @@ __device__ __forceinline__ bool pci_record_alive(const uint4& r) {
 }
 struct PciClassifyOp {
   using Item = uint4;
+  static constexpr uint32_t REC_BYTES = 16;
+  __device__ __forceinline__ const void* src() const { return recs; }
+  __device__ __forceinline__ Item from_smem(const uint8_t* p) const {
+    return *reinterpret_cast<const uint4*>(p);
+  }
   const uint4* recs;
   uint32_t n;
   kvg_pci_surv* out;
@@ -175,6 +330,14 @@ struct MdevItem {
 };
 struct MdevClassifyOp {
   using Item = MdevItem;
+  static constexpr uint32_t REC_BYTES = 32;
+  __device__ __forceinline__ const void* src() const { return recs; }
+  __device__ __forceinline__ Item from_smem(const uint8_t* p) const {
+    Item it;
+    it.lo = *reinterpret_cast<const uint4*>(p);
+    it.hi = *reinterpret_cast<const uint4*>(p + 16);
+    return it;
+  }
   const uint4* recs;  // 2 x uint4 per record
   uint32_t n;
   uint4* out;

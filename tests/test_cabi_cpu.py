@@ -16,8 +16,9 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 30
     assert [s for s in syms if not hasattr(lib, s)] == []
     assert lib.kvg_abi_version() == 1
-    assert lib.kvg_text_pad(1) == 16384 + 16
-    assert lib.kvg_text_pad(16384) == 16384 + 16 and lib.kvg_text_pad(16385) == 2 * 16384 + 16
+    tile = lib.kvg_text_pad(1) - 16           # text is padded to whole TMA tiles + a 16-byte halo
+    assert tile % 16 == 0 and tile >= 4096
+    assert lib.kvg_text_pad(tile) == tile + 16 and lib.kvg_text_pad(tile + 1) == 2 * tile + 16
 
 
 @pytest.mark.skipif(conftest.HAS_GPU, reason="checks the no-GPU failure mode")

@@ -127,10 +127,10 @@ def test_random_grammar_fuzz(ctx):
 
 
 def test_tile_boundaries_and_scanner_limit(ctx):
-    TILE = 16384
+    TILE = 8192
     base = b"8086  Intel\n\t1234  wrong vendor\n"
     # the 10de line, device lines and a section end placed on every offset around a tile edge
-    for delta in range(-8, 9):
+    for delta in list(range(-8, 9)) + [8192 - 8, 8192, 8192 + 5]:
         pad_len = TILE - len(base) + delta - 2
         text = base + b"#" + b"c" * pad_len + b"\n" + b"10de  NVIDIA\n\t1234  Edge [case]\n" + \
             b"#" + b"d" * (TILE - 40) + b"\n\t5678  second tile\n10df  next\n\t9999  other\n"
