@@ -274,6 +274,7 @@ static int classify_grid(kvg_ctx* ctx, size_t n_items, size_t* smem_out) {
   *smem_out = smem;
   size_t tiles = (n_items + (size_t)KVG_BLOCK * ROWS - 1) / ((size_t)KVG_BLOCK * ROWS);
   size_t g = (size_t)ctx->sm_count * (size_t)occ;
+  if (g > CLASSIFY_MAX_GRID) g = CLASSIFY_MAX_GRID;  // look-back batch covers 32*LB_KMAX CTAs
   if (tiles < g) g = tiles;
   return g < 1 ? 1 : (int)g;
 }
@@ -400,8 +401,9 @@ int kvg_kernel_times(kvg_ctx* ctx, float* ms, char* names, size_t names_cap, int
 size_t kvg_text_pad(size_t len) { return ((len + P_TILE - 1) / P_TILE) * P_TILE + P_HALO; }
 
 static uint32_t table_log2_for(size_t len) {
-  // ~1 device line per 77 bytes in pci.ids; keep the load factor under ~0.6
-  size_t want = len / 48 + 64;
+  // ~1 device line per 77 bytes in pci.ids; aim at a load factor <= 0.3: every extra probe of
+  // an insert is a serialized L2 atomic round trip inside the parse kernel
+  size_t want = len / 24 + 64;
   uint32_t l = 10;
   while (((size_t)1 << l) < want) l++;
   return l;
@@ -501,14 +503,14 @@ static int parse_with_regrow(kvg_ctx* ctx, const uint8_t* d_text, size_t len, si
     rc = table_publish(ctx, d_text, len);
     if (rc) return rc;
     size_t cap = (size_t)1 << cap_log2;
-    bool crowded = (size_t)ctx->h_info.n_entries * 10 > cap * 7;
+    bool crowded = (size_t)ctx->h_info.n_entries * 10 > cap * 5;
     if (!ctx->h_info.overflow && !crowded) return KVG_OK;
     ctx->table_ready = false;
     if (cap_log2 >= 30) {
       ctx->err = "pci.ids hash table cannot grow further";
       return KVG_ENOMEM;
     }
-    size_t want = ctx->h_info.overflow ? cap * 4 : (size_t)ctx->h_info.n_entries * 2;
+    size_t want = ctx->h_info.overflow ? cap * 4 : (size_t)ctx->h_info.n_entries * 4;
     while (((size_t)1 << cap_log2) < want) cap_log2++;
   }
 }
@@ -840,7 +842,8 @@ static int enqueue_pci_orderings(kvg_ctx* ctx, size_t surv_cap) {
 }
 
 static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d_out) {
-  ENSURE(ctx->classify_state, (n + (size_t)KVG_BLOCK * PCI_ROWS - 1) / ((size_t)KVG_BLOCK * PCI_ROWS) + 1);
+  const size_t pci_tiles = (n + (size_t)KVG_BLOCK * PCI_ROWS - 1) / ((size_t)KVG_BLOCK * PCI_ROWS) + 1;
+  ENSURE(ctx->classify_state, 2 * pci_tiles);  // per-tile aggregates, then per-round prefixes
   PciClassifyOp op;
   op.recs = (const uint4*)d_recs;
   op.n = (uint32_t)n;
@@ -855,7 +858,7 @@ static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d
   size_t smem = 0;
   int grid = classify_grid<PciClassifyOp, PCI_ROWS, PCI_STAGES>(ctx, n, &smem);
   LAUNCH("classify_compact", (k_classify_tma<PciClassifyOp, PCI_ROWS, PCI_STAGES>), grid, KVG_BLOCK, smem, op,
-         ctx->classify_state.p, ++ctx->epoch);
+         ctx->classify_state.p, ctx->classify_state.p + pci_tiles, ++ctx->epoch);
   return check_launch(ctx, "classify");
 }
 
@@ -1130,7 +1133,8 @@ int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type
     if (rc) return rc;
   }
   ENSURE(ctx->surv, 2 * (n + 1));
-  ENSURE(ctx->classify_state, (n + (size_t)KVG_BLOCK * MDEV_ROWS - 1) / ((size_t)KVG_BLOCK * MDEV_ROWS) + 1);
+  const size_t mdev_tiles = (n + (size_t)KVG_BLOCK * MDEV_ROWS - 1) / ((size_t)KVG_BLOCK * MDEV_ROWS) + 1;
+  ENSURE(ctx->classify_state, 2 * mdev_tiles);
   CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
   MdevClassifyOp op;
   op.recs = (const uint4*)d_recs;
@@ -1144,7 +1148,7 @@ int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type
   size_t msmem = 0;
   int mgrid = classify_grid<MdevClassifyOp, MDEV_ROWS, MDEV_STAGES>(ctx, n, &msmem);
   LAUNCH("mdev_classify_compact", (k_classify_tma<MdevClassifyOp, MDEV_ROWS, MDEV_STAGES>), mgrid, KVG_BLOCK, msmem, op,
-         ctx->classify_state.p, ++ctx->epoch);
+         ctx->classify_state.p, ctx->classify_state.p + mdev_tiles, ++ctx->epoch);
   rc = check_launch(ctx, "mdev classify");
   if (rc) return rc;
   rc = ensure_order(ctx, ctx->ord_dev, n);

@@ -61,6 +61,11 @@ struct ParseArgs {
 __device__ __forceinline__ uint32_t hash32(uint32_t key, uint32_t shift) {
   return (key * 0x9E3779B1u) >> shift;
 }
+// double hashing: an odd stride visits every slot of the power-of-two table and avoids the
+// primary clustering of linear probing (each extra probe is a serialized L2 atomic round trip)
+__device__ __forceinline__ uint32_t hash_step(uint32_t key, uint32_t shift) {
+  return ((key * 0x85EBCA6Bu) >> shift) | 1u;
+}
 
 // 0x80 in every byte of w that equals '\n' (exact, no cross-byte carries)
 __device__ __forceinline__ uint32_t nl_flags(uint32_t w) {
@@ -94,6 +99,7 @@ __device__ __forceinline__ bool table_insert(uint64_t* table, uint32_t mask, uin
                                              uint32_t key, uint32_t off, uint32_t* overflow) {
   uint64_t item = ((uint64_t)key << 32) | off;
   uint32_t h = hash32(key, shift) & mask;
+  const uint32_t step = hash_step(key, shift);
   for (uint32_t probes = 0;; probes++) {
     if (probes > mask) {
       atomicExch(overflow, 1u);
@@ -106,17 +112,18 @@ __device__ __forceinline__ bool table_insert(uint64_t* table, uint32_t mask, uin
       if ((uint32_t)old > off) atomicMin((unsigned long long*)&table[h], (unsigned long long)item);
       return false;
     }
-    h = (h + 1) & mask;
+    h = (h + step) & mask;
   }
 }
 __device__ __forceinline__ uint32_t table_probe(const uint64_t* __restrict__ table, uint32_t mask,
                                                 uint32_t shift, uint32_t key) {
   uint32_t h = hash32(key, shift) & mask;
+  const uint32_t step = hash_step(key, shift);
   for (uint32_t probes = 0; probes <= mask; probes++) {
     uint64_t s = __ldg((const unsigned long long*)&table[h]);
     if (s == P_EMPTY) return P_NONE;
     if ((uint32_t)(s >> 32) == key) return (uint32_t)s;
-    h = (h + 1) & mask;
+    h = (h + step) & mask;
   }
   return P_NONE;
 }

@@ -113,8 +113,17 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_compact(Op op, uint64_t* tile_sta
 // Iteration i:  [prefetch look-back words of tile i-1] -> wait TMA(i) -> LDS, predicate, ballots,
 //   probes -> sync -> warp 0: publish count(i), resolve base(i-1) -> sync -> emit tile i-1.
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t LB_KMAX = 16;             // look-back loads per lane: covers grids up to 512 CTAs
+constexpr uint32_t CLASSIFY_MAX_GRID = 32 * LB_KMAX;
+
 template <class Op, int ROWS, int STAGES>
-__global__ void __launch_bounds__(KVG_BLOCK) k_classify_tma(Op op, uint64_t* tile_state, uint32_t epoch) {
+__global__ void __launch_bounds__(KVG_BLOCK, 3) k_classify_tma(Op op, uint64_t* tile_agg,
+                                                            uint64_t* round_incl, uint32_t epoch) {
+  // Tile t = b + r*G (CTA b, round r).  Its base offset is
+  //     round_incl[r-1]  +  sum of tile_agg[r*G + k] for k < b
+  // i.e. ONE batch of independent loads (prefetched a phase early) instead of a serial walk:
+  // with co-resident CTAs running in lockstep every tile of a round resolves at the same time,
+  // so a classic look-back would crawl through ~G/2 not-yet-inclusive predecessors.
   constexpr uint32_t TILE = KVG_BLOCK * ROWS;
   constexpr uint32_t RB = Op::REC_BYTES;
   constexpr uint32_t STAGE_BYTES = TILE * RB;
@@ -135,10 +144,11 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_classify_tma(Op op, uint64_t* til
     return;
   }
   if (b >= n_tiles) return;
-  const uint32_t my_count = (n_tiles - b + G - 1) / G;  // tiles b, b+G, ...
+  const uint32_t my_count = (n_tiles - b + G - 1) / G;  // rounds in which this CTA has a tile
   const uint8_t* src = reinterpret_cast<const uint8_t*>(op.src());
+  const uint32_t tag = epoch & 0x3fffffffu;
 
-  auto issue = [&](uint32_t i) {  // thread 0: TMA for my i-th tile into stage i % STAGES
+  auto issue = [&](uint32_t i) {  // thread 0: TMA for my round-i tile into stage i % STAGES
     if (i >= my_count) return;
     uint32_t tile = b + i * G;
     uint32_t items = min(TILE, n - tile * TILE);
@@ -160,12 +170,17 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_classify_tma(Op op, uint64_t* til
   for (int k = 0; k < ROWS; k++) prev_bal[k] = prev_aux[k] = 0;
 
   for (uint32_t i = 0; i <= my_count; ++i) {
-    // -- warp 0: prefetch the look-back window of tile i-1 (consumed after the ballots)
-    uint64_t lbw = 0;
-    const uint32_t ptile = b + (i - 1) * G;  // valid when i > 0
-    if (i > 0 && warp == 0 && ptile > 0) {
-      int idx = (int)ptile - 1 - (int)lane;
-      lbw = idx >= 0 ? ld_relaxed_u64(&tile_state[idx]) : lb_pack(epoch, LB_INCLUSIVE, 0);
+    // -- warp 0: prefetch everything the base of my round-(i-1) tile needs
+    const uint32_t r = i - 1;                // round being resolved (valid when i > 0)
+    const uint32_t ptile = b + r * G;
+    uint64_t w[LB_KMAX], wr = 0;
+    if (i > 0 && warp == 0) {
+#pragma unroll
+      for (uint32_t k = 0; k < LB_KMAX; k++) {
+        uint32_t j = lane + 32 * k;
+        w[k] = j < b ? ld_relaxed_u64(&tile_agg[r * G + j]) : 0;
+      }
+      if (r > 0) wr = ld_relaxed_u64(&round_incl[r - 1]);
     }
     uint32_t bal[ROWS], aux[ROWS];
 #pragma unroll
@@ -194,36 +209,31 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_classify_tma(Op op, uint64_t* til
       uint32_t my_total = 0;
       if (i < my_count) {
         const uint32_t tile = b + i * G;
-        uint32_t w = lane < KVG_WARPS ? s_wtot[lane] : 0;
-        uint32_t wi = warp_incl_sum(w);
-        if (lane < KVG_WARPS) s_woff[i & 1][lane] = wi - w;
+        uint32_t wv = lane < KVG_WARPS ? s_wtot[lane] : 0;
+        uint32_t wi = warp_incl_sum(wv);
+        if (lane < KVG_WARPS) s_woff[i & 1][lane] = wi - wv;
         my_total = __shfl_sync(KVG_FULL, wi, KVG_WARPS - 1);
-        if (lane == 0)
-          st_relaxed_u64(&tile_state[tile], lb_pack(epoch, tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE, my_total));
+        if (lane == 0) st_relaxed_u64(&tile_agg[tile], ((uint64_t)tag << 34) | my_total);
       }
       if (i > 0) {
-        uint32_t excl = 0;
-        if (ptile > 0) {
-          int look = (int)ptile - 1;
-          uint64_t w = lbw;
-          for (;;) {
-            uint32_t st = lb_status(w, epoch);
-            uint32_t incl_mask = __ballot_sync(KVG_FULL, st == LB_INCLUSIVE);
-            uint32_t inv_mask = __ballot_sync(KVG_FULL, st == LB_INVALID);
-            uint32_t first = incl_mask ? (uint32_t)__ffs(incl_mask) - 1 : 32;
-            uint32_t need = first >= 31 ? KVG_FULL : ((2u << first) - 1);
-            if (!(inv_mask & need)) {
-              excl += warp_sum(lane <= first ? (uint32_t)w : 0u);
-              if (first < 32) break;
-              look -= 32;
-            }
-            int idx = look - (int)lane;
-            w = idx >= 0 ? ld_relaxed_u64(&tile_state[idx]) : lb_pack(epoch, LB_INCLUSIVE, 0);
+        uint32_t part = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < LB_KMAX; k++) {
+          uint32_t j = lane + 32 * k;
+          if (j < b) {
+            uint64_t v = w[k];
+            while ((uint32_t)(v >> 34) != tag) v = ld_relaxed_u64(&tile_agg[r * G + j]);
+            part += (uint32_t)v;
           }
-          if (lane == 0) st_relaxed_u64(&tile_state[ptile], lb_pack(epoch, LB_INCLUSIVE, excl + prev_total));
+        }
+        uint32_t excl = warp_sum(part);
+        if (r > 0) {
+          while ((uint32_t)(wr >> 34) != tag) wr = ld_relaxed_u64(&round_incl[r - 1]);
+          excl += (uint32_t)wr;
         }
         if (lane == 0) {
           s_base = excl;
+          if (b == G - 1) st_relaxed_u64(&round_incl[r], ((uint64_t)tag << 34) | (excl + prev_total));
           if (ptile == n_tiles - 1) op.finish(excl + prev_total);
         }
       }
