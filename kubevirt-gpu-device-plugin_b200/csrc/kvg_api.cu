@@ -117,6 +117,7 @@ struct kvg_ctx {
   DevBuf<uint64_t> parse_state;
   DevBuf<uint32_t> parse_ticket;
   DevBuf<uint8_t> pool;
+  DevBuf<uint32_t> nv_index;  // [65536] vendor-10de device id -> name pool slot
   std::vector<uint8_t> h_pool;
   PciIdsInfo h_info{};
   bool table_ready = false;
@@ -278,8 +279,32 @@ static int classify_grid(kvg_ctx* ctx, size_t n_items, size_t* smem_out) {
   if (tiles < g) g = tiles;
   return g < 1 ? 1 : (int)g;
 }
+template <class Op, int ROWS, int STAGES>
+static int classify_ws_grid(kvg_ctx* ctx, size_t n_items, size_t* smem_out) {
+  static int occ = 0;
+  const size_t smem = (size_t)STAGES * KVG_BLOCK * ROWS * Op::REC_BYTES;
+  if (!occ) {
+    cudaFuncSetAttribute(k_classify_ws<Op, ROWS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_classify_ws<Op, ROWS, STAGES>, WS_THREADS, smem);
+    if (occ < 1) occ = 1;
+  }
+  *smem_out = smem;
+  size_t tiles = (n_items + (size_t)KVG_BLOCK * ROWS - 1) / ((size_t)KVG_BLOCK * ROWS);
+  size_t g = (size_t)ctx->sm_count * (size_t)occ;
+  if (g > CLASSIFY_MAX_GRID) g = CLASSIFY_MAX_GRID;
+  if (tiles < g) g = tiles;
+  return g < 1 ? 1 : (int)g;
+}
 constexpr int PCI_ROWS = 4, PCI_STAGES = 4;    // 16 KiB stages, 64 KiB ring -> 3 CTAs / SM
 constexpr int MDEV_ROWS = 2, MDEV_STAGES = 4;  // 16 KiB stages
+static int classify_variant() {  // KVG_CLASSIFY=tma selects the non-specialised kernel (A/B tests)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("KVG_CLASSIFY");
+    v = (e && !strcmp(e, "tma")) ? 1 : 0;
+  }
+  return v;
+}
 
 extern "C" {
 
@@ -329,6 +354,7 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   release(ctx->text); release(ctx->tables); release(ctx->info); release(ctx->tile_arrays);
   release(ctx->parse_state); release(ctx->parse_ticket); release(ctx->pool); release(ctx->ctrl);
+  release(ctx->nv_index);
   release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist);
   for (OrderBufs* o : {&ctx->ord_dev, &ctx->ord_grp}) {
     release(o->k0); release(o->v0); release(o->k1); release(o->v1);
@@ -460,6 +486,10 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
   if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
   LAUNCH("pciids_parse", k_pciids_parse, grid, KVG_BLOCK, P_SMEM, A);
   LAUNCH("pciids_finalize", k_pciids_finalize, n_files, KVG_BLOCK, 0, A);
+  // flatten the table for vendor 10de: the scans' per-survivor join is then a single load
+  ENSURE(ctx->nv_index, 65536);
+  LAUNCH("pciids_nv_index", k_probe_keys, 256, 256, 0, ctx->tables.p, A.cap_mask, A.cap_shift,
+         ctx->info.p, 0u, 65536u, ctx->nv_index.p);
   return check_launch(ctx, "pciids parse");
 }
 
@@ -853,12 +883,19 @@ static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d
   op.cap_mask = (1u << ctx->cap_log2) - 1;
   op.cap_shift = 32 - ctx->cap_log2;
   op.info = ctx->info.p;
+  op.nv_index = ctx->nv_index.p;
   op.local_max_group = 0;
   op.local_max_dev = 0;
   size_t smem = 0;
-  int grid = classify_grid<PciClassifyOp, PCI_ROWS, PCI_STAGES>(ctx, n, &smem);
-  LAUNCH("classify_compact", (k_classify_tma<PciClassifyOp, PCI_ROWS, PCI_STAGES>), grid, KVG_BLOCK, smem, op,
-         ctx->classify_state.p, ctx->classify_state.p + pci_tiles, ++ctx->epoch);
+  if (classify_variant() == 1) {
+    int grid = classify_grid<PciClassifyOp, PCI_ROWS, PCI_STAGES>(ctx, n, &smem);
+    LAUNCH("classify_compact", (k_classify_tma<PciClassifyOp, PCI_ROWS, PCI_STAGES>), grid, KVG_BLOCK, smem, op,
+           ctx->classify_state.p, ctx->classify_state.p + pci_tiles, ++ctx->epoch);
+  } else {
+    int grid = classify_ws_grid<PciClassifyOp, PCI_ROWS, PCI_STAGES>(ctx, n, &smem);
+    LAUNCH("classify_compact", (k_classify_ws<PciClassifyOp, PCI_ROWS, PCI_STAGES>), grid, WS_THREADS, smem, op,
+           ctx->classify_state.p, ctx->classify_state.p + pci_tiles, ++ctx->epoch);
+  }
   return check_launch(ctx, "classify");
 }
 
@@ -1146,8 +1183,8 @@ int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type
   op.local_max_parent = 0;
   op.local_max_type = 0;
   size_t msmem = 0;
-  int mgrid = classify_grid<MdevClassifyOp, MDEV_ROWS, MDEV_STAGES>(ctx, n, &msmem);
-  LAUNCH("mdev_classify_compact", (k_classify_tma<MdevClassifyOp, MDEV_ROWS, MDEV_STAGES>), mgrid, KVG_BLOCK, msmem, op,
+  int mgrid = classify_ws_grid<MdevClassifyOp, MDEV_ROWS, MDEV_STAGES>(ctx, n, &msmem);
+  LAUNCH("mdev_classify_compact", (k_classify_ws<MdevClassifyOp, MDEV_ROWS, MDEV_STAGES>), mgrid, WS_THREADS, msmem, op,
          ctx->classify_state.p, ctx->classify_state.p + mdev_tiles, ++ctx->epoch);
   rc = check_launch(ctx, "mdev classify");
   if (rc) return rc;

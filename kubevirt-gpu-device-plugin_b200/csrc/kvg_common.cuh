@@ -90,6 +90,17 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
       : "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// named barriers (id 1..15; id 0 is __syncthreads): producer/consumer hand-off inside a CTA
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---- scans --------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_incl_sum(uint32_t v) {
 #pragma unroll

@@ -262,17 +262,174 @@ __global__ void __launch_bounds__(KVG_BLOCK, 3) k_classify_tma(Op op, uint64_t* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3/K5, warp-specialised form (the one the scans launch).  9 warps per CTA:
+//   warp 8  "scan" warp: issues the TMA ring, publishes the tile count, resolves the tile's base
+//           offset (round prefix + same-round aggregates, independent loads) and hands it over;
+//   warps 0..7 compute: wait TMA -> LDS -> predicate -> ballots (phase 1 of tile i), then write
+//           out tile i-1 whose base the scan warp produced meanwhile.  They never spin on global
+//           memory and never wait for the look-back.
+// Hand-off: named barriers X[p] (counts ready) and Y[p] (base ready), p = tile parity; stage
+// recycling through an mbarrier per stage that the compute warps arrive on after their write-out.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t WS_THREADS = KVG_BLOCK + 32;
+
+template <class Op, int ROWS, int STAGES>
+__global__ void __launch_bounds__(WS_THREADS) k_classify_ws(Op op, uint64_t* tile_agg,
+                                                            uint64_t* round_incl, uint32_t epoch) {
+  constexpr uint32_t TILE = KVG_BLOCK * ROWS;
+  constexpr uint32_t RB = Op::REC_BYTES;
+  constexpr uint32_t STAGE_BYTES = TILE * RB;
+  constexpr uint32_t WARP_ITEMS = 32 * ROWS;
+  extern __shared__ __align__(128) uint8_t c_smem[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
+  __shared__ uint32_t s_wtot[2][KVG_WARPS];
+  __shared__ uint32_t s_woff[2][KVG_WARPS];
+  __shared__ uint32_t s_base[2];
+
+  op.begin();
+  const uint32_t n = op.count();
+  const uint32_t n_tiles = (n + TILE - 1) / TILE;
+  const uint32_t lane = lane_id(), warp = warp_id(), tid = threadIdx.x;
+  const uint32_t G = gridDim.x, b = blockIdx.x;
+  if (n_tiles == 0) {
+    if (b == 0 && tid == 0) op.finish(0);
+    return;
+  }
+  if (b >= n_tiles) return;
+  const uint32_t my_count = (n_tiles - b + G - 1) / G;
+  const uint32_t tag = epoch & 0x3fffffffu;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], KVG_WARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == KVG_WARPS) {
+    // ============================== scan / producer warp =====================================
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(op.src());
+    auto issue = [&](uint32_t i) {  // lane 0
+      if (i >= my_count) return;
+      uint32_t tile = b + i * G;
+      uint32_t items = min(TILE, n - tile * TILE);
+      uint32_t st = i % STAGES;
+      mbar_arrive_expect_tx(&full_bar[st], items * RB);
+      tma_load_1d(c_smem + st * STAGE_BYTES, src + (size_t)tile * STAGE_BYTES, items * RB, &full_bar[st]);
+    };
+    if (lane == 0)
+      for (int s = 0; s < STAGES; s++) issue((uint32_t)s);
+    for (uint32_t i = 0; i < my_count; ++i) {
+      const uint32_t tile = b + i * G;
+      named_bar_sync(1 + (i & 1), WS_THREADS);  // X: the 8 warp counts of tile i are in s_wtot
+      uint32_t wv = lane < KVG_WARPS ? s_wtot[i & 1][lane] : 0;
+      uint32_t wi = warp_incl_sum(wv);
+      if (lane < KVG_WARPS) s_woff[i & 1][lane] = wi - wv;
+      const uint32_t total = __shfl_sync(KVG_FULL, wi, KVG_WARPS - 1);
+      if (lane == 0) st_relaxed_u64(&tile_agg[tile], ((uint64_t)tag << 34) | total);
+      // base = round_incl[i-1] + sum of this round's aggregates of CTAs 0..b-1
+      uint64_t w[LB_KMAX], wr = 0;
+#pragma unroll
+      for (uint32_t k = 0; k < LB_KMAX; k++) {
+        uint32_t j = lane + 32 * k;
+        w[k] = j < b ? ld_relaxed_u64(&tile_agg[i * G + j]) : 0;
+      }
+      if (i > 0) wr = ld_relaxed_u64(&round_incl[i - 1]);
+      uint32_t part = 0;
+#pragma unroll
+      for (uint32_t k = 0; k < LB_KMAX; k++) {
+        uint32_t j = lane + 32 * k;
+        if (j < b) {
+          uint64_t v = w[k];
+          while ((uint32_t)(v >> 34) != tag) v = ld_relaxed_u64(&tile_agg[i * G + j]);
+          part += (uint32_t)v;
+        }
+      }
+      uint32_t excl = warp_sum(part);
+      if (i > 0) {
+        while ((uint32_t)(wr >> 34) != tag) wr = ld_relaxed_u64(&round_incl[i - 1]);
+        excl += (uint32_t)wr;
+      }
+      if (lane == 0) {
+        s_base[i & 1] = excl;
+        if (b == G - 1) st_relaxed_u64(&round_incl[i], ((uint64_t)tag << 34) | (excl + total));
+        if (tile == n_tiles - 1) op.finish(excl + total);
+      }
+      named_bar_arrive(3 + (i & 1), WS_THREADS);  // Y: base + warp offsets of tile i are ready
+      // recycle the stage of tile i-1 once every compute warp has written that tile out
+      if (i >= 1 && i - 1 + STAGES < my_count) {
+        mbar_wait(&empty_bar[(i - 1) % STAGES], ((i - 1) / STAGES) & 1);
+        if (lane == 0) issue(i - 1 + STAGES);
+      }
+    }
+    return;
+  }
+
+  // ================================== compute warps ==========================================
+  uint32_t prev_bal[ROWS], prev_aux[ROWS];
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) prev_bal[k] = prev_aux[k] = 0;
+  for (uint32_t i = 0; i <= my_count; ++i) {
+    uint32_t bal[ROWS], aux[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) bal[k] = aux[k] = 0;
+    if (i < my_count) {
+      const uint32_t tile = b + i * G;
+      const uint32_t st = i % STAGES;
+      mbar_wait(&full_bar[st], (i / STAGES) & 1);
+      const uint8_t* stage = c_smem + st * STAGE_BYTES;
+      uint32_t wtot = 0;
+#pragma unroll
+      for (int k = 0; k < ROWS; k++) {
+        uint32_t j = warp * WARP_ITEMS + k * 32 + lane;
+        bool ok = tile * TILE + j < n;
+        typename Op::Item it = op.from_smem(stage + (size_t)j * RB);
+        bool p = ok && op.pred(it, tile * TILE + j);
+        bal[k] = __ballot_sync(KVG_FULL, p);
+        wtot += __popc(bal[k]);
+        aux[k] = p ? op.prepare(it) : 0u;
+      }
+      if (lane == 0) s_wtot[i & 1][warp] = wtot;
+      named_bar_arrive(1 + (i & 1), WS_THREADS);  // X
+    }
+    if (i > 0) {
+      const uint32_t pi = i - 1, ptile = b + pi * G;
+      named_bar_sync(3 + (pi & 1), WS_THREADS);  // Y
+      const uint8_t* stage = c_smem + (pi % STAGES) * STAGE_BYTES;
+      uint32_t off = s_base[pi & 1] + s_woff[pi & 1][warp];
+#pragma unroll
+      for (int k = 0; k < ROWS; k++) {
+        if ((prev_bal[k] >> lane) & 1u) {
+          uint32_t j = warp * WARP_ITEMS + k * 32 + lane;
+          typename Op::Item it = op.from_smem(stage + (size_t)j * RB);
+          op.emit(off + __popc(prev_bal[k] & lanemask_lt()), it, ptile * TILE + j, prev_aux[k]);
+        }
+        off += __popc(prev_bal[k]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[pi % STAGES]);
+    }
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) {
+      prev_bal[k] = bal[k];
+      prev_aux[k] = aux[k];
+    }
+  }
+  op.tile_epilogue();  // running maxima -> one atomic per warp
+}
+
 // ---- K3: PCI classify ---------------------------------------------------------------------------
 // record = {addr, vendor | device<<16, iommu_group, driver | flags<<8 | numa<<16}
 // device_plugin.go:203-238: any of the vendor/driver/iommu/device read errors drops the entry,
 // vendor must be "10de" (:209), driver must be in supportedVfioDrivers (:217, :75-78)
 __device__ __forceinline__ bool pci_record_alive(const uint4& r) {
-  uint32_t vendor = r.y & 0xffffu;
-  uint32_t driver = r.w & 0xffu;
-  uint32_t flags = (r.w >> 8) & 0xffu;
-  const uint32_t drop = KVG_PF_VENDOR_ERR | KVG_PF_DRIVER_ERR | KVG_PF_IOMMU_ERR | KVG_PF_DEVICE_ERR;
-  return vendor == 0x10deu && (flags & drop) == 0 &&
-         (driver == KVG_DRV_VFIO_PCI || driver == KVG_DRV_NVGRACE);
+  // low 12 bits of r.w = driver | (drop flags << 8): alive iff they equal 1 or 2 exactly
+  static_assert(KVG_DRV_VFIO_PCI == 1 && KVG_DRV_NVGRACE == 2, "driver codes");
+  static_assert((KVG_PF_VENDOR_ERR | KVG_PF_DRIVER_ERR | KVG_PF_IOMMU_ERR | KVG_PF_DEVICE_ERR) == 0xf, "flags");
+  return (r.y & 0xffffu) == 0x10deu && ((r.w & 0x0fffu) - 1u) < 2u;
 }
 struct PciClassifyOp {
   using Item = uint4;
@@ -288,6 +445,7 @@ struct PciClassifyOp {
   const uint64_t* table;
   uint32_t cap_mask, cap_shift;
   const PciIdsInfo* info;
+  const uint32_t* nv_index;                 // device id -> name pool slot (NULL: probe the hash)
   uint32_t local_max_group, local_max_dev;  // per-thread running maxima (registers)
   uint32_t v_off, sec_end;                  // section bounds, read once per thread
 
@@ -295,8 +453,10 @@ struct PciClassifyOp {
     v_off = info ? info->v_off : P_NONE;
     sec_end = info ? info->sec_end : 0;
   }
-  // the name join: hash probe (vendor 10de, device) -> line offset -> pool slot
+  // the name join.  nv_index is the pci.ids hash table flattened for vendor 10de by
+  // k_probe_keys right after every parse (65,536 x u32 pool slots): one load per survivor.
   __device__ __forceinline__ uint32_t prepare(const Item& r) const {
+    if (nv_index) return __ldg(&nv_index[r.y >> 16]);
     uint32_t off = table_probe(table, cap_mask, cap_shift, (0x10deu << 16) | (r.y >> 16));
     return (off != P_NONE && v_off != P_NONE && off > v_off && off < sec_end) ? off - v_off : P_NONE;
   }
