@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <string>
 #include <vector>
 
@@ -77,6 +78,16 @@ struct NcclApi {
 };
 static NcclApi g_nccl;
 static std::string g_create_error;
+// Look-back state words carry a launch epoch so they never need clearing.  The epoch is
+// PROCESS-global (not per context): cudaMalloc may hand a context memory that another context
+// just freed, and a per-context counter would let a stale word alias a live epoch.  Newly
+// allocated buffers are zero-filled as well (epoch 0 is never issued).
+static std::atomic<uint32_t> g_epoch{0};
+static inline uint32_t next_epoch() {
+  uint32_t e = g_epoch.fetch_add(1, std::memory_order_relaxed) + 1;
+  if ((e & 0x3fffffffu) == 0) e = g_epoch.fetch_add(1, std::memory_order_relaxed) + 1;
+  return e;
+}
 
 // ------------------------------------------------------------------------------------------------
 // context
@@ -191,6 +202,7 @@ static int ensure(kvg_ctx* ctx, DevBuf<T>& b, size_t n) {
     return e == cudaErrorMemoryAllocation ? KVG_ENOMEM : KVG_ECUDA;
   }
   b.cap = cap;
+  cudaMemsetAsync(b.p, 0, cap * sizeof(T), ctx->stream);
   return KVG_OK;
 }
 #define ENSURE(buf, n)                      \
@@ -301,7 +313,7 @@ static int classify_variant() {  // KVG_CLASSIFY=tma selects the non-specialised
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("KVG_CLASSIFY");
-    v = (e && !strcmp(e, "tma")) ? 1 : 0;
+    v = (e && !strcmp(e, "tma")) ? 1 : (e && !strcmp(e, "ws")) ? 0 : (e && !strcmp(e, "oneshot4")) ? 3 : 2;
   }
   return v;
 }
@@ -470,7 +482,7 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
   A.tile_first_nl = ctx->tile_arrays.p + n_tiles;
   A.tile_last_nl = ctx->tile_arrays.p + 2 * (size_t)n_tiles;
   A.tile_state = ctx->parse_state.p;
-  A.epoch = ++ctx->epoch;
+  A.epoch = next_epoch();
 
   // table slots <- EMPTY, info <- {v_off = NONE, 0...}, ticket <- 0
   {
@@ -850,7 +862,7 @@ static int enqueue_heads(kvg_ctx* ctx, OrderBufs& o, size_t cap, int npass_max, 
   h.n_seg_out = d_n_seg;
   h.keys = nullptr;
   LAUNCH("segment_heads", k_compact<HeadsSelOp>, compact_grid<HeadsSelOp>(ctx, cap), KVG_BLOCK, 0, h,
-         o.heads_state.p, ++ctx->epoch);
+         o.heads_state.p, next_epoch());
   return check_launch(ctx, "segment heads");
 }
 
@@ -873,7 +885,7 @@ static int enqueue_pci_orderings(kvg_ctx* ctx, size_t surv_cap) {
 
 static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d_out) {
   const size_t pci_tiles = (n + (size_t)KVG_BLOCK * PCI_ROWS - 1) / ((size_t)KVG_BLOCK * PCI_ROWS) + 1;
-  ENSURE(ctx->classify_state, 2 * pci_tiles);  // per-tile aggregates, then per-round prefixes
+  ENSURE(ctx->classify_state, 2 * pci_tiles + n / 512 + 2);  // aggregates + round prefixes / per-tile states
   PciClassifyOp op;
   op.recs = (const uint4*)d_recs;
   op.n = (uint32_t)n;
@@ -887,14 +899,26 @@ static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d
   op.local_max_group = 0;
   op.local_max_dev = 0;
   size_t smem = 0;
-  if (classify_variant() == 1) {
+  if (classify_variant() >= 2) {  // one tile per CTA, hardware-scheduled (default)
+    if (classify_variant() == 2) {
+      constexpr int T = 128, R = 8;
+      size_t tiles = (n + (size_t)T * R - 1) / ((size_t)T * R);
+      LAUNCH("classify_compact", (k_classify_oneshot<PciClassifyOp, T, R>), (unsigned)(tiles ? tiles : 1), T, 0, op,
+             ctx->classify_state.p, next_epoch());
+    } else {
+      constexpr int T = 128, R = 4;
+      size_t tiles = (n + (size_t)T * R - 1) / ((size_t)T * R);
+      LAUNCH("classify_compact", (k_classify_oneshot<PciClassifyOp, T, R>), (unsigned)(tiles ? tiles : 1), T, 0, op,
+             ctx->classify_state.p, next_epoch());
+    }
+  } else if (classify_variant() == 1) {
     int grid = classify_grid<PciClassifyOp, PCI_ROWS, PCI_STAGES>(ctx, n, &smem);
     LAUNCH("classify_compact", (k_classify_tma<PciClassifyOp, PCI_ROWS, PCI_STAGES>), grid, KVG_BLOCK, smem, op,
-           ctx->classify_state.p, ctx->classify_state.p + pci_tiles, ++ctx->epoch);
+           ctx->classify_state.p, ctx->classify_state.p + pci_tiles, next_epoch());
   } else {
     int grid = classify_ws_grid<PciClassifyOp, PCI_ROWS, PCI_STAGES>(ctx, n, &smem);
     LAUNCH("classify_compact", (k_classify_ws<PciClassifyOp, PCI_ROWS, PCI_STAGES>), grid, WS_THREADS, smem, op,
-           ctx->classify_state.p, ctx->classify_state.p + pci_tiles, ++ctx->epoch);
+           ctx->classify_state.p, ctx->classify_state.p + pci_tiles, next_epoch());
   }
   return check_launch(ctx, "classify");
 }
@@ -1066,7 +1090,7 @@ int kvg_health_rescan(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, kvg_healt
   op.ctrl = ctx->ctrl.p;
   op.local_alive = 0;
   LAUNCH("health_diff", k_compact<HealthOp>, compact_grid<HealthOp>(ctx, n), KVG_BLOCK, 0, op,
-         ctx->classify_state.p, ++ctx->epoch);
+         ctx->classify_state.p, next_epoch());
   rc = check_launch(ctx, "health");
   if (rc) return rc;
   CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1185,7 +1209,7 @@ int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type
   size_t msmem = 0;
   int mgrid = classify_ws_grid<MdevClassifyOp, MDEV_ROWS, MDEV_STAGES>(ctx, n, &msmem);
   LAUNCH("mdev_classify_compact", (k_classify_ws<MdevClassifyOp, MDEV_ROWS, MDEV_STAGES>), mgrid, WS_THREADS, msmem, op,
-         ctx->classify_state.p, ctx->classify_state.p + mdev_tiles, ++ctx->epoch);
+         ctx->classify_state.p, ctx->classify_state.p + mdev_tiles, next_epoch());
   rc = check_launch(ctx, "mdev classify");
   if (rc) return rc;
   rc = ensure_order(ctx, ctx->ord_dev, n);
@@ -1342,7 +1366,7 @@ int kvg_dev_flush_l2(kvg_ctx* ctx) {
   CK(cudaSetDevice(ctx->device));
   const size_t n16 = (size_t)(192u << 20) / 16;  // 192 MiB > 126 MB L2
   ENSURE(ctx->flush, n16);
-  kvg::k_fill<<<ctx->sm_count * 8, KVG_BLOCK, 0, ctx->stream>>>(ctx->flush.p, n16, ctx->epoch);
+  kvg::k_fill<<<ctx->sm_count * 8, KVG_BLOCK, 0, ctx->stream>>>(ctx->flush.p, n16, (uint32_t)ctx->launches);
   return check_launch(ctx, "flush");
 }
 

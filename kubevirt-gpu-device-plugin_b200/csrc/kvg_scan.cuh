@@ -421,6 +421,70 @@ __global__ void __launch_bounds__(WS_THREADS) k_classify_ws(Op op, uint64_t* til
   op.tile_epilogue();  // running maxima -> one atomic per warp
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3/K5, one-tile-per-CTA form: small CTAs (THREADS x ROWS records kept in registers), thousands
+// of them, dispatched in blockIdx order by the hardware.  Many resident CTAs per SM hide the
+// count -> look-back -> write-out latency chain of each other; predecessors were dispatched
+// earlier, so the classic decoupled look-back usually finds an inclusive prefix close by.
+// ------------------------------------------------------------------------------------------------
+template <class Op, int THREADS, int ROWS>
+__global__ void __launch_bounds__(THREADS) k_classify_oneshot(Op op, uint64_t* tile_state, uint32_t epoch) {
+  constexpr uint32_t TILE = THREADS * ROWS;
+  constexpr uint32_t NW = THREADS / 32;
+  constexpr uint32_t WARP_ITEMS = 32 * ROWS;
+  __shared__ uint32_t s_wtot[NW], s_woff[NW];
+  __shared__ uint32_t s_base;
+  op.begin();
+  const uint32_t n = op.count();
+  const uint32_t n_tiles = (n + TILE - 1) / TILE;
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t tile = blockIdx.x;
+  if (n_tiles == 0) {
+    if (tile == 0 && threadIdx.x == 0) op.finish(0);
+    return;
+  }
+  if (tile >= n_tiles) return;
+  const uint32_t base = tile * TILE + warp * WARP_ITEMS;
+  typename Op::Item item[ROWS];
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) {
+    uint32_t i = base + k * 32 + lane;
+    item[k] = op.load(i, i < n);
+  }
+  uint32_t bal[ROWS], aux[ROWS];
+  uint32_t wtot = 0;
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) {
+    uint32_t i = base + k * 32 + lane;
+    bool p = i < n && op.pred(item[k], i);
+    bal[k] = __ballot_sync(KVG_FULL, p);
+    wtot += __popc(bal[k]);
+    aux[k] = p ? op.prepare(item[k]) : 0u;
+  }
+  if (lane == 0) s_wtot[warp] = wtot;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < NW ? s_wtot[lane] : 0;
+    uint32_t wi = warp_incl_sum(w);
+    if (lane < NW) s_woff[lane] = wi - w;
+    uint32_t tile_total = __shfl_sync(KVG_FULL, wi, NW - 1);
+    uint32_t excl = lookback_sum(tile_state, tile, tile_total, epoch);
+    if (lane == 0) {
+      s_base = excl;
+      if (tile == n_tiles - 1) op.finish(excl + tile_total);
+    }
+  }
+  __syncthreads();
+  uint32_t off = s_base + s_woff[warp];
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) {
+    uint32_t i = base + k * 32 + lane;
+    if ((bal[k] >> lane) & 1u) op.emit(off + __popc(bal[k] & lanemask_lt()), item[k], i, aux[k]);
+    off += __popc(bal[k]);
+  }
+  op.tile_epilogue();
+}
+
 // ---- K3: PCI classify ---------------------------------------------------------------------------
 // record = {addr, vendor | device<<16, iommu_group, driver | flags<<8 | numa<<16}
 // device_plugin.go:203-238: any of the vendor/driver/iommu/device read errors drops the entry,
