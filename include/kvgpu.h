@@ -249,6 +249,10 @@ int kvg_dev_gen_pci(kvg_ctx *ctx, void *d_recs, uint64_t first, size_t n, const 
 int kvg_dev_gen_mdev(kvg_ctx *ctx, void *d_recs, uint64_t first, size_t n);
 int kvg_dev_scan_mdev(kvg_ctx *ctx, const void *d_recs, size_t n, const kvg_type_dict *types);
 int kvg_dev_scan_mdev_fetch(kvg_ctx *ctx, kvg_mdev_result **res);
+/* diagnostic only: decomposed classify kernel (mode 0 read+count, 1 +tile-local writes, 2 +join);
+ * rows = records per thread (4, 8 or 16); *ms_out = device time of the launch */
+int kvg_dev_debug_classify(kvg_ctx *ctx, const void *d_recs, size_t n, int mode, int rows,
+                           float *ms_out);
 /* write `bytes` of zeros through a scratch buffer larger than L2 (timing hygiene, untimed) */
 int kvg_dev_flush_l2(kvg_ctx *ctx);
 /* per-kernel device time of the last kvg_dev_scan_pci / kvg_dev_pciids_parse, CUDA events on the

@@ -140,6 +140,8 @@ struct kvg_ctx {
   ScanCtrl* h_ctrl = nullptr;  // pinned
   DevBuf<uint4> recs;          // staging for host entry points
   DevBuf<uint4> surv;
+  DevBuf<uint4> ragged;          // tile-local survivor scratch of k_classify_ragged
+  DevBuf<uint32_t> tile_count, tile_off;
   DevBuf<uint64_t> classify_state;
   OrderBufs ord_dev, ord_grp;
   DevBuf<uint32_t> tile_hist;
@@ -313,7 +315,8 @@ static int classify_variant() {  // KVG_CLASSIFY=tma selects the non-specialised
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("KVG_CLASSIFY");
-    v = (e && !strcmp(e, "tma")) ? 1 : (e && !strcmp(e, "ws")) ? 0 : (e && !strcmp(e, "oneshot4")) ? 3 : 2;
+    v = (e && !strcmp(e, "tma")) ? 1 : (e && !strcmp(e, "ws")) ? 0 : (e && !strcmp(e, "oneshot4")) ? 3
+        : (e && !strcmp(e, "oneshot")) ? 2 : 4;  // default 4: split ragged / offsets / pack
   }
   return v;
 }
@@ -366,7 +369,7 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   release(ctx->text); release(ctx->tables); release(ctx->info); release(ctx->tile_arrays);
   release(ctx->parse_state); release(ctx->parse_ticket); release(ctx->pool); release(ctx->ctrl);
-  release(ctx->nv_index);
+  release(ctx->nv_index); release(ctx->ragged); release(ctx->tile_count); release(ctx->tile_off);
   release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist);
   for (OrderBufs* o : {&ctx->ord_dev, &ctx->ord_grp}) {
     release(o->k0); release(o->v0); release(o->k1); release(o->v1);
@@ -899,7 +902,22 @@ static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d
   op.local_max_group = 0;
   op.local_max_dev = 0;
   size_t smem = 0;
-  if (classify_variant() >= 2) {  // one tile per CTA, hardware-scheduled (default)
+  if (classify_variant() == 4) {
+    constexpr int T = 128, R = 8;
+    const size_t tiles = (n + (size_t)T * R - 1) / ((size_t)T * R);
+    if (tiles == 0) {  // nothing to classify: n_surv stays 0 from the control-block memset
+      return KVG_OK;
+    }
+    ENSURE(ctx->ragged, tiles * T * R);
+    ENSURE(ctx->tile_count, tiles + 1);
+    ENSURE(ctx->tile_off, tiles + 2);
+    op.out = (kvg_pci_surv*)ctx->ragged.p;
+    LAUNCH("classify_compact", (k_classify_ragged<PciClassifyOp, T, R>), (unsigned)tiles, T, 0, op, ctx->tile_count.p);
+    LAUNCH("tile_offsets", k_tile_offsets, 1, 1024, 0, ctx->tile_count.p, (uint32_t)tiles, ctx->tile_off.p,
+           &ctx->ctrl.p->n_surv);
+    LAUNCH("pack_survivors", k_pack_survivors<1>, (unsigned)tiles, 128, 0, ctx->ragged.p, ctx->tile_off.p,
+           (uint32_t)(T * R), d_out);
+  } else if (classify_variant() >= 2) {  // one tile per CTA with look-back
     if (classify_variant() == 2) {
       constexpr int T = 128, R = 8;
       size_t tiles = (n + (size_t)T * R - 1) / ((size_t)T * R);
@@ -1206,10 +1224,23 @@ int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type
   op.n_types = nt;
   op.local_max_parent = 0;
   op.local_max_type = 0;
-  size_t msmem = 0;
-  int mgrid = classify_ws_grid<MdevClassifyOp, MDEV_ROWS, MDEV_STAGES>(ctx, n, &msmem);
-  LAUNCH("mdev_classify_compact", (k_classify_ws<MdevClassifyOp, MDEV_ROWS, MDEV_STAGES>), mgrid, WS_THREADS, msmem, op,
-         ctx->classify_state.p, ctx->classify_state.p + mdev_tiles, next_epoch());
+  {
+    constexpr int T = 128, R = 4;  // 512 x 32-byte records = 16 KiB per tile
+    const size_t tiles = (n + (size_t)T * R - 1) / ((size_t)T * R);
+    if (tiles) {
+      ENSURE(ctx->ragged, 2 * tiles * T * R);
+      ENSURE(ctx->tile_count, tiles + 1);
+      ENSURE(ctx->tile_off, tiles + 2);
+      uint4* dense = op.out;
+      op.out = ctx->ragged.p;
+      LAUNCH("mdev_classify_compact", (k_classify_ragged<MdevClassifyOp, T, R>), (unsigned)tiles, T, 0, op,
+             ctx->tile_count.p);
+      LAUNCH("tile_offsets", k_tile_offsets, 1, 1024, 0, ctx->tile_count.p, (uint32_t)tiles, ctx->tile_off.p,
+             &ctx->ctrl.p->n_surv);
+      LAUNCH("pack_survivors", k_pack_survivors<2>, (unsigned)tiles, 128, 0, ctx->ragged.p, ctx->tile_off.p,
+             (uint32_t)(T * R), dense);
+    }
+  }
   rc = check_launch(ctx, "mdev classify");
   if (rc) return rc;
   rc = ensure_order(ctx, ctx->ord_dev, n);
@@ -1361,6 +1392,36 @@ int kvg_dev_gen_mdev(kvg_ctx* ctx, void* d_recs, uint64_t first, size_t n) {
   LAUNCH("gen_mdev", k_gen_mdev, ctx->sm_count * 8, KVG_BLOCK, 0, (uint4*)d_recs, first, (uint32_t)n);
   return check_launch(ctx, "gen_mdev");
 }
+// diagnostic: decomposed classify kernel (see k_debug_classify); returns device ms via *ms_out
+int kvg_dev_debug_classify(kvg_ctx* ctx, const void* d_recs, size_t n, int mode, int rows, float* ms_out) {
+  if (!ctx || !d_recs || !ms_out || n == 0 || n > 0xfffffff0ull) return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  ENSURE(ctx->surv, n + 1);
+  ENSURE(ctx->probe_slots, 4);
+  ENSURE(ctx->nv_index, 65536);
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  CK(cudaMemsetAsync(ctx->probe_slots.p, 0, 4, ctx->stream));
+  cudaEventRecord(a, ctx->stream);
+  if (rows == 4) {
+    size_t tiles = (n + 511) / 512;
+    k_debug_classify<128, 4><<<(unsigned)tiles, 128, 0, ctx->stream>>>((const uint4*)d_recs, (uint32_t)n, ctx->surv.p, ctx->nv_index.p, ctx->probe_slots.p, mode);
+  } else if (rows == 16) {
+    size_t tiles = (n + 2047) / 2048;
+    k_debug_classify<128, 16><<<(unsigned)tiles, 128, 0, ctx->stream>>>((const uint4*)d_recs, (uint32_t)n, ctx->surv.p, ctx->nv_index.p, ctx->probe_slots.p, mode);
+  } else {
+    size_t tiles = (n + 1023) / 1024;
+    k_debug_classify<128, 8><<<(unsigned)tiles, 128, 0, ctx->stream>>>((const uint4*)d_recs, (uint32_t)n, ctx->surv.p, ctx->nv_index.p, ctx->probe_slots.p, mode);
+  }
+  cudaEventRecord(b, ctx->stream);
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaEventElapsedTime(ms_out, a, b);
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  return check_launch(ctx, "debug classify");
+}
+
 int kvg_dev_flush_l2(kvg_ctx* ctx) {
   if (!ctx) return KVG_EINVAL;
   CK(cudaSetDevice(ctx->device));

@@ -184,9 +184,11 @@ __device__ __forceinline__ uint32_t lb_status(uint64_t w, uint32_t epoch) {
 }
 
 // Sum look-back, executed by one full warp.  Publishes this tile's aggregate, walks predecessors
-// 32 at a time and returns the exclusive prefix (valid in every lane); publishes the inclusive.
-// Tiles must be handed out in increasing order by an atomic ticket so a predecessor is always
-// owned by a resident CTA.
+// and returns the exclusive prefix (valid in every lane); publishes the inclusive.
+// The walk reads LB_WIDE*32 predecessor states per step with INDEPENDENT loads: with ~1000 tiles
+// in flight the nearest inclusive prefix is typically hundreds of tiles back, and a 32-wide
+// window would turn that into a chain of ~15 dependent L2 round trips per tile.
+constexpr int LB_WIDE = 8;
 __device__ __forceinline__ uint32_t lookback_sum(uint64_t* state, uint32_t tile, uint32_t aggregate,
                                                  uint32_t epoch) {
   const uint32_t lane = lane_id();
@@ -198,17 +200,29 @@ __device__ __forceinline__ uint32_t lookback_sum(uint64_t* state, uint32_t tile,
   uint32_t excl = 0;
   int look = (int)tile - 1;
   for (;;) {
-    int idx = look - (int)lane;
-    uint64_t w = idx >= 0 ? ld_relaxed_u64(&state[idx]) : lb_pack(epoch, LB_INCLUSIVE, 0);
-    uint32_t st = lb_status(w, epoch);
-    uint32_t incl_mask = __ballot_sync(KVG_FULL, st == LB_INCLUSIVE);
-    uint32_t inv_mask = __ballot_sync(KVG_FULL, st == LB_INVALID);
-    uint32_t first = incl_mask ? (uint32_t)__ffs(incl_mask) - 1 : 32;
-    uint32_t need = first >= 31 ? KVG_FULL : ((2u << first) - 1);  // lanes 0..first
-    if (inv_mask & need) continue;                                 // a needed predecessor not ready
-    excl += warp_sum(lane <= first ? (uint32_t)w : 0u);
-    if (first < 32) break;
-    look -= 32;
+    uint64_t w[LB_WIDE];
+#pragma unroll
+    for (int k = 0; k < LB_WIDE; k++) {
+      int idx = look - (int)lane - 32 * k;
+      w[k] = idx >= 0 ? ld_relaxed_u64(&state[idx]) : lb_pack(epoch, LB_INCLUSIVE, 0);
+    }
+    bool done = false;
+#pragma unroll
+    for (int k = 0; k < LB_WIDE; k++) {
+      uint32_t st = lb_status(w[k], epoch);
+      uint32_t incl_mask = __ballot_sync(KVG_FULL, st == LB_INCLUSIVE);
+      uint32_t inv_mask = __ballot_sync(KVG_FULL, st == LB_INVALID);
+      uint32_t first = incl_mask ? (uint32_t)__ffs(incl_mask) - 1 : 32;
+      uint32_t need = first >= 31 ? KVG_FULL : ((2u << first) - 1);  // lanes 0..first
+      if (inv_mask & need) break;  // a needed predecessor is not published yet: reload from here
+      excl += warp_sum(lane <= first ? (uint32_t)w[k] : 0u);
+      if (first < 32) {
+        done = true;
+        break;
+      }
+      look -= 32;
+    }
+    if (done) break;
   }
   if (lane == 0) st_relaxed_u64(&state[tile], lb_pack(epoch, LB_INCLUSIVE, excl + aggregate));
   return excl;

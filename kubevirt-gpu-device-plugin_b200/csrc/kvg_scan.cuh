@@ -958,4 +958,163 @@ __global__ void k_fill32(uint32_t* __restrict__ p, size_t n, uint32_t v) {
     p[i] = v;
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3/K5 default form: classification without any cross-tile dependency.
+//   k_classify_ragged  every CTA owns one tile (THREADS x ROWS records, 128-bit streaming loads, all
+//                      in flight at once), evaluates the predicate, joins the name and writes its
+//                      survivors — already in output format — at the TILE-LOCAL base tile*TILE of a
+//                      scratch array, plus one count per tile.  Reads each record once, writes each
+//                      survivor once, no waiting on other CTAs: this is the HBM-roofline kernel.
+//   k_tile_offsets     exclusive scan of the tile counts (one CTA; n_tiles is ~N/1024)
+//   k_pack_survivors   dense, order-preserving copy scratch -> survivors using the known offsets
+// A single-pass look-back compaction (k_classify_oneshot / _tma / _ws, kept for A/B measurements,
+// KVG_CLASSIFY=oneshot|tma|ws) moves fewer bytes but spends ~2/3 of each CTA's lifetime waiting
+// for its base offset; measured on B200 it is ~1.7x slower end to end than this split form.
+// ------------------------------------------------------------------------------------------------
+template <class Op, int THREADS, int ROWS>
+__global__ void __launch_bounds__(THREADS) k_classify_ragged(Op op, uint32_t* __restrict__ tile_count) {
+  constexpr uint32_t TILE = THREADS * ROWS;
+  constexpr uint32_t NW = THREADS / 32;
+  constexpr uint32_t WARP_ITEMS = 32 * ROWS;
+  __shared__ uint32_t s_wtot[NW];
+  op.begin();
+  const uint32_t n = op.count();
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t tile = blockIdx.x;
+  const uint32_t base = tile * TILE + warp * WARP_ITEMS;
+  typename Op::Item item[ROWS];
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) {
+    uint32_t i = base + k * 32 + lane;
+    item[k] = op.load(i, i < n);
+  }
+  uint32_t bal[ROWS], aux[ROWS];
+  uint32_t wtot = 0;
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) {
+    uint32_t i = base + k * 32 + lane;
+    bool p = i < n && op.pred(item[k], i);
+    bal[k] = __ballot_sync(KVG_FULL, p);
+    wtot += __popc(bal[k]);
+    aux[k] = p ? op.prepare(item[k]) : 0u;
+  }
+  if (lane == 0) s_wtot[warp] = wtot;
+  __syncthreads();
+  uint32_t off = tile * TILE;  // tile-local base: survivors of a tile stay contiguous and ordered
+#pragma unroll
+  for (uint32_t w = 0; w < NW; w++) {
+    uint32_t c = s_wtot[w];
+    if (w < warp) off += c;
+    if (w == NW - 1 && threadIdx.x == 0) {
+      uint32_t tot = 0;
+#pragma unroll
+      for (uint32_t v = 0; v < NW; v++) tot += s_wtot[v];
+      tile_count[tile] = tot;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) {
+    uint32_t i = base + k * 32 + lane;
+    if ((bal[k] >> lane) & 1u) op.emit(off + __popc(bal[k] & lanemask_lt()), item[k], i, aux[k]);
+    off += __popc(bal[k]);
+  }
+  op.tile_epilogue();
+}
+
+// exclusive scan of tile_count[0..n_tiles) -> tile_off[0..n_tiles], total -> *n_out (one CTA)
+__global__ void __launch_bounds__(1024) k_tile_offsets(const uint32_t* __restrict__ tile_count,
+                                                       uint32_t n_tiles, uint32_t* __restrict__ tile_off,
+                                                       uint32_t* __restrict__ n_out) {
+  __shared__ uint32_t s_part[1024];
+  __shared__ uint32_t s_warp[32];
+  const uint32_t t = threadIdx.x;
+  const uint32_t per = (n_tiles + 1023) / 1024;
+  const uint32_t lo = min(t * per, n_tiles), hi = min(lo + per, n_tiles);
+  uint32_t sum = 0;
+  for (uint32_t i = lo; i < hi; i++) sum += tile_count[i];
+  uint32_t incl = warp_incl_sum(sum);
+  if ((t & 31) == 31) s_warp[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    uint32_t w = s_warp[t];
+    uint32_t wi = warp_incl_sum(w);
+    s_warp[t] = wi - w;
+    if (t == 31) {
+      *n_out = wi;
+      tile_off[n_tiles] = wi;
+    }
+  }
+  __syncthreads();
+  uint32_t run = s_warp[t >> 5] + incl - sum;
+  (void)s_part;
+  for (uint32_t i = lo; i < hi; i++) {
+    tile_off[i] = run;
+    run += tile_count[i];
+  }
+}
+
+// dense, order-preserving pack: CTA = one tile, 16-byte units, fully coalesced on both sides
+template <int UNITS_PER_ITEM>
+__global__ void __launch_bounds__(128) k_pack_survivors(const uint4* __restrict__ ragged,
+                                                        const uint32_t* __restrict__ tile_off,
+                                                        uint32_t tile_items, uint4* __restrict__ dense) {
+  const uint32_t tile = blockIdx.x;
+  const uint32_t o0 = tile_off[tile], o1 = tile_off[tile + 1];
+  const uint32_t units = (o1 - o0) * UNITS_PER_ITEM;
+  const uint4* src = ragged + (size_t)tile * tile_items * UNITS_PER_ITEM;
+  uint4* dst = dense + (size_t)o0 * UNITS_PER_ITEM;
+  for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) st_stream(dst + u, ld_stream(src + u));
+}
+
+// Diagnostic decomposition of the classify kernel (kvg_dev_debug_classify):
+//   mode 0  read + predicate + count only (one atomicAdd per tile)
+//   mode 1  + write survivors at a TILE-LOCAL base (no cross-tile dependency, output not compact)
+//   mode 2  + direct-index name join
+template <int THREADS, int ROWS>
+__global__ void __launch_bounds__(THREADS) k_debug_classify(const uint4* __restrict__ recs, uint32_t n,
+                                                             uint4* __restrict__ out,
+                                                             const uint32_t* __restrict__ nv_index,
+                                                             uint32_t* counter, int mode) {
+  constexpr uint32_t TILE = THREADS * ROWS;
+  constexpr uint32_t NW = THREADS / 32;
+  __shared__ uint32_t s_wtot[NW], s_woff[NW];
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  const uint32_t tile = blockIdx.x;
+  const uint32_t base = tile * TILE + warp * 32 * ROWS;
+  uint4 item[ROWS];
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) {
+    uint32_t i = base + k * 32 + lane;
+    item[k] = i < n ? ld_stream(recs + i) : make_uint4(0, 0, 0, 0xff00u);
+  }
+  uint32_t bal[ROWS], aux[ROWS], wtot = 0;
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) {
+    bool p = pci_record_alive(item[k]);
+    bal[k] = __ballot_sync(KVG_FULL, p);
+    wtot += __popc(bal[k]);
+    aux[k] = (mode >= 2 && p) ? __ldg(&nv_index[item[k].y >> 16]) : 0u;
+  }
+  if (lane == 0) s_wtot[warp] = wtot;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < NW ? s_wtot[lane] : 0;
+    uint32_t wi = warp_incl_sum(w);
+    if (lane < NW) s_woff[lane] = wi - w;
+    if (lane == NW - 1) atomicAdd(counter, wi);
+  }
+  if (mode == 0) return;
+  __syncthreads();
+  uint32_t off = tile * TILE + s_woff[warp];
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) {
+    if ((bal[k] >> lane) & 1u) {
+      uint4 sv = item[k];
+      sv.w = aux[k];
+      st_stream(out + off + __popc(bal[k] & lanemask_lt()), sv);
+    }
+    off += __popc(bal[k]);
+  }
+}
+
 }  // namespace kvg
