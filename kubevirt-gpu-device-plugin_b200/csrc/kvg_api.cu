@@ -142,6 +142,8 @@ struct kvg_ctx {
   DevBuf<uint4> surv;
   DevBuf<uint4> ragged;          // tile-local survivor scratch of k_classify_ragged
   DevBuf<uint32_t> tile_count, tile_off;
+  DevBuf<uint2> tile_max;
+  DevBuf<uint64_t> offs_state;
   DevBuf<uint64_t> classify_state;
   OrderBufs ord_dev, ord_grp;
   DevBuf<uint32_t> tile_hist;
@@ -370,6 +372,7 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   release(ctx->text); release(ctx->tables); release(ctx->info); release(ctx->tile_arrays);
   release(ctx->parse_state); release(ctx->parse_ticket); release(ctx->pool); release(ctx->ctrl);
   release(ctx->nv_index); release(ctx->ragged); release(ctx->tile_count); release(ctx->tile_off);
+  release(ctx->tile_max); release(ctx->offs_state);
   release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist);
   for (OrderBufs* o : {&ctx->ord_dev, &ctx->ord_grp}) {
     release(o->k0); release(o->v0); release(o->k1); release(o->v1);
@@ -911,10 +914,14 @@ static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d
     ENSURE(ctx->ragged, tiles * T * R);
     ENSURE(ctx->tile_count, tiles + 1);
     ENSURE(ctx->tile_off, tiles + 2);
+    ENSURE(ctx->tile_max, tiles + 1);
+    const unsigned chunks = (unsigned)((tiles + C_TILE - 1) / C_TILE);
+    ENSURE(ctx->offs_state, (size_t)chunks + 1);
     op.out = (kvg_pci_surv*)ctx->ragged.p;
-    LAUNCH("classify_compact", (k_classify_ragged<PciClassifyOp, T, R>), (unsigned)tiles, T, 0, op, ctx->tile_count.p);
-    LAUNCH("tile_offsets", k_tile_offsets, 1, 1024, 0, ctx->tile_count.p, (uint32_t)tiles, ctx->tile_off.p,
-           &ctx->ctrl.p->n_surv);
+    LAUNCH("classify_compact", (k_classify_ragged<PciClassifyOp, T, R>), (unsigned)tiles, T, 0, op,
+           ctx->tile_count.p, ctx->tile_max.p);
+    LAUNCH("tile_offsets", k_tile_offsets, chunks, KVG_BLOCK, 0, ctx->tile_count.p, ctx->tile_max.p,
+           (uint32_t)tiles, ctx->tile_off.p, ctx->ctrl.p, ctx->offs_state.p, next_epoch());
     LAUNCH("pack_survivors", k_pack_survivors<1>, (unsigned)tiles, 128, 0, ctx->ragged.p, ctx->tile_off.p,
            (uint32_t)(T * R), d_out);
   } else if (classify_variant() >= 2) {  // one tile per CTA with look-back
@@ -1231,12 +1238,15 @@ int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type
       ENSURE(ctx->ragged, 2 * tiles * T * R);
       ENSURE(ctx->tile_count, tiles + 1);
       ENSURE(ctx->tile_off, tiles + 2);
+      ENSURE(ctx->tile_max, tiles + 1);
+      const unsigned chunks = (unsigned)((tiles + C_TILE - 1) / C_TILE);
+      ENSURE(ctx->offs_state, (size_t)chunks + 1);
       uint4* dense = op.out;
       op.out = ctx->ragged.p;
       LAUNCH("mdev_classify_compact", (k_classify_ragged<MdevClassifyOp, T, R>), (unsigned)tiles, T, 0, op,
-             ctx->tile_count.p);
-      LAUNCH("tile_offsets", k_tile_offsets, 1, 1024, 0, ctx->tile_count.p, (uint32_t)tiles, ctx->tile_off.p,
-             &ctx->ctrl.p->n_surv);
+             ctx->tile_count.p, ctx->tile_max.p);
+      LAUNCH("tile_offsets", k_tile_offsets, chunks, KVG_BLOCK, 0, ctx->tile_count.p, ctx->tile_max.p,
+             (uint32_t)tiles, ctx->tile_off.p, ctx->ctrl.p, ctx->offs_state.p, next_epoch());
       LAUNCH("pack_survivors", k_pack_survivors<2>, (unsigned)tiles, 128, 0, ctx->ragged.p, ctx->tile_off.p,
              (uint32_t)(T * R), dense);
     }

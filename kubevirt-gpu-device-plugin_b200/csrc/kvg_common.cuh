@@ -188,7 +188,7 @@ __device__ __forceinline__ uint32_t lb_status(uint64_t w, uint32_t epoch) {
 // The walk reads LB_WIDE*32 predecessor states per step with INDEPENDENT loads: with ~1000 tiles
 // in flight the nearest inclusive prefix is typically hundreds of tiles back, and a 32-wide
 // window would turn that into a chain of ~15 dependent L2 round trips per tile.
-constexpr int LB_WIDE = 8;
+constexpr int LB_WIDE = 1;  // measured: 8-wide windows were slower (more polling traffic), 1 = classic
 __device__ __forceinline__ uint32_t lookback_sum(uint64_t* state, uint32_t tile, uint32_t aggregate,
                                                  uint32_t epoch) {
   const uint32_t lane = lane_id();

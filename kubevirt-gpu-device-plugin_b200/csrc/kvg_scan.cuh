@@ -556,6 +556,11 @@ struct PciClassifyOp {
     local_max_dev = 0;
   }
   __device__ __forceinline__ void finish(uint32_t total) { ctrl->n_surv = total; }
+  __device__ __forceinline__ uint2 take_maxima() {
+    uint2 m = make_uint2(local_max_group, local_max_dev);
+    local_max_group = local_max_dev = 0;
+    return m;
+  }
 };
 
 // ---- K5: mdev classify --------------------------------------------------------------------------
@@ -624,6 +629,11 @@ struct MdevClassifyOp {
     local_max_type = 0;
   }
   __device__ __forceinline__ void finish(uint32_t total) { ctrl->n_surv = total; }
+  __device__ __forceinline__ uint2 take_maxima() {
+    uint2 m = make_uint2(local_max_parent, local_max_type);
+    local_max_parent = local_max_type = 0;
+    return m;
+  }
 };
 
 // ---- K6: health diff ----------------------------------------------------------------------------
@@ -972,11 +982,13 @@ __global__ void k_fill32(uint32_t* __restrict__ p, size_t n, uint32_t v) {
 // for its base offset; measured on B200 it is ~1.7x slower end to end than this split form.
 // ------------------------------------------------------------------------------------------------
 template <class Op, int THREADS, int ROWS>
-__global__ void __launch_bounds__(THREADS) k_classify_ragged(Op op, uint32_t* __restrict__ tile_count) {
+__global__ void __launch_bounds__(THREADS) k_classify_ragged(Op op, uint32_t* __restrict__ tile_count,
+                                                             uint2* __restrict__ tile_max) {
   constexpr uint32_t TILE = THREADS * ROWS;
   constexpr uint32_t NW = THREADS / 32;
   constexpr uint32_t WARP_ITEMS = 32 * ROWS;
   __shared__ uint32_t s_wtot[NW];
+  __shared__ uint2 s_wmax[NW];
   op.begin();
   const uint32_t n = op.count();
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
@@ -1018,38 +1030,71 @@ __global__ void __launch_bounds__(THREADS) k_classify_ragged(Op op, uint32_t* __
     if ((bal[k] >> lane) & 1u) op.emit(off + __popc(bal[k] & lanemask_lt()), item[k], i, aux[k]);
     off += __popc(bal[k]);
   }
-  op.tile_epilogue();
+  // largest keys of the tile (they bound the radix pass counts): per-tile slot, no global atomics
+  uint2 m = op.take_maxima();
+  m.x = warp_max(m.x);
+  m.y = warp_max(m.y);
+  if (lane == 0) s_wmax[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint2 t = s_wmax[0];
+#pragma unroll
+    for (uint32_t w = 1; w < NW; w++) {
+      t.x = max(t.x, s_wmax[w].x);
+      t.y = max(t.y, s_wmax[w].y);
+    }
+    tile_max[tile] = t;
+  }
 }
 
-// exclusive scan of tile_count[0..n_tiles) -> tile_off[0..n_tiles], total -> *n_out (one CTA)
-__global__ void __launch_bounds__(1024) k_tile_offsets(const uint32_t* __restrict__ tile_count,
-                                                       uint32_t n_tiles, uint32_t* __restrict__ tile_off,
-                                                       uint32_t* __restrict__ n_out) {
-  __shared__ uint32_t s_part[1024];
-  __shared__ uint32_t s_warp[32];
-  const uint32_t t = threadIdx.x;
-  const uint32_t per = (n_tiles + 1023) / 1024;
-  const uint32_t lo = min(t * per, n_tiles), hi = min(lo + per, n_tiles);
-  uint32_t sum = 0;
-  for (uint32_t i = lo; i < hi; i++) sum += tile_count[i];
-  uint32_t incl = warp_incl_sum(sum);
-  if ((t & 31) == 31) s_warp[t >> 5] = incl;
-  __syncthreads();
-  if (t < 32) {
-    uint32_t w = s_warp[t];
-    uint32_t wi = warp_incl_sum(w);
-    s_warp[t] = wi - w;
-    if (t == 31) {
-      *n_out = wi;
-      tile_off[n_tiles] = wi;
+// exclusive scan of tile_count[0..n_tiles) -> tile_off[0..n_tiles], total -> ctrl->n_surv, and the
+// reduction of the per-tile maxima -> ctrl->max_group / max_devkey.  Chained scan: 2048 counts per
+// CTA, coalesced, base by decoupled look-back (a few dozen CTAs at most, launched in order).
+__global__ void __launch_bounds__(KVG_BLOCK) k_tile_offsets(const uint32_t* __restrict__ tile_count,
+                                                            const uint2* __restrict__ tile_max,
+                                                            uint32_t n_tiles, uint32_t* __restrict__ tile_off,
+                                                            ScanCtrl* ctrl, uint64_t* state, uint32_t epoch) {
+  __shared__ uint32_t scratch[KVG_WARPS + 1];
+  __shared__ uint32_t s_base;
+  const uint32_t chunk = blockIdx.x;
+  const uint32_t i0 = chunk * C_TILE + threadIdx.x * C_ROWS;
+  uint32_t v[C_ROWS], sum = 0, mg = 0, md = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < C_ROWS; k++) {
+    uint32_t i = i0 + k;
+    v[k] = i < n_tiles ? tile_count[i] : 0;
+    sum += v[k];
+    if (i < n_tiles) {
+      uint2 m = tile_max[i];
+      mg = max(mg, m.x);
+      md = max(md, m.y);
     }
   }
+  uint32_t total;
+  uint32_t excl = block_excl_sum(sum, scratch, &total);
+  if (warp_id() == 0) {
+    uint32_t base = lookback_sum(state, chunk, total, epoch);
+    if (lane_id() == 0) {
+      s_base = base;
+      if (chunk == gridDim.x - 1) {
+        ctrl->n_surv = base + total;
+        tile_off[n_tiles] = base + total;
+      }
+    }
+  }
+  mg = warp_max(mg);
+  md = warp_max(md);
+  if (lane_id() == 0) {
+    if (mg) atomicMax(&ctrl->max_group, mg);
+    if (md) atomicMax(&ctrl->max_devkey, md);
+  }
   __syncthreads();
-  uint32_t run = s_warp[t >> 5] + incl - sum;
-  (void)s_part;
-  for (uint32_t i = lo; i < hi; i++) {
-    tile_off[i] = run;
-    run += tile_count[i];
+  uint32_t run = s_base + excl;
+#pragma unroll
+  for (uint32_t k = 0; k < C_ROWS; k++) {
+    uint32_t i = i0 + k;
+    if (i < n_tiles) tile_off[i] = run;
+    run += v[k];
   }
 }
 
