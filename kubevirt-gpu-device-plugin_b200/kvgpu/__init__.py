@@ -10,6 +10,6 @@ from .plugin import (DiscoveryScan, Maps, MdevSnapshot, NvidiaGpuDevice, PciSnap
                      ReferencePanic, canonical_dump, format_bdf, format_uuid,
                      mdev_maps_from_result, parse_bdf, pci_maps_from_result, snapshot_mdev_tree,
                      snapshot_pci_tree)
-from .parallel import shard_range, ShardedScan
+from .parallel import ShardedScan, allgatherv_torch, concat_in_rank_order, shard_range
 
 __all__ = [n for n in dir() if not n.startswith("_")]

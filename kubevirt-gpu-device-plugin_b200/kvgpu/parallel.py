@@ -29,6 +29,30 @@ def concat_in_rank_order(parts: list) -> list:
     return out
 
 
+def allgatherv_torch(local, dist_mod=None):
+    """Backend-agnostic statement of the exchange step (same algorithm as the NCCL path in
+    kvg_dev_scan_pci_sharded): all-gather the per-rank counts, then one broadcast per root into the
+    rank-ordered output.  `local` is a 1-D torch tensor; works on gloo (CPU tests) and nccl."""
+    import torch
+    import torch.distributed as dist
+    dist = dist_mod or dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    cnt = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    counts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt)
+    counts = [int(c.item()) for c in counts]
+    out = torch.empty(sum(counts), dtype=local.dtype, device=local.device)
+    off = 0
+    for root in range(world):
+        seg = out[off:off + counts[root]]
+        if root == rank:
+            seg.copy_(local)
+        if counts[root]:
+            dist.broadcast(seg, root)
+        off += counts[root]
+    return out, counts
+
+
 class ShardedScan:
     def __init__(self, ctx: Context, rank: int, world: int, broadcast_bytes):
         """broadcast_bytes(b: bytes | None, src=0) -> bytes : collective byte broadcast."""

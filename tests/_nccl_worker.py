@@ -1,0 +1,61 @@
+"""Worker for the multi-GPU parity test: rank r scans its shard on GPU r; the gathered result on
+every rank must equal the oracle on the unsharded snapshot."""
+import hashlib
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "kubevirt-gpu-device-plugin_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+import kvgpu
+import util
+from oracle import oracle as O
+
+
+def main():
+    n = int(sys.argv[1])
+    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    text = util.pciids_text()
+    ids = O.nv_ids(text)
+    ctx = kvgpu.Context(local_rank)
+    ctx.pciids_load(text)
+
+    def bcast(b, src):
+        t = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == src:
+            t.copy_(torch.frombuffer(bytearray(b), dtype=torch.uint8))
+        dist.broadcast(t, src)
+        return bytes(t.cpu().numpy().tobytes())
+
+    sh = kvgpu.ShardedScan(ctx, rank, world, bcast)
+    lo, hi = kvgpu.shard_range(n, rank, world)
+    buf = torch.empty(max(hi - lo, 1) * 16, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    ctx.dev_gen_pci(buf.data_ptr(), lo, hi - lo, ids, 17)
+    for rep in range(2):
+        sh.scan_device_shard(buf.data_ptr(), hi - lo)
+        res = sh.fetch()
+        got = kvgpu.canonical_dump(kvgpu.pci_maps_from_result(res))
+        m = O.Maps()
+        m.create_iommu_device_map_flat(O.gen_pci(0, n, ids, 17))
+        want = m.dump(text)
+        assert got == want, "rank %d rep %d: sharded dump differs (%s vs %s)" % (
+            rank, rep, hashlib.sha256(got).hexdigest()[:12], hashlib.sha256(want).hexdigest()[:12])
+    dist.barrier()
+    if rank == 0:
+        print("nccl-ok world=%d n=%d sha=%s" % (world, n, hashlib.sha256(got).hexdigest()[:16]))
+    sh.close()
+    ctx.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -417,3 +417,29 @@ def test_full_size_properties(kv, loaded, pciids):
     names = loaded.name_table(0, 65536)
     for k in range(0, len(res.dev_keys), 97):
         assert res.name_at(int(res.dev_name_slot[k])) == names[int(res.dev_keys[k])]
+
+
+# ------------------------------------------------------------------------------------------------
+# multi-GPU (BASELINE.json config 4): sharded scan == single scan == oracle
+# ------------------------------------------------------------------------------------------------
+def _gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs at least 2 GPUs on the box")
+@pytest.mark.parametrize("n", [200_003, 5])
+def test_sharded_scan_matches_oracle(n):
+    import subprocess
+    import sys
+    world = min(_gpu_count(), 8)
+    here = os.path.dirname(os.path.abspath(__file__))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + n % 300),
+           os.path.join(here, "_nccl_worker.py"), str(n)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "nccl-ok world=%d n=%d" % (world, n) in r.stdout
