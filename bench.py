@@ -367,13 +367,21 @@ def main():
         p_text = torch.from_numpy(np.frombuffer(text, dtype=np.uint8).copy()).pin_memory()
         lib = kvgpu.load()
 
+        import ctypes as C
+
         def e2e_step():
             rc = lib.kvg_pciids_load(ctx.handle, p_text.data_ptr(), len(text))
             assert rc == 0
-            with torch.cuda.stream(ext):
-                d_recs[:n * 16].copy_(p_recs[:n * 16], non_blocking=True)
+            d_recs[:n * 16].copy_(p_recs[:n * 16], non_blocking=True)   # H2D of the rank's shard
+            torch.cuda.current_stream().synchronize()
             sharded.scan_device_shard(d_recs.data_ptr(), n)
-            return ctx.dev_scan_pci_fetch()
+            res = C.POINTER(kvgpu._lib.PciResultC)()
+            rc = lib.kvg_dev_scan_pci_fetch(ctx.handle, C.byref(res))       # gathered result -> host
+            assert rc == 0
+            r = res.contents
+            out = (int(r.n_survivors), int(r.n_dev_keys), int(r.n_groups))
+            lib.kvg_result_free(res)
+            return out
         for _ in range(3):
             r = e2e_step()
         dist.barrier()
@@ -387,7 +395,7 @@ def main():
         e2e = {"value": n * world * args.steps / te, "unit": "records/s",
                "ms_per_step": 1e3 * te / args.steps,
                "h2d_bytes_per_step": len(text) + 16 * n,
-               "d2h_bytes_per_step": int(len(r.survivors) * 24 + len(r.dev_keys) * 10 + len(r.grp_keys) * 8),
+               "d2h_bytes_per_step": int(r[0] * 24 + r[1] * 10 + r[2] * 8),
                "timing": "host wall clock, max over ranks"}
 
     if rank == 0:
@@ -418,10 +426,14 @@ def main():
             "clocks": clocks,
         }
         print(json.dumps(line))
+    # free torch tensors before the context (and its stream) goes away
+    del d_recs, d_text
+    torch.cuda.synchronize()
     if sharded:
         sharded.close()
     ctx.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

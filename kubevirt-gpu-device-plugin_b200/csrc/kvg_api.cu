@@ -104,8 +104,10 @@ struct PinnedBlock {
 };
 
 struct OrderBufs {  // one stable ordering (sorted (key, index) pairs + segment heads)
-  DevBuf<uint32_t> k0, v0, k1, v1;
+  DevBuf<uint2> p0, p1;           // ping-pong {key, survivor index}
+  DevBuf<uint32_t> perm;          // final permutation
   DevBuf<uint32_t> seg_key, seg_off;
+  DevBuf<uint32_t> tile_heads, tile_off;
   DevBuf<uint64_t> heads_state;
 };
 
@@ -375,7 +377,7 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   release(ctx->tile_max); release(ctx->offs_state);
   release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist);
   for (OrderBufs* o : {&ctx->ord_dev, &ctx->ord_grp}) {
-    release(o->k0); release(o->v0); release(o->k1); release(o->v1);
+    release(o->p0); release(o->p1); release(o->perm); release(o->tile_heads); release(o->tile_off);
     release(o->seg_key); release(o->seg_off); release(o->heads_state);
   }
   release(ctx->type_raw); release(ctx->type_label); release(ctx->type_off);
@@ -768,9 +770,11 @@ static int compact_grid(kvg_ctx* ctx, size_t n_items) {
 extern "C" {
 
 static int ensure_order(kvg_ctx* ctx, OrderBufs& o, size_t cap) {
-  ENSURE(o.k0, cap); ENSURE(o.v0, cap); ENSURE(o.k1, cap); ENSURE(o.v1, cap);
+  const size_t T = (cap + C_TILE - 1) / C_TILE + 1;
+  ENSURE(o.p0, cap + 1); ENSURE(o.p1, cap + 1); ENSURE(o.perm, cap + 1);
   ENSURE(o.seg_key, cap + 1); ENSURE(o.seg_off, cap + 2);
-  ENSURE(o.heads_state, (cap + C_TILE - 1) / C_TILE + 1);
+  ENSURE(o.tile_heads, T + 1); ENSURE(o.tile_off, T + 2);
+  ENSURE(o.heads_state, T / C_TILE + 2);
   return KVG_OK;
 }
 
@@ -781,17 +785,14 @@ static int enqueue_order(kvg_ctx* ctx, OrderBufs& o, size_t cap, int src, int so
   size_t T = (cap + C_TILE - 1) / C_TILE;
   if (T == 0) T = 1;
   ENSURE(ctx->tile_hist, 256 * T);
-  uint32_t* kin = nullptr;
-  uint32_t* vin = nullptr;
+  const uint2* pin = nullptr;
   for (int p = 0; p < npass_max; p++) {
     RadixArgs a;
     a.n_ptr = &ctx->ctrl.p->n_surv;
     a.max_key = d_max_key;
     a.src_records = ctx->surv.p;
-    a.keys_in = kin;
-    a.vals_in = vin;
-    a.keys_out = (p & 1) ? o.k1.p : o.k0.p;
-    a.vals_out = (p & 1) ? o.v1.p : o.v0.p;
+    a.pairs_in = pin;
+    a.pairs_out = (p & 1) ? o.p1.p : o.p0.p;
     a.tile_hist = ctx->tile_hist.p;
     a.bin_total = ctx->ctrl.p->bin_total[sort_idx][p];
     a.shift = 8 * p;
@@ -799,8 +800,7 @@ static int enqueue_order(kvg_ctx* ctx, OrderBufs& o, size_t cap, int src, int so
     LAUNCH("radix_hist", k_radix_hist, (int)T, KVG_BLOCK, 0, a);
     LAUNCH("radix_tilescan", k_radix_tilescan, 256, KVG_BLOCK, 0, a);
     LAUNCH("radix_scatter", k_radix_scatter, (int)T, KVG_BLOCK, 0, a);
-    kin = a.keys_out;
-    vin = a.vals_out;
+    pin = a.pairs_out;
   }
   // heads of the final key array; the number of executed passes is device-side knowledge
   // (max key), the heads kernel is launched once per possible final buffer and the wrong one
@@ -812,64 +812,36 @@ static int enqueue_order(kvg_ctx* ctx, OrderBufs& o, size_t cap, int src, int so
 
 }  // extern "C"
 
-// heads kernel wrapper that picks the final ping-pong buffer from the device-side max key
-struct HeadsSelOp {
-  using Item = uint2;
-  const uint32_t* k0;
-  const uint32_t* k1;
-  const uint32_t* max_key;
-  int npass_max;
-  const uint32_t* n_ptr;
-  uint32_t* seg_key;
-  uint32_t* seg_off;
-  uint32_t* n_seg_out;
-  const uint32_t* keys;  // resolved in count()
-  __device__ __forceinline__ void begin() {}
-  __device__ __forceinline__ uint32_t prepare(const Item&) const { return 0; }
-  __device__ __forceinline__ uint32_t count() {
-    uint32_t mk = *max_key;
-    int np = 1;
-    while (np < npass_max && (mk >> (8 * np)) != 0) np++;
-    keys = ((np - 1) & 1) ? k1 : k0;
-    return *n_ptr;
-  }
-  __device__ __forceinline__ Item load(uint32_t i, bool ok) const {
-    if (!ok) return make_uint2(0, 0);
-    return make_uint2(keys[i], i ? keys[i - 1] : 0);
-  }
-  __device__ __forceinline__ bool pred(const Item& v, uint32_t i) const { return i == 0 || v.x != v.y; }
-  __device__ __forceinline__ void emit(uint32_t pos, const Item& v, uint32_t i, uint32_t) {
-    seg_key[pos] = v.x;
-    seg_off[pos] = i;
-  }
-  __device__ __forceinline__ void tile_epilogue() {}
-  __device__ __forceinline__ void finish(uint32_t total) {
-    *n_seg_out = total;
-    seg_off[total] = *n_ptr;
-  }
-};
-
 static int active_passes(uint32_t max_key, int npass_max) {
   int np = 1;
   while (np < npass_max && (max_key >> (8 * np)) != 0) np++;
   return np;
 }
 
+// final permutation + distinct keys of one ordering: count heads per tile, scan, emit
 static int enqueue_heads(kvg_ctx* ctx, OrderBufs& o, size_t cap, int npass_max, uint32_t* d_max_key,
                          uint32_t* d_n_seg, uint32_t* ticket) {
-  HeadsSelOp h;
-  h.k0 = o.k0.p;
-  h.k1 = o.k1.p;
-  h.max_key = d_max_key;
-  h.npass_max = npass_max;
-  h.n_ptr = &ctx->ctrl.p->n_surv;
-  h.seg_key = o.seg_key.p;
-  h.seg_off = o.seg_off.p;
-  h.n_seg_out = d_n_seg;
-  h.keys = nullptr;
-  LAUNCH("segment_heads", k_compact<HeadsSelOp>, compact_grid<HeadsSelOp>(ctx, cap), KVG_BLOCK, 0, h,
-         o.heads_state.p, next_epoch());
-  return check_launch(ctx, "segment heads");
+  (void)ticket;
+  size_t T = (cap + C_TILE - 1) / C_TILE;
+  if (T == 0) T = 1;
+  OrderFinalArgs a;
+  a.p0 = o.p0.p;
+  a.p1 = o.p1.p;
+  a.max_key = d_max_key;
+  a.npass_max = npass_max;
+  a.n_ptr = &ctx->ctrl.p->n_surv;
+  a.perm = o.perm.p;
+  a.tile_heads = o.tile_heads.p;
+  a.tile_off = o.tile_off.p;
+  a.seg_key = o.seg_key.p;
+  a.seg_off = o.seg_off.p;
+  a.n_seg = d_n_seg;
+  LAUNCH("order_count", k_order_final<false>, (unsigned)T, KVG_BLOCK, 0, a);
+  const unsigned chunks = (unsigned)((T + C_TILE - 1) / C_TILE);
+  LAUNCH("tile_offsets", k_tile_offsets, chunks, KVG_BLOCK, 0, o.tile_heads.p, (const uint2*)nullptr,
+         &ctx->ctrl.p->n_surv, 0u, o.tile_off.p, d_n_seg, ctx->ctrl.p, o.heads_state.p, next_epoch());
+  LAUNCH("order_emit", k_order_final<true>, (unsigned)T, KVG_BLOCK, 0, a);
+  return check_launch(ctx, "order finalize");
 }
 
 // classify + both orderings of `n` device-resident PCI records (or of an already-gathered
@@ -921,7 +893,8 @@ static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d
     LAUNCH("classify_compact", (k_classify_ragged<PciClassifyOp, T, R>), (unsigned)tiles, T, 0, op,
            ctx->tile_count.p, ctx->tile_max.p);
     LAUNCH("tile_offsets", k_tile_offsets, chunks, KVG_BLOCK, 0, ctx->tile_count.p, ctx->tile_max.p,
-           (uint32_t)tiles, ctx->tile_off.p, ctx->ctrl.p, ctx->offs_state.p, next_epoch());
+           (const uint32_t*)nullptr, (uint32_t)tiles, ctx->tile_off.p, &ctx->ctrl.p->n_surv, ctx->ctrl.p,
+           ctx->offs_state.p, next_epoch());
     LAUNCH("pack_survivors", k_pack_survivors<1>, (unsigned)tiles, 128, 0, ctx->ragged.p, ctx->tile_off.p,
            (uint32_t)(T * R), d_out);
   } else if (classify_variant() >= 2) {  // one tile per CTA with look-back
@@ -1018,10 +991,10 @@ int kvg_dev_scan_pci_fetch(kvg_ctx* ctx, kvg_pci_result** res) {
   CK(D2H(o_surv, ctx->surv.p, S * 16));
   CK(D2H(o_dkeys32, od.seg_key.p, KD * 4));
   CK(D2H(o_doff, od.seg_off.p, (KD + 1) * 4));
-  CK(D2H(o_dperm, ((np_dev - 1) & 1) ? od.v1.p : od.v0.p, S * 4));
+  CK(D2H(o_dperm, od.perm.p, S * 4));
   CK(D2H(o_gkeys, og.seg_key.p, G * 4));
   CK(D2H(o_goff, og.seg_off.p, (G + 1) * 4));
-  CK(D2H(o_gperm, ((np_grp - 1) & 1) ? og.v1.p : og.v0.p, S * 4));
+  CK(D2H(o_gperm, og.perm.p, S * 4));
   CK(cudaStreamSynchronize(ctx->stream));
   kvg_pci_result* r = (kvg_pci_result*)b;
   memset(r, 0, sizeof *r);
@@ -1246,7 +1219,8 @@ int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type
       LAUNCH("mdev_classify_compact", (k_classify_ragged<MdevClassifyOp, T, R>), (unsigned)tiles, T, 0, op,
              ctx->tile_count.p, ctx->tile_max.p);
       LAUNCH("tile_offsets", k_tile_offsets, chunks, KVG_BLOCK, 0, ctx->tile_count.p, ctx->tile_max.p,
-             (uint32_t)tiles, ctx->tile_off.p, ctx->ctrl.p, ctx->offs_state.p, next_epoch());
+             (const uint32_t*)nullptr, (uint32_t)tiles, ctx->tile_off.p, &ctx->ctrl.p->n_surv, ctx->ctrl.p,
+             ctx->offs_state.p, next_epoch());
       LAUNCH("pack_survivors", k_pack_survivors<2>, (unsigned)tiles, 128, 0, ctx->ragged.p, ctx->tile_off.p,
              (uint32_t)(T * R), dense);
     }
@@ -1313,10 +1287,10 @@ int kvg_dev_scan_mdev_fetch(kvg_ctx* ctx, kvg_mdev_result** res) {
   CK(D2H(o_surv, ctx->surv.p, S * 32));
   CK(D2H(o_tk32, ot.seg_key.p, KT * 4));
   CK(D2H(o_toff, ot.seg_off.p, (KT + 1) * 4));
-  CK(D2H(o_tperm, ((np_t - 1) & 1) ? ot.v1.p : ot.v0.p, S * 4));
+  CK(D2H(o_tperm, ot.perm.p, S * 4));
   CK(D2H(o_pk, op.seg_key.p, P * 4));
   CK(D2H(o_poff, op.seg_off.p, (P + 1) * 4));
-  CK(D2H(o_pperm, ((np_p - 1) & 1) ? op.v1.p : op.v0.p, S * 4));
+  CK(D2H(o_pperm, op.perm.p, S * 4));
   if (nt) {
     CK(D2H(o_lraw, ctx->type_label.p, raw_len));
     CK(D2H(o_llen, ctx->type_label_len.p, (size_t)nt * 4));

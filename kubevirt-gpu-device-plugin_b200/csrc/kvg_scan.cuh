@@ -672,7 +672,18 @@ struct HealthOp {
 };
 
 // ------------------------------------------------------------------------------------------------
-// K4: stable LSD radix sort, 8-bit digits, tiles of 2048 pairs
+// K4: stable LSD radix sort of (key, survivor index) pairs, 8-bit digits, tiles of 2048 pairs.
+//   k_radix_hist      per-tile digit histogram: one MATCH-aggregated shared-memory add per distinct
+//                     digit per warp row (device ids are heavily skewed: naive atomics serialise)
+//   k_radix_tilescan  per digit: exclusive scan of the per-tile counts (one CTA per digit)
+//   k_radix_scatter   stable ranks (match + per-warp counters), pairs staged in shared memory in
+//                     tile-sorted order, then written out so that consecutive threads write
+//                     consecutive addresses of a bucket (coalesced runs instead of 4-byte scatters)
+//   k_order_count / k_tile_offsets / k_order_emit
+//                     final permutation + distinct keys (segment heads) without any look-back:
+//                     count heads per tile -> scan -> emit at known offsets
+// Passes whose digit is above the largest key (device-side knowledge) return immediately; the
+// ping-pong parity then tells consumers which buffer is final.
 // ------------------------------------------------------------------------------------------------
 enum : int { SRC_PAIRS = 0, SRC_PCI_GROUP = 1, SRC_PCI_DEVICE = 2, SRC_MDEV_PARENT = 3, SRC_MDEV_TYPE = 4 };
 
@@ -680,10 +691,8 @@ struct RadixArgs {
   const uint32_t* n_ptr;      // element count (device)
   const uint32_t* max_key;    // largest key (device): passes at or above its bit width are skipped
   const void* src_records;    // survivors (SRC_* != PAIRS)
-  const uint32_t* keys_in;
-  const uint32_t* vals_in;
-  uint32_t* keys_out;
-  uint32_t* vals_out;
+  const uint2* pairs_in;      // {key, val}
+  uint2* pairs_out;
   uint32_t* tile_hist;        // [256][T]  (T = ceil(n / C_TILE)), digit-major
   uint32_t* bin_total;        // [256] for this pass
   uint32_t shift;
@@ -693,13 +702,17 @@ struct RadixArgs {
 __device__ __forceinline__ bool radix_pass_active(const RadixArgs& a) {
   return a.shift == 0 || (*a.max_key >> a.shift) != 0;
 }
-__device__ __forceinline__ uint32_t radix_key(const RadixArgs& a, uint32_t i) {
+__device__ __forceinline__ uint2 radix_load(const RadixArgs& a, uint32_t i) {
   switch (a.src) {
-    case SRC_PCI_GROUP: return reinterpret_cast<const kvg_pci_surv*>(a.src_records)[i].iommu_group;
-    case SRC_PCI_DEVICE: return reinterpret_cast<const kvg_pci_surv*>(a.src_records)[i].device;
-    case SRC_MDEV_PARENT: return reinterpret_cast<const kvg_mdev_surv*>(a.src_records)[i].parent;
-    case SRC_MDEV_TYPE: return reinterpret_cast<const kvg_mdev_surv*>(a.src_records)[i].type_key;
-    default: return a.keys_in[i];
+    case SRC_PCI_GROUP:
+      return make_uint2(reinterpret_cast<const kvg_pci_surv*>(a.src_records)[i].iommu_group, i);
+    case SRC_PCI_DEVICE:
+      return make_uint2(reinterpret_cast<const kvg_pci_surv*>(a.src_records)[i].device, i);
+    case SRC_MDEV_PARENT:
+      return make_uint2(reinterpret_cast<const kvg_mdev_surv*>(a.src_records)[i].parent, i);
+    case SRC_MDEV_TYPE:
+      return make_uint2(reinterpret_cast<const kvg_mdev_surv*>(a.src_records)[i].type_key, i);
+    default: return a.pairs_in[i];
   }
 }
 
@@ -711,11 +724,15 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_radix_hist(RadixArgs a) {
   __shared__ uint32_t h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
-  const uint32_t base = tile * C_TILE;
+  const uint32_t lane = lane_id();
+  const uint32_t base = tile * C_TILE + warp_id() * C_WARP_ITEMS;
 #pragma unroll
   for (uint32_t k = 0; k < C_ROWS; k++) {
-    uint32_t i = base + k * KVG_BLOCK + threadIdx.x;
-    if (i < n) atomicAdd(&h[(radix_key(a, i) >> a.shift) & 0xffu], 1u);
+    uint32_t i = base + k * 32 + lane;
+    bool ok = i < n;
+    uint32_t d = ok ? ((radix_load(a, i).x >> a.shift) & 0xffu) : (0x100u + lane);
+    uint32_t peers = __match_any_sync(KVG_FULL, d);
+    if (ok && lane == (uint32_t)__ffs(peers) - 1) atomicAdd(&h[d], (uint32_t)__popc(peers));
   }
   __syncthreads();
   uint32_t c = h[threadIdx.x];
@@ -746,47 +763,32 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_radix_scatter(RadixArgs a) {
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
   const uint32_t tile = blockIdx.x;
-  if (tile >= T) return;
-  const uint32_t lane = lane_id(), warp = warp_id();
+  if (tile >= T || !radix_pass_active(a)) return;
+  const uint32_t lane = lane_id(), warp = warp_id(), tid = threadIdx.x;
   const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
-  if (!radix_pass_active(a)) {
-    // skipped pass: keep the ping-pong parity by copying (only pass-0 sources never skip)
-#pragma unroll
-    for (uint32_t k = 0; k < C_ROWS; k++) {
-      uint32_t i = base + k * 32 + lane;
-      if (i < n) {
-        a.keys_out[i] = a.keys_in[i];
-        a.vals_out[i] = a.vals_in[i];
-      }
-    }
-    return;
-  }
   __shared__ uint32_t s_cnt[KVG_WARPS][256];  // per-warp digit counts, then warp bases
-  __shared__ uint32_t s_bin[256];             // global base of each digit for this tile
+  __shared__ uint32_t s_start[256];           // tile-local exclusive start of each digit
+  __shared__ int32_t s_goff[256];             // global position of a digit's run minus its local start
   __shared__ uint32_t scratch[KVG_WARPS + 1];
+  __shared__ uint2 s_stage[C_TILE];           // pairs in tile-sorted order (16 KiB)
 #pragma unroll
-  for (uint32_t w = 0; w < KVG_WARPS; w++) s_cnt[w][threadIdx.x] = 0;
-  {
-    uint32_t total;
-    uint32_t e = block_excl_sum(a.bin_total[threadIdx.x], scratch, &total);  // syncs inside
-    s_bin[threadIdx.x] = e + a.tile_hist[(size_t)threadIdx.x * T + tile];
-  }
-  __syncthreads();
+  for (uint32_t w = 0; w < KVG_WARPS; w++) s_cnt[w][tid] = 0;
+  uint32_t total;
+  const uint32_t bin_base = block_excl_sum(a.bin_total[tid], scratch, &total);  // syncs inside
 
-  uint32_t key[C_ROWS], val[C_ROWS], rank[C_ROWS];
+  uint2 kv[C_ROWS];
+  uint32_t rank[C_ROWS];
 #pragma unroll
   for (uint32_t k = 0; k < C_ROWS; k++) {
     uint32_t i = base + k * 32 + lane;
-    bool ok = i < n;
-    key[k] = ok ? radix_key(a, i) : 0;
-    val[k] = ok ? (a.src == SRC_PAIRS ? a.vals_in[i] : i) : 0;
+    kv[k] = i < n ? radix_load(a, i) : make_uint2(0, 0);
   }
   // stable rank inside the warp: rows in order, lanes in order within a row
 #pragma unroll
   for (uint32_t k = 0; k < C_ROWS; k++) {
     uint32_t i = base + k * 32 + lane;
     bool ok = i < n;
-    uint32_t d = ok ? ((key[k] >> a.shift) & 0xffu) : (0x100u + lane);  // inactive lanes: unique
+    uint32_t d = ok ? ((kv[k].x >> a.shift) & 0xffu) : (0x100u + lane);  // inactive lanes: unique
     uint32_t peers = __match_any_sync(KVG_FULL, d);
     uint32_t leader = (uint32_t)__ffs(peers) - 1;
     uint32_t before = 0;
@@ -799,26 +801,110 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_radix_scatter(RadixArgs a) {
     __syncwarp();
   }
   __syncthreads();
-  {  // exclusive prefix over warps for digit == threadIdx.x
-    uint32_t run = 0;
+  uint32_t dtot = 0;
+  {  // digit == tid: exclusive prefix over warps, total of the digit in this tile
 #pragma unroll
     for (uint32_t w = 0; w < KVG_WARPS; w++) {
-      uint32_t c = s_cnt[w][threadIdx.x];
-      s_cnt[w][threadIdx.x] = run;
-      run += c;
+      uint32_t c = s_cnt[w][tid];
+      s_cnt[w][tid] = dtot;
+      dtot += c;
     }
   }
+  const uint32_t lstart = block_excl_sum(dtot, scratch, &total);  // syncs inside
+  s_start[tid] = lstart;
+  s_goff[tid] = (int32_t)(bin_base + a.tile_hist[(size_t)tid * T + tile]) - (int32_t)lstart;
   __syncthreads();
 #pragma unroll
   for (uint32_t k = 0; k < C_ROWS; k++) {
     uint32_t i = base + k * 32 + lane;
     if (i < n) {
-      uint32_t d = (key[k] >> a.shift) & 0xffu;
-      uint32_t pos = s_bin[d] + s_cnt[warp][d] + rank[k];
-      a.keys_out[pos] = key[k];
-      a.vals_out[pos] = val[k];
+      uint32_t d = (kv[k].x >> a.shift) & 0xffu;
+      s_stage[s_start[d] + s_cnt[warp][d] + rank[k]] = kv[k];
     }
   }
+  __syncthreads();
+  const uint32_t cnt = min(C_TILE, n - tile * C_TILE);
+  for (uint32_t j = tid; j < cnt; j += KVG_BLOCK) {
+    uint2 e = s_stage[j];
+    uint32_t d = (e.x >> a.shift) & 0xffu;
+    a.pairs_out[(uint32_t)(s_goff[d] + (int32_t)j)] = e;
+  }
+}
+
+// ---- final permutation + distinct keys of one ordering, look-back free --------------------------
+struct OrderFinalArgs {
+  const uint2* p0;            // ping-pong buffers of the radix passes
+  const uint2* p1;
+  const uint32_t* max_key;
+  int npass_max;
+  const uint32_t* n_ptr;
+  uint32_t* perm;             // [n] survivor indices in key order (stable)
+  uint32_t* tile_heads;       // [T] number of segment heads in each tile
+  const uint32_t* tile_off;   // [T+1] exclusive scan of tile_heads (emit only)
+  uint32_t* seg_key;
+  uint32_t* seg_off;          // [n_seg + 1]
+  const uint32_t* n_seg;      // total heads (emit only)
+};
+__device__ __forceinline__ const uint2* order_final_buf(const OrderFinalArgs& a) {
+  uint32_t mk = *a.max_key;
+  int np = 1;
+  while (np < a.npass_max && (mk >> (8 * np)) != 0) np++;
+  return ((np - 1) & 1) ? a.p1 : a.p0;
+}
+template <bool EMIT>
+__global__ void __launch_bounds__(KVG_BLOCK) k_order_final(OrderFinalArgs a) {
+  const uint32_t n = *a.n_ptr;
+  const uint32_t T = (n + C_TILE - 1) / C_TILE;
+  const uint32_t tile = blockIdx.x;
+  if (tile >= T) {
+    if (EMIT && n == 0 && tile == 0 && threadIdx.x == 0) a.seg_off[0] = 0;
+    return;
+  }
+  const uint2* pairs = order_final_buf(a);
+  const uint32_t lane = lane_id(), warp = warp_id();
+  const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
+  __shared__ uint32_t s_w[KVG_WARPS];
+  uint32_t bal[C_ROWS], key[C_ROWS], wtot = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < C_ROWS; k++) {
+    uint32_t i = base + k * 32 + lane;
+    bool head = false;
+    key[k] = 0;
+    if (i < n) {
+      uint2 e = pairs[i];
+      key[k] = e.x;
+      head = i == 0 || pairs[i - 1].x != e.x;
+      if (!EMIT) a.perm[i] = e.y;
+    }
+    bal[k] = __ballot_sync(KVG_FULL, head);
+    wtot += __popc(bal[k]);
+  }
+  if (lane == 0) s_w[warp] = wtot;
+  __syncthreads();
+  if (!EMIT) {
+    if (threadIdx.x == 0) {
+      uint32_t t = 0;
+#pragma unroll
+      for (uint32_t w = 0; w < KVG_WARPS; w++) t += s_w[w];
+      a.tile_heads[tile] = t;
+    }
+    return;
+  }
+  uint32_t off = a.tile_off[tile];
+#pragma unroll
+  for (uint32_t w = 0; w < KVG_WARPS; w++)
+    if (w < warp) off += s_w[w];
+#pragma unroll
+  for (uint32_t k = 0; k < C_ROWS; k++) {
+    uint32_t i = base + k * 32 + lane;
+    if ((bal[k] >> lane) & 1u) {
+      uint32_t pos = off + __popc(bal[k] & lanemask_lt());
+      a.seg_key[pos] = key[k];
+      a.seg_off[pos] = i;
+    }
+    off += __popc(bal[k]);
+  }
+  if (tile == T - 1 && threadIdx.x == 0) a.seg_off[*a.n_seg] = n;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1052,8 +1138,20 @@ __global__ void __launch_bounds__(THREADS) k_classify_ragged(Op op, uint32_t* __
 // CTA, coalesced, base by decoupled look-back (a few dozen CTAs at most, launched in order).
 __global__ void __launch_bounds__(KVG_BLOCK) k_tile_offsets(const uint32_t* __restrict__ tile_count,
                                                             const uint2* __restrict__ tile_max,
-                                                            uint32_t n_tiles, uint32_t* __restrict__ tile_off,
-                                                            ScanCtrl* ctrl, uint64_t* state, uint32_t epoch) {
+                                                            const uint32_t* n_items_ptr, uint32_t n_tiles_host,
+                                                            uint32_t* __restrict__ tile_off,
+                                                            uint32_t* total_out, ScanCtrl* ctrl,
+                                                            uint64_t* state, uint32_t epoch) {
+  // n_tiles is either known on the host or derived from a device-side item count (C_TILE items/tile)
+  const uint32_t n_tiles = n_items_ptr ? (*n_items_ptr + C_TILE - 1) / C_TILE : n_tiles_host;
+  if (blockIdx.x * C_TILE >= n_tiles) {
+    if (n_tiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+      *total_out = 0;
+      tile_off[0] = 0;
+    }
+    return;
+  }
+  const uint32_t last_chunk = (n_tiles - 1) / C_TILE;
   __shared__ uint32_t scratch[KVG_WARPS + 1];
   __shared__ uint32_t s_base;
   const uint32_t chunk = blockIdx.x;
@@ -1064,7 +1162,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_tile_offsets(const uint32_t* __re
     uint32_t i = i0 + k;
     v[k] = i < n_tiles ? tile_count[i] : 0;
     sum += v[k];
-    if (i < n_tiles) {
+    if (tile_max && i < n_tiles) {
       uint2 m = tile_max[i];
       mg = max(mg, m.x);
       md = max(md, m.y);
@@ -1076,8 +1174,8 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_tile_offsets(const uint32_t* __re
     uint32_t base = lookback_sum(state, chunk, total, epoch);
     if (lane_id() == 0) {
       s_base = base;
-      if (chunk == gridDim.x - 1) {
-        ctrl->n_surv = base + total;
+      if (chunk == last_chunk) {
+        *total_out = base + total;
         tile_off[n_tiles] = base + total;
       }
     }
