@@ -493,13 +493,7 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
   A.epoch = next_epoch();
 
   // table slots <- EMPTY, info <- {v_off = NONE, 0...}, ticket <- 0
-  {
-    size_t n64 = cap * n_files;
-    int grid = (int)((n64 / 4 + KVG_BLOCK - 1) / KVG_BLOCK);
-    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-    if (grid < 1) grid = 1;
-    LAUNCH("table_clear", k_fill64, grid, KVG_BLOCK, 0, ctx->tables.p, n64, P_EMPTY);
-  }
+  CK(cudaMemsetAsync(ctx->tables.p, 0xff, cap * n_files * sizeof(uint64_t), ctx->stream));  // P_EMPTY
   CK(cudaMemsetAsync(ctx->info.p, 0, sizeof(PciIdsInfo) * n_files, ctx->stream));
   CK(cudaMemset2DAsync(ctx->info.p, sizeof(PciIdsInfo), 0xff, sizeof(uint32_t), n_files, ctx->stream));
   int grid = ctx->parse_grid;
@@ -524,7 +518,7 @@ static int table_publish(kvg_ctx* ctx, const uint8_t* d_text, size_t len) {
     size_t sec = (size_t)ctx->h_info.sec_end - ctx->h_info.v_off;
     ENSURE(ctx->pool, sec + 16);
     CK(cudaMemsetAsync(ctx->pool.p, 0, sec + 16, ctx->stream));
-    int grid = (int)((sec + KVG_BLOCK - 1) / KVG_BLOCK);
+    int grid = (int)((sec + S_WIN - 1) / S_WIN);
     if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
     if (grid < 1) grid = 1;
     LAUNCH("pciids_sanitise", k_pciids_sanitise, grid, KVG_BLOCK, 0, d_text, (uint32_t)len,
@@ -604,8 +598,9 @@ int kvg_dev_pciids_parse(kvg_ctx* ctx, const void* d_text, size_t len, size_t st
   if (rc) return rc;
   size_t sec = ctx->h_pool.size();
   if (sec > 16) {
-    int grid = (int)((sec + KVG_BLOCK - 1) / KVG_BLOCK);
+    int grid = (int)((sec + S_WIN - 1) / S_WIN);
     if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    if (grid < 1) grid = 1;
     LAUNCH("pciids_sanitise", k_pciids_sanitise, grid, KVG_BLOCK, 0, (const uint8_t*)d_text,
            (uint32_t)len, ctx->info.p, ctx->pool.p);
   }
@@ -778,39 +773,84 @@ static int ensure_order(kvg_ctx* ctx, OrderBufs& o, size_t cap) {
   return KVG_OK;
 }
 
-// stable LSD radix ordering of the survivors by one field + segment heads.
-//   sort_idx selects bin_total rows in ScanCtrl; npass_max bounds the passes launched.
-static int enqueue_order(kvg_ctx* ctx, OrderBufs& o, size_t cap, int src, int sort_idx,
-                         int npass_max, uint32_t* d_max_key, uint32_t* d_n_seg, uint32_t* ticket) {
+}  // extern "C"
+// Both stable orderings of the survivor list — ordering 0 by device id / mdev type (<= 16 bits,
+// 2 passes), ordering 1 by iommu group / parent (32 bits, up to 4 passes) — share their launches:
+// grid.y = 2 while both have a pass, grid.y = 1 (ordering 1 only, passed in slot 0) afterwards.
+static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1) {
+  int rc = ensure_order(ctx, ctx->ord_dev, cap);
+  if (rc) return rc;
+  rc = ensure_order(ctx, ctx->ord_grp, cap);
+  if (rc) return rc;
   size_t T = (cap + C_TILE - 1) / C_TILE;
   if (T == 0) T = 1;
-  ENSURE(ctx->tile_hist, 256 * T);
-  const uint2* pin = nullptr;
-  for (int p = 0; p < npass_max; p++) {
+  ENSURE(ctx->tile_hist, 2 * 256 * T);
+  ScanCtrl* c = ctx->ctrl.p;
+  OrderBufs* ob[2] = {&ctx->ord_dev, &ctx->ord_grp};
+  uint32_t* maxk[2] = {&c->max_devkey, &c->max_group};
+  const int npass[2] = {2, 4};
+  const int srcs[2] = {src0, src1};
+  auto fill = [&](int ord, int p) {
     RadixArgs a;
-    a.n_ptr = &ctx->ctrl.p->n_surv;
-    a.max_key = d_max_key;
+    a.n_ptr = &c->n_surv;
+    a.max_key = maxk[ord];
     a.src_records = ctx->surv.p;
-    a.pairs_in = pin;
-    a.pairs_out = (p & 1) ? o.p1.p : o.p0.p;
-    a.tile_hist = ctx->tile_hist.p;
-    a.bin_total = ctx->ctrl.p->bin_total[sort_idx][p];
-    a.shift = 8 * p;
-    a.src = p == 0 ? src : SRC_PAIRS;
-    LAUNCH("radix_hist", k_radix_hist, (int)T, KVG_BLOCK, 0, a);
-    LAUNCH("radix_tilescan", k_radix_tilescan, 256, KVG_BLOCK, 0, a);
-    LAUNCH("radix_scatter", k_radix_scatter, (int)T, KVG_BLOCK, 0, a);
-    pin = a.pairs_out;
+    a.pairs_in = p == 0 ? nullptr : ((p & 1) ? ob[ord]->p0.p : ob[ord]->p1.p);
+    a.pairs_out = (p & 1) ? ob[ord]->p1.p : ob[ord]->p0.p;
+    a.tile_hist = ctx->tile_hist.p + (size_t)ord * 256 * T;
+    a.bin_total = c->bin_total[ord][p];
+    a.shift = p < npass[ord] ? 8u * (uint32_t)p : 0xffu;
+    a.src = p == 0 ? srcs[ord] : SRC_PAIRS;
+    return a;
+  };
+  for (int p = 0; p < 4; p++) {
+    RadixArgs2 aa;
+    dim3 grid((unsigned)T, p < 2 ? 2 : 1);
+    if (p < 2) {
+      aa.o[0] = fill(0, p);
+      aa.o[1] = fill(1, p);
+    } else {
+      aa.o[0] = fill(1, p);
+      aa.o[1] = aa.o[0];
+    }
+    dim3 sgrid(256, grid.y);
+    LAUNCH("radix_hist", k_radix_hist, grid, KVG_BLOCK, 0, aa);
+    LAUNCH("radix_tilescan", k_radix_tilescan, sgrid, KVG_BLOCK, 0, aa);
+    LAUNCH("radix_scatter", k_radix_scatter, grid, KVG_BLOCK, 0, aa);
   }
-  // heads of the final key array; the number of executed passes is device-side knowledge
-  // (max key), the heads kernel is launched once per possible final buffer and the wrong one
-  // exits immediately (its n_ptr reads 0 through the selector below)
-  (void)d_n_seg;
-  (void)ticket;
-  return check_launch(ctx, "radix order");
+  // final permutation + distinct keys of both orderings: count heads per tile, scan, emit
+  OrderFinalArgs2 ff;
+  TileOffsetsArgs2 tt;
+  uint32_t* nseg[2] = {&c->n_dev_keys, &c->n_groups};
+  for (int ord = 0; ord < 2; ord++) {
+    OrderFinalArgs& a = ff.o[ord];
+    a.p0 = ob[ord]->p0.p;
+    a.p1 = ob[ord]->p1.p;
+    a.max_key = maxk[ord];
+    a.npass_max = npass[ord];
+    a.n_ptr = &c->n_surv;
+    a.perm = ob[ord]->perm.p;
+    a.tile_heads = ob[ord]->tile_heads.p;
+    a.tile_off = ob[ord]->tile_off.p;
+    a.seg_key = ob[ord]->seg_key.p;
+    a.seg_off = ob[ord]->seg_off.p;
+    a.n_seg = nseg[ord];
+    TileOffsetsArgs& t = tt.o[ord];
+    t.tile_count = ob[ord]->tile_heads.p;
+    t.tile_max = nullptr;
+    t.n_items_ptr = &c->n_surv;
+    t.n_tiles_host = 0;
+    t.tile_off = ob[ord]->tile_off.p;
+    t.total_out = nseg[ord];
+    t.state = ob[ord]->heads_state.p;
+  }
+  dim3 fgrid((unsigned)T, 2);
+  LAUNCH("order_count", k_order_final<false>, fgrid, KVG_BLOCK, 0, ff);
+  dim3 ogrid((unsigned)((T + C_TILE - 1) / C_TILE), 2);
+  LAUNCH("tile_offsets", k_tile_offsets, ogrid, KVG_BLOCK, 0, tt, c, next_epoch());
+  LAUNCH("order_emit", k_order_final<true>, fgrid, KVG_BLOCK, 0, ff);
+  return check_launch(ctx, "orderings");
 }
-
-}  // extern "C"
 
 static int active_passes(uint32_t max_key, int npass_max) {
   int np = 1;
@@ -818,47 +858,8 @@ static int active_passes(uint32_t max_key, int npass_max) {
   return np;
 }
 
-// final permutation + distinct keys of one ordering: count heads per tile, scan, emit
-static int enqueue_heads(kvg_ctx* ctx, OrderBufs& o, size_t cap, int npass_max, uint32_t* d_max_key,
-                         uint32_t* d_n_seg, uint32_t* ticket) {
-  (void)ticket;
-  size_t T = (cap + C_TILE - 1) / C_TILE;
-  if (T == 0) T = 1;
-  OrderFinalArgs a;
-  a.p0 = o.p0.p;
-  a.p1 = o.p1.p;
-  a.max_key = d_max_key;
-  a.npass_max = npass_max;
-  a.n_ptr = &ctx->ctrl.p->n_surv;
-  a.perm = o.perm.p;
-  a.tile_heads = o.tile_heads.p;
-  a.tile_off = o.tile_off.p;
-  a.seg_key = o.seg_key.p;
-  a.seg_off = o.seg_off.p;
-  a.n_seg = d_n_seg;
-  LAUNCH("order_count", k_order_final<false>, (unsigned)T, KVG_BLOCK, 0, a);
-  const unsigned chunks = (unsigned)((T + C_TILE - 1) / C_TILE);
-  LAUNCH("tile_offsets", k_tile_offsets, chunks, KVG_BLOCK, 0, o.tile_heads.p, (const uint2*)nullptr,
-         &ctx->ctrl.p->n_surv, 0u, o.tile_off.p, d_n_seg, ctx->ctrl.p, o.heads_state.p, next_epoch());
-  LAUNCH("order_emit", k_order_final<true>, (unsigned)T, KVG_BLOCK, 0, a);
-  return check_launch(ctx, "order finalize");
-}
-
-// classify + both orderings of `n` device-resident PCI records (or of an already-gathered
-// survivor list when n_records == 0 and surv/ctrl were filled by the sharded path)
 static int enqueue_pci_orderings(kvg_ctx* ctx, size_t surv_cap) {
-  int rc = ensure_order(ctx, ctx->ord_dev, surv_cap);
-  if (rc) return rc;
-  rc = ensure_order(ctx, ctx->ord_grp, surv_cap);
-  if (rc) return rc;
-  ScanCtrl* c = ctx->ctrl.p;
-  rc = enqueue_order(ctx, ctx->ord_dev, surv_cap, SRC_PCI_DEVICE, 0, 2, &c->max_devkey, &c->n_dev_keys, &c->ticket[1]);
-  if (rc) return rc;
-  rc = enqueue_heads(ctx, ctx->ord_dev, surv_cap, 2, &c->max_devkey, &c->n_dev_keys, &c->ticket[1]);
-  if (rc) return rc;
-  rc = enqueue_order(ctx, ctx->ord_grp, surv_cap, SRC_PCI_GROUP, 1, 4, &c->max_group, &c->n_groups, &c->ticket[2]);
-  if (rc) return rc;
-  return enqueue_heads(ctx, ctx->ord_grp, surv_cap, 4, &c->max_group, &c->n_groups, &c->ticket[2]);
+  return enqueue_orderings(ctx, surv_cap, SRC_PCI_DEVICE, SRC_PCI_GROUP);
 }
 
 static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d_out) {
@@ -892,9 +893,13 @@ static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d
     op.out = (kvg_pci_surv*)ctx->ragged.p;
     LAUNCH("classify_compact", (k_classify_ragged<PciClassifyOp, T, R>), (unsigned)tiles, T, 0, op,
            ctx->tile_count.p, ctx->tile_max.p);
-    LAUNCH("tile_offsets", k_tile_offsets, chunks, KVG_BLOCK, 0, ctx->tile_count.p, ctx->tile_max.p,
-           (const uint32_t*)nullptr, (uint32_t)tiles, ctx->tile_off.p, &ctx->ctrl.p->n_surv, ctx->ctrl.p,
-           ctx->offs_state.p, next_epoch());
+    {
+      TileOffsetsArgs2 tt;
+      tt.o[0] = {ctx->tile_count.p, ctx->tile_max.p, nullptr, (uint32_t)tiles, ctx->tile_off.p,
+                 &ctx->ctrl.p->n_surv, ctx->offs_state.p};
+      tt.o[1] = tt.o[0];
+      LAUNCH("tile_offsets", k_tile_offsets, chunks, KVG_BLOCK, 0, tt, ctx->ctrl.p, next_epoch());
+    }
     LAUNCH("pack_survivors", k_pack_survivors<1>, (unsigned)tiles, 128, 0, ctx->ragged.p, ctx->tile_off.p,
            (uint32_t)(T * R), d_out);
   } else if (classify_variant() >= 2) {  // one tile per CTA with look-back
@@ -1218,27 +1223,20 @@ int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type
       op.out = ctx->ragged.p;
       LAUNCH("mdev_classify_compact", (k_classify_ragged<MdevClassifyOp, T, R>), (unsigned)tiles, T, 0, op,
              ctx->tile_count.p, ctx->tile_max.p);
-      LAUNCH("tile_offsets", k_tile_offsets, chunks, KVG_BLOCK, 0, ctx->tile_count.p, ctx->tile_max.p,
-             (const uint32_t*)nullptr, (uint32_t)tiles, ctx->tile_off.p, &ctx->ctrl.p->n_surv, ctx->ctrl.p,
-             ctx->offs_state.p, next_epoch());
+      {
+        TileOffsetsArgs2 tt;
+        tt.o[0] = {ctx->tile_count.p, ctx->tile_max.p, nullptr, (uint32_t)tiles, ctx->tile_off.p,
+                   &ctx->ctrl.p->n_surv, ctx->offs_state.p};
+        tt.o[1] = tt.o[0];
+        LAUNCH("tile_offsets", k_tile_offsets, chunks, KVG_BLOCK, 0, tt, ctx->ctrl.p, next_epoch());
+      }
       LAUNCH("pack_survivors", k_pack_survivors<2>, (unsigned)tiles, 128, 0, ctx->ragged.p, ctx->tile_off.p,
              (uint32_t)(T * R), dense);
     }
   }
   rc = check_launch(ctx, "mdev classify");
   if (rc) return rc;
-  rc = ensure_order(ctx, ctx->ord_dev, n);
-  if (rc) return rc;
-  rc = ensure_order(ctx, ctx->ord_grp, n);
-  if (rc) return rc;
-  ScanCtrl* c = ctx->ctrl.p;
-  rc = enqueue_order(ctx, ctx->ord_dev, n, SRC_MDEV_TYPE, 0, 2, &c->max_devkey, &c->n_dev_keys, &c->ticket[1]);
-  if (rc) return rc;
-  rc = enqueue_heads(ctx, ctx->ord_dev, n, 2, &c->max_devkey, &c->n_dev_keys, &c->ticket[1]);
-  if (rc) return rc;
-  rc = enqueue_order(ctx, ctx->ord_grp, n, SRC_MDEV_PARENT, 1, 4, &c->max_group, &c->n_groups, &c->ticket[2]);
-  if (rc) return rc;
-  rc = enqueue_heads(ctx, ctx->ord_grp, n, 4, &c->max_group, &c->n_groups, &c->ticket[2]);
+  rc = enqueue_orderings(ctx, n, SRC_MDEV_TYPE, SRC_MDEV_PARENT);
   if (rc) return rc;
   ctx->last_n = n;
   ctx->last_total = n;

@@ -699,7 +699,13 @@ struct RadixArgs {
   int src;                    // where pass-0 keys come from
 };
 
+// both orderings (device id, iommu group) run their passes in the SAME launches: blockIdx.y
+// selects the ordering; an ordering that has no such pass carries shift == 0xff
+struct RadixArgs2 {
+  RadixArgs o[2];
+};
 __device__ __forceinline__ bool radix_pass_active(const RadixArgs& a) {
+  if (a.shift >= 32) return false;
   return a.shift == 0 || (*a.max_key >> a.shift) != 0;
 }
 __device__ __forceinline__ uint2 radix_load(const RadixArgs& a, uint32_t i) {
@@ -716,7 +722,8 @@ __device__ __forceinline__ uint2 radix_load(const RadixArgs& a, uint32_t i) {
   }
 }
 
-__global__ void __launch_bounds__(KVG_BLOCK) k_radix_hist(RadixArgs a) {
+__global__ void __launch_bounds__(KVG_BLOCK) k_radix_hist(RadixArgs2 aa) {
+  const RadixArgs& a = aa.o[blockIdx.y];
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
   const uint32_t tile = blockIdx.x;
@@ -726,14 +733,15 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_radix_hist(RadixArgs a) {
   __syncthreads();
   const uint32_t lane = lane_id();
   const uint32_t base = tile * C_TILE + warp_id() * C_WARP_ITEMS;
+  uint32_t d[C_ROWS];
 #pragma unroll
-  for (uint32_t k = 0; k < C_ROWS; k++) {
+  for (uint32_t k = 0; k < C_ROWS; k++) {  // all loads in flight before the first shared atomic
     uint32_t i = base + k * 32 + lane;
-    bool ok = i < n;
-    uint32_t d = ok ? ((radix_load(a, i).x >> a.shift) & 0xffu) : (0x100u + lane);
-    uint32_t peers = __match_any_sync(KVG_FULL, d);
-    if (ok && lane == (uint32_t)__ffs(peers) - 1) atomicAdd(&h[d], (uint32_t)__popc(peers));
+    d[k] = i < n ? ((radix_load(a, i).x >> a.shift) & 0xffu) : 0x100u;
   }
+#pragma unroll
+  for (uint32_t k = 0; k < C_ROWS; k++)
+    if (d[k] < 0x100u) atomicAdd(&h[d[k]], 1u);
   __syncthreads();
   uint32_t c = h[threadIdx.x];
   a.tile_hist[(size_t)threadIdx.x * T + tile] = c;
@@ -741,7 +749,8 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_radix_hist(RadixArgs a) {
 }
 
 // one CTA per digit: exclusive scan of that digit's per-tile counts, in place
-__global__ void __launch_bounds__(KVG_BLOCK) k_radix_tilescan(RadixArgs a) {
+__global__ void __launch_bounds__(KVG_BLOCK) k_radix_tilescan(RadixArgs2 aa) {
+  const RadixArgs& a = aa.o[blockIdx.y];
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
   if (T == 0 || !radix_pass_active(a)) return;
@@ -759,7 +768,8 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_radix_tilescan(RadixArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(KVG_BLOCK) k_radix_scatter(RadixArgs a) {
+__global__ void __launch_bounds__(KVG_BLOCK) k_radix_scatter(RadixArgs2 aa) {
+  const RadixArgs& a = aa.o[blockIdx.y];
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
   const uint32_t tile = blockIdx.x;
@@ -851,8 +861,12 @@ __device__ __forceinline__ const uint2* order_final_buf(const OrderFinalArgs& a)
   while (np < a.npass_max && (mk >> (8 * np)) != 0) np++;
   return ((np - 1) & 1) ? a.p1 : a.p0;
 }
+struct OrderFinalArgs2 {
+  OrderFinalArgs o[2];
+};
 template <bool EMIT>
-__global__ void __launch_bounds__(KVG_BLOCK) k_order_final(OrderFinalArgs a) {
+__global__ void __launch_bounds__(KVG_BLOCK) k_order_final(OrderFinalArgs2 aa) {
+  const OrderFinalArgs& a = aa.o[blockIdx.y];
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
   const uint32_t tile = blockIdx.x;
@@ -1136,12 +1150,28 @@ __global__ void __launch_bounds__(THREADS) k_classify_ragged(Op op, uint32_t* __
 // exclusive scan of tile_count[0..n_tiles) -> tile_off[0..n_tiles], total -> ctrl->n_surv, and the
 // reduction of the per-tile maxima -> ctrl->max_group / max_devkey.  Chained scan: 2048 counts per
 // CTA, coalesced, base by decoupled look-back (a few dozen CTAs at most, launched in order).
-__global__ void __launch_bounds__(KVG_BLOCK) k_tile_offsets(const uint32_t* __restrict__ tile_count,
-                                                            const uint2* __restrict__ tile_max,
-                                                            const uint32_t* n_items_ptr, uint32_t n_tiles_host,
-                                                            uint32_t* __restrict__ tile_off,
-                                                            uint32_t* total_out, ScanCtrl* ctrl,
-                                                            uint64_t* state, uint32_t epoch) {
+struct TileOffsetsArgs {
+  const uint32_t* tile_count;
+  const uint2* tile_max;        // optional per-tile maxima to reduce into ctrl
+  const uint32_t* n_items_ptr;  // device-side item count (C_TILE items per tile) or NULL
+  uint32_t n_tiles_host;
+  uint32_t* tile_off;
+  uint32_t* total_out;
+  uint64_t* state;
+};
+struct TileOffsetsArgs2 {
+  TileOffsetsArgs o[2];
+};
+__global__ void __launch_bounds__(KVG_BLOCK) k_tile_offsets(TileOffsetsArgs2 aa, ScanCtrl* ctrl,
+                                                            uint32_t epoch) {
+  const TileOffsetsArgs& A = aa.o[blockIdx.y];
+  const uint32_t* __restrict__ tile_count = A.tile_count;
+  const uint2* __restrict__ tile_max = A.tile_max;
+  const uint32_t* n_items_ptr = A.n_items_ptr;
+  const uint32_t n_tiles_host = A.n_tiles_host;
+  uint32_t* __restrict__ tile_off = A.tile_off;
+  uint32_t* total_out = A.total_out;
+  uint64_t* state = A.state;
   // n_tiles is either known on the host or derived from a device-side item count (C_TILE items/tile)
   const uint32_t n_tiles = n_items_ptr ? (*n_items_ptr + C_TILE - 1) / C_TILE : n_tiles_host;
   if (blockIdx.x * C_TILE >= n_tiles) {
