@@ -559,11 +559,11 @@ __device__ uint32_t d_sanitise_name(const uint8_t* s, uint32_t n, uint8_t* out, 
   return o;
 }
 
-// K2: each CTA stages a 2 KiB window of the NVIDIA section (+ 512 B so that an ordinary line is
-// fully inside) in shared memory with coalesced loads; the thread sitting on the first byte of a
+// K2: each CTA stages a 256-byte window of the NVIDIA section (+ 256 B so that an ordinary line
+// is fully inside) in shared memory with coalesced loads; the thread sitting on the first byte of a
 // candidate line ("\t" + 4 lower-hex) sanitises it into pool[off - V] = u16 len + bytes.  Lines
-// running past the staged bytes (pathological: > 512 B) are read from global memory instead.
-constexpr uint32_t S_WIN = 2048, S_HALO = 512;
+// running past the staged bytes (> 256 B) are read from global memory instead.
+constexpr uint32_t S_WIN = 256, S_HALO = 256;  // one byte position per thread: line work is not serialised
 __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_sanitise(const uint8_t* __restrict__ text,
                                                                uint32_t len,
                                                                const PciIdsInfo* __restrict__ info,

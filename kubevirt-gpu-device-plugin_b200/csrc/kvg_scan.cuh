@@ -723,7 +723,7 @@ __device__ __forceinline__ uint2 radix_load(const RadixArgs& a, uint32_t i) {
 }
 
 __global__ void __launch_bounds__(KVG_BLOCK) k_radix_hist(RadixArgs2 aa) {
-  const RadixArgs& a = aa.o[blockIdx.y];
+  const RadixArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
   const uint32_t tile = blockIdx.x;
@@ -750,7 +750,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_radix_hist(RadixArgs2 aa) {
 
 // one CTA per digit: exclusive scan of that digit's per-tile counts, in place
 __global__ void __launch_bounds__(KVG_BLOCK) k_radix_tilescan(RadixArgs2 aa) {
-  const RadixArgs& a = aa.o[blockIdx.y];
+  const RadixArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
   if (T == 0 || !radix_pass_active(a)) return;
@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_radix_tilescan(RadixArgs2 aa) {
 }
 
 __global__ void __launch_bounds__(KVG_BLOCK) k_radix_scatter(RadixArgs2 aa) {
-  const RadixArgs& a = aa.o[blockIdx.y];
+  const RadixArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
   const uint32_t tile = blockIdx.x;
@@ -866,7 +866,7 @@ struct OrderFinalArgs2 {
 };
 template <bool EMIT>
 __global__ void __launch_bounds__(KVG_BLOCK) k_order_final(OrderFinalArgs2 aa) {
-  const OrderFinalArgs& a = aa.o[blockIdx.y];
+  const OrderFinalArgs a = blockIdx.y ? aa.o[1] : aa.o[0];
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
   const uint32_t tile = blockIdx.x;
@@ -1164,7 +1164,7 @@ struct TileOffsetsArgs2 {
 };
 __global__ void __launch_bounds__(KVG_BLOCK) k_tile_offsets(TileOffsetsArgs2 aa, ScanCtrl* ctrl,
                                                             uint32_t epoch) {
-  const TileOffsetsArgs& A = aa.o[blockIdx.y];
+  const TileOffsetsArgs A = blockIdx.y ? aa.o[1] : aa.o[0];
   const uint32_t* __restrict__ tile_count = A.tile_count;
   const uint2* __restrict__ tile_max = A.tile_max;
   const uint32_t* n_items_ptr = A.n_items_ptr;
