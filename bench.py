@@ -270,16 +270,35 @@ def main():
     kavg = {k: sum(v) / len(v) for k, v in per.items()}          # ms per launch
     S, KD, G = ctx.dev_scan_pci_count()
     info = ctx.pciids_info()
-    algo = {"classify_compact": 16 * n + 16 * (S if not sharded else S // world),
-            "pciids_parse": len(text) + 8 * info["n_entries"]}
-    dominant = max(("classify_compact", "pciids_parse"), key=lambda k: ksum.get(k, 0.0))
+    S_local = S if not sharded else S // world   # survivors this rank classified (its shard)
+    grp_passes = max(1, (int(gbits) + 7) // 8)
+    # ALGORITHMIC bytes per step of every kernel family (DESIGN.md "Kernels"): what must move.
+    algo = {
+        "pciids_parse": len(text) + 8 * info["n_entries"],
+        "classify_compact": 16 * n + 16 * S_local,            # every record read, every survivor written
+        "pack_survivors": 32 * S_local,                       # ragged -> dense
+        "radix_hist": 4 * S * 2 + 8 * S * (1 + (grp_passes - 1)),     # pass 0 keys, later passes pairs
+        "radix_scatter": 16 * S * (2 + grp_passes),           # 8 B read + 8 B written per pair per pass
+        "order_count": (8 * S + 4 * S) * 2,                   # pairs read, permutation written
+        "order_emit": 8 * S * 2 + 8 * (KD + G),
+    }
+    main_kernels = [k for k in algo if k in ksum]
+    dominant = max(main_kernels, key=lambda k: ksum.get(k, 0.0))
+    step_ms = sum(ksum.values())
 
-    def roof(name, nbytes, ms):
+    def roof(name, nbytes, ms, launches_per_step=1):
         ach = nbytes / (ms * 1e-3) / 1e9 if ms else 0.0
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": None, "algorithmic_bytes": nbytes,
-                "avg_launch_ms": ms, "peak_source": peak_src}
-    roofline = roof(dominant, algo[dominant], kavg.get(dominant, 0.0))
+                "avg_launch_ms": ms / launches_per_step, "peak_source": peak_src}
+    nl = {k: len(v) / passes for k, v in per.items()}     # launches per step
+    roofline = roof(dominant, algo[dominant], ksum[dominant], nl[dominant])
+    roofline["share_of_step"] = ksum[dominant] / step_ms
+    roofline["note"] = ("bytes and time are per STEP for the whole kernel family (all its launches); "
+                        "at this 1M-record config every kernel is latency-bound — see roofline_hbm_bound")
+    kernel_rooflines = {k: {"ms_per_step": ksum[k], "share": ksum[k] / step_ms,
+                            "GBps": algo[k] / (ksum[k] * 1e-3) / 1e9, "frac": algo[k] / (ksum[k] * 1e-3) / 1e9 / hbm_peak}
+                        for k in main_kernels}
 
     # ---- HBM-bound legs (inputs larger than L2): the >=70 % target is judged here
     roofline_big = {}
@@ -418,6 +437,7 @@ def main():
                        "wall_s_timed_loop_incl_flush": t_wall},
             "pciids_parse_GBps": len(text) / (kavg.get("pciids_parse", 0) * 1e-3) / 1e9 if kavg.get("pciids_parse") else None,
             "roofline": roofline,
+            "kernel_rooflines": kernel_rooflines,
             "roofline_hbm_bound": roofline_big,
             "kernel_ms_per_step": ksum,
             "cpu_baseline": cpu,

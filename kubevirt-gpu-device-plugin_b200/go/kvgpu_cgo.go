@@ -1,0 +1,309 @@
+//go:build cgo
+
+// Package device_plugin — cgo shim that routes the reference's discovery scan through libkvgpu.so.
+//
+// SOURCE ONLY: this image has no Go toolchain, so this file has never been compiled here.  It is
+// the binding a maintainer of NVIDIA/kubevirt-gpu-device-plugin drops into pkg/device_plugin/
+// next to device_plugin.go (see INTEGRATION.md).  It contains marshalling only — every decision
+// (filter, join, bucketing, name sanitising) is made by the CUDA library behind include/kvgpu.h.
+//
+// It replaces the BODIES of three functions and keeps their signatures and side effects:
+//
+//	createIommuDeviceMap()            device_plugin.go:187  -> createIommuDeviceMapGPU()
+//	createVgpuIDMap()                 device_plugin.go:255  -> createVgpuIDMapGPU()
+//	getDeviceName(deviceID string)    device_plugin.go:371  -> getDeviceNameGPU(deviceID)
+//
+// The five sysfs readers stay the reference's own package variables (readIDFromFile, readLink,
+// readNUMANode, readVgpuIDFromFile is replaced by a raw read, readGpuIDForVgpu :80-85), so the
+// existing Ginkgo fakes keep working unchanged.
+package device_plugin
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/.. -lkvgpu -Wl,-rpath,${SRCDIR}/..
+#include <stdlib.h>
+#include "kvgpu.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"log"
+	"os"
+	"path/filepath"
+	"sort"
+	"strconv"
+	"strings"
+	"unsafe"
+)
+
+var kvgCtx *C.kvg_ctx
+var kvgLoadedPath string
+
+// kvgEnsure creates the context once and (re)loads the pci.ids table when the path changed.
+// A CUDA failure is reported like the reference reports a failed walk: log + empty maps.
+func kvgEnsure() error {
+	if kvgCtx == nil {
+		if rc := C.kvg_ctx_create(0, &kvgCtx); rc != C.KVG_OK {
+			return fmt.Errorf("kvg_ctx_create: %d %s", int(rc), C.GoString(C.kvg_last_error(nil)))
+		}
+	}
+	if kvgLoadedPath != pciIdsFilePath {
+		data, err := os.ReadFile(pciIdsFilePath)
+		if err != nil {
+			log.Printf("Error opening pci ids file %s", pciIdsFilePath) // :375
+			data = nil                                                  // empty table: every name is ""
+		}
+		var p *C.uint8_t
+		if len(data) > 0 {
+			p = (*C.uint8_t)(unsafe.Pointer(&data[0]))
+		}
+		if rc := C.kvg_pciids_load(kvgCtx, p, C.size_t(len(data))); rc != C.KVG_OK {
+			return fmt.Errorf("kvg_pciids_load: %s", C.GoString(C.kvg_last_error(kvgCtx)))
+		}
+		kvgLoadedPath = pciIdsFilePath
+	}
+	return nil
+}
+
+func getDeviceNameGPU(deviceID string) string {
+	if err := kvgEnsure(); err != nil {
+		log.Printf("Error: %v", err)
+		return ""
+	}
+	out := make([]byte, 1<<17)
+	var n C.size_t
+	key := C.CString(deviceID)
+	defer C.free(unsafe.Pointer(key))
+	rc := C.kvg_name_lookup(kvgCtx, key, C.size_t(len(deviceID)), (*C.char)(unsafe.Pointer(&out[0])),
+		C.size_t(len(out)), &n)
+	if rc != C.KVG_OK {
+		return ""
+	}
+	return string(out[:n])
+}
+
+func parseHex4(s string) (uint16, bool) {
+	if len(s) != 4 {
+		return 0, false
+	}
+	v, err := strconv.ParseUint(s, 16, 16)
+	if err != nil || strings.ToLower(s) != s {
+		return 0, false
+	}
+	return uint16(v), true
+}
+
+// createIommuDeviceMapGPU: same walk, same readers, same short-circuit order as :192-246, but the
+// entries are only RECORDED (read failures become flag bits); the GPU filters, joins and buckets.
+func createIommuDeviceMapGPU() {
+	iommuMap = make(map[string][]NvidiaGpuDevice)
+	deviceMap = make(map[string][]NvidiaGpuDevice)
+	bdfToIommuMap = make(map[string]string)
+	var names []string
+	var recs []C.kvg_pci_rec
+	groupIDs := map[string]uint32{}
+	var groupNames []string
+	filepath.Walk(basePath, func(path string, info os.FileInfo, err error) error {
+		if err != nil {
+			log.Printf("Error accessing file path %q: %v\n", path, err)
+			return err
+		}
+		if info.IsDir() {
+			return nil
+		}
+		var r C.kvg_pci_rec
+		r.addr = C.uint32_t(len(names)) // index mode: names[] maps the handle back
+		r.vendor = 0xffff
+		vendorID, err := readIDFromFile(basePath, info.Name(), "vendor")
+		if err != nil {
+			r.flags |= C.KVG_PF_VENDOR_ERR
+		} else if v, ok := parseHex4(vendorID); ok {
+			r.vendor = C.uint16_t(v)
+		}
+		if err == nil && vendorID == nvidiaVendorID {
+			driver, err := readLink(basePath, info.Name(), "driver")
+			switch {
+			case err != nil:
+				r.flags |= C.KVG_PF_DRIVER_ERR
+			case driver == "vfio-pci":
+				r.driver = C.KVG_DRV_VFIO_PCI
+			case driver == "nvgrace_gpu_vfio_pci":
+				r.driver = C.KVG_DRV_NVGRACE
+			default:
+				r.driver = C.KVG_DRV_OTHER
+			}
+			if err == nil && isSupportedVfioDriver(driver) {
+				iommuGroup, err := readLink(basePath, info.Name(), "iommu_group")
+				if err != nil {
+					r.flags |= C.KVG_PF_IOMMU_ERR
+				} else {
+					id, ok := groupIDs[iommuGroup]
+					if !ok {
+						id = uint32(len(groupNames))
+						groupIDs[iommuGroup] = id
+						groupNames = append(groupNames, iommuGroup)
+					}
+					r.iommu_group = C.uint32_t(id)
+					numaNode, err := readNUMANode(basePath, info.Name())
+					if err != nil {
+						r.flags |= C.KVG_PF_NUMA_ERR
+					}
+					r.numa = C.int16_t(numaNode)
+					deviceID, err := readIDFromFile(basePath, info.Name(), "device")
+					if err != nil {
+						r.flags |= C.KVG_PF_DEVICE_ERR
+					} else if d, ok := parseHex4(deviceID); ok {
+						r.device = C.uint16_t(d)
+					} else {
+						log.Printf("device id %q of %s is not 4 lower-case hex digits", deviceID, info.Name())
+						r.flags |= C.KVG_PF_DEVICE_ERR
+					}
+				}
+			}
+		}
+		names = append(names, info.Name())
+		recs = append(recs, r)
+		return nil
+	})
+	if err := kvgEnsure(); err != nil {
+		log.Printf("Error: %v", err) // maps stay empty, like a failed walk (:193-196)
+		return
+	}
+	var res *C.kvg_pci_result
+	var p *C.kvg_pci_rec
+	if len(recs) > 0 {
+		p = &recs[0]
+	}
+	if rc := C.kvg_scan_pci(kvgCtx, p, C.size_t(len(recs)), &res); rc != C.KVG_OK {
+		log.Printf("Error: kvg_scan_pci: %s", C.GoString(C.kvg_last_error(kvgCtx)))
+		return
+	}
+	defer C.kvg_result_free(unsafe.Pointer(res))
+	S := int(res.n_survivors)
+	surv := unsafe.Slice(res.survivors, S)
+	dev := func(i uint32) NvidiaGpuDevice {
+		return NvidiaGpuDevice{addr: names[surv[i].addr], numaNode: int64(surv[i].numa)}
+	}
+	devKeys := unsafe.Slice(res.dev_keys, int(res.n_dev_keys))
+	devOff := unsafe.Slice(res.dev_off, int(res.n_dev_keys)+1)
+	devPerm := unsafe.Slice(res.dev_perm, S)
+	for k := range devKeys {
+		key := fmt.Sprintf("%04x", uint16(devKeys[k]))
+		for _, i := range devPerm[devOff[k]:devOff[k+1]] {
+			deviceMap[key] = append(deviceMap[key], dev(uint32(i)))
+		}
+	}
+	grpKeys := unsafe.Slice(res.grp_keys, int(res.n_groups))
+	grpOff := unsafe.Slice(res.grp_off, int(res.n_groups)+1)
+	grpPerm := unsafe.Slice(res.grp_perm, S)
+	for k := range grpKeys {
+		g := groupNames[grpKeys[k]]
+		for _, i := range grpPerm[grpOff[k]:grpOff[k+1]] {
+			iommuMap[g] = append(iommuMap[g], dev(uint32(i)))
+		}
+	}
+	for i := 0; i < S; i++ {
+		bdfToIommuMap[names[surv[i].addr]] = groupNames[surv[i].iommu_group]
+	}
+}
+
+// createVgpuIDMapGPU: :259-290 with the label rule (:341-342) and both group-bys on the GPU.
+func createVgpuIDMapGPU() {
+	vGpuMap = make(map[string][]NvidiaGpuDevice)
+	gpuVgpuMap = make(map[string][]string)
+	var names, parentNames []string
+	var recs []C.kvg_mdev_rec
+	typeIDs := map[string]uint16{}
+	var rawTypes [][]byte
+	parentIDs := map[string]uint32{}
+	filepath.Walk(vGpuBasePath, func(path string, info os.FileInfo, err error) error {
+		if err != nil {
+			return err
+		}
+		if info.IsDir() {
+			return nil
+		}
+		var r C.kvg_mdev_rec
+		idx := uint32(len(names))
+		r.uuid[0], r.uuid[1], r.uuid[2], r.uuid[3] = C.uint8_t(idx>>24), C.uint8_t(idx>>16), C.uint8_t(idx>>8), C.uint8_t(idx)
+		raw, err := os.ReadFile(filepath.Join(vGpuBasePath, info.Name(), "mdev_type/name")) // raw: the GPU sanitises
+		if err != nil {
+			r.flags |= C.KVG_MF_TYPE_ERR
+		} else {
+			id, ok := typeIDs[string(raw)]
+			if !ok {
+				id = uint16(len(rawTypes))
+				typeIDs[string(raw)] = id
+				rawTypes = append(rawTypes, raw)
+			}
+			r.type_idx = C.uint16_t(id)
+			gpuID, err := readGpuIDForVgpu(vGpuBasePath, info.Name())
+			if err != nil {
+				r.flags |= C.KVG_MF_PARENT_ERR
+			} else {
+				id, ok := parentIDs[gpuID]
+				if !ok {
+					id = uint32(len(parentNames))
+					parentIDs[gpuID] = id
+					parentNames = append(parentNames, gpuID)
+				}
+				r.parent = C.uint32_t(id)
+				numaNode, err := readNUMANode(basePath, gpuID)
+				if err != nil {
+					r.flags |= C.KVG_MF_NUMA_ERR
+				}
+				r.parent_numa = C.int16_t(numaNode)
+			}
+		}
+		names = append(names, info.Name())
+		recs = append(recs, r)
+		return nil
+	})
+	if err := kvgEnsure(); err != nil {
+		log.Printf("Error: %v", err)
+		return
+	}
+	off := make([]C.uint32_t, len(rawTypes)+1)
+	var blob []byte
+	for i, t := range rawTypes {
+		blob = append(blob, t...)
+		off[i+1] = C.uint32_t(len(blob))
+	}
+	blob = append(blob, 0)
+	dict := C.kvg_type_dict{n_types: C.uint32_t(len(rawTypes)), off: &off[0], bytes: (*C.uint8_t)(unsafe.Pointer(&blob[0]))}
+	var res *C.kvg_mdev_result
+	var p *C.kvg_mdev_rec
+	if len(recs) > 0 {
+		p = &recs[0]
+	}
+	if rc := C.kvg_scan_mdev(kvgCtx, p, C.size_t(len(recs)), &dict, &res); rc != C.KVG_OK {
+		log.Printf("Error: kvg_scan_mdev: %s", C.GoString(C.kvg_last_error(kvgCtx)))
+		return
+	}
+	defer C.kvg_result_free(unsafe.Pointer(res))
+	S := int(res.n_survivors)
+	surv := unsafe.Slice(res.survivors, S)
+	labelOff := unsafe.Slice(res.label_off, int(res.n_types)+1)
+	labels := unsafe.Slice((*byte)(unsafe.Pointer(res.label_bytes)), int(labelOff[res.n_types]))
+	tKeys := unsafe.Slice(res.type_keys, int(res.n_type_keys))
+	tOff := unsafe.Slice(res.type_off, int(res.n_type_keys)+1)
+	tPerm := unsafe.Slice(res.type_perm, S)
+	for k := range tKeys {
+		t := tKeys[k]
+		label := string(labels[labelOff[t]:labelOff[t+1]])
+		for _, i := range tPerm[tOff[k]:tOff[k+1]] {
+			vGpuMap[label] = append(vGpuMap[label], NvidiaGpuDevice{addr: names[surv[i].src], numaNode: int64(surv[i].numa)})
+		}
+	}
+	pKeys := unsafe.Slice(res.par_keys, int(res.n_parents))
+	pOff := unsafe.Slice(res.par_off, int(res.n_parents)+1)
+	pPerm := unsafe.Slice(res.par_perm, S)
+	for k := range pKeys {
+		g := parentNames[pKeys[k]]
+		for _, i := range pPerm[pOff[k]:pOff[k+1]] {
+			gpuVgpuMap[g] = append(gpuVgpuMap[g], names[surv[i].src])
+		}
+	}
+	_ = sort.Strings // (kept: callers that want deterministic logs sort the keys)
+}
