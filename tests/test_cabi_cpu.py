@@ -135,3 +135,73 @@ def test_shard_ranges_tile_exactly():
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---- native (C++) host layer: libkvghost.so / kvg-discover ------------------------------------
+def _host_lib():
+    import ctypes as C
+    path = os.path.join(conftest.PKG, "libkvghost.so")
+    L = C.CDLL(path)
+    L.kvgh_snapshot_pci.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.kvgh_free.argtypes = [C.c_void_p]
+    L.kvgh_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
+    return L
+
+
+def _native_snapshot(base):
+    import ctypes as C
+    import kvgpu
+    L = _host_lib()
+    recs, n, names, nl, groups, gl = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
+    rc = L.kvgh_snapshot_pci(base.encode(), C.byref(recs), C.byref(n), C.byref(names), C.byref(nl),
+                             C.byref(groups), C.byref(gl))
+    if rc != 0:
+        return rc, None, None, None
+    arr = np.frombuffer(C.string_at(recs, n.value * 16), dtype=kvgpu.PCI_REC).copy()
+    nm = C.string_at(names, nl.value).split(b"\0")[:-1]
+    gr = C.string_at(groups, gl.value).split(b"\0")[:-1]
+    for p in (recs, names, groups):
+        L.kvgh_free(p)
+    return 0, arr, [x.decode() for x in nm], [x.decode() for x in gr]
+
+
+def test_native_snapshot_equals_python_snapshot(tmp_path):
+    """The C++ snapshotter (index mode) and the Python one see the same sysfs facts."""
+    import kvgpu
+    ent = util.c1_tree_entries()
+    ent.update(util.ginkgo()["create_iommu_device_map"]["entries"])
+    base = util.make_pci_tree(str(tmp_path), ent)
+    rc, recs, names, groups = _native_snapshot(base)
+    assert rc == 0
+    py = kvgpu.snapshot_pci_tree(base)
+    assert names == py.names and list(recs["addr"]) == list(range(len(names)))
+    for f in ("vendor", "device", "driver", "flags", "numa"):
+        assert np.array_equal(recs[f], py.recs[f]), f
+    py_groups = py.group_names if py.group_names is not None else None
+    nat = [groups[g] if (fl & 4) == 0 and drv in (1, 2) and v == 0x10de and (fl & 3) == 0 else None
+           for g, fl, drv, v in zip(recs["iommu_group"], recs["flags"], recs["driver"], recs["vendor"])]
+    pyg = [(py_groups[g] if py_groups is not None else str(g)) if x is not None else None
+           for g, x in zip(py.recs["iommu_group"], nat)]
+    assert nat == pyg
+
+
+def test_native_snapshot_reports_reference_panic(tmp_path):
+    ent = {"0000:01:00.0": dict(vendor="10de", device="1b38", driver="vfio-pci", iommu_group="1")}
+    base = util.make_pci_tree(str(tmp_path), ent)
+    with open(os.path.join(base, "0000:01:00.0", "device"), "w") as f:
+        f.write("0")
+    rc, *_ = _native_snapshot(base)
+    assert rc == -100  # KVGH_EPANIC
+
+
+@pytest.mark.skipif(conftest.HAS_GPU, reason="checks the no-GPU failure mode")
+def test_native_host_has_no_cpu_fallback():
+    import ctypes as C
+    import subprocess
+    L = _host_lib()
+    h = C.c_void_p()
+    assert L.kvgh_create(b"/x", b"/y", b"/z", 0, C.byref(h)) == -2  # KVG_ECUDA
+    r = subprocess.run([os.path.join(conftest.PKG, "kvg-discover")], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr

@@ -443,3 +443,32 @@ def test_sharded_scan_matches_oracle(n):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "nccl-ok world=%d n=%d" % (world, n) in r.stdout
+
+
+def test_native_host_layer_matches_oracle(tmp_path, pciids):
+    """libkvghost.so / kvg-discover (C++ host above the C-ABI) on real trees == oracle dump."""
+    import subprocess
+    ids_path = tmp_path / "pci.ids"
+    ids_path.write_bytes(pciids)
+    G = util.ginkgo()
+    ent = util.c1_tree_entries()
+    ent.update(G["create_iommu_device_map"]["entries"])
+    base = util.make_pci_tree(str(tmp_path / "pci"), ent)
+    spec = G["create_vgpu_id_map"]
+    mdev, mpci = util.make_mdev_tree(str(tmp_path / "vg"), {spec["parent_dir"]: spec["parent_numa_content"]},
+                                     spec["entries"])
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       "kubevirt-gpu-device-plugin_b200", "kvg-discover")
+    r = subprocess.run([exe, "--pci-ids", str(ids_path), "--sysfs-pci", base, "--sysfs-mdev", mdev, "--dump"],
+                       capture_output=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    m = O.Maps()
+    m.create_iommu_device_map_tree(base)
+    m.create_vgpu_id_map_tree(mdev, base)   # parents' numa is read under the PCI base (:280)
+    assert r.stdout == m.dump(pciids)
+    r = subprocess.run([exe, "--pci-ids", str(ids_path), "--sysfs-pci", base, "--sysfs-mdev", mdev],
+                       capture_output=True, text=True, timeout=120)
+    assert ("P 1b38 GP102GL_TESLA_P40 nvidia.com/GP102GL_TESLA_P40 "
+            "/var/lib/kubelet/device-plugins/kubevirt-GP102GL_TESLA_P40.sock "
+            "PCI_RESOURCE_NVIDIA_COM_GP102GL_TESLA_P40 8\n  0000:04:00.0 Healthy 0\n") in r.stdout
+    assert "P vGPUId vGPUId nvidia.com/vGPUId " in r.stdout and "MDEV_PCI_RESOURCE_NVIDIA_COM_VGPUID 2" in r.stdout
