@@ -17,6 +17,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <string>
 #include <vector>
@@ -128,6 +129,8 @@ struct kvg_ctx {
   DevBuf<PciIdsInfo> info;
   DevBuf<uint32_t> tile_arrays;  // 3 x n_tiles
   DevBuf<uint64_t> parse_state;
+  DevBuf<uint64_t> parse_pairs;
+  DevBuf<uint32_t> parse_pair_cnt;
   DevBuf<uint32_t> parse_ticket;
   DevBuf<uint8_t> pool;
   DevBuf<uint32_t> nv_index;  // [65536] vendor-10de device id -> name pool slot
@@ -372,7 +375,7 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   release(ctx->text); release(ctx->tables); release(ctx->info); release(ctx->tile_arrays);
-  release(ctx->parse_state); release(ctx->parse_ticket); release(ctx->pool); release(ctx->ctrl);
+  release(ctx->parse_state); release(ctx->parse_pairs); release(ctx->parse_pair_cnt); release(ctx->parse_ticket); release(ctx->pool); release(ctx->ctrl);
   release(ctx->nv_index); release(ctx->ragged); release(ctx->tile_count); release(ctx->tile_off);
   release(ctx->tile_max); release(ctx->offs_state);
   release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist);
@@ -474,6 +477,8 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
   ENSURE(ctx->info, n_files);
   ENSURE(ctx->tile_arrays, 3 * (size_t)n_tiles);
   ENSURE(ctx->parse_state, n_tiles);
+  ENSURE(ctx->parse_pairs, (size_t)n_tiles * KVG_WARPS * P_PAIR_CAP);
+  ENSURE(ctx->parse_pair_cnt, (size_t)n_tiles * KVG_WARPS);
 
   ParseArgs A;
   A.text = d_text;
@@ -490,6 +495,8 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
   A.tile_first_nl = ctx->tile_arrays.p + n_tiles;
   A.tile_last_nl = ctx->tile_arrays.p + 2 * (size_t)n_tiles;
   A.tile_state = ctx->parse_state.p;
+  A.pairs = ctx->parse_pairs.p;
+  A.pair_cnt = ctx->parse_pair_cnt.p;
   A.epoch = next_epoch();
 
   // table slots <- EMPTY, info <- {v_off = NONE, 0...}, ticket <- 0
@@ -499,6 +506,7 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
   int grid = ctx->parse_grid;
   if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
   LAUNCH("pciids_parse", k_pciids_parse, grid, KVG_BLOCK, P_SMEM, A);
+  LAUNCH("pciids_insert", k_pciids_insert, n_tiles, KVG_BLOCK, 0, A);
   LAUNCH("pciids_finalize", k_pciids_finalize, n_files, KVG_BLOCK, 0, A);
   // flatten the table for vendor 10de: the scans' per-survivor join is then a single load
   ENSURE(ctx->nv_index, 65536);
@@ -805,7 +813,10 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1) {
   };
   for (int p = 0; p < 4; p++) {
     RadixArgs2 aa;
-    dim3 grid((unsigned)T, p < 2 ? 2 : 1);
+    // passes 0/1 always run: one CTA per tile.  Passes 2/3 exist only for keys >= 2^16 / 2^24 and are
+    // usually ruled out on the device: a small persistent grid makes a ruled-out pass nearly free.
+    const unsigned gx = p < 2 ? (unsigned)T : (unsigned)std::min<size_t>(T, (size_t)ctx->sm_count * 4);
+    dim3 grid(gx, p < 2 ? 2 : 1);
     if (p < 2) {
       aa.o[0] = fill(0, p);
       aa.o[1] = fill(1, p);

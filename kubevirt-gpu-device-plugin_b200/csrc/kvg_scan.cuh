@@ -726,26 +726,28 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_radix_hist(RadixArgs2 aa) {
   const RadixArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
-  const uint32_t tile = blockIdx.x;
-  if (tile >= T || !radix_pass_active(a)) return;
+  if (!radix_pass_active(a)) return;
   __shared__ uint32_t h[256];
-  h[threadIdx.x] = 0;
-  __syncthreads();
   const uint32_t lane = lane_id();
-  const uint32_t base = tile * C_TILE + warp_id() * C_WARP_ITEMS;
-  uint32_t d[C_ROWS];
+  // tile loop: launched with one CTA per tile for the always-active passes, with a small grid for the
+  // high passes that are usually ruled out by the device-side max key (they then cost ~nothing)
+  for (uint32_t tile = blockIdx.x; tile < T; tile += gridDim.x) {
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = tile * C_TILE + warp_id() * C_WARP_ITEMS;
+    uint32_t d[C_ROWS];
 #pragma unroll
-  for (uint32_t k = 0; k < C_ROWS; k++) {  // all loads in flight before the first shared atomic
-    uint32_t i = base + k * 32 + lane;
-    d[k] = i < n ? ((radix_load(a, i).x >> a.shift) & 0xffu) : 0x100u;
+    for (uint32_t k = 0; k < C_ROWS; k++) {  // all loads in flight before the first shared atomic
+      uint32_t i = base + k * 32 + lane;
+      d[k] = i < n ? ((radix_load(a, i).x >> a.shift) & 0xffu) : 0x100u;
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < C_ROWS; k++)
+      if (d[k] < 0x100u) atomicAdd(&h[d[k]], 1u);
+    __syncthreads();
+    a.tile_hist[(size_t)threadIdx.x * T + tile] = h[threadIdx.x];
+    __syncthreads();
   }
-#pragma unroll
-  for (uint32_t k = 0; k < C_ROWS; k++)
-    if (d[k] < 0x100u) atomicAdd(&h[d[k]], 1u);
-  __syncthreads();
-  uint32_t c = h[threadIdx.x];
-  a.tile_hist[(size_t)threadIdx.x * T + tile] = c;
-  if (c) atomicAdd(&a.bin_total[threadIdx.x], c);
 }
 
 // one CTA per digit: exclusive scan of that digit's per-tile counts, in place
@@ -766,25 +768,28 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_radix_tilescan(RadixArgs2 aa) {
     carry += total;
     __syncthreads();
   }
+  if (threadIdx.x == 0) a.bin_total[blockIdx.x] = carry;  // total of this digit (was: atomics in the histogram)
 }
 
 __global__ void __launch_bounds__(KVG_BLOCK) k_radix_scatter(RadixArgs2 aa) {
   const RadixArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
-  const uint32_t tile = blockIdx.x;
-  if (tile >= T || !radix_pass_active(a)) return;
+  if (!radix_pass_active(a)) return;
   const uint32_t lane = lane_id(), warp = warp_id(), tid = threadIdx.x;
-  const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
   __shared__ uint32_t s_cnt[KVG_WARPS][256];  // per-warp digit counts, then warp bases
   __shared__ uint32_t s_start[256];           // tile-local exclusive start of each digit
   __shared__ int32_t s_goff[256];             // global position of a digit's run minus its local start
   __shared__ uint32_t scratch[KVG_WARPS + 1];
   __shared__ uint2 s_stage[C_TILE];           // pairs in tile-sorted order (16 KiB)
-#pragma unroll
-  for (uint32_t w = 0; w < KVG_WARPS; w++) s_cnt[w][tid] = 0;
   uint32_t total;
   const uint32_t bin_base = block_excl_sum(a.bin_total[tid], scratch, &total);  // syncs inside
+  for (uint32_t tile = blockIdx.x; tile < T; tile += gridDim.x) {
+  const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
+  __syncthreads();  // previous tile's stage fully written out
+#pragma unroll
+  for (uint32_t w = 0; w < KVG_WARPS; w++) s_cnt[w][tid] = 0;
+  __syncthreads();
 
   uint2 kv[C_ROWS];
   uint32_t rank[C_ROWS];
@@ -839,6 +844,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_radix_scatter(RadixArgs2 aa) {
     uint32_t d = (e.x >> a.shift) & 0xffu;
     a.pairs_out[(uint32_t)(s_goff[d] + (int32_t)j)] = e;
   }
+  }  // tile loop
 }
 
 // ---- final permutation + distinct keys of one ordering, look-back free --------------------------
