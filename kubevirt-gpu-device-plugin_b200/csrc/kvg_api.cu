@@ -129,8 +129,6 @@ struct kvg_ctx {
   DevBuf<PciIdsInfo> info;
   DevBuf<uint32_t> tile_arrays;  // 3 x n_tiles
   DevBuf<uint64_t> parse_state;
-  DevBuf<uint64_t> parse_pairs;
-  DevBuf<uint32_t> parse_pair_cnt;
   DevBuf<uint32_t> parse_ticket;
   DevBuf<uint8_t> pool;
   DevBuf<uint32_t> nv_index;  // [65536] vendor-10de device id -> name pool slot
@@ -375,7 +373,7 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   release(ctx->text); release(ctx->tables); release(ctx->info); release(ctx->tile_arrays);
-  release(ctx->parse_state); release(ctx->parse_pairs); release(ctx->parse_pair_cnt); release(ctx->parse_ticket); release(ctx->pool); release(ctx->ctrl);
+  release(ctx->parse_state); release(ctx->parse_ticket); release(ctx->pool); release(ctx->ctrl);
   release(ctx->nv_index); release(ctx->ragged); release(ctx->tile_count); release(ctx->tile_off);
   release(ctx->tile_max); release(ctx->offs_state);
   release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist);
@@ -477,8 +475,6 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
   ENSURE(ctx->info, n_files);
   ENSURE(ctx->tile_arrays, 3 * (size_t)n_tiles);
   ENSURE(ctx->parse_state, n_tiles);
-  ENSURE(ctx->parse_pairs, (size_t)n_tiles * KVG_WARPS * P_PAIR_CAP);
-  ENSURE(ctx->parse_pair_cnt, (size_t)n_tiles * KVG_WARPS);
 
   ParseArgs A;
   A.text = d_text;
@@ -495,8 +491,6 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
   A.tile_first_nl = ctx->tile_arrays.p + n_tiles;
   A.tile_last_nl = ctx->tile_arrays.p + 2 * (size_t)n_tiles;
   A.tile_state = ctx->parse_state.p;
-  A.pairs = ctx->parse_pairs.p;
-  A.pair_cnt = ctx->parse_pair_cnt.p;
   A.epoch = next_epoch();
 
   // table slots <- EMPTY, info <- {v_off = NONE, 0...}, ticket <- 0
@@ -506,7 +500,6 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
   int grid = ctx->parse_grid;
   if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
   LAUNCH("pciids_parse", k_pciids_parse, grid, KVG_BLOCK, P_SMEM, A);
-  LAUNCH("pciids_insert", k_pciids_insert, n_tiles, KVG_BLOCK, 0, A);
   LAUNCH("pciids_finalize", k_pciids_finalize, n_files, KVG_BLOCK, 0, A);
   // flatten the table for vendor 10de: the scans' per-survivor join is then a single load
   ENSURE(ctx->nv_index, 65536);

@@ -22,7 +22,6 @@ constexpr uint32_t P_SPAN = P_TILE / KVG_BLOCK;  // 32 text bytes per thread
 constexpr uint32_t P_WSPAN = 32 * P_SPAN;        // 1 KiB of text per warp
 constexpr uint32_t P_WCAP = P_WSPAN + 8;         // worst case: every byte of the warp span is '\n'
 constexpr uint32_t P_SMEM = P_STAGES * P_STAGE + 2 * KVG_WARPS * P_WCAP * 2;  // ring + line lists
-constexpr uint32_t P_PAIR_CAP = 176;  // a device line needs >= 6 bytes: <= 171 start in a 1 KiB warp span
 constexpr uint32_t P_NONE = 0xffffffffu;
 constexpr uint64_t P_EMPTY = 0xffffffffffffffffull;
 constexpr uint32_t SCAN_TOKEN_MAX = 65536;  // bufio.MaxScanTokenSize
@@ -56,8 +55,6 @@ struct ParseArgs {
   uint32_t* tile_first_nl;   // [n_tiles] file offset of the first / last '\n' in the tile
   uint32_t* tile_last_nl;
   uint64_t* tile_state;  // [n_tiles] vendor-context look-back
-  uint64_t* pairs;       // [n_tiles * 8 warps][P_PAIR_CAP]  key<<32 | line offset, per-warp regions
-  uint32_t* pair_cnt;    // [n_tiles * 8]
   uint32_t epoch;
 };
 
@@ -144,8 +141,7 @@ __device__ __forceinline__ uint32_t table_probe(const uint64_t* __restrict__ tab
 //               last header is reduced.  Warp 0 then scans the 8 warp summaries, publishes the
 //               tile's context state and the tile summaries used by k_pciids_finalize.
 //   phase 2(i-1) warp-dense over the saved list: 32 lines per round with all lanes converged —
-//               classify, intra-round header scan, and the (vendor,device)->offset pairs of the
-//               round appended to the warp's pair region (coalesced 8-byte stores, no atomics).
+//               classify, intra-round header scan, and ONE batch of hash inserts per round.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_parse(ParseArgs A) {
   extern __shared__ __align__(128) uint8_t p_smem[];
@@ -182,6 +178,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_parse(ParseArgs A) {
   if (tid == 0)
     for (uint32_t s = 0; s < P_STAGES; s++) issue(s);
 
+  uint32_t n_new = 0;                   // per-thread tally of first-time inserts
   bool prev_defines = false, prev_first = false;  // warp 0: facts about tile i-1
 
   for (uint32_t i = 0; i <= my_count; ++i) {
@@ -325,10 +322,6 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_parse(ParseArgs A) {
       const uint32_t cnt = s_wcnt[(i - 1) & 1][warp];
       const uint32_t c0 = s_wctx[(i - 1) & 1][warp];
       uint32_t running = c0 ? (c0 & 0x1ffffu) : s_carry;  // valid<<16 | vendor
-      // (vendor,device) -> line offset pairs of this warp's span, appended densely to the warp's
-      // own region: no atomics and no waiting here — k_pciids_insert builds the hash afterwards
-      uint64_t* region = A.pairs + ((size_t)ptile * KVG_WARPS + warp) * P_PAIR_CAP;
-      uint32_t npairs = 0;
       for (uint32_t base = 0; base < cnt; base += 32) {
         const uint32_t e = base + lane;
         uint32_t hval = 0, dv = 0, p = 0;
@@ -342,39 +335,17 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_parse(ParseArgs A) {
         }
         uint32_t sc = warp_incl_max(hval);  // last header at or before this line, this round
         uint32_t ctx = sc ? (sc & 0x1ffffu) : running;
-        const bool is = ((dv & ctx) & 0x10000u) != 0;
-        const uint32_t bal = __ballot_sync(KVG_FULL, is);
-        if (is)
-          region[npairs + __popc(bal & lanemask_lt())] =
-              ((uint64_t)(((ctx & 0xffffu) << 16) | (dv & 0xffffu)) << 32) | (a + p);
-        npairs += __popc(bal);
+        if ((dv & ctx) & 0x10000u)
+          n_new += table_insert(table, A.cap_mask, A.cap_shift,
+                                ((ctx & 0xffffu) << 16) | (dv & 0xffffu), a + p, &A.info[f].overflow);
         uint32_t last = __shfl_sync(KVG_FULL, sc, 31);
         if (last) running = last & 0x1ffffu;
       }
-      if (lane == 0) A.pair_cnt[(size_t)ptile * KVG_WARPS + warp] = npairs;
+      uint32_t e2 = warp_sum(n_new);
+      if (lane == 0 && e2) atomicAdd(&A.info[f].n_entries, e2);
+      n_new = 0;
     }
   }
-}
-
-// K1b: build the open-addressed hash from the pair regions.  One warp per region, every lane an
-// independent atomicCAS chain: tens of thousands of inserts in flight hide the L2 atomic latency that
-// serialised the scan kernel when the inserts lived inside it.
-__global__ void __launch_bounds__(KVG_BLOCK) k_pciids_insert(ParseArgs A) {
-  const uint32_t region = blockIdx.x * KVG_WARPS + warp_id();
-  if (region >= A.n_tiles * KVG_WARPS) return;
-  const uint32_t tile = region / KVG_WARPS;
-  const uint32_t f = tile / A.tiles_per_file;
-  uint64_t* table = A.tables + (uint64_t)f * (A.cap_mask + 1);
-  const uint32_t cnt = A.pair_cnt[region];
-  const uint64_t* src = A.pairs + (size_t)region * P_PAIR_CAP;
-  uint32_t n_new = 0;
-  for (uint32_t k = lane_id(); k < cnt; k += 32) {
-    uint64_t kv = src[k];
-    n_new += table_insert(table, A.cap_mask, A.cap_shift, (uint32_t)(kv >> 32), (uint32_t)kv,
-                          &A.info[f].overflow);
-  }
-  n_new = warp_sum(n_new);
-  if (lane_id() == 0 && n_new) atomicAdd(&A.info[f].n_entries, n_new);
 }
 
 // ------------------------------------------------------------------------------------------------
