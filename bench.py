@@ -346,6 +346,65 @@ def main():
         c2.close()
         del bigt
 
+    # ---- BASELINE.json configs 3 and 5 (extra keys; the headline stays config 2)
+    extra = {}
+    if world == 1:
+        import ctypes as C
+        lib = kvgpu.load()
+        # config 3: 65,536 mdev UUIDs over 256 raw type names (128 labels), 2,048 parents
+        m = 65536
+        mrecs = torch.from_numpy(np.frombuffer(O.gen_mdev(0, m).tobytes(), dtype=np.uint8).copy()).pin_memory()
+        types = O.gen_type_names(256)
+        td, keep = ctx._type_dict(types)
+        def mdev_step():
+            res = C.POINTER(kvgpu._lib.MdevResultC)()
+            rc = lib.kvg_scan_mdev(ctx.handle, mrecs.data_ptr(), m, C.byref(td), C.byref(res))
+            assert rc == 0
+            s_ = int(res.contents.n_survivors)
+            lib.kvg_result_free(res)
+            return s_
+        for _ in range(5):
+            ms_ = mdev_step()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            mdev_step()
+        tm = (time.perf_counter() - t0) / 50
+        extra["config3_mdev"] = {"mdevs": m, "raw_types": 256, "survivors": ms_, "ms_per_scan_e2e": tm * 1e3,
+                                 "mdevs_per_s_e2e": m / tm,
+                                 "what": "kvg_scan_mdev: pinned host records in, host result out (labels, "
+                                         "256 exact-prefix name lookups, 2 orderings)"}
+        # config 5: 10,000 devices re-scanned at 1 kHz; 0.1 % of the records flip per tick
+        hn = 10_000
+        hrecs = torch.from_numpy(np.frombuffer(O.gen_pci(0, hn, ids, 12).tobytes(), dtype=np.uint8).copy()).pin_memory()
+        hview = np.frombuffer(hrecs.numpy(), dtype=kvgpu.PCI_REC)
+        rng = np.random.default_rng(5)
+        lib.kvg_health_reset(ctx.handle)
+        lat = []
+        ticks = 3000
+        period = 1e-3
+        t_next = time.perf_counter()
+        for tick in range(ticks + 50):
+            flip = rng.integers(0, hn, 10)
+            hview["driver"][flip] = rng.integers(0, 5, 10)
+            t0 = time.perf_counter()                        # snapshot is in the pinned buffer
+            res = C.POINTER(kvgpu._lib.HealthDeltaC)()
+            rc = lib.kvg_health_rescan(ctx.handle, hrecs.data_ptr(), hn, C.byref(res))
+            dt = time.perf_counter() - t0                   # delta list visible to the host
+            assert rc == 0
+            lib.kvg_result_free(res)
+            if tick >= 50:
+                lat.append(dt)
+            t_next += period
+            while time.perf_counter() < t_next:
+                pass
+        lat = np.array(lat) * 1e6
+        extra["config5_health_rescan"] = {"devices": hn, "poll_hz": 1000, "ticks": ticks,
+                                          "p50_us": float(np.percentile(lat, 50)),
+                                          "p99_us": float(np.percentile(lat, 99)),
+                                          "max_us": float(lat.max()),
+                                          "what": "host wall time from snapshot-in-pinned-buffer to "
+                                                  "transition list on the host (H2D 160 KB + K6 + D2H)"}
+
     # ---- end to end through the reference-facing calls: pinned host in, host results out
     e2e = None
     if world == 1:
@@ -441,6 +500,7 @@ def main():
             "roofline_hbm_bound": roofline_big,
             "kernel_ms_per_step": ksum,
             "cpu_baseline": cpu,
+            "other_configs": extra,
             "e2e": e2e,
             "gpu_launches": launches,
             "clocks": clocks,

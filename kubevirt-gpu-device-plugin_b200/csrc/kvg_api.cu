@@ -321,7 +321,7 @@ static int classify_variant() {  // KVG_CLASSIFY=tma selects the non-specialised
   if (v < 0) {
     const char* e = getenv("KVG_CLASSIFY");
     v = (e && !strcmp(e, "tma")) ? 1 : (e && !strcmp(e, "ws")) ? 0 : (e && !strcmp(e, "oneshot4")) ? 3
-        : (e && !strcmp(e, "oneshot")) ? 2 : 4;  // default 4: split ragged / offsets / pack
+        : (e && !strcmp(e, "oneshot")) ? 2 : (e && !strcmp(e, "ragged")) ? 4 : 5;  // 5 = auto
   }
   return v;
 }
@@ -882,7 +882,11 @@ static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d
   op.local_max_group = 0;
   op.local_max_dev = 0;
   size_t smem = 0;
-  if (classify_variant() == 4) {
+  // auto: below ~2 M records the step is launch-bound and ONE look-back kernel beats the three
+  // launches of the split form; above, the split form (no cross-CTA wait) runs at the HBM roofline
+  int variant = classify_variant();
+  if (variant == 5) variant = n < (2u << 20) ? 2 : 4;
+  if (variant == 4) {
     constexpr int T = 128, R = 8;
     const size_t tiles = (n + (size_t)T * R - 1) / ((size_t)T * R);
     if (tiles == 0) {  // nothing to classify: n_surv stays 0 from the control-block memset
@@ -906,8 +910,8 @@ static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d
     }
     LAUNCH("pack_survivors", k_pack_survivors<1>, (unsigned)tiles, 128, 0, ctx->ragged.p, ctx->tile_off.p,
            (uint32_t)(T * R), d_out);
-  } else if (classify_variant() >= 2) {  // one tile per CTA with look-back
-    if (classify_variant() == 2) {
+  } else if (variant >= 2) {  // one tile per CTA with look-back
+    if (variant == 2) {
       constexpr int T = 128, R = 8;
       size_t tiles = (n + (size_t)T * R - 1) / ((size_t)T * R);
       LAUNCH("classify_compact", (k_classify_oneshot<PciClassifyOp, T, R>), (unsigned)(tiles ? tiles : 1), T, 0, op,
@@ -918,7 +922,7 @@ static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d
       LAUNCH("classify_compact", (k_classify_oneshot<PciClassifyOp, T, R>), (unsigned)(tiles ? tiles : 1), T, 0, op,
              ctx->classify_state.p, next_epoch());
     }
-  } else if (classify_variant() == 1) {
+  } else if (variant == 1) {
     int grid = classify_grid<PciClassifyOp, PCI_ROWS, PCI_STAGES>(ctx, n, &smem);
     LAUNCH("classify_compact", (k_classify_tma<PciClassifyOp, PCI_ROWS, PCI_STAGES>), grid, KVG_BLOCK, smem, op,
            ctx->classify_state.p, ctx->classify_state.p + pci_tiles, next_epoch());
