@@ -132,6 +132,7 @@ struct kvg_ctx {
   DevBuf<uint32_t> parse_ticket;
   DevBuf<uint8_t> pool;
   DevBuf<uint32_t> nv_index;  // [65536] vendor-10de device id -> name pool slot
+  DevBuf<uint32_t> nv_lines;  // [65536 + 1] offsets of the lines that have a name, then their count
   std::vector<uint8_t> h_pool;
   PciIdsInfo h_info{};
   bool table_ready = false;
@@ -374,7 +375,7 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   release(ctx->text); release(ctx->tables); release(ctx->info); release(ctx->tile_arrays);
   release(ctx->parse_state); release(ctx->parse_ticket); release(ctx->pool); release(ctx->ctrl);
-  release(ctx->nv_index); release(ctx->ragged); release(ctx->tile_count); release(ctx->tile_off);
+  release(ctx->nv_index); release(ctx->nv_lines); release(ctx->ragged); release(ctx->tile_count); release(ctx->tile_off);
   release(ctx->tile_max); release(ctx->offs_state);
   release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist);
   for (OrderBufs* o : {&ctx->ord_dev, &ctx->ord_grp}) {
@@ -503,8 +504,10 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
   LAUNCH("pciids_finalize", k_pciids_finalize, n_files, KVG_BLOCK, 0, A);
   // flatten the table for vendor 10de: the scans' per-survivor join is then a single load
   ENSURE(ctx->nv_index, 65536);
-  LAUNCH("pciids_nv_index", k_probe_keys, 256, 256, 0, ctx->tables.p, A.cap_mask, A.cap_shift,
-         ctx->info.p, 0u, 65536u, ctx->nv_index.p);
+  ENSURE(ctx->nv_lines, 65536 + 8);
+  CK(cudaMemsetAsync(ctx->nv_lines.p + 65536, 0, sizeof(uint32_t), ctx->stream));
+  LAUNCH("pciids_nv_index", k_nv_index, 256, 256, 0, ctx->tables.p, A.cap_mask, A.cap_shift, ctx->info.p,
+         ctx->nv_index.p, ctx->nv_lines.p, ctx->nv_lines.p + 65536);
   return check_launch(ctx, "pciids parse");
 }
 
@@ -519,11 +522,9 @@ static int table_publish(kvg_ctx* ctx, const uint8_t* d_text, size_t len) {
     size_t sec = (size_t)ctx->h_info.sec_end - ctx->h_info.v_off;
     ENSURE(ctx->pool, sec + 16);
     CK(cudaMemsetAsync(ctx->pool.p, 0, sec + 16, ctx->stream));
-    int grid = (int)((sec + S_WIN - 1) / S_WIN);
-    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-    if (grid < 1) grid = 1;
-    LAUNCH("pciids_sanitise", k_pciids_sanitise, grid, KVG_BLOCK, 0, d_text, (uint32_t)len,
-           ctx->info.p, ctx->pool.p);
+    // one warp per named line (<= 65,536 lines; the shipped file has 1,931)
+    LAUNCH("pciids_sanitise", k_pciids_sanitise_lines, 256, KVG_BLOCK, 0, d_text, (uint32_t)len, ctx->info.p,
+           ctx->nv_lines.p, ctx->nv_lines.p + 65536, ctx->pool.p);
     int rc = check_launch(ctx, "pciids sanitise");
     if (rc) return rc;
     ctx->h_pool.resize(sec + 16);
@@ -599,11 +600,8 @@ int kvg_dev_pciids_parse(kvg_ctx* ctx, const void* d_text, size_t len, size_t st
   if (rc) return rc;
   size_t sec = ctx->h_pool.size();
   if (sec > 16) {
-    int grid = (int)((sec + S_WIN - 1) / S_WIN);
-    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-    if (grid < 1) grid = 1;
-    LAUNCH("pciids_sanitise", k_pciids_sanitise, grid, KVG_BLOCK, 0, (const uint8_t*)d_text,
-           (uint32_t)len, ctx->info.p, ctx->pool.p);
+    LAUNCH("pciids_sanitise", k_pciids_sanitise_lines, 256, KVG_BLOCK, 0, (const uint8_t*)d_text, (uint32_t)len,
+           ctx->info.p, ctx->nv_lines.p, ctx->nv_lines.p + 65536, ctx->pool.p);
   }
   return check_launch(ctx, "pciids sanitise");
 }

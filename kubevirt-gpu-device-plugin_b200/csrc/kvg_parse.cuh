@@ -608,6 +608,104 @@ __device__ __forceinline__ uint32_t probe_name_slot(const uint64_t* __restrict__
   uint32_t V = info->v_off, E = info->sec_end;
   return (off != P_NONE && V != P_NONE && off > V && off < E) ? off - V : P_NONE;
 }
+// nv_index[d] for all 65,536 device ids of vendor 10de + the list of line offsets that have a name
+// (order irrelevant: each entry is sanitised independently by k_pciids_sanitise_lines)
+__global__ void k_nv_index(const uint64_t* __restrict__ table, uint32_t mask, uint32_t shift,
+                           const PciIdsInfo* __restrict__ info, uint32_t* __restrict__ nv_index,
+                           uint32_t* __restrict__ line_list, uint32_t* __restrict__ line_count) {
+  uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t slot = probe_name_slot(table, mask, shift, info, d & 0xffffu);
+  nv_index[d] = slot;
+  uint32_t hit = __ballot_sync(KVG_FULL, slot != P_NONE);
+  if (hit) {
+    uint32_t base = 0;
+    if (lane_id() == 0) base = atomicAdd(line_count, (uint32_t)__popc(hit));
+    base = __shfl_sync(KVG_FULL, base, 0);
+    if (slot != P_NONE) line_list[base + __popc(hit & lanemask_lt())] = slot;  // offset - V
+  }
+}
+
+// K2, one warp per NVIDIA device line: lanes classify 32 characters at a time.  ASCII-only lines
+// (every line of the shipped file's NVIDIA block) take the lane-parallel path; a line with any byte
+// >= 0x80 falls back to the exact serial routine (Unicode TrimSpace / ToUpper rules).
+__global__ void __launch_bounds__(KVG_BLOCK) k_pciids_sanitise_lines(const uint8_t* __restrict__ text,
+                                                                     uint32_t len,
+                                                                     const PciIdsInfo* __restrict__ info,
+                                                                     const uint32_t* __restrict__ line_list,
+                                                                     const uint32_t* __restrict__ line_count,
+                                                                     uint8_t* __restrict__ pool) {
+  const uint32_t V = info->v_off;
+  if (V == P_NONE) return;
+  const uint32_t n_lines = *line_count;
+  const uint32_t lane = lane_id();
+  for (uint32_t w = blockIdx.x * KVG_WARPS + warp_id(); w < n_lines; w += gridDim.x * KVG_WARPS) {
+    const uint32_t slot = line_list[w];
+    const uint32_t s0 = V + slot + 5;  // first byte after "\t" + 4 hex
+    uint8_t* out = pool + slot;
+    // line end and ASCII test
+    uint32_t n = 0;
+    bool ascii = true;
+    for (uint32_t c0 = 0;; c0 += 32) {
+      uint32_t pos = s0 + c0 + lane;
+      uint32_t c = pos < len ? text[pos] : '\n';
+      uint32_t nl = __ballot_sync(KVG_FULL, c == '\n');
+      uint32_t hi = __ballot_sync(KVG_FULL, c >= 0x80);
+      if (nl) {
+        uint32_t k = (uint32_t)__ffs(nl) - 1;
+        n = c0 + k;
+        if (hi & ((1u << k) - 1)) ascii = false;
+        break;
+      }
+      if (hi) ascii = false;
+    }
+    if (!ascii) {
+      if (lane == 0) {
+        uint32_t m = d_sanitise_name(text + s0, n, out + 2, n);
+        out[0] = (uint8_t)(m & 0xff);
+        out[1] = (uint8_t)(m >> 8);
+      }
+      continue;
+    }
+    // trim: first / last byte that is not ASCII white space (TrimSpace; includes \v)
+    uint32_t first = n, last = 0;
+    for (uint32_t c0 = 0; c0 < n; c0 += 32) {
+      uint32_t i = c0 + lane;
+      bool ns = i < n && !d_ascii_space(text[s0 + i]);
+      uint32_t b = __ballot_sync(KVG_FULL, ns);
+      if (b) {
+        if (first == n) first = c0 + (uint32_t)__ffs(b) - 1;
+        last = c0 + 32 - (uint32_t)__clz(b);  // one past the last non-space
+      }
+    }
+    uint32_t o = 0;
+    if (first < last) {
+      for (uint32_t c0 = first; c0 < last; c0 += 32) {
+        uint32_t i = c0 + lane;
+        uint32_t e = 0;
+        if (i < last) {
+          uint32_t c = text[s0 + i];
+          if (d_re2_space(c)) {
+            if (!(i > first && d_re2_space(text[s0 + i - 1]))) e = '_';  // one '_' per run
+          } else if (c >= 'a' && c <= 'z') {
+            e = c - 32;
+          } else if ((c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9') || c == '_') {
+            e = c;
+          } else if (c == '/' || c == '.') {
+            e = '_';
+          }
+        }
+        uint32_t b = __ballot_sync(KVG_FULL, e != 0);
+        if (e) out[2 + o + __popc(b & lanemask_lt())] = (uint8_t)e;
+        o += __popc(b);
+      }
+    }
+    if (lane == 0) {
+      out[0] = (uint8_t)(o & 0xff);
+      out[1] = (uint8_t)(o >> 8);
+    }
+  }
+}
+
 __global__ void k_probe_keys(const uint64_t* __restrict__ table, uint32_t mask, uint32_t shift,
                              const PciIdsInfo* __restrict__ info, uint32_t first, uint32_t count,
                              uint32_t* __restrict__ slots) {

@@ -771,7 +771,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_radix_tilescan(RadixArgs2 aa) {
   if (threadIdx.x == 0) a.bin_total[blockIdx.x] = carry;  // total of this digit (was: atomics in the histogram)
 }
 
-__global__ void __launch_bounds__(KVG_BLOCK) k_radix_scatter(RadixArgs2 aa) {
+__global__ void __launch_bounds__(KVG_BLOCK, 6) k_radix_scatter(RadixArgs2 aa) {
   const RadixArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
