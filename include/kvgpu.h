@@ -265,8 +265,11 @@ int kvg_set_kernel_timing(kvg_ctx *ctx, int enabled);
 int kvg_comm_unique_id(void *out128);
 int kvg_comm_init(kvg_ctx *ctx, int rank, int nranks, const void *unique_id128);
 int kvg_comm_destroy(kvg_ctx *ctx);
-/* classify the local shard, allgatherv the survivors over NCCL (rank order == Walk order),
- * bucket the gathered list on every rank.  d_recs is device memory. */
+/* classify the local shard, allgatherv the survivors over NCCL (rank order == Walk order): every rank
+ * ends up with the FULL survivor list.  The bucketing is partitioned by key: rank r's orderings
+ * (dev_* / grp_* of the fetched result) cover exactly the keys with key % nranks == r, so the key
+ * sets of the ranks are disjoint and their union is the global deviceMap / iommuMap; dev_perm and
+ * grp_perm then hold only the members of the owned keys.  d_recs is device memory. */
 int kvg_dev_scan_pci_sharded(kvg_ctx *ctx, const void *d_recs, size_t n_local);
 
 #ifdef __cplusplus

@@ -154,6 +154,7 @@ struct kvg_ctx {
   size_t last_n = 0;     // records of the last enqueued scan
   size_t last_total = 0; // survivors capacity used by the last scan (sharded: all ranks)
   int last_kind = 0;     // 1 = pci, 2 = mdev
+  bool last_owned = false;  // sharded scan: the orderings cover only the keys this rank owns
   // mdev dictionary
   DevBuf<uint8_t> type_raw, type_label;
   DevBuf<uint32_t> type_off, type_label_len, type_match, type_name_len;
@@ -776,7 +777,7 @@ static int ensure_order(kvg_ctx* ctx, OrderBufs& o, size_t cap) {
 // Both stable orderings of the survivor list — ordering 0 by device id / mdev type (<= 16 bits,
 // 2 passes), ordering 1 by iommu group / parent (32 bits, up to 4 passes) — share their launches:
 // grid.y = 2 while both have a pass, grid.y = 1 (ordering 1 only, passed in slot 0) afterwards.
-static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1) {
+static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1, bool owned_only = false) {
   int rc = ensure_order(ctx, ctx->ord_dev, cap);
   if (rc) return rc;
   rc = ensure_order(ctx, ctx->ord_grp, cap);
@@ -787,19 +788,51 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1) {
   ScanCtrl* c = ctx->ctrl.p;
   OrderBufs* ob[2] = {&ctx->ord_dev, &ctx->ord_grp};
   uint32_t* maxk[2] = {&c->max_devkey, &c->max_group};
+  // element count per ordering: all survivors, or (sharded) the survivors whose key this rank owns
+  uint32_t* cnt[2] = {owned_only ? &c->n_own[0] : &c->n_surv, owned_only ? &c->n_own[1] : &c->n_surv};
+  if (owned_only && cap) {
+    // select the owned {key, index} pairs of each ordering into p1 (pass 0 then reads pairs)
+    constexpr int TT = 128, RR = 8;
+    const size_t tiles = (cap + (size_t)TT * RR - 1) / ((size_t)TT * RR);
+    ENSURE(ctx->ragged, tiles * TT * RR);  // as uint2 this needs half of it
+    ENSURE(ctx->tile_count, tiles + 1);
+    ENSURE(ctx->tile_off, tiles + 2);
+    ENSURE(ctx->tile_max, tiles + 1);
+    const unsigned chunks = (unsigned)((tiles + C_TILE - 1) / C_TILE);
+    ENSURE(ctx->offs_state, (size_t)chunks + 1);
+    for (int ord = 0; ord < 2; ord++) {
+      OwnedPairOp op;
+      op.surv = ctx->surv.p;
+      op.n = (uint32_t)cap;
+      op.out = (uint2*)ctx->ragged.p;
+      op.field = (uint32_t)ord;
+      op.nranks = (uint32_t)ctx->nranks;
+      op.rank = (uint32_t)ctx->rank;
+      op.local_max = 0;
+      LAUNCH("own_select", (k_classify_ragged<OwnedPairOp, TT, RR>), (unsigned)tiles, TT, 0, op, ctx->tile_count.p,
+             ctx->tile_max.p);
+      TileOffsetsArgs2 tt;
+      tt.o[0] = {ctx->tile_count.p, ctx->tile_max.p, nullptr, (uint32_t)tiles, ctx->tile_off.p, cnt[ord],
+                 ctx->offs_state.p};
+      tt.o[1] = tt.o[0];
+      LAUNCH("tile_offsets", k_tile_offsets, chunks, KVG_BLOCK, 0, tt, c, next_epoch());
+      LAUNCH("own_pack", k_pack_pairs, (unsigned)tiles, 128, 0, (const uint2*)ctx->ragged.p, ctx->tile_off.p,
+             (uint32_t)(TT * RR), ob[ord]->p1.p);
+    }
+  }
   const int npass[2] = {2, 4};
   const int srcs[2] = {src0, src1};
   auto fill = [&](int ord, int p) {
     RadixArgs a;
-    a.n_ptr = &c->n_surv;
+    a.n_ptr = cnt[ord];
     a.max_key = maxk[ord];
     a.src_records = ctx->surv.p;
-    a.pairs_in = p == 0 ? nullptr : ((p & 1) ? ob[ord]->p0.p : ob[ord]->p1.p);
+    a.pairs_in = (p == 0 && !owned_only) ? nullptr : ((p & 1) ? ob[ord]->p0.p : ob[ord]->p1.p);
     a.pairs_out = (p & 1) ? ob[ord]->p1.p : ob[ord]->p0.p;
     a.tile_hist = ctx->tile_hist.p + (size_t)ord * 256 * T;
     a.bin_total = c->bin_total[ord][p];
     a.shift = p < npass[ord] ? 8u * (uint32_t)p : 0xffu;
-    a.src = p == 0 ? srcs[ord] : SRC_PAIRS;
+    a.src = (p == 0 && !owned_only) ? srcs[ord] : SRC_PAIRS;
     return a;
   };
   for (int p = 0; p < 4; p++) {
@@ -830,7 +863,7 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1) {
     a.p1 = ob[ord]->p1.p;
     a.max_key = maxk[ord];
     a.npass_max = npass[ord];
-    a.n_ptr = &c->n_surv;
+    a.n_ptr = cnt[ord];
     a.perm = ob[ord]->perm.p;
     a.tile_heads = ob[ord]->tile_heads.p;
     a.tile_off = ob[ord]->tile_off.p;
@@ -840,7 +873,7 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1) {
     TileOffsetsArgs& t = tt.o[ord];
     t.tile_count = ob[ord]->tile_heads.p;
     t.tile_max = nullptr;
-    t.n_items_ptr = &c->n_surv;
+    t.n_items_ptr = cnt[ord];
     t.n_tiles_host = 0;
     t.tile_off = ob[ord]->tile_off.p;
     t.total_out = nseg[ord];
@@ -860,8 +893,8 @@ static int active_passes(uint32_t max_key, int npass_max) {
   return np;
 }
 
-static int enqueue_pci_orderings(kvg_ctx* ctx, size_t surv_cap) {
-  return enqueue_orderings(ctx, surv_cap, SRC_PCI_DEVICE, SRC_PCI_GROUP);
+static int enqueue_pci_orderings(kvg_ctx* ctx, size_t surv_cap, bool owned_only = false) {
+  return enqueue_orderings(ctx, surv_cap, SRC_PCI_DEVICE, SRC_PCI_GROUP, owned_only);
 }
 
 static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d_out) {
@@ -950,6 +983,7 @@ int kvg_dev_scan_pci(kvg_ctx* ctx, const void* d_recs, size_t n) {
   ctx->last_n = n;
   ctx->last_total = n;
   ctx->last_kind = 1;
+  ctx->last_owned = false;
   return KVG_OK;
 }
 
@@ -972,19 +1006,20 @@ int kvg_dev_scan_pci_fetch(kvg_ctx* ctx, kvg_pci_result** res) {
   CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   const size_t S = ctx->h_ctrl->n_surv, KD = ctx->h_ctrl->n_dev_keys, G = ctx->h_ctrl->n_groups;
-  const int np_dev = active_passes(ctx->h_ctrl->max_devkey, 2);
-  const int np_grp = active_passes(ctx->h_ctrl->max_group, 4);
+  // members covered by each ordering: all survivors, or (sharded) those whose key this rank owns
+  const size_t SD = ctx->last_owned ? ctx->h_ctrl->n_own[0] : S;
+  const size_t SG = ctx->last_owned ? ctx->h_ctrl->n_own[1] : S;
   const size_t pool_len = ctx->h_pool.size();
   size_t o_hdr = 0, o = align64(sizeof(kvg_pci_result));
   size_t o_surv = o; o += align64(S * 16);
   size_t o_dkeys32 = o; o += align64(KD * 4);
   size_t o_dkeys = o; o += align64(KD * 2);
   size_t o_doff = o; o += align64((KD + 1) * 4);
-  size_t o_dperm = o; o += align64(S * 4);
+  size_t o_dperm = o; o += align64(SD * 4);
   size_t o_dname = o; o += align64(KD * 4);
   size_t o_gkeys = o; o += align64(G * 4);
   size_t o_goff = o; o += align64((G + 1) * 4);
-  size_t o_gperm = o; o += align64(S * 4);
+  size_t o_gperm = o; o += align64(SG * 4);
   size_t o_pool = o; o += align64(pool_len);
   void* blk = pinned_alloc(ctx, o);
   if (!blk) {
@@ -1002,10 +1037,10 @@ int kvg_dev_scan_pci_fetch(kvg_ctx* ctx, kvg_pci_result** res) {
   CK(D2H(o_surv, ctx->surv.p, S * 16));
   CK(D2H(o_dkeys32, od.seg_key.p, KD * 4));
   CK(D2H(o_doff, od.seg_off.p, (KD + 1) * 4));
-  CK(D2H(o_dperm, od.perm.p, S * 4));
+  CK(D2H(o_dperm, od.perm.p, SD * 4));
   CK(D2H(o_gkeys, og.seg_key.p, G * 4));
   CK(D2H(o_goff, og.seg_off.p, (G + 1) * 4));
-  CK(D2H(o_gperm, og.perm.p, S * 4));
+  CK(D2H(o_gperm, og.perm.p, SG * 4));
   CK(cudaStreamSynchronize(ctx->stream));
   kvg_pci_result* r = (kvg_pci_result*)b;
   memset(r, 0, sizeof *r);
@@ -1018,7 +1053,8 @@ int kvg_dev_scan_pci_fetch(kvg_ctx* ctx, kvg_pci_result** res) {
   uint32_t* dname = (uint32_t*)(b + o_dname);
   const uint32_t* doff = (const uint32_t*)(b + o_doff);
   const uint32_t* dperm = (const uint32_t*)(b + o_dperm);
-  if (S == 0) ((uint32_t*)(b + o_doff))[0] = 0, ((uint32_t*)(b + o_goff))[0] = 0;
+  if (SD == 0) ((uint32_t*)(b + o_doff))[0] = 0;
+  if (SG == 0) ((uint32_t*)(b + o_goff))[0] = 0;
   for (size_t k = 0; k < KD; k++) {  // marshalling only: narrow the key, pick the joined slot
     dk[k] = (uint16_t)dk32[k];
     dname[k] = r->survivors[dperm[doff[k]]].name_slot;
@@ -1549,11 +1585,13 @@ int kvg_dev_scan_pci_sharded(kvg_ctx* ctx, const void* d_recs, size_t n_local) {
   CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
   LAUNCH("gathered_maxima", k_gathered_maxima, ctx->sm_count * 4, KVG_BLOCK, 0,
          (const kvg_pci_surv*)ctx->surv.p, (uint32_t)total, ctx->ctrl.p);
-  rc = enqueue_pci_orderings(ctx, total);
+  // bucketing partitioned by key: this rank orders only the keys with key % nranks == rank
+  rc = enqueue_pci_orderings(ctx, total, /*owned_only=*/P > 1);
   if (rc) return rc;
   ctx->last_n = n_local;
   ctx->last_total = total;
   ctx->last_kind = 1;
+  ctx->last_owned = P > 1;
   return KVG_OK;
 }
 

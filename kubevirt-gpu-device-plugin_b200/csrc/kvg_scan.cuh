@@ -23,7 +23,8 @@ constexpr uint32_t C_WARP_ITEMS = 32 * C_ROWS;      // 256 contiguous items per 
 
 // device-resident control block of one scan (zeroed by one memset per step)
 struct ScanCtrl {
-  uint32_t ticket[8];     // tile tickets, one per compaction launch in a step
+  uint32_t n_own[2];      // sharded scans: survivors whose key this rank owns, per ordering
+  uint32_t reserved[6];
   uint32_t n_surv;        // survivors of the classify kernel
   uint32_t max_group;     // max iommu group / parent among survivors (radix pass count)
   uint32_t max_devkey;    // max device / type key among survivors
@@ -783,14 +784,14 @@ __global__ void __launch_bounds__(KVG_BLOCK, 6) k_radix_scatter(RadixArgs2 aa) {
   __shared__ uint32_t scratch[KVG_WARPS + 1];
   __shared__ uint2 s_stage[C_TILE];           // pairs in tile-sorted order (16 KiB)
   uint32_t total;
-  const uint32_t bin_base = block_excl_sum(a.bin_total[tid], scratch, &total);  // syncs inside
+  const uint32_t bin_total_mine = a.bin_total[tid];
+  uint32_t bin_base = 0;
+  bool have_base = false;
   for (uint32_t tile = blockIdx.x; tile < T; tile += gridDim.x) {
   const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
-  __syncthreads();  // previous tile's stage fully written out
-#pragma unroll
-  for (uint32_t w = 0; w < KVG_WARPS; w++) s_cnt[w][tid] = 0;
-  __syncthreads();
-
+  // every global load of the tile is issued before anything waits: the pairs, this digit's
+  // scanned tile count and (first tile only) the digit totals -> ONE memory latency per tile
+  const uint32_t tile_prefix = a.tile_hist[(size_t)tid * T + tile];
   uint2 kv[C_ROWS];
   uint32_t rank[C_ROWS];
 #pragma unroll
@@ -798,6 +799,14 @@ __global__ void __launch_bounds__(KVG_BLOCK, 6) k_radix_scatter(RadixArgs2 aa) {
     uint32_t i = base + k * 32 + lane;
     kv[k] = i < n ? radix_load(a, i) : make_uint2(0, 0);
   }
+  __syncthreads();  // previous tile's stage fully written out
+#pragma unroll
+  for (uint32_t w = 0; w < KVG_WARPS; w++) s_cnt[w][tid] = 0;
+  if (!have_base) {
+    bin_base = block_excl_sum(bin_total_mine, scratch, &total);  // syncs inside
+    have_base = true;
+  }
+  __syncthreads();
   // stable rank inside the warp: rows in order, lanes in order within a row
 #pragma unroll
   for (uint32_t k = 0; k < C_ROWS; k++) {
@@ -827,7 +836,7 @@ __global__ void __launch_bounds__(KVG_BLOCK, 6) k_radix_scatter(RadixArgs2 aa) {
   }
   const uint32_t lstart = block_excl_sum(dtot, scratch, &total);  // syncs inside
   s_start[tid] = lstart;
-  s_goff[tid] = (int32_t)(bin_base + a.tile_hist[(size_t)tid * T + tile]) - (int32_t)lstart;
+  s_goff[tid] = (int32_t)(bin_base + tile_prefix) - (int32_t)lstart;
   __syncthreads();
 #pragma unroll
   for (uint32_t k = 0; k < C_ROWS; k++) {
@@ -1243,6 +1252,50 @@ __global__ void __launch_bounds__(128) k_pack_survivors(const uint4* __restrict_
   const uint4* src = ragged + (size_t)tile * tile_items * UNITS_PER_ITEM;
   uint4* dst = dense + (size_t)o0 * UNITS_PER_ITEM;
   for (uint32_t u = threadIdx.x; u < units; u += blockDim.x) st_stream(dst + u, ld_stream(src + u));
+}
+
+// ---- multi-GPU: key-partitioned bucketing -------------------------------------------------------
+// After the allgatherv every rank holds the full survivor list; rank r orders only the survivors
+// whose key (device id for ordering 0, iommu group for ordering 1) satisfies key % nranks == r.
+// Key sets are disjoint, so the union of the per-rank buckets is the global map and the per-rank
+// ordering work stays constant as GPUs are added.  This op selects the owned {key, index} pairs
+// (same ragged -> offsets -> pack machinery as the classification).
+struct OwnedPairOp {
+  using Item = uint4;  // one kvg_pci_surv
+  const uint4* surv;
+  uint32_t n;
+  uint2* out;
+  uint32_t field;  // 0: device id (ordering 0), 1: iommu group (ordering 1)
+  uint32_t nranks, rank;
+  uint32_t local_max;
+  __device__ __forceinline__ void begin() {}
+  __device__ __forceinline__ uint32_t count() const { return n; }
+  __device__ __forceinline__ Item load(uint32_t i, bool ok) const {
+    return ok ? ld_stream(surv + i) : make_uint4(0, 0, 0, 0);
+  }
+  __device__ __forceinline__ uint32_t key_of(const Item& r) const { return field ? r.y : (r.z & 0xffffu); }
+  __device__ __forceinline__ bool pred(const Item& r, uint32_t) const { return key_of(r) % nranks == rank; }
+  __device__ __forceinline__ uint32_t prepare(const Item& r) const { return key_of(r); }
+  __device__ __forceinline__ void emit(uint32_t pos, const Item&, uint32_t i, uint32_t key) {
+    out[pos] = make_uint2(key, i);
+    local_max = max(local_max, key);
+  }
+  __device__ __forceinline__ void tile_epilogue() {}
+  __device__ __forceinline__ void finish(uint32_t) {}
+  __device__ __forceinline__ uint2 take_maxima() {
+    uint2 m = field ? make_uint2(local_max, 0) : make_uint2(0, local_max);
+    local_max = 0;
+    return m;
+  }
+};
+// dense, order-preserving pack of 8-byte pairs (tile_items pairs of scratch per tile)
+__global__ void __launch_bounds__(128) k_pack_pairs(const uint2* __restrict__ ragged,
+                                                    const uint32_t* __restrict__ tile_off,
+                                                    uint32_t tile_items, uint2* __restrict__ dense) {
+  const uint32_t tile = blockIdx.x;
+  const uint32_t o0 = tile_off[tile], o1 = tile_off[tile + 1];
+  const uint2* src = ragged + (size_t)tile * tile_items;
+  for (uint32_t u = threadIdx.x; u < o1 - o0; u += blockDim.x) dense[o0 + u] = src[u];
 }
 
 // Diagnostic decomposition of the classify kernel (kvg_dev_debug_classify):

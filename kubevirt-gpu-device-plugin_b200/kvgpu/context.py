@@ -131,16 +131,19 @@ class Context:
     def _take_pci(self, res) -> PciResult:
         r = res.contents
         S, KD, G = int(r.n_survivors), int(r.n_dev_keys), int(r.n_groups)
+        dev_off = L._arr(r.dev_off, KD + 1, np.uint32)
+        grp_off = L._arr(r.grp_off, G + 1, np.uint32)
+        # a sharded scan orders only the keys this rank owns: perms are as long as off[-1]
         out = PciResult(
             n_records=int(r.n_records),
             survivors=L._arr(r.survivors, S, L.PCI_SURV),
             dev_keys=L._arr(r.dev_keys, KD, np.uint16),
-            dev_off=L._arr(r.dev_off, KD + 1, np.uint32),
-            dev_perm=L._arr(r.dev_perm, S, np.uint32),
+            dev_off=dev_off,
+            dev_perm=L._arr(r.dev_perm, int(dev_off[-1]), np.uint32),
             dev_name_slot=L._arr(r.dev_name_slot, KD, np.uint32),
             grp_keys=L._arr(r.grp_keys, G, np.uint32),
-            grp_off=L._arr(r.grp_off, G + 1, np.uint32),
-            grp_perm=L._arr(r.grp_perm, S, np.uint32),
+            grp_off=grp_off,
+            grp_perm=L._arr(r.grp_perm, int(grp_off[-1]), np.uint32),
             name_pool=C.string_at(r.name_pool, r.name_pool_len) if r.name_pool_len else b"")
         self._lib.kvg_result_free(res)
         return out

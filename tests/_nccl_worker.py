@@ -43,7 +43,19 @@ def main():
     for rep in range(2):
         sh.scan_device_shard(buf.data_ptr(), hi - lo)
         res = sh.fetch()
-        got = kvgpu.canonical_dump(kvgpu.pci_maps_from_result(res))
+        part = kvgpu.pci_maps_from_result(res)
+        # the bucketing is partitioned by key: rank r owns the keys with key % world == r
+        assert all(int(k, 16) % world == rank for k in part.deviceMap), "foreign device key"
+        assert all(int(k) % world == rank for k in part.iommuMap), "foreign iommu group"
+        parts = [None] * world
+        dist.all_gather_object(parts, (part.deviceMap, part.iommuMap, part.deviceNames))
+        merged = kvgpu.Maps(bdfToIommuMap=part.bdfToIommuMap)   # survivor list is replicated
+        for dm, im, nm in parts:                                # disjoint key sets: plain union
+            assert not (set(dm) & set(merged.deviceMap)) and not (set(im) & set(merged.iommuMap))
+            merged.deviceMap.update(dm)
+            merged.iommuMap.update(im)
+            merged.deviceNames.update(nm)
+        got = kvgpu.canonical_dump(merged)
         m = O.Maps()
         m.create_iommu_device_map_flat(O.gen_pci(0, n, ids, 17))
         want = m.dump(text)
