@@ -1581,10 +1581,15 @@ int kvg_dev_scan_pci_sharded(kvg_ctx* ctx, const void* d_recs, size_t n_local) {
       return KVG_ENCCL;
     }
   }
-  // the orderings are recomputed on every rank from the gathered list (replicated, cheap)
+  // control block for the ordering phase: zero, then n_surv <- total (known on the host; a 4-byte
+  // copy from pinned memory).  The key maxima come from the ownership select (k_tile_offsets).
   CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
-  LAUNCH("gathered_maxima", k_gathered_maxima, ctx->sm_count * 4, KVG_BLOCK, 0,
-         (const kvg_pci_surv*)ctx->surv.p, (uint32_t)total, ctx->ctrl.p);
+  ctx->h_counts[P] = total;  // pinned; low 32 bits are the value (little endian)
+  CK(cudaMemcpyAsync(&ctx->ctrl.p->n_surv, &ctx->h_counts[P], sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (P == 1) {  // single rank: no ownership select runs, so reduce the maxima here
+    LAUNCH("gathered_maxima", k_gathered_maxima, ctx->sm_count * 4, KVG_BLOCK, 0,
+           (const kvg_pci_surv*)ctx->surv.p, (uint32_t)total, ctx->ctrl.p);
+  }
   // bucketing partitioned by key: this rank orders only the keys with key % nranks == rank
   rc = enqueue_pci_orderings(ctx, total, /*owned_only=*/P > 1);
   if (rc) return rc;
