@@ -157,6 +157,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=100_000)
     ap.add_argument("--cpu-sample", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config-3 / config-5 legs")
     ap.add_argument("--big-records", type=int, default=1 << 24,
                     help="records for the HBM-bound roofline leg (N=1 only; 0 disables)")
     ap.add_argument("--big-files", type=int, default=128,
@@ -348,7 +349,7 @@ def main():
 
     # ---- BASELINE.json configs 3 and 5 (extra keys; the headline stays config 2)
     extra = {}
-    if world == 1:
+    if world == 1 and not args.no_extra:
         import ctypes as C
         lib = kvgpu.load()
         # config 3: 65,536 mdev UUIDs over 256 raw type names (128 labels), 2,048 parents

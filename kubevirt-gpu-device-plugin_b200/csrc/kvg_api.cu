@@ -133,6 +133,9 @@ struct kvg_ctx {
   DevBuf<uint8_t> pool;
   DevBuf<uint32_t> nv_index;  // [65536] vendor-10de device id -> name pool slot
   DevBuf<uint32_t> nv_lines;  // [65536 + 1] offsets of the lines that have a name, then their count
+  DevBuf<uint32_t> sec_lines; // '\t' line starts of the NVIDIA section, then their count (general lookups)
+  size_t sec_lines_cap = 0;
+  DevBuf<uint64_t> type_hash;
   std::vector<uint8_t> h_pool;
   PciIdsInfo h_info{};
   bool table_ready = false;
@@ -376,7 +379,7 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   release(ctx->text); release(ctx->tables); release(ctx->info); release(ctx->tile_arrays);
   release(ctx->parse_state); release(ctx->parse_ticket); release(ctx->pool); release(ctx->ctrl);
-  release(ctx->nv_index); release(ctx->nv_lines); release(ctx->ragged); release(ctx->tile_count); release(ctx->tile_off);
+  release(ctx->nv_index); release(ctx->nv_lines); release(ctx->sec_lines); release(ctx->type_hash); release(ctx->ragged); release(ctx->tile_count); release(ctx->tile_off);
   release(ctx->tile_max); release(ctx->offs_state);
   release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist);
   for (OrderBufs* o : {&ctx->ord_dev, &ctx->ord_grp}) {
@@ -534,6 +537,20 @@ static int table_publish(kvg_ctx* ctx, const uint8_t* d_text, size_t len) {
   } else {
     ENSURE(ctx->pool, 16);
   }
+  {  // candidate lines of the general (arbitrary-key) lookup: every '\t' line of the section
+    size_t sec = ctx->h_info.v_off == P_NONE ? 0 : (size_t)ctx->h_info.sec_end - ctx->h_info.v_off;
+    ctx->sec_lines_cap = sec / 2 + 8;  // a line needs >= 2 bytes ("\t\n")
+    ENSURE(ctx->sec_lines, ctx->sec_lines_cap + 1);
+    CK(cudaMemsetAsync(ctx->sec_lines.p + ctx->sec_lines_cap, 0, sizeof(uint32_t), ctx->stream));
+    if (sec) {
+      int grid = (int)((sec + KVG_BLOCK - 1) / KVG_BLOCK);
+      if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+      LAUNCH("section_lines", k_section_lines, grid, KVG_BLOCK, 0, d_text, ctx->info.p, ctx->sec_lines.p,
+             ctx->sec_lines.p + ctx->sec_lines_cap, (uint32_t)ctx->sec_lines_cap);
+      int rc = check_launch(ctx, "section lines");
+      if (rc) return rc;
+    }
+  }
   ctx->table_ready = true;
   return KVG_OK;
 }
@@ -650,13 +667,13 @@ static int lookup_general(kvg_ctx* ctx, const uint8_t* d_keys, const uint32_t* d
   }
   size_t sec = ctx->h_info.v_off == P_NONE ? 0 : (size_t)ctx->h_info.sec_end - ctx->h_info.v_off;
   if (sec) {
-    int gx = (int)((sec + KVG_BLOCK - 1) / KVG_BLOCK);
-    if (gx > 1024) gx = 1024;
+    int gx = (int)((ctx->sec_lines_cap + KVG_BLOCK - 1) / KVG_BLOCK);
+    if (gx > 32) gx = 32;  // a few thousand candidate lines
     for (uint32_t k0 = 0; k0 < n_keys; k0 += 65535) {
       uint32_t nk = n_keys - k0 > 65535 ? 65535 : n_keys - k0;
       dim3 grid(gx, nk);
       LAUNCH("lookup_general", k_lookup_general, grid, KVG_BLOCK, 0, ctx->d_text, ctx->text_len,
-             ctx->info.p, d_keys, d_key_off + k0, d_match + k0);
+             ctx->sec_lines.p, ctx->sec_lines.p + ctx->sec_lines_cap, d_keys, d_key_off + k0, d_match + k0);
     }
   }
   int grid = (int)((n_keys + 63) / 64);
@@ -1174,6 +1191,7 @@ static int load_type_dict(kvg_ctx* ctx, const kvg_type_dict* types) {
   ENSURE(ctx->type_canon, (size_t)nt + 1);
   ENSURE(ctx->type_match, (size_t)nt + 1);
   ENSURE(ctx->type_name_len, (size_t)nt + 1);
+  ENSURE(ctx->type_hash, (size_t)nt + 1);
   ctx->n_types = nt;
   ctx->h_type_off.assign(types->off, types->off + nt + 1);
   if (nt == 0) return KVG_OK;
@@ -1182,9 +1200,9 @@ static int load_type_dict(kvg_ctx* ctx, const kvg_type_dict* types) {
   CK(cudaStreamSynchronize(ctx->stream));  // the caller's dictionary may be freed after return
   int grid = (int)((nt + 63) / 64);
   LAUNCH("mdev_labels", k_mdev_labels, grid, 64, 0, ctx->type_raw.p, ctx->type_off.p, nt,
-         ctx->type_label.p, ctx->type_label_len.p);
+         ctx->type_label.p, ctx->type_label_len.p, ctx->type_hash.p);
   LAUNCH("mdev_canon", k_mdev_canon, grid, 64, 0, ctx->type_label.p, ctx->type_off.p,
-         ctx->type_label_len.p, nt, ctx->type_canon.p);
+         ctx->type_label_len.p, ctx->type_hash.p, nt, ctx->type_canon.p);
   return check_launch(ctx, "mdev labels");
 }
 

@@ -713,24 +713,39 @@ __global__ void k_probe_keys(const uint64_t* __restrict__ table, uint32_t mask, 
   if (i < count) slots[i] = probe_name_slot(table, mask, shift, info, (first + i) & 0xffffu);
 }
 
-// Exact :388-402 for arbitrary keys.  grid.y = key index; threads sweep the section bytes.
-//   candidate = a line start b in (V, E) whose line is not a comment; E already excludes
-//   everything past the first non-'\t' non-'#' line.  match = HasPrefix(line, "\t"+key) on the
-//   token bufio.ScanLines returns (one trailing '\r' dropped).
+// every line start of the NVIDIA section that begins with '\t' (candidates of the prefix match),
+// collected once per table load; order is irrelevant (matches are reduced with atomicMin)
+__global__ void __launch_bounds__(KVG_BLOCK) k_section_lines(const uint8_t* __restrict__ text,
+                                                             const PciIdsInfo* __restrict__ info,
+                                                             uint32_t* __restrict__ lines,
+                                                             uint32_t* __restrict__ n_lines, uint32_t cap) {
+  const uint32_t V = info->v_off, E = info->sec_end;
+  if (V == P_NONE) return;
+  for (uint32_t b = V + 1 + blockIdx.x * blockDim.x + threadIdx.x; b < E; b += gridDim.x * blockDim.x) {
+    if (text[b - 1] == '\n' && text[b] == '\t') {
+      uint32_t k = atomicAdd(n_lines, 1u);
+      if (k < cap) lines[k] = b;
+    }
+  }
+}
+
+// Exact :388-402 for arbitrary keys.  grid.y = key index; threads sweep the section's '\t' lines
+// (E already excludes everything past the first non-'\t' non-'#' line; '#' lines are not listed).
+//   match = HasPrefix(line, "\t"+key) on the token bufio.ScanLines returns (one trailing '\r'
+//   dropped); the first matching line wins (atomicMin on its offset).
 __global__ void __launch_bounds__(KVG_BLOCK) k_lookup_general(const uint8_t* __restrict__ text,
                                                               uint32_t len,
-                                                              const PciIdsInfo* __restrict__ info,
+                                                              const uint32_t* __restrict__ lines,
+                                                              const uint32_t* __restrict__ n_lines_ptr,
                                                               const uint8_t* __restrict__ keys,
                                                               const uint32_t* __restrict__ key_off,
                                                               uint32_t* __restrict__ match_off) {
-  const uint32_t V = info->v_off, E = info->sec_end;
-  if (V == P_NONE) return;
+  const uint32_t n_lines = *n_lines_ptr;
   const uint32_t kidx = blockIdx.y;
   const uint8_t* key = keys + key_off[kidx];
   const uint32_t klen = key_off[kidx + 1] - key_off[kidx];
-  for (uint32_t b = V + 1 + blockIdx.x * blockDim.x + threadIdx.x; b < E;
-       b += gridDim.x * blockDim.x) {
-    if (text[b - 1] != '\n' || text[b] != '\t') continue;  // '#' lines and non-starts skipped
+  for (uint32_t li = blockIdx.x * blockDim.x + threadIdx.x; li < n_lines; li += gridDim.x * blockDim.x) {
+    const uint32_t b = lines[li];
     bool ok = true;
     for (uint32_t k = 0; k < klen && ok; k++) {
       uint32_t pos = b + 1 + k;

@@ -942,7 +942,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_order_final(OrderFinalArgs2 aa) {
 // ------------------------------------------------------------------------------------------------
 __global__ void k_mdev_labels(const uint8_t* __restrict__ raw, const uint32_t* __restrict__ raw_off,
                               uint32_t n_types, uint8_t* __restrict__ label,
-                              uint32_t* __restrict__ label_len) {
+                              uint32_t* __restrict__ label_len, uint64_t* __restrict__ label_hash) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_types) return;
   uint32_t a = raw_off[k], b = raw_off[k + 1];
@@ -950,26 +950,35 @@ __global__ void k_mdev_labels(const uint8_t* __restrict__ raw, const uint32_t* _
   while (b > a && raw[b - 1] == '\n') b--;
   uint8_t* out = label + raw_off[k];  // sanitised text is never longer than the raw text
   uint32_t o = 0;
+  uint64_t h = 1469598103934665603ull;  // FNV-1a of the label: cheap first-level equality test
   for (uint32_t i = a; i < b;) {
+    uint8_t c;
     if (d_re2_space(raw[i])) {
-      out[o++] = '_';
+      c = '_';
       while (i < b && d_re2_space(raw[i])) i++;
     } else {
-      out[o++] = raw[i++];
+      c = raw[i++];
     }
+    out[o++] = c;
+    h = (h ^ c) * 1099511628211ull;
   }
   label_len[k] = o;
+  label_hash[k] = h;
 }
+// canonical id = smallest raw index with an identical label: hash + length first (independent,
+// pipelined loads), bytes only on a hash match
 __global__ void k_mdev_canon(const uint8_t* __restrict__ label, const uint32_t* __restrict__ raw_off,
-                             const uint32_t* __restrict__ label_len, uint32_t n_types,
+                             const uint32_t* __restrict__ label_len,
+                             const uint64_t* __restrict__ label_hash, uint32_t n_types,
                              uint16_t* __restrict__ canon) {
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_types) return;
-  uint32_t len = label_len[k];
+  const uint32_t len = label_len[k];
+  const uint64_t h = label_hash[k];
   const uint8_t* mine = label + raw_off[k];
   uint32_t c = k;
   for (uint32_t j = 0; j < k; j++) {
-    if (label_len[j] != len) continue;
+    if (label_hash[j] != h || label_len[j] != len) continue;
     const uint8_t* other = label + raw_off[j];
     bool eq = true;
     for (uint32_t t = 0; t < len && eq; t++) eq = other[t] == mine[t];
