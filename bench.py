@@ -207,7 +207,13 @@ def main():
                 t.copy_(torch.frombuffer(bytearray(b), dtype=torch.uint8))
             dist.broadcast(t, src)
             return bytes(t.cpu().numpy().tobytes())
-        sharded = kvgpu.ShardedScan(ctx, rank, world, bcast)
+        def allgather(b):
+            t = torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+            outs = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(outs, t)
+            return [bytes(o.cpu().numpy().tobytes()) for o in outs]
+        use_p2p = os.environ.get("KVG_P2P", "1") != "0"
+        sharded = kvgpu.ShardedScan(ctx, rank, world, bcast, allgather if use_p2p else None, n)
 
     def step():
         ctx.dev_pciids_parse(d_text.data_ptr(), len(text), pad + 16, 1)
@@ -489,8 +495,11 @@ def main():
             "config": {"workload": "BASELINE.json configs[1]: full utils/pci.ids (%d B, %d lines) parse "
                                    "+ %d synthetic PCI records per GPU per step%s" % (
                                        len(text), info["n_lines"], n,
-                                       "" if world == 1 else ", range-sharded over %d GPUs, NCCL "
-                                       "allgatherv of survivors" % world),
+                                       "" if world == 1 else ", range-sharded over %d GPUs, survivors all-gathered "
+                                       "(%s), bucketing partitioned by key" % (
+                                           world, "pack fused with peer-memory stores over NVLink"
+                                           if sharded.mode == "p2p" else "NCCL grouped broadcast")),
+                       "exchange": None if world == 1 else sharded.mode,
                        "records_per_gpu": n, "survivors": S, "device_ids": KD, "iommu_groups": G,
                        "iommu_group_order": "bijective scramble of i>>1 (group_bits=%d)" % gbits,
                        "l2": "flushed between timed steps (192 MiB fill, outside the event bracket)",

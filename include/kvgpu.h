@@ -265,6 +265,16 @@ int kvg_set_kernel_timing(kvg_ctx *ctx, int enabled);
 int kvg_comm_unique_id(void *out128);
 int kvg_comm_init(kvg_ctx *ctx, int rank, int nranks, const void *unique_id128);
 int kvg_comm_destroy(kvg_ctx *ctx);
+/* Peer-memory variant of the exchange step (CUDA IPC over NVLink, one process per GPU of ONE node):
+ * export allocates this rank's gather windows for shards of up to cap_local records and returns a
+ * 64-byte handle; import opens all ranks' handles (nranks x 64 bytes, rank order).  Afterwards
+ * kvg_dev_scan_pci_sharded fuses the dense pack with the all-gather (each survivor is stored straight
+ * into every peer's window) and needs neither NCCL nor a host synchronisation.  If either call fails
+ * the NCCL path (kvg_comm_init) remains usable. */
+int kvg_comm_p2p_export(kvg_ctx *ctx, int rank, int nranks, size_t cap_local, void *handle_out64);
+int kvg_comm_p2p_import(kvg_ctx *ctx, const void *all_handles);
+/* collective decision: enable only when import succeeded on every rank */
+int kvg_comm_p2p_enable(kvg_ctx *ctx, int on);
 /* classify the local shard, allgatherv the survivors over NCCL (rank order == Walk order): every rank
  * ends up with the FULL survivor list.  The bucketing is partitioned by key: rank r's orderings
  * (dev_* / grp_* of the fetched result) cover exactly the keys with key % nranks == r, so the key

@@ -190,7 +190,16 @@ struct kvg_ctx {
   DevBuf<uint64_t> gather_counts;  // [nranks]
   DevBuf<uint4> local_surv;
   uint64_t* h_counts = nullptr;  // pinned [nranks]
+  // peer-memory gather (CUDA IPC over NVLink)
+  bool p2p = false;
+  uint8_t* p2p_mine = nullptr;            // [P2PCtrl pad 4 KiB][window 0][window 1]
+  size_t p2p_cap = 0;                     // survivors per region
+  uint8_t* p2p_peer[P2P_MAX_RANKS] = {};  // peer-mapped bases (own entry = p2p_mine)
+  unsigned long long p2p_step = 0;
+  DevBuf<uint32_t> gather_base;
+  DevBuf<uint32_t> p2p_err;
 };
+static const size_t P2P_HDR = 4096;
 
 #define CK(call)                                                                              \
   do {                                                                                        \
@@ -392,6 +401,10 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   release(ctx->changed); release(ctx->flush); release(ctx->nv_ids); release(ctx->probe_slots);
   release(ctx->keys_blob); release(ctx->keys_off); release(ctx->match_off); release(ctx->match_len);
   release(ctx->match_out); release(ctx->gather_counts); release(ctx->local_surv);
+  release(ctx->gather_base); release(ctx->p2p_err);
+  for (int q = 0; q < P2P_MAX_RANKS; q++)
+    if (ctx->p2p_peer[q] && ctx->p2p_peer[q] != ctx->p2p_mine) cudaIpcCloseMemHandle(ctx->p2p_peer[q]);
+  if (ctx->p2p_mine) cudaFree(ctx->p2p_mine);
   for (auto& b : ctx->pinned_free) cudaFreeHost(b.p);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
@@ -1507,6 +1520,71 @@ int kvg_comm_init(kvg_ctx* ctx, int rank, int nranks, const void* unique_id128) 
   return KVG_OK;
 }
 
+// ---- peer-memory gather: set-up ------------------------------------------------------------------
+// kvg_comm_p2p_export: allocate this rank's gather windows for shards of up to cap_local records and
+// return the 64-byte CUDA IPC handle the other ranks need.  kvg_comm_p2p_import: open every rank's
+// handle (all_handles = nranks x 64 bytes, rank order).  After both succeeded kvg_dev_scan_pci_sharded
+// uses the peer-memory path (no NCCL, no host synchronisation).  Any failure leaves the NCCL path.
+int kvg_comm_p2p_export(kvg_ctx* ctx, int rank, int nranks, size_t cap_local, void* handle_out64) {
+  if (!ctx || !handle_out64 || nranks < 1 || nranks > P2P_MAX_RANKS || rank < 0 || rank >= nranks || !cap_local)
+    return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  static_assert(sizeof(P2PCtrl) <= P2P_HDR, "control block fits its pad");
+  if (ctx->p2p_mine) {
+    ctx->err = "peer windows already exported";
+    return KVG_ESTATE;
+  }
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  ctx->p2p_cap = cap_local;
+  const size_t bytes = P2P_HDR + 2 * (size_t)nranks * cap_local * 16;
+  CK(cudaMalloc((void**)&ctx->p2p_mine, bytes));
+  CK(cudaMemset(ctx->p2p_mine, 0, P2P_HDR));
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, ctx->p2p_mine));
+  memcpy(handle_out64, &h, 64);
+  return KVG_OK;
+}
+
+int kvg_comm_p2p_import(kvg_ctx* ctx, const void* all_handles) {
+  if (!ctx || !all_handles || !ctx->p2p_mine) return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  for (int q = 0; q < ctx->nranks; q++) {
+    if (q == ctx->rank) {
+      ctx->p2p_peer[q] = ctx->p2p_mine;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const uint8_t*)all_handles + 64 * (size_t)q, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      ctx->err = std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(q) + "): " + cudaGetErrorString(e);
+      cudaGetLastError();
+      return KVG_ECUDA;
+    }
+    ctx->p2p_peer[q] = (uint8_t*)p;
+  }
+  ENSURE(ctx->gather_base, P2P_MAX_RANKS + 2);
+  ENSURE(ctx->p2p_err, 4);
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->p2p_step = 0;
+  return KVG_OK;
+}
+
+// switch the sharded scan between the peer-memory path (on != 0; needs a successful import on EVERY
+// rank — the caller agrees on that collectively) and the NCCL path
+int kvg_comm_p2p_enable(kvg_ctx* ctx, int on) {
+  if (!ctx) return KVG_EINVAL;
+  if (on && (!ctx->p2p_mine || !ctx->gather_base.p)) {
+    ctx->err = "peer windows are not imported";
+    return KVG_ESTATE;
+  }
+  ctx->p2p = on != 0;
+  return KVG_OK;
+}
+
 int kvg_comm_destroy(kvg_ctx* ctx) {
   if (!ctx) return KVG_EINVAL;
   if (ctx->comm) {
@@ -1520,6 +1598,83 @@ int kvg_comm_destroy(kvg_ctx* ctx) {
 }
 
 }  // extern "C"
+
+// Sharded scan over peer memory: classify -> offsets -> [pack fused with the all-gather] -> signal;
+// wait for all regions -> dense copy -> ack; key-partitioned orderings.  Fully asynchronous.
+static int scan_sharded_p2p(kvg_ctx* ctx, const void* d_recs, size_t n_local) {
+  const int P = ctx->nranks;
+  if (n_local > ctx->p2p_cap) {
+    ctx->err = "shard larger than the exported peer window";
+    return KVG_ERANGE;
+  }
+  const size_t cap_total = (size_t)P * ctx->p2p_cap;
+  ENSURE(ctx->surv, cap_total + 1);
+  constexpr int T = 128, R = 8;
+  const size_t tiles = (n_local + (size_t)T * R - 1) / ((size_t)T * R);
+  ENSURE(ctx->ragged, (tiles ? tiles : 1) * T * R);
+  ENSURE(ctx->tile_count, tiles + 1);
+  ENSURE(ctx->tile_off, tiles + 2);
+  ENSURE(ctx->tile_max, tiles + 1);
+  const unsigned chunks = (unsigned)((tiles + C_TILE - 1) / C_TILE);
+  ENSURE(ctx->offs_state, (size_t)chunks + 2);
+  const unsigned long long step = ++ctx->p2p_step;
+  const uint32_t w = (uint32_t)(step & 1);
+  P2PPeers peers;
+  memset(&peers, 0, sizeof peers);
+  for (int q = 0; q < P; q++) {
+    peers.ctrl[q] = (P2PCtrl*)ctx->p2p_peer[q];
+    peers.win[q] = (uint4*)(ctx->p2p_peer[q] + P2P_HDR) + (size_t)w * cap_total;
+  }
+  P2PCtrl* mine = (P2PCtrl*)ctx->p2p_mine;
+  const uint4* my_window = (const uint4*)(ctx->p2p_mine + P2P_HDR) + (size_t)w * cap_total;
+
+  CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
+  CK(cudaMemsetAsync(ctx->p2p_err.p, 0, sizeof(uint32_t), ctx->stream));
+  if (step > 2) LAUNCH("p2p_wait_acks", k_p2p_wait_acks, 1, 32, 0, mine, (uint32_t)P, step - 2, ctx->p2p_err.p);
+  if (tiles) {
+    PciClassifyOp op;
+    op.recs = (const uint4*)d_recs;
+    op.n = (uint32_t)n_local;
+    op.out = (kvg_pci_surv*)ctx->ragged.p;
+    op.ctrl = ctx->ctrl.p;
+    op.table = ctx->tables.p;
+    op.cap_mask = (1u << ctx->cap_log2) - 1;
+    op.cap_shift = 32 - ctx->cap_log2;
+    op.info = ctx->info.p;
+    op.nv_index = ctx->nv_index.p;
+    op.local_max_group = 0;
+    op.local_max_dev = 0;
+    LAUNCH("classify_compact", (k_classify_ragged<PciClassifyOp, T, R>), (unsigned)tiles, T, 0, op,
+           ctx->tile_count.p, ctx->tile_max.p);
+    TileOffsetsArgs2 tt;
+    tt.o[0] = {ctx->tile_count.p, ctx->tile_max.p, nullptr, (uint32_t)tiles, ctx->tile_off.p,
+               &ctx->ctrl.p->n_own[0], ctx->offs_state.p};  // n_own[0] doubles as "local count" here
+    tt.o[1] = tt.o[0];
+    LAUNCH("tile_offsets", k_tile_offsets, chunks, KVG_BLOCK, 0, tt, ctx->ctrl.p, next_epoch());
+    // the pack IS the all-gather: every survivor goes straight into every peer's window
+    LAUNCH("pack_to_peers", k_pack_to_peers, (unsigned)tiles, 128, 0, (const uint4*)ctx->ragged.p,
+           ctx->tile_off.p, (uint32_t)(T * R), peers, (uint32_t)P, (size_t)ctx->rank * ctx->p2p_cap);
+  }
+  LAUNCH("p2p_signal", k_p2p_signal, 1, 32, 0, peers, (uint32_t)P, (uint32_t)ctx->rank, w, step,
+         &ctx->ctrl.p->n_own[0]);
+  LAUNCH("p2p_wait_gather", k_p2p_wait_gather, 1, 32, 0, mine, (uint32_t)P, w, step, ctx->gather_base.p,
+         ctx->ctrl.p, ctx->p2p_err.p);
+  dim3 cgrid((unsigned)std::max(1, ctx->sm_count * 2 / P), (unsigned)P);
+  LAUNCH("p2p_copy_regions", k_p2p_copy_regions, cgrid, KVG_BLOCK, 0, my_window, ctx->p2p_cap,
+         ctx->gather_base.p, ctx->surv.p);
+  LAUNCH("p2p_ack", k_p2p_ack, 1, 32, 0, peers, (uint32_t)P, (uint32_t)ctx->rank, step);
+  int rc = check_launch(ctx, "p2p gather");
+  if (rc) return rc;
+  // n_own[0] was used as scratch for the local count: the ownership select rewrites it.  The key
+  // maxima reduced by k_tile_offsets (local shard, then the owned pairs) bound the radix passes.
+  rc = enqueue_pci_orderings(ctx, cap_total, /*owned_only=*/P > 1);
+  if (rc) return rc;
+  ctx->last_n = n_local;
+  ctx->last_total = cap_total;
+  ctx->last_kind = 1;
+  ctx->last_owned = P > 1;
+  return KVG_OK;
+}
 
 // after the gather: n_surv <- total, maxima already all-reduced by construction (each rank
 // recomputes them from the gathered list)
@@ -1542,8 +1697,8 @@ extern "C" {
 
 int kvg_dev_scan_pci_sharded(kvg_ctx* ctx, const void* d_recs, size_t n_local) {
   if (!ctx || (!d_recs && n_local) || n_local > 0xfffffff0ull) return KVG_EINVAL;
-  if (!ctx->comm) {
-    ctx->err = "kvg_comm_init has not been called";
+  if (!ctx->comm && !ctx->p2p) {
+    ctx->err = "kvg_comm_init / kvg_comm_p2p_import has not been called";
     return KVG_ESTATE;
   }
   if (!ctx->table_ready) {
@@ -1552,6 +1707,7 @@ int kvg_dev_scan_pci_sharded(kvg_ctx* ctx, const void* d_recs, size_t n_local) {
   }
   CK(cudaSetDevice(ctx->device));
   const int P = ctx->nranks;
+  if (ctx->p2p) return scan_sharded_p2p(ctx, d_recs, n_local);
   ENSURE(ctx->local_surv, n_local + 1);
   CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
   int rc = enqueue_classify(ctx, d_recs, n_local, ctx->local_surv.p);

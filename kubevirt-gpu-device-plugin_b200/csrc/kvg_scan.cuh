@@ -1307,6 +1307,107 @@ __global__ void __launch_bounds__(128) k_pack_pairs(const uint2* __restrict__ ra
   for (uint32_t u = threadIdx.x; u < o1 - o0; u += blockDim.x) dense[o0 + u] = src[u];
 }
 
+// ---- multi-GPU over peer memory (NVLink, CUDA IPC): compaction fused with the all-gather -----------
+// Every rank owns a "gather window" with one region per rank.  k_pack_to_peers is the dense pack of
+// the classification AND the collective: each 16-byte survivor is stored into region `rank` of every
+// peer's window (P-1 NVLink stores + 1 local) at its final rank-local position.  Counts and completion
+// travel as release/acquire flags in the peers' control blocks; nothing returns to the host.
+// Two windows alternate by step parity and a consumed-ack per rank protects their reuse.
+constexpr int P2P_MAX_RANKS = 16;
+struct P2PCtrl {  // lives at the head of every rank's window allocation; written by the peers
+  unsigned long long flag[2][P2P_MAX_RANKS];  // [window][src rank] = step whose region is complete
+  unsigned long long ack[P2P_MAX_RANKS];      // [rank] = last step that rank has consumed
+  uint32_t count[2][P2P_MAX_RANKS];           // [window][src rank] survivors in the region
+};
+struct P2PPeers {
+  uint4* win[P2P_MAX_RANKS];     // window base (of the step's parity) on every rank, peer-mapped
+  P2PCtrl* ctrl[P2P_MAX_RANKS];  // control block of every rank, peer-mapped
+};
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+constexpr long long P2P_SPIN_LIMIT = 20000000000ll;  // ~10 s of SM clocks, then give up loudly
+
+// before reusing a window: every peer must have consumed the step that used it two steps ago
+__global__ void k_p2p_wait_acks(const P2PCtrl* mine, uint32_t P, unsigned long long need, uint32_t* err) {
+  const uint32_t q = threadIdx.x;
+  if (q >= P) return;
+  const long long t0 = clock64();
+  while (ld_acquire_sys(&mine->ack[q]) < need) {
+    if (clock64() - t0 > P2P_SPIN_LIMIT) {
+      atomicExch(err, 1u);
+      return;
+    }
+  }
+}
+__global__ void __launch_bounds__(128) k_pack_to_peers(const uint4* __restrict__ ragged,
+                                                       const uint32_t* __restrict__ tile_off,
+                                                       uint32_t tile_items, P2PPeers peers, uint32_t P,
+                                                       size_t region_off) {
+  const uint32_t tile = blockIdx.x;
+  const uint32_t o0 = tile_off[tile], o1 = tile_off[tile + 1];
+  const uint4* src = ragged + (size_t)tile * tile_items;
+  for (uint32_t u = threadIdx.x; u < o1 - o0; u += blockDim.x) {
+    const uint4 v = ld_stream(src + u);
+    for (uint32_t q = 0; q < P; q++) peers.win[q][region_off + o0 + u] = v;  // NVLink stores
+  }
+}
+__global__ void k_p2p_signal(P2PPeers peers, uint32_t P, uint32_t rank, uint32_t w, unsigned long long step,
+                             const uint32_t* n_local) {
+  const uint32_t q = threadIdx.x;
+  if (q >= P) return;
+  peers.ctrl[q]->count[w][rank] = *n_local;
+  __threadfence_system();
+  st_release_sys(&peers.ctrl[q]->flag[w][rank], step);
+}
+// wait for every region of this step, then publish the region bases and the total
+__global__ void k_p2p_wait_gather(const P2PCtrl* mine, uint32_t P, uint32_t w, unsigned long long step,
+                                  uint32_t* gather_base, ScanCtrl* ctrl, uint32_t* err) {
+  __shared__ uint32_t cnt[P2P_MAX_RANKS];
+  const uint32_t q = threadIdx.x;
+  if (q < P) {
+    const long long t0 = clock64();
+    bool ok = true;
+    while (ld_acquire_sys(&mine->flag[w][q]) != step) {
+      if (clock64() - t0 > P2P_SPIN_LIMIT) {
+        atomicExch(err, 1u);
+        ok = false;
+        break;
+      }
+    }
+    cnt[q] = ok ? *((volatile const uint32_t*)&mine->count[w][q]) : 0;
+  }
+  __syncthreads();
+  if (q == 0) {
+    uint32_t run = 0;
+    for (uint32_t r = 0; r < P; r++) {
+      gather_base[r] = run;
+      run += cnt[r];
+    }
+    gather_base[P] = run;
+    ctrl->n_surv = run;
+  }
+}
+// window regions (rank order == Walk order) -> the dense survivor array every later kernel uses
+__global__ void __launch_bounds__(KVG_BLOCK) k_p2p_copy_regions(const uint4* __restrict__ window, size_t cap,
+                                                                const uint32_t* __restrict__ gather_base,
+                                                                uint4* __restrict__ dense) {
+  const uint32_t q = blockIdx.y;
+  const uint32_t b0 = gather_base[q], n = gather_base[q + 1] - b0;
+  const uint4* src = window + (size_t)q * cap;
+  for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x)
+    st_stream(dense + b0 + u, ld_stream(src + u));
+}
+__global__ void k_p2p_ack(P2PPeers peers, uint32_t P, uint32_t rank, unsigned long long step) {
+  const uint32_t q = threadIdx.x;
+  if (q < P) st_release_sys(&peers.ctrl[q]->ack[rank], step);
+}
+
 // Diagnostic decomposition of the classify kernel (kvg_dev_debug_classify):
 //   mode 0  read + predicate + count only (one atomicAdd per tile)
 //   mode 1  + write survivors at a TILE-LOCAL base (no cross-tile dependency, output not compact)

@@ -127,6 +127,9 @@ def load() -> C.CDLL:
         "kvg_comm_unique_id": (C.c_int, [vp]),
         "kvg_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
         "kvg_comm_destroy": (C.c_int, [vp]),
+        "kvg_comm_p2p_export": (C.c_int, [vp, C.c_int, C.c_int, sz, vp]),
+        "kvg_comm_p2p_import": (C.c_int, [vp, vp]),
+        "kvg_comm_p2p_enable": (C.c_int, [vp, C.c_int]),
         "kvg_dev_scan_pci_sharded": (C.c_int, [vp, vp, sz]),
     }
     for name, (res, args) in sig.items():

@@ -275,6 +275,18 @@ class Context:
         buf = C.create_string_buffer(uid, 128)
         self._ck(self._lib.kvg_comm_init(self._h, rank, nranks, buf))
 
+    def comm_p2p_export(self, rank: int, nranks: int, cap_local: int) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self._lib.kvg_comm_p2p_export(self._h, rank, nranks, cap_local, buf))
+        return buf.raw
+
+    def comm_p2p_import(self, all_handles: bytes):
+        buf = C.create_string_buffer(all_handles, len(all_handles))
+        self._ck(self._lib.kvg_comm_p2p_import(self._h, buf))
+
+    def comm_p2p_enable(self, on: bool):
+        self._ck(self._lib.kvg_comm_p2p_enable(self._h, 1 if on else 0))
+
     def comm_destroy(self):
         self._ck(self._lib.kvg_comm_destroy(self._h))
 

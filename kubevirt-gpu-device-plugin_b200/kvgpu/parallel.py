@@ -54,12 +54,32 @@ def allgatherv_torch(local, dist_mod=None):
 
 
 class ShardedScan:
-    def __init__(self, ctx: Context, rank: int, world: int, broadcast_bytes):
-        """broadcast_bytes(b: bytes | None, src=0) -> bytes : collective byte broadcast."""
+    def __init__(self, ctx: Context, rank: int, world: int, broadcast_bytes, allgather_bytes=None,
+                 p2p_cap: int = 0):
+        """broadcast_bytes(b: bytes | None, src=0) -> bytes : collective byte broadcast (NCCL unique id).
+        allgather_bytes(b: bytes) -> list[bytes] (rank order) + p2p_cap (records per shard): also set
+        up the peer-memory exchange (CUDA IPC over NVLink); on any failure the NCCL path is used."""
         self.ctx, self.rank, self.world = ctx, rank, world
+        self.mode = "nccl"
         uid = ctx.comm_unique_id() if rank == 0 else None
         uid = broadcast_bytes(uid, 0)
         ctx.comm_init(rank, world, uid)
+        if allgather_bytes is not None and p2p_cap > 0:
+            try:
+                mine = ctx.comm_p2p_export(rank, world, p2p_cap)
+                ok = b"\1"
+            except Exception:
+                mine, ok = b"\0" * 64, b"\0"
+            blobs = allgather_bytes(mine + ok)            # every rank learns whether all exported
+            if all(b[64:65] == b"\1" for b in blobs):
+                try:
+                    ctx.comm_p2p_import(b"".join(b[:64] for b in blobs))
+                    good = b"\1"
+                except Exception:
+                    good = b"\0"
+                if all(g == b"\1" for g in allgather_bytes(good)):
+                    ctx.comm_p2p_enable(True)
+                    self.mode = "p2p"
 
     def scan_device_shard(self, d_recs: int, n_local: int):
         self.ctx.dev_scan_pci_sharded(d_recs, n_local)

@@ -35,12 +35,22 @@ def main():
         dist.broadcast(t, src)
         return bytes(t.cpu().numpy().tobytes())
 
-    sh = kvgpu.ShardedScan(ctx, rank, world, bcast)
+    def allgather(b):
+        t = torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        return [bytes(o.cpu().numpy().tobytes()) for o in outs]
+
+    mode = sys.argv[2] if len(sys.argv) > 2 else "p2p"
+    sh = kvgpu.ShardedScan(ctx, rank, world, bcast, allgather if mode == "p2p" else None,
+                           (n + world - 1) // world + 1)
+    if mode == "p2p" and sh.mode != "p2p" and rank == 0:
+        print("note: peer-memory path unavailable, fell back to NCCL")
     lo, hi = kvgpu.shard_range(n, rank, world)
     buf = torch.empty(max(hi - lo, 1) * 16, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
     ctx.dev_gen_pci(buf.data_ptr(), lo, hi - lo, ids, 17)
-    for rep in range(2):
+    for rep in range(4):   # > 2: exercises window reuse and the consumed-acks
         sh.scan_device_shard(buf.data_ptr(), hi - lo)
         res = sh.fetch()
         part = kvgpu.pci_maps_from_result(res)
@@ -63,7 +73,7 @@ def main():
             rank, rep, hashlib.sha256(got).hexdigest()[:12], hashlib.sha256(want).hexdigest()[:12])
     dist.barrier()
     if rank == 0:
-        print("nccl-ok world=%d n=%d sha=%s" % (world, n, hashlib.sha256(got).hexdigest()[:16]))
+        print("nccl-ok world=%d n=%d sha=%s exchange=%s" % (world, n, hashlib.sha256(got).hexdigest()[:16], sh.mode))
     sh.close()
     ctx.close()
     dist.destroy_process_group()
