@@ -833,7 +833,7 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1, bool 
     for (int ord = 0; ord < 2; ord++) {
       OwnedPairOp op;
       op.surv = ctx->surv.p;
-      op.n = (uint32_t)cap;
+      op.n_ptr = &c->n_surv;  // launches are sized for `cap`; tiles past the count retire at once
       op.out = (uint2*)ctx->ragged.p;
       op.field = (uint32_t)ord;
       op.nranks = (uint32_t)ctx->nranks;

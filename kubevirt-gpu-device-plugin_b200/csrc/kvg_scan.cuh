@@ -1272,13 +1272,13 @@ __global__ void __launch_bounds__(128) k_pack_survivors(const uint4* __restrict_
 struct OwnedPairOp {
   using Item = uint4;  // one kvg_pci_surv
   const uint4* surv;
-  uint32_t n;
+  const uint32_t* n_ptr;  // gathered survivor count lives on the device (peer-memory path: never on the host)
   uint2* out;
   uint32_t field;  // 0: device id (ordering 0), 1: iommu group (ordering 1)
   uint32_t nranks, rank;
   uint32_t local_max;
   __device__ __forceinline__ void begin() {}
-  __device__ __forceinline__ uint32_t count() const { return n; }
+  __device__ __forceinline__ uint32_t count() const { return *n_ptr; }
   __device__ __forceinline__ Item load(uint32_t i, bool ok) const {
     return ok ? ld_stream(surv + i) : make_uint4(0, 0, 0, 0);
   }

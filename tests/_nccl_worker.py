@@ -50,9 +50,14 @@ def main():
     buf = torch.empty(max(hi - lo, 1) * 16, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
     ctx.dev_gen_pci(buf.data_ptr(), lo, hi - lo, ids, 17)
+    trace = os.environ.get("KVG_WORKER_TRACE") == "1"
     for rep in range(4):   # > 2: exercises window reuse and the consumed-acks
+        if trace:
+            print("rank %d rep %d scan" % (rank, rep), file=sys.stderr, flush=True)
         sh.scan_device_shard(buf.data_ptr(), hi - lo)
         res = sh.fetch()
+        if trace:
+            print("rank %d rep %d fetched S=%d" % (rank, rep, len(res.survivors)), file=sys.stderr, flush=True)
         part = kvgpu.pci_maps_from_result(res)
         # the bucketing is partitioned by key: rank r owns the keys with key % world == r
         assert all(int(k, 16) % world == rank for k in part.deviceMap), "foreign device key"
@@ -80,4 +85,14 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # a failing rank must take the job down instead of hanging in collective teardown: dump where
+    # every thread is if the run stalls, and leave without running destructors on an exception
+    import faulthandler
+    import traceback
+    faulthandler.dump_traceback_later(int(os.environ.get("KVG_WORKER_STALL_S", "150")), exit=True)
+    try:
+        main()
+    except BaseException:
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)

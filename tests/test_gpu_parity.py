@@ -439,9 +439,9 @@ def test_sharded_scan_matches_oracle(n, mode):
     world = min(_gpu_count(), 8)
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-           "--master-addr", "127.0.0.1", "--master-port", str(29600 + n % 300),
+           "--master-addr", "127.0.0.1", "--master-port", str(29600 + n % 300 + (0 if mode == "p2p" else 301)),
            os.path.join(here, "_nccl_worker.py"), str(n), mode]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=400)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert "nccl-ok world=%d n=%d" % (world, n) in r.stdout
 
