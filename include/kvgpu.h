@@ -199,7 +199,12 @@ void *kvg_stream(kvg_ctx *ctx);
 /* ---- pci.ids name table (getDeviceName, device_plugin.go:371-438) --------------------------- */
 
 /* Parse `text` on the GPU: line split, vendor context, (vendor,device)->line hash, NVIDIA
- * section bounds, sanitised names.  Idempotent: a second call replaces the table. */
+ * section bounds, sanitised names.  Idempotent: a second call replaces the table.
+ * Pageable `text` (Go, Python bytes): copied and published before the call returns.
+ * Page-locked `text` (cudaHostAlloc / cudaHostRegister): the call only ENQUEUES copy + parse, so
+ * that the next call's host-to-device traffic overlaps it; the buffer must stay valid, and a
+ * table-capacity error is reported, by the first later call on `ctx` that consumes the table
+ * (kvg_name_lookup / kvg_name_table / kvg_pciids_info / any scan). */
 int kvg_pciids_load(kvg_ctx *ctx, const uint8_t *text, size_t len);
 
 /* Exact getDeviceName(key) for ANY key bytes: "" (outlen 0) when not found.  4-lower-hex keys go
@@ -219,6 +224,8 @@ int kvg_pciids_info(kvg_ctx *ctx, uint32_t *vendor_off, uint32_t *section_end, u
 
 /* ---- scans, host buffers in / host results out (the reference-facing calls) ---------------- */
 int kvg_scan_pci(kvg_ctx *ctx, const kvg_pci_rec *recs, size_t n, kvg_pci_result **res);
+/* (128 Ki <= n <= 16 Mi records: the snapshot is copied, classified and its survivors returned
+ *  chunk by chunk on separate copy streams; results are identical.  KVG_PIPELINE=0 disables.) */
 int kvg_scan_mdev(kvg_ctx *ctx, const kvg_mdev_rec *recs, size_t n, const kvg_type_dict *types,
                   kvg_mdev_result **res);
 /* Classify `recs`, diff against the alive-set of the previous call on this context (first call:

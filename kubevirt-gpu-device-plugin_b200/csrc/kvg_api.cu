@@ -139,6 +139,12 @@ struct kvg_ctx {
   std::vector<uint8_t> h_pool;
   PciIdsInfo h_info{};
   bool table_ready = false;
+  // kvg_pciids_load only ENQUEUES (copy + parse); the host-side publication (overflow check, name
+  // pool mirror) happens in the first call that consumes the table -> the next call's host-to-device
+  // copy overlaps the parse
+  bool load_pending = false;
+  size_t pend_len = 0, pend_stride = 0;
+  uint32_t pend_cap_log2 = 0;
   uint32_t parsed_files = 0;
   int parse_grid = 0;
 
@@ -179,6 +185,10 @@ struct kvg_ctx {
   std::vector<PinnedBlock> pinned_free;
   void* h_stage = nullptr;
   size_t h_stage_cap = 0;
+  // pipelined host entry point (kvg_scan_pci): copy streams, per-chunk events, mapped counters
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  std::vector<cudaEvent_t> pipe_ev;
+  uint32_t* h_pipe = nullptr;  // pinned + mapped: cumulative survivor count after each chunk
   // kernel timing
   bool timing = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
@@ -262,10 +272,36 @@ struct LaunchScope {
     if (idx != (size_t)-1) cudaEventRecord(ctx->ev[idx].second, ctx->stream);
   }
 };
-#define LAUNCH(name, kernel, grid, block, smem, ...)              \
-  do {                                                            \
-    LaunchScope ls_(ctx, name);                                   \
-    kernel<<<grid, block, smem, ctx->stream>>>(__VA_ARGS__);      \
+// Launches carry the programmatic-stream-serialization attribute (PDL): the next kernel's CTAs are
+// scheduled while this one drains and park in griddepcontrol.wait (pdl_enter() in every kernel), which
+// removes most of the dependent-launch gap of the ~40-kernel scan.  KVG_PDL=0 restores plain launches.
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("KVG_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+template <class... KArgs, class... Args>
+static void launch_kernel(kvg_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = (pdl_enabled() && !ctx->timing) ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define LAUNCH(name, kernel, grid, block, smem, ...)                                   \
+  do {                                                                                 \
+    LaunchScope ls_(ctx, name);                                                        \
+    launch_kernel(ctx, kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__);  \
   } while (0)
 
 static int check_launch(kvg_ctx* ctx, const char* what) {
@@ -385,6 +421,8 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->s_h2d) cudaStreamSynchronize(ctx->s_h2d);
+  if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   release(ctx->text); release(ctx->tables); release(ctx->info); release(ctx->tile_arrays);
   release(ctx->parse_state); release(ctx->parse_ticket); release(ctx->pool); release(ctx->ctrl);
@@ -409,6 +447,10 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
   if (ctx->h_counts) cudaFreeHost(ctx->h_counts);
+  if (ctx->h_pipe) cudaFreeHost(ctx->h_pipe);
+  for (cudaEvent_t e : ctx->pipe_ev) cudaEventDestroy(e);
+  if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+  if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
   for (auto& p : ctx->ev) {
     cudaEventDestroy(p.first);
     cudaEventDestroy(p.second);
@@ -572,12 +614,15 @@ static int table_publish(kvg_ctx* ctx, const uint8_t* d_text, size_t len) {
 // denser device lines overflows it, which K1 reports instead of spinning: re-parse with a table
 // sized from the line count until the load factor is sane.
 static int parse_with_regrow(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t stride,
-                             uint32_t n_files) {
-  uint32_t cap_log2 = table_log2_for(len);
+                             uint32_t n_files, bool enqueued = false, uint32_t cap_log2 = 0) {
+  if (!enqueued) cap_log2 = table_log2_for(len);
   for (;;) {
-    int rc = parse_enqueue(ctx, d_text, len, stride, n_files, cap_log2);
-    if (rc) return rc;
-    rc = table_publish(ctx, d_text, len);
+    if (!enqueued) {
+      int rc = parse_enqueue(ctx, d_text, len, stride, n_files, cap_log2);
+      if (rc) return rc;
+    }
+    enqueued = false;
+    int rc = table_publish(ctx, d_text, len);
     if (rc) return rc;
     size_t cap = (size_t)1 << cap_log2;
     bool crowded = (size_t)ctx->h_info.n_entries * 10 > cap * 5;
@@ -592,10 +637,25 @@ static int parse_with_regrow(kvg_ctx* ctx, const uint8_t* d_text, size_t len, si
   }
 }
 
+// complete a pending kvg_pciids_load (see load_pending), then require a published table
+static int table_needed(kvg_ctx* ctx, const char* why_missing) {
+  if (ctx->load_pending) {
+    ctx->load_pending = false;
+    int rc = parse_with_regrow(ctx, ctx->text.p, ctx->pend_len, ctx->pend_stride, 1, true, ctx->pend_cap_log2);
+    if (rc) return rc;
+  }
+  if (!ctx->table_ready) {
+    ctx->err = why_missing;
+    return KVG_ESTATE;
+  }
+  return KVG_OK;
+}
+
 int kvg_pciids_load(kvg_ctx* ctx, const uint8_t* text, size_t len) {
   if (!ctx || (!text && len)) return KVG_EINVAL;
   CK(cudaSetDevice(ctx->device));
   ctx->table_ready = false;
+  ctx->load_pending = false;
   if (len == 0) {  // an empty file: locateVendor fails, every lookup is "" (:382-385)
     ENSURE(ctx->info, 1);
     ENSURE(ctx->tables, 1024);
@@ -611,8 +671,22 @@ int kvg_pciids_load(kvg_ctx* ctx, const uint8_t* text, size_t len) {
   size_t padded = kvg_text_pad(len);
   ENSURE(ctx->text, padded);
   CK(cudaMemsetAsync(ctx->text.p, '\n', padded, ctx->stream));
+  // the caller's buffer must stay readable until the copy has run: pinned memory is copied
+  // asynchronously (the caller keeps it alive until the next consuming call, as with any cudaMemcpyAsync
+  // source), pageable memory is copied synchronously by the runtime's own staging
   CK(cudaMemcpyAsync(ctx->text.p, text, len, cudaMemcpyHostToDevice, ctx->stream));
-  return parse_with_regrow(ctx, ctx->text.p, len, padded, 1);
+  const uint32_t cap_log2 = table_log2_for(len);
+  int rc = parse_enqueue(ctx, ctx->text.p, len, padded, 1, cap_log2);
+  if (rc) return rc;
+  cudaPointerAttributes attr;
+  bool pinned = cudaPointerGetAttributes(&attr, text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (!pinned) return parse_with_regrow(ctx, ctx->text.p, len, padded, 1, true, cap_log2);
+  ctx->load_pending = true;
+  ctx->pend_len = len;
+  ctx->pend_stride = padded;
+  ctx->pend_cap_log2 = cap_log2;
+  return KVG_OK;
 }
 
 int kvg_dev_pciids_parse(kvg_ctx* ctx, const void* d_text, size_t len, size_t stride, uint32_t n_files) {
@@ -622,6 +696,10 @@ int kvg_dev_pciids_parse(kvg_ctx* ctx, const void* d_text, size_t len, size_t st
   CK(cudaSetDevice(ctx->device));
   // first call on an image publishes (host mirror of the name pool, table sizing); later calls on
   // the same image stay fully asynchronous: parse + finalize + sanitise enqueued, no host sync
+  if (ctx->load_pending) {
+    int rc_t = table_needed(ctx, "");
+    if (rc_t && rc_t != KVG_ESTATE) return rc_t;
+  }
   if (!ctx->table_ready || ctx->d_text != d_text || ctx->text_len != len || ctx->parsed_files != n_files) {
     int rc0 = parse_with_regrow(ctx, (const uint8_t*)d_text, len, stride, n_files);
     if (rc0 == KVG_OK) ctx->parsed_files = n_files;
@@ -640,9 +718,9 @@ int kvg_dev_pciids_parse(kvg_ctx* ctx, const void* d_text, size_t len, size_t st
 int kvg_pciids_info(kvg_ctx* ctx, uint32_t* vendor_off, uint32_t* section_end, uint32_t* n_entries,
                     uint32_t* n_lines) {
   if (!ctx) return KVG_EINVAL;
-  if (!ctx->table_ready) {
-    ctx->err = "kvg_pciids_load has not been called";
-    return KVG_ESTATE;
+  {
+    int rc_t = table_needed(ctx, "kvg_pciids_load has not been called");
+    if (rc_t) return rc_t;
   }
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpyAsync(&ctx->h_info, ctx->info.p, sizeof(PciIdsInfo), cudaMemcpyDeviceToHost, ctx->stream));
@@ -697,9 +775,9 @@ static int lookup_general(kvg_ctx* ctx, const uint8_t* d_keys, const uint32_t* d
 
 int kvg_name_lookup(kvg_ctx* ctx, const char* key, size_t keylen, char* out, size_t cap, size_t* outlen) {
   if (!ctx || (!key && keylen) || !outlen) return KVG_EINVAL;
-  if (!ctx->table_ready) {
-    ctx->err = "kvg_pciids_load has not been called";
-    return KVG_ESTATE;
+  {
+    int rc_t = table_needed(ctx, "kvg_pciids_load has not been called");
+    if (rc_t) return rc_t;
   }
   CK(cudaSetDevice(ctx->device));
   *outlen = 0;
@@ -748,9 +826,9 @@ int kvg_name_lookup(kvg_ctx* ctx, const char* key, size_t keylen, char* out, siz
 
 int kvg_name_table(kvg_ctx* ctx, uint32_t first, uint32_t count, uint32_t* out_off, uint8_t* out_bytes, size_t cap) {
   if (!ctx || !out_off || (!out_bytes && cap) || (uint64_t)first + count > 65536) return KVG_EINVAL;
-  if (!ctx->table_ready) {
-    ctx->err = "kvg_pciids_load has not been called";
-    return KVG_ESTATE;
+  {
+    int rc_t = table_needed(ctx, "kvg_pciids_load has not been called");
+    if (rc_t) return rc_t;
   }
   CK(cudaSetDevice(ctx->device));
   out_off[0] = 0;
@@ -999,9 +1077,9 @@ extern "C" {
 
 int kvg_dev_scan_pci(kvg_ctx* ctx, const void* d_recs, size_t n) {
   if (!ctx || (!d_recs && n) || n > 0xfffffff0ull || ((uintptr_t)d_recs & 15)) return KVG_EINVAL;
-  if (!ctx->table_ready) {
-    ctx->err = "kvg_pciids_load must precede a scan (the scan joins names)";
-    return KVG_ESTATE;
+  {
+    int rc_t = table_needed(ctx, "kvg_pciids_load must precede a scan (the scan joins names)");
+    if (rc_t) return rc_t;
   }
   CK(cudaSetDevice(ctx->device));
   ENSURE(ctx->surv, n + 1);
@@ -1030,18 +1108,28 @@ int kvg_dev_scan_pci_count(kvg_ctx* ctx, uint64_t* n_survivors, uint32_t* n_dev_
 
 static size_t align64(size_t x) { return (x + 63) & ~(size_t)63; }
 
-int kvg_dev_scan_pci_fetch(kvg_ctx* ctx, kvg_pci_result** res) {
-  if (!ctx || !res || ctx->last_kind != 1) return KVG_EINVAL;
-  CK(cudaSetDevice(ctx->device));
+// result-block layout: [header][survivors, `surv_reserve` slots][orderings...][name pool]
+static size_t pci_block_bytes(size_t surv_reserve, size_t S, size_t KD, size_t G, size_t SD, size_t SG,
+                              size_t pool_len) {
+  auto a64 = [](size_t x) { return (x + 63) & ~(size_t)63; };
+  return a64(sizeof(kvg_pci_result)) + a64(surv_reserve * 16) + a64(KD * 4) + a64(KD * 2) + a64((KD + 1) * 4) +
+         a64(SD * 4) + a64(KD * 4) + a64(G * 4) + a64((G + 1) * 4) + a64(SG * 4) + a64(pool_len);
+}
+
+// blk == NULL: allocate for the exact counts and copy the survivors too.  Otherwise `blk` was sized
+// for the worst case by the pipelined entry point, which has already copied the survivors into it.
+static int fetch_pci(kvg_ctx* ctx, kvg_pci_result** res, void* blk, size_t surv_reserve) {
   CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  const bool surv_done = blk != nullptr;
   const size_t S = ctx->h_ctrl->n_surv, KD = ctx->h_ctrl->n_dev_keys, G = ctx->h_ctrl->n_groups;
+  if (!surv_done) surv_reserve = S;
   // members covered by each ordering: all survivors, or (sharded) those whose key this rank owns
   const size_t SD = ctx->last_owned ? ctx->h_ctrl->n_own[0] : S;
   const size_t SG = ctx->last_owned ? ctx->h_ctrl->n_own[1] : S;
   const size_t pool_len = ctx->h_pool.size();
   size_t o_hdr = 0, o = align64(sizeof(kvg_pci_result));
-  size_t o_surv = o; o += align64(S * 16);
+  size_t o_surv = o; o += align64(surv_reserve * 16);
   size_t o_dkeys32 = o; o += align64(KD * 4);
   size_t o_dkeys = o; o += align64(KD * 2);
   size_t o_doff = o; o += align64((KD + 1) * 4);
@@ -1051,7 +1139,7 @@ int kvg_dev_scan_pci_fetch(kvg_ctx* ctx, kvg_pci_result** res) {
   size_t o_goff = o; o += align64((G + 1) * 4);
   size_t o_gperm = o; o += align64(SG * 4);
   size_t o_pool = o; o += align64(pool_len);
-  void* blk = pinned_alloc(ctx, o);
+  if (!blk) blk = pinned_alloc(ctx, o);
   if (!blk) {
     ctx->err = "cudaMallocHost failed for the result block";
     return KVG_ENOMEM;
@@ -1064,7 +1152,7 @@ int kvg_dev_scan_pci_fetch(kvg_ctx* ctx, kvg_pci_result** res) {
   };
   OrderBufs& od = ctx->ord_dev;
   OrderBufs& og = ctx->ord_grp;
-  CK(D2H(o_surv, ctx->surv.p, S * 16));
+  if (!surv_done) CK(D2H(o_surv, ctx->surv.p, S * 16));
   CK(D2H(o_dkeys32, od.seg_key.p, KD * 4));
   CK(D2H(o_doff, od.seg_off.p, (KD + 1) * 4));
   CK(D2H(o_dperm, od.perm.p, SD * 4));
@@ -1072,6 +1160,7 @@ int kvg_dev_scan_pci_fetch(kvg_ctx* ctx, kvg_pci_result** res) {
   CK(D2H(o_goff, og.seg_off.p, (G + 1) * 4));
   CK(D2H(o_gperm, og.perm.p, SG * 4));
   CK(cudaStreamSynchronize(ctx->stream));
+  if (surv_done) CK(cudaStreamSynchronize(ctx->s_d2h));
   kvg_pci_result* r = (kvg_pci_result*)b;
   memset(r, 0, sizeof *r);
   r->n_records = ctx->last_n;
@@ -1104,6 +1193,12 @@ int kvg_dev_scan_pci_fetch(kvg_ctx* ctx, kvg_pci_result** res) {
   return KVG_OK;
 }
 
+int kvg_dev_scan_pci_fetch(kvg_ctx* ctx, kvg_pci_result** res) {
+  if (!ctx || !res || ctx->last_kind != 1) return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  return fetch_pci(ctx, res, nullptr, 0);
+}
+
 static int stage_h2d(kvg_ctx* ctx, const void* host, size_t bytes, void* dev) {
   if (!bytes) return KVG_OK;
   cudaPointerAttributes attr;
@@ -1125,9 +1220,151 @@ static int stage_h2d(kvg_ctx* ctx, const void* host, size_t bytes, void* dev) {
   return KVG_OK;
 }
 
+// Host entry point, pipelined: the snapshot crosses PCIe in chunks on a copy stream while the previous
+// chunk is classified and packed (tile-independent k_classify_ragged; the offsets kernel re-scans the
+// tile counts seen so far, a few thousand words); each chunk's survivors start their way back on a
+// second copy stream as soon as their count is known (a 4-byte store to mapped host memory), so the
+// device-to-host copy of the survivor list runs under the remaining host-to-device traffic and under
+// the ordering kernels.  Only the orderings' own arrays are copied after the last kernel.
+static const size_t PIPE_MIN_RECORDS = 128u << 10, PIPE_MAX_RECORDS = 16u << 20, PIPE_MAX_CHUNKS = 16;
+
+__global__ void k_publish_count(const uint32_t* __restrict__ src, volatile uint32_t* host_dst) {
+  pdl_enter();
+  *host_dst = *src;
+  __threadfence_system();
+}
+
+static int scan_pci_pipelined(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, kvg_pci_result** res) {
+  constexpr int T = 128, R = 8;
+  constexpr size_t TILE = (size_t)T * R;
+  if (!ctx->s_h2d) {
+    CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    CK(cudaMallocHost((void**)&ctx->h_pipe, sizeof(uint32_t) * PIPE_MAX_CHUNKS));
+    ctx->pipe_ev.resize(2 * PIPE_MAX_CHUNKS + 1);
+    for (auto& e : ctx->pipe_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  // ~256 K records (4 MiB) per chunk, whole tiles
+  size_t n_chunks = std::min(PIPE_MAX_CHUNKS, std::max((size_t)2, (n + (256u << 10) - 1) / (256u << 10)));
+  size_t chunk = ((n + n_chunks - 1) / n_chunks + TILE - 1) / TILE * TILE;
+  n_chunks = (n + chunk - 1) / chunk;
+  const size_t tiles = (n + TILE - 1) / TILE;
+  ENSURE(ctx->recs, n + 1);
+  ENSURE(ctx->surv, n + 1);
+  ENSURE(ctx->ragged, tiles * TILE);
+  ENSURE(ctx->tile_count, tiles + 1);
+  ENSURE(ctx->tile_off, tiles + 2);
+  ENSURE(ctx->tile_max, tiles + 1);
+  ENSURE(ctx->offs_state, (tiles + C_TILE - 1) / C_TILE + 1);
+  // host side of the copies
+  cudaPointerAttributes attr;
+  bool pinned = cudaPointerGetAttributes(&attr, recs) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  const uint8_t* src = (const uint8_t*)recs;
+  if (!pinned && ctx->h_stage_cap < n * 16) {  // cgo rule: never keep the caller's pointer -> stage it
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    ctx->h_stage = nullptr;
+    ctx->h_stage_cap = 0;
+    size_t cap = n * 16 + n * 4 + 4096;
+    CK(cudaMallocHost(&ctx->h_stage, cap));
+    ctx->h_stage_cap = cap;
+  }
+  // the copy stream must not overtake earlier work on the context stream that still reads recs
+  cudaEvent_t ev_prev = ctx->pipe_ev[2 * PIPE_MAX_CHUNKS];
+  CK(cudaEventRecord(ev_prev, ctx->stream));
+  CK(cudaStreamWaitEvent(ctx->s_h2d, ev_prev, 0));
+  CK(cudaStreamWaitEvent(ctx->s_d2h, ev_prev, 0));
+  for (size_t k = 0; k < n_chunks; k++) {
+    const size_t c0 = k * chunk, cn = std::min(chunk, n - c0);
+    const uint8_t* from = src + c0 * 16;
+    if (!pinned) {
+      memcpy((uint8_t*)ctx->h_stage + c0 * 16, from, cn * 16);
+      from = (const uint8_t*)ctx->h_stage + c0 * 16;
+    }
+    CK(cudaMemcpyAsync(ctx->recs.p + c0, from, cn * 16, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaEventRecord(ctx->pipe_ev[k], ctx->s_h2d));
+  }
+  // the table (a pending kvg_pciids_load is completed here, under the copies already in flight)
+  {
+    int rc_t = table_needed(ctx, "kvg_pciids_load must precede a scan (the scan joins names)");
+    if (rc_t) {
+      cudaStreamSynchronize(ctx->s_h2d);
+      return rc_t;
+    }
+  }
+  const size_t pool_len = ctx->h_pool.size();
+  void* blk = pinned_alloc(ctx, pci_block_bytes(n, n, std::min<size_t>(n, 65536), n, n, n, pool_len));
+  if (!blk) {
+    cudaStreamSynchronize(ctx->s_h2d);
+    ctx->err = "cudaMallocHost failed for the result block";
+    return KVG_ENOMEM;
+  }
+  uint8_t* b = pinned_payload(blk);
+  const size_t o_surv = (sizeof(kvg_pci_result) + 63) & ~(size_t)63;
+  CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
+  PciClassifyOp op;
+  op.ctrl = ctx->ctrl.p;
+  op.table = ctx->tables.p;
+  op.cap_mask = (1u << ctx->cap_log2) - 1;
+  op.cap_shift = 32 - ctx->cap_log2;
+  op.info = ctx->info.p;
+  op.nv_index = ctx->nv_index.p;
+  op.local_max_group = 0;
+  op.local_max_dev = 0;
+  for (size_t k = 0; k < n_chunks; k++) {
+    const size_t c0 = k * chunk, cn = std::min(chunk, n - c0);
+    const size_t t0 = c0 / TILE, tn = (cn + TILE - 1) / TILE, t1 = t0 + tn;
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->pipe_ev[k], 0));
+    op.recs = ctx->recs.p + c0;
+    op.n = (uint32_t)cn;
+    op.out = (kvg_pci_surv*)(ctx->ragged.p + c0);
+    LAUNCH("classify_compact", (k_classify_ragged<PciClassifyOp, T, R>), (unsigned)tn, T, 0, op,
+           ctx->tile_count.p + t0, ctx->tile_max.p + t0);
+    TileOffsetsArgs2 tt;
+    tt.o[0] = {ctx->tile_count.p, ctx->tile_max.p, nullptr, (uint32_t)t1, ctx->tile_off.p, &ctx->ctrl.p->n_surv,
+               ctx->offs_state.p};
+    tt.o[1] = tt.o[0];
+    LAUNCH("tile_offsets", k_tile_offsets, (unsigned)((t1 + C_TILE - 1) / C_TILE), KVG_BLOCK, 0, tt, ctx->ctrl.p,
+           next_epoch());
+    LAUNCH("pack_survivors", k_pack_survivors<1>, (unsigned)tn, 128, 0, (const uint4*)(ctx->ragged.p + c0),
+           (const uint32_t*)(ctx->tile_off.p + t0), (uint32_t)TILE, ctx->surv.p);
+    LAUNCH("publish_count", k_publish_count, 1, 32, 0, (const uint32_t*)&ctx->ctrl.p->n_surv,
+           (volatile uint32_t*)(ctx->h_pipe + k));
+    CK(cudaEventRecord(ctx->pipe_ev[PIPE_MAX_CHUNKS + k], ctx->stream));
+  }
+  int rc = check_launch(ctx, "classify");
+  if (rc == KVG_OK) rc = enqueue_pci_orderings(ctx, n);
+  if (rc) {
+    cudaStreamSynchronize(ctx->stream);
+    ctx->pinned_free.push_back({blk, (size_t)((uint64_t*)blk)[1]});
+    return rc;
+  }
+  ctx->last_n = n;
+  ctx->last_total = n;
+  ctx->last_kind = 1;
+  ctx->last_owned = false;
+  // survivors go home chunk by chunk while later chunks and the orderings still run
+  size_t prev = 0;
+  for (size_t k = 0; k < n_chunks; k++) {
+    CK(cudaEventSynchronize(ctx->pipe_ev[PIPE_MAX_CHUNKS + k]));
+    const size_t cum = ctx->h_pipe[k];
+    if (cum > prev)
+      CK(cudaMemcpyAsync(b + o_surv + prev * 16, ctx->surv.p + prev, (cum - prev) * 16, cudaMemcpyDeviceToHost,
+                         ctx->s_d2h));
+    prev = cum;
+  }
+  return fetch_pci(ctx, res, blk, n);
+}
+
 int kvg_scan_pci(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, kvg_pci_result** res) {
   if (!ctx || !res || (!recs && n)) return KVG_EINVAL;
   CK(cudaSetDevice(ctx->device));
+  static const bool pipe = [] {
+    const char* e = getenv("KVG_PIPELINE");
+    return !(e && e[0] == '0');
+  }();
+  if (pipe && !ctx->timing && n >= PIPE_MIN_RECORDS && n <= PIPE_MAX_RECORDS)
+    return scan_pci_pipelined(ctx, recs, n, res);
   ENSURE(ctx->recs, n + 1);
   int rc = stage_h2d(ctx, recs, n * sizeof(kvg_pci_rec), ctx->recs.p);
   if (rc) return rc;
@@ -1226,6 +1463,7 @@ static int load_type_dict(kvg_ctx* ctx, const kvg_type_dict* types) {
 __global__ void k_pack_labels(const uint8_t* __restrict__ label, const uint32_t* __restrict__ raw_off,
                               const uint32_t* __restrict__ label_len, uint32_t n_types,
                               uint8_t* __restrict__ blob, uint32_t* __restrict__ blob_off) {
+  pdl_enter();
   // single thread per type after a serial prefix by thread 0 (n_types <= 65535, tiny)
   __shared__ uint32_t total;
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -1249,9 +1487,9 @@ extern "C" {
 
 int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type_dict* types) {
   if (!ctx || !types || (!d_recs && n) || n > 0xfffffff0ull || ((uintptr_t)d_recs & 15)) return KVG_EINVAL;
-  if (!ctx->table_ready) {
-    ctx->err = "kvg_pciids_load must precede a scan (the scan joins names)";
-    return KVG_ESTATE;
+  {
+    int rc_t = table_needed(ctx, "kvg_pciids_load must precede a scan (the scan joins names)");
+    if (rc_t) return rc_t;
   }
   CK(cudaSetDevice(ctx->device));
   int rc = load_type_dict(ctx, types);
@@ -1679,6 +1917,7 @@ static int scan_sharded_p2p(kvg_ctx* ctx, const void* d_recs, size_t n_local) {
 // after the gather: n_surv <- total, maxima already all-reduced by construction (each rank
 // recomputes them from the gathered list)
 __global__ void k_gathered_maxima(const kvg_pci_surv* __restrict__ s, uint32_t n, ScanCtrl* ctrl) {
+  pdl_enter();
   uint32_t mg = 0, md = 0;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     mg = max(mg, s[i].iommu_group);
@@ -1701,9 +1940,9 @@ int kvg_dev_scan_pci_sharded(kvg_ctx* ctx, const void* d_recs, size_t n_local) {
     ctx->err = "kvg_comm_init / kvg_comm_p2p_import has not been called";
     return KVG_ESTATE;
   }
-  if (!ctx->table_ready) {
-    ctx->err = "kvg_pciids_load must precede a scan";
-    return KVG_ESTATE;
+  {
+    int rc_t = table_needed(ctx, "kvg_pciids_load must precede a scan");
+    if (rc_t) return rc_t;
   }
   CK(cudaSetDevice(ctx->device));
   const int P = ctx->nranks;

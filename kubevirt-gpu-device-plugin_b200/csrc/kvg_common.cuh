@@ -24,6 +24,14 @@ __device__ __forceinline__ uint32_t lanemask_lt() {
 }
 
 // ---- streaming memory access --------------------------------------------------------------------
+// Programmatic dependent launch (sm_90+): every kernel on the scan path opens with pdl_enter().
+// launch_dependents lets the NEXT kernel of the stream be scheduled while this one still runs (its CTAs
+// park in griddepcontrol.wait); wait returns once the PREVIOUS kernel has completed and its writes are
+// visible.  Without the launch attribute both instructions are no-ops, so plain launches stay correct.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

@@ -144,6 +144,7 @@ __device__ __forceinline__ uint32_t table_probe(const uint64_t* __restrict__ tab
 //               classify, intra-round header scan, and ONE batch of hash inserts per round.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_parse(ParseArgs A) {
+  pdl_enter();
   extern __shared__ __align__(128) uint8_t p_smem[];
   uint8_t* stage_buf = p_smem;                                                      // ring
   uint16_t* lists = reinterpret_cast<uint16_t*>(p_smem + P_STAGES * P_STAGE);       // [2][8][P_WCAP]
@@ -352,6 +353,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_parse(ParseArgs A) {
 // One CTA per image: section end and scanner limit.  (Cheap: a few hundred tiles at most.)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_finalize(ParseArgs A) {
+  pdl_enter();
   const uint32_t f = blockIdx.x;
   const uint8_t* text = A.text + (uint64_t)f * A.stride;
   const uint32_t t0 = f * A.tiles_per_file;
@@ -568,6 +570,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_sanitise(const uint8_t* __
                                                                uint32_t len,
                                                                const PciIdsInfo* __restrict__ info,
                                                                uint8_t* __restrict__ pool) {
+  pdl_enter();
   __shared__ __align__(16) uint8_t win[S_WIN + S_HALO];
   const uint32_t V = info->v_off, E = info->sec_end;
   if (V == P_NONE) return;
@@ -613,6 +616,7 @@ __device__ __forceinline__ uint32_t probe_name_slot(const uint64_t* __restrict__
 __global__ void k_nv_index(const uint64_t* __restrict__ table, uint32_t mask, uint32_t shift,
                            const PciIdsInfo* __restrict__ info, uint32_t* __restrict__ nv_index,
                            uint32_t* __restrict__ line_list, uint32_t* __restrict__ line_count) {
+  pdl_enter();
   uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t slot = probe_name_slot(table, mask, shift, info, d & 0xffffu);
   nv_index[d] = slot;
@@ -634,6 +638,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_sanitise_lines(const uint8
                                                                      const uint32_t* __restrict__ line_list,
                                                                      const uint32_t* __restrict__ line_count,
                                                                      uint8_t* __restrict__ pool) {
+  pdl_enter();
   const uint32_t V = info->v_off;
   if (V == P_NONE) return;
   const uint32_t n_lines = *line_count;
@@ -709,6 +714,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_sanitise_lines(const uint8
 __global__ void k_probe_keys(const uint64_t* __restrict__ table, uint32_t mask, uint32_t shift,
                              const PciIdsInfo* __restrict__ info, uint32_t first, uint32_t count,
                              uint32_t* __restrict__ slots) {
+  pdl_enter();
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) slots[i] = probe_name_slot(table, mask, shift, info, (first + i) & 0xffffu);
 }
@@ -719,6 +725,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_section_lines(const uint8_t* __re
                                                              const PciIdsInfo* __restrict__ info,
                                                              uint32_t* __restrict__ lines,
                                                              uint32_t* __restrict__ n_lines, uint32_t cap) {
+  pdl_enter();
   const uint32_t V = info->v_off, E = info->sec_end;
   if (V == P_NONE) return;
   for (uint32_t b = V + 1 + blockIdx.x * blockDim.x + threadIdx.x; b < E; b += gridDim.x * blockDim.x) {
@@ -740,6 +747,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_lookup_general(const uint8_t* __r
                                                               const uint8_t* __restrict__ keys,
                                                               const uint32_t* __restrict__ key_off,
                                                               uint32_t* __restrict__ match_off) {
+  pdl_enter();
   const uint32_t n_lines = *n_lines_ptr;
   const uint32_t kidx = blockIdx.y;
   const uint8_t* key = keys + key_off[kidx];
@@ -768,6 +776,7 @@ __global__ void k_sanitise_matches(const uint8_t* __restrict__ text, uint32_t le
                                    const uint32_t* __restrict__ match_off, uint32_t n_keys,
                                    uint8_t* __restrict__ out, uint32_t cap,
                                    uint32_t* __restrict__ out_len) {
+  pdl_enter();
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_keys) return;
   uint32_t b = match_off[k];

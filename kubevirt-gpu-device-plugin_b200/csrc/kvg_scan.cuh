@@ -48,6 +48,7 @@ struct ScanCtrl {
 // ------------------------------------------------------------------------------------------------
 template <class Op>
 __global__ void __launch_bounds__(KVG_BLOCK) k_compact(Op op, uint64_t* tile_state, uint32_t epoch) {
+  pdl_enter();
   __shared__ uint32_t s_base;
   __shared__ uint32_t s_wtot[KVG_WARPS], s_woff[KVG_WARPS];
   op.begin();
@@ -120,6 +121,7 @@ constexpr uint32_t CLASSIFY_MAX_GRID = 32 * LB_KMAX;
 template <class Op, int ROWS, int STAGES>
 __global__ void __launch_bounds__(KVG_BLOCK, 3) k_classify_tma(Op op, uint64_t* tile_agg,
                                                             uint64_t* round_incl, uint32_t epoch) {
+  pdl_enter();
   // Tile t = b + r*G (CTA b, round r).  Its base offset is
   //     round_incl[r-1]  +  sum of tile_agg[r*G + k] for k < b
   // i.e. ONE batch of independent loads (prefetched a phase early) instead of a serial walk:
@@ -278,6 +280,7 @@ constexpr uint32_t WS_THREADS = KVG_BLOCK + 32;
 template <class Op, int ROWS, int STAGES>
 __global__ void __launch_bounds__(WS_THREADS) k_classify_ws(Op op, uint64_t* tile_agg,
                                                             uint64_t* round_incl, uint32_t epoch) {
+  pdl_enter();
   constexpr uint32_t TILE = KVG_BLOCK * ROWS;
   constexpr uint32_t RB = Op::REC_BYTES;
   constexpr uint32_t STAGE_BYTES = TILE * RB;
@@ -430,6 +433,7 @@ __global__ void __launch_bounds__(WS_THREADS) k_classify_ws(Op op, uint64_t* til
 // ------------------------------------------------------------------------------------------------
 template <class Op, int THREADS, int ROWS>
 __global__ void __launch_bounds__(THREADS) k_classify_oneshot(Op op, uint64_t* tile_state, uint32_t epoch) {
+  pdl_enter();
   constexpr uint32_t TILE = THREADS * ROWS;
   constexpr uint32_t NW = THREADS / 32;
   constexpr uint32_t WARP_ITEMS = 32 * ROWS;
@@ -724,6 +728,7 @@ __device__ __forceinline__ uint2 radix_load(const RadixArgs& a, uint32_t i) {
 }
 
 __global__ void __launch_bounds__(KVG_BLOCK) k_radix_hist(RadixArgs2 aa) {
+  pdl_enter();
   const RadixArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
@@ -753,6 +758,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_radix_hist(RadixArgs2 aa) {
 
 // one CTA per digit: exclusive scan of that digit's per-tile counts, in place
 __global__ void __launch_bounds__(KVG_BLOCK) k_radix_tilescan(RadixArgs2 aa) {
+  pdl_enter();
   const RadixArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
@@ -773,6 +779,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_radix_tilescan(RadixArgs2 aa) {
 }
 
 __global__ void __launch_bounds__(KVG_BLOCK, 6) k_radix_scatter(RadixArgs2 aa) {
+  pdl_enter();
   const RadixArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
@@ -881,6 +888,7 @@ struct OrderFinalArgs2 {
 };
 template <bool EMIT>
 __global__ void __launch_bounds__(KVG_BLOCK) k_order_final(OrderFinalArgs2 aa) {
+  pdl_enter();
   const OrderFinalArgs a = blockIdx.y ? aa.o[1] : aa.o[0];
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
@@ -943,6 +951,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_order_final(OrderFinalArgs2 aa) {
 __global__ void k_mdev_labels(const uint8_t* __restrict__ raw, const uint32_t* __restrict__ raw_off,
                               uint32_t n_types, uint8_t* __restrict__ label,
                               uint32_t* __restrict__ label_len, uint64_t* __restrict__ label_hash) {
+  pdl_enter();
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_types) return;
   uint32_t a = raw_off[k], b = raw_off[k + 1];
@@ -971,6 +980,7 @@ __global__ void k_mdev_canon(const uint8_t* __restrict__ label, const uint32_t* 
                              const uint32_t* __restrict__ label_len,
                              const uint64_t* __restrict__ label_hash, uint32_t n_types,
                              uint16_t* __restrict__ canon) {
+  pdl_enter();
   uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n_types) return;
   const uint32_t len = label_len[k];
@@ -1002,6 +1012,7 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
 __global__ void k_gen_pci(uint4* __restrict__ out, uint64_t first, uint32_t n,
                           const uint16_t* __restrict__ nv_ids, uint32_t n_nv_ids,
                           uint32_t group_bits) {
+  pdl_enter();
   const uint64_t SEED = 0x10DE000020250711ull;
   const uint16_t other[8] = {0x8086, 0x1002, 0x15b3, 0x1022, 0x144d, 0x14e4, 0x1af4, 0x10df};
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
@@ -1050,6 +1061,7 @@ __global__ void k_gen_pci(uint4* __restrict__ out, uint64_t first, uint32_t n,
   }
 }
 __global__ void k_gen_mdev(uint4* __restrict__ out, uint64_t first, uint32_t n) {
+  pdl_enter();
   const uint64_t SEED = 0x4D44455600010000ull;
   for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     uint64_t j = first + k;
@@ -1077,16 +1089,19 @@ __global__ void k_gen_mdev(uint4* __restrict__ out, uint64_t first, uint32_t n) 
 
 // L2 flush helper: stream zeros through a buffer larger than L2
 __global__ void k_fill(uint4* __restrict__ p, size_t n16, uint32_t v) {
+  pdl_enter();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16;
        i += (size_t)gridDim.x * blockDim.x)
     p[i] = make_uint4(v, v, v, v);
 }
 __global__ void k_fill64(uint64_t* __restrict__ p, size_t n, uint64_t v) {
+  pdl_enter();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x)
     p[i] = v;
 }
 __global__ void k_fill32(uint32_t* __restrict__ p, size_t n, uint32_t v) {
+  pdl_enter();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
        i += (size_t)gridDim.x * blockDim.x)
     p[i] = v;
@@ -1108,6 +1123,7 @@ __global__ void k_fill32(uint32_t* __restrict__ p, size_t n, uint32_t v) {
 template <class Op, int THREADS, int ROWS>
 __global__ void __launch_bounds__(THREADS) k_classify_ragged(Op op, uint32_t* __restrict__ tile_count,
                                                              uint2* __restrict__ tile_max) {
+  pdl_enter();
   constexpr uint32_t TILE = THREADS * ROWS;
   constexpr uint32_t NW = THREADS / 32;
   constexpr uint32_t WARP_ITEMS = 32 * ROWS;
@@ -1188,6 +1204,7 @@ struct TileOffsetsArgs2 {
 };
 __global__ void __launch_bounds__(KVG_BLOCK) k_tile_offsets(TileOffsetsArgs2 aa, ScanCtrl* ctrl,
                                                             uint32_t epoch) {
+  pdl_enter();
   const TileOffsetsArgs A = blockIdx.y ? aa.o[1] : aa.o[0];
   const uint32_t* __restrict__ tile_count = A.tile_count;
   const uint2* __restrict__ tile_max = A.tile_max;
@@ -1255,6 +1272,7 @@ template <int UNITS_PER_ITEM>
 __global__ void __launch_bounds__(128) k_pack_survivors(const uint4* __restrict__ ragged,
                                                         const uint32_t* __restrict__ tile_off,
                                                         uint32_t tile_items, uint4* __restrict__ dense) {
+  pdl_enter();
   const uint32_t tile = blockIdx.x;
   const uint32_t o0 = tile_off[tile], o1 = tile_off[tile + 1];
   const uint32_t units = (o1 - o0) * UNITS_PER_ITEM;
@@ -1301,6 +1319,7 @@ struct OwnedPairOp {
 __global__ void __launch_bounds__(128) k_pack_pairs(const uint2* __restrict__ ragged,
                                                     const uint32_t* __restrict__ tile_off,
                                                     uint32_t tile_items, uint2* __restrict__ dense) {
+  pdl_enter();
   const uint32_t tile = blockIdx.x;
   const uint32_t o0 = tile_off[tile], o1 = tile_off[tile + 1];
   const uint2* src = ragged + (size_t)tile * tile_items;
@@ -1335,6 +1354,7 @@ constexpr long long P2P_SPIN_LIMIT = 20000000000ll;  // ~10 s of SM clocks, then
 
 // before reusing a window: every peer must have consumed the step that used it two steps ago
 __global__ void k_p2p_wait_acks(const P2PCtrl* mine, uint32_t P, unsigned long long need, uint32_t* err) {
+  pdl_enter();
   const uint32_t q = threadIdx.x;
   if (q >= P) return;
   const long long t0 = clock64();
@@ -1349,6 +1369,7 @@ __global__ void __launch_bounds__(128) k_pack_to_peers(const uint4* __restrict__
                                                        const uint32_t* __restrict__ tile_off,
                                                        uint32_t tile_items, P2PPeers peers, uint32_t P,
                                                        size_t region_off) {
+  pdl_enter();
   const uint32_t tile = blockIdx.x;
   const uint32_t o0 = tile_off[tile], o1 = tile_off[tile + 1];
   const uint4* src = ragged + (size_t)tile * tile_items;
@@ -1359,6 +1380,7 @@ __global__ void __launch_bounds__(128) k_pack_to_peers(const uint4* __restrict__
 }
 __global__ void k_p2p_signal(P2PPeers peers, uint32_t P, uint32_t rank, uint32_t w, unsigned long long step,
                              const uint32_t* n_local) {
+  pdl_enter();
   const uint32_t q = threadIdx.x;
   if (q >= P) return;
   peers.ctrl[q]->count[w][rank] = *n_local;
@@ -1368,6 +1390,7 @@ __global__ void k_p2p_signal(P2PPeers peers, uint32_t P, uint32_t rank, uint32_t
 // wait for every region of this step, then publish the region bases and the total
 __global__ void k_p2p_wait_gather(const P2PCtrl* mine, uint32_t P, uint32_t w, unsigned long long step,
                                   uint32_t* gather_base, ScanCtrl* ctrl, uint32_t* err) {
+  pdl_enter();
   __shared__ uint32_t cnt[P2P_MAX_RANKS];
   const uint32_t q = threadIdx.x;
   if (q < P) {
@@ -1397,6 +1420,7 @@ __global__ void k_p2p_wait_gather(const P2PCtrl* mine, uint32_t P, uint32_t w, u
 __global__ void __launch_bounds__(KVG_BLOCK) k_p2p_copy_regions(const uint4* __restrict__ window, size_t cap,
                                                                 const uint32_t* __restrict__ gather_base,
                                                                 uint4* __restrict__ dense) {
+  pdl_enter();
   const uint32_t q = blockIdx.y;
   const uint32_t b0 = gather_base[q], n = gather_base[q + 1] - b0;
   const uint4* src = window + (size_t)q * cap;
@@ -1404,6 +1428,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_p2p_copy_regions(const uint4* __r
     st_stream(dense + b0 + u, ld_stream(src + u));
 }
 __global__ void k_p2p_ack(P2PPeers peers, uint32_t P, uint32_t rank, unsigned long long step) {
+  pdl_enter();
   const uint32_t q = threadIdx.x;
   if (q < P) st_release_sys(&peers.ctrl[q]->ack[rank], step);
 }
@@ -1417,6 +1442,7 @@ __global__ void __launch_bounds__(THREADS) k_debug_classify(const uint4* __restr
                                                              uint4* __restrict__ out,
                                                              const uint32_t* __restrict__ nv_index,
                                                              uint32_t* counter, int mode) {
+  pdl_enter();
   constexpr uint32_t TILE = THREADS * ROWS;
   constexpr uint32_t NW = THREADS / 32;
   __shared__ uint32_t s_wtot[NW], s_woff[NW];
