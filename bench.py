@@ -441,8 +441,27 @@ def main():
         for _ in range(args.steps):
             d2h, _ = e2e_step()
         te = time.perf_counter() - t0
+        # what the link itself does on this box (pinned <-> device, same buffers): the e2e floor
+        dev_tmp = torch.empty_like(p_recs, device="cuda")
+        host_tmp = torch.empty_like(p_recs).pin_memory()
+        bw = {}
+        for name, dst, src_ in (("h2d", dev_tmp, p_recs), ("d2h", host_tmp, dev_tmp)):
+            dst.copy_(src_, non_blocking=True)
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                dst.copy_(src_, non_blocking=True)
+            b_.record()
+            torch.cuda.synchronize()
+            bw[name] = 5 * p_recs.numel() / (a.elapsed_time(b_) * 1e-3) / 1e9
+        del dev_tmp, host_tmp
         e2e = {"value": n * args.steps / te, "unit": "records/s", "ms_per_step": 1e3 * te / args.steps,
                "h2d_bytes_per_step": len(text) + 16 * n, "d2h_bytes_per_step": d2h,
+               "pcie_measured_GBps": {k: round(v, 1) for k, v in bw.items()},
+               "pcie_floor_ms": {"h2d_only": 1e3 * (len(text) + 16 * n) / (bw["h2d"] * 1e9),
+                                 "h2d_plus_d2h_serial": 1e3 * ((len(text) + 16 * n) / (bw["h2d"] * 1e9) +
+                                                               d2h / (bw["d2h"] * 1e9))},
                "timing": "host wall clock around kvg_pciids_load + kvg_scan_pci (pinned host buffers "
                          "in, pinned host result out)"}
     else:

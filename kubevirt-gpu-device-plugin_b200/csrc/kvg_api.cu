@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -99,6 +100,31 @@ struct DevBuf {
   size_t cap = 0;  // elements
 };
 
+// page-locked byte buffer with the few std::vector members the name-pool mirror uses: device-to-host
+// copies into it are truly asynchronous (a pageable destination is staged synchronously by the runtime)
+struct PinnedBytes {
+  uint8_t* p = nullptr;
+  size_t len = 0, cap = 0;
+  ~PinnedBytes() {
+    if (p) cudaFreeHost(p);
+  }
+  size_t size() const { return len; }
+  uint8_t* data() { return p; }
+  uint8_t& operator[](size_t i) { return p[i]; }
+  void clear() { len = 0; }
+  bool resize(size_t n) {
+    if (n > cap) {
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+      cap = 0;
+      if (cudaMallocHost((void**)&p, n + n / 4 + 4096) != cudaSuccess) return false;
+      cap = n + n / 4 + 4096;
+    }
+    len = n;
+    return true;
+  }
+};
+
 struct PinnedBlock {
   void* p;
   size_t size;
@@ -107,7 +133,7 @@ struct PinnedBlock {
 struct OrderBufs {  // one stable ordering (sorted (key, index) pairs + segment heads)
   DevBuf<uint2> p0, p1;           // ping-pong {key, survivor index}
   DevBuf<uint32_t> perm;          // final permutation
-  DevBuf<uint32_t> seg_key, seg_off;
+  DevBuf<uint32_t> seg_key, seg_off, seg_name;
   DevBuf<uint32_t> tile_heads, tile_off;
   DevBuf<uint64_t> heads_state;
 };
@@ -136,7 +162,7 @@ struct kvg_ctx {
   DevBuf<uint32_t> sec_lines; // '\t' line starts of the NVIDIA section, then their count (general lookups)
   size_t sec_lines_cap = 0;
   DevBuf<uint64_t> type_hash;
-  std::vector<uint8_t> h_pool;
+  PinnedBytes h_pool;
   PciIdsInfo h_info{};
   bool table_ready = false;
   // kvg_pciids_load only ENQUEUES (copy + parse); the host-side publication (overflow check, name
@@ -275,6 +301,30 @@ struct LaunchScope {
 // Launches carry the programmatic-stream-serialization attribute (PDL): the next kernel's CTAs are
 // scheduled while this one drains and park in griddepcontrol.wait (pdl_enter() in every kernel), which
 // removes most of the dependent-launch gap of the ~40-kernel scan.  KVG_PDL=0 restores plain launches.
+// KVG_TRACE=1: host-clock phase marks of the pipelined entry point on stderr (diagnostics only)
+struct PhaseTrace {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  std::string line;
+  PhaseTrace() {
+    static const bool env = [] { const char* e = getenv("KVG_TRACE"); return e && e[0] == '1'; }();
+    on = env;
+    if (on) t0 = std::chrono::steady_clock::now();
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    double us = std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    char buf[64];
+    snprintf(buf, sizeof buf, " %s=%.0f", what, us);
+    line += buf;
+  }
+  ~PhaseTrace() {
+    if (on) fprintf(stderr, "[kvg trace us]%s\n", line.c_str());
+  }
+};
+static PhaseTrace* g_trace = nullptr;
+#define TRACE(what) do { if (g_trace) g_trace->mark(what); } while (0)
+
 static bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
@@ -431,7 +481,7 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist);
   for (OrderBufs* o : {&ctx->ord_dev, &ctx->ord_grp}) {
     release(o->p0); release(o->p1); release(o->perm); release(o->tile_heads); release(o->tile_off);
-    release(o->seg_key); release(o->seg_off); release(o->heads_state);
+    release(o->seg_key); release(o->seg_off); release(o->seg_name); release(o->heads_state);
   }
   release(ctx->type_raw); release(ctx->type_label); release(ctx->type_off);
   release(ctx->type_label_len); release(ctx->type_match); release(ctx->type_name_len);
@@ -586,7 +636,10 @@ static int table_publish(kvg_ctx* ctx, const uint8_t* d_text, size_t len) {
            ctx->nv_lines.p, ctx->nv_lines.p + 65536, ctx->pool.p);
     int rc = check_launch(ctx, "pciids sanitise");
     if (rc) return rc;
-    ctx->h_pool.resize(sec + 16);
+    if (!ctx->h_pool.resize(sec + 16)) {
+      ctx->err = "cudaMallocHost failed for the name pool mirror";
+      return KVG_ENOMEM;
+    }
     CK(cudaMemcpyAsync(ctx->h_pool.data(), ctx->pool.p, sec + 16, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
   } else {
@@ -875,7 +928,7 @@ extern "C" {
 static int ensure_order(kvg_ctx* ctx, OrderBufs& o, size_t cap) {
   const size_t T = (cap + C_TILE - 1) / C_TILE + 1;
   ENSURE(o.p0, cap + 1); ENSURE(o.p1, cap + 1); ENSURE(o.perm, cap + 1);
-  ENSURE(o.seg_key, cap + 1); ENSURE(o.seg_off, cap + 2);
+  ENSURE(o.seg_key, cap + 1); ENSURE(o.seg_off, cap + 2); ENSURE(o.seg_name, cap + 1);
   ENSURE(o.tile_heads, T + 1); ENSURE(o.tile_off, T + 2);
   ENSURE(o.heads_state, T / C_TILE + 2);
   return KVG_OK;
@@ -978,6 +1031,9 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1, bool 
     a.seg_key = ob[ord]->seg_key.p;
     a.seg_off = ob[ord]->seg_off.p;
     a.n_seg = nseg[ord];
+    // PCI device-id ordering: the bucket's joined name slot comes back with the keys
+    a.head_surv = (ord == 0 && src0 == SRC_PCI_DEVICE) ? ctx->surv.p : nullptr;
+    a.head_name = a.head_surv ? ob[ord]->seg_name.p : nullptr;
     TileOffsetsArgs& t = tt.o[ord];
     t.tile_count = ob[ord]->tile_heads.p;
     t.tile_max = nullptr;
@@ -1121,6 +1177,7 @@ static size_t pci_block_bytes(size_t surv_reserve, size_t S, size_t KD, size_t G
 static int fetch_pci(kvg_ctx* ctx, kvg_pci_result** res, void* blk, size_t surv_reserve) {
   CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  TRACE("ctrl");
   const bool surv_done = blk != nullptr;
   const size_t S = ctx->h_ctrl->n_surv, KD = ctx->h_ctrl->n_dev_keys, G = ctx->h_ctrl->n_groups;
   if (!surv_done) surv_reserve = S;
@@ -1152,15 +1209,24 @@ static int fetch_pci(kvg_ctx* ctx, kvg_pci_result** res, void* blk, size_t surv_
   };
   OrderBufs& od = ctx->ord_dev;
   OrderBufs& og = ctx->ord_grp;
+  // every kernel has completed (the control block was just read): the group ordering's arrays may
+  // ride the second copy stream next to the device ordering's
+  cudaStream_t s2 = ctx->s_d2h ? ctx->s_d2h : ctx->stream;
+  auto D2H2 = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+    if (!bytes) return cudaSuccess;
+    return cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyDeviceToHost, s2);
+  };
   if (!surv_done) CK(D2H(o_surv, ctx->surv.p, S * 16));
-  CK(D2H(o_dkeys32, od.seg_key.p, KD * 4));
-  CK(D2H(o_doff, od.seg_off.p, (KD + 1) * 4));
+  CK(D2H2(o_gperm, og.perm.p, SG * 4));
   CK(D2H(o_dperm, od.perm.p, SD * 4));
-  CK(D2H(o_gkeys, og.seg_key.p, G * 4));
-  CK(D2H(o_goff, og.seg_off.p, (G + 1) * 4));
-  CK(D2H(o_gperm, og.perm.p, SG * 4));
+  CK(D2H2(o_goff, og.seg_off.p, (G + 1) * 4));
+  CK(D2H(o_dkeys32, od.seg_key.p, KD * 4));
+  CK(D2H2(o_gkeys, og.seg_key.p, G * 4));
+  CK(D2H(o_doff, od.seg_off.p, (KD + 1) * 4));
+  CK(D2H(o_dname, od.seg_name.p, KD * 4));
   CK(cudaStreamSynchronize(ctx->stream));
-  if (surv_done) CK(cudaStreamSynchronize(ctx->s_d2h));
+  if (s2 != ctx->stream) CK(cudaStreamSynchronize(s2));
+  TRACE("d2h");
   kvg_pci_result* r = (kvg_pci_result*)b;
   memset(r, 0, sizeof *r);
   r->n_records = ctx->last_n;
@@ -1174,10 +1240,7 @@ static int fetch_pci(kvg_ctx* ctx, kvg_pci_result** res, void* blk, size_t surv_
   const uint32_t* dperm = (const uint32_t*)(b + o_dperm);
   if (SD == 0) ((uint32_t*)(b + o_doff))[0] = 0;
   if (SG == 0) ((uint32_t*)(b + o_goff))[0] = 0;
-  for (size_t k = 0; k < KD; k++) {  // marshalling only: narrow the key, pick the joined slot
-    dk[k] = (uint16_t)dk32[k];
-    dname[k] = r->survivors[dperm[doff[k]]].name_slot;
-  }
+  for (size_t k = 0; k < KD; k++) dk[k] = (uint16_t)dk32[k];  // marshalling only: narrow the keys
   r->dev_keys = dk;
   r->dev_off = doff;
   r->dev_perm = dperm;
@@ -1190,6 +1253,7 @@ static int fetch_pci(kvg_ctx* ctx, kvg_pci_result** res, void* blk, size_t surv_
   r->name_pool = b + o_pool;
   r->name_pool_len = pool_len;
   *res = r;
+  TRACE("marshalled");
   return KVG_OK;
 }
 
@@ -1237,6 +1301,9 @@ __global__ void k_publish_count(const uint32_t* __restrict__ src, volatile uint3
 static int scan_pci_pipelined(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, kvg_pci_result** res) {
   constexpr int T = 128, R = 8;
   constexpr size_t TILE = (size_t)T * R;
+  PhaseTrace trace;
+  g_trace = trace.on ? &trace : nullptr;
+  struct Unset { ~Unset() { g_trace = nullptr; } } unset_;
   if (!ctx->s_h2d) {
     CK(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
@@ -1244,11 +1311,17 @@ static int scan_pci_pipelined(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, k
     ctx->pipe_ev.resize(2 * PIPE_MAX_CHUNKS + 1);
     for (auto& e : ctx->pipe_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  // ~256 K records (4 MiB) per chunk, whole tiles
-  size_t n_chunks = std::min(PIPE_MAX_CHUNKS, std::max((size_t)2, (n + (256u << 10) - 1) / (256u << 10)));
+  // ~512 K records (8 MiB) per chunk, whole tiles: per-chunk stream/event overheads outweigh finer overlap
+  static const size_t chunk_target = [] {
+    const char* e = getenv("KVG_PIPE_CHUNK_K");  // records per chunk in Ki (A/B knob)
+    long v = e ? atol(e) : 0;
+    return (size_t)(v > 0 ? v : 512) << 10;
+  }();
+  size_t n_chunks = std::min(PIPE_MAX_CHUNKS, std::max((size_t)2, (n + chunk_target - 1) / chunk_target));
   size_t chunk = ((n + n_chunks - 1) / n_chunks + TILE - 1) / TILE * TILE;
   n_chunks = (n + chunk - 1) / chunk;
   const size_t tiles = (n + TILE - 1) / TILE;
+  const uint4* recs_before = ctx->recs.p;
   ENSURE(ctx->recs, n + 1);
   ENSURE(ctx->surv, n + 1);
   ENSURE(ctx->ragged, tiles * TILE);
@@ -1269,11 +1342,10 @@ static int scan_pci_pipelined(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, k
     CK(cudaMallocHost(&ctx->h_stage, cap));
     ctx->h_stage_cap = cap;
   }
-  // the copy stream must not overtake earlier work on the context stream that still reads recs
-  cudaEvent_t ev_prev = ctx->pipe_ev[2 * PIPE_MAX_CHUNKS];
-  CK(cudaEventRecord(ev_prev, ctx->stream));
-  CK(cudaStreamWaitEvent(ctx->s_h2d, ev_prev, 0));
-  CK(cudaStreamWaitEvent(ctx->s_d2h, ev_prev, 0));
+  // ctx->recs is only ever touched by host entry points, which synchronise before they return, so the
+  // copy stream may start at once — it must NOT wait behind a pending kvg_pciids_load's parse kernels.
+  // Exception: a fresh allocation is zero-filled on the context stream.
+  if (ctx->recs.p != recs_before) CK(cudaStreamSynchronize(ctx->stream));
   for (size_t k = 0; k < n_chunks; k++) {
     const size_t c0 = k * chunk, cn = std::min(chunk, n - c0);
     const uint8_t* from = src + c0 * 16;
@@ -1284,6 +1356,7 @@ static int scan_pci_pipelined(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, k
     CK(cudaMemcpyAsync(ctx->recs.p + c0, from, cn * 16, cudaMemcpyHostToDevice, ctx->s_h2d));
     CK(cudaEventRecord(ctx->pipe_ev[k], ctx->s_h2d));
   }
+  TRACE("h2d_issued");
   // the table (a pending kvg_pciids_load is completed here, under the copies already in flight)
   {
     int rc_t = table_needed(ctx, "kvg_pciids_load must precede a scan (the scan joins names)");
@@ -1292,6 +1365,7 @@ static int scan_pci_pipelined(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, k
       return rc_t;
     }
   }
+  TRACE("table");
   const size_t pool_len = ctx->h_pool.size();
   void* blk = pinned_alloc(ctx, pci_block_bytes(n, n, std::min<size_t>(n, 65536), n, n, n, pool_len));
   if (!blk) {
@@ -1343,6 +1417,7 @@ static int scan_pci_pipelined(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, k
   ctx->last_total = n;
   ctx->last_kind = 1;
   ctx->last_owned = false;
+  TRACE("enqueued");
   // survivors go home chunk by chunk while later chunks and the orderings still run
   size_t prev = 0;
   for (size_t k = 0; k < n_chunks; k++) {
@@ -1352,6 +1427,7 @@ static int scan_pci_pipelined(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, k
       CK(cudaMemcpyAsync(b + o_surv + prev * 16, ctx->surv.p + prev, (cum - prev) * 16, cudaMemcpyDeviceToHost,
                          ctx->s_d2h));
     prev = cum;
+    TRACE("chunk");
   }
   return fetch_pci(ctx, res, blk, n);
 }

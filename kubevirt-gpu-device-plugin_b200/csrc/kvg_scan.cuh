@@ -876,6 +876,8 @@ struct OrderFinalArgs {
   uint32_t* seg_key;
   uint32_t* seg_off;          // [n_seg + 1]
   const uint32_t* n_seg;      // total heads (emit only)
+  const uint4* head_surv;     // optional: survivors, to publish the joined name slot of each segment
+  uint32_t* head_name;        // [n_seg] name slot of the segment's first member (NULL: skip)
 };
 __device__ __forceinline__ const uint2* order_final_buf(const OrderFinalArgs& a) {
   uint32_t mk = *a.max_key;
@@ -938,6 +940,8 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_order_final(OrderFinalArgs2 aa) {
       uint32_t pos = off + __popc(bal[k] & lanemask_lt());
       a.seg_key[pos] = key[k];
       a.seg_off[pos] = i;
+      // all members of a device-id bucket share the name (same id): take the first member's slot
+      if (a.head_name) a.head_name[pos] = __ldg(&a.head_surv[pairs[i].y].w);
     }
     off += __popc(bal[k]);
   }
