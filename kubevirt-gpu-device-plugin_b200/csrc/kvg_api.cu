@@ -558,9 +558,10 @@ int kvg_kernel_times(kvg_ctx* ctx, float* ms, char* names, size_t names_cap, int
 size_t kvg_text_pad(size_t len) { return ((len + P_TILE - 1) / P_TILE) * P_TILE + P_HALO; }
 
 static uint32_t table_log2_for(size_t len) {
-  // ~1 device line per 77 bytes in pci.ids; aim at a load factor <= 0.3: every extra probe of
-  // an insert is a serialized L2 atomic round trip inside the parse kernel
-  size_t want = len / 24 + 64;
+  // only the device lines under vendor 10de are inserted (~1 per 800 bytes of the shipped file); a
+  // file that is denser than 1 per 96 bytes trips the overflow / crowding check and is re-parsed
+  // with a table sized from its real entry count (parse_with_regrow)
+  size_t want = len / 96 + 1024;
   uint32_t l = 10;
   while (((size_t)1 << l) < want) l++;
   return l;

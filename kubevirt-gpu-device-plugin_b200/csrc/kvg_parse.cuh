@@ -3,7 +3,8 @@
 //
 //   k_pciids_parse     K1  TMA-staged 16 KiB text tiles -> newline flags -> per-line classify ->
 //                          vendor context (last-writer look-back across tiles) -> open-addressed
-//                          (vendor<<16|device) -> line-offset hash, first line wins (atomicMin)
+//                          (vendor<<16|device) -> line-offset hash of the lines under vendor 10de,
+//                          first line wins (atomicMin)
 //   k_pciids_finalize      section bounds of the FIRST "10de" line, bufio.Scanner 64 KiB limit
 //   k_pciids_sanitise  K2  name transform of :404-414 for every candidate line of the section
 //   k_probe_keys           hash probe for 4-lower-hex keys (the join used by the scans)
@@ -336,7 +337,10 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_parse(ParseArgs A) {
         }
         uint32_t sc = warp_incl_max(hval);  // last header at or before this line, this round
         uint32_t ctx = sc ? (sc & 0x1ffffu) : running;
-        if ((dv & ctx) & 0x10000u)
+        // only vendor 10de is ever looked up (getDeviceName opens the FIRST "10de" section, :424-431):
+        // lines under any other vendor never reach the table, which keeps the serialised L2 atomics of
+        // the inserts (the parse kernel's former bottleneck) to ~5 % of the device lines
+        if (((dv & ctx) & 0x10000u) && (ctx & 0xffffu) == 0x10deu)
           n_new += table_insert(table, A.cap_mask, A.cap_shift,
                                 ((ctx & 0xffffu) << 16) | (dv & 0xffffu), a + p, &A.info[f].overflow);
         uint32_t last = __shfl_sync(KVG_FULL, sc, 31);

@@ -381,7 +381,8 @@ def test_batch_parse_device_resident(kv, pciids):
     d = util.pciids_names()
     names = c.name_table(0, 65536)
     assert {"%04x" % i: n for i, n in enumerate(names) if n} == {k: v for k, v in d["names"].items() if v}
-    assert info["n_entries"] > 19000
+    # the table holds the device lines under vendor 10de only (nothing else is ever looked up)
+    assert sum(1 for v in d["names"].values() if v) <= info["n_entries"] < 4000
     c.dev_pciids_parse(dev.data_ptr(), len(pciids), stride, n_files)  # steady-state path
     assert c.name_lookup("2901") == "GB100_B200"
     c.close()
