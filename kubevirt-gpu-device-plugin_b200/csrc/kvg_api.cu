@@ -185,7 +185,7 @@ struct kvg_ctx {
   DevBuf<uint64_t> offs_state;
   DevBuf<uint64_t> classify_state;
   OrderBufs ord_dev, ord_grp;
-  DevBuf<uint32_t> tile_hist;
+  DevBuf<uint32_t> tile_hist, bin_total;
   size_t last_n = 0;     // records of the last enqueued scan
   size_t last_total = 0; // survivors capacity used by the last scan (sharded: all ranks)
   int last_kind = 0;     // 1 = pci, 2 = mdev
@@ -478,7 +478,7 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   release(ctx->parse_state); release(ctx->parse_ticket); release(ctx->pool); release(ctx->ctrl);
   release(ctx->nv_index); release(ctx->nv_lines); release(ctx->sec_lines); release(ctx->type_hash); release(ctx->ragged); release(ctx->tile_count); release(ctx->tile_off);
   release(ctx->tile_max); release(ctx->offs_state);
-  release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist);
+  release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist); release(ctx->bin_total);
   for (OrderBufs* o : {&ctx->ord_dev, &ctx->ord_grp}) {
     release(o->p0); release(o->p1); release(o->perm); release(o->tile_heads); release(o->tile_off);
     release(o->seg_key); release(o->seg_off); release(o->seg_name); release(o->heads_state);
@@ -946,7 +946,8 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1, bool 
   if (rc) return rc;
   size_t T = (cap + C_TILE - 1) / C_TILE;
   if (T == 0) T = 1;
-  ENSURE(ctx->tile_hist, 2 * 256 * T);
+  ENSURE(ctx->tile_hist, 2 * (size_t)RADIX_MAX_DIGITS * T);
+  ENSURE(ctx->bin_total, 2 * (size_t)RADIX_MAX_DIGITS);
   ScanCtrl* c = ctx->ctrl.p;
   OrderBufs* ob[2] = {&ctx->ord_dev, &ctx->ord_grp};
   uint32_t* maxk[2] = {&c->max_devkey, &c->max_group};
@@ -982,8 +983,13 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1, bool 
              (uint32_t)(TT * RR), ob[ord]->p1.p);
     }
   }
-  const int npass[2] = {2, 4};
+  const uint32_t key_bits[2] = {16, 32};  // device id / mdev type: u16; iommu group / parent: u32
   const int srcs[2] = {src0, src1};
+  // digit width: up to 11 bits where the scan is latency-bound (fewer passes: 19-bit groups sort in 2),
+  // 8 bits for inputs large enough to be bandwidth-bound (half the shared memory, twice the CTAs/SM)
+  const uint32_t max_bits = cap >= (8u << 20) ? 8 : RADIX_MAX_BITS;
+  const int nsets[2] = {(int)((key_bits[0] + max_bits - 1) / max_bits),
+                        (int)((key_bits[1] + max_bits - 1) / max_bits)};  // 2 and 3 (or 4) launch sets
   auto fill = [&](int ord, int p) {
     RadixArgs a;
     a.n_ptr = cnt[ord];
@@ -991,29 +997,41 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1, bool 
     a.src_records = ctx->surv.p;
     a.pairs_in = (p == 0 && !owned_only) ? nullptr : ((p & 1) ? ob[ord]->p0.p : ob[ord]->p1.p);
     a.pairs_out = (p & 1) ? ob[ord]->p1.p : ob[ord]->p0.p;
-    a.tile_hist = ctx->tile_hist.p + (size_t)ord * 256 * T;
-    a.bin_total = c->bin_total[ord][p];
-    a.shift = p < npass[ord] ? 8u * (uint32_t)p : 0xffu;
+    a.tile_hist = ctx->tile_hist.p + (size_t)ord * RADIX_MAX_DIGITS * T;
+    a.bin_total = ctx->bin_total.p + (size_t)ord * RADIX_MAX_DIGITS;
+    a.pass = p < nsets[ord] ? (uint32_t)p : 0xffu;
+    a.key_bits_max = key_bits[ord];
+    a.max_bits = max_bits;
     a.src = (p == 0 && !owned_only) ? srcs[ord] : SRC_PAIRS;
     return a;
   };
-  for (int p = 0; p < 4; p++) {
+  static bool scatter_smem_set = false;
+  if (!scatter_smem_set) {
+    CK(cudaFuncSetAttribute(k_radix_scatter<RADIX_MAX_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)RadixScatterCfg<RADIX_MAX_BITS>::SMEM));
+    scatter_smem_set = true;
+  }
+  for (int p = 0; p < nsets[1]; p++) {
     RadixArgs2 aa;
-    // passes 0/1 always run: one CTA per tile.  Passes 2/3 exist only for keys >= 2^16 / 2^24 and are
+    // sets 0/1 always have work: one CTA per tile.  Set 2 exists only for keys wider than 22 bits and is
     // usually ruled out on the device: a small persistent grid makes a ruled-out pass nearly free.
-    const unsigned gx = p < 2 ? (unsigned)T : (unsigned)std::min<size_t>(T, (size_t)ctx->sm_count * 4);
-    dim3 grid(gx, p < 2 ? 2 : 1);
-    if (p < 2) {
+    const bool both = p < nsets[0];
+    const unsigned gx = p < 2 ? (unsigned)T : (unsigned)std::min<size_t>(T, (size_t)ctx->sm_count * (max_bits == 8 ? 5 : 3));
+    dim3 grid(gx, both ? 2 : 1);
+    if (both) {
       aa.o[0] = fill(0, p);
       aa.o[1] = fill(1, p);
     } else {
       aa.o[0] = fill(1, p);
       aa.o[1] = aa.o[0];
     }
-    dim3 sgrid(256, grid.y);
+    dim3 sgrid(KVG_BLOCK, grid.y);
     LAUNCH("radix_hist", k_radix_hist, grid, KVG_BLOCK, 0, aa);
     LAUNCH("radix_tilescan", k_radix_tilescan, sgrid, KVG_BLOCK, 0, aa);
-    LAUNCH("radix_scatter", k_radix_scatter, grid, KVG_BLOCK, 0, aa);
+    if (max_bits == 8)
+      LAUNCH("radix_scatter", k_radix_scatter<8>, grid, KVG_BLOCK, RadixScatterCfg<8>::SMEM, aa);
+    else
+      LAUNCH("radix_scatter", k_radix_scatter<RADIX_MAX_BITS>, grid, KVG_BLOCK, RadixScatterCfg<RADIX_MAX_BITS>::SMEM, aa);
   }
   // final permutation + distinct keys of both orderings: count heads per tile, scan, emit
   OrderFinalArgs2 ff;
@@ -1024,7 +1042,8 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1, bool 
     a.p0 = ob[ord]->p0.p;
     a.p1 = ob[ord]->p1.p;
     a.max_key = maxk[ord];
-    a.npass_max = npass[ord];
+    a.key_bits_max = key_bits[ord];
+    a.max_bits = max_bits;
     a.n_ptr = cnt[ord];
     a.perm = ob[ord]->perm.p;
     a.tile_heads = ob[ord]->tile_heads.p;
@@ -1050,12 +1069,6 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1, bool 
   LAUNCH("tile_offsets", k_tile_offsets, ogrid, KVG_BLOCK, 0, tt, c, next_epoch());
   LAUNCH("order_emit", k_order_final<true>, fgrid, KVG_BLOCK, 0, ff);
   return check_launch(ctx, "orderings");
-}
-
-static int active_passes(uint32_t max_key, int npass_max) {
-  int np = 1;
-  while (np < npass_max && (max_key >> (8 * np)) != 0) np++;
-  return np;
 }
 
 static int enqueue_pci_orderings(kvg_ctx* ctx, size_t surv_cap, bool owned_only = false) {
@@ -1638,8 +1651,6 @@ int kvg_dev_scan_mdev_fetch(kvg_ctx* ctx, kvg_mdev_result** res) {
   CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   const size_t S = ctx->h_ctrl->n_surv, KT = ctx->h_ctrl->n_dev_keys, P = ctx->h_ctrl->n_groups;
-  const int np_t = active_passes(ctx->h_ctrl->max_devkey, 2);
-  const int np_p = active_passes(ctx->h_ctrl->max_group, 4);
   const uint32_t nt = ctx->n_types;
   const size_t raw_len = nt ? ctx->h_type_off[nt] : 0;
   const uint32_t NAME_CAP = 256;

@@ -33,7 +33,7 @@ struct ScanCtrl {
   uint32_t n_alive;       // health
   uint32_t n_changed;
   uint32_t pad0;
-  uint32_t bin_total[2][4][256];  // [sort][pass][digit]
+  uint32_t reserved2[16];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -692,26 +692,58 @@ struct HealthOp {
 // ------------------------------------------------------------------------------------------------
 enum : int { SRC_PAIRS = 0, SRC_PCI_GROUP = 1, SRC_PCI_DEVICE = 2, SRC_MDEV_PARENT = 3, SRC_MDEV_TYPE = 4 };
 
+// Digit width is decided ON THE DEVICE from the largest key of the ordering: the fewest passes of at
+// most RADIX_MAX_BITS bits, the key bits split evenly between them (19-bit keys: 2 passes of 10 bits
+// instead of 3 of 8; 16-bit keys: 2 x 8; 23-bit: 3 x 8).  Every CTA of every kernel of a pass derives
+// the same plan from the same word, so nothing about it crosses the host.
+constexpr uint32_t RADIX_MAX_BITS = 11;
+constexpr uint32_t RADIX_MAX_DIGITS = 1u << RADIX_MAX_BITS;  // 2048
+constexpr uint32_t RADIX_CHUNKS = RADIX_MAX_DIGITS / KVG_BLOCK;  // digit chunks of one thread each
+struct RadixPlan {
+  uint32_t npass, shift, bits;  // of the queried pass; bits == 0: the pass does not exist
+};
+__host__ __device__ __forceinline__ RadixPlan radix_plan(uint32_t max_key, uint32_t key_bits_max, uint32_t pass,
+                                                         uint32_t max_bits) {
+#ifdef __CUDA_ARCH__
+  uint32_t kb = max_key ? 32u - (uint32_t)__clz((int)max_key) : 1u;
+#else
+  uint32_t kb = 1;
+  while (kb < 32 && (max_key >> kb) != 0) kb++;
+#endif
+  if (kb > key_bits_max) kb = key_bits_max;
+  RadixPlan r;
+  r.npass = (kb + max_bits - 1) / max_bits;
+  const uint32_t w = (kb + r.npass - 1) / r.npass;
+  r.shift = pass * w;
+  r.bits = pass < r.npass ? (kb - r.shift < w ? kb - r.shift : w) : 0;
+  return r;
+}
+
 struct RadixArgs {
   const uint32_t* n_ptr;      // element count (device)
-  const uint32_t* max_key;    // largest key (device): passes at or above its bit width are skipped
+  const uint32_t* max_key;    // largest key (device): decides the plan
   const void* src_records;    // survivors (SRC_* != PAIRS)
   const uint2* pairs_in;      // {key, val}
   uint2* pairs_out;
-  uint32_t* tile_hist;        // [256][T]  (T = ceil(n / C_TILE)), digit-major
-  uint32_t* bin_total;        // [256] for this pass
-  uint32_t shift;
+  uint32_t* tile_hist;        // [digits][T]  (T = ceil(n / C_TILE)), digit-major
+  uint32_t* bin_total;        // [RADIX_MAX_DIGITS] for this ordering (rewritten by every pass)
+  uint32_t pass;              // 0xff: this ordering has no such pass
+  uint32_t key_bits_max;      // 16 (device id / type) or 32 (iommu group / parent)
+  uint32_t max_bits;          // widest digit: 11 (latency-bound sizes) or 8 (large inputs: 6 CTAs/SM)
   int src;                    // where pass-0 keys come from
 };
 
 // both orderings (device id, iommu group) run their passes in the SAME launches: blockIdx.y
-// selects the ordering; an ordering that has no such pass carries shift == 0xff
+// selects the ordering
 struct RadixArgs2 {
   RadixArgs o[2];
 };
-__device__ __forceinline__ bool radix_pass_active(const RadixArgs& a) {
-  if (a.shift >= 32) return false;
-  return a.shift == 0 || (*a.max_key >> a.shift) != 0;
+__device__ __forceinline__ RadixPlan radix_pass(const RadixArgs& a) {
+  if (a.pass == 0xffu) {
+    RadixPlan r = {0, 0, 0};
+    return r;
+  }
+  return radix_plan(*a.max_key, a.key_bits_max, a.pass, a.max_bits);
 }
 __device__ __forceinline__ uint2 radix_load(const RadixArgs& a, uint32_t i) {
   switch (a.src) {
@@ -732,73 +764,109 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_radix_hist(RadixArgs2 aa) {
   const RadixArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
-  if (!radix_pass_active(a)) return;
-  __shared__ uint32_t h[256];
+  const RadixPlan pl = radix_pass(a);
+  if (!pl.bits) return;
+  const uint32_t dmask = (1u << pl.bits) - 1;
+  const uint32_t nj = ((1u << pl.bits) + KVG_BLOCK - 1) / KVG_BLOCK;  // digit chunks in use
+  __shared__ uint32_t h[RADIX_MAX_DIGITS];
   const uint32_t lane = lane_id();
   // tile loop: launched with one CTA per tile for the always-active passes, with a small grid for the
   // high passes that are usually ruled out by the device-side max key (they then cost ~nothing)
   for (uint32_t tile = blockIdx.x; tile < T; tile += gridDim.x) {
-    h[threadIdx.x] = 0;
+    for (uint32_t j = 0; j < nj; j++) h[j * KVG_BLOCK + threadIdx.x] = 0;
     __syncthreads();
     const uint32_t base = tile * C_TILE + warp_id() * C_WARP_ITEMS;
     uint32_t d[C_ROWS];
 #pragma unroll
     for (uint32_t k = 0; k < C_ROWS; k++) {  // all loads in flight before the first shared atomic
       uint32_t i = base + k * 32 + lane;
-      d[k] = i < n ? ((radix_load(a, i).x >> a.shift) & 0xffu) : 0x100u;
+      d[k] = i < n ? ((radix_load(a, i).x >> pl.shift) & dmask) : 0xffffffffu;
     }
 #pragma unroll
     for (uint32_t k = 0; k < C_ROWS; k++)
-      if (d[k] < 0x100u) atomicAdd(&h[d[k]], 1u);
+      if (d[k] != 0xffffffffu) atomicAdd(&h[d[k]], 1u);
     __syncthreads();
-    a.tile_hist[(size_t)threadIdx.x * T + tile] = h[threadIdx.x];
+    for (uint32_t j = 0; j < nj; j++) {
+      const uint32_t dg = j * KVG_BLOCK + threadIdx.x;
+      a.tile_hist[(size_t)dg * T + tile] = h[dg];
+    }
     __syncthreads();
   }
 }
 
-// one CTA per digit: exclusive scan of that digit's per-tile counts, in place
+// one CTA per digit (and per 256-digit chunk): exclusive scan of that digit's per-tile counts, in place
 __global__ void __launch_bounds__(KVG_BLOCK) k_radix_tilescan(RadixArgs2 aa) {
   pdl_enter();
   const RadixArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
-  if (T == 0 || !radix_pass_active(a)) return;
+  const RadixPlan pl = radix_pass(a);
+  if (T == 0 || !pl.bits) return;
+  const uint32_t nj = ((1u << pl.bits) + KVG_BLOCK - 1) / KVG_BLOCK;
   __shared__ uint32_t scratch[KVG_WARPS + 1];
-  uint32_t* row = a.tile_hist + (size_t)blockIdx.x * T;
-  uint32_t carry = 0;
-  for (uint32_t b = 0; b < T; b += KVG_BLOCK) {
-    uint32_t i = b + threadIdx.x;
-    uint32_t v = i < T ? row[i] : 0;
-    uint32_t total;
-    uint32_t e = block_excl_sum(v, scratch, &total);
-    if (i < T) row[i] = carry + e;
-    carry += total;
-    __syncthreads();
+  for (uint32_t j = 0; j < nj; j++) {  // grid.x == KVG_BLOCK: CTA b owns digits b, b + 256, ...
+    const uint32_t dg = j * KVG_BLOCK + blockIdx.x;
+    uint32_t* row = a.tile_hist + (size_t)dg * T;
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < T; b += KVG_BLOCK) {
+      uint32_t i = b + threadIdx.x;
+      uint32_t v = i < T ? row[i] : 0;
+      uint32_t total;
+      uint32_t e = block_excl_sum(v, scratch, &total);
+      if (i < T) row[i] = carry + e;
+      carry += total;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) a.bin_total[dg] = carry;  // total of this digit (was: atomics in the histogram)
   }
-  if (threadIdx.x == 0) a.bin_total[blockIdx.x] = carry;  // total of this digit (was: atomics in the histogram)
 }
 
-__global__ void __launch_bounds__(KVG_BLOCK, 6) k_radix_scatter(RadixArgs2 aa) {
+// dynamic shared memory of k_radix_scatter: per-warp digit counts (u16: a warp owns 256 items),
+// tile-local digit starts, global run offsets, the staged tile
+// (11-bit digits: 32 + 4 + 8 + 16 = 60 KiB, 3 CTAs/SM; 8-bit digits: 4 + 0.5 + 1 + 16 KiB, 5 CTAs/SM)
+template <uint32_t MAXB>
+struct RadixScatterCfg {
+  static constexpr uint32_t DIGITS = 1u << MAXB;
+  static constexpr uint32_t CHUNKS = DIGITS / KVG_BLOCK;
+  static constexpr uint32_t CNT_BYTES = KVG_WARPS * DIGITS * 2;
+  static constexpr uint32_t START_BYTES = DIGITS * 2;
+  static constexpr uint32_t GOFF_BYTES = DIGITS * 4;
+  static constexpr uint32_t STAGE_BYTES = C_TILE * 8;
+  static constexpr uint32_t SMEM = CNT_BYTES + START_BYTES + GOFF_BYTES + STAGE_BYTES;
+  static constexpr int MIN_CTAS = MAXB <= 8 ? 5 : 3;  // 6 would cap registers at 40 and spill
+};
+
+template <uint32_t MAXB>
+__global__ void __launch_bounds__(KVG_BLOCK, RadixScatterCfg<MAXB>::MIN_CTAS) k_radix_scatter(RadixArgs2 aa) {
+  using Cfg = RadixScatterCfg<MAXB>;
+  constexpr uint32_t RADIX_CHUNKS = Cfg::CHUNKS, RADIX_MAX_DIGITS = Cfg::DIGITS;
+  constexpr uint32_t RS_CNT_BYTES = Cfg::CNT_BYTES, RS_START_BYTES = Cfg::START_BYTES, RS_GOFF_BYTES = Cfg::GOFF_BYTES;
   pdl_enter();
   const RadixArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
-  if (!radix_pass_active(a)) return;
+  const RadixPlan pl = radix_pass(a);
+  if (!pl.bits) return;
+  const uint32_t dmask = (1u << pl.bits) - 1;
+  const uint32_t nj = RADIX_CHUNKS == 1 ? 1u : ((1u << pl.bits) + KVG_BLOCK - 1) / KVG_BLOCK;
   const uint32_t lane = lane_id(), warp = warp_id(), tid = threadIdx.x;
-  __shared__ uint32_t s_cnt[KVG_WARPS][256];  // per-warp digit counts, then warp bases
-  __shared__ uint32_t s_start[256];           // tile-local exclusive start of each digit
-  __shared__ int32_t s_goff[256];             // global position of a digit's run minus its local start
+  extern __shared__ __align__(16) uint8_t rs_smem[];
+  uint16_t (*s_cnt)[RADIX_MAX_DIGITS] = reinterpret_cast<uint16_t (*)[RADIX_MAX_DIGITS]>(rs_smem);
+  uint16_t* s_start = reinterpret_cast<uint16_t*>(rs_smem + RS_CNT_BYTES);  // tile-local exclusive start of each digit
+  int32_t* s_goff = reinterpret_cast<int32_t*>(rs_smem + RS_CNT_BYTES + RS_START_BYTES);  // global run position - local start
+  uint2* s_stage = reinterpret_cast<uint2*>(rs_smem + RS_CNT_BYTES + RS_START_BYTES + RS_GOFF_BYTES);
   __shared__ uint32_t scratch[KVG_WARPS + 1];
-  __shared__ uint2 s_stage[C_TILE];           // pairs in tile-sorted order (16 KiB)
   uint32_t total;
-  const uint32_t bin_total_mine = a.bin_total[tid];
-  uint32_t bin_base = 0;
+  uint32_t bin_base[RADIX_CHUNKS];
   bool have_base = false;
   for (uint32_t tile = blockIdx.x; tile < T; tile += gridDim.x) {
   const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
-  // every global load of the tile is issued before anything waits: the pairs, this digit's
-  // scanned tile count and (first tile only) the digit totals -> ONE memory latency per tile
-  const uint32_t tile_prefix = a.tile_hist[(size_t)tid * T + tile];
+  // every global load of the tile is issued before anything waits: the pairs, the scanned tile
+  // counts of this thread's digits and (first tile only) the digit totals -> ONE memory latency
+  uint32_t tile_prefix[RADIX_CHUNKS];
+#pragma unroll
+  for (uint32_t j = 0; j < RADIX_CHUNKS; j++)
+    tile_prefix[j] = j < nj ? a.tile_hist[(size_t)(j * KVG_BLOCK + tid) * T + tile] : 0;
   uint2 kv[C_ROWS];
   uint32_t rank[C_ROWS];
 #pragma unroll
@@ -807,10 +875,22 @@ __global__ void __launch_bounds__(KVG_BLOCK, 6) k_radix_scatter(RadixArgs2 aa) {
     kv[k] = i < n ? radix_load(a, i) : make_uint2(0, 0);
   }
   __syncthreads();  // previous tile's stage fully written out
+  for (uint32_t j = 0; j < nj; j++) {
 #pragma unroll
-  for (uint32_t w = 0; w < KVG_WARPS; w++) s_cnt[w][tid] = 0;
-  if (!have_base) {
-    bin_base = block_excl_sum(bin_total_mine, scratch, &total);  // syncs inside
+    for (uint32_t w = 0; w < KVG_WARPS; w++) s_cnt[w][j * KVG_BLOCK + tid] = 0;
+  }
+  if (!have_base) {  // exclusive scan of the digit totals, digit chunks in order
+    uint32_t carry = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < RADIX_CHUNKS; j++) {
+      bin_base[j] = 0;
+      if (j < nj) {
+        const uint32_t mine = a.bin_total[j * KVG_BLOCK + tid];
+        bin_base[j] = carry + block_excl_sum(mine, scratch, &total);  // syncs inside
+        carry += total;
+        __syncthreads();
+      }
+    }
     have_base = true;
   }
   __syncthreads();
@@ -819,45 +899,57 @@ __global__ void __launch_bounds__(KVG_BLOCK, 6) k_radix_scatter(RadixArgs2 aa) {
   for (uint32_t k = 0; k < C_ROWS; k++) {
     uint32_t i = base + k * 32 + lane;
     bool ok = i < n;
-    uint32_t d = ok ? ((kv[k].x >> a.shift) & 0xffu) : (0x100u + lane);  // inactive lanes: unique
+    uint32_t d = ok ? ((kv[k].x >> pl.shift) & dmask) : (0x10000u + lane);  // inactive lanes: unique
     uint32_t peers = __match_any_sync(KVG_FULL, d);
     uint32_t leader = (uint32_t)__ffs(peers) - 1;
     uint32_t before = 0;
     if (ok && lane == leader) {
       before = s_cnt[warp][d];
-      s_cnt[warp][d] = before + __popc(peers);
+      s_cnt[warp][d] = (uint16_t)(before + __popc(peers));
     }
     before = __shfl_sync(KVG_FULL, before, leader);
     rank[k] = before + __popc(peers & lanemask_lt());
     __syncwarp();
   }
   __syncthreads();
-  uint32_t dtot = 0;
-  {  // digit == tid: exclusive prefix over warps, total of the digit in this tile
+  {  // per digit: exclusive prefix over warps, tile-local start, global run offset
+    uint32_t carry = 0;
+    for (uint32_t j = 0; j < nj; j++) {
+      const uint32_t dg = j * KVG_BLOCK + tid;
+      uint32_t dtot = 0;
 #pragma unroll
-    for (uint32_t w = 0; w < KVG_WARPS; w++) {
-      uint32_t c = s_cnt[w][tid];
-      s_cnt[w][tid] = dtot;
-      dtot += c;
+      for (uint32_t w = 0; w < KVG_WARPS; w++) {
+        uint32_t c = s_cnt[w][dg];
+        s_cnt[w][dg] = (uint16_t)dtot;
+        dtot += c;
+      }
+      const uint32_t lstart = carry + block_excl_sum(dtot, scratch, &total);  // syncs inside
+      carry += total;
+      s_start[dg] = (uint16_t)lstart;
+      uint32_t bb = 0, tp = 0;
+#pragma unroll
+      for (uint32_t q = 0; q < RADIX_CHUNKS; q++)  // static register indices
+        if (q == j) {
+          bb = bin_base[q];
+          tp = tile_prefix[q];
+        }
+      s_goff[dg] = (int32_t)(bb + tp) - (int32_t)lstart;
+      __syncthreads();
     }
   }
-  const uint32_t lstart = block_excl_sum(dtot, scratch, &total);  // syncs inside
-  s_start[tid] = lstart;
-  s_goff[tid] = (int32_t)(bin_base + tile_prefix) - (int32_t)lstart;
-  __syncthreads();
 #pragma unroll
   for (uint32_t k = 0; k < C_ROWS; k++) {
     uint32_t i = base + k * 32 + lane;
     if (i < n) {
-      uint32_t d = (kv[k].x >> a.shift) & 0xffu;
-      s_stage[s_start[d] + s_cnt[warp][d] + rank[k]] = kv[k];
+      uint32_t d = (kv[k].x >> pl.shift) & dmask;
+      s_stage[(uint32_t)s_start[d] + s_cnt[warp][d] + rank[k]] = kv[k];
     }
   }
   __syncthreads();
   const uint32_t cnt = min(C_TILE, n - tile * C_TILE);
   for (uint32_t j = tid; j < cnt; j += KVG_BLOCK) {
     uint2 e = s_stage[j];
-    uint32_t d = (e.x >> a.shift) & 0xffu;
+    uint32_t d = (e.x >> pl.shift) & dmask;
     a.pairs_out[(uint32_t)(s_goff[d] + (int32_t)j)] = e;
   }
   }  // tile loop
@@ -868,7 +960,7 @@ struct OrderFinalArgs {
   const uint2* p0;            // ping-pong buffers of the radix passes
   const uint2* p1;
   const uint32_t* max_key;
-  int npass_max;
+  uint32_t key_bits_max, max_bits;
   const uint32_t* n_ptr;
   uint32_t* perm;             // [n] survivor indices in key order (stable)
   uint32_t* tile_heads;       // [T] number of segment heads in each tile
@@ -880,9 +972,7 @@ struct OrderFinalArgs {
   uint32_t* head_name;        // [n_seg] name slot of the segment's first member (NULL: skip)
 };
 __device__ __forceinline__ const uint2* order_final_buf(const OrderFinalArgs& a) {
-  uint32_t mk = *a.max_key;
-  int np = 1;
-  while (np < a.npass_max && (mk >> (8 * np)) != 0) np++;
+  const uint32_t np = radix_plan(*a.max_key, a.key_bits_max, 0, a.max_bits).npass;
   return ((np - 1) & 1) ? a.p1 : a.p0;
 }
 struct OrderFinalArgs2 {
