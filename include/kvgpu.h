@@ -256,6 +256,12 @@ int kvg_dev_gen_pci(kvg_ctx *ctx, void *d_recs, uint64_t first, size_t n, const 
 int kvg_dev_gen_mdev(kvg_ctx *ctx, void *d_recs, uint64_t first, size_t n);
 int kvg_dev_scan_mdev(kvg_ctx *ctx, const void *d_recs, size_t n, const kvg_type_dict *types);
 int kvg_dev_scan_mdev_fetch(kvg_ctx *ctx, kvg_mdev_result **res);
+/* Diagnostics: the pass structure (count, shift and width of each pass) the radix kernels derive on
+ * the device for an ordering whose largest key is `max_key` (key_bits_max 16 or 32; max_bits 11, or 8 for
+ * inputs >= 8 Mi records).  Pure host arithmetic: usable without a GPU. */
+int kvg_debug_radix_plan(uint32_t max_key, uint32_t key_bits_max, uint32_t max_bits, uint32_t *npass,
+                         uint32_t *shifts4, uint32_t *bits4);
+
 /* diagnostic only: decomposed classify kernel (mode 0 read+count, 1 +tile-local writes, 2 +join);
  * rows = records per thread (4, 8 or 16); *ms_out = device time of the launch */
 int kvg_dev_debug_classify(kvg_ctx *ctx, const void *d_recs, size_t n, int mode, int rows,

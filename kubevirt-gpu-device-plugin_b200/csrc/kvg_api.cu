@@ -1774,6 +1774,21 @@ int kvg_dev_gen_mdev(kvg_ctx* ctx, void* d_recs, uint64_t first, size_t n) {
   return check_launch(ctx, "gen_mdev");
 }
 // diagnostic: decomposed classify kernel (see k_debug_classify); returns device ms via *ms_out
+// host-side view of the device's radix plan (same __host__ __device__ function): lets CPU-only tests pin
+// the pass structure the kernels will choose for a given largest key
+int kvg_debug_radix_plan(uint32_t max_key, uint32_t key_bits_max, uint32_t max_bits, uint32_t* npass,
+                         uint32_t* shifts4, uint32_t* bits4) {
+  if (!npass || !shifts4 || !bits4 || key_bits_max == 0 || key_bits_max > 32 || max_bits == 0 || max_bits > 16)
+    return KVG_EINVAL;
+  *npass = radix_plan(max_key, key_bits_max, 0, max_bits).npass;
+  for (uint32_t p = 0; p < 4; p++) {
+    RadixPlan r = radix_plan(max_key, key_bits_max, p, max_bits);
+    shifts4[p] = r.shift;
+    bits4[p] = r.bits;
+  }
+  return KVG_OK;
+}
+
 int kvg_dev_debug_classify(kvg_ctx* ctx, const void* d_recs, size_t n, int mode, int rows, float* ms_out) {
   if (!ctx || !d_recs || !ms_out || n == 0 || n > 0xfffffff0ull) return KVG_EINVAL;
   CK(cudaSetDevice(ctx->device));

@@ -130,6 +130,7 @@ def load() -> C.CDLL:
         "kvg_comm_p2p_export": (C.c_int, [vp, C.c_int, C.c_int, sz, vp]),
         "kvg_comm_p2p_import": (C.c_int, [vp, vp]),
         "kvg_comm_p2p_enable": (C.c_int, [vp, C.c_int]),
+        "kvg_debug_radix_plan": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp]),
         "kvg_dev_scan_pci_sharded": (C.c_int, [vp, vp, sz]),
     }
     for name, (res, args) in sig.items():

@@ -205,3 +205,29 @@ def test_native_host_has_no_cpu_fallback():
     assert L.kvgh_create(b"/x", b"/y", b"/z", 0, C.byref(h)) == -2  # KVG_ECUDA
     r = subprocess.run([os.path.join(conftest.PKG, "kvg-discover")], capture_output=True, text=True)
     assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+def test_radix_plan_covers_every_key_width():
+    """The device-side digit plan (kvg_scan.cuh: radix_plan), evaluated on the host: passes are
+    contiguous, no wider than the limit, as few as possible, and cover exactly the key's bits."""
+    import ctypes as C
+    import kvgpu
+    lib = kvgpu.load()
+    for max_bits in (8, 11):
+        for key_bits_max in (16, 32):
+            for kb in range(1, key_bits_max + 1):
+                for max_key in {1 << (kb - 1), (1 << kb) - 1}:
+                    np_, sh, bt = C.c_uint32(), (C.c_uint32 * 4)(), (C.c_uint32 * 4)()
+                    assert lib.kvg_debug_radix_plan(max_key, key_bits_max, max_bits, C.byref(np_), sh, bt) == 0
+                    n = np_.value
+                    assert n == -(-kb // max_bits) and 1 <= n <= 4
+                    assert sh[0] == 0 and all(0 < bt[p] <= max_bits for p in range(n))
+                    assert all(sh[p] == sh[p - 1] + bt[p - 1] for p in range(1, n))
+                    assert sum(bt[p] for p in range(n)) == kb
+                    assert all(bt[p] == 0 for p in range(n, 4))
+                    assert max(bt[:n]) - min(bt[:n]) <= max_bits   # even split: no degenerate 1-bit tail pass
+    # keys wider than the ordering allows are clamped (device ids are 16-bit by construction)
+    np_, sh, bt = C.c_uint32(), (C.c_uint32 * 4)(), (C.c_uint32 * 4)()
+    assert lib.kvg_debug_radix_plan(0xffffffff, 16, 11, C.byref(np_), sh, bt) == 0
+    assert np_.value == 2 and list(bt) == [8, 8, 0, 0]
+    assert lib.kvg_debug_radix_plan(0, 32, 11, C.byref(np_), sh, bt) == 0 and np_.value == 1

@@ -191,6 +191,36 @@ def test_scan_pci_matches_oracle(kv, loaded, pciids, n, group_bits):
     assert res.n_records == n
 
 
+@pytest.mark.parametrize("bits", [1, 8, 9, 11, 12, 16, 17, 21, 22, 23, 24, 31, 32])
+def test_orderings_at_key_width_boundaries(kv, loaded, pciids, bits):
+    """The radix digit width is derived on the device from the largest key: walk the plan through
+    every pass-count boundary (11 / 22 bits), narrow and full-width keys, and a small device-id range."""
+    ids = O.nv_ids(pciids)
+    n = 40_000
+    recs = O.gen_pci(0, n, ids, 0)
+    rng = np.random.default_rng(bits)
+    hi = (1 << bits) - 1
+    recs["iommu_group"] = rng.integers(0, hi + 1, n, dtype=np.uint64).astype(np.uint32)
+    recs[0] = (0x0100, 0x10de, int(ids[0]), hi, 1, 0, 0)      # a certain survivor carrying the widest key
+    recs[n - 1] = (0x0200, 0x10de, int(ids[1]), 0, 1, 0, 0)   # ... and the narrowest
+    if bits == 8:   # few distinct small device ids: a single-pass ordering 0
+        recs["device"] = (recs["device"] & 0x3f).astype(np.uint16)
+    got, res = _pci_dump_gpu(kv, loaded, recs)
+    assert got == _pci_dump_oracle(recs, pciids)
+
+
+@pytest.mark.parametrize("n", [131_072, 131_077, 300_001, 1_048_576 + 1])
+def test_pipelined_host_entry_matches_oracle(kv, loaded, pciids, n):
+    """kvg_scan_pci switches to the chunked copy / classify / copy-back pipeline at 128 Ki records:
+    sizes on and off the tile and chunk boundaries, plus the plain path forced on the same input."""
+    ids = O.nv_ids(pciids)
+    recs = O.gen_pci(7, n, ids, 18)
+    want = _pci_dump_oracle(recs, pciids)
+    for rep in range(2):
+        got, res = _pci_dump_gpu(kv, loaded, recs)
+        assert got == want and res.n_records == n
+
+
 def test_scan_pci_config2_one_million(kv, loaded, pciids):
     """BASELINE.json config 2: full pci.ids + 1,000,000 synthetic PCI records."""
     ids = O.nv_ids(pciids)
