@@ -299,7 +299,20 @@ def main():
                 "frac": ach / hbm_peak, "traffic": None, "algorithmic_bytes": nbytes,
                 "avg_launch_ms": ms / launches_per_step, "peak_source": peak_src}
     nl = {k: len(v) / passes for k, v in per.items()}     # launches per step
+    # DRAM traffic per launch from the committed ncu --set full captures (never measured here: a
+    # number taken under a profiler is not a bench number, and ncu is not run by bench.py)
+    try:
+        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+    except (OSError, ValueError):
+        ncu_traffic = {}
+
+    def traffic_for(key):
+        t = ncu_traffic.get(key)
+        return t["bytes_per_launch"] if t else None
     roofline = roof(dominant, algo[dominant], ksum[dominant], nl[dominant])
+    if n == 1_000_000:
+        roofline["traffic"] = traffic_for(dominant + "@config2")
+        roofline["traffic_note"] = "per launch, from profiles/r01_ncu_traffic.json (ncu --set full capture of the same kernel and size)"
     roofline["share_of_step"] = ksum[dominant] / step_ms
     roofline["note"] = ("bytes and time are per STEP for the whole kernel family (all its launches); "
                         "at this 1M-record config every kernel is latency-bound — see roofline_hbm_bound")
@@ -328,6 +341,7 @@ def main():
         r = roof("classify_compact", 16 * nb + 16 * Sb, sum(ts) / len(ts))
         r.update({"records": nb, "survivors": Sb, "whole_scan_ms": tot_ms,
                   "whole_scan_records_per_s": nb / (tot_ms * 1e-3)})
+        r["traffic"] = traffic_for("classify_compact@%d" % nb)
         roofline_big["classify_compact"] = r
         del big
     if world == 1 and args.big_files:
@@ -349,6 +363,7 @@ def main():
         r = roof("pciids_parse", nf * (len(text) + 8 * ent), sum(ts) / len(ts))
         r.update({"images": nf, "text_bytes": nf * len(text), "entries_per_image": ent,
                   "parse_GBps_text_only": nf * len(text) / (sum(ts) / len(ts) * 1e-3) / 1e9})
+        r["traffic"] = traffic_for("pciids_parse@%d" % nf)
         roofline_big["pciids_parse"] = r
         c2.close()
         del bigt

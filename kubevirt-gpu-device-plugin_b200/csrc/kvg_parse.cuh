@@ -6,7 +6,7 @@
 //                          (vendor<<16|device) -> line-offset hash of the lines under vendor 10de,
 //                          first line wins (atomicMin)
 //   k_pciids_finalize      section bounds of the FIRST "10de" line, bufio.Scanner 64 KiB limit
-//   k_pciids_sanitise  K2  name transform of :404-414 for every candidate line of the section
+//   k_pciids_sanitise_lines  K2  name transform of :404-414, one warp per named line of the section
 //   k_probe_keys           hash probe for 4-lower-hex keys (the join used by the scans)
 //   k_lookup_general       exact prefix semantics of :388-402 for arbitrary key bytes
 //   k_sanitise_matches     name transform for the lines found by k_lookup_general
@@ -565,46 +565,6 @@ __device__ uint32_t d_sanitise_name(const uint8_t* s, uint32_t n, uint8_t* out, 
   return o;
 }
 
-// K2: each CTA stages a 256-byte window of the NVIDIA section (+ 256 B so that an ordinary line
-// is fully inside) in shared memory with coalesced loads; the thread sitting on the first byte of a
-// candidate line ("\t" + 4 lower-hex) sanitises it into pool[off - V] = u16 len + bytes.  Lines
-// running past the staged bytes (> 256 B) are read from global memory instead.
-constexpr uint32_t S_WIN = 256, S_HALO = 256;  // one byte position per thread: line work is not serialised
-__global__ void __launch_bounds__(KVG_BLOCK) k_pciids_sanitise(const uint8_t* __restrict__ text,
-                                                               uint32_t len,
-                                                               const PciIdsInfo* __restrict__ info,
-                                                               uint8_t* __restrict__ pool) {
-  pdl_enter();
-  __shared__ __align__(16) uint8_t win[S_WIN + S_HALO];
-  const uint32_t V = info->v_off, E = info->sec_end;
-  if (V == P_NONE) return;
-  for (uint32_t w0 = V + blockIdx.x * S_WIN; w0 < E; w0 += gridDim.x * S_WIN) {
-    const uint32_t have = min(S_WIN + S_HALO, len - w0);
-    __syncthreads();
-    for (uint32_t t = threadIdx.x; t < have; t += blockDim.x) win[t] = text[w0 + t];
-    __syncthreads();
-    for (uint32_t t = threadIdx.x; t < S_WIN; t += blockDim.x) {
-      const uint32_t b = w0 + t;
-      if (b <= V || b >= E) continue;
-      if ((t ? win[t - 1] : text[b - 1]) != '\n' || win[t] != '\t') continue;
-      if (b + 5 > len || t + 5 > have) continue;
-      if (!(parse_hex4(win + t + 1) & 0x10000u)) continue;
-      uint32_t e = t + 5;
-      while (e < have && win[e] != '\n') e++;
-      uint8_t* slot = pool + (b - V);
-      uint32_t n;
-      if (e < have || w0 + e >= len) {  // the whole line is staged
-        n = d_sanitise_name(win + t + 5, e - (t + 5), slot + 2, e - (t + 5));
-      } else {  // runs past the window: fall back to global memory
-        uint32_t ge = b + 5;
-        while (ge < len && text[ge] != '\n') ge++;
-        n = d_sanitise_name(text + b + 5, ge - (b + 5), slot + 2, ge - (b + 5));
-      }
-      slot[0] = (uint8_t)(n & 0xff);
-      slot[1] = (uint8_t)(n >> 8);
-    }
-  }
-}
 
 // hash probe for canonical keys: keys[i] = (vendor<<16)|device -> pool slot (off - V) or P_NONE
 __device__ __forceinline__ uint32_t probe_name_slot(const uint64_t* __restrict__ table,
