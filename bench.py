@@ -278,7 +278,12 @@ def main():
     S, KD, G = ctx.dev_scan_pci_count()
     info = ctx.pciids_info()
     S_local = S if not sharded else S // world   # survivors this rank classified (its shard)
-    grp_passes = max(1, (int(gbits) + 7) // 8)
+    # radix passes of the group ordering: the same plan the kernels derive on the device
+    import ctypes as _C
+    _np, _sh, _bt = _C.c_uint32(), (_C.c_uint32 * 4)(), (_C.c_uint32 * 4)()
+    kvgpu.load().kvg_debug_radix_plan((1 << int(gbits)) - 1 if gbits else max(n // 2, 1), 32,
+                                      8 if n >= (8 << 20) else 11, _C.byref(_np), _sh, _bt)
+    grp_passes = max(1, int(_np.value))
     # ALGORITHMIC bytes per step of every kernel family (DESIGN.md "Kernels"): what must move.
     algo = {
         "pciids_parse": len(text) + 8 * info["n_entries"],
