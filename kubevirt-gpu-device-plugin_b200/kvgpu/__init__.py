@@ -8,7 +8,8 @@ from ._lib import (KVG_NO_NAME, MDEV_REC, MDEV_SURV, PCI_REC, PCI_SURV, KvgError
 from .context import Context, HealthDelta, MdevResult, PciResult
 from .plugin import (DiscoveryScan, Maps, MdevSnapshot, NvidiaGpuDevice, PciSnapshot, PluginSpec,
                      ReferencePanic, canonical_dump, format_bdf, format_uuid,
-                     mdev_maps_from_result, parse_bdf, pci_maps_from_result, snapshot_mdev_tree,
+                     mdev_maps_from_result, parse_bdf, pci_maps_from_result, plugin_specs_from_maps,
+                     snapshot_mdev_tree,
                      snapshot_pci_tree)
 from .parallel import ShardedScan, allgatherv_torch, concat_in_rank_order, shard_range
 

@@ -457,21 +457,27 @@ class DiscoveryScan:
         return mdev_maps_from_result(res, snap, self.maps)
 
     def create_device_plugins(self) -> list:
-        specs = []
-        for key, devs in self.maps.deviceMap.items():
-            name = self.maps.deviceNames.get(key, "") or key
-            specs.append(PluginSpec(
-                key, name, "%s/%s" % (DEVICE_NAMESPACE, name),
-                "%skubevirt-%s.sock" % (DEVICE_PLUGIN_PATH, name),
-                "%s_%s" % (GPU_PREFIX, name.upper()),
-                [{"ID": d.addr, "Health": HEALTHY, "Topology": {"Nodes": [{"ID": d.numaNode}]}}
-                 for d in devs]))
-        for key, devs in self.maps.vGpuMap.items():
-            name = self.maps.deviceNames.get(key, "") or key
-            specs.append(PluginSpec(
-                key, name, "%s/%s" % (DEVICE_NAMESPACE, name),
-                "%skubevirt-%s.sock" % (DEVICE_PLUGIN_PATH, name),
-                "%s_%s" % (VGPU_PREFIX, name.upper()),
-                [{"ID": d.addr, "Health": HEALTHY, "Topology": {"Nodes": [{"ID": d.numaNode}]}}
-                 for d in devs], vgpu=True))
-        return specs
+        return plugin_specs_from_maps(self.maps)
+
+
+def plugin_specs_from_maps(maps: Maps) -> list:
+    """createDevicePlugins' payload half (device_plugin.go:99-157): one PluginSpec per deviceMap key,
+    then one per vGpuMap key; name falls back to the key when getDeviceName returned ""."""
+    specs = []
+    for key, devs in maps.deviceMap.items():
+        name = maps.deviceNames.get(key, "") or key
+        specs.append(PluginSpec(
+            key, name, "%s/%s" % (DEVICE_NAMESPACE, name),
+            "%skubevirt-%s.sock" % (DEVICE_PLUGIN_PATH, name),
+            "%s_%s" % (GPU_PREFIX, name.upper()),
+            [{"ID": d.addr, "Health": HEALTHY, "Topology": {"Nodes": [{"ID": d.numaNode}]}}
+             for d in devs]))
+    for key, devs in maps.vGpuMap.items():
+        name = maps.deviceNames.get(key, "") or key
+        specs.append(PluginSpec(
+            key, name, "%s/%s" % (DEVICE_NAMESPACE, name),
+            "%skubevirt-%s.sock" % (DEVICE_PLUGIN_PATH, name),
+            "%s_%s" % (VGPU_PREFIX, name.upper()),
+            [{"ID": d.addr, "Health": HEALTHY, "Topology": {"Nodes": [{"ID": d.numaNode}]}}
+             for d in devs], vgpu=True))
+    return specs
