@@ -23,7 +23,9 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <ctype.h>
 #include <map>
+#include <set>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -527,6 +529,144 @@ int kvgh_device_plugins(kvgh_scan* h, char** out, size_t* outlen) {
 }
 
 void kvgh_free(void* p) { free(p); }
+
+// ---- consumer-side host logic, native twins of kvgpu/serve.py ------------
+// Lists cross the boundary as '\n'-separated text; results are malloc'd (kvgh_free).
+#define KVGH_EALLOC (-101) /* the reference returns an error for this request; *out holds its text */
+
+static std::vector<std::string> split_lines(const char* text) {
+  std::vector<std::string> v;
+  if (!text) return v;
+  std::string cur;
+  for (const char* p = text; *p; p++) {
+    if (*p == '\n') {
+      v.push_back(cur);
+      cur.clear();
+    } else {
+      cur.push_back(*p);
+    }
+  }
+  if (!cur.empty()) v.push_back(cur);
+  return v;
+}
+static int give(const std::string& s, char** out, size_t* outlen) {
+  char* b = (char*)malloc(s.size() + 1);
+  if (!b) return KVG_ENOMEM;
+  memcpy(b, s.c_str(), s.size() + 1);
+  *out = b;
+  if (outlen) *outlen = s.size();
+  return KVG_OK;
+}
+
+// GetPreferredAllocation for one container request (generic_device_plugin.go:470-608).
+//   devs          "id\tnuma" per line ("id" alone: a device without topology)
+//   available / must_include   one id per line
+//   out           the preferred ids, one per line — or the error text with KVGH_EALLOC
+int kvgh_preferred_allocation(const char* devs, const char* available, const char* must_include, int allocation_size,
+                              char** out, size_t* outlen) {
+  if (!out) return KVG_EINVAL;
+  std::map<std::string, long long> numa_of;
+  for (const std::string& line : split_lines(devs)) {
+    size_t t = line.find('\t');
+    if (t != std::string::npos) numa_of[line.substr(0, t)] = atoll(line.c_str() + t + 1);
+  }
+  auto node = [&](const std::string& id) -> long long {
+    auto it = numa_of.find(id);
+    return it == numa_of.end() ? -1 : it->second;
+  };
+  const std::vector<std::string> avail = split_lines(available), must = split_lines(must_include);
+  std::map<long long, std::vector<std::string>> by_node;
+  std::vector<long long> node_order;
+  for (const std::string& id : avail) {
+    long long n = node(id);
+    if (!by_node.count(n)) node_order.push_back(n);
+    by_node[n].push_back(id);
+  }
+  std::vector<std::string> preferred;
+  std::set<std::string> chosen;
+  std::map<long long, int> selected;
+  auto add = [&](const std::string& id) {
+    if (!chosen.insert(id).second) return;
+    selected[node(id)]++;
+    preferred.push_back(id);
+  };
+  std::vector<long long> selected_order;
+  for (const std::string& id : must) {
+    if (chosen.count(id)) continue;
+    add(id);
+    long long n = node(id);
+    if (std::find(selected_order.begin(), selected_order.end(), n) == selected_order.end()) selected_order.push_back(n);
+  }
+  if ((long long)preferred.size() > allocation_size) {
+    char msg[128];
+    snprintf(msg, sizeof msg, "number of MustIncludeDeviceIDs (%zu) exceeds allocation size (%d)", preferred.size(),
+             allocation_size);
+    int rc = give(msg, out, outlen);
+    return rc ? rc : KVGH_EALLOC;
+  }
+  if ((long long)preferred.size() < allocation_size) {
+    std::vector<long long> cand = selected_order;
+    for (long long n : node_order)
+      if (std::find(selected_order.begin(), selected_order.end(), n) == selected_order.end()) cand.push_back(n);
+    long long target = -1;  // -1 doubles as "devices without topology": never a target (:552-575)
+    for (long long n : cand) {
+      int freecnt = 0;
+      for (const std::string& id : by_node[n]) freecnt += !chosen.count(id);
+      if (selected[n] + freecnt >= allocation_size) {
+        target = n;
+        break;
+      }
+    }
+    if (target != -1)
+      for (const std::string& id : by_node[target]) {
+        if ((long long)preferred.size() >= allocation_size) break;
+        add(id);
+      }
+  }
+  for (const std::string& id : avail) {
+    if ((long long)preferred.size() >= allocation_size) break;
+    add(id);
+  }
+  std::string joined;
+  for (const std::string& id : preferred) joined += id + "\n";
+  return give(joined, out, outlen);
+}
+
+// egmPathsForAllocatedGPUs (:159-184).  egm: "devpath\tbdf bdf ..." per line; allocated: one BDF per line.
+int kvgh_egm_paths_for_allocated(const char* allocated, const char* egm, char** out, size_t* outlen) {
+  if (!out) return KVG_EINVAL;
+  auto norm = [](std::string s) {
+    size_t a = 0, b = s.size();
+    while (a < b && isspace((unsigned char)s[a])) a++;
+    while (b > a && isspace((unsigned char)s[b - 1])) b--;
+    s = s.substr(a, b - a);
+    for (char& c : s) c = (char)tolower((unsigned char)c);
+    return s;
+  };
+  std::set<std::string> have;
+  for (const std::string& b : split_lines(allocated)) have.insert(norm(b));
+  std::vector<std::string> paths;
+  for (const std::string& line : split_lines(egm)) {
+    size_t t = line.find('\t');
+    if (t == std::string::npos) continue;
+    bool all = true;
+    std::string cur;
+    const std::string gpus = line.substr(t + 1) + " ";
+    for (char c : gpus) {
+      if (c == ' ') {
+        if (!cur.empty() && !have.count(norm(cur))) all = false;
+        cur.clear();
+      } else {
+        cur.push_back(c);
+      }
+    }
+    if (all) paths.push_back(line.substr(0, t));
+  }
+  std::sort(paths.begin(), paths.end());
+  std::string joined;
+  for (const std::string& p : paths) joined += p + "\n";
+  return give(joined, out, outlen);
+}
 
 }  // extern "C"
 

@@ -384,3 +384,78 @@ def test_start_twice_and_register_without_kubelet():
     finally:
         p.stop()
         shutil.rmtree(sockdir, ignore_errors=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# native twins in libkvghost.so (kvg_host.cpp): same vectors, plus a differential fuzz
+# ------------------------------------------------------------------------------------------------
+def _host_lib():
+    import ctypes as C
+    L = C.CDLL(os.path.join(conftest.PKG, "libkvghost.so"))
+    L.kvgh_preferred_allocation.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p),
+                                            C.POINTER(C.c_size_t)]
+    L.kvgh_egm_paths_for_allocated.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.kvgh_free.argtypes = [C.c_void_p]
+    return L
+
+
+def _native_text(L, fn, *args):
+    import ctypes as C
+    out, n = C.c_void_p(), C.c_size_t()
+    rc = fn(*args, C.byref(out), C.byref(n))
+    text = C.string_at(out, n.value).decode() if out.value else ""
+    L.kvgh_free(out)
+    return rc, text
+
+
+def native_preferred(L, devs, available, must, size):
+    blob = "".join("%s\t%d\n" % (i, n) if n is not None else "%s\n" % i for i, n in devs).encode()
+    rc, text = _native_text(L, L.kvgh_preferred_allocation, blob, "\n".join(available).encode(),
+                            "\n".join(must).encode(), size)
+    if rc == -101:
+        raise serve.AllocateError(text)
+    assert rc == 0
+    return text.split("\n")[:-1] if text else []
+
+
+def test_native_preferred_allocation_matches_vectors_and_python(V):
+    L = _host_lib()
+    p = V["preferred_allocation"]
+    devs = [(d["id"], d["numa"]) for d in p["devs"]]
+    for c in p["cases"]:
+        if "want_error" in c:
+            with pytest.raises(serve.AllocateError) as e:
+                native_preferred(L, devs, c["available"], c["must_include"], c["size"])
+            assert str(e.value) == c["want_error"]
+        else:
+            got = native_preferred(L, devs, c["available"], c["must_include"], c["size"])
+            assert got == serve.preferred_allocation(devs, c["available"], c["must_include"], c["size"])
+            assert got == c["want"] if "want" in c else sorted(got) == sorted(c["want_set"])
+    rng = np.random.default_rng(11)
+    pool = ["g%d" % i for i in range(12)]
+    for trial in range(400):
+        devs = [(i, (int(rng.integers(0, 3)) if rng.random() < 0.8 else None)) for i in pool[:int(rng.integers(1, 12))]]
+        ids = [d[0] for d in devs] + ["ghost"]
+        available = [str(x) for x in rng.permutation(ids)[:int(rng.integers(0, len(ids) + 1))]]
+        must = [str(x) for x in rng.choice(ids, size=int(rng.integers(0, 4)))]
+        size = int(rng.integers(0, 6))
+        try:
+            want = serve.preferred_allocation(devs, available, must, size)
+        except serve.AllocateError as e:
+            with pytest.raises(serve.AllocateError) as e2:
+                native_preferred(L, devs, available, must, size)
+            assert str(e2.value) == str(e)
+            continue
+        assert native_preferred(L, devs, available, must, size) == want, (devs, available, must, size)
+
+
+def test_native_egm_selection_matches_python():
+    L = _host_lib()
+    egm = [serve.EGMDeviceInfo("/dev/egm5", ["0000:0b:00.0", "0000:0c:00.0"]),
+           serve.EGMDeviceInfo("/dev/egm4", ["0000:09:00.0", "0000:0A:00.0"])]
+    blob = "".join("%s\t%s\n" % (e.dev_path, " ".join(e.gpu_bdfs)) for e in egm).encode()
+    for alloc in ([], ["0000:09:00.0"], ["0000:0a:00.0 ", " 0000:09:00.0"],
+                  ["0000:0c:00.0", "0000:0b:00.0", "0000:09:00.0", "0000:0A:00.0"]):
+        rc, text = _native_text(L, L.kvgh_egm_paths_for_allocated, "\n".join(alloc).encode(), blob)
+        assert rc == 0
+        assert (text.split("\n")[:-1] if text else []) == serve.egm_paths_for_allocated_gpus(alloc, egm)
