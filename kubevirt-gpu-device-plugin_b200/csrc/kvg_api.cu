@@ -26,6 +26,7 @@
 #include "../../include/kvgpu.h"
 #include "kvg_common.cuh"
 #include "kvg_parse.cuh"
+#include "kvg_parse_v2.cuh"
 #include "kvg_scan.cuh"
 
 using namespace kvg;
@@ -155,6 +156,7 @@ struct kvg_ctx {
   DevBuf<PciIdsInfo> info;
   DevBuf<uint32_t> tile_arrays;  // 3 x n_tiles
   DevBuf<uint64_t> parse_state;
+  DevBuf<uint32_t> v2_state, v2_pending;  // KVG_PARSE=v2 (experimental): span states + pending counts, pending lines
   DevBuf<uint32_t> parse_ticket;
   DevBuf<uint8_t> pool;
   DevBuf<uint32_t> nv_index;  // [65536] vendor-10de device id -> name pool slot
@@ -475,7 +477,7 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
   release(ctx->text); release(ctx->tables); release(ctx->info); release(ctx->tile_arrays);
-  release(ctx->parse_state); release(ctx->parse_ticket); release(ctx->pool); release(ctx->ctrl);
+  release(ctx->parse_state); release(ctx->v2_state); release(ctx->v2_pending); release(ctx->parse_ticket); release(ctx->pool); release(ctx->ctrl);
   release(ctx->nv_index); release(ctx->nv_lines); release(ctx->sec_lines); release(ctx->type_hash); release(ctx->ragged); release(ctx->tile_count); release(ctx->tile_off);
   release(ctx->tile_max); release(ctx->offs_state);
   release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist); release(ctx->bin_total);
@@ -567,12 +569,82 @@ static uint32_t table_log2_for(size_t len) {
   return l;
 }
 
+// KVG_PARSE=v2: the barrier-free parse of kvg_parse_v2.cuh (experimental, see its header)
+static bool parse_v2_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("KVG_PARSE");
+    return e && strcmp(e, "v2") == 0;
+  }();
+  return on;
+}
+
+static int parse_enqueue_v2(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t stride, uint32_t n_files,
+                            uint32_t cap_log2) {
+  const uint32_t spf = (uint32_t)((len + V2_SPAN - 1) / V2_SPAN);
+  const uint64_t n_spans64 = (uint64_t)spf * n_files;
+  if (n_spans64 > 0x7fffffffull) {
+    ctx->err = "too many spans";
+    return KVG_EINVAL;
+  }
+  const uint32_t n_spans = (uint32_t)n_spans64;
+  ctx->cap_log2 = cap_log2;
+  const size_t cap = (size_t)1 << cap_log2;
+  ENSURE(ctx->tables, cap * n_files);
+  ENSURE(ctx->info, n_files);
+  ENSURE(ctx->tile_arrays, 3 * (size_t)n_spans);
+  ENSURE(ctx->v2_state, 2 * (size_t)n_spans);
+  ENSURE(ctx->v2_pending, (size_t)n_spans * V2_PEND_CAP);
+  ParseV2Args A;
+  A.text = d_text;
+  A.stride = stride;
+  A.len = (uint32_t)len;
+  A.n_files = n_files;
+  A.spans_per_file = spf;
+  A.n_spans = n_spans;
+  A.tables = ctx->tables.p;
+  A.cap_mask = (uint32_t)cap - 1;
+  A.cap_shift = 32 - cap_log2;
+  A.info = ctx->info.p;
+  A.span_first_hdr = ctx->tile_arrays.p;
+  A.span_first_nl = ctx->tile_arrays.p + n_spans;
+  A.span_last_nl = ctx->tile_arrays.p + 2 * (size_t)n_spans;
+  A.span_state = ctx->v2_state.p;
+  A.pend_cnt = ctx->v2_state.p + n_spans;
+  A.pending = ctx->v2_pending.p;
+  CK(cudaMemsetAsync(ctx->tables.p, 0xff, cap * n_files * sizeof(uint64_t), ctx->stream));  // P_EMPTY
+  CK(cudaMemsetAsync(ctx->info.p, 0, sizeof(PciIdsInfo) * n_files, ctx->stream));
+  CK(cudaMemset2DAsync(ctx->info.p, sizeof(PciIdsInfo), 0xff, sizeof(uint32_t), n_files, ctx->stream));
+  const unsigned grid = (n_spans + V2_WARPS - 1) / V2_WARPS;
+  LAUNCH("pciids_parse", k_pciids_scan_v2, grid, V2_WARPS * 32, 0, A);
+  LAUNCH("pciids_resolve", k_pciids_resolve_v2, grid, V2_WARPS * 32, 0, A);
+  ParseArgs F;  // the finalize kernel reads the span summaries through the tile arrays
+  memset(&F, 0, sizeof F);
+  F.text = d_text;
+  F.stride = stride;
+  F.len = (uint32_t)len;
+  F.n_files = n_files;
+  F.tiles_per_file = spf;
+  F.n_tiles = n_spans;
+  F.info = ctx->info.p;
+  F.tile_first_hdr = A.span_first_hdr;
+  F.tile_first_nl = A.span_first_nl;
+  F.tile_last_nl = A.span_last_nl;
+  LAUNCH("pciids_finalize", k_pciids_finalize_v2, n_files, KVG_BLOCK, 0, F);
+  ENSURE(ctx->nv_index, 65536);
+  ENSURE(ctx->nv_lines, 65536 + 8);
+  CK(cudaMemsetAsync(ctx->nv_lines.p + 65536, 0, sizeof(uint32_t), ctx->stream));
+  LAUNCH("pciids_nv_index", k_nv_index, 256, 256, 0, ctx->tables.p, A.cap_mask, A.cap_shift, ctx->info.p,
+         ctx->nv_index.p, ctx->nv_lines.p, ctx->nv_lines.p + 65536);
+  return check_launch(ctx, "pciids parse (v2)");
+}
+
 static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t stride,
                          uint32_t n_files, uint32_t cap_log2) {
   if (len == 0 || len >= 0xfffffff0ull) {
     ctx->err = "pci.ids length out of range";
     return KVG_EINVAL;
   }
+  if (parse_v2_enabled()) return parse_enqueue_v2(ctx, d_text, len, stride, n_files, cap_log2);
   uint32_t tpf = (uint32_t)((len + P_TILE - 1) / P_TILE);
   uint64_t n_tiles64 = (uint64_t)tpf * n_files;
   if (n_tiles64 > 0x7fffffffull) {
