@@ -307,3 +307,68 @@ func createVgpuIDMapGPU() {
 	}
 	_ = sort.Strings // (kept: callers that want deterministic logs sort the keys)
 }
+
+// revalidateBatchGPU is the Allocate-time re-check of generic_device_plugin.go:387-399 for ALL devices
+// of a container request in one pass of the classification kernel (Python twin:
+// kvgpu/serve.py BatchRevalidator, pinned by tests/test_serve.py).  devs[i] is re-read with the
+// reference's own readers, in the reference's order; want[i] is the IOMMU group the maps hold for it.
+// It returns the index of the first device the reference would reject, or -1.
+//
+// The record's driver is pinned to vfio-pci and its device id to 0 because Allocate re-checks only the
+// group link and the vendor; K3's predicate is then exactly "vendor is 10de and both reads worked" and
+// the survivor's interned group id says whether the link still points at the expected group.
+//
+// Call site (generic_device_plugin.go:376-416): collect (dev.addr, iommuId) for every dev of every
+// requested BDF, call this once, and return the "unknown device" error for devs[first] if first >= 0.
+func revalidateBatchGPU(devs []string, want []string) (first int, err error) {
+	if len(devs) == 0 {
+		return -1, nil
+	}
+	if err := kvgEnsure(); err != nil {
+		return 0, err
+	}
+	intern := map[string]uint32{}
+	id := func(s string) uint32 {
+		if v, ok := intern[s]; ok {
+			return v
+		}
+		v := uint32(len(intern))
+		intern[s] = v
+		return v
+	}
+	recs := make([]C.kvg_pci_rec, len(devs))
+	for i, addr := range devs {
+		r := &recs[i]
+		r.addr = C.uint32_t(i)
+		r.vendor = 0xffff
+		r.driver = C.KVG_DRV_VFIO_PCI
+		r.iommu_group = C.uint32_t(id(want[i]))
+		group, err := readLink(basePath, addr, "iommu_group")
+		if err != nil {
+			r.flags |= C.KVG_PF_IOMMU_ERR
+		} else {
+			r.iommu_group = C.uint32_t(id(group))
+		}
+		vendorID, err := readIDFromFile(basePath, addr, "vendor")
+		if err != nil {
+			r.flags |= C.KVG_PF_VENDOR_ERR
+		} else if vendorID == nvidiaVendorID {
+			r.vendor = 0x10de
+		}
+	}
+	var res *C.kvg_pci_result
+	if rc := C.kvg_scan_pci(kvgCtx, &recs[0], C.size_t(len(recs)), &res); rc != C.KVG_OK {
+		return 0, fmt.Errorf("kvg_scan_pci: %s", C.GoString(C.kvg_last_error(kvgCtx)))
+	}
+	defer C.kvg_result_free(unsafe.Pointer(res))
+	ok := make(map[uint32]uint32, int(res.n_survivors))
+	for _, s := range unsafe.Slice(res.survivors, int(res.n_survivors)) {
+		ok[uint32(s.addr)] = uint32(s.iommu_group)
+	}
+	for i := range devs {
+		if g, alive := ok[uint32(i)]; !alive || g != intern[want[i]] {
+			return i, nil
+		}
+	}
+	return -1, nil
+}
