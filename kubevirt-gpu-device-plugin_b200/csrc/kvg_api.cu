@@ -188,6 +188,7 @@ struct kvg_ctx {
   DevBuf<uint64_t> classify_state;
   OrderBufs ord_dev, ord_grp;
   DevBuf<uint32_t> tile_hist, bin_total;
+  bool scatter_smem_set = false;  // dynamic shared-memory opt-in of k_radix_scatter<11> done on this device
   size_t last_n = 0;     // records of the last enqueued scan
   size_t last_total = 0; // survivors capacity used by the last scan (sharded: all ranks)
   int last_kind = 0;     // 1 = pci, 2 = mdev
@@ -1077,11 +1078,10 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1, bool 
     a.src = (p == 0 && !owned_only) ? srcs[ord] : SRC_PAIRS;
     return a;
   };
-  static bool scatter_smem_set = false;
-  if (!scatter_smem_set) {
+  if (!ctx->scatter_smem_set) {  // a function attribute is per device: remember it per context
     CK(cudaFuncSetAttribute(k_radix_scatter<RADIX_MAX_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)RadixScatterCfg<RADIX_MAX_BITS>::SMEM));
-    scatter_smem_set = true;
+    ctx->scatter_smem_set = true;
   }
   for (int p = 0; p < nsets[1]; p++) {
     RadixArgs2 aa;
