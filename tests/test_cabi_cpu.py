@@ -231,3 +231,29 @@ def test_radix_plan_covers_every_key_width():
     assert lib.kvg_debug_radix_plan(0xffffffff, 16, 11, C.byref(np_), sh, bt) == 0
     assert np_.value == 2 and list(bt) == [8, 8, 0, 0]
     assert lib.kvg_debug_radix_plan(0, 32, 11, C.byref(np_), sh, bt) == 0 and np_.value == 1
+
+
+def test_header_is_plain_c99_and_links(tmp_path):
+    """include/kvgpu.h is the contract a cgo / C caller compiles against: it must be valid C99 (no C++
+    types, no torch types) and a C program that takes the address of EVERY declared entry point must
+    link against libkvgpu.so.  Without a GPU the program's kvg_ctx_create fails loudly (exit code 3)."""
+    import subprocess
+    import kvgpu
+    syms = sorted(kvgpu.declared_symbols())
+    src = tmp_path / "all_symbols.c"
+    src.write_text('#include "kvgpu.h"\n#include <stdio.h>\n'
+                   "typedef void (*any_fn)(void);\n"
+                   "static const any_fn table[] = {%s};\n" % ", ".join("(any_fn)%s" % s for s in syms) +
+                   "int main(void) {\n  kvg_ctx *c = 0;\n  if (sizeof table / sizeof *table != %d) return 2;\n" % len(syms) +
+                   "  if (sizeof(kvg_pci_rec) != 16 || sizeof(kvg_mdev_rec) != 32 || sizeof(kvg_pci_surv) != 16) return 4;\n"
+                   "  if (kvg_ctx_create(0, &c) != KVG_OK) { puts(kvg_last_error(0)); return 3; }\n"
+                   "  kvg_ctx_destroy(c);\n  return 0;\n}\n")
+    exe = tmp_path / "all_symbols"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic",
+                        "-I", os.path.join(conftest.ROOT, "include"), str(src), "-L", conftest.PKG, "-lkvgpu",
+                        "-Wl,-rpath," + conftest.PKG, "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == (0 if conftest.HAS_GPU else 3), (r.returncode, r.stdout)
+    if not conftest.HAS_GPU:
+        assert "CUDA" in r.stdout or "device" in r.stdout
