@@ -644,3 +644,94 @@ class MockKubelet:
             os.remove(self.socket_path)
         except FileNotFoundError:
             pass
+
+
+# ------------------------------------------------------------------------------------------------
+# healthCheck(): the reference's own health source (generic_device_plugin.go:611-690) — inotify on the
+# device nodes and on the plugin socket.  (HealthRescanFeed above is the GPU-side alternative.)
+# ------------------------------------------------------------------------------------------------
+class DeviceNodeWatcher:
+    """Watches <device_path>/<iommu group> for every advertised device and the plugin's own socket:
+
+      node created            -> healthy(id)   for every device of that group   (:659-662)
+      node removed / renamed  -> unhealthy(id)                                   (:663-668)
+      plugin socket removed   -> kubelet restarted: restart() = Stop + Start + Register, then the
+                                 watcher ends, like the goroutine does            (:669-679)
+
+    fsnotify watches the PARENT directories; so does this (inotify through libc, no extra package)."""
+    IN_CREATE, IN_DELETE, IN_MOVED_FROM, IN_DELETE_SELF, IN_MOVE_SELF = 0x100, 0x200, 0x40, 0x400, 0x800
+
+    def __init__(self, plugin: GenericDevicePlugin, bdf_to_iommu=None):
+        import ctypes
+        self.plugin = plugin
+        self._libc = ctypes.CDLL("libc.so.6", use_errno=True)
+        self._fd = self._libc.inotify_init1(0o4000)          # IN_NONBLOCK
+        if self._fd < 0:
+            raise OSError(ctypes.get_errno(), "inotify_init1")
+        bdf_to_iommu = bdf_to_iommu if bdf_to_iommu is not None else plugin.maps.bdfToIommuMap
+        self.path_devices = {}                               # node path -> [device ids]
+        for dev in plugin.devs:
+            group = bdf_to_iommu.get(dev.ID)
+            if group is None:                                # :634-637 logged and skipped
+                continue
+            self.path_devices.setdefault(os.path.join(plugin.device_path, group), []).append(dev.ID)
+        self._wd_dir = {}
+        dirs = {os.path.dirname(p) for p in self.path_devices} | {os.path.dirname(plugin.socket_path)}
+        mask = self.IN_CREATE | self.IN_DELETE | self.IN_MOVED_FROM
+        for d in sorted(dirs):
+            wd = self._libc.inotify_add_watch(self._fd, d.encode(), mask)
+            if wd < 0:
+                err = ctypes.get_errno()
+                os.close(self._fd)
+                raise OSError(err, "inotify_add_watch(%s)" % d)
+            self._wd_dir[wd] = d
+        self._stop = threading.Event()
+        self._thread = None
+        self.restarted = threading.Event()
+
+    def poll_once(self) -> int:
+        """Drain pending inotify events; returns how many health / restart actions were taken."""
+        import struct
+        try:
+            buf = os.read(self._fd, 65536)
+        except BlockingIOError:
+            return 0
+        acted, off = 0, 0
+        while off + 16 <= len(buf):
+            wd, mask, _cookie, ln = struct.unpack_from("iIII", buf, off)
+            name = buf[off + 16:off + 16 + ln].split(b"\0", 1)[0].decode()
+            off += 16 + ln
+            path = os.path.join(self._wd_dir.get(wd, ""), name)
+            ids = self.path_devices.get(path)
+            if ids is not None:
+                if mask & self.IN_CREATE:
+                    for i in ids:
+                        self.plugin.healthy(i)
+                    acted += len(ids)
+                elif mask & (self.IN_DELETE | self.IN_MOVED_FROM):
+                    for i in ids:
+                        self.plugin.unhealthy(i)
+                    acted += len(ids)
+            elif path == self.plugin.socket_path and mask & self.IN_DELETE:
+                self.plugin.restart()
+                self.restarted.set()
+                self._stop.set()
+                acted += 1
+        return acted
+
+    def start(self, period_s: float = 0.01):
+        def loop():
+            while not self._stop.is_set():
+                self.poll_once()
+                time.sleep(period_s)
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(2.0)
+        try:
+            os.close(self._fd)
+        except OSError:
+            pass

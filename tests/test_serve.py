@@ -459,3 +459,49 @@ def test_native_egm_selection_matches_python():
         rc, text = _native_text(L, L.kvgh_egm_paths_for_allocated, "\n".join(alloc).encode(), blob)
         assert rc == 0
         assert (text.split("\n")[:-1] if text else []) == serve.egm_paths_for_allocated_gpus(alloc, egm)
+
+
+def test_device_node_watcher_like_the_reference_health_check(V):
+    """generic_device_plugin.go:611-690 / generic_device_plugin_test.go:333-345: removing a device node
+    marks its devices unhealthy, re-creating it marks them healthy; removing the plugin socket (kubelet
+    restart) makes the plugin re-register."""
+    a = V["allocate"]
+    sockdir = tempfile.mkdtemp(prefix="kvg", dir="/tmp")
+    devdir = os.path.join(sockdir, "vfio")
+    os.makedirs(devdir)
+    for g in ("1", "2"):
+        open(os.path.join(devdir, g), "w").close()
+    kubelet = serve.MockKubelet(sockdir).start()
+    maps = maps_from_vectors(a)
+    p = serve.GenericDevicePlugin("foo", devdir, [dpapi.Device(ID=i, health=dpapi.HEALTHY) for i in a["plugin_devs"]],
+                                  maps, socket_dir=sockdir)
+    w = None
+    try:
+        p.start()
+        assert len(kubelet.wait_for(1)) == 1
+        w = serve.DeviceNodeWatcher(p)
+        assert w.path_devices == {os.path.join(devdir, "1"): ["11"], os.path.join(devdir, "2"): ["22"]}
+        stream = p.ListAndWatch(dpapi.Empty(), None)
+        next(stream)
+        os.remove(os.path.join(devdir, "2"))
+        assert w.poll_once() == 1
+        assert [(d.ID, d.health) for d in next(stream).devices] == [("11", "Healthy"), ("22", "Unhealthy")]
+        open(os.path.join(devdir, "2"), "w").close()
+        assert w.poll_once() == 1
+        assert [d.health for d in next(stream).devices] == ["Healthy", "Healthy"]
+        os.rename(os.path.join(devdir, "1"), os.path.join(devdir, "1.gone"))     # fsnotify.Rename
+        assert w.poll_once() == 1
+        assert [d.health for d in next(stream).devices] == ["Unhealthy", "Healthy"]
+        open(os.path.join(devdir, "unrelated"), "w").close()
+        assert w.poll_once() == 0
+        # kubelet restart: the device-plugin directory is wiped, our socket disappears
+        os.remove(p.socket_path)
+        assert w.poll_once() == 1 and w.restarted.is_set()
+        regs = kubelet.wait_for(2)
+        assert [r.endpoint for r in regs] == ["kubevirt-foo.sock"] * 2 and os.path.exists(p.socket_path)
+    finally:
+        if w:
+            w.stop()
+        p.stop()
+        kubelet.stop()
+        shutil.rmtree(sockdir, ignore_errors=True)
