@@ -418,7 +418,7 @@ static int classify_ws_grid(kvg_ctx* ctx, size_t n_items, size_t* smem_out) {
   return g < 1 ? 1 : (int)g;
 }
 constexpr int PCI_ROWS = 4, PCI_STAGES = 4;    // 16 KiB stages, 64 KiB ring -> 3 CTAs / SM
-constexpr int MDEV_ROWS = 2, MDEV_STAGES = 4;  // 16 KiB stages
+constexpr int MDEV_ROWS = 2;
 static int classify_variant() {  // KVG_CLASSIFY=tma selects the non-specialised kernel (A/B tests)
   static int v = -1;
   if (v < 0) {
@@ -1271,7 +1271,7 @@ static int fetch_pci(kvg_ctx* ctx, kvg_pci_result** res, void* blk, size_t surv_
   const size_t SD = ctx->last_owned ? ctx->h_ctrl->n_own[0] : S;
   const size_t SG = ctx->last_owned ? ctx->h_ctrl->n_own[1] : S;
   const size_t pool_len = ctx->h_pool.size();
-  size_t o_hdr = 0, o = align64(sizeof(kvg_pci_result));
+  size_t o = align64(sizeof(kvg_pci_result));  // header first
   size_t o_surv = o; o += align64(surv_reserve * 16);
   size_t o_dkeys32 = o; o += align64(KD * 4);
   size_t o_dkeys = o; o += align64(KD * 2);
@@ -1288,7 +1288,6 @@ static int fetch_pci(kvg_ctx* ctx, kvg_pci_result** res, void* blk, size_t surv_
     return KVG_ENOMEM;
   }
   uint8_t* b = pinned_payload(blk);
-  (void)o_hdr;
   auto D2H = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
     if (!bytes) return cudaSuccess;
     return cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
