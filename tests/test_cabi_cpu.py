@@ -257,3 +257,17 @@ def test_header_is_plain_c99_and_links(tmp_path):
     assert r.returncode == (0 if conftest.HAS_GPU else 3), (r.returncode, r.stdout)
     if not conftest.HAS_GPU:
         assert "CUDA" in r.stdout or "device" in r.stdout
+
+
+def test_module_entry_point_fails_loudly_without_gpu():
+    """python -m kvgpu is InitiateDevicePlugin(): with no CUDA device it must refuse (exit 2, message),
+    never fall back to a CPU scan."""
+    import subprocess
+    import sys
+    env = dict(os.environ, PYTHONPATH=conftest.PKG)
+    r = subprocess.run([sys.executable, "-m", "kvgpu", "--help"], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "--once" in r.stdout and "InitiateDevicePlugin" in r.stdout
+    if conftest.HAS_GPU:
+        return
+    r = subprocess.run([sys.executable, "-m", "kvgpu", "--once", "--dump"], capture_output=True, text=True, env=env)
+    assert r.returncode == 2 and "no CPU fallback" in r.stderr and r.stdout == ""
