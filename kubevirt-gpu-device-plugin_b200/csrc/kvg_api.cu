@@ -28,6 +28,7 @@
 #include "kvg_parse.cuh"
 #include "kvg_parse_v2.cuh"
 #include "kvg_scan.cuh"
+#include "kvg_radix_exp.cuh"
 
 using namespace kvg;
 
@@ -1099,7 +1100,16 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1, bool 
     }
     dim3 sgrid(KVG_BLOCK, grid.y);
     LAUNCH("radix_hist", k_radix_hist, grid, KVG_BLOCK, 0, aa);
-    LAUNCH("radix_tilescan", k_radix_tilescan, sgrid, KVG_BLOCK, 0, aa);
+    static const bool tilescan_warp = [] {  // KVG_TILESCAN=warp: experimental, see kvg_radix_exp.cuh
+      const char* e = getenv("KVG_TILESCAN");
+      return e && strcmp(e, "warp") == 0;
+    }();
+    if (tilescan_warp) {
+      dim3 wgrid(RADIX_MAX_DIGITS / TS_WARPS, grid.y);
+      LAUNCH("radix_tilescan", k_radix_tilescan_warp, wgrid, TS_WARPS * 32, 0, aa);
+    } else {
+      LAUNCH("radix_tilescan", k_radix_tilescan, sgrid, KVG_BLOCK, 0, aa);
+    }
     if (max_bits == 8)
       LAUNCH("radix_scatter", k_radix_scatter<8>, grid, KVG_BLOCK, RadixScatterCfg<8>::SMEM, aa);
     else

@@ -1,0 +1,61 @@
+// radix_emu.cpp — the radix family of csrc/kvg_scan.cuh (k_radix_hist, k_radix_tilescan,
+// k_radix_scatter<8|11>) and the experimental k_radix_tilescan_warp of csrc/kvg_radix_exp.cuh, compiled
+// for the CPU from their real source on top of warp_emu.h.  The pass loop below is the one of
+// enqueue_orderings (kvg_api.cu): passes 0..nsets-1, ping-pong between two pair buffers.
+#define KVG_HOST_EMU 1
+#include "warp_emu.h"
+#include "kvgpu.h"
+namespace kvg {
+#include "emu_radix.inc"
+}
+#include "../../kubevirt-gpu-device-plugin_b200/csrc/kvg_radix_exp.cuh"
+
+using namespace kvg;
+
+extern "C" {
+
+// Stable sort of {key, index} pairs the way the device does it.  pairs_io: n x {key, index}; on return
+// the sorted pairs.  variant: 0 = k_radix_tilescan, 1 = k_radix_tilescan_warp.  Returns the pass count
+// the device-side plan chose, or a negative number.
+int emu_radix_sort(uint2* pairs_io, uint32_t n, uint32_t key_bits_max, uint32_t max_bits, int variant) {
+  if (max_bits != 8 && max_bits != RADIX_MAX_BITS) return -1;
+  uint32_t max_key = 0;
+  for (uint32_t i = 0; i < n; i++) max_key = pairs_io[i].x > max_key ? pairs_io[i].x : max_key;
+  const size_t T = n ? (n + C_TILE - 1) / C_TILE : 1;
+  std::vector<uint2> p0(n + 1), p1(n + 1);
+  memcpy(p1.data(), pairs_io, sizeof(uint2) * n);   // pass 0 reads p1 (SRC_PAIRS), like the owned-pairs path
+  std::vector<uint32_t> tile_hist(RADIX_MAX_DIGITS * T, 0xdeadbeefu), bin_total(RADIX_MAX_DIGITS, 0xdeadbeefu);
+  const int nsets = (int)((key_bits_max + max_bits - 1) / max_bits);
+  for (int p = 0; p < nsets; p++) {
+    RadixArgs a;
+    a.n_ptr = &n;
+    a.max_key = &max_key;
+    a.src_records = nullptr;
+    a.pairs_in = (p & 1) ? p0.data() : p1.data();
+    a.pairs_out = (p & 1) ? p1.data() : p0.data();
+    a.tile_hist = tile_hist.data();
+    a.bin_total = bin_total.data();
+    a.pass = (uint32_t)p;
+    a.key_bits_max = key_bits_max;
+    a.max_bits = max_bits;
+    a.src = SRC_PAIRS;
+    RadixArgs2 aa;
+    aa.o[0] = a;
+    aa.o[1] = a;
+    emu_launch(k_radix_hist, dim3((unsigned)T, 1), KVG_BLOCK, aa);
+    if (variant == 1)
+      emu_launch(k_radix_tilescan_warp, dim3(RADIX_MAX_DIGITS / TS_WARPS, 1), TS_WARPS * 32, aa);
+    else
+      emu_launch(k_radix_tilescan, dim3(KVG_BLOCK, 1), KVG_BLOCK, aa);
+    if (max_bits == 8)
+      emu_launch(k_radix_scatter<8>, dim3((unsigned)T, 1), KVG_BLOCK, aa);
+    else
+      emu_launch(k_radix_scatter<RADIX_MAX_BITS>, dim3((unsigned)T, 1), KVG_BLOCK, aa);
+  }
+  const uint32_t np = radix_plan(max_key, key_bits_max, 0, max_bits).npass;
+  const std::vector<uint2>& fin = ((np - 1) & 1) ? p1 : p0;   // order_final_buf
+  memcpy(pairs_io, fin.data(), sizeof(uint2) * n);
+  return (int)np;
+}
+
+}  // extern "C"

@@ -1,42 +1,65 @@
-// warp_emu.h — run CUDA kernel SOURCE on the CPU, one OS thread per CUDA thread, blocks one after
-// another.  Just enough of the CUDA surface for kernels that are written in the warp-synchronous
-// style of csrc/kvg_parse_v2.cuh: full-mask warp collectives, __syncwarp, __syncthreads, global and
-// shared atomics, static __shared__ arrays.  Collectives are real rendezvous (std::barrier), so a lane
-// that skips one, or lanes that disagree about how many they execute, deadlock here exactly like a
-// mis-synchronised kernel misbehaves on the GPU (the harness aborts after a timeout).
+// warp_emu.h — run CUDA kernel SOURCE on the CPU: one FIBER (ucontext) per CUDA thread, the fibers of a
+// block scheduled round-robin on the calling OS thread, blocks one after another.  Just enough of the
+// CUDA surface for kernels written in the warp-synchronous style of this repo: full-mask warp
+// collectives, __syncwarp, __syncthreads, global and shared atomics, static __shared__ arrays.
+// Collectives are real rendezvous: a lane that skips one, or lanes that disagree about how many they
+// execute, leave the block with runnable-but-blocked fibers only, which the scheduler reports as a
+// deadlock (abort) — the CPU-side picture of a mis-synchronised kernel.
 //
 // Test infrastructure only (tests/test_parse_v2_emu.py); never part of the product.
 #pragma once
-#include <barrier>
+#include <ucontext.h>
+
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <memory>
-#include <thread>
 #include <vector>
 
 struct uint4 {
   uint32_t x, y, z, w;
 };
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+struct uint2 {
+  uint32_t x, y;
+};
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
 struct EmuDim3 {
   unsigned x = 1, y = 1, z = 1;
 };
-static thread_local EmuDim3 threadIdx, blockIdx, blockDim, gridDim;
+static EmuDim3 threadIdx, blockIdx, blockDim, gridDim;  // restored by the scheduler on every resume
 
+struct EmuFiber {
+  ucontext_t ctx;
+  std::unique_ptr<char[]> stack;
+  bool done = false;
+};
 struct EmuBlock {
-  unsigned n_threads;
-  std::barrier<> block_bar;
-  std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
+  unsigned n_threads, n_warps;
+  unsigned block_expected, block_arrived = 0, block_gen = 0;
+  std::vector<unsigned> warp_expected, warp_arrived, warp_gen;
   std::vector<uint64_t> xchg;  // [warp][lane]
-  explicit EmuBlock(unsigned n) : n_threads(n), block_bar(n), xchg(n) {
-    for (unsigned w = 0; w < (n + 31) / 32; w++) {
-      unsigned lanes = (w + 1) * 32 <= n ? 32 : n - w * 32;
-      warp_bar.emplace_back(new std::barrier<>(lanes));
-    }
+  std::vector<EmuFiber> fibers;
+  ucontext_t sched;
+  unsigned current = 0;
+  bool progressed = false;
+  explicit EmuBlock(unsigned n)
+      : n_threads(n), n_warps((n + 31) / 32), block_expected(n), warp_expected(n_warps), warp_arrived(n_warps, 0),
+        warp_gen(n_warps, 0), xchg(n_warps * 32), fibers(n) {
+    for (unsigned w = 0; w < n_warps; w++) warp_expected[w] = (w + 1) * 32 <= n ? 32 : n - w * 32;
   }
 };
-static thread_local EmuBlock* emu_block = nullptr;
+static EmuBlock* emu_block = nullptr;
+static inline void emu_yield() {
+  EmuBlock* b = emu_block;
+  swapcontext(&b->fibers[b->current].ctx, &b->sched);
+}
 
 #define __global__
 #define __device__ static inline
@@ -48,6 +71,7 @@ static thread_local EmuBlock* emu_block = nullptr;
 #define __restrict__ __restrict
 #define KVG_FULL 0xffffffffu
 constexpr uint32_t KVG_BLOCK = 256;
+constexpr uint32_t KVG_WARPS = KVG_BLOCK / 32;
 
 static inline uint32_t lane_id() { return threadIdx.x & 31u; }
 static inline uint32_t warp_id() { return threadIdx.x >> 5; }
@@ -61,8 +85,28 @@ static inline int __clz(uint32_t v) { return v ? __builtin_clz(v) : 32; }
 static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
-static inline void __syncthreads() { emu_block->block_bar.arrive_and_wait(); }
-static inline void __syncwarp() { emu_block->warp_bar[warp_id()]->arrive_and_wait(); }
+static inline void __syncthreads() {
+  EmuBlock* b = emu_block;
+  const unsigned gen = b->block_gen;
+  b->progressed = true;
+  if (++b->block_arrived == b->block_expected) {
+    b->block_arrived = 0;
+    b->block_gen++;
+    return;
+  }
+  while (b->block_gen == gen) emu_yield();
+}
+static inline void __syncwarp() {
+  EmuBlock* b = emu_block;
+  const unsigned w = threadIdx.x >> 5, gen = b->warp_gen[w];
+  b->progressed = true;
+  if (++b->warp_arrived[w] == b->warp_expected[w]) {
+    b->warp_arrived[w] = 0;
+    b->warp_gen[w]++;
+    return;
+  }
+  while (b->warp_gen[w] == gen) emu_yield();
+}
 // every lane publishes, everybody reads, everybody leaves: two rendezvous per collective
 static inline uint64_t emu_exchange(uint64_t mine, uint32_t src_lane) {
   uint64_t* slot = &emu_block->xchg[warp_id() * 32];
@@ -88,6 +132,16 @@ static inline uint32_t __ballot_sync(uint32_t, bool p) {
   return m;
 }
 static inline bool __any_sync(uint32_t mask, bool p) { return __ballot_sync(mask, p) != 0; }
+static inline uint32_t __match_any_sync(uint32_t, uint32_t v) {
+  uint64_t* slot = &emu_block->xchg[warp_id() * 32];
+  slot[lane_id()] = v;
+  __syncwarp();
+  uint32_t m = 0;
+  for (uint32_t l = 0; l < 32; l++) m |= (uint32_t)(slot[l] == v) << l;
+  __syncwarp();
+  return m;
+}
+static inline uint32_t lanemask_lt() { return (1u << lane_id()) - 1u; }
 
 // the reductions of kvg_common.cuh, on top of the emulated shuffles
 static inline uint32_t warp_sum(uint32_t v) {
@@ -129,25 +183,65 @@ static inline unsigned long long atomicMin(unsigned long long* p, unsigned long 
   return old;
 }
 
-// kernel<<<grid, block>>>(args): blocks run one after another, threads of a block concurrently
-template <class Args>
-static void emu_launch(void (*kernel)(Args), unsigned grid, unsigned block, Args args) {
-  for (unsigned b = 0; b < grid; b++) {
-    EmuBlock blk(block);
-    std::vector<std::thread> ts;
-    ts.reserve(block);
-    for (unsigned t = 0; t < block; t++)
-      ts.emplace_back([&, t] {
-        emu_block = &blk;
-        threadIdx.x = t;
-        blockIdx.x = b;
-        blockDim.x = block;
-        gridDim.x = grid;
-        kernel(args);
-        // a thread that left early must not strand its warp / block at a later rendezvous
-        blk.warp_bar[t >> 5]->arrive_and_drop();
-        blk.block_bar.arrive_and_drop();
-      });
-    for (auto& th : ts) th.join();
+// kernel<<<grid, block>>>(args)
+static std::function<void()> emu_entry;
+static void emu_trampoline() {
+  EmuBlock* b = emu_block;
+  const unsigned t = b->current;
+  emu_entry();
+  // the thread leaves the kernel: later rendezvous of its warp / block no longer wait for it
+  b = emu_block;
+  b->fibers[t].done = true;
+  b->progressed = true;
+  const unsigned w = t >> 5;
+  if (--b->warp_expected[w] > 0 && b->warp_arrived[w] == b->warp_expected[w]) {
+    b->warp_arrived[w] = 0;
+    b->warp_gen[w]++;
   }
+  if (--b->block_expected > 0 && b->block_arrived == b->block_expected) {
+    b->block_arrived = 0;
+    b->block_gen++;
+  }
+  swapcontext(&b->fibers[t].ctx, &b->sched);
+}
+template <class Args>
+static void emu_launch(void (*kernel)(Args), dim3 grid2, unsigned block, Args args) {
+  constexpr size_t STACK = 256 << 10;
+  emu_entry = [=] { kernel(args); };
+  for (unsigned by = 0; by < grid2.y; by++)
+    for (unsigned bx = 0; bx < grid2.x; bx++) {
+      EmuBlock blk(block);
+      emu_block = &blk;
+      for (unsigned t = 0; t < block; t++) {
+        EmuFiber& f = blk.fibers[t];
+        f.stack.reset(new char[STACK]);
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack.get();
+        f.ctx.uc_stack.ss_size = STACK;
+        f.ctx.uc_link = &blk.sched;
+        makecontext(&f.ctx, emu_trampoline, 0);
+      }
+      for (unsigned live = block; live;) {
+        blk.progressed = false;
+        live = 0;
+        for (unsigned t = 0; t < block; t++) {
+          if (blk.fibers[t].done) continue;
+          blk.current = t;
+          threadIdx.x = t;
+          blockIdx.x = bx;
+          blockIdx.y = by;
+          blockDim.x = block;
+          gridDim.x = grid2.x;
+          gridDim.y = grid2.y;
+          swapcontext(&blk.sched, &blk.fibers[t].ctx);
+          live += !blk.fibers[t].done;
+        }
+        if (live && !blk.progressed) {
+          fprintf(stderr, "warp_emu: deadlock in block (%u,%u): %u threads blocked at a rendezvous that cannot complete\n",
+                  bx, by, live);
+          abort();
+        }
+      }
+    }
+  emu_block = nullptr;
 }
