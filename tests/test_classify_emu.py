@@ -1,0 +1,58 @@
+"""K3, the record-classification pipeline (k_classify_ragged -> k_tile_offsets -> k_pack_survivors, and
+the one-launch k_classify_oneshot), executed on the CPU from its real kernel source under the warp
+emulator of tools/emu/: drop rules of device_plugin.go:203-238, NUMA clamp, name join through nv_index,
+Walk-order compaction across tiles, the device-side maxima that size the radix plan."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import conftest  # noqa: F401
+import kvgpu
+import util
+from oracle import oracle as O
+
+sys.path.insert(0, os.path.join(conftest.ROOT, "tools", "emu"))
+import build as emu_build  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emu():
+    L = C.CDLL(emu_build.build_classify())
+    L.emu_classify_pci.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    return L
+
+
+def expected_survivors(recs, nv_index):
+    drop = 1 | 2 | 4 | 8
+    keep = (recs["vendor"] == 0x10de) & ((recs["flags"] & drop) == 0) & ((recs["driver"] == 1) | (recs["driver"] == 2))
+    r = recs[keep]
+    s = np.zeros(len(r), dtype=kvgpu.PCI_SURV)
+    s["addr"], s["iommu_group"], s["device"] = r["addr"], r["iommu_group"], r["device"]
+    numa = r["numa"].astype(np.int32)
+    numa[(numa < 0) | ((r["flags"] & 16) != 0)] = 0          # :227-230, :316-318
+    s["numa"] = numa.astype(np.uint16)
+    s["name_slot"] = nv_index[r["device"]]
+    return s
+
+
+@pytest.mark.parametrize("variant", [0, 1], ids=["ragged_offsets_pack", "oneshot"])
+def test_classify_pipeline_matches_the_drop_rules(emu, variant):
+    ids = O.nv_ids(util.pciids_text())
+    rng = np.random.default_rng(3)
+    nv_index = rng.integers(0, 1 << 20, 65536, dtype=np.uint64).astype(np.uint32)
+    for n, gbits in ((0, 0), (1, 0), (1023, 8), (1024, 8), (1025, 8), (3000, 0), (5000, 12)):
+        recs = O.gen_pci(11, n, ids, gbits)
+        if n >= 1024:
+            recs[1023] = (0xabc, 0x10de, int(ids[3]), 0x7fffffff, 2, 0, -1)     # tile edge, widest group, numa -1
+        out = np.zeros(n + 1, dtype=kvgpu.PCI_SURV)
+        ctrl = np.zeros(3, dtype=np.uint32)
+        buf = np.ascontiguousarray(recs) if n else np.zeros(1, dtype=kvgpu.PCI_REC)
+        assert emu.emu_classify_pci(buf.ctypes.data, n, nv_index.ctypes.data, variant, out.ctypes.data, ctrl.ctypes.data) == 0
+        want = expected_survivors(recs, nv_index)
+        assert int(ctrl[0]) == len(want), (n, variant)
+        assert np.array_equal(out[:len(want)], want), (n, variant)
+        if len(want):
+            assert int(ctrl[1]) == int(want["iommu_group"].max()) and int(ctrl[2]) == int(want["device"].max())

@@ -1,0 +1,60 @@
+// classify_emu.cpp — the record-classification pipeline of csrc/kvg_scan.cuh compiled for the CPU from
+// its real source on top of warp_emu.h: the split form the large inputs and the pipelined host entry
+// point use (k_classify_ragged -> k_tile_offsets -> k_pack_survivors) and the one-launch look-back form
+// used below 2 M records (k_classify_oneshot).  Launch shapes are those of enqueue_classify (kvg_api.cu).
+#define KVG_HOST_EMU 1
+#include "warp_emu.h"
+#include "kvgpu.h"
+namespace kvg {
+#include "emu_classify.inc"
+}
+using namespace kvg;
+
+extern "C" {
+
+// recs: n x 16 B records; nv_index: 65536 name slots; surv_out: room for n survivors.
+// variant 0 = ragged / offsets / pack, 1 = oneshot.  ctrl_out: {n_surv, max_group, max_devkey}.
+int emu_classify_pci(const uint4* recs, uint32_t n, const uint32_t* nv_index, int variant, uint4* surv_out,
+                     uint32_t* ctrl_out) {
+  constexpr int T = 128, R = 8;
+  const size_t tiles = (n + (size_t)T * R - 1) / ((size_t)T * R);
+  ScanCtrl ctrl;
+  memset(&ctrl, 0, sizeof ctrl);
+  std::vector<uint4> ragged((tiles + 1) * T * R, uint4{0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu});
+  std::vector<uint32_t> tile_count(tiles + 2, 0xdeadbeefu), tile_off(tiles + 3, 0xdeadbeefu);
+  std::vector<uint2> tile_max(tiles + 2);
+  std::vector<uint64_t> state(tiles + 4, 0);
+  PciIdsInfo info;
+  memset(&info, 0, sizeof info);
+  PciClassifyOp op;
+  op.recs = recs;
+  op.n = n;
+  op.ctrl = &ctrl;
+  op.table = nullptr;
+  op.cap_mask = 0;
+  op.cap_shift = 0;
+  op.info = &info;
+  op.nv_index = nv_index;
+  op.local_max_group = 0;
+  op.local_max_dev = 0;
+  const uint32_t epoch = 7;
+  if (variant == 1) {
+    op.out = (kvg_pci_surv*)surv_out;
+    emu_launch(k_classify_oneshot<PciClassifyOp, T, R>, dim3((unsigned)(tiles ? tiles : 1)), T, op, state.data(), epoch);
+  } else if (tiles) {
+    op.out = (kvg_pci_surv*)ragged.data();
+    emu_launch(k_classify_ragged<PciClassifyOp, T, R>, dim3((unsigned)tiles), T, op, tile_count.data(), tile_max.data());
+    TileOffsetsArgs2 tt;
+    tt.o[0] = {tile_count.data(), tile_max.data(), nullptr, (uint32_t)tiles, tile_off.data(), &ctrl.n_surv, state.data()};
+    tt.o[1] = tt.o[0];
+    emu_launch(k_tile_offsets, dim3((unsigned)((tiles + C_TILE - 1) / C_TILE)), KVG_BLOCK, tt, &ctrl, epoch);
+    emu_launch(k_pack_survivors<1>, dim3((unsigned)tiles), 128, (const uint4*)ragged.data(), (const uint32_t*)tile_off.data(),
+               (uint32_t)(T * R), surv_out);
+  }
+  ctrl_out[0] = ctrl.n_surv;
+  ctrl_out[1] = ctrl.max_group;
+  ctrl_out[2] = ctrl.max_devkey;
+  return 0;
+}
+
+}  // extern "C"

@@ -62,9 +62,9 @@ static inline void emu_yield() {
 }
 
 #define __global__
-#define __device__ static inline
+#define __device__
 #define __host__
-#define __forceinline__
+#define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
@@ -77,6 +77,9 @@ static inline uint32_t lane_id() { return threadIdx.x & 31u; }
 static inline uint32_t warp_id() { return threadIdx.x >> 5; }
 static inline void pdl_enter() {}
 static inline uint4 ld_stream(const uint4* p) { return *p; }
+static inline void st_stream(uint4* p, const uint4& v) { *p = v; }
+static inline uint64_t ld_relaxed_u64(const uint64_t* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
+static inline void st_relaxed_u64(uint64_t* p, uint64_t v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
 template <class T>
 static inline T __ldg(const T* p) { return *p; }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
@@ -166,6 +169,12 @@ static inline uint32_t warp_incl_max(uint32_t v) {
 
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline uint32_t atomicExch(uint32_t* p, uint32_t v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+static inline uint32_t atomicMax(uint32_t* p, uint32_t v) {
+  uint32_t old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (v > old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+  }
+  return old;
+}
 static inline uint32_t atomicMin(uint32_t* p, uint32_t v) {
   uint32_t old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
   while (v < old && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
@@ -204,10 +213,10 @@ static void emu_trampoline() {
   }
   swapcontext(&b->fibers[t].ctx, &b->sched);
 }
-template <class Args>
-static void emu_launch(void (*kernel)(Args), dim3 grid2, unsigned block, Args args) {
+template <class... KArgs, class... Args>
+static void emu_launch(void (*kernel)(KArgs...), dim3 grid2, unsigned block, Args... args) {
   constexpr size_t STACK = 256 << 10;
-  emu_entry = [=] { kernel(args); };
+  emu_entry = [=] { kernel(args...); };
   for (unsigned by = 0; by < grid2.y; by++)
     for (unsigned bx = 0; bx < grid2.x; bx++) {
       EmuBlock blk(block);

@@ -17,3 +17,12 @@ p = d['roofline_hbm_bound']['pciids_parse']
 print('$v', 'step_ms', round(d['ms_per_step'], 4), 'parse128_GBps', round(p['achieved'], 1), 'frac', round(p['frac'], 3),
       'kernels_us', {k: round(v * 1e3, 1) for k, v in d['kernel_ms_per_step'].items() if k.startswith('pciids')})"
 done
+# 3. the warp-per-digit tile scan (csrc/kvg_radix_exp.cuh): parity, then the config-2 step
+KVG_TILESCAN=warp python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "scan_pci or orderings or million or mdev or properties" 2>&1 | tail -3
+for v in block warp; do
+  KVG_TILESCAN=$v python bench.py --no-extra --no-cpu-baseline --steps 10 --warmup 3 2>/dev/null | python -c "
+import json, sys
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('tilescan=$v', 'step_ms', round(d['ms_per_step'], 4), 'radix_tilescan_us', round(d['kernel_ms_per_step']['radix_tilescan'] * 1e3, 1),
+      'scan16M_ms', round(d['roofline_hbm_bound']['classify_compact']['whole_scan_ms'], 4))"
+done
