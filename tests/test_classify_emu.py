@@ -56,3 +56,32 @@ def test_classify_pipeline_matches_the_drop_rules(emu, variant):
         assert np.array_equal(out[:len(want)], want), (n, variant)
         if len(want):
             assert int(ctrl[1]) == int(want["iommu_group"].max()) and int(ctrl[2]) == int(want["device"].max())
+
+
+def test_health_diff_kernel_reports_transitions_in_record_order(emu):
+    """K6 = k_compact<HealthOp> (BASELINE.json config 5): the transition list of every tick, like
+    tests/test_gpu_parity.py::test_health_rescan_transitions, from kernel source."""
+    emu.emu_health_rescan.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    ids = O.nv_ids(util.pciids_text())
+    n = 10_000
+    recs = O.gen_pci(0, n, ids, 0)
+    alive_prev = np.zeros(n + 1, dtype=np.uint8)
+    prev = np.zeros(n, dtype=bool)
+    rng = np.random.default_rng(5)
+    drop = 1 | 2 | 4 | 8
+    for tick in range(5):
+        if tick:
+            flip = rng.integers(0, n, 10)
+            recs["driver"][flip] = rng.integers(0, 5, 10)
+            recs["flags"][flip] ^= rng.integers(0, 32, 10).astype(np.uint8)
+        changed = np.zeros(n + 1, dtype=np.uint32)
+        ctrl = np.zeros(2, dtype=np.uint32)
+        assert emu.emu_health_rescan(np.ascontiguousarray(recs).ctypes.data, n, alive_prev.ctypes.data,
+                                     changed.ctypes.data, ctrl.ctypes.data) == 0
+        now = (recs["vendor"] == 0x10de) & ((recs["flags"] & drop) == 0) & ((recs["driver"] == 1) | (recs["driver"] == 2))
+        idx = np.nonzero(now != prev)[0]
+        want = (idx.astype(np.uint32) << 1) | now[idx].astype(np.uint32)
+        assert int(ctrl[0]) == len(want) and int(ctrl[1]) == int(now.sum())
+        assert np.array_equal(changed[:len(want)], want)
+        assert np.array_equal(alive_prev[:n].astype(bool), now)
+        prev = now

@@ -57,4 +57,26 @@ int emu_classify_pci(const uint4* recs, uint32_t n, const uint32_t* nv_index, in
   return 0;
 }
 
+// K6 (kvg_health_rescan): alive-set diff against the previous scan, transitions in record order.
+// alive_prev: n bytes, updated in place.  changed_out: room for n words.  ctrl_out: {n_changed, n_alive}.
+// The grid is one CTA per tile — what compact_grid() picks whenever the tiles fit the GPU, and the only
+// shape a sequential emulation of a look-back kernel can run.
+int emu_health_rescan(const uint4* recs, uint32_t n, uint8_t* alive_prev, uint32_t* changed_out, uint32_t* ctrl_out) {
+  const size_t tiles = (n + C_TILE - 1) / C_TILE;
+  ScanCtrl ctrl;
+  memset(&ctrl, 0, sizeof ctrl);
+  std::vector<uint64_t> state(tiles + 4, 0);
+  HealthOp op;
+  op.recs = recs;
+  op.n = n;
+  op.alive_prev = alive_prev;
+  op.changed = changed_out;
+  op.ctrl = &ctrl;
+  op.local_alive = 0;
+  emu_launch(k_compact<HealthOp>, dim3((unsigned)(tiles ? tiles : 1)), KVG_BLOCK, op, state.data(), 11u);
+  ctrl_out[0] = ctrl.n_changed;
+  ctrl_out[1] = ctrl.n_alive;
+  return 0;
+}
+
 }  // extern "C"
