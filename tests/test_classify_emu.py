@@ -85,3 +85,44 @@ def test_health_diff_kernel_reports_transitions_in_record_order(emu):
         assert np.array_equal(changed[:len(want)], want)
         assert np.array_equal(alive_prev[:n].astype(bool), now)
         prev = now
+
+
+def test_mdev_dictionary_and_classification_from_kernel_source(emu):
+    """K5: label rule (Trim "\\n", \\s+ -> "_", device_plugin.go:341-342), equal labels merge into the
+    smallest raw index, drop rules :270-279, NUMA clamp, survivors in Walk order with their source index."""
+    import re
+    emu.emu_scan_mdev.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p]
+    raw_types = O.gen_type_names(64) + [b"\n\nGRID  P100X-1B\n", b"GRID P100X-1B", b"GRID\tP100X-1B\n\n", b"", b"\n", b" x \r\n y"]
+    nt = len(raw_types)
+    blob = np.frombuffer(b"".join(raw_types) + b"\0", dtype=np.uint8).copy()
+    off = np.zeros(nt + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(t) for t in raw_types])
+    want_labels = [re.sub(rb"[\t\n\f\r ]+", b"_", t.strip(b"\n")) for t in raw_types]
+    want_canon = [want_labels.index(l) for l in want_labels]
+    for n in (0, 1, 511, 512, 513, 3000):
+        recs = O.gen_mdev(5, n)
+        if n:
+            recs["type_idx"] = recs["type_idx"] % (nt + 3)           # a few out-of-range type indices
+        label = np.zeros(len(blob) + 1, dtype=np.uint8)
+        label_len = np.zeros(nt, dtype=np.uint32)
+        canon = np.zeros(nt, dtype=np.uint16)
+        surv = np.zeros(n + 1, dtype=O.MDEV_SURV)
+        ctrl = np.zeros(3, dtype=np.uint32)
+        buf = np.ascontiguousarray(recs) if n else np.zeros(1, dtype=O.MDEV_REC)
+        assert emu.emu_scan_mdev(buf.ctypes.data, n, blob.ctypes.data, off.ctypes.data, nt, label.ctypes.data,
+                                 label_len.ctypes.data, canon.ctypes.data, surv.ctypes.data, ctrl.ctypes.data) == 0
+        got_labels = [bytes(label[off[k]:off[k] + label_len[k]]) for k in range(nt)]
+        assert got_labels == want_labels and list(canon) == want_canon
+        keep = ((recs["flags"] & 3) == 0) & (recs["type_idx"] < nt)
+        r = recs[keep]
+        assert int(ctrl[0]) == len(r)
+        s = surv[:len(r)]
+        assert np.array_equal(s["uuid"], r["uuid"]) and np.array_equal(s["parent"], r["parent"])
+        assert np.array_equal(s["type_key"], np.array(want_canon, dtype=np.uint16)[r["type_idx"]])
+        numa = r["parent_numa"].astype(np.int32)
+        numa[(numa < 0) | ((r["flags"] & 4) != 0)] = 0
+        assert np.array_equal(s["numa"], numa.astype(np.uint16))
+        assert np.array_equal(s["src"], np.nonzero(keep)[0].astype(np.uint32))
+        if len(r):
+            assert int(ctrl[1]) == int(r["parent"].max()) and int(ctrl[2]) == int(s["type_key"].max())

@@ -79,4 +79,48 @@ int emu_health_rescan(const uint4* recs, uint32_t n, uint8_t* alive_prev, uint32
   return 0;
 }
 
+// K5 (kvg_dev_scan_mdev up to the survivor list): type dictionary -> labels -> canonical ids, then the
+// 32-byte mdev records through k_classify_ragged<MdevClassifyOp,128,4> -> k_tile_offsets -> k_pack_survivors<2>.
+// raw / raw_off: the dictionary blob with n_types+1 offsets.  Outputs: label bytes per entry (at raw_off),
+// label_len, canon; surv_out: 2 x uint4 per survivor; ctrl_out: {n_surv, max_parent, max_type}.
+int emu_scan_mdev(const uint4* recs, uint32_t n, const uint8_t* raw, const uint32_t* raw_off, uint32_t n_types, uint8_t* label,
+                  uint32_t* label_len, uint16_t* canon, uint4* surv_out, uint32_t* ctrl_out) {
+  std::vector<uint64_t> label_hash(n_types + 1);
+  if (n_types) {
+    emu_launch(k_mdev_labels, dim3((n_types + 127) / 128), 128, raw, raw_off, n_types, label, label_len, label_hash.data());
+    emu_launch(k_mdev_canon, dim3((n_types + 127) / 128), 128, (const uint8_t*)label, raw_off, (const uint32_t*)label_len,
+               (const uint64_t*)label_hash.data(), n_types, canon);
+  }
+  constexpr int T = 128, R = 4;
+  const size_t tiles = (n + (size_t)T * R - 1) / ((size_t)T * R);
+  ScanCtrl ctrl;
+  memset(&ctrl, 0, sizeof ctrl);
+  std::vector<uint4> ragged(2 * (tiles + 1) * T * R);
+  std::vector<uint32_t> tile_count(tiles + 2), tile_off(tiles + 3);
+  std::vector<uint2> tile_max(tiles + 2);
+  std::vector<uint64_t> state(tiles + 4, 0);
+  MdevClassifyOp op;
+  op.recs = recs;
+  op.n = n;
+  op.out = ragged.data();
+  op.ctrl = &ctrl;
+  op.type_canon = canon;
+  op.n_types = n_types;
+  op.local_max_parent = 0;
+  op.local_max_type = 0;
+  if (tiles) {
+    emu_launch(k_classify_ragged<MdevClassifyOp, T, R>, dim3((unsigned)tiles), T, op, tile_count.data(), tile_max.data());
+    TileOffsetsArgs2 tt;
+    tt.o[0] = {tile_count.data(), tile_max.data(), nullptr, (uint32_t)tiles, tile_off.data(), &ctrl.n_surv, state.data()};
+    tt.o[1] = tt.o[0];
+    emu_launch(k_tile_offsets, dim3((unsigned)((tiles + C_TILE - 1) / C_TILE)), KVG_BLOCK, tt, &ctrl, 13u);
+    emu_launch(k_pack_survivors<2>, dim3((unsigned)tiles), 128, (const uint4*)ragged.data(), (const uint32_t*)tile_off.data(),
+               (uint32_t)(T * R), surv_out);
+  }
+  ctrl_out[0] = ctrl.n_surv;
+  ctrl_out[1] = ctrl.max_group;
+  ctrl_out[2] = ctrl.max_devkey;
+  return 0;
+}
+
 }  // extern "C"
