@@ -1,5 +1,6 @@
-"""getDeviceName (device_plugin.go:371-438) end to end from KERNEL SOURCE on the CPU: the barrier-free
-parse, k_nv_index, k_pciids_sanitise_lines (the lane-parallel name transform with its Unicode fall-back),
+"""getDeviceName (device_plugin.go:371-438) end to end from KERNEL SOURCE on the CPU: the default parse
+(k_pciids_parse with its TMA text ring, mbarriers and cross-tile vendor look-back) or the barrier-free
+one, k_nv_index, k_pciids_sanitise_lines (the lane-parallel name transform with its Unicode fall-back),
 k_section_lines / k_lookup_general / k_sanitise_matches (prefix semantics for arbitrary keys) — sequenced
 like libkvgpu.so does and compared with the oracle on the reference's Ginkgo fixture, the shipped
 pci.ids and the grammar fuzz.  Runs under the warp emulator of tools/emu/."""
@@ -25,12 +26,15 @@ NAME_CAP = 4096
 @pytest.fixture(scope="module")
 def emu():
     L = C.CDLL(emu_build.build_names())
-    L.emu_get_device_names.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
-                                       C.c_uint32, C.c_void_p]
+    L.emu_get_device_names.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+                                       C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     return L
 
 
-def device_names(emu, text, keys, cap_log2=12):
+PARSERS = pytest.mark.parametrize("parser", [1, 2], ids=["k_pciids_parse", "scan_v2"])
+
+
+def device_names(emu, text, keys, cap_log2=12, parser=1, want_info=False):
     buf = pad(text)
     blob = b"".join(keys) + b"\0"
     off = np.zeros(len(keys) + 1, dtype=np.uint32)
@@ -38,44 +42,63 @@ def device_names(emu, text, keys, cap_log2=12):
     kb = np.frombuffer(blob, dtype=np.uint8).copy()
     out = np.zeros(len(keys) * NAME_CAP, dtype=np.uint8)
     ln = np.zeros(len(keys), dtype=np.uint32)
-    rc = emu.emu_get_device_names(buf.ctypes.data, len(text), cap_log2, kb.ctypes.data, off.ctypes.data, len(keys),
-                                  out.ctypes.data, NAME_CAP, ln.ctypes.data)
+    info = np.zeros(8, dtype=np.uint32)
+    rc = emu.emu_get_device_names(parser, buf.ctypes.data, len(text), cap_log2, kb.ctypes.data, off.ctypes.data, len(keys),
+                                  out.ctypes.data, NAME_CAP, ln.ctypes.data, info.ctypes.data)
     assert rc == 0
-    return [bytes(out[i * NAME_CAP:i * NAME_CAP + int(ln[i])]).decode("latin-1") for i in range(len(keys))]
+    names = [bytes(out[i * NAME_CAP:i * NAME_CAP + int(ln[i])]).decode("latin-1") for i in range(len(keys))]
+    return (names, info) if want_info else names
 
 
-def check(emu, text, keys, cap_log2=12):
+def check(emu, text, keys, cap_log2=12, parser=1):
     if not text:
         return
     keys = [k if isinstance(k, bytes) else k.encode("utf-8") for k in keys]
-    got = device_names(emu, text, keys, cap_log2)
+    got = device_names(emu, text, keys, cap_log2, parser)
     for k, g in zip(keys, got):
         assert g == O.get_device_name(text, k), (k, text[:100])
 
 
-def test_ginkgo_kats_from_kernel_source(emu):
+@PARSERS
+def test_ginkgo_kats_from_kernel_source(emu, parser):
     G = util.ginkgo()["get_device_name"]
     text = G["fixture"].encode()
     for kat in G["kats"]:
         if kat["missing_file"]:
             continue
-        assert device_names(emu, text, [kat["key"].encode()])[0] == kat["want"], kat["title"]
+        assert device_names(emu, text, [kat["key"].encode()], parser=parser)[0] == kat["want"], kat["title"]
 
 
-def test_shipped_pciids_names_from_kernel_source(emu):
+@PARSERS
+def test_shipped_pciids_names_from_kernel_source(emu, parser):
     text = util.pciids_text()
     names = util.pciids_names()["names"]
     keys = sorted(names)[::9] + ["1b38", "2901", "2330", "05be", "ffff", "0000"]
-    got = device_names(emu, text, [k.encode() for k in keys], cap_log2=15)
+    got, info = device_names(emu, text, [k.encode() for k in keys], cap_log2=15, parser=parser, want_info=True)
+    assert int(info[0]) == text.index(b"\n10de  NVIDIA") + 1 and int(info[2]) == 1931 and int(info[3]) == text.count(b"\n")
     for k, g in zip(keys, got):
         assert g == names.get(k, O.get_device_name(text, k.encode())), k
     general = ["", "1", "1b", "1b3", "1b38 ", "1b38  GP102GL", "\t1043", "1B38", "2901  ", "x", "10de",
                "0008  NV1 [STG2000X-B Series]", "0008  NV1 [STG2000X-B Series]x", "#", "\n", "1b38\n", "ffffff", "é", "1b3\r"]
-    check(emu, text, general, cap_log2=15)
+    check(emu, text, general, cap_log2=15, parser=parser)
 
 
-def test_grammar_fuzz_names_from_kernel_source(emu):
+@PARSERS
+def test_grammar_fuzz_names_from_kernel_source(emu, parser):
     rng = np.random.default_rng(20250711)
     keys = ["%04x" % i for i in range(0, 40, 3)] + ["", "0", "00", "000", "0001 ", "\t", "001\r", "0001\r"]
     for it in range(25):
-        check(emu, _random_pciids(rng, int(rng.integers(1, 300))), keys)
+        check(emu, _random_pciids(rng, int(rng.integers(1, 300))), keys, parser=parser)
+
+
+def test_both_parsers_agree_on_every_parse_fact(emu):
+    """v_off, section end, entry count, line count and scanner limit of the default parse and of the
+    barrier-free one on tile-edge, long-line and multi-tile inputs (8 KiB tiles vs 4 KiB spans)."""
+    rng = np.random.default_rng(77)
+    texts = [_random_pciids(rng, int(rng.integers(800, 4000))) for _ in range(4)]
+    texts += [b"x" * 65536 + b"\n10de  NVIDIA\n\t1234  name\n", b"10de\n\t" + b"y" * 70000 + b"\n\t1234  n\n",
+              b"8086  Intel\n" + b"#" + b"c" * 8170 + b"\n10de  NVIDIA\n\t1234  Edge\n" + b"#" + b"d" * 9000 + b"\n\t5678  far\n10df x\n"]
+    for text in texts:
+        _, a = device_names(emu, text, [b"1234"], cap_log2=14, parser=1, want_info=True)
+        _, b = device_names(emu, text, [b"1234"], cap_log2=14, parser=2, want_info=True)
+        assert list(a[:6]) == list(b[:6]), text[:60]

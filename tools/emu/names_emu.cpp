@@ -1,17 +1,15 @@
-// names_emu.cpp — getDeviceName end to end from kernel source on the CPU: the barrier-free parse
-// (csrc/kvg_parse_v2.cuh) followed by the name path of csrc/kvg_parse.cuh exactly as the library
-// sequences it (kvg_api.cu: parse_enqueue_v2, table_publish, kvg_name_lookup, lookup_general):
+// names_emu.cpp — getDeviceName end to end from kernel source on the CPU: the DEFAULT parse
+// (k_pciids_parse of csrc/kvg_parse.cuh, parser = 1) or the barrier-free one (csrc/kvg_parse_v2.cuh,
+// parser = 2), followed by the name path of csrc/kvg_parse.cuh exactly as the library sequences it
+// (kvg_api.cu: parse_enqueue / parse_enqueue_v2, table_publish, kvg_name_lookup, lookup_general):
 //   hash path      k_nv_index -> k_pciids_sanitise_lines -> pool[slot] = u16 length + bytes
 //   general path   k_section_lines -> k_lookup_general -> k_sanitise_matches   (non-canonical keys)
 #define KVG_HOST_EMU 1
 #include "warp_emu.h"
 namespace kvg {
-#include "emu_helpers.inc"
+#include "emu_parse_all.inc"   // all of csrc/kvg_parse.cuh: the default parse (TMA ring) and the name path
 }
 #include "../../kubevirt-gpu-device-plugin_b200/csrc/kvg_parse_v2.cuh"
-namespace kvg {
-#include "emu_names.inc"
-}
 using namespace kvg;
 
 static bool canonical_key(const uint8_t* k, uint32_t n, uint32_t* v) {  // kvg_api.cu: 4 lower-case hex digits
@@ -30,8 +28,9 @@ extern "C" {
 
 // text: one image padded like kvg_text_pad.  keys: blob + n_keys+1 offsets.  names_out: n_keys x name_cap
 // bytes, names_len: n_keys.  Returns 0.
-int emu_get_device_names(const uint8_t* text, uint32_t len, uint32_t cap_log2, const uint8_t* keys, const uint32_t* key_off,
-                         uint32_t n_keys, uint8_t* names_out, uint32_t name_cap, uint32_t* names_len) {
+int emu_get_device_names(int parser, const uint8_t* text, uint32_t len, uint32_t cap_log2, const uint8_t* keys,
+                         const uint32_t* key_off, uint32_t n_keys, uint8_t* names_out, uint32_t name_cap, uint32_t* names_len,
+                         uint32_t* info_out) {
   const uint32_t spf = (len + V2_SPAN - 1) / V2_SPAN, n_spans = spf;
   const size_t cap = (size_t)1 << cap_log2;
   std::vector<uint64_t> table(cap, P_EMPTY);
@@ -56,23 +55,51 @@ int emu_get_device_names(const uint8_t* text, uint32_t len, uint32_t cap_log2, c
   A.span_state = state.data();
   A.pend_cnt = state.data() + n_spans;
   A.pending = pending.data();
-  const unsigned grid = (n_spans + V2_WARPS - 1) / V2_WARPS;
-  if (n_spans) {
-    emu_launch(k_pciids_scan_v2, dim3(grid), V2_WARPS * 32, A);
-    emu_launch(k_pciids_resolve_v2, dim3(grid), V2_WARPS * 32, A);
+  if (parser == 2) {
+    const unsigned grid = (n_spans + V2_WARPS - 1) / V2_WARPS;
+    if (n_spans) {
+      emu_launch(k_pciids_scan_v2, dim3(grid), V2_WARPS * 32, A);
+      emu_launch(k_pciids_resolve_v2, dim3(grid), V2_WARPS * 32, A);
+    }
+    ParseArgs F;
+    memset(&F, 0, sizeof F);
+    F.text = text;
+    F.len = len;
+    F.n_files = 1;
+    F.tiles_per_file = spf;
+    F.n_tiles = n_spans;
+    F.info = &info;
+    F.tile_first_hdr = A.span_first_hdr;
+    F.tile_first_nl = A.span_first_nl;
+    F.tile_last_nl = A.span_last_nl;
+    emu_launch(k_pciids_finalize_v2, dim3(1), KVG_BLOCK, F);
+  } else {
+    // parse_enqueue: ONE persistent CTA walks every tile in order (any grid <= n_tiles is legal on the GPU;
+    // a sequential emulation can only honour the look-back of a single CTA)
+    const uint32_t tpf = (len + P_TILE - 1) / P_TILE;
+    std::vector<uint32_t> tile_arrays(3 * (size_t)tpf + 1, 0xdeadbeefu);
+    std::vector<uint64_t> tile_state(tpf + 1, 0);
+    ParseArgs P;
+    memset(&P, 0, sizeof P);
+    P.text = text;
+    P.stride = 0;
+    P.len = len;
+    P.n_files = 1;
+    P.tiles_per_file = tpf;
+    P.n_tiles = tpf;
+    P.tables = table.data();
+    P.cap_mask = (uint32_t)cap - 1;
+    P.cap_shift = 32 - cap_log2;
+    P.info = &info;
+    P.tile_first_hdr = tile_arrays.data();
+    P.tile_first_nl = tile_arrays.data() + tpf;
+    P.tile_last_nl = tile_arrays.data() + 2 * (size_t)tpf;
+    P.tile_state = tile_state.data();
+    P.epoch = 5;
+    if (tpf) emu_launch(k_pciids_parse, dim3(1), KVG_BLOCK, P);
+    emu_launch(k_pciids_finalize, dim3(1), KVG_BLOCK, P);
   }
-  ParseArgs F;
-  memset(&F, 0, sizeof F);
-  F.text = text;
-  F.len = len;
-  F.n_files = 1;
-  F.tiles_per_file = spf;
-  F.n_tiles = n_spans;
-  F.info = &info;
-  F.tile_first_hdr = A.span_first_hdr;
-  F.tile_first_nl = A.span_first_nl;
-  F.tile_last_nl = A.span_last_nl;
-  emu_launch(k_pciids_finalize_v2, dim3(1), KVG_BLOCK, F);
+  memcpy(info_out, &info, sizeof info);
   if (info.overflow) return 1;
   // ---- table_publish: nv_index + named lines, sanitised pool, candidate lines of the general lookup
   std::vector<uint32_t> nv_index(65536), nv_lines(65536 + 8, 0);

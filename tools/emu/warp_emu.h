@@ -146,6 +146,21 @@ static inline uint32_t __match_any_sync(uint32_t, uint32_t v) {
 }
 static inline uint32_t lanemask_lt() { return (1u << lane_id()) - 1u; }
 
+// mbarrier + TMA 1-D bulk copy (kvg_common.cuh) as used by the 4-stage text ring of k_pciids_parse: the
+// copy completes at issue time, the barrier word counts completed phases, a wait on parity p returns once
+// phase p has completed — the same observable protocol, minus the asynchrony
+static inline void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
+static inline void mbar_fence_init() {}
+static inline void mbar_arrive_expect_tx(uint64_t*, uint32_t) {}
+static inline void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  memcpy(smem_dst, gmem_src, bytes);
+  (*bar)++;
+  emu_block->progressed = true;
+}
+static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (((*bar) & 1u) == parity) emu_yield();
+}
+
 // the reductions of kvg_common.cuh, on top of the emulated shuffles
 static inline uint32_t warp_sum(uint32_t v) {
   for (uint32_t o = 16; o; o >>= 1) v += __shfl_xor_sync(KVG_FULL, v, o);
