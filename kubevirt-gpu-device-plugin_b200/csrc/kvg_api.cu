@@ -190,6 +190,7 @@ struct kvg_ctx {
   OrderBufs ord_dev, ord_grp;
   DevBuf<uint32_t> tile_hist, bin_total;
   bool scatter_smem_set = false;  // dynamic shared-memory opt-in of k_radix_scatter<11> done on this device
+  bool scatter_c_smem_set = false;
   size_t last_n = 0;     // records of the last enqueued scan
   size_t last_total = 0; // survivors capacity used by the last scan (sharded: all ranks)
   int last_kind = 0;     // 1 = pci, 2 = mdev
@@ -1110,10 +1111,22 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1, bool 
     } else {
       LAUNCH("radix_tilescan", k_radix_tilescan, sgrid, KVG_BLOCK, 0, aa);
     }
-    if (max_bits == 8)
+    static const bool scatter_c = [] {  // KVG_SCATTER=c: experimental, see kvg_radix_exp.cuh
+      const char* e = getenv("KVG_SCATTER");
+      return e && strcmp(e, "c") == 0;
+    }();
+    if (max_bits == 8) {
       LAUNCH("radix_scatter", k_radix_scatter<8>, grid, KVG_BLOCK, RadixScatterCfg<8>::SMEM, aa);
-    else
+    } else if (scatter_c) {
+      if (!ctx->scatter_c_smem_set) {
+        CK(cudaFuncSetAttribute(k_radix_scatter_c, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)RadixScatterCfg<RADIX_MAX_BITS>::SMEM));
+        ctx->scatter_c_smem_set = true;
+      }
+      LAUNCH("radix_scatter", k_radix_scatter_c, grid, KVG_BLOCK, RadixScatterCfg<RADIX_MAX_BITS>::SMEM, aa);
+    } else {
       LAUNCH("radix_scatter", k_radix_scatter<RADIX_MAX_BITS>, grid, KVG_BLOCK, RadixScatterCfg<RADIX_MAX_BITS>::SMEM, aa);
+    }
   }
   // final permutation + distinct keys of both orderings: count heads per tile, scan, emit
   OrderFinalArgs2 ff;

@@ -15,7 +15,8 @@ using namespace kvg;
 extern "C" {
 
 // Stable sort of {key, index} pairs the way the device does it.  pairs_io: n x {key, index}; on return
-// the sorted pairs.  variant: 0 = k_radix_tilescan, 1 = k_radix_tilescan_warp.  Returns the pass count
+// the sorted pairs.  variant: 0 = default kernels, 1 = k_radix_tilescan_warp, 2 = k_radix_scatter_c (11-bit only),
+// 3 = both experimental kernels.  Returns the pass count
 // the device-side plan chose, or a negative number.
 int emu_radix_sort(uint2* pairs_io, uint32_t n, uint32_t key_bits_max, uint32_t max_bits, int variant) {
   if (max_bits != 8 && max_bits != RADIX_MAX_BITS) return -1;
@@ -43,12 +44,14 @@ int emu_radix_sort(uint2* pairs_io, uint32_t n, uint32_t key_bits_max, uint32_t 
     aa.o[0] = a;
     aa.o[1] = a;
     emu_launch(k_radix_hist, dim3((unsigned)T, 1), KVG_BLOCK, aa);
-    if (variant == 1)
+    if (variant & 1)
       emu_launch(k_radix_tilescan_warp, dim3(RADIX_MAX_DIGITS / TS_WARPS, 1), TS_WARPS * 32, aa);
     else
       emu_launch(k_radix_tilescan, dim3(KVG_BLOCK, 1), KVG_BLOCK, aa);
     if (max_bits == 8)
       emu_launch(k_radix_scatter<8>, dim3((unsigned)T, 1), KVG_BLOCK, aa);
+    else if (variant & 2)
+      emu_launch(k_radix_scatter_c, dim3((unsigned)T, 1), KVG_BLOCK, aa);
     else
       emu_launch(k_radix_scatter<RADIX_MAX_BITS>, dim3((unsigned)T, 1), KVG_BLOCK, aa);
   }

@@ -26,3 +26,11 @@ d = json.loads(sys.stdin.read().strip().splitlines()[-1])
 print('tilescan=$v', 'step_ms', round(d['ms_per_step'], 4), 'radix_tilescan_us', round(d['kernel_ms_per_step']['radix_tilescan'] * 1e3, 1),
       'scan16M_ms', round(d['roofline_hbm_bound']['classify_compact']['whole_scan_ms'], 4))"
 done
+# 4. the contiguous-ownership scatter (csrc/kvg_radix_exp.cuh), alone and with the warp tile scan
+KVG_SCATTER=c python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "scan_pci or orderings or million or mdev or properties" 2>&1 | tail -3
+for env in "KVG_SCATTER=c" "KVG_SCATTER=c KVG_TILESCAN=warp" "KVG_SCATTER=c KVG_TILESCAN=warp KVG_PARSE=v2"; do
+  env $env python bench.py --no-extra --no-cpu-baseline --steps 10 --warmup 3 2>/dev/null | python -c "
+import json, sys
+d = json.loads(sys.stdin.read().strip().splitlines()[-1])
+print('$env', 'step_ms', round(d['ms_per_step'], 4), {k: round(v * 1e3, 1) for k, v in d['kernel_ms_per_step'].items() if k.startswith('radix') or k.startswith('pciids')})"
+done
