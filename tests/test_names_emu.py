@@ -27,7 +27,8 @@ NAME_CAP = 4096
 def emu():
     L = C.CDLL(emu_build.build_names())
     L.emu_get_device_names.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
-                                       C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+                                       C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                       C.c_void_p]
     return L
 
 
@@ -44,7 +45,7 @@ def device_names(emu, text, keys, cap_log2=12, parser=1, want_info=False):
     ln = np.zeros(len(keys), dtype=np.uint32)
     info = np.zeros(8, dtype=np.uint32)
     rc = emu.emu_get_device_names(parser, buf.ctypes.data, len(text), cap_log2, kb.ctypes.data, off.ctypes.data, len(keys),
-                                  out.ctypes.data, NAME_CAP, ln.ctypes.data, info.ctypes.data)
+                                  out.ctypes.data, NAME_CAP, ln.ctypes.data, info.ctypes.data, None, None, 0, None)
     assert rc == 0
     names = [bytes(out[i * NAME_CAP:i * NAME_CAP + int(ln[i])]).decode("latin-1") for i in range(len(keys))]
     return (names, info) if want_info else names

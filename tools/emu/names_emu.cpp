@@ -30,7 +30,7 @@ extern "C" {
 // bytes, names_len: n_keys.  Returns 0.
 int emu_get_device_names(int parser, const uint8_t* text, uint32_t len, uint32_t cap_log2, const uint8_t* keys,
                          const uint32_t* key_off, uint32_t n_keys, uint8_t* names_out, uint32_t name_cap, uint32_t* names_len,
-                         uint32_t* info_out) {
+                         uint32_t* info_out, uint32_t* nv_index_out, uint8_t* pool_out, uint32_t pool_cap, uint32_t* pool_len) {
   const uint32_t spf = (len + V2_SPAN - 1) / V2_SPAN, n_spans = spf;
   const size_t cap = (size_t)1 << cap_log2;
   std::vector<uint64_t> table(cap, P_EMPTY);
@@ -115,6 +115,12 @@ int emu_get_device_names(int parser, const uint8_t* text, uint32_t len, uint32_t
   if (sec)
     emu_launch(k_section_lines, dim3(8), KVG_BLOCK, text, (const PciIdsInfo*)&info, sec_lines.data(), sec_lines.data() + sec_cap,
                sec_cap);
+  if (nv_index_out) {   // table export for the end-to-end scan test: what the scans join against
+    memcpy(nv_index_out, nv_index.data(), sizeof(uint32_t) * 65536);
+    if (pool.size() > pool_cap) return 3;
+    memcpy(pool_out, pool.data(), pool.size());
+    *pool_len = (uint32_t)pool.size();
+  }
   // ---- kvg_name_lookup per key
   for (uint32_t k = 0; k < n_keys; k++) {
     const uint8_t* key = keys + key_off[k];
