@@ -68,7 +68,7 @@ def test_create_iommu_device_map_from_kernel_source(libs, parser, variant):
     text = util.pciids_text()
     nv_index, pool = name_table(names, text, parser)
     ids = O.nv_ids(text)
-    for n, gbits in ((0, 0), (700, 0), (4000, 11)):
+    for n, gbits in ((0, 0), (700, 0), (2600, 11)):
         recs = O.gen_pci(3, n, ids, gbits)
         surv = np.zeros(n + 1, dtype=kvgpu.PCI_SURV)
         ctrl = np.zeros(3, dtype=np.uint32)
