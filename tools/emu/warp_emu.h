@@ -37,7 +37,6 @@ static EmuDim3 threadIdx, blockIdx, blockDim, gridDim;  // restored by the sched
 
 struct EmuFiber {
   ucontext_t ctx;
-  std::unique_ptr<char[]> stack;
   bool done = false;
 };
 struct EmuBlock {
@@ -232,15 +231,17 @@ template <class... KArgs, class... Args>
 static void emu_launch(void (*kernel)(KArgs...), dim3 grid2, unsigned block, Args... args) {
   constexpr size_t STACK = 256 << 10;
   emu_entry = [=] { kernel(args...); };
+  // fiber stacks are allocated once per process and reused by every block of every launch
+  static std::vector<std::unique_ptr<char[]>> stacks;
+  while (stacks.size() < block) stacks.emplace_back(new char[STACK]);
   for (unsigned by = 0; by < grid2.y; by++)
     for (unsigned bx = 0; bx < grid2.x; bx++) {
       EmuBlock blk(block);
       emu_block = &blk;
       for (unsigned t = 0; t < block; t++) {
         EmuFiber& f = blk.fibers[t];
-        f.stack.reset(new char[STACK]);
         getcontext(&f.ctx);
-        f.ctx.uc_stack.ss_sp = f.stack.get();
+        f.ctx.uc_stack.ss_sp = stacks[t].get();
         f.ctx.uc_stack.ss_size = STACK;
         f.ctx.uc_link = &blk.sched;
         makecontext(&f.ctx, emu_trampoline, 0);
