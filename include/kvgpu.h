@@ -175,6 +175,61 @@ typedef struct kvg_mdev_result {
   const uint32_t *par_perm;
 } kvg_mdev_result;
 
+/* ---- results of the SHARDED scans (one process per GPU; BASELINE.json config 4) ---------------------
+ * Rank r scans records [r*N/P, (r+1)*N/P).  Its survivors stay local (concatenating the ranks' `local`
+ * lists in rank order is the global Walk-order list, i.e. bdfToIommuMap / the mdev list).  The two group-by
+ * maps are partitioned BY KEY: rank r holds exactly the keys with key % nranks == r, with ALL their members
+ * (from every shard, Walk order).  Key sets of different ranks are disjoint; their union is the global map. */
+typedef struct kvg_pci_shard_result {
+  uint64_t n_records;             /* records of this rank's shard */
+  uint64_t n_local;
+  const kvg_pci_surv *local;      /* [n_local] this shard's survivors, Walk order */
+  /* deviceMap part: members of the device ids this rank owns; key k = dev_members[dev_perm[dev_off[k]..)] */
+  uint64_t n_dev_members;
+  const kvg_pci_surv *dev_members;
+  uint32_t n_dev_keys;
+  const uint16_t *dev_keys;
+  const uint32_t *dev_off;
+  const uint32_t *dev_perm;
+  const uint32_t *dev_name_slot;
+  /* iommuMap part */
+  uint64_t n_grp_members;
+  const kvg_pci_surv *grp_members;
+  uint32_t n_groups;
+  const uint32_t *grp_keys;
+  const uint32_t *grp_off;
+  const uint32_t *grp_perm;
+  const uint8_t *name_pool;
+  size_t name_pool_len;
+} kvg_pci_shard_result;
+
+typedef struct kvg_mdev_shard_result {
+  uint64_t n_records;
+  uint64_t n_local;
+  const kvg_mdev_surv *local;     /* [n_local] this shard's surviving mdevs, Walk order */
+  /* vGpuMap part: canonical type ids owned by this rank */
+  uint64_t n_type_members;
+  const kvg_mdev_surv *type_members;
+  uint32_t n_type_keys;
+  const uint16_t *type_keys;
+  const uint32_t *type_off;
+  const uint32_t *type_perm;
+  /* gpuVgpuMap part: parent handles owned by this rank */
+  uint64_t n_par_members;
+  const kvg_mdev_surv *par_members;
+  uint32_t n_parents;
+  const uint32_t *par_keys;
+  const uint32_t *par_off;
+  const uint32_t *par_perm;
+  /* the type dictionary as in kvg_mdev_result (every rank loads the same dictionary) */
+  uint32_t n_types;
+  const uint32_t *label_off;
+  const uint8_t *label_bytes;
+  const uint16_t *type_canon;
+  const uint32_t *type_name_off;
+  const uint8_t *type_name_bytes;
+} kvg_mdev_shard_result;
+
 /* Health transitions of one re-scan relative to the previous one (record order). */
 typedef struct kvg_health_delta {
   uint32_t n_records;
@@ -208,12 +263,12 @@ void *kvg_stream(kvg_ctx *ctx);
 int kvg_pciids_load(kvg_ctx *ctx, const uint8_t *text, size_t len);
 
 /* Exact getDeviceName(key) for ANY key bytes: "" (outlen 0) when not found.  4-lower-hex keys go
- * through the hash; every other key through the prefix-match kernel (device_plugin.go:388-400). */
+ * through the table; every other key through the prefix-match kernel (device_plugin.go:388-400). */
 int kvg_name_lookup(kvg_ctx *ctx, const char *key, size_t keylen, char *out, size_t cap,
                     size_t *outlen);
 
 /* Bulk form used by tests and the Go shim: names of device ids [first, first+count) through the
- * hash path; out_off has count+1 entries into out_bytes (cap bytes). */
+ * table path; out_off has count+1 entries into out_bytes (cap bytes). */
 int kvg_name_table(kvg_ctx *ctx, uint32_t first, uint32_t count, uint32_t *out_off,
                    uint8_t *out_bytes, size_t cap);
 
@@ -239,7 +294,7 @@ int kvg_health_reset(kvg_ctx *ctx);
  * kvg_text_pad(len) readable bytes from it, all padding bytes '\n'.  n_files images of `len`
  * bytes each, image f at d_text + f*stride (stride % 16 == 0, stride >= kvg_text_pad(len)+16).
  * Image 0 becomes the context's table; images >= 1 are parsed into scratch tables (batch
- * throughput measurement: every byte is split, every device line hashed). */
+ * throughput measurement: every byte is split, every line start classified). */
 size_t kvg_text_pad(size_t len);
 int kvg_dev_pciids_parse(kvg_ctx *ctx, const void *d_text, size_t len, size_t stride,
                          uint32_t n_files);
@@ -258,14 +313,11 @@ int kvg_dev_scan_mdev(kvg_ctx *ctx, const void *d_recs, size_t n, const kvg_type
 int kvg_dev_scan_mdev_fetch(kvg_ctx *ctx, kvg_mdev_result **res);
 /* Diagnostics: the pass structure (count, shift and width of each pass) the radix kernels derive on
  * the device for an ordering whose largest key is `max_key` (key_bits_max 16 or 32; max_bits 11, or 8 for
- * inputs >= 8 Mi records).  Pure host arithmetic: usable without a GPU. */
+ * inputs >= 8 Mi records): pass 0 always takes the low max_bits bits, the remaining key bits are split
+ * evenly over the fewest further passes.  Pure host arithmetic: usable without a GPU. */
 int kvg_debug_radix_plan(uint32_t max_key, uint32_t key_bits_max, uint32_t max_bits, uint32_t *npass,
                          uint32_t *shifts4, uint32_t *bits4);
 
-/* diagnostic only: decomposed classify kernel (mode 0 read+count, 1 +tile-local writes, 2 +join);
- * rows = records per thread (4, 8 or 16); *ms_out = device time of the launch */
-int kvg_dev_debug_classify(kvg_ctx *ctx, const void *d_recs, size_t n, int mode, int rows,
-                           float *ms_out);
 /* write `bytes` of zeros through a scratch buffer larger than L2 (timing hygiene, untimed) */
 int kvg_dev_flush_l2(kvg_ctx *ctx);
 /* per-kernel device time of the last kvg_dev_scan_pci / kvg_dev_pciids_parse, CUDA events on the
@@ -278,22 +330,25 @@ int kvg_set_kernel_timing(kvg_ctx *ctx, int enabled);
 int kvg_comm_unique_id(void *out128);
 int kvg_comm_init(kvg_ctx *ctx, int rank, int nranks, const void *unique_id128);
 int kvg_comm_destroy(kvg_ctx *ctx);
-/* Peer-memory variant of the exchange step (CUDA IPC over NVLink, one process per GPU of ONE node):
- * export allocates this rank's gather windows for shards of up to cap_local records and returns a
- * 64-byte handle; import opens all ranks' handles (nranks x 64 bytes, rank order).  Afterwards
- * kvg_dev_scan_pci_sharded fuses the dense pack with the all-gather (each survivor is stored straight
- * into every peer's window) and needs neither NCCL nor a host synchronisation.  If either call fails
- * the NCCL path (kvg_comm_init) remains usable. */
+/* Peer-memory exchange (CUDA IPC over NVLink, one process per GPU of ONE node): export allocates this
+ * rank's receive window for shards of up to cap_local PCI records (cap_local / 2 mdev records) and returns
+ * a 64-byte handle; import opens all ranks' handles (nranks x 64 bytes, rank order).  Afterwards the sharded
+ * scans exchange by storing into the owners' windows and need neither NCCL nor a host synchronisation.
+ * If either call fails the NCCL path (kvg_comm_init) remains usable. */
 int kvg_comm_p2p_export(kvg_ctx *ctx, int rank, int nranks, size_t cap_local, void *handle_out64);
 int kvg_comm_p2p_import(kvg_ctx *ctx, const void *all_handles);
 /* collective decision: enable only when import succeeded on every rank */
 int kvg_comm_p2p_enable(kvg_ctx *ctx, int on);
-/* classify the local shard, allgatherv the survivors over NCCL (rank order == Walk order): every rank
- * ends up with the FULL survivor list.  The bucketing is partitioned by key: rank r's orderings
- * (dev_* / grp_* of the fetched result) cover exactly the keys with key % nranks == r, so the key
- * sets of the ranks are disjoint and their union is the global deviceMap / iommuMap; dev_perm and
- * grp_perm then hold only the members of the owned keys.  d_recs is device memory. */
+/* Classify the local shard (device memory), send every survivor to the owner of its key (once per
+ * group-by map: key % nranks), order the owned members.  Peer windows: the multisplit stores straight into
+ * the owners' windows over NVLink, nothing returns to the host.  NCCL mode: one allgatherv of the survivor
+ * lists (two host synchronisations for the counts), then the same kernels keep what this rank owns.
+ * Collective: every rank of the communicator must call it, in the same order. */
 int kvg_dev_scan_pci_sharded(kvg_ctx *ctx, const void *d_recs, size_t n_local);
+int kvg_dev_scan_pci_shard_fetch(kvg_ctx *ctx, kvg_pci_shard_result **res);
+/* the same for mdev records (createVgpuIDMap): type / parent orderings of the owned members */
+int kvg_dev_scan_mdev_sharded(kvg_ctx *ctx, const void *d_recs, size_t n_local, const kvg_type_dict *types);
+int kvg_dev_scan_mdev_shard_fetch(kvg_ctx *ctx, kvg_mdev_shard_result **res);
 
 #ifdef __cplusplus
 }

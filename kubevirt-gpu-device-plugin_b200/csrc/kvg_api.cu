@@ -3,7 +3,8 @@
 //
 // HBM layout owned by a context (all cudaMalloc'd once and grown geometrically, never per call):
 //   text      pci.ids image(s), padded with '\n' to a tile multiple + 16 (TMA halo)
-//   tables    open-addressed u64 slots  key(vendor<<16|device)<<32 | line offset
+//   dev_off   per image 65,536 x u32: line offset of the first "\t<id>" line under a 10de header
+//   nv_index  65,536 x u32: device id -> name pool slot (what the scans join against)
 //   pool      sanitised names of the NVIDIA section, slot = line offset - section offset
 //   recs      record staging (host entry points only)
 //   surv      compacted survivors, Walk order
@@ -26,9 +27,10 @@
 #include "../../include/kvgpu.h"
 #include "kvg_common.cuh"
 #include "kvg_parse.cuh"
-#include "kvg_parse_v2.cuh"
+#include "kvg_parse_k1.cuh"
 #include "kvg_scan.cuh"
-#include "kvg_radix_exp.cuh"
+#include "kvg_order.cuh"
+#include "kvg_shard.cuh"
 
 using namespace kvg;
 
@@ -152,16 +154,13 @@ struct kvg_ctx {
   DevBuf<uint8_t> text;  // owned copy (host entry point)
   const uint8_t* d_text = nullptr;
   uint32_t text_len = 0;
-  DevBuf<uint64_t> tables;
-  uint32_t cap_log2 = 0;
+  DevBuf<uint32_t> dev_off;   // [n_files][65536]
   DevBuf<PciIdsInfo> info;
-  DevBuf<uint32_t> tile_arrays;  // 3 x n_tiles
-  DevBuf<uint64_t> parse_state;
-  DevBuf<uint32_t> v2_state, v2_pending;  // KVG_PARSE=v2 (experimental): span states + pending counts, pending lines
-  DevBuf<uint32_t> parse_ticket;
+  DevBuf<uint4> span_sum;     // K1: one 16-byte summary per 4 KiB span
+  int k1_grid = 0;            // co-resident CTAs of k_pciids_scan on this device
+  bool sec_lines_ready = false;  // candidate lines of the general lookup collected for the current table
   DevBuf<uint8_t> pool;
   DevBuf<uint32_t> nv_index;  // [65536] vendor-10de device id -> name pool slot
-  DevBuf<uint32_t> nv_lines;  // [65536 + 1] offsets of the lines that have a name, then their count
   DevBuf<uint32_t> sec_lines; // '\t' line starts of the NVIDIA section, then their count (general lookups)
   size_t sec_lines_cap = 0;
   DevBuf<uint64_t> type_hash;
@@ -173,9 +172,7 @@ struct kvg_ctx {
   // copy overlaps the parse
   bool load_pending = false;
   size_t pend_len = 0, pend_stride = 0;
-  uint32_t pend_cap_log2 = 0;
   uint32_t parsed_files = 0;
-  int parse_grid = 0;
 
   // scans
   DevBuf<ScanCtrl> ctrl;
@@ -188,13 +185,12 @@ struct kvg_ctx {
   DevBuf<uint64_t> offs_state;
   DevBuf<uint64_t> classify_state;
   OrderBufs ord_dev, ord_grp;
-  DevBuf<uint32_t> tile_hist, bin_total;
-  bool scatter_smem_set = false;  // dynamic shared-memory opt-in of k_radix_scatter<11> done on this device
-  bool scatter_c_smem_set = false;
+  DevBuf<uint32_t> tile_hist;     // K4: [2 orderings][<= 2048 digits][T tiles]
+  DevBuf<uint32_t> bin_total;     // [2 orderings][2048] digit totals
+  bool scatter_smem_set = false;  // dynamic shared-memory opt-in of k_order_scatter<11> done on this device
   size_t last_n = 0;     // records of the last enqueued scan
   size_t last_total = 0; // survivors capacity used by the last scan (sharded: all ranks)
   int last_kind = 0;     // 1 = pci, 2 = mdev
-  bool last_owned = false;  // sharded scan: the orderings cover only the keys this rank owns
   // mdev dictionary
   DevBuf<uint8_t> type_raw, type_label;
   DevBuf<uint32_t> type_off, type_label_len, type_match, type_name_len;
@@ -225,22 +221,23 @@ struct kvg_ctx {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
   std::vector<std::string> ev_names;
   size_t ev_used = 0;
-  // multi-GPU
+  // multi-GPU (kvg_shard.cuh): receive window [ShardCtrl pad 4 KiB][parity][ordering][source][cap records]
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
-  DevBuf<uint64_t> gather_counts;  // [nranks]
-  DevBuf<uint4> local_surv;
-  uint64_t* h_counts = nullptr;  // pinned [nranks]
-  // peer-memory gather (CUDA IPC over NVLink)
-  bool p2p = false;
-  uint8_t* p2p_mine = nullptr;            // [P2PCtrl pad 4 KiB][window 0][window 1]
-  size_t p2p_cap = 0;                     // survivors per region
-  uint8_t* p2p_peer[P2P_MAX_RANKS] = {};  // peer-mapped bases (own entry = p2p_mine)
-  unsigned long long p2p_step = 0;
-  DevBuf<uint32_t> gather_base;
-  DevBuf<uint32_t> p2p_err;
+  bool p2p = false;                      // peer windows imported on every rank: exchange over NVLink stores
+  uint8_t* win_mine = nullptr;           // my window allocation (IPC-exported in p2p mode)
+  size_t win_cap = 0;                    // PCI records per region (an mdev record takes two)
+  uint8_t* win_peer[SH_MAX_RANKS] = {};  // peer-mapped bases (own entry = win_mine)
+  unsigned long long shard_step = 0;
+  DevBuf<uint32_t> shard_cnt;            // [2][P] totals, 2 tickets, 1 error word (64-word header), then [2][P][T] tile counts
+  uint32_t* shard_err = nullptr;         // that error word (device)
+  DevBuf<uint4> owned0, owned1;          // dense owned lists of ordering 0 / 1
+  DevBuf<uint4> gathered;                // NCCL mode: the all-gathered survivor list
+  DevBuf<uint64_t> gather_counts;        // NCCL mode: [nranks + 1]
+  uint64_t* h_counts = nullptr;          // pinned [nranks + 1]
+  int last_units = 1;                    // 16-byte units per record of the last sharded scan
 };
-static const size_t P2P_HDR = 4096;
+static const size_t SH_HDR = 4096;
 
 #define CK(call)                                                                              \
   do {                                                                                        \
@@ -386,51 +383,6 @@ static void* pinned_alloc(kvg_ctx* ctx, size_t size) {
 }
 static inline uint8_t* pinned_payload(void* blk) { return (uint8_t*)blk + 64; }
 
-// grid for the TMA-pipelined classify kernels: co-resident, capped by the tile count
-template <class Op, int ROWS, int STAGES>
-static int classify_grid(kvg_ctx* ctx, size_t n_items, size_t* smem_out) {
-  static int occ = 0;
-  const size_t smem = (size_t)STAGES * KVG_BLOCK * ROWS * Op::REC_BYTES;
-  if (!occ) {
-    cudaFuncSetAttribute(k_classify_tma<Op, ROWS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_classify_tma<Op, ROWS, STAGES>, KVG_BLOCK, smem);
-    if (occ < 1) occ = 1;
-  }
-  *smem_out = smem;
-  size_t tiles = (n_items + (size_t)KVG_BLOCK * ROWS - 1) / ((size_t)KVG_BLOCK * ROWS);
-  size_t g = (size_t)ctx->sm_count * (size_t)occ;
-  if (g > CLASSIFY_MAX_GRID) g = CLASSIFY_MAX_GRID;  // look-back batch covers 32*LB_KMAX CTAs
-  if (tiles < g) g = tiles;
-  return g < 1 ? 1 : (int)g;
-}
-template <class Op, int ROWS, int STAGES>
-static int classify_ws_grid(kvg_ctx* ctx, size_t n_items, size_t* smem_out) {
-  static int occ = 0;
-  const size_t smem = (size_t)STAGES * KVG_BLOCK * ROWS * Op::REC_BYTES;
-  if (!occ) {
-    cudaFuncSetAttribute(k_classify_ws<Op, ROWS, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_classify_ws<Op, ROWS, STAGES>, WS_THREADS, smem);
-    if (occ < 1) occ = 1;
-  }
-  *smem_out = smem;
-  size_t tiles = (n_items + (size_t)KVG_BLOCK * ROWS - 1) / ((size_t)KVG_BLOCK * ROWS);
-  size_t g = (size_t)ctx->sm_count * (size_t)occ;
-  if (g > CLASSIFY_MAX_GRID) g = CLASSIFY_MAX_GRID;
-  if (tiles < g) g = tiles;
-  return g < 1 ? 1 : (int)g;
-}
-constexpr int PCI_ROWS = 4, PCI_STAGES = 4;    // 16 KiB stages, 64 KiB ring -> 3 CTAs / SM
-constexpr int MDEV_ROWS = 2;
-static int classify_variant() {  // KVG_CLASSIFY=tma selects the non-specialised kernel (A/B tests)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("KVG_CLASSIFY");
-    v = (e && !strcmp(e, "tma")) ? 1 : (e && !strcmp(e, "ws")) ? 0 : (e && !strcmp(e, "oneshot4")) ? 3
-        : (e && !strcmp(e, "oneshot")) ? 2 : (e && !strcmp(e, "ragged")) ? 4 : 5;  // 5 = auto
-  }
-  return v;
-}
-
 extern "C" {
 
 int kvg_abi_version(void) { return KVG_ABI_VERSION; }
@@ -458,11 +410,6 @@ int kvg_ctx_create(int cuda_device, kvg_ctx** out) {
     return KVG_ECUDA;
   }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, cuda_device);
-  cudaFuncSetAttribute(k_pciids_parse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM);
-  int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pciids_parse, KVG_BLOCK, P_SMEM);
-  if (occ < 1) occ = 1;
-  ctx->parse_grid = ctx->sm_count * occ;
   if (ensure(ctx, ctx->ctrl, 1) != KVG_OK || cudaMallocHost((void**)&ctx->h_ctrl, sizeof(ScanCtrl)) != cudaSuccess) {
     g_create_error = "control block allocation failed: " + ctx->err;
     kvg_ctx_destroy(ctx);
@@ -479,9 +426,8 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   if (ctx->s_h2d) cudaStreamSynchronize(ctx->s_h2d);
   if (ctx->s_d2h) cudaStreamSynchronize(ctx->s_d2h);
   if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
-  release(ctx->text); release(ctx->tables); release(ctx->info); release(ctx->tile_arrays);
-  release(ctx->parse_state); release(ctx->v2_state); release(ctx->v2_pending); release(ctx->parse_ticket); release(ctx->pool); release(ctx->ctrl);
-  release(ctx->nv_index); release(ctx->nv_lines); release(ctx->sec_lines); release(ctx->type_hash); release(ctx->ragged); release(ctx->tile_count); release(ctx->tile_off);
+  release(ctx->text); release(ctx->dev_off); release(ctx->info); release(ctx->span_sum); release(ctx->pool); release(ctx->ctrl);
+  release(ctx->nv_index); release(ctx->sec_lines); release(ctx->type_hash); release(ctx->ragged); release(ctx->tile_count); release(ctx->tile_off);
   release(ctx->tile_max); release(ctx->offs_state);
   release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist); release(ctx->bin_total);
   for (OrderBufs* o : {&ctx->ord_dev, &ctx->ord_grp}) {
@@ -493,11 +439,11 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   release(ctx->type_canon); release(ctx->type_names); release(ctx->alive_prev);
   release(ctx->changed); release(ctx->flush); release(ctx->nv_ids); release(ctx->probe_slots);
   release(ctx->keys_blob); release(ctx->keys_off); release(ctx->match_off); release(ctx->match_len);
-  release(ctx->match_out); release(ctx->gather_counts); release(ctx->local_surv);
-  release(ctx->gather_base); release(ctx->p2p_err);
-  for (int q = 0; q < P2P_MAX_RANKS; q++)
-    if (ctx->p2p_peer[q] && ctx->p2p_peer[q] != ctx->p2p_mine) cudaIpcCloseMemHandle(ctx->p2p_peer[q]);
-  if (ctx->p2p_mine) cudaFree(ctx->p2p_mine);
+  release(ctx->match_out); release(ctx->gather_counts); release(ctx->gathered);
+  release(ctx->shard_cnt); release(ctx->owned0); release(ctx->owned1);
+  for (int q = 0; q < SH_MAX_RANKS; q++)
+    if (ctx->win_peer[q] && ctx->win_peer[q] != ctx->win_mine) cudaIpcCloseMemHandle(ctx->win_peer[q]);
+  if (ctx->win_mine) cudaFree(ctx->win_mine);
   for (auto& b : ctx->pinned_free) cudaFreeHost(b.p);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_ctrl) cudaFreeHost(ctx->h_ctrl);
@@ -562,215 +508,122 @@ int kvg_kernel_times(kvg_ctx* ctx, float* ms, char* names, size_t names_cap, int
 // ================================================================================================
 size_t kvg_text_pad(size_t len) { return ((len + P_TILE - 1) / P_TILE) * P_TILE + P_HALO; }
 
-static uint32_t table_log2_for(size_t len) {
-  // only the device lines under vendor 10de are inserted (~1 per 800 bytes of the shipped file); a
-  // file that is denser than 1 per 96 bytes trips the overflow / crowding check and is re-parsed
-  // with a table sized from its real entry count (parse_with_regrow)
-  size_t want = len / 96 + 1024;
-  uint32_t l = 10;
-  while (((size_t)1 << l) < want) l++;
-  return l;
-}
-
-// KVG_PARSE=v2: the barrier-free parse of kvg_parse_v2.cuh (experimental, see its header)
-static bool parse_v2_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("KVG_PARSE");
-    return e && strcmp(e, "v2") == 0;
-  }();
-  return on;
-}
-
-static int parse_enqueue_v2(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t stride, uint32_t n_files,
-                            uint32_t cap_log2) {
-  const uint32_t spf = (uint32_t)((len + V2_SPAN - 1) / V2_SPAN);
+// K1 (kvg_parse_k1.cuh) for n_files images: prep -> scan -> resolve + finalize -> names (image 0).
+// Everything is enqueued; nothing here waits for the device.
+static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t stride, uint32_t n_files) {
+  if (len == 0 || len >= 0xfffffff0ull) {
+    ctx->err = "pci.ids length out of range";
+    return KVG_EINVAL;
+  }
+  const uint32_t spf = (uint32_t)((len + K1_SPAN - 1) / K1_SPAN);
   const uint64_t n_spans64 = (uint64_t)spf * n_files;
   if (n_spans64 > 0x7fffffffull) {
     ctx->err = "too many spans";
     return KVG_EINVAL;
   }
   const uint32_t n_spans = (uint32_t)n_spans64;
-  ctx->cap_log2 = cap_log2;
-  const size_t cap = (size_t)1 << cap_log2;
-  ENSURE(ctx->tables, cap * n_files);
+  const size_t pool_bytes = (len + 16 + 15) & ~(size_t)15;
+  ENSURE(ctx->dev_off, (size_t)K1_IDS * n_files);
   ENSURE(ctx->info, n_files);
-  ENSURE(ctx->tile_arrays, 3 * (size_t)n_spans);
-  ENSURE(ctx->v2_state, 2 * (size_t)n_spans);
-  ENSURE(ctx->v2_pending, (size_t)n_spans * V2_PEND_CAP);
-  ParseV2Args A;
+  ENSURE(ctx->span_sum, n_spans);
+  ENSURE(ctx->nv_index, K1_IDS);
+  ENSURE(ctx->pool, pool_bytes);
+  if (!ctx->k1_grid) {
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_pciids_scan, K1_WARPS * 32, K1_SMEM);
+    ctx->k1_grid = ctx->sm_count * (occ < 1 ? 1 : occ);
+  }
+  K1Args A;
   A.text = d_text;
   A.stride = stride;
   A.len = (uint32_t)len;
   A.n_files = n_files;
   A.spans_per_file = spf;
   A.n_spans = n_spans;
-  A.tables = ctx->tables.p;
-  A.cap_mask = (uint32_t)cap - 1;
-  A.cap_shift = 32 - cap_log2;
+  A.dev_off = ctx->dev_off.p;
   A.info = ctx->info.p;
-  A.span_first_hdr = ctx->tile_arrays.p;
-  A.span_first_nl = ctx->tile_arrays.p + n_spans;
-  A.span_last_nl = ctx->tile_arrays.p + 2 * (size_t)n_spans;
-  A.span_state = ctx->v2_state.p;
-  A.pend_cnt = ctx->v2_state.p + n_spans;
-  A.pending = ctx->v2_pending.p;
-  CK(cudaMemsetAsync(ctx->tables.p, 0xff, cap * n_files * sizeof(uint64_t), ctx->stream));  // P_EMPTY
-  CK(cudaMemsetAsync(ctx->info.p, 0, sizeof(PciIdsInfo) * n_files, ctx->stream));
-  CK(cudaMemset2DAsync(ctx->info.p, sizeof(PciIdsInfo), 0xff, sizeof(uint32_t), n_files, ctx->stream));
-  const unsigned grid = (n_spans + V2_WARPS - 1) / V2_WARPS;
-  LAUNCH("pciids_parse", k_pciids_scan_v2, grid, V2_WARPS * 32, 0, A);
-  LAUNCH("pciids_resolve", k_pciids_resolve_v2, grid, V2_WARPS * 32, 0, A);
-  ParseArgs F;  // the finalize kernel reads the span summaries through the tile arrays
-  memset(&F, 0, sizeof F);
-  F.text = d_text;
-  F.stride = stride;
-  F.len = (uint32_t)len;
-  F.n_files = n_files;
-  F.tiles_per_file = spf;
-  F.n_tiles = n_spans;
-  F.info = ctx->info.p;
-  F.tile_first_hdr = A.span_first_hdr;
-  F.tile_first_nl = A.span_first_nl;
-  F.tile_last_nl = A.span_last_nl;
-  LAUNCH("pciids_finalize", k_pciids_finalize_v2, n_files, KVG_BLOCK, 0, F);
-  ENSURE(ctx->nv_index, 65536);
-  ENSURE(ctx->nv_lines, 65536 + 8);
-  CK(cudaMemsetAsync(ctx->nv_lines.p + 65536, 0, sizeof(uint32_t), ctx->stream));
-  LAUNCH("pciids_nv_index", k_nv_index, 256, 256, 0, ctx->tables.p, A.cap_mask, A.cap_shift, ctx->info.p,
-         ctx->nv_index.p, ctx->nv_lines.p, ctx->nv_lines.p + 65536);
-  return check_launch(ctx, "pciids parse (v2)");
-}
-
-static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t stride,
-                         uint32_t n_files, uint32_t cap_log2) {
-  if (len == 0 || len >= 0xfffffff0ull) {
-    ctx->err = "pci.ids length out of range";
-    return KVG_EINVAL;
+  A.span_sum = ctx->span_sum.p;
+  K1PrepArgs P;
+  P.dev_off = (uint4*)ctx->dev_off.p;
+  P.dev_off16 = (uint64_t)K1_IDS * n_files / 4;
+  P.info = ctx->info.p;
+  P.n_files = n_files;
+  P.nv_index = (uint4*)ctx->nv_index.p;
+  P.pool = (uint4*)ctx->pool.p;
+  P.pool16 = (uint32_t)(pool_bytes / 16);
+  {
+    size_t work = std::max<size_t>(P.dev_off16, std::max<size_t>(P.pool16, K1_IDS / 4));
+    unsigned grid = (unsigned)std::min<size_t>((work + KVG_BLOCK - 1) / KVG_BLOCK, (size_t)ctx->sm_count * 8);
+    LAUNCH("pciids_prep", k_pciids_prep, grid ? grid : 1, KVG_BLOCK, 0, P);
   }
-  if (parse_v2_enabled()) return parse_enqueue_v2(ctx, d_text, len, stride, n_files, cap_log2);
-  uint32_t tpf = (uint32_t)((len + P_TILE - 1) / P_TILE);
-  uint64_t n_tiles64 = (uint64_t)tpf * n_files;
-  if (n_tiles64 > 0x7fffffffull) {
-    ctx->err = "too many tiles";
-    return KVG_EINVAL;
+  {
+    unsigned grid = (n_spans + K1_WARPS - 1) / K1_WARPS;
+    if (grid > (unsigned)ctx->k1_grid) grid = (unsigned)ctx->k1_grid;
+    LAUNCH("pciids_parse", k_pciids_scan, grid, K1_WARPS * 32, K1_SMEM, A);
   }
-  uint32_t n_tiles = (uint32_t)n_tiles64;
-  ctx->cap_log2 = cap_log2;
-  size_t cap = (size_t)1 << ctx->cap_log2;
-  ENSURE(ctx->tables, cap * n_files);
-  ENSURE(ctx->info, n_files);
-  ENSURE(ctx->tile_arrays, 3 * (size_t)n_tiles);
-  ENSURE(ctx->parse_state, n_tiles);
-
-  ParseArgs A;
-  A.text = d_text;
-  A.stride = stride;
-  A.len = (uint32_t)len;
-  A.n_files = n_files;
-  A.tiles_per_file = tpf;
-  A.n_tiles = n_tiles;
-  A.tables = ctx->tables.p;
-  A.cap_mask = (uint32_t)cap - 1;
-  A.cap_shift = 32 - ctx->cap_log2;
-  A.info = ctx->info.p;
-  A.tile_first_hdr = ctx->tile_arrays.p;
-  A.tile_first_nl = ctx->tile_arrays.p + n_tiles;
-  A.tile_last_nl = ctx->tile_arrays.p + 2 * (size_t)n_tiles;
-  A.tile_state = ctx->parse_state.p;
-  A.epoch = next_epoch();
-
-  // table slots <- EMPTY, info <- {v_off = NONE, 0...}, ticket <- 0
-  CK(cudaMemsetAsync(ctx->tables.p, 0xff, cap * n_files * sizeof(uint64_t), ctx->stream));  // P_EMPTY
-  CK(cudaMemsetAsync(ctx->info.p, 0, sizeof(PciIdsInfo) * n_files, ctx->stream));
-  CK(cudaMemset2DAsync(ctx->info.p, sizeof(PciIdsInfo), 0xff, sizeof(uint32_t), n_files, ctx->stream));
-  int grid = ctx->parse_grid;
-  if ((uint32_t)grid > n_tiles) grid = (int)n_tiles;
-  LAUNCH("pciids_parse", k_pciids_parse, grid, KVG_BLOCK, P_SMEM, A);
-  LAUNCH("pciids_finalize", k_pciids_finalize, n_files, KVG_BLOCK, 0, A);
-  // flatten the table for vendor 10de: the scans' per-survivor join is then a single load
-  ENSURE(ctx->nv_index, 65536);
-  ENSURE(ctx->nv_lines, 65536 + 8);
-  CK(cudaMemsetAsync(ctx->nv_lines.p + 65536, 0, sizeof(uint32_t), ctx->stream));
-  LAUNCH("pciids_nv_index", k_nv_index, 256, 256, 0, ctx->tables.p, A.cap_mask, A.cap_shift, ctx->info.p,
-         ctx->nv_index.p, ctx->nv_lines.p, ctx->nv_lines.p + 65536);
+  LAUNCH("pciids_resolve", k_pciids_resolve_finalize, n_files + (n_spans + K1_RWARPS - 1) / K1_RWARPS, KVG_BLOCK,
+         K1_RWARPS * K1_STAGE, A);
+  LAUNCH("pciids_names", k_pciids_names, K1_IDS / 32 / KVG_WARPS, KVG_BLOCK, 0, (const uint32_t*)ctx->dev_off.p, d_text,
+         (uint32_t)len, ctx->info.p, ctx->nv_index.p, ctx->pool.p);
+  ctx->sec_lines_ready = false;
   return check_launch(ctx, "pciids parse");
 }
 
-// after the parse of image 0: sanitise the NVIDIA section into the pool and mirror it on the host
+// after the parse of image 0: mirror the section facts and the name pool on the host
 static int table_publish(kvg_ctx* ctx, const uint8_t* d_text, size_t len) {
   CK(cudaMemcpyAsync(&ctx->h_info, ctx->info.p, sizeof(PciIdsInfo), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->d_text = d_text;
   ctx->text_len = (uint32_t)len;
   ctx->h_pool.clear();
+  ctx->sec_lines_ready = false;
   if (ctx->h_info.v_off != P_NONE) {
     size_t sec = (size_t)ctx->h_info.sec_end - ctx->h_info.v_off;
-    ENSURE(ctx->pool, sec + 16);
-    CK(cudaMemsetAsync(ctx->pool.p, 0, sec + 16, ctx->stream));
-    // one warp per named line (<= 65,536 lines; the shipped file has 1,931)
-    LAUNCH("pciids_sanitise", k_pciids_sanitise_lines, 256, KVG_BLOCK, 0, d_text, (uint32_t)len, ctx->info.p,
-           ctx->nv_lines.p, ctx->nv_lines.p + 65536, ctx->pool.p);
-    int rc = check_launch(ctx, "pciids sanitise");
-    if (rc) return rc;
     if (!ctx->h_pool.resize(sec + 16)) {
       ctx->err = "cudaMallocHost failed for the name pool mirror";
       return KVG_ENOMEM;
     }
     CK(cudaMemcpyAsync(ctx->h_pool.data(), ctx->pool.p, sec + 16, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-  } else {
-    ENSURE(ctx->pool, 16);
-  }
-  {  // candidate lines of the general (arbitrary-key) lookup: every '\t' line of the section
-    size_t sec = ctx->h_info.v_off == P_NONE ? 0 : (size_t)ctx->h_info.sec_end - ctx->h_info.v_off;
-    ctx->sec_lines_cap = sec / 2 + 8;  // a line needs >= 2 bytes ("\t\n")
-    ENSURE(ctx->sec_lines, ctx->sec_lines_cap + 1);
-    CK(cudaMemsetAsync(ctx->sec_lines.p + ctx->sec_lines_cap, 0, sizeof(uint32_t), ctx->stream));
-    if (sec) {
-      int grid = (int)((sec + KVG_BLOCK - 1) / KVG_BLOCK);
-      if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
-      LAUNCH("section_lines", k_section_lines, grid, KVG_BLOCK, 0, d_text, ctx->info.p, ctx->sec_lines.p,
-             ctx->sec_lines.p + ctx->sec_lines_cap, (uint32_t)ctx->sec_lines_cap);
-      int rc = check_launch(ctx, "section lines");
-      if (rc) return rc;
-    }
   }
   ctx->table_ready = true;
   return KVG_OK;
 }
 
-// The table is sized from the text length (pci.ids has ~1 device line per 77 bytes); an input with
-// denser device lines overflows it, which K1 reports instead of spinning: re-parse with a table
-// sized from the line count until the load factor is sane.
-static int parse_with_regrow(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t stride,
-                             uint32_t n_files, bool enqueued = false, uint32_t cap_log2 = 0) {
-  if (!enqueued) cap_log2 = table_log2_for(len);
-  for (;;) {
-    if (!enqueued) {
-      int rc = parse_enqueue(ctx, d_text, len, stride, n_files, cap_log2);
-      if (rc) return rc;
-    }
-    enqueued = false;
-    int rc = table_publish(ctx, d_text, len);
+// candidate lines of the general (arbitrary-key) lookup: every '\t' line of the section, collected on
+// the first general lookup after a table load (most loads are never followed by one)
+static int ensure_section_lines(kvg_ctx* ctx) {
+  if (ctx->sec_lines_ready) return KVG_OK;
+  size_t sec = ctx->h_info.v_off == P_NONE ? 0 : (size_t)ctx->h_info.sec_end - ctx->h_info.v_off;
+  ctx->sec_lines_cap = sec / 2 + 8;  // a line needs >= 2 bytes ("\t\n")
+  ENSURE(ctx->sec_lines, ctx->sec_lines_cap + 1);
+  CK(cudaMemsetAsync(ctx->sec_lines.p + ctx->sec_lines_cap, 0, sizeof(uint32_t), ctx->stream));
+  if (sec) {
+    int grid = (int)((sec + KVG_BLOCK - 1) / KVG_BLOCK);
+    if (grid > ctx->sm_count * 8) grid = ctx->sm_count * 8;
+    LAUNCH("section_lines", k_section_lines, grid, KVG_BLOCK, 0, ctx->d_text, ctx->info.p, ctx->sec_lines.p,
+           ctx->sec_lines.p + ctx->sec_lines_cap, (uint32_t)ctx->sec_lines_cap);
+    int rc = check_launch(ctx, "section lines");
     if (rc) return rc;
-    size_t cap = (size_t)1 << cap_log2;
-    bool crowded = (size_t)ctx->h_info.n_entries * 10 > cap * 5;
-    if (!ctx->h_info.overflow && !crowded) return KVG_OK;
-    ctx->table_ready = false;
-    if (cap_log2 >= 30) {
-      ctx->err = "pci.ids hash table cannot grow further";
-      return KVG_ENOMEM;
-    }
-    size_t want = ctx->h_info.overflow ? cap * 4 : (size_t)ctx->h_info.n_entries * 4;
-    while (((size_t)1 << cap_log2) < want) cap_log2++;
   }
+  ctx->sec_lines_ready = true;
+  return KVG_OK;
+}
+
+static int parse_and_publish(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t stride, uint32_t n_files,
+                             bool enqueued = false) {
+  if (!enqueued) {
+    int rc = parse_enqueue(ctx, d_text, len, stride, n_files);
+    if (rc) return rc;
+  }
+  return table_publish(ctx, d_text, len);
 }
 
 // complete a pending kvg_pciids_load (see load_pending), then require a published table
 static int table_needed(kvg_ctx* ctx, const char* why_missing) {
   if (ctx->load_pending) {
     ctx->load_pending = false;
-    int rc = parse_with_regrow(ctx, ctx->text.p, ctx->pend_len, ctx->pend_stride, 1, true, ctx->pend_cap_log2);
+    int rc = parse_and_publish(ctx, ctx->text.p, ctx->pend_len, ctx->pend_stride, 1, true);
     if (rc) return rc;
   }
   if (!ctx->table_ready) {
@@ -787,14 +640,23 @@ int kvg_pciids_load(kvg_ctx* ctx, const uint8_t* text, size_t len) {
   ctx->load_pending = false;
   if (len == 0) {  // an empty file: locateVendor fails, every lookup is "" (:382-385)
     ENSURE(ctx->info, 1);
-    ENSURE(ctx->tables, 1024);
-    ctx->cap_log2 = 10;
-    LAUNCH("table_clear", k_fill64, 4, KVG_BLOCK, 0, ctx->tables.p, (size_t)1024, P_EMPTY);
+    ENSURE(ctx->dev_off, K1_IDS);
+    ENSURE(ctx->nv_index, K1_IDS);
+    ENSURE(ctx->pool, 16);
+    ENSURE(ctx->text, 64);
+    K1PrepArgs P;
+    P.dev_off = (uint4*)ctx->dev_off.p;
+    P.dev_off16 = K1_IDS / 4;
+    P.info = ctx->info.p;
+    P.n_files = 1;
+    P.nv_index = (uint4*)ctx->nv_index.p;
+    P.pool = (uint4*)ctx->pool.p;
+    P.pool16 = 1;
+    LAUNCH("pciids_prep", k_pciids_prep, 64, KVG_BLOCK, 0, P);
     PciIdsInfo z;
     memset(&z, 0, sizeof z);
     z.v_off = z.sec_end = P_NONE;
     CK(cudaMemcpyAsync(ctx->info.p, &z, sizeof z, cudaMemcpyHostToDevice, ctx->stream));
-    ENSURE(ctx->text, 64);
     return table_publish(ctx, ctx->text.p, 0);
   }
   size_t padded = kvg_text_pad(len);
@@ -804,17 +666,15 @@ int kvg_pciids_load(kvg_ctx* ctx, const uint8_t* text, size_t len) {
   // asynchronously (the caller keeps it alive until the next consuming call, as with any cudaMemcpyAsync
   // source), pageable memory is copied synchronously by the runtime's own staging
   CK(cudaMemcpyAsync(ctx->text.p, text, len, cudaMemcpyHostToDevice, ctx->stream));
-  const uint32_t cap_log2 = table_log2_for(len);
-  int rc = parse_enqueue(ctx, ctx->text.p, len, padded, 1, cap_log2);
+  int rc = parse_enqueue(ctx, ctx->text.p, len, padded, 1);
   if (rc) return rc;
   cudaPointerAttributes attr;
   bool pinned = cudaPointerGetAttributes(&attr, text) == cudaSuccess && attr.type == cudaMemoryTypeHost;
   cudaGetLastError();
-  if (!pinned) return parse_with_regrow(ctx, ctx->text.p, len, padded, 1, true, cap_log2);
+  if (!pinned) return parse_and_publish(ctx, ctx->text.p, len, padded, 1, true);
   ctx->load_pending = true;
   ctx->pend_len = len;
   ctx->pend_stride = padded;
-  ctx->pend_cap_log2 = cap_log2;
   return KVG_OK;
 }
 
@@ -823,25 +683,21 @@ int kvg_dev_pciids_parse(kvg_ctx* ctx, const void* d_text, size_t len, size_t st
       (n_files > 1 && stride < kvg_text_pad(len)))
     return KVG_EINVAL;
   CK(cudaSetDevice(ctx->device));
-  // first call on an image publishes (host mirror of the name pool, table sizing); later calls on
-  // the same image stay fully asynchronous: parse + finalize + sanitise enqueued, no host sync
+  // first call on an image publishes (host mirror of the section facts and the name pool); later calls on
+  // the same image stay fully asynchronous: the whole K1 chain enqueued, no host sync
   if (ctx->load_pending) {
     int rc_t = table_needed(ctx, "");
     if (rc_t && rc_t != KVG_ESTATE) return rc_t;
   }
   if (!ctx->table_ready || ctx->d_text != d_text || ctx->text_len != len || ctx->parsed_files != n_files) {
-    int rc0 = parse_with_regrow(ctx, (const uint8_t*)d_text, len, stride, n_files);
+    int rc0 = parse_and_publish(ctx, (const uint8_t*)d_text, len, stride, n_files);
     if (rc0 == KVG_OK) ctx->parsed_files = n_files;
     return rc0;
   }
-  int rc = parse_enqueue(ctx, (const uint8_t*)d_text, len, stride, n_files, ctx->cap_log2);
-  if (rc) return rc;
-  size_t sec = ctx->h_pool.size();
-  if (sec > 16) {
-    LAUNCH("pciids_sanitise", k_pciids_sanitise_lines, 256, KVG_BLOCK, 0, (const uint8_t*)d_text, (uint32_t)len,
-           ctx->info.p, ctx->nv_lines.p, ctx->nv_lines.p + 65536, ctx->pool.p);
-  }
-  return check_launch(ctx, "pciids sanitise");
+  const bool lines_ready = ctx->sec_lines_ready;
+  int rc = parse_enqueue(ctx, (const uint8_t*)d_text, len, stride, n_files);
+  ctx->sec_lines_ready = lines_ready;  // same image: a candidate list collected for it stays valid
+  return rc;
 }
 
 int kvg_pciids_info(kvg_ctx* ctx, uint32_t* vendor_off, uint32_t* section_end, uint32_t* n_entries,
@@ -882,6 +738,10 @@ static int lookup_general(kvg_ctx* ctx, const uint8_t* d_keys, const uint32_t* d
                           uint32_t* d_match) {
   if (n_keys == 0) return KVG_OK;
   {
+    int rc_s = ensure_section_lines(ctx);
+    if (rc_s) return rc_s;
+  }
+  {
     int grid = (int)((n_keys + KVG_BLOCK - 1) / KVG_BLOCK);
     LAUNCH("match_clear", k_fill32, grid, KVG_BLOCK, 0, d_match, (size_t)n_keys, P_NONE);
   }
@@ -911,12 +771,9 @@ int kvg_name_lookup(kvg_ctx* ctx, const char* key, size_t keylen, char* out, siz
   CK(cudaSetDevice(ctx->device));
   *outlen = 0;
   uint32_t v;
-  if (canonical_key(key, keylen, &v)) {  // hash path
-    ENSURE(ctx->probe_slots, 1);
-    LAUNCH("probe_keys", k_probe_keys, 1, 32, 0, ctx->tables.p, (1u << ctx->cap_log2) - 1,
-           32 - ctx->cap_log2, ctx->info.p, v, 1u, ctx->probe_slots.p);
+  if (canonical_key(key, keylen, &v)) {  // table path: the id's slot, then the host mirror of the name pool
     uint32_t slot;
-    CK(cudaMemcpyAsync(&slot, ctx->probe_slots.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&slot, ctx->nv_index.p + v, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (slot == P_NONE) return KVG_OK;
     size_t n = ctx->h_pool[slot] | ((size_t)ctx->h_pool[slot + 1] << 8);
@@ -962,11 +819,8 @@ int kvg_name_table(kvg_ctx* ctx, uint32_t first, uint32_t count, uint32_t* out_o
   CK(cudaSetDevice(ctx->device));
   out_off[0] = 0;
   if (count == 0) return KVG_OK;
-  ENSURE(ctx->probe_slots, count);
-  LAUNCH("probe_keys", k_probe_keys, (count + 255) / 256, 256, 0, ctx->tables.p,
-         (1u << ctx->cap_log2) - 1, 32 - ctx->cap_log2, ctx->info.p, first, count, ctx->probe_slots.p);
   std::vector<uint32_t> slots(count);
-  CK(cudaMemcpyAsync(slots.data(), ctx->probe_slots.p, 4 * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(slots.data(), ctx->nv_index.p + first, 4 * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   size_t o = 0;
   for (uint32_t i = 0; i < count; i++) {
@@ -1006,15 +860,25 @@ static int ensure_order(kvg_ctx* ctx, OrderBufs& o, size_t cap) {
   ENSURE(o.p0, cap + 1); ENSURE(o.p1, cap + 1); ENSURE(o.perm, cap + 1);
   ENSURE(o.seg_key, cap + 1); ENSURE(o.seg_off, cap + 2); ENSURE(o.seg_name, cap + 1);
   ENSURE(o.tile_heads, T + 1); ENSURE(o.tile_off, T + 2);
-  ENSURE(o.heads_state, T / C_TILE + 2);
+  ENSURE(o.heads_state, T + 2);
   return KVG_OK;
 }
 
 }  // extern "C"
-// Both stable orderings of the survivor list — ordering 0 by device id / mdev type (<= 16 bits,
-// 2 passes), ordering 1 by iommu group / parent (32 bits, up to 4 passes) — share their launches:
-// grid.y = 2 while both have a pass, grid.y = 1 (ordering 1 only, passed in slot 0) afterwards.
-static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1, bool owned_only = false) {
+
+// Both stable orderings of the survivor list — ordering 0 by device id / mdev type (<= 16 bits, 2 passes),
+// ordering 1 by iommu group / parent (32 bits, up to 4 passes) — share their launches: grid.y = 2 while
+// both have a pass, grid.y = 1 (ordering 1 only, passed in slot 0) afterwards.  The host always enqueues
+// the launch sets a 32-bit key could need; a set whose pass does not exist for the keys at hand returns at
+// once (small persistent grid).
+struct OrdInput {
+  const void* recs[2];     // record list each ordering reads its pass-0 keys from
+  uint32_t* cnt[2];        // its length (device)
+  int src[2];              // SRC_*
+  uint32_t* max_key[2];    // its largest key (device): decides the digit plan
+  const uint4* head_surv;  // PCI device-id ordering: records whose name slot the segment heads publish (or NULL)
+};
+static int enqueue_orderings(kvg_ctx* ctx, size_t cap, const OrdInput& in) {
   int rc = ensure_order(ctx, ctx->ord_dev, cap);
   if (rc) return rc;
   rc = ensure_order(ctx, ctx->ord_grp, cap);
@@ -1025,72 +889,41 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1, bool 
   ENSURE(ctx->bin_total, 2 * (size_t)RADIX_MAX_DIGITS);
   ScanCtrl* c = ctx->ctrl.p;
   OrderBufs* ob[2] = {&ctx->ord_dev, &ctx->ord_grp};
-  uint32_t* maxk[2] = {&c->max_devkey, &c->max_group};
-  // element count per ordering: all survivors, or (sharded) the survivors whose key this rank owns
-  uint32_t* cnt[2] = {owned_only ? &c->n_own[0] : &c->n_surv, owned_only ? &c->n_own[1] : &c->n_surv};
-  if (owned_only && cap) {
-    // select the owned {key, index} pairs of each ordering into p1 (pass 0 then reads pairs)
-    constexpr int TT = 128, RR = 8;
-    const size_t tiles = (cap + (size_t)TT * RR - 1) / ((size_t)TT * RR);
-    ENSURE(ctx->ragged, tiles * TT * RR);  // as uint2 this needs half of it
-    ENSURE(ctx->tile_count, tiles + 1);
-    ENSURE(ctx->tile_off, tiles + 2);
-    ENSURE(ctx->tile_max, tiles + 1);
-    const unsigned chunks = (unsigned)((tiles + C_TILE - 1) / C_TILE);
-    ENSURE(ctx->offs_state, (size_t)chunks + 1);
-    for (int ord = 0; ord < 2; ord++) {
-      OwnedPairOp op;
-      op.surv = ctx->surv.p;
-      op.n_ptr = &c->n_surv;  // launches are sized for `cap`; tiles past the count retire at once
-      op.out = (uint2*)ctx->ragged.p;
-      op.field = (uint32_t)ord;
-      op.nranks = (uint32_t)ctx->nranks;
-      op.rank = (uint32_t)ctx->rank;
-      op.local_max = 0;
-      LAUNCH("own_select", (k_classify_ragged<OwnedPairOp, TT, RR>), (unsigned)tiles, TT, 0, op, ctx->tile_count.p,
-             ctx->tile_max.p);
-      TileOffsetsArgs2 tt;
-      tt.o[0] = {ctx->tile_count.p, ctx->tile_max.p, nullptr, (uint32_t)tiles, ctx->tile_off.p, cnt[ord],
-                 ctx->offs_state.p};
-      tt.o[1] = tt.o[0];
-      LAUNCH("tile_offsets", k_tile_offsets, chunks, KVG_BLOCK, 0, tt, c, next_epoch());
-      LAUNCH("own_pack", k_pack_pairs, (unsigned)tiles, 128, 0, (const uint2*)ctx->ragged.p, ctx->tile_off.p,
-             (uint32_t)(TT * RR), ob[ord]->p1.p);
-    }
-  }
+  uint32_t* const* maxk = in.max_key;
+  uint32_t* const* cnt = in.cnt;
   const uint32_t key_bits[2] = {16, 32};  // device id / mdev type: u16; iommu group / parent: u32
-  const int srcs[2] = {src0, src1};
   // digit width: up to 11 bits where the scan is latency-bound (fewer passes: 19-bit groups sort in 2),
-  // 8 bits for inputs large enough to be bandwidth-bound (half the shared memory, twice the CTAs/SM)
-  const uint32_t max_bits = cap >= (8u << 20) ? 8 : RADIX_MAX_BITS;
+  // 8 bits for inputs large enough to be bandwidth-bound (half the shared memory, more CTAs/SM)
+  const bool big = cap >= (8u << 20);
+  const uint32_t max_bits = big ? 8 : RADIX_MAX_BITS;
   const int nsets[2] = {(int)((key_bits[0] + max_bits - 1) / max_bits),
                         (int)((key_bits[1] + max_bits - 1) / max_bits)};  // 2 and 3 (or 4) launch sets
   auto fill = [&](int ord, int p) {
-    RadixArgs a;
+    OrdArgs a;
     a.n_ptr = cnt[ord];
     a.max_key = maxk[ord];
-    a.src_records = ctx->surv.p;
-    a.pairs_in = (p == 0 && !owned_only) ? nullptr : ((p & 1) ? ob[ord]->p0.p : ob[ord]->p1.p);
+    a.src_records = in.recs[ord];
+    a.pairs_in = p == 0 ? nullptr : ((p & 1) ? ob[ord]->p0.p : ob[ord]->p1.p);
     a.pairs_out = (p & 1) ? ob[ord]->p1.p : ob[ord]->p0.p;
     a.tile_hist = ctx->tile_hist.p + (size_t)ord * RADIX_MAX_DIGITS * T;
     a.bin_total = ctx->bin_total.p + (size_t)ord * RADIX_MAX_DIGITS;
     a.pass = p < nsets[ord] ? (uint32_t)p : 0xffu;
     a.key_bits_max = key_bits[ord];
     a.max_bits = max_bits;
-    a.src = (p == 0 && !owned_only) ? srcs[ord] : SRC_PAIRS;
+    a.src = p == 0 ? in.src[ord] : SRC_PAIRS;
     return a;
   };
   if (!ctx->scatter_smem_set) {  // a function attribute is per device: remember it per context
-    CK(cudaFuncSetAttribute(k_radix_scatter<RADIX_MAX_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            (int)RadixScatterCfg<RADIX_MAX_BITS>::SMEM));
+    CK(cudaFuncSetAttribute(k_order_scatter<RADIX_MAX_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)OrdScatterCfg<RADIX_MAX_BITS>::SMEM));
     ctx->scatter_smem_set = true;
   }
   for (int p = 0; p < nsets[1]; p++) {
-    RadixArgs2 aa;
-    // sets 0/1 always have work: one CTA per tile.  Set 2 exists only for keys wider than 22 bits and is
-    // usually ruled out on the device: a small persistent grid makes a ruled-out pass nearly free.
+    OrdArgs2 aa;
+    // sets 0/1 always have work: one CTA per tile.  Later sets exist only for wide keys and are usually
+    // ruled out on the device: a small persistent grid makes a ruled-out pass nearly free.
     const bool both = p < nsets[0];
-    const unsigned gx = p < 2 ? (unsigned)T : (unsigned)std::min<size_t>(T, (size_t)ctx->sm_count * (max_bits == 8 ? 5 : 3));
+    const unsigned gx = p < 2 ? (unsigned)T : (unsigned)std::min<size_t>(T, (size_t)ctx->sm_count * (big ? 5 : 3));
     dim3 grid(gx, both ? 2 : 1);
     if (both) {
       aa.o[0] = fill(0, p);
@@ -1099,41 +932,25 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1, bool 
       aa.o[0] = fill(1, p);
       aa.o[1] = aa.o[0];
     }
-    dim3 sgrid(KVG_BLOCK, grid.y);
-    LAUNCH("radix_hist", k_radix_hist, grid, KVG_BLOCK, 0, aa);
-    static const bool tilescan_warp = [] {  // KVG_TILESCAN=warp: experimental, see kvg_radix_exp.cuh
-      const char* e = getenv("KVG_TILESCAN");
-      return e && strcmp(e, "warp") == 0;
-    }();
-    if (tilescan_warp) {
-      dim3 wgrid(RADIX_MAX_DIGITS / TS_WARPS, grid.y);
-      LAUNCH("radix_tilescan", k_radix_tilescan_warp, wgrid, TS_WARPS * 32, 0, aa);
+    LAUNCH("order_hist", k_order_hist, grid, KVG_BLOCK, 0, aa);
+    if (T > 2048) {
+      dim3 sgrid(1u << max_bits, grid.y);
+      LAUNCH("order_tilescan", k_order_tilescan_long, sgrid, KVG_BLOCK, 0, aa);
     } else {
-      LAUNCH("radix_tilescan", k_radix_tilescan, sgrid, KVG_BLOCK, 0, aa);
+      dim3 sgrid((1u << max_bits) / TS_WARPS, grid.y);
+      LAUNCH("order_tilescan", k_order_tilescan, sgrid, TS_WARPS * 32, 0, aa);
     }
-    static const bool scatter_c = [] {  // KVG_SCATTER=c: experimental, see kvg_radix_exp.cuh
-      const char* e = getenv("KVG_SCATTER");
-      return e && strcmp(e, "c") == 0;
-    }();
-    if (max_bits == 8) {
-      LAUNCH("radix_scatter", k_radix_scatter<8>, grid, KVG_BLOCK, RadixScatterCfg<8>::SMEM, aa);
-    } else if (scatter_c) {
-      if (!ctx->scatter_c_smem_set) {
-        CK(cudaFuncSetAttribute(k_radix_scatter_c, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)RadixScatterCfg<RADIX_MAX_BITS>::SMEM));
-        ctx->scatter_c_smem_set = true;
-      }
-      LAUNCH("radix_scatter", k_radix_scatter_c, grid, KVG_BLOCK, RadixScatterCfg<RADIX_MAX_BITS>::SMEM, aa);
-    } else {
-      LAUNCH("radix_scatter", k_radix_scatter<RADIX_MAX_BITS>, grid, KVG_BLOCK, RadixScatterCfg<RADIX_MAX_BITS>::SMEM, aa);
-    }
+    if (big)
+      LAUNCH("order_scatter", k_order_scatter<8>, grid, KVG_BLOCK, OrdScatterCfg<8>::SMEM, aa);
+    else
+      LAUNCH("order_scatter", k_order_scatter<RADIX_MAX_BITS>, grid, KVG_BLOCK, OrdScatterCfg<RADIX_MAX_BITS>::SMEM, aa);
   }
-  // final permutation + distinct keys of both orderings: count heads per tile, scan, emit
-  OrderFinalArgs2 ff;
+  // final permutation + distinct keys of both orderings
+  OrdFinalArgs2 ff;
   TileOffsetsArgs2 tt;
   uint32_t* nseg[2] = {&c->n_dev_keys, &c->n_groups};
   for (int ord = 0; ord < 2; ord++) {
-    OrderFinalArgs& a = ff.o[ord];
+    OrdFinalArgs& a = ff.o[ord];
     a.p0 = ob[ord]->p0.p;
     a.p1 = ob[ord]->p1.p;
     a.max_key = maxk[ord];
@@ -1141,13 +958,14 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1, bool 
     a.max_bits = max_bits;
     a.n_ptr = cnt[ord];
     a.perm = ob[ord]->perm.p;
+    a.state = ob[ord]->heads_state.p;
     a.tile_heads = ob[ord]->tile_heads.p;
     a.tile_off = ob[ord]->tile_off.p;
     a.seg_key = ob[ord]->seg_key.p;
     a.seg_off = ob[ord]->seg_off.p;
     a.n_seg = nseg[ord];
     // PCI device-id ordering: the bucket's joined name slot comes back with the keys
-    a.head_surv = (ord == 0 && src0 == SRC_PCI_DEVICE) ? ctx->surv.p : nullptr;
+    a.head_surv = ord == 0 ? in.head_surv : nullptr;
     a.head_name = a.head_surv ? ob[ord]->seg_name.p : nullptr;
     TileOffsetsArgs& t = tt.o[ord];
     t.tile_count = ob[ord]->tile_heads.p;
@@ -1159,43 +977,44 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, int src0, int src1, bool 
     t.state = ob[ord]->heads_state.p;
   }
   dim3 fgrid((unsigned)T, 2);
-  LAUNCH("order_count", k_order_final<false>, fgrid, KVG_BLOCK, 0, ff);
-  dim3 ogrid((unsigned)((T + C_TILE - 1) / C_TILE), 2);
-  LAUNCH("tile_offsets", k_tile_offsets, ogrid, KVG_BLOCK, 0, tt, c, next_epoch());
-  LAUNCH("order_emit", k_order_final<true>, fgrid, KVG_BLOCK, 0, ff);
+  if (cap < (2u << 20)) {  // latency-bound: one launch (chained scan of the head counts)
+    LAUNCH("order_final", k_order_final, fgrid, KVG_BLOCK, 0, ff, next_epoch());
+  } else {                 // bandwidth-bound: no CTA waits for another
+    LAUNCH("order_count", k_order_heads<false>, fgrid, KVG_BLOCK, 0, ff);
+    dim3 ogrid((unsigned)((T + C_TILE - 1) / C_TILE), 2);
+    LAUNCH("tile_offsets", k_tile_offsets, ogrid, KVG_BLOCK, 0, tt, c, next_epoch());
+    LAUNCH("order_emit", k_order_heads<true>, fgrid, KVG_BLOCK, 0, ff);
+  }
   return check_launch(ctx, "orderings");
 }
 
-static int enqueue_pci_orderings(kvg_ctx* ctx, size_t surv_cap, bool owned_only = false) {
-  return enqueue_orderings(ctx, surv_cap, SRC_PCI_DEVICE, SRC_PCI_GROUP, owned_only);
+static int enqueue_pci_orderings(kvg_ctx* ctx, size_t surv_cap) {
+  ScanCtrl* c = ctx->ctrl.p;
+  OrdInput in = {{ctx->surv.p, ctx->surv.p}, {&c->n_surv, &c->n_surv}, {SRC_PCI_DEVICE, SRC_PCI_GROUP},
+                 {&c->max_devkey, &c->max_group}, ctx->surv.p};
+  return enqueue_orderings(ctx, surv_cap, in);
 }
 
+// K3 into d_out (dense, Walk order).  Below ~2 M records the step is launch-bound and ONE look-back kernel
+// beats the three launches of the split form; above, the split form (no cross-CTA wait) runs at the HBM
+// roofline.
 static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d_out) {
-  const size_t pci_tiles = (n + (size_t)KVG_BLOCK * PCI_ROWS - 1) / ((size_t)KVG_BLOCK * PCI_ROWS) + 1;
-  ENSURE(ctx->classify_state, 2 * pci_tiles + n / 512 + 2);  // aggregates + round prefixes / per-tile states
   PciClassifyOp op;
   op.recs = (const uint4*)d_recs;
   op.n = (uint32_t)n;
   op.out = (kvg_pci_surv*)d_out;
   op.ctrl = ctx->ctrl.p;
-  op.table = ctx->tables.p;
-  op.cap_mask = (1u << ctx->cap_log2) - 1;
-  op.cap_shift = 32 - ctx->cap_log2;
-  op.info = ctx->info.p;
   op.nv_index = ctx->nv_index.p;
   op.local_max_group = 0;
   op.local_max_dev = 0;
-  size_t smem = 0;
-  // auto: below ~2 M records the step is launch-bound and ONE look-back kernel beats the three
-  // launches of the split form; above, the split form (no cross-CTA wait) runs at the HBM roofline
-  int variant = classify_variant();
-  if (variant == 5) variant = n < (2u << 20) ? 2 : 4;
-  if (variant == 4) {
-    constexpr int T = 128, R = 8;
-    const size_t tiles = (n + (size_t)T * R - 1) / ((size_t)T * R);
-    if (tiles == 0) {  // nothing to classify: n_surv stays 0 from the control-block memset
-      return KVG_OK;
-    }
+  constexpr int T = 128, R = 8;
+  const size_t tiles = (n + (size_t)T * R - 1) / ((size_t)T * R);
+  if (tiles == 0) return KVG_OK;  // nothing to classify: n_surv stays 0 from the control-block memset
+  if (n < (2u << 20)) {
+    ENSURE(ctx->classify_state, tiles + 2);
+    LAUNCH("classify_compact", (k_classify_oneshot<PciClassifyOp, T, R>), (unsigned)tiles, T, 0, op,
+           ctx->classify_state.p, next_epoch());
+  } else {
     ENSURE(ctx->ragged, tiles * T * R);
     ENSURE(ctx->tile_count, tiles + 1);
     ENSURE(ctx->tile_off, tiles + 2);
@@ -1212,28 +1031,8 @@ static int enqueue_classify(kvg_ctx* ctx, const void* d_recs, size_t n, uint4* d
       tt.o[1] = tt.o[0];
       LAUNCH("tile_offsets", k_tile_offsets, chunks, KVG_BLOCK, 0, tt, ctx->ctrl.p, next_epoch());
     }
-    LAUNCH("pack_survivors", k_pack_survivors<1>, (unsigned)tiles, 128, 0, ctx->ragged.p, ctx->tile_off.p,
-           (uint32_t)(T * R), d_out);
-  } else if (variant >= 2) {  // one tile per CTA with look-back
-    if (variant == 2) {
-      constexpr int T = 128, R = 8;
-      size_t tiles = (n + (size_t)T * R - 1) / ((size_t)T * R);
-      LAUNCH("classify_compact", (k_classify_oneshot<PciClassifyOp, T, R>), (unsigned)(tiles ? tiles : 1), T, 0, op,
-             ctx->classify_state.p, next_epoch());
-    } else {
-      constexpr int T = 128, R = 4;
-      size_t tiles = (n + (size_t)T * R - 1) / ((size_t)T * R);
-      LAUNCH("classify_compact", (k_classify_oneshot<PciClassifyOp, T, R>), (unsigned)(tiles ? tiles : 1), T, 0, op,
-             ctx->classify_state.p, next_epoch());
-    }
-  } else if (variant == 1) {
-    int grid = classify_grid<PciClassifyOp, PCI_ROWS, PCI_STAGES>(ctx, n, &smem);
-    LAUNCH("classify_compact", (k_classify_tma<PciClassifyOp, PCI_ROWS, PCI_STAGES>), grid, KVG_BLOCK, smem, op,
-           ctx->classify_state.p, ctx->classify_state.p + pci_tiles, next_epoch());
-  } else {
-    int grid = classify_ws_grid<PciClassifyOp, PCI_ROWS, PCI_STAGES>(ctx, n, &smem);
-    LAUNCH("classify_compact", (k_classify_ws<PciClassifyOp, PCI_ROWS, PCI_STAGES>), grid, WS_THREADS, smem, op,
-           ctx->classify_state.p, ctx->classify_state.p + pci_tiles, next_epoch());
+    LAUNCH("pack_survivors", k_pack_survivors<1>, (unsigned)tiles, 128, 0, (const uint4*)ctx->ragged.p,
+           (const uint32_t*)ctx->tile_off.p, (uint32_t)(T * R), d_out);
   }
   return check_launch(ctx, "classify");
 }
@@ -1256,7 +1055,6 @@ int kvg_dev_scan_pci(kvg_ctx* ctx, const void* d_recs, size_t n) {
   ctx->last_n = n;
   ctx->last_total = n;
   ctx->last_kind = 1;
-  ctx->last_owned = false;
   return KVG_OK;
 }
 
@@ -1290,9 +1088,7 @@ static int fetch_pci(kvg_ctx* ctx, kvg_pci_result** res, void* blk, size_t surv_
   const bool surv_done = blk != nullptr;
   const size_t S = ctx->h_ctrl->n_surv, KD = ctx->h_ctrl->n_dev_keys, G = ctx->h_ctrl->n_groups;
   if (!surv_done) surv_reserve = S;
-  // members covered by each ordering: all survivors, or (sharded) those whose key this rank owns
-  const size_t SD = ctx->last_owned ? ctx->h_ctrl->n_own[0] : S;
-  const size_t SG = ctx->last_owned ? ctx->h_ctrl->n_own[1] : S;
+  const size_t SD = S, SG = S;
   const size_t pool_len = ctx->h_pool.size();
   size_t o = align64(sizeof(kvg_pci_result));  // header first
   size_t o_surv = o; o += align64(surv_reserve * 16);
@@ -1486,10 +1282,6 @@ static int scan_pci_pipelined(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, k
   CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
   PciClassifyOp op;
   op.ctrl = ctx->ctrl.p;
-  op.table = ctx->tables.p;
-  op.cap_mask = (1u << ctx->cap_log2) - 1;
-  op.cap_shift = 32 - ctx->cap_log2;
-  op.info = ctx->info.p;
   op.nv_index = ctx->nv_index.p;
   op.local_max_group = 0;
   op.local_max_dev = 0;
@@ -1524,7 +1316,6 @@ static int scan_pci_pipelined(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, k
   ctx->last_n = n;
   ctx->last_total = n;
   ctx->last_kind = 1;
-  ctx->last_owned = false;
   TRACE("enqueued");
   // survivors go home chunk by chunk while later chunks and the orderings still run
   size_t prev = 0;
@@ -1669,8 +1460,9 @@ __global__ void k_pack_labels(const uint8_t* __restrict__ label, const uint32_t*
 
 extern "C" {
 
-int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type_dict* types) {
-  if (!ctx || !types || (!d_recs && n) || n > 0xfffffff0ull || ((uintptr_t)d_recs & 15)) return KVG_EINVAL;
+// K5 up to the dense survivor list (ctx->surv, 2 x 16 bytes per mdev): type dictionary (labels, canonical
+// ids, the resource-name join of every label) + classification + stable compaction
+static int mdev_classify(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type_dict* types) {
   {
     int rc_t = table_needed(ctx, "kvg_pciids_load must precede a scan (the scan joins names)");
     if (rc_t) return rc_t;
@@ -1692,8 +1484,6 @@ int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type
     if (rc) return rc;
   }
   ENSURE(ctx->surv, 2 * (n + 1));
-  const size_t mdev_tiles = (n + (size_t)KVG_BLOCK * MDEV_ROWS - 1) / ((size_t)KVG_BLOCK * MDEV_ROWS) + 1;
-  ENSURE(ctx->classify_state, 2 * mdev_tiles);
   CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
   MdevClassifyOp op;
   op.recs = (const uint4*)d_recs;
@@ -1725,13 +1515,23 @@ int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type
         tt.o[1] = tt.o[0];
         LAUNCH("tile_offsets", k_tile_offsets, chunks, KVG_BLOCK, 0, tt, ctx->ctrl.p, next_epoch());
       }
-      LAUNCH("pack_survivors", k_pack_survivors<2>, (unsigned)tiles, 128, 0, ctx->ragged.p, ctx->tile_off.p,
-             (uint32_t)(T * R), dense);
+      LAUNCH("pack_survivors", k_pack_survivors<2>, (unsigned)tiles, 128, 0, (const uint4*)ctx->ragged.p,
+             (const uint32_t*)ctx->tile_off.p, (uint32_t)(T * R), dense);
     }
   }
-  rc = check_launch(ctx, "mdev classify");
+  return check_launch(ctx, "mdev classify");
+}
+
+int kvg_dev_scan_mdev(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type_dict* types) {
+  if (!ctx || !types || (!d_recs && n) || n > 0xfffffff0ull || ((uintptr_t)d_recs & 15)) return KVG_EINVAL;
+  int rc = mdev_classify(ctx, d_recs, n, types);
   if (rc) return rc;
-  rc = enqueue_orderings(ctx, n, SRC_MDEV_TYPE, SRC_MDEV_PARENT);
+  {
+    ScanCtrl* c = ctx->ctrl.p;
+    OrdInput in = {{ctx->surv.p, ctx->surv.p}, {&c->n_surv, &c->n_surv}, {SRC_MDEV_TYPE, SRC_MDEV_PARENT},
+                   {&c->max_devkey, &c->max_group}, nullptr};
+    rc = enqueue_orderings(ctx, n, in);
+  }
   if (rc) return rc;
   ctx->last_n = n;
   ctx->last_total = n;
@@ -1883,35 +1683,6 @@ int kvg_debug_radix_plan(uint32_t max_key, uint32_t key_bits_max, uint32_t max_b
   return KVG_OK;
 }
 
-int kvg_dev_debug_classify(kvg_ctx* ctx, const void* d_recs, size_t n, int mode, int rows, float* ms_out) {
-  if (!ctx || !d_recs || !ms_out || n == 0 || n > 0xfffffff0ull) return KVG_EINVAL;
-  CK(cudaSetDevice(ctx->device));
-  ENSURE(ctx->surv, n + 1);
-  ENSURE(ctx->probe_slots, 4);
-  ENSURE(ctx->nv_index, 65536);
-  cudaEvent_t a, b;
-  cudaEventCreate(&a);
-  cudaEventCreate(&b);
-  CK(cudaMemsetAsync(ctx->probe_slots.p, 0, 4, ctx->stream));
-  cudaEventRecord(a, ctx->stream);
-  if (rows == 4) {
-    size_t tiles = (n + 511) / 512;
-    k_debug_classify<128, 4><<<(unsigned)tiles, 128, 0, ctx->stream>>>((const uint4*)d_recs, (uint32_t)n, ctx->surv.p, ctx->nv_index.p, ctx->probe_slots.p, mode);
-  } else if (rows == 16) {
-    size_t tiles = (n + 2047) / 2048;
-    k_debug_classify<128, 16><<<(unsigned)tiles, 128, 0, ctx->stream>>>((const uint4*)d_recs, (uint32_t)n, ctx->surv.p, ctx->nv_index.p, ctx->probe_slots.p, mode);
-  } else {
-    size_t tiles = (n + 1023) / 1024;
-    k_debug_classify<128, 8><<<(unsigned)tiles, 128, 0, ctx->stream>>>((const uint4*)d_recs, (uint32_t)n, ctx->surv.p, ctx->nv_index.p, ctx->probe_slots.p, mode);
-  }
-  cudaEventRecord(b, ctx->stream);
-  CK(cudaStreamSynchronize(ctx->stream));
-  cudaEventElapsedTime(ms_out, a, b);
-  cudaEventDestroy(a);
-  cudaEventDestroy(b);
-  return check_launch(ctx, "debug classify");
-}
-
 int kvg_dev_flush_l2(kvg_ctx* ctx) {
   if (!ctx) return KVG_EINVAL;
   CK(cudaSetDevice(ctx->device));
@@ -1955,39 +1726,43 @@ int kvg_comm_init(kvg_ctx* ctx, int rank, int nranks, const void* unique_id128) 
   return KVG_OK;
 }
 
-// ---- peer-memory gather: set-up ------------------------------------------------------------------
-// kvg_comm_p2p_export: allocate this rank's gather windows for shards of up to cap_local records and
-// return the 64-byte CUDA IPC handle the other ranks need.  kvg_comm_p2p_import: open every rank's
-// handle (all_handles = nranks x 64 bytes, rank order).  After both succeeded kvg_dev_scan_pci_sharded
-// uses the peer-memory path (no NCCL, no host synchronisation).  Any failure leaves the NCCL path.
+
+// ---- peer windows: set-up -------------------------------------------------------------------------
+// kvg_comm_p2p_export: allocate this rank's receive window for shards of up to cap_local PCI records
+// (cap_local / 2 mdev records) and return the 64-byte CUDA IPC handle the other ranks need.
+// kvg_comm_p2p_import: open every rank's handle (all_handles = nranks x 64 bytes, rank order).  After both
+// succeeded on EVERY rank (kvg_comm_p2p_enable) the sharded scans exchange over NVLink stores; otherwise the
+// NCCL path (kvg_comm_init) allocates a private window of the same shape on first use.
+static size_t window_bytes(int nranks, size_t cap_local) {
+  return SH_HDR + 2 * 2 * (size_t)nranks * cap_local * 16;
+}
 int kvg_comm_p2p_export(kvg_ctx* ctx, int rank, int nranks, size_t cap_local, void* handle_out64) {
-  if (!ctx || !handle_out64 || nranks < 1 || nranks > P2P_MAX_RANKS || rank < 0 || rank >= nranks || !cap_local)
+  if (!ctx || !handle_out64 || nranks < 1 || nranks > SH_MAX_RANKS || rank < 0 || rank >= nranks || !cap_local)
     return KVG_EINVAL;
   CK(cudaSetDevice(ctx->device));
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  static_assert(sizeof(P2PCtrl) <= P2P_HDR, "control block fits its pad");
-  if (ctx->p2p_mine) {
-    ctx->err = "peer windows already exported";
+  static_assert(sizeof(ShardCtrl) <= SH_HDR, "control block fits its pad");
+  if (ctx->win_mine) {
+    ctx->err = "receive window already allocated";
     return KVG_ESTATE;
   }
   ctx->rank = rank;
   ctx->nranks = nranks;
-  ctx->p2p_cap = cap_local;
-  const size_t bytes = P2P_HDR + 2 * (size_t)nranks * cap_local * 16;
-  CK(cudaMalloc((void**)&ctx->p2p_mine, bytes));
-  CK(cudaMemset(ctx->p2p_mine, 0, P2P_HDR));
+  ctx->win_cap = cap_local;
+  CK(cudaMalloc((void**)&ctx->win_mine, window_bytes(nranks, cap_local)));
+  CK(cudaMemset(ctx->win_mine, 0, SH_HDR));
   cudaIpcMemHandle_t h;
-  CK(cudaIpcGetMemHandle(&h, ctx->p2p_mine));
+  CK(cudaIpcGetMemHandle(&h, ctx->win_mine));
   memcpy(handle_out64, &h, 64);
   return KVG_OK;
 }
 
 int kvg_comm_p2p_import(kvg_ctx* ctx, const void* all_handles) {
-  if (!ctx || !all_handles || !ctx->p2p_mine) return KVG_EINVAL;
+  if (!ctx || !all_handles || !ctx->win_mine) return KVG_EINVAL;
   CK(cudaSetDevice(ctx->device));
   for (int q = 0; q < ctx->nranks; q++) {
     if (q == ctx->rank) {
-      ctx->p2p_peer[q] = ctx->p2p_mine;
+      ctx->win_peer[q] = ctx->win_mine;
       continue;
     }
     cudaIpcMemHandle_t h;
@@ -1999,22 +1774,25 @@ int kvg_comm_p2p_import(kvg_ctx* ctx, const void* all_handles) {
       cudaGetLastError();
       return KVG_ECUDA;
     }
-    ctx->p2p_peer[q] = (uint8_t*)p;
+    ctx->win_peer[q] = (uint8_t*)p;
   }
-  ENSURE(ctx->gather_base, P2P_MAX_RANKS + 2);
-  ENSURE(ctx->p2p_err, 4);
-  CK(cudaStreamSynchronize(ctx->stream));
-  ctx->p2p_step = 0;
+  ctx->shard_step = 0;
   return KVG_OK;
 }
 
-// switch the sharded scan between the peer-memory path (on != 0; needs a successful import on EVERY
-// rank — the caller agrees on that collectively) and the NCCL path
+// collective decision: enable only when import succeeded on every rank
 int kvg_comm_p2p_enable(kvg_ctx* ctx, int on) {
   if (!ctx) return KVG_EINVAL;
-  if (on && (!ctx->p2p_mine || !ctx->gather_base.p)) {
-    ctx->err = "peer windows are not imported";
-    return KVG_ESTATE;
+  if (on) {
+    if (!ctx->win_mine) {
+      ctx->err = "peer windows are not exported";
+      return KVG_ESTATE;
+    }
+    for (int q = 0; q < ctx->nranks; q++)
+      if (!ctx->win_peer[q]) {
+        ctx->err = "peer windows are not imported";
+        return KVG_ESTATE;
+      }
   }
   ctx->p2p = on != 0;
   return KVG_OK;
@@ -2034,179 +1812,396 @@ int kvg_comm_destroy(kvg_ctx* ctx) {
 
 }  // extern "C"
 
-// Sharded scan over peer memory: classify -> offsets -> [pack fused with the all-gather] -> signal;
-// wait for all regions -> dense copy -> ack; key-partitioned orderings.  Fully asynchronous.
-static int scan_sharded_p2p(kvg_ctx* ctx, const void* d_recs, size_t n_local) {
+// NCCL mode: every rank learns every shard's survivor count, then one allgatherv (NCCL has none: a grouped
+// broadcast per root) of U x 16-byte records; rank order == Walk order.  Returns the gathered total.
+static int nccl_allgatherv(kvg_ctx* ctx, const uint4* local, int U, size_t* total_out) {
   const int P = ctx->nranks;
-  if (n_local > ctx->p2p_cap) {
-    ctx->err = "shard larger than the exported peer window";
+  CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->h_counts[P] = ctx->h_ctrl->n_surv;
+  CK(cudaMemcpyAsync(ctx->gather_counts.p + P, &ctx->h_counts[P], 8, cudaMemcpyHostToDevice, ctx->stream));
+  ncclResult_t r = g_nccl.AllGather(ctx->gather_counts.p + P, ctx->gather_counts.p, 1, ncclUint64, ctx->comm,
+                                    ctx->stream);
+  if (r != 0) {
+    ctx->err = std::string("ncclAllGather(counts): ") + g_nccl.GetErrorString(r);
+    return KVG_ENCCL;
+  }
+  CK(cudaMemcpyAsync(ctx->h_counts, ctx->gather_counts.p, 8 * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  size_t total = 0;
+  std::vector<size_t> displ((size_t)P);
+  for (int q = 0; q < P; q++) {
+    displ[(size_t)q] = total;
+    total += ctx->h_counts[q];
+  }
+  if (total > 0x7ffffff0ull) {
+    ctx->err = "gathered survivor list exceeds 2^31 entries";
     return KVG_ERANGE;
   }
-  const size_t cap_total = (size_t)P * ctx->p2p_cap;
-  ENSURE(ctx->surv, cap_total + 1);
-  constexpr int T = 128, R = 8;
-  const size_t tiles = (n_local + (size_t)T * R - 1) / ((size_t)T * R);
-  ENSURE(ctx->ragged, (tiles ? tiles : 1) * T * R);
-  ENSURE(ctx->tile_count, tiles + 1);
-  ENSURE(ctx->tile_off, tiles + 2);
-  ENSURE(ctx->tile_max, tiles + 1);
-  const unsigned chunks = (unsigned)((tiles + C_TILE - 1) / C_TILE);
-  ENSURE(ctx->offs_state, (size_t)chunks + 2);
-  const unsigned long long step = ++ctx->p2p_step;
-  const uint32_t w = (uint32_t)(step & 1);
-  P2PPeers peers;
-  memset(&peers, 0, sizeof peers);
-  for (int q = 0; q < P; q++) {
-    peers.ctrl[q] = (P2PCtrl*)ctx->p2p_peer[q];
-    peers.win[q] = (uint4*)(ctx->p2p_peer[q] + P2P_HDR) + (size_t)w * cap_total;
+  ENSURE(ctx->gathered, (total + 1) * (size_t)U);
+  r = g_nccl.GroupStart();
+  for (int root = 0; root < P && r == 0; root++) {
+    size_t cnt = ctx->h_counts[root];
+    if (cnt == 0) continue;
+    r = g_nccl.Broadcast(root == ctx->rank ? (const void*)local : nullptr,
+                         ctx->gathered.p + displ[(size_t)root] * U, cnt * 16 * U, ncclUint8, root, ctx->comm,
+                         ctx->stream);
   }
-  P2PCtrl* mine = (P2PCtrl*)ctx->p2p_mine;
-  const uint4* my_window = (const uint4*)(ctx->p2p_mine + P2P_HDR) + (size_t)w * cap_total;
-
-  CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
-  CK(cudaMemsetAsync(ctx->p2p_err.p, 0, sizeof(uint32_t), ctx->stream));
-  if (step > 2) LAUNCH("p2p_wait_acks", k_p2p_wait_acks, 1, 32, 0, mine, (uint32_t)P, step - 2, ctx->p2p_err.p);
-  if (tiles) {
-    PciClassifyOp op;
-    op.recs = (const uint4*)d_recs;
-    op.n = (uint32_t)n_local;
-    op.out = (kvg_pci_surv*)ctx->ragged.p;
-    op.ctrl = ctx->ctrl.p;
-    op.table = ctx->tables.p;
-    op.cap_mask = (1u << ctx->cap_log2) - 1;
-    op.cap_shift = 32 - ctx->cap_log2;
-    op.info = ctx->info.p;
-    op.nv_index = ctx->nv_index.p;
-    op.local_max_group = 0;
-    op.local_max_dev = 0;
-    LAUNCH("classify_compact", (k_classify_ragged<PciClassifyOp, T, R>), (unsigned)tiles, T, 0, op,
-           ctx->tile_count.p, ctx->tile_max.p);
-    TileOffsetsArgs2 tt;
-    tt.o[0] = {ctx->tile_count.p, ctx->tile_max.p, nullptr, (uint32_t)tiles, ctx->tile_off.p,
-               &ctx->ctrl.p->n_own[0], ctx->offs_state.p};  // n_own[0] doubles as "local count" here
-    tt.o[1] = tt.o[0];
-    LAUNCH("tile_offsets", k_tile_offsets, chunks, KVG_BLOCK, 0, tt, ctx->ctrl.p, next_epoch());
-    // the pack IS the all-gather: every survivor goes straight into every peer's window
-    LAUNCH("pack_to_peers", k_pack_to_peers, (unsigned)tiles, 128, 0, (const uint4*)ctx->ragged.p,
-           ctx->tile_off.p, (uint32_t)(T * R), peers, (uint32_t)P, (size_t)ctx->rank * ctx->p2p_cap);
+  ncclResult_t r2 = g_nccl.GroupEnd();
+  if (r != 0 || r2 != 0) {
+    ctx->err = std::string("ncclBroadcast group: ") + g_nccl.GetErrorString(r ? r : r2);
+    return KVG_ENCCL;
   }
-  LAUNCH("p2p_signal", k_p2p_signal, 1, 32, 0, peers, (uint32_t)P, (uint32_t)ctx->rank, w, step,
-         &ctx->ctrl.p->n_own[0]);
-  LAUNCH("p2p_wait_gather", k_p2p_wait_gather, 1, 32, 0, mine, (uint32_t)P, w, step, ctx->gather_base.p,
-         ctx->ctrl.p, ctx->p2p_err.p);
-  dim3 cgrid((unsigned)std::max(1, ctx->sm_count * 2 / P), (unsigned)P);
-  LAUNCH("p2p_copy_regions", k_p2p_copy_regions, cgrid, KVG_BLOCK, 0, my_window, ctx->p2p_cap,
-         ctx->gather_base.p, ctx->surv.p);
-  LAUNCH("p2p_ack", k_p2p_ack, 1, 32, 0, peers, (uint32_t)P, (uint32_t)ctx->rank, step);
-  int rc = check_launch(ctx, "p2p gather");
-  if (rc) return rc;
-  // n_own[0] was used as scratch for the local count: the ownership select rewrites it.  The key
-  // maxima reduced by k_tile_offsets (local shard, then the owned pairs) bound the radix passes.
-  rc = enqueue_pci_orderings(ctx, cap_total, /*owned_only=*/P > 1);
-  if (rc) return rc;
-  ctx->last_n = n_local;
-  ctx->last_total = cap_total;
-  ctx->last_kind = 1;
-  ctx->last_owned = P > 1;
+  *total_out = total;
   return KVG_OK;
 }
 
-// after the gather: n_surv <- total, maxima already all-reduced by construction (each rank
-// recomputes them from the gathered list)
-__global__ void k_gathered_maxima(const kvg_pci_surv* __restrict__ s, uint32_t n, ScanCtrl* ctrl) {
-  pdl_enter();
-  uint32_t mg = 0, md = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    mg = max(mg, s[i].iommu_group);
-    md = max(md, (uint32_t)s[i].device);
+// The exchange step behind a dense local survivor list of <= n_cap records (U x 16 bytes each) whose length
+// lives in ctrl->n_surv: multisplit by owner -> windows -> owned lists (ctx->owned0 / owned1, lengths in
+// ctrl->n_own[], largest keys in ctrl->max_devkey / max_group).  Returns the capacity of an owned list.
+template <int U>
+static int enqueue_exchange(kvg_ctx* ctx, const uint4* local, size_t n_cap, size_t* owned_cap_out) {
+  const int P = ctx->nranks;
+  const bool peer = ctx->p2p;
+  if (!peer && !ctx->comm) {
+    ctx->err = "kvg_comm_init / kvg_comm_p2p_import has not been called";
+    return KVG_ESTATE;
   }
-  mg = warp_max(mg);
-  md = warp_max(md);
-  if (lane_id() == 0) {
-    if (mg) atomicMax(&ctrl->max_group, mg);
-    if (md) atomicMax(&ctrl->max_devkey, md);
+  ScanCtrl* c = ctx->ctrl.p;
+  const uint4* list = local;
+  size_t list_cap = n_cap;
+  uint32_t* n_ptr = &c->n_surv;
+  if (!peer) {  // NCCL: all-gather, then the same kernels in local mode on the gathered list
+    size_t total = 0;
+    int rc = nccl_allgatherv(ctx, local, U, &total);
+    if (rc) return rc;
+    list = ctx->gathered.p;
+    list_cap = total;
+    ctx->h_counts[P] = total;  // pinned; the low 32 bits are the value (little endian)
+    CK(cudaMemcpyAsync(&c->n_gathered, &ctx->h_counts[P], sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    n_ptr = &c->n_gathered;
+    if (!ctx->win_mine) {  // private window of the shape a peer window has
+      size_t cap = std::max<size_t>(ctx->win_cap, n_cap * U);
+      ctx->win_cap = cap;
+      CK(cudaMalloc((void**)&ctx->win_mine, window_bytes(P, cap)));
+      CK(cudaMemsetAsync(ctx->win_mine, 0, SH_HDR, ctx->stream));
+      ctx->win_peer[ctx->rank] = ctx->win_mine;
+    }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) ctrl->n_surv = n;
+  if (n_cap * U > ctx->win_cap) {
+    ctx->err = "shard larger than the receive window (kvg_comm_p2p_export cap_local)";
+    return KVG_ERANGE;
+  }
+  // an owned list holds at most what the window regions of one ordering hold
+  const size_t owned_cap = (size_t)P * ctx->win_cap / U;
+  ENSURE(ctx->owned0, (owned_cap + 1) * U);
+  ENSURE(ctx->owned1, (owned_cap + 1) * U);
+  const size_t T = (list_cap + C_TILE - 1) / C_TILE + 1;
+  // [0, 2P) totals, [32, 34) self-resetting tickets, [34] error word, [64, ...) tile counts; a fresh
+  // allocation is zero-filled, the tickets return to zero by themselves, the error word is sticky
+  ENSURE(ctx->shard_cnt, 64 + 2 * (size_t)P * T);
+  uint32_t* totals = ctx->shard_cnt.p;
+  uint32_t* tickets = ctx->shard_cnt.p + 32;
+  uint32_t* err = ctx->shard_cnt.p + 34;
+  ctx->shard_err = err;
+  const unsigned long long step = ++ctx->shard_step;
+  ShardArgs A;
+  A.list = list;
+  A.n_ptr = n_ptr;
+  A.tile_cnt = ctx->shard_cnt.p + 64;
+  A.totals = totals;
+  A.ticket = tickets;
+  A.T = (uint32_t)T;
+  A.P = (uint32_t)P;
+  A.me = (uint32_t)ctx->rank;
+  A.only = peer ? SH_ALL : (uint32_t)ctx->rank;
+  A.n_src = peer ? (uint32_t)P : 1u;
+  A.src = peer ? (uint32_t)ctx->rank : 0u;
+  A.region_cap = peer ? ctx->win_cap / U : (size_t)P * ctx->win_cap / U;
+  A.parity = (uint32_t)(step & 1);
+  A.step = step;
+  ShardPeers peers;
+  memset(&peers, 0, sizeof peers);
+  for (int q = 0; q < P; q++) {
+    uint8_t* base = ctx->win_peer[q] ? ctx->win_peer[q] : ctx->win_mine;  // local mode: only my own entry is used
+    peers.ctrl[q] = (ShardCtrl*)base;
+    peers.win[q] = (uint4*)(base + SH_HDR);
+  }
+  const ShardCtrl* mine = (const ShardCtrl*)ctx->win_mine;
+  LAUNCH("shard_count", k_shard_count<U>, (unsigned)T, KVG_BLOCK, 0, A);
+  LAUNCH("shard_scan", k_shard_scan, (unsigned)((2 * P + KVG_WARPS - 1) / KVG_WARPS), KVG_BLOCK, 0, A);
+  LAUNCH("shard_send", k_shard_send<U>, (unsigned)T, KVG_BLOCK, 0, A, peers, mine, err);
+  GatherArgs G;
+  G.window = (const uint4*)(ctx->win_mine + SH_HDR);
+  G.owned[0] = ctx->owned0.p;
+  G.owned[1] = ctx->owned1.p;
+  G.n_own = &c->n_own[0];
+  G.max_key = &c->own_max[0];
+  dim3 ggrid((unsigned)std::max(1, ctx->sm_count), 2);
+  LAUNCH("shard_gather", k_shard_gather<U>, ggrid, KVG_BLOCK, 0, A, G, peers, mine, err);
+  *owned_cap_out = owned_cap;
+  return check_launch(ctx, "shard exchange");
+}
+
+// orderings of the two owned lists
+static int enqueue_owned_orderings(kvg_ctx* ctx, size_t owned_cap, int src0, int src1, bool names) {
+  ScanCtrl* c = ctx->ctrl.p;
+  OrdInput in = {{ctx->owned0.p, ctx->owned1.p}, {&c->n_own[0], &c->n_own[1]}, {src0, src1},
+                 {&c->own_max[0], &c->own_max[1]}, names ? ctx->owned0.p : nullptr};
+  return enqueue_orderings(ctx, owned_cap, in);
 }
 
 extern "C" {
 
 int kvg_dev_scan_pci_sharded(kvg_ctx* ctx, const void* d_recs, size_t n_local) {
-  if (!ctx || (!d_recs && n_local) || n_local > 0xfffffff0ull) return KVG_EINVAL;
-  if (!ctx->comm && !ctx->p2p) {
-    ctx->err = "kvg_comm_init / kvg_comm_p2p_import has not been called";
-    return KVG_ESTATE;
-  }
+  if (!ctx || (!d_recs && n_local) || n_local > 0x7ffffff0ull || ((uintptr_t)d_recs & 15)) return KVG_EINVAL;
   {
     int rc_t = table_needed(ctx, "kvg_pciids_load must precede a scan");
     if (rc_t) return rc_t;
   }
   CK(cudaSetDevice(ctx->device));
-  const int P = ctx->nranks;
-  if (ctx->p2p) return scan_sharded_p2p(ctx, d_recs, n_local);
-  ENSURE(ctx->local_surv, n_local + 1);
+  ENSURE(ctx->surv, n_local + 1);
   CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
-  int rc = enqueue_classify(ctx, d_recs, n_local, ctx->local_surv.p);
+  int rc = enqueue_classify(ctx, d_recs, n_local, ctx->surv.p);
   if (rc) return rc;
-  // counts: every rank learns every shard's survivor count (8 bytes per rank)
-  {
-    // widen the device-side u32 count to u64 in place of a dedicated kernel: copy via host pinned
-    CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    ctx->h_counts[P] = ctx->h_ctrl->n_surv;
-    CK(cudaMemcpyAsync(ctx->gather_counts.p + P, &ctx->h_counts[P], 8, cudaMemcpyHostToDevice, ctx->stream));
-    ncclResult_t r = g_nccl.AllGather(ctx->gather_counts.p + P, ctx->gather_counts.p, 1, ncclUint64,
-                                      ctx->comm, ctx->stream);
-    if (r != 0) {
-      ctx->err = std::string("ncclAllGather(counts): ") + g_nccl.GetErrorString(r);
-      return KVG_ENCCL;
-    }
-    CK(cudaMemcpyAsync(ctx->h_counts, ctx->gather_counts.p, 8 * (size_t)P, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-  }
-  size_t total = 0;
-  std::vector<size_t> displ((size_t)P);
-  for (int r = 0; r < P; r++) {
-    displ[(size_t)r] = total;
-    total += ctx->h_counts[r];
-  }
-  if (total > 0xfffffff0ull) {
-    ctx->err = "gathered survivor list exceeds 2^32 entries";
-    return KVG_ERANGE;
-  }
-  ENSURE(ctx->surv, total + 1);
-  // allgatherv = one grouped broadcast per root; rank order == Walk order of the shards
-  {
-    ncclResult_t r = g_nccl.GroupStart();
-    for (int root = 0; root < P && r == 0; root++) {
-      size_t cnt = ctx->h_counts[root];
-      if (cnt == 0) continue;
-      r = g_nccl.Broadcast(root == ctx->rank ? (const void*)ctx->local_surv.p : nullptr,
-                           ctx->surv.p + displ[(size_t)root], cnt * 16, ncclUint8, root, ctx->comm,
-                           ctx->stream);
-    }
-    ncclResult_t r2 = g_nccl.GroupEnd();
-    if (r != 0 || r2 != 0) {
-      ctx->err = std::string("ncclBroadcast group: ") + g_nccl.GetErrorString(r ? r : r2);
-      return KVG_ENCCL;
-    }
-  }
-  // control block for the ordering phase: zero, then n_surv <- total (known on the host; a 4-byte
-  // copy from pinned memory).  The key maxima come from the ownership select (k_tile_offsets).
-  CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
-  ctx->h_counts[P] = total;  // pinned; low 32 bits are the value (little endian)
-  CK(cudaMemcpyAsync(&ctx->ctrl.p->n_surv, &ctx->h_counts[P], sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  if (P == 1) {  // single rank: no ownership select runs, so reduce the maxima here
-    LAUNCH("gathered_maxima", k_gathered_maxima, ctx->sm_count * 4, KVG_BLOCK, 0,
-           (const kvg_pci_surv*)ctx->surv.p, (uint32_t)total, ctx->ctrl.p);
-  }
-  // bucketing partitioned by key: this rank orders only the keys with key % nranks == rank
-  rc = enqueue_pci_orderings(ctx, total, /*owned_only=*/P > 1);
+  size_t owned_cap = 0;
+  rc = enqueue_exchange<1>(ctx, ctx->surv.p, n_local, &owned_cap);
+  if (rc) return rc;
+  rc = enqueue_owned_orderings(ctx, owned_cap, SRC_PCI_DEVICE, SRC_PCI_GROUP, true);
   if (rc) return rc;
   ctx->last_n = n_local;
-  ctx->last_total = total;
-  ctx->last_kind = 1;
-  ctx->last_owned = P > 1;
+  ctx->last_total = owned_cap;
+  ctx->last_kind = 3;
+  ctx->last_units = 1;
+  return KVG_OK;
+}
+
+}  // extern "C"
+
+// ---- sharded fetches ---------------------------------------------------------------------------------
+namespace {
+struct BlockLayout {
+  size_t o = 0;
+  size_t take(size_t bytes) {
+    size_t at = o;
+    o += (bytes + 63) & ~(size_t)63;
+    return at;
+  }
+};
+// the type dictionary part of an mdev result: layout, device-to-host copies, host-side repack
+struct DictPart {
+  size_t o_lraw, o_llen, o_loff, o_lbytes, o_canon, o_nraw, o_nlen, o_noff, o_nbytes;
+  static constexpr uint32_t NAME_CAP = 256;
+  void layout(BlockLayout& L, uint32_t nt, size_t raw_len) {
+    o_lraw = L.take(raw_len + 16);
+    o_llen = L.take(((size_t)nt + 1) * 4);
+    o_loff = L.take(((size_t)nt + 1) * 4);
+    o_lbytes = L.take(raw_len + 16);
+    o_canon = L.take(((size_t)nt + 1) * 2);
+    o_nraw = L.take((size_t)nt * NAME_CAP + 16);
+    o_nlen = L.take(((size_t)nt + 1) * 4);
+    o_noff = L.take(((size_t)nt + 1) * 4);
+    o_nbytes = L.take((size_t)nt * NAME_CAP + 16);
+  }
+};
+}  // namespace
+
+static int dict_copy(kvg_ctx* ctx, uint8_t* b, const DictPart& D) {
+  const uint32_t nt = ctx->n_types;
+  if (!nt) return KVG_OK;
+  const size_t raw_len = ctx->h_type_off[nt];
+  CK(cudaMemcpyAsync(b + D.o_lraw, ctx->type_label.p, raw_len, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(b + D.o_llen, ctx->type_label_len.p, (size_t)nt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(b + D.o_canon, ctx->type_canon.p, (size_t)nt * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(b + D.o_nraw, ctx->type_names.p, (size_t)nt * DictPart::NAME_CAP, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(b + D.o_nlen, ctx->type_name_len.p, (size_t)nt * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  return KVG_OK;
+}
+// repack labels / names contiguously (marshalling of GPU-produced bytes)
+static void dict_finish(kvg_ctx* ctx, uint8_t* b, const DictPart& D, uint32_t* n_types, const uint32_t** label_off,
+                        const uint8_t** label_bytes, const uint16_t** type_canon, const uint32_t** name_off,
+                        const uint8_t** name_bytes) {
+  const uint32_t nt = ctx->n_types;
+  uint32_t* loff = (uint32_t*)(b + D.o_loff);
+  uint32_t* noff = (uint32_t*)(b + D.o_noff);
+  const uint32_t* llen = (const uint32_t*)(b + D.o_llen);
+  const uint32_t* nlen = (const uint32_t*)(b + D.o_nlen);
+  size_t lo = 0, no = 0;
+  for (uint32_t k = 0; k < nt; k++) {
+    loff[k] = (uint32_t)lo;
+    memcpy(b + D.o_lbytes + lo, b + D.o_lraw + ctx->h_type_off[k], llen[k]);
+    lo += llen[k];
+    noff[k] = (uint32_t)no;
+    uint32_t nl = nlen[k] > DictPart::NAME_CAP ? DictPart::NAME_CAP : nlen[k];
+    memcpy(b + D.o_nbytes + no, b + D.o_nraw + (size_t)k * DictPart::NAME_CAP, nl);
+    no += nl;
+  }
+  loff[nt] = (uint32_t)lo;
+  noff[nt] = (uint32_t)no;
+  *n_types = nt;
+  *label_off = loff;
+  *label_bytes = b + D.o_lbytes;
+  *type_canon = (const uint16_t*)(b + D.o_canon);
+  *name_off = noff;
+  *name_bytes = b + D.o_nbytes;
+}
+
+// control block + the exchange's error word; a spin that timed out means a peer never delivered
+static int shard_ctrl_fetch(kvg_ctx* ctx) {
+  CK(cudaMemcpyAsync(ctx->h_ctrl, ctx->ctrl.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(&ctx->h_ctrl->reserved2[0], ctx->shard_err, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_ctrl->reserved2[0]) {
+    ctx->err = "sharded scan: a peer did not deliver its regions (or acknowledge a window) within the time limit";
+    return KVG_ENCCL;
+  }
+  return KVG_OK;
+}
+
+extern "C" {
+
+int kvg_dev_scan_pci_shard_fetch(kvg_ctx* ctx, kvg_pci_shard_result** res) {
+  if (!ctx || !res || ctx->last_kind != 3) return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  int rc = shard_ctrl_fetch(ctx);
+  if (rc) return rc;
+  const size_t S = ctx->h_ctrl->n_surv, SD = ctx->h_ctrl->n_own[0], SG = ctx->h_ctrl->n_own[1];
+  const size_t KD = ctx->h_ctrl->n_dev_keys, G = ctx->h_ctrl->n_groups;
+  const size_t pool_len = ctx->h_pool.size();
+  BlockLayout L;
+  L.take(sizeof(kvg_pci_shard_result));
+  const size_t o_local = L.take(S * 16), o_dm = L.take(SD * 16), o_dk32 = L.take(KD * 4), o_dk = L.take(KD * 2);
+  const size_t o_doff = L.take((KD + 1) * 4), o_dperm = L.take(SD * 4), o_dname = L.take(KD * 4);
+  const size_t o_gm = L.take(SG * 16), o_gk = L.take(G * 4), o_goff = L.take((G + 1) * 4), o_gperm = L.take(SG * 4);
+  const size_t o_pool = L.take(pool_len);
+  void* blk = pinned_alloc(ctx, L.o);
+  if (!blk) {
+    ctx->err = "cudaMallocHost failed for the result block";
+    return KVG_ENOMEM;
+  }
+  uint8_t* b = pinned_payload(blk);
+  auto D2H = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+    if (!bytes) return cudaSuccess;
+    return cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  };
+  OrderBufs& od = ctx->ord_dev;
+  OrderBufs& og = ctx->ord_grp;
+  CK(D2H(o_local, ctx->surv.p, S * 16));
+  CK(D2H(o_dm, ctx->owned0.p, SD * 16));
+  CK(D2H(o_dk32, od.seg_key.p, KD * 4));
+  CK(D2H(o_doff, od.seg_off.p, (KD + 1) * 4));
+  CK(D2H(o_dperm, od.perm.p, SD * 4));
+  CK(D2H(o_dname, od.seg_name.p, KD * 4));
+  CK(D2H(o_gm, ctx->owned1.p, SG * 16));
+  CK(D2H(o_gk, og.seg_key.p, G * 4));
+  CK(D2H(o_goff, og.seg_off.p, (G + 1) * 4));
+  CK(D2H(o_gperm, og.perm.p, SG * 4));
+  CK(cudaStreamSynchronize(ctx->stream));
+  kvg_pci_shard_result* r = (kvg_pci_shard_result*)b;
+  memset(r, 0, sizeof *r);
+  if (SD == 0) ((uint32_t*)(b + o_doff))[0] = 0;
+  if (SG == 0) ((uint32_t*)(b + o_goff))[0] = 0;
+  uint16_t* dk = (uint16_t*)(b + o_dk);
+  for (size_t k = 0; k < KD; k++) dk[k] = (uint16_t)((const uint32_t*)(b + o_dk32))[k];  // marshalling: narrow
+  r->n_records = ctx->last_n;
+  r->n_local = S;
+  r->local = (const kvg_pci_surv*)(b + o_local);
+  r->n_dev_members = SD;
+  r->dev_members = (const kvg_pci_surv*)(b + o_dm);
+  r->n_dev_keys = (uint32_t)KD;
+  r->dev_keys = dk;
+  r->dev_off = (const uint32_t*)(b + o_doff);
+  r->dev_perm = (const uint32_t*)(b + o_dperm);
+  r->dev_name_slot = (const uint32_t*)(b + o_dname);
+  r->n_grp_members = SG;
+  r->grp_members = (const kvg_pci_surv*)(b + o_gm);
+  r->n_groups = (uint32_t)G;
+  r->grp_keys = (const uint32_t*)(b + o_gk);
+  r->grp_off = (const uint32_t*)(b + o_goff);
+  r->grp_perm = (const uint32_t*)(b + o_gperm);
+  if (pool_len) memcpy(b + o_pool, ctx->h_pool.data(), pool_len);
+  r->name_pool = b + o_pool;
+  r->name_pool_len = pool_len;
+  *res = r;
+  return KVG_OK;
+}
+
+int kvg_dev_scan_mdev_sharded(kvg_ctx* ctx, const void* d_recs, size_t n_local, const kvg_type_dict* types) {
+  if (!ctx || !types || (!d_recs && n_local) || n_local > 0x7ffffff0ull || ((uintptr_t)d_recs & 15)) return KVG_EINVAL;
+  int rc = mdev_classify(ctx, d_recs, n_local, types);
+  if (rc) return rc;
+  size_t owned_cap = 0;
+  rc = enqueue_exchange<2>(ctx, ctx->surv.p, n_local, &owned_cap);
+  if (rc) return rc;
+  rc = enqueue_owned_orderings(ctx, owned_cap, SRC_MDEV_TYPE, SRC_MDEV_PARENT, false);
+  if (rc) return rc;
+  ctx->last_n = n_local;
+  ctx->last_total = owned_cap;
+  ctx->last_kind = 4;
+  ctx->last_units = 2;
+  return KVG_OK;
+}
+
+int kvg_dev_scan_mdev_shard_fetch(kvg_ctx* ctx, kvg_mdev_shard_result** res) {
+  if (!ctx || !res || ctx->last_kind != 4) return KVG_EINVAL;
+  CK(cudaSetDevice(ctx->device));
+  int rc = shard_ctrl_fetch(ctx);
+  if (rc) return rc;
+  const size_t S = ctx->h_ctrl->n_surv, ST = ctx->h_ctrl->n_own[0], SP = ctx->h_ctrl->n_own[1];
+  const size_t KT = ctx->h_ctrl->n_dev_keys, NP = ctx->h_ctrl->n_groups;
+  const uint32_t nt = ctx->n_types;
+  BlockLayout L;
+  L.take(sizeof(kvg_mdev_shard_result));
+  const size_t o_local = L.take(S * 32), o_tm = L.take(ST * 32), o_tk32 = L.take(KT * 4), o_tk = L.take(KT * 2);
+  const size_t o_toff = L.take((KT + 1) * 4), o_tperm = L.take(ST * 4);
+  const size_t o_pm = L.take(SP * 32), o_pk = L.take(NP * 4), o_poff = L.take((NP + 1) * 4), o_pperm = L.take(SP * 4);
+  DictPart D;
+  D.layout(L, nt, nt ? ctx->h_type_off[nt] : 0);
+  void* blk = pinned_alloc(ctx, L.o);
+  if (!blk) return KVG_ENOMEM;
+  uint8_t* b = pinned_payload(blk);
+  auto D2H = [&](size_t off, const void* src, size_t bytes) -> cudaError_t {
+    if (!bytes) return cudaSuccess;
+    return cudaMemcpyAsync(b + off, src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+  };
+  OrderBufs& ot = ctx->ord_dev;
+  OrderBufs& op = ctx->ord_grp;
+  CK(D2H(o_local, ctx->surv.p, S * 32));
+  CK(D2H(o_tm, ctx->owned0.p, ST * 32));
+  CK(D2H(o_tk32, ot.seg_key.p, KT * 4));
+  CK(D2H(o_toff, ot.seg_off.p, (KT + 1) * 4));
+  CK(D2H(o_tperm, ot.perm.p, ST * 4));
+  CK(D2H(o_pm, ctx->owned1.p, SP * 32));
+  CK(D2H(o_pk, op.seg_key.p, NP * 4));
+  CK(D2H(o_poff, op.seg_off.p, (NP + 1) * 4));
+  CK(D2H(o_pperm, op.perm.p, SP * 4));
+  rc = dict_copy(ctx, b, D);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  kvg_mdev_shard_result* r = (kvg_mdev_shard_result*)b;
+  memset(r, 0, sizeof *r);
+  if (ST == 0) ((uint32_t*)(b + o_toff))[0] = 0;
+  if (SP == 0) ((uint32_t*)(b + o_poff))[0] = 0;
+  uint16_t* tk = (uint16_t*)(b + o_tk);
+  for (size_t k = 0; k < KT; k++) tk[k] = (uint16_t)((const uint32_t*)(b + o_tk32))[k];
+  r->n_records = ctx->last_n;
+  r->n_local = S;
+  r->local = (const kvg_mdev_surv*)(b + o_local);
+  r->n_type_members = ST;
+  r->type_members = (const kvg_mdev_surv*)(b + o_tm);
+  r->n_type_keys = (uint32_t)KT;
+  r->type_keys = tk;
+  r->type_off = (const uint32_t*)(b + o_toff);
+  r->type_perm = (const uint32_t*)(b + o_tperm);
+  r->n_par_members = SP;
+  r->par_members = (const kvg_mdev_surv*)(b + o_pm);
+  r->n_parents = (uint32_t)NP;
+  r->par_keys = (const uint32_t*)(b + o_pk);
+  r->par_off = (const uint32_t*)(b + o_poff);
+  r->par_perm = (const uint32_t*)(b + o_pperm);
+  dict_finish(ctx, b, D, &r->n_types, &r->label_off, &r->label_bytes, &r->type_canon, &r->type_name_off,
+              &r->type_name_bytes);
+  *res = r;
   return KVG_OK;
 }
 

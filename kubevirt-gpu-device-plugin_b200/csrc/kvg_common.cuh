@@ -126,21 +126,10 @@ __device__ __forceinline__ uint32_t warp_incl_max(uint32_t v) {
   }
   return v;
 }
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(KVG_FULL, v, d);
-  return v;
-}
-__device__ __forceinline__ uint32_t warp_max(uint32_t v) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(KVG_FULL, v, d));
-  return v;
-}
-__device__ __forceinline__ uint32_t warp_min(uint32_t v) {
-#pragma unroll
-  for (int d = 16; d > 0; d >>= 1) v = min(v, __shfl_xor_sync(KVG_FULL, v, d));
-  return v;
-}
+// full-warp reductions: one REDUX instruction each (sm_80+)
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) { return __reduce_add_sync(KVG_FULL, v); }
+__device__ __forceinline__ uint32_t warp_max(uint32_t v) { return __reduce_max_sync(KVG_FULL, v); }
+__device__ __forceinline__ uint32_t warp_min(uint32_t v) { return __reduce_min_sync(KVG_FULL, v); }
 
 // Block-wide exclusive sum over KVG_BLOCK threads; *total receives the block sum.
 // `scratch` is KVG_WARPS+1 words of shared memory; contains two __syncthreads().

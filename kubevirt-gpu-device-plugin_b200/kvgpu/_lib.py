@@ -121,7 +121,6 @@ def load() -> C.CDLL:
         "kvg_dev_scan_mdev": (C.c_int, [vp, vp, sz, P(TypeDict)]),
         "kvg_dev_scan_mdev_fetch": (C.c_int, [vp, P(P(MdevResultC))]),
         "kvg_dev_flush_l2": (C.c_int, [vp]),
-        "kvg_dev_debug_classify": (C.c_int, [vp, vp, sz, C.c_int, C.c_int, P(C.c_float)]),
         "kvg_kernel_times": (C.c_int, [vp, P(C.c_float), C.c_char_p, sz, C.c_int]),
         "kvg_set_kernel_timing": (C.c_int, [vp, C.c_int]),
         "kvg_comm_unique_id": (C.c_int, [vp]),

@@ -1,6 +1,5 @@
-"""getDeviceName (device_plugin.go:371-438) end to end from KERNEL SOURCE on the CPU: the default parse
-(k_pciids_parse with its TMA text ring, mbarriers and cross-tile vendor look-back) or the barrier-free
-one, k_nv_index, k_pciids_sanitise_lines (the lane-parallel name transform with its Unicode fall-back),
+"""getDeviceName (device_plugin.go:371-438) end to end from KERNEL SOURCE on the CPU: K1 (per-warp TMA
+ring, span summaries, resolve + finalize), k_pciids_names (the lane-parallel name transform with its Unicode fall-back),
 k_section_lines / k_lookup_general / k_sanitise_matches (prefix semantics for arbitrary keys) — sequenced
 like libkvgpu.so does and compared with the oracle on the reference's Ginkgo fixture, the shipped
 pci.ids and the grammar fuzz.  Runs under the warp emulator of tools/emu/."""
@@ -18,7 +17,7 @@ from oracle import oracle as O
 sys.path.insert(0, os.path.join(conftest.ROOT, "tools", "emu"))
 import build as emu_build  # noqa: E402
 from test_gpu_parity import _random_pciids  # noqa: E402
-from test_parse_v2_emu import pad  # noqa: E402
+from test_parse_k1_emu import pad  # noqa: E402
 
 NAME_CAP = 4096
 
@@ -26,13 +25,13 @@ NAME_CAP = 4096
 @pytest.fixture(scope="module")
 def emu():
     L = C.CDLL(emu_build.build_names())
-    L.emu_get_device_names.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+    L.emu_get_device_names.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                        C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                        C.c_void_p]
     return L
 
 
-PARSERS = pytest.mark.parametrize("parser", [1, 2], ids=["k_pciids_parse", "scan_v2"])
+PARSERS = pytest.mark.parametrize("parser", [3], ids=["K1"])
 
 
 def device_names(emu, text, keys, cap_log2=12, parser=1, want_info=False):
@@ -44,7 +43,7 @@ def device_names(emu, text, keys, cap_log2=12, parser=1, want_info=False):
     out = np.zeros(len(keys) * NAME_CAP, dtype=np.uint8)
     ln = np.zeros(len(keys), dtype=np.uint32)
     info = np.zeros(8, dtype=np.uint32)
-    rc = emu.emu_get_device_names(parser, buf.ctypes.data, len(text), cap_log2, kb.ctypes.data, off.ctypes.data, len(keys),
+    rc = emu.emu_get_device_names(buf.ctypes.data, len(text), kb.ctypes.data, off.ctypes.data, len(keys),
                                   out.ctypes.data, NAME_CAP, ln.ctypes.data, info.ctypes.data, None, None, 0, None)
     assert rc == 0
     names = [bytes(out[i * NAME_CAP:i * NAME_CAP + int(ln[i])]).decode("latin-1") for i in range(len(keys))]
@@ -90,16 +89,3 @@ def test_grammar_fuzz_names_from_kernel_source(emu, parser):
     keys = ["%04x" % i for i in range(0, 40, 3)] + ["", "0", "00", "000", "0001 ", "\t", "001\r", "0001\r"]
     for it in range(25):
         check(emu, _random_pciids(rng, int(rng.integers(1, 300))), keys, parser=parser)
-
-
-def test_both_parsers_agree_on_every_parse_fact(emu):
-    """v_off, section end, entry count, line count and scanner limit of the default parse and of the
-    barrier-free one on tile-edge, long-line and multi-tile inputs (8 KiB tiles vs 4 KiB spans)."""
-    rng = np.random.default_rng(77)
-    texts = [_random_pciids(rng, int(rng.integers(800, 4000))) for _ in range(4)]
-    texts += [b"x" * 65536 + b"\n10de  NVIDIA\n\t1234  name\n", b"10de\n\t" + b"y" * 70000 + b"\n\t1234  n\n",
-              b"8086  Intel\n" + b"#" + b"c" * 8170 + b"\n10de  NVIDIA\n\t1234  Edge\n" + b"#" + b"d" * 9000 + b"\n\t5678  far\n10df x\n"]
-    for text in texts:
-        _, a = device_names(emu, text, [b"1234"], cap_log2=14, parser=1, want_info=True)
-        _, b = device_names(emu, text, [b"1234"], cap_log2=14, parser=2, want_info=True)
-        assert list(a[:6]) == list(b[:6]), text[:60]

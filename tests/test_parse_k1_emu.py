@@ -1,8 +1,9 @@
-"""csrc/kvg_parse_v2.cuh — the barrier-free pci.ids parse — executed on the CPU from its REAL kernel
-source (tools/emu/: one OS thread per CUDA thread, warp collectives as rendezvous) and compared with
-the oracle and with the Python model of its decomposition.  This is as close as a GPU-less box gets to
-running the kernels: the same scan / resolve / finalize code, the same helper source (cut out of
-kvg_parse.cuh at build time), poisoned scratch buffers, real atomics."""
+"""csrc/kvg_parse_k1.cuh — K1, the pci.ids parse (prep -> scan with the per-warp TMA ring -> resolve +
+finalize) — executed on the CPU from its REAL kernel source under the warp emulator (tools/emu/) and
+compared with the oracle and with the Python model of the span decomposition (tools/parse_v2_model.py:
+same spans, same ownership rule, same section / scanner-limit arithmetic).  Scratch buffers are
+poisoned (the prep kernel must clear what the parse relies on) and the persistent scan kernel runs
+with several grid sizes so that the two-stage ring is exercised over many iterations per warp."""
 import ctypes as C
 import os
 import sys
@@ -25,10 +26,8 @@ NONE = 0xFFFFFFFF
 
 @pytest.fixture(scope="module")
 def emu():
-    L = C.CDLL(emu_build.build())
-    L.emu_parse_v2.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
-    L.emu_table_probe.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
-    L.emu_table_probe.restype = C.c_uint32
+    L = C.CDLL(emu_build.build_names())
+    L.emu_parse_k1.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
     return L
 
 
@@ -40,20 +39,20 @@ def pad(text: bytes) -> np.ndarray:
     return buf
 
 
-def run(emu, text: bytes, n_files: int = 1, cap_log2: int = 15):
+def run(emu, text: bytes, n_files: int = 1, cap_log2: int = 0, scan_ctas: int = 0):
     buf = pad(text)
     stride = len(buf)
     images = np.tile(buf, n_files)
     info = np.zeros((n_files, 8), dtype=np.uint32)
-    tables = np.zeros((n_files, 1 << cap_log2), dtype=np.uint64)
-    assert emu.emu_parse_v2(images.ctypes.data, stride, len(text), n_files, cap_log2, info.ctypes.data,
+    tables = np.zeros((n_files, 65536), dtype=np.uint32)
+    assert emu.emu_parse_k1(images.ctypes.data, stride, len(text), n_files, scan_ctas, info.ctypes.data,
                             tables.ctypes.data) == 0
     return info, tables
 
 
 def emu_name(emu, text, info, table, cap_log2, key):
-    """What kvg_name_lookup's hash path returns: probe, section check (probe_name_slot), the line."""
-    off = emu.emu_table_probe(table.ctypes.data, cap_log2, (0x10de << 16) | int(key, 16))
+    """What kvg_name_lookup's table path returns: the id's slot, the section check of k_pciids_names, the line."""
+    off = int(table[int(key, 16)])
     v_off, sec_end = int(info[0]), int(info[1])
     if off == NONE or v_off == NONE or not (v_off < off < sec_end):
         return ""
@@ -62,55 +61,56 @@ def emu_name(emu, text, info, table, cap_log2, key):
     return O.get_device_name(b"10de\n" + line + b"\n", key.encode())
 
 
-def check(emu, text, keys, cap_log2=15):
+def check(emu, text, keys, cap_log2=15, scan_ctas=0):
     if len(text) == 0:
         return            # the product never launches the parse on an empty file (kvg_pciids_load, len == 0)
-    info, tables = run(emu, text, 1, cap_log2)
+    info, tables = run(emu, text, 1, cap_log2, scan_ctas)
     model = M.parse(text)
     v_off, sec_end, n_entries, n_lines, limit, overflow = (int(x) for x in info[0][:6])
     assert overflow == 0
     assert (v_off, sec_end, limit, n_lines) == (model["v_off"], model["sec_end"], model["limit"], model["n_lines"])
-    assert n_entries == len(model["table"])
     for dev, off in model["table"].items():       # every (device -> first line) pair, straight from the table
-        assert emu.emu_table_probe(tables[0].ctypes.data, cap_log2, (0x10de << 16) | dev) == off
+        assert int(tables[0][dev]) == off
+    assert int((tables[0] != NONE).sum()) == len(model["table"])   # nothing else was recorded
     for k in keys:
         assert emu_name(emu, text, info[0], tables[0], cap_log2, k) == O.get_device_name(text, k.encode()), k
 
 
-def test_emulated_kernels_on_shipped_pciids(emu):
+def test_k1_on_shipped_pciids(emu):
     text = util.pciids_text()
     names = util.pciids_names()["names"]
     rng = np.random.default_rng(5)
     keys = list(names)[::7] + ["%04x" % int(k) for k in rng.integers(0, 65536, 60)] + ["2330", "2901", "1b38", "ffff"]
-    check(emu, text, keys)
+    check(emu, text, keys, cap_log2=13)
+    check(emu, text, keys[:40], cap_log2=13, scan_ctas=7)     # 28 warps x ~14 spans each: the ring wraps many times
 
 
-def test_emulated_kernels_two_images_are_independent(emu):
+def test_k1_two_images_are_independent(emu):
     text = util.pciids_text()[:200_000] + b"10de  NVIDIA tail\n\t2901  GB100 [B200]\n"
-    info, tables = run(emu, text, 2)
+    info, tables = run(emu, text, 2, scan_ctas=5)
     assert (info[0] == info[1]).all() and (tables[0] == tables[1]).all()
-    assert int(info[0][2]) == len(M.parse(text)["table"])
+    assert int((tables[1] != NONE).sum()) == len(M.parse(text)["table"])
 
 
-def test_emulated_kernels_on_grammar_fuzz(emu):
+def test_k1_on_grammar_fuzz(emu):
     rng = np.random.default_rng(20250711)
     keys = ["%04x" % i for i in range(0, 40)]
     for it in range(40):
-        check(emu, _random_pciids(rng, int(rng.integers(1, 400))), keys, cap_log2=12)
+        check(emu, _random_pciids(rng, int(rng.integers(1, 400))), keys, cap_log2=12, scan_ctas=it % 3)
     for it in range(3):
-        check(emu, _random_pciids(rng, int(rng.integers(3000, 6000))), keys, cap_log2=14)
+        check(emu, _random_pciids(rng, int(rng.integers(3000, 6000))), keys, cap_log2=14, scan_ctas=1 + it)
 
 
-def test_emulated_kernels_span_boundaries_and_scanner_limit(emu):
+def test_k1_span_boundaries_and_scanner_limit(emu):
     S = M.SPAN
     base = b"8086  Intel\n\t1234  wrong vendor\n"
     for delta in list(range(-8, 9)) + [S - 8, S, S + 5]:
         pad_len = S - len(base) + delta - 2
         text = base + b"#" + b"c" * pad_len + b"\n" + b"10de  NVIDIA\n\t1234  Edge [case]\n" + \
             b"#" + b"d" * (S - 40) + b"\n\t5678  second tile\n10df  next\n\t9999  other\n"
-        check(emu, text, ("1234", "5678", "9999", "abcd"), cap_log2=10)
+        check(emu, text, ("1234", "5678", "9999", "abcd"), cap_log2=10, scan_ctas=delta % 2)
     many = b"10de  NVIDIA\n" + b"".join(b"\t%04x  dev %d\n" % (i, i) for i in range(0, 9000)) + b"1000 x\n\t0001  y\n"
-    check(emu, many, ("0000", "0100", "1fff", "2327", "2328", "0001"), cap_log2=15)
+    check(emu, many, ("0000", "0100", "1fff", "2327", "2328", "0001"), cap_log2=15, scan_ctas=2)
     tail = b"10de  NVIDIA\n\t1234  name\n"
     for n in (65535, 65536, 70000):
         check(emu, b"x" * n + b"\n" + tail, ("1234",), cap_log2=10)
@@ -121,6 +121,10 @@ def test_emulated_kernels_span_boundaries_and_scanner_limit(emu):
                  b"10de\n# c\n\t1234  after comment\n", b"10de  x\n10de  dup\n\t1234  under dup\n",
                  b"\t1234  line zero is a device line\n", b"10de  no newline at all\t1234"):
         check(emu, text, ("1234", "0000"), cap_log2=10)
-    # the densest span: every line a 10de device line before any header of its span (pending capacity)
+    # the densest span: every line a 10de device line in front of any header of its span
     dense = b"10de\n" + b"".join(b"\t%04x\n" % (i & 0xffff) for i in range(3000))
     check(emu, dense, ("0000", "0abc"), cap_log2=13)
+    # a 10de header whose device lines start exactly on a span boundary, and one ending a span
+    for k in (S - 13, S - 12, S - 1, S, S + 1):
+        text = b"#" + b"z" * (k - 2) + b"\n" + b"10de  NVIDIA\n\t1111  first\n" + b"#" + b"q" * 5000 + b"\n\t2222  resolved\n"
+        check(emu, text, ("1111", "2222"), cap_log2=10)

@@ -1,7 +1,7 @@
-"""The radix family of csrc/kvg_scan.cuh (k_radix_hist, k_radix_tilescan, k_radix_scatter<8|11>) and the
-experimental k_radix_tilescan_warp (csrc/kvg_radix_exp.cuh), executed on the CPU from their real kernel
-source under the warp emulator of tools/emu/ and checked against a stable numpy sort: device-chosen
-digit widths, multi-tile inputs, ragged last tiles, duplicate-heavy and full-width keys."""
+"""K4, the stable orderings of csrc/kvg_order.cuh (k_order_tilescan, k_order_scatter<8|11, 8>, k_order_final),
+executed on the CPU from their real kernel source under the warp emulator of tools/emu/ and checked against a
+stable numpy sort: device-chosen digit widths, multi-tile inputs, ragged last tiles, duplicate-heavy and
+full-width keys; both forms of the final step (one fused launch / count - offsets - emit)."""
 import ctypes as C
 import os
 import sys
@@ -44,52 +44,55 @@ CASES = [  # (n, key bits in the data, key_bits_max, max_bits)
 ]
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2], ids=["default", "tilescan_warp", "scatter_c"])
-def test_device_radix_sort_is_a_stable_sort(emu, variant):
-    rng = np.random.default_rng(17 + variant)
-    cases = CASES if variant == 0 else [(31, 5, 16, 11), (2049, 11, 32, 11), (5000, 19, 32, 11)]
-    for n, bits, kmax, mb in cases:       # the experimental kernels replace 11-bit-plan kernels only
+def want_passes(bits, kmax, mb):
+    return -(-max(1, min(bits, kmax)) // mb)
+
+
+def test_device_radix_sort_is_a_stable_sort(emu):
+    rng = np.random.default_rng(17)
+    for n, bits, kmax, mb in CASES:
         keys = rng.integers(0, 1 << bits, n, dtype=np.uint64).astype(np.uint32)
         keys[rng.integers(0, n)] = (1 << bits) - 1          # the widest key is present: the plan sees it
         if n > 100:
             keys[rng.integers(0, n, n // 3)] = keys[0]       # a heavy bucket: long runs of equal keys
-        got, npass = device_sort(emu, keys, kmax, mb, variant)
+        got, npass = device_sort(emu, keys, kmax, mb, 0)
         want_k, want_i = expected(keys)
-        assert npass == -(-min(bits, kmax) // mb), (n, bits, mb)
+        assert npass == want_passes(bits, kmax, mb), (n, bits, mb)
         assert np.array_equal(got["key"], want_k) and np.array_equal(got["idx"], want_i), (n, bits, kmax, mb)
 
 
-def test_experimental_kernels_agree_with_the_default_on_skewed_input(emu):
+def test_skewed_input(emu):
     rng = np.random.default_rng(5)
     keys = np.concatenate([np.full(3000, 7, np.uint32), rng.integers(0, 1 << 19, 1500, dtype=np.uint64).astype(np.uint32),
                            np.zeros(700, np.uint32)])
     rng.shuffle(keys)
     a, _ = device_sort(emu, keys, 32, 11, 0)
-    b, _ = device_sort(emu, keys, 32, 11, 3)      # both experimental kernels together
-    assert np.array_equal(a, b)
     want_k, want_i = expected(keys)
     assert np.array_equal(a["key"], want_k) and np.array_equal(a["idx"], want_i)
 
 
 def test_whole_ordering_permutation_segments_and_bucket_names(emu):
-    """radix passes + k_order_final<false> -> k_tile_offsets -> k_order_final<true>: the final permutation,
-    the distinct keys with their segment offsets, and (device-id ordering) each bucket's joined name slot."""
+    """radix passes + the final step (fused k_order_final, or k_order_heads<false> -> k_tile_offsets ->
+    k_order_heads<true>): the final permutation, the distinct keys with their segment offsets, and (device-id
+    ordering) each bucket's joined name slot."""
     emu.emu_ordering.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_void_p]
+                                 C.c_void_p, C.c_void_p, C.c_int]
     rng = np.random.default_rng(23)
-    for n, bits, kmax in ((1, 3, 16), (2048, 6, 16), (4500, 16, 16), (3000, 19, 32)):
+    for n, bits, kmax in ((1, 3, 16), (2048, 6, 16), (4500, 16, 16), (3000, 19, 32), (2500, 25, 32), (0, 1, 32)):
         keys = rng.integers(0, 1 << bits, n, dtype=np.uint64).astype(np.uint32)
-        surv = np.zeros((n, 4), dtype=np.uint32)
-        surv[:, 3] = (keys * 7 + 1) & 0xffff          # name slot: a function of the key, like the real join
+        if n:
+            keys[0] = (1 << bits) - 1
+        surv = np.zeros((max(n, 1), 4), dtype=np.uint32)
+        surv[:n, 3] = (keys * 7 + 1) & 0xffff          # name slot: a function of the key, like the real join
         pairs = np.zeros(n + 1, dtype=PAIR)
         pairs["key"][:n], pairs["idx"][:n] = keys, np.arange(n, dtype=np.uint32)
         perm = np.zeros(n + 1, np.uint32)
         seg_key, seg_off, seg_name = np.zeros(n + 2, np.uint32), np.zeros(n + 2, np.uint32), np.zeros(n + 2, np.uint32)
         n_seg = emu.emu_ordering(pairs.ctypes.data, n, surv.ctypes.data, kmax, 11, perm.ctypes.data, seg_key.ctypes.data,
-                                 seg_off.ctypes.data, seg_name.ctypes.data)
+                                 seg_off.ctypes.data, seg_name.ctypes.data, n % 2)
         order = np.argsort(keys, kind="stable")
         uniq, first = np.unique(keys[order], return_index=True)
-        assert n_seg == len(uniq)
+        assert n_seg == len(uniq), n_seg
         assert np.array_equal(perm[:n], order.astype(np.uint32))
         assert np.array_equal(seg_key[:n_seg], uniq) and np.array_equal(seg_off[:n_seg], first.astype(np.uint32))
         assert int(seg_off[n_seg]) == n

@@ -17,7 +17,7 @@ from oracle import oracle as O
 
 sys.path.insert(0, os.path.join(conftest.ROOT, "tools", "emu"))
 import build as emu_build  # noqa: E402
-from test_parse_v2_emu import pad  # noqa: E402
+from test_parse_k1_emu import pad  # noqa: E402
 
 PAIR = np.dtype([("key", "<u4"), ("idx", "<u4")])
 
@@ -25,14 +25,14 @@ PAIR = np.dtype([("key", "<u4"), ("idx", "<u4")])
 @pytest.fixture(scope="module")
 def libs():
     names = C.CDLL(emu_build.build_names())
-    names.emu_get_device_names.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
+    names.emu_get_device_names.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32,
                                            C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
                                            C.c_void_p]
     cls = C.CDLL(emu_build.build_classify())
     cls.emu_classify_pci.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     rdx = C.CDLL(emu_build.build_radix())
     rdx.emu_ordering.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_void_p]
+                                 C.c_void_p, C.c_void_p, C.c_int]
     return names, cls, rdx
 
 
@@ -43,7 +43,7 @@ def name_table(names, text, parser):
     pool_len, info = C.c_uint32(), np.zeros(8, dtype=np.uint32)
     key = np.zeros(1, dtype=np.uint8)
     off = np.zeros(1, dtype=np.uint32)
-    rc = names.emu_get_device_names(parser, buf.ctypes.data, len(text), 15, key.ctypes.data, off.ctypes.data, 0, None, 64, None,
+    rc = names.emu_get_device_names(buf.ctypes.data, len(text), key.ctypes.data, off.ctypes.data, 0, None, 64, None,
                                     info.ctypes.data, nv_index.ctypes.data, pool.ctypes.data, len(pool), C.byref(pool_len))
     assert rc == 0
     return nv_index, bytes(pool[:pool_len.value])
@@ -57,12 +57,12 @@ def ordering(rdx, surv, field, key_bits):
     seg_key, seg_off, seg_name = np.zeros(n + 2, np.uint32), np.zeros(n + 2, np.uint32), np.zeros(n + 2, np.uint32)
     raw = np.ascontiguousarray(surv).view(np.uint32).reshape(-1, 4) if n else np.zeros((1, 4), np.uint32)
     k = rdx.emu_ordering(pairs.ctypes.data, n, raw.ctypes.data, key_bits, 11, perm.ctypes.data, seg_key.ctypes.data,
-                         seg_off.ctypes.data, seg_name.ctypes.data)
+                         seg_off.ctypes.data, seg_name.ctypes.data, 1)
     assert k >= 0
     return seg_key[:k].copy(), seg_off[:k + 1].copy(), perm[:n].copy(), seg_name[:k].copy()
 
 
-@pytest.mark.parametrize("parser,variant", [(1, 1), (2, 0)], ids=["default_parse+oneshot", "parse_v2+ragged"])
+@pytest.mark.parametrize("parser,variant", [(3, 1), (3, 0)], ids=["K1+oneshot", "K1+ragged"])
 def test_create_iommu_device_map_from_kernel_source(libs, parser, variant):
     names, cls, rdx = libs
     text = util.pciids_text()
@@ -118,7 +118,7 @@ def test_key_partitioned_bucketing_from_kernel_source(libs):
                 buf = np.zeros(cnt + 1, dtype=PAIR)
                 buf[:cnt] = own
                 k = rdx.emu_ordering(buf.ctypes.data, cnt, raw.ctypes.data, bits, 11, perm.ctypes.data, sk.ctypes.data,
-                                     so.ctypes.data, sn.ctypes.data)
+                                     so.ctypes.data, sn.ctypes.data, 0)
                 for i in range(k):
                     assert int(sk[i]) not in union
                     union[int(sk[i])] = list(perm[so[i]:so[i + 1]])

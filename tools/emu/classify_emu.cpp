@@ -6,6 +6,10 @@
 #include "warp_emu.h"
 #include "kvgpu.h"
 namespace kvg {
+#include "emu_order.inc"
+}
+#include "../../kubevirt-gpu-device-plugin_b200/csrc/kvg_order.cuh"   // tile constants
+namespace kvg {
 #include "emu_classify.inc"
 }
 using namespace kvg;
@@ -24,16 +28,10 @@ int emu_classify_pci(const uint4* recs, uint32_t n, const uint32_t* nv_index, in
   std::vector<uint32_t> tile_count(tiles + 2, 0xdeadbeefu), tile_off(tiles + 3, 0xdeadbeefu);
   std::vector<uint2> tile_max(tiles + 2);
   std::vector<uint64_t> state(tiles + 4, 0);
-  PciIdsInfo info;
-  memset(&info, 0, sizeof info);
   PciClassifyOp op;
   op.recs = recs;
   op.n = n;
   op.ctrl = &ctrl;
-  op.table = nullptr;
-  op.cap_mask = 0;
-  op.cap_shift = 0;
-  op.info = &info;
   op.nv_index = nv_index;
   op.local_max_group = 0;
   op.local_max_dev = 0;
@@ -48,8 +46,8 @@ int emu_classify_pci(const uint4* recs, uint32_t n, const uint32_t* nv_index, in
     tt.o[0] = {tile_count.data(), tile_max.data(), nullptr, (uint32_t)tiles, tile_off.data(), &ctrl.n_surv, state.data()};
     tt.o[1] = tt.o[0];
     emu_launch(k_tile_offsets, dim3((unsigned)((tiles + C_TILE - 1) / C_TILE)), KVG_BLOCK, tt, &ctrl, epoch);
-    emu_launch(k_pack_survivors<1>, dim3((unsigned)tiles), 128, (const uint4*)ragged.data(), (const uint32_t*)tile_off.data(),
-               (uint32_t)(T * R), surv_out);
+    emu_launch(k_pack_survivors<1>, dim3((unsigned)tiles), 128, (const uint4*)ragged.data(),
+               (const uint32_t*)tile_off.data(), (uint32_t)(T * R), surv_out);
   }
   ctrl_out[0] = ctrl.n_surv;
   ctrl_out[1] = ctrl.max_group;
@@ -114,8 +112,8 @@ int emu_scan_mdev(const uint4* recs, uint32_t n, const uint8_t* raw, const uint3
     tt.o[0] = {tile_count.data(), tile_max.data(), nullptr, (uint32_t)tiles, tile_off.data(), &ctrl.n_surv, state.data()};
     tt.o[1] = tt.o[0];
     emu_launch(k_tile_offsets, dim3((unsigned)((tiles + C_TILE - 1) / C_TILE)), KVG_BLOCK, tt, &ctrl, 13u);
-    emu_launch(k_pack_survivors<2>, dim3((unsigned)tiles), 128, (const uint4*)ragged.data(), (const uint32_t*)tile_off.data(),
-               (uint32_t)(T * R), surv_out);
+    emu_launch(k_pack_survivors<2>, dim3((unsigned)tiles), 128, (const uint4*)ragged.data(),
+               (const uint32_t*)tile_off.data(), (uint32_t)(T * R), surv_out);
   }
   ctrl_out[0] = ctrl.n_surv;
   ctrl_out[1] = ctrl.max_group;

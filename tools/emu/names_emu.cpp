@@ -1,16 +1,49 @@
-// names_emu.cpp — getDeviceName end to end from kernel source on the CPU: the DEFAULT parse
-// (k_pciids_parse of csrc/kvg_parse.cuh, parser = 1) or the barrier-free one (csrc/kvg_parse_v2.cuh,
-// parser = 2), followed by the name path of csrc/kvg_parse.cuh exactly as the library sequences it
-// (kvg_api.cu: parse_enqueue / parse_enqueue_v2, table_publish, kvg_name_lookup, lookup_general):
-//   hash path      k_nv_index -> k_pciids_sanitise_lines -> pool[slot] = u16 length + bytes
-//   general path   k_section_lines -> k_lookup_general -> k_sanitise_matches   (non-canonical keys)
+// names_emu.cpp — getDeviceName end to end from kernel source on the CPU: K1 (csrc/kvg_parse_k1.cuh:
+// prep -> scan with the per-warp TMA ring -> resolve + finalize -> names) followed by the lookup path of
+// csrc/kvg_parse.cuh exactly as the library sequences it (kvg_api.cu: parse_enqueue, table_publish,
+// kvg_name_lookup, lookup_general):
+//   table path     nv_index[id] -> pool[slot] = u16 length + bytes        (4-lower-hex keys)
+//   general path   k_section_lines -> k_lookup_general -> k_sanitise_matches   (every other key)
 #define KVG_HOST_EMU 1
 #include "warp_emu.h"
 namespace kvg {
-#include "emu_parse_all.inc"   // all of csrc/kvg_parse.cuh: the default parse (TMA ring) and the name path
+#include "emu_parse_all.inc"   // all of csrc/kvg_parse.cuh
 }
-#include "../../kubevirt-gpu-device-plugin_b200/csrc/kvg_parse_v2.cuh"
+#include "../../kubevirt-gpu-device-plugin_b200/csrc/kvg_parse_k1.cuh"
 using namespace kvg;
+
+// K1 sequenced as parse_enqueue does.  scan_ctas = grid of the persistent scan kernel (0: one warp per
+// span).  nv_index / pool may be NULL (then the names kernel is skipped).
+static void run_k1(const uint8_t* text, uint64_t stride, uint32_t len, uint32_t n_files, uint32_t scan_ctas,
+                   uint32_t* dev_off, PciIdsInfo* info, uint32_t* nv_index, uint8_t* pool, uint32_t pool16) {
+  const uint32_t spf = (len + K1_SPAN - 1) / K1_SPAN, n_spans = spf * n_files;
+  std::vector<uint4> sums(n_spans + 1, make_uint4(0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu));  // poisoned
+  K1Args A;
+  A.text = text;
+  A.stride = stride;
+  A.len = len;
+  A.n_files = n_files;
+  A.spans_per_file = spf;
+  A.n_spans = n_spans;
+  A.dev_off = dev_off;
+  A.info = info;
+  A.span_sum = sums.data();
+  K1PrepArgs P;
+  P.dev_off = (uint4*)dev_off;
+  P.dev_off16 = (uint64_t)K1_IDS * n_files / 4;
+  P.info = info;
+  P.n_files = n_files;
+  P.nv_index = (uint4*)nv_index;
+  P.pool = (uint4*)pool;
+  P.pool16 = pool16;
+  emu_launch(k_pciids_prep, dim3(3), KVG_BLOCK, P);
+  unsigned grid = (n_spans + K1_WARPS - 1) / K1_WARPS;
+  if (scan_ctas && scan_ctas < grid) grid = scan_ctas;
+  if (n_spans) emu_launch(k_pciids_scan, dim3(grid), K1_WARPS * 32, A);
+  emu_launch(k_pciids_resolve_finalize, dim3(n_files + (n_spans + K1_RWARPS - 1) / K1_RWARPS), KVG_BLOCK, A);
+  if (nv_index)
+    emu_launch(k_pciids_names, dim3(K1_IDS / 32 / KVG_WARPS), KVG_BLOCK, (const uint32_t*)dev_off, text, len, info, nv_index, pool);
+}
 
 static bool canonical_key(const uint8_t* k, uint32_t n, uint32_t* v) {  // kvg_api.cu: 4 lower-case hex digits
   if (n != 4) return false;
@@ -26,90 +59,34 @@ static bool canonical_key(const uint8_t* k, uint32_t n, uint32_t* v) {  // kvg_a
 
 extern "C" {
 
+// K1 alone: n_files images (text + f*stride); outputs per image info[8 words] and the device-id table
+int emu_parse_k1(const uint8_t* text, uint64_t stride, uint32_t len, uint32_t n_files, uint32_t scan_ctas,
+                 uint32_t* info_out, uint32_t* dev_off_out) {
+  std::vector<uint32_t> dev_off((size_t)K1_IDS * n_files, 0x12345678u);  // poisoned: the prep kernel clears
+  std::vector<PciIdsInfo> info(n_files);
+  memset(info.data(), 0x5a, sizeof(PciIdsInfo) * n_files);
+  run_k1(text, stride, len, n_files, scan_ctas, dev_off.data(), info.data(), nullptr, nullptr, 0);
+  memcpy(info_out, info.data(), sizeof(PciIdsInfo) * n_files);
+  memcpy(dev_off_out, dev_off.data(), sizeof(uint32_t) * dev_off.size());
+  return 0;
+}
+
 // text: one image padded like kvg_text_pad.  keys: blob + n_keys+1 offsets.  names_out: n_keys x name_cap
 // bytes, names_len: n_keys.  Returns 0.
-int emu_get_device_names(int parser, const uint8_t* text, uint32_t len, uint32_t cap_log2, const uint8_t* keys,
-                         const uint32_t* key_off, uint32_t n_keys, uint8_t* names_out, uint32_t name_cap, uint32_t* names_len,
-                         uint32_t* info_out, uint32_t* nv_index_out, uint8_t* pool_out, uint32_t pool_cap, uint32_t* pool_len) {
-  const uint32_t spf = (len + V2_SPAN - 1) / V2_SPAN, n_spans = spf;
-  const size_t cap = (size_t)1 << cap_log2;
-  std::vector<uint64_t> table(cap, P_EMPTY);
+int emu_get_device_names(const uint8_t* text, uint32_t len, const uint8_t* keys, const uint32_t* key_off, uint32_t n_keys,
+                         uint8_t* names_out, uint32_t name_cap, uint32_t* names_len, uint32_t* info_out,
+                         uint32_t* nv_index_out, uint8_t* pool_out, uint32_t pool_cap, uint32_t* pool_len) {
   PciIdsInfo info;
-  memset(&info, 0, sizeof info);
-  info.v_off = P_NONE;
-  std::vector<uint32_t> arrays(3 * (size_t)n_spans + 1), state(2 * (size_t)n_spans + 1), pending((size_t)n_spans * V2_PEND_CAP + 1);
-  ParseV2Args A;
-  A.text = text;
-  A.stride = 0;
-  A.len = len;
-  A.n_files = 1;
-  A.spans_per_file = spf;
-  A.n_spans = n_spans;
-  A.tables = table.data();
-  A.cap_mask = (uint32_t)cap - 1;
-  A.cap_shift = 32 - cap_log2;
-  A.info = &info;
-  A.span_first_hdr = arrays.data();
-  A.span_first_nl = arrays.data() + n_spans;
-  A.span_last_nl = arrays.data() + 2 * (size_t)n_spans;
-  A.span_state = state.data();
-  A.pend_cnt = state.data() + n_spans;
-  A.pending = pending.data();
-  if (parser == 2) {
-    const unsigned grid = (n_spans + V2_WARPS - 1) / V2_WARPS;
-    if (n_spans) {
-      emu_launch(k_pciids_scan_v2, dim3(grid), V2_WARPS * 32, A);
-      emu_launch(k_pciids_resolve_v2, dim3(grid), V2_WARPS * 32, A);
-    }
-    ParseArgs F;
-    memset(&F, 0, sizeof F);
-    F.text = text;
-    F.len = len;
-    F.n_files = 1;
-    F.tiles_per_file = spf;
-    F.n_tiles = n_spans;
-    F.info = &info;
-    F.tile_first_hdr = A.span_first_hdr;
-    F.tile_first_nl = A.span_first_nl;
-    F.tile_last_nl = A.span_last_nl;
-    emu_launch(k_pciids_finalize_v2, dim3(1), KVG_BLOCK, F);
-  } else {
-    // parse_enqueue: ONE persistent CTA walks every tile in order (any grid <= n_tiles is legal on the GPU;
-    // a sequential emulation can only honour the look-back of a single CTA)
-    const uint32_t tpf = (len + P_TILE - 1) / P_TILE;
-    std::vector<uint32_t> tile_arrays(3 * (size_t)tpf + 1, 0xdeadbeefu);
-    std::vector<uint64_t> tile_state(tpf + 1, 0);
-    ParseArgs P;
-    memset(&P, 0, sizeof P);
-    P.text = text;
-    P.stride = 0;
-    P.len = len;
-    P.n_files = 1;
-    P.tiles_per_file = tpf;
-    P.n_tiles = tpf;
-    P.tables = table.data();
-    P.cap_mask = (uint32_t)cap - 1;
-    P.cap_shift = 32 - cap_log2;
-    P.info = &info;
-    P.tile_first_hdr = tile_arrays.data();
-    P.tile_first_nl = tile_arrays.data() + tpf;
-    P.tile_last_nl = tile_arrays.data() + 2 * (size_t)tpf;
-    P.tile_state = tile_state.data();
-    P.epoch = 5;
-    if (tpf) emu_launch(k_pciids_parse, dim3(1), KVG_BLOCK, P);
-    emu_launch(k_pciids_finalize, dim3(1), KVG_BLOCK, P);
-  }
+  memset(&info, 0x5a, sizeof info);
+  const uint32_t pool_bytes = (len + 16 + 15) & ~15u;
+  std::vector<uint32_t> dev_off(K1_IDS, 0x12345678u), nv_index(K1_IDS, 0x77777777u);
+  std::vector<uint8_t> k1_pool(pool_bytes, 0xee);
+  run_k1(text, 0, len, 1, 3, dev_off.data(), &info, nv_index.data(), k1_pool.data(), pool_bytes / 16);
   memcpy(info_out, &info, sizeof info);
-  if (info.overflow) return 1;
-  // ---- table_publish: nv_index + named lines, sanitised pool, candidate lines of the general lookup
-  std::vector<uint32_t> nv_index(65536), nv_lines(65536 + 8, 0);
-  emu_launch(k_nv_index, dim3(256), 256, (const uint64_t*)table.data(), A.cap_mask, A.cap_shift, (const PciIdsInfo*)&info,
-             nv_index.data(), nv_lines.data(), nv_lines.data() + 65536);
+  // ---- table_publish: the host mirrors sec + 16 bytes of the pool; the general lookup's candidate lines
   const size_t sec = info.v_off == P_NONE ? 0 : (size_t)info.sec_end - info.v_off;
   std::vector<uint8_t> pool(sec + 16, 0);
-  if (info.v_off != P_NONE)
-    emu_launch(k_pciids_sanitise_lines, dim3(64), KVG_BLOCK, text, len, (const PciIdsInfo*)&info, (const uint32_t*)nv_lines.data(),
-               (const uint32_t*)(nv_lines.data() + 65536), pool.data());
+  memcpy(pool.data(), k1_pool.data(), std::min(pool.size(), k1_pool.size()));
   const uint32_t sec_cap = (uint32_t)(sec / 2 + 8);
   std::vector<uint32_t> sec_lines(sec_cap + 1, 0);
   if (sec)
@@ -129,9 +106,7 @@ int emu_get_device_names(int parser, const uint8_t* text, uint32_t len, uint32_t
     names_len[k] = 0;
     uint32_t v;
     if (canonical_key(key, klen, &v)) {
-      uint32_t slot = P_NONE;
-      emu_launch(k_probe_keys, dim3(1), 32, (const uint64_t*)table.data(), A.cap_mask, A.cap_shift, (const PciIdsInfo*)&info, v, 1u,
-                 &slot);
+      const uint32_t slot = nv_index[v];
       if (slot == P_NONE) continue;
       const uint32_t n = pool[slot] | ((uint32_t)pool[slot + 1] << 8);
       if (n > name_cap) return 2;

@@ -6,7 +6,7 @@
 // execute, leave the block with runnable-but-blocked fibers only, which the scheduler reports as a
 // deadlock (abort) — the CPU-side picture of a mis-synchronised kernel.
 //
-// Test infrastructure only (tests/test_parse_v2_emu.py); never part of the product.
+// Test infrastructure only (tests/test_*_emu.py); never part of the product.
 #pragma once
 #include <ucontext.h>
 
@@ -64,6 +64,7 @@ static inline void emu_yield() {
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __launch_bounds__(...)
 #define __shared__ static
 #define __align__(n) __attribute__((aligned(n)))
@@ -75,6 +76,7 @@ constexpr uint32_t KVG_WARPS = KVG_BLOCK / 32;
 static inline uint32_t lane_id() { return threadIdx.x & 31u; }
 static inline uint32_t warp_id() { return threadIdx.x >> 5; }
 static inline void pdl_enter() {}
+static inline void __threadfence() {}
 static inline uint4 ld_stream(const uint4* p) { return *p; }
 static inline void st_stream(uint4* p, const uint4& v) { *p = v; }
 static inline uint64_t ld_relaxed_u64(const uint64_t* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
