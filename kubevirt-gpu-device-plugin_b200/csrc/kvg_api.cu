@@ -1880,10 +1880,14 @@ static int enqueue_exchange(kvg_ctx* ctx, const uint4* local, size_t n_cap, size
     ctx->h_counts[P] = total;  // pinned; the low 32 bits are the value (little endian)
     CK(cudaMemcpyAsync(&c->n_gathered, &ctx->h_counts[P], sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     n_ptr = &c->n_gathered;
-    if (!ctx->win_mine) {  // private window of the shape a peer window has
+    if (!ctx->win_mine || n_cap * U > ctx->win_cap) {  // private window of the shape a peer window has, grown on demand
+      CK(cudaStreamSynchronize(ctx->stream));
+      if (ctx->win_mine) cudaFree(ctx->win_mine);
+      ctx->win_mine = nullptr;
       size_t cap = std::max<size_t>(ctx->win_cap, n_cap * U);
-      ctx->win_cap = cap;
+      cap += cap / 4 + 64;
       CK(cudaMalloc((void**)&ctx->win_mine, window_bytes(P, cap)));
+      ctx->win_cap = cap;
       CK(cudaMemsetAsync(ctx->win_mine, 0, SH_HDR, ctx->stream));
       ctx->win_peer[ctx->rank] = ctx->win_mine;
     }

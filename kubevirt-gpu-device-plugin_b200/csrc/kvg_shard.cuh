@@ -168,8 +168,8 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_shard_send(ShardArgs A, ShardPeer
   pdl_enter();
   const uint32_t n = *A.n_ptr;
   const uint32_t tile = blockIdx.x;
-  __shared__ uint32_t s_base[2][SH_MAX_RANKS];  // running base of (ordering, owner) inside this tile, per warp walk
-  __shared__ uint32_t s_wcnt[KVG_WARPS][2][SH_MAX_RANKS];
+  __shared__ uint32_t s_wcnt[KVG_WARPS][2][SH_MAX_RANKS];   // per warp: survivors of every (ordering, owner)
+  __shared__ uint32_t s_wbase[KVG_WARPS][2][SH_MAX_RANKS];  // per warp: running position in the owner's region
   __shared__ uint32_t s_last;
   const uint32_t lane = lane_id(), warp = warp_id();
   // the window parity is rewritten: every owner must have consumed the step that used it two steps ago
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_shard_send(ShardArgs A, ShardPeer
       const uint32_t o = lane / A.P, q = lane - o * A.P;
       uint32_t b = A.tile_cnt[((size_t)o * A.P + q) * A.T + tile];
       for (uint32_t w = 0; w < warp; w++) b += s_wcnt[w][o][q];
-      s_wcnt[warp][o][q] = b;  // reuse: now the warp's base (only my own warp reads it again)
+      s_wbase[warp][o][q] = b;
     }
     __syncwarp();
 #pragma unroll
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_shard_send(ShardArgs A, ShardPeer
           }
         }
         if (q != SH_ALL) {
-          const uint32_t pos = s_wcnt[warp][o][q] + before;
+          const uint32_t pos = s_wbase[warp][o][q] + before;
           if (A.only == SH_ALL || q == A.only) {
             uint4* dst = peers.win[q] + shard_region(A, o, A.src, U) + (size_t)pos * U;
 #pragma unroll
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_shard_send(ShardArgs A, ShardPeer
           }
         }
         __syncwarp();
-        if (q != SH_ALL && before == 0) s_wcnt[warp][o][q] += total_q;  // the first lane of each owner advances the base
+        if (q != SH_ALL && before == 0) s_wbase[warp][o][q] += total_q;  // the first lane of each owner advances the base
         __syncwarp();
       }
     }

@@ -69,6 +69,30 @@ class MdevResultC(C.Structure):
                 ("par_perm", C.c_void_p)]
 
 
+class PciShardResultC(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("n_local", C.c_uint64), ("local", C.c_void_p),
+                ("n_dev_members", C.c_uint64), ("dev_members", C.c_void_p),
+                ("n_dev_keys", C.c_uint32), ("dev_keys", C.c_void_p), ("dev_off", C.c_void_p),
+                ("dev_perm", C.c_void_p), ("dev_name_slot", C.c_void_p),
+                ("n_grp_members", C.c_uint64), ("grp_members", C.c_void_p),
+                ("n_groups", C.c_uint32), ("grp_keys", C.c_void_p), ("grp_off", C.c_void_p),
+                ("grp_perm", C.c_void_p),
+                ("name_pool", C.c_void_p), ("name_pool_len", C.c_size_t)]
+
+
+class MdevShardResultC(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("n_local", C.c_uint64), ("local", C.c_void_p),
+                ("n_type_members", C.c_uint64), ("type_members", C.c_void_p),
+                ("n_type_keys", C.c_uint32), ("type_keys", C.c_void_p), ("type_off", C.c_void_p),
+                ("type_perm", C.c_void_p),
+                ("n_par_members", C.c_uint64), ("par_members", C.c_void_p),
+                ("n_parents", C.c_uint32), ("par_keys", C.c_void_p), ("par_off", C.c_void_p),
+                ("par_perm", C.c_void_p),
+                ("n_types", C.c_uint32), ("label_off", C.c_void_p), ("label_bytes", C.c_void_p),
+                ("type_canon", C.c_void_p), ("type_name_off", C.c_void_p),
+                ("type_name_bytes", C.c_void_p)]
+
+
 class HealthDeltaC(C.Structure):
     _fields_ = [("n_records", C.c_uint32), ("n_alive", C.c_uint32), ("n_changed", C.c_uint32),
                 ("changed", C.c_void_p)]
@@ -131,6 +155,9 @@ def load() -> C.CDLL:
         "kvg_comm_p2p_enable": (C.c_int, [vp, C.c_int]),
         "kvg_debug_radix_plan": (C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, vp, vp, vp]),
         "kvg_dev_scan_pci_sharded": (C.c_int, [vp, vp, sz]),
+        "kvg_dev_scan_pci_shard_fetch": (C.c_int, [vp, P(P(PciShardResultC))]),
+        "kvg_dev_scan_mdev_sharded": (C.c_int, [vp, vp, sz, P(TypeDict)]),
+        "kvg_dev_scan_mdev_shard_fetch": (C.c_int, [vp, P(P(MdevShardResultC))]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass
 
 import numpy as np
@@ -46,15 +47,50 @@ class MdevResult:
 
 
 @dataclass
+class PciShardResult:
+    """One rank's part of a sharded PCI scan (include/kvgpu.h kvg_pci_shard_result): its own shard's
+    survivors, and ALL members of the device ids / iommu groups it owns (key % nranks == rank)."""
+    n_records: int
+    local: np.ndarray           # PCI_SURV, this shard's survivors, Walk order
+    dev: PciResult              # deviceMap part: survivors = the owned members (grp_* arrays empty)
+    grp: PciResult              # iommuMap part:  survivors = the owned members (dev_* arrays empty)
+
+
+@dataclass
+class MdevShardResult:
+    n_records: int
+    local: np.ndarray           # MDEV_SURV
+    by_type: MdevResult         # vGpuMap part (par_* empty)
+    by_parent: MdevResult       # gpuVgpuMap part (type_* empty)
+
+
+@dataclass
 class HealthDelta:
     n_records: int
     n_alive: int
     changed: np.ndarray         # (index << 1) | now_alive
 
 
+class _LockedLib:
+    """A kvg_ctx is single-threaded (include/kvgpu.h).  gRPC handler threads, the health feed and the
+    Allocate re-validation all share one Context (kvgpu/serve.py), so every C call on it is serialised."""
+
+    def __init__(self, lib, lock):
+        self._lib, self._lock = lib, lock
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+
+        def call(*a):
+            with self._lock:
+                return fn(*a)
+        return call
+
+
 class Context:
     def __init__(self, device: int = 0):
-        self._lib = L.load()
+        self._lock = threading.RLock()
+        self._lib = _LockedLib(L.load(), self._lock)
         h = C.c_void_p()
         rc = self._lib.kvg_ctx_create(device, C.byref(h))
         if rc != 0:
@@ -292,3 +328,50 @@ class Context:
 
     def dev_scan_pci_sharded(self, d_recs: int, n_local: int):
         self._ck(self._lib.kvg_dev_scan_pci_sharded(self._h, d_recs, n_local))
+
+    def dev_scan_pci_shard_fetch(self) -> PciShardResult:
+        res = C.POINTER(L.PciShardResultC)()
+        self._ck(self._lib.kvg_dev_scan_pci_shard_fetch(self._h, C.byref(res)))
+        r = res.contents
+        KD, G = int(r.n_dev_keys), int(r.n_groups)
+        pool = C.string_at(r.name_pool, r.name_pool_len) if r.name_pool_len else b""
+        e32, e16 = np.zeros(0, np.uint32), np.zeros(0, np.uint16)
+        z32 = np.zeros(1, np.uint32)
+        dev = PciResult(int(r.n_records), L._arr(r.dev_members, int(r.n_dev_members), L.PCI_SURV),
+                        L._arr(r.dev_keys, KD, np.uint16), L._arr(r.dev_off, KD + 1, np.uint32),
+                        L._arr(r.dev_perm, int(r.n_dev_members), np.uint32), L._arr(r.dev_name_slot, KD, np.uint32),
+                        e32, z32, e32, pool)
+        grp = PciResult(int(r.n_records), L._arr(r.grp_members, int(r.n_grp_members), L.PCI_SURV),
+                        e16, z32, e32, e32, L._arr(r.grp_keys, G, np.uint32), L._arr(r.grp_off, G + 1, np.uint32),
+                        L._arr(r.grp_perm, int(r.n_grp_members), np.uint32), pool)
+        out = PciShardResult(int(r.n_records), L._arr(r.local, int(r.n_local), L.PCI_SURV), dev, grp)
+        self._lib.kvg_result_free(res)
+        return out
+
+    def dev_scan_mdev_sharded(self, d_recs: int, n_local: int, raw_types: list):
+        td, keep = self._type_dict(raw_types)
+        self._ck(self._lib.kvg_dev_scan_mdev_sharded(self._h, d_recs, n_local, C.byref(td)))
+        del keep
+
+    def dev_scan_mdev_shard_fetch(self) -> MdevShardResult:
+        res = C.POINTER(L.MdevShardResultC)()
+        self._ck(self._lib.kvg_dev_scan_mdev_shard_fetch(self._h, C.byref(res)))
+        r = res.contents
+        KT, NP, nt = int(r.n_type_keys), int(r.n_parents), int(r.n_types)
+        loff = L._arr(r.label_off, nt + 1, np.uint32)
+        noff = L._arr(r.type_name_off, nt + 1, np.uint32)
+        lbytes = C.string_at(r.label_bytes, int(loff[-1])) if nt and loff[-1] else b""
+        nbytes = C.string_at(r.type_name_bytes, int(noff[-1])) if nt and noff[-1] else b""
+        labels = [lbytes[loff[i]:loff[i + 1]] for i in range(nt)]
+        names = [nbytes[noff[i]:noff[i + 1]].decode("latin-1") for i in range(nt)]
+        canon = L._arr(r.type_canon, nt, np.uint16)
+        e32, e16, z32 = np.zeros(0, np.uint32), np.zeros(0, np.uint16), np.zeros(1, np.uint32)
+        by_type = MdevResult(int(r.n_records), L._arr(r.type_members, int(r.n_type_members), L.MDEV_SURV),
+                             L._arr(r.type_keys, KT, np.uint16), L._arr(r.type_off, KT + 1, np.uint32),
+                             L._arr(r.type_perm, int(r.n_type_members), np.uint32), labels, canon, names, e32, z32, e32)
+        by_parent = MdevResult(int(r.n_records), L._arr(r.par_members, int(r.n_par_members), L.MDEV_SURV),
+                               e16, z32, e32, labels, canon, names, L._arr(r.par_keys, NP, np.uint32),
+                               L._arr(r.par_off, NP + 1, np.uint32), L._arr(r.par_perm, int(r.n_par_members), np.uint32))
+        out = MdevShardResult(int(r.n_records), L._arr(r.local, int(r.n_local), L.MDEV_SURV), by_type, by_parent)
+        self._lib.kvg_result_free(res)
+        return out

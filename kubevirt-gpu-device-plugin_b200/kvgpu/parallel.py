@@ -1,16 +1,19 @@
 """Multi-GPU sharding of the scan (BASELINE.json config 4): one process per GPU.
 
-Records are range-partitioned in Walk order, rank r owns [r*N/P, (r+1)*N/P).  Every rank
-classifies its shard; ONE exchange step — an allgatherv of the 16-byte survivor records over
-NCCL/NVLink, rank order == Walk order — rebuilds the global survivor list on every rank, which
-then runs the (replicated) bucketing.  The pci.ids table is parsed by every rank itself.
+Records are range-partitioned in Walk order, rank r owns [r*N/P, (r+1)*N/P).  Every rank classifies its
+shard; its survivors stay local (rank order == Walk order: the host concatenates them for bdfToIommuMap).
+ONE exchange step sends every survivor to the OWNER of its key (key % P), once per group-by map, so each
+rank ends up with all members of the keys it owns — constant volume per GPU whatever P is.  Transport:
+stores into the owners' peer windows over NVLink (CUDA IPC), or — fallback — one NCCL allgatherv of the
+survivor lists followed by a local select.  The pci.ids table is parsed by every rank itself.
 
-`ShardedScan` needs only a byte-broadcast callable to distribute the 128-byte NCCL unique id, so
-the same class is driven by torch.distributed (bench.py) or by any other launcher.
+`ShardedScan` needs only byte collectives (broadcast for the 128-byte NCCL unique id, all-gather for the
+64-byte IPC handles), so the same class is driven by torch.distributed (bench.py) or any other launcher.
 """
 from __future__ import annotations
 
-from .context import Context, PciResult
+from .context import Context, MdevShardResult, PciResult, PciShardResult
+from .plugin import Maps, mdev_maps_from_result, pci_maps_from_result
 
 
 def shard_range(n: int, rank: int, world: int) -> tuple[int, int]:
@@ -53,12 +56,49 @@ def allgatherv_torch(local, dist_mod=None):
     return out, counts
 
 
+def pci_maps_from_shard(sh: PciShardResult) -> Maps:
+    """This rank's part of the three PCI maps: deviceMap / iommuMap for the keys it owns (all members),
+    bdfToIommuMap for its own shard's survivors."""
+    m = pci_maps_from_result(sh.dev)
+    part = Maps(deviceMap=m.deviceMap, deviceNames=m.deviceNames)
+    part.iommuMap = pci_maps_from_result(sh.grp).iommuMap
+    e = sh.dev.grp_perm[:0]
+    local = PciResult(sh.n_records, sh.local, sh.dev.dev_keys[:0], sh.dev.grp_off[:1], e, e, sh.dev.grp_keys[:0],
+                      sh.dev.grp_off[:1], e, b"")
+    part.bdfToIommuMap = pci_maps_from_result(local).bdfToIommuMap
+    return part
+
+
+def mdev_maps_from_shard(sh: MdevShardResult) -> Maps:
+    """This rank's part of vGpuMap (type labels it owns) and gpuVgpuMap (parents it owns)."""
+    a = mdev_maps_from_result(sh.by_type)
+    b = mdev_maps_from_result(sh.by_parent)
+    return Maps(vGpuMap=a.vGpuMap, gpuVgpuMap=b.gpuVgpuMap, deviceNames=a.deviceNames)
+
+
+def merge_parts(parts: list) -> Maps:
+    """Union of the ranks' parts (rank order): key sets are disjoint, bdfToIommuMap concatenates in rank
+    order == Walk order."""
+    out = Maps()
+    for p in parts:
+        for name in ("deviceMap", "iommuMap", "vGpuMap", "gpuVgpuMap"):
+            mine, theirs = getattr(out, name), getattr(p, name)
+            clash = set(mine) & set(theirs)
+            if clash:
+                raise ValueError("%s: key owned by two ranks: %r" % (name, sorted(clash)[:3]))
+            mine.update(theirs)
+        out.bdfToIommuMap.update(p.bdfToIommuMap)
+        out.deviceNames.update(p.deviceNames)
+    return out
+
+
 class ShardedScan:
     def __init__(self, ctx: Context, rank: int, world: int, broadcast_bytes, allgather_bytes=None,
                  p2p_cap: int = 0):
         """broadcast_bytes(b: bytes | None, src=0) -> bytes : collective byte broadcast (NCCL unique id).
-        allgather_bytes(b: bytes) -> list[bytes] (rank order) + p2p_cap (records per shard): also set
-        up the peer-memory exchange (CUDA IPC over NVLink); on any failure the NCCL path is used."""
+        allgather_bytes(b: bytes) -> list[bytes] (rank order) + p2p_cap (PCI records per shard; an mdev
+        record takes two): also set up the peer windows (CUDA IPC over NVLink); on any failure the NCCL
+        path is used."""
         self.ctx, self.rank, self.world = ctx, rank, world
         self.mode = "nccl"
         uid = ctx.comm_unique_id() if rank == 0 else None
@@ -84,8 +124,14 @@ class ShardedScan:
     def scan_device_shard(self, d_recs: int, n_local: int):
         self.ctx.dev_scan_pci_sharded(d_recs, n_local)
 
-    def fetch(self) -> PciResult:
-        return self.ctx.dev_scan_pci_fetch()
+    def fetch(self) -> PciShardResult:
+        return self.ctx.dev_scan_pci_shard_fetch()
+
+    def scan_device_mdev_shard(self, d_recs: int, n_local: int, raw_types: list):
+        self.ctx.dev_scan_mdev_sharded(d_recs, n_local, raw_types)
+
+    def fetch_mdev(self) -> MdevShardResult:
+        return self.ctx.dev_scan_mdev_shard_fetch()
 
     def close(self):
         self.ctx.comm_destroy()

@@ -1,5 +1,6 @@
-"""Worker for the multi-GPU parity test: rank r scans its shard on GPU r; the gathered result on
-every rank must equal the oracle on the unsharded snapshot."""
+"""Worker for the multi-GPU parity test: rank r scans its shard on GPU r (PCI records, then mdev records);
+the union of the ranks' parts — every rank holds the keys it owns, with ALL their members — must equal the
+oracle on the unsharded snapshot, byte for byte, for several back-to-back steps (window reuse, acks)."""
 import hashlib
 import os
 import sys
@@ -20,6 +21,8 @@ from oracle import oracle as O
 
 def main():
     n = int(sys.argv[1])
+    mode = sys.argv[2] if len(sys.argv) > 2 else "p2p"
+    m_total = int(sys.argv[3]) if len(sys.argv) > 3 else max(n // 8, 3)
     rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -41,39 +44,42 @@ def main():
         dist.all_gather(outs, t)
         return [bytes(o.cpu().numpy().tobytes()) for o in outs]
 
-    mode = sys.argv[2] if len(sys.argv) > 2 else "p2p"
-    sh = kvgpu.ShardedScan(ctx, rank, world, bcast, allgather if mode == "p2p" else None,
-                           (n + world - 1) // world + 1)
-    if mode == "p2p" and sh.mode != "p2p" and rank == 0:
-        print("note: peer-memory path unavailable, fell back to NCCL")
     lo, hi = kvgpu.shard_range(n, rank, world)
+    mlo, mhi = kvgpu.shard_range(m_total, rank, world)
+    cap = max((n + world - 1) // world + 1, 2 * ((m_total + world - 1) // world + 1))
+    sh = kvgpu.ShardedScan(ctx, rank, world, bcast, allgather if mode == "p2p" else None, cap)
+    if mode == "p2p" and sh.mode != "p2p" and rank == 0:
+        print("note: peer windows unavailable, fell back to NCCL")
     buf = torch.empty(max(hi - lo, 1) * 16, dtype=torch.uint8, device="cuda")
+    mbuf = torch.empty(max(mhi - mlo, 1) * 32, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
     ctx.dev_gen_pci(buf.data_ptr(), lo, hi - lo, ids, 17)
+    ctx.dev_gen_mdev(mbuf.data_ptr(), mlo, mhi - mlo)
+    types = O.gen_type_names(256)
+    want_m = O.Maps()
+    want_m.create_iommu_device_map_flat(O.gen_pci(0, n, ids, 17))
+    want_m.create_vgpu_id_map_flat(O.gen_mdev(0, m_total), types)
+    want = want_m.dump(text)
     trace = os.environ.get("KVG_WORKER_TRACE") == "1"
     for rep in range(4):   # > 2: exercises window reuse and the consumed-acks
         if trace:
             print("rank %d rep %d scan" % (rank, rep), file=sys.stderr, flush=True)
         sh.scan_device_shard(buf.data_ptr(), hi - lo)
         res = sh.fetch()
-        if trace:
-            print("rank %d rep %d fetched S=%d" % (rank, rep, len(res.survivors)), file=sys.stderr, flush=True)
-        part = kvgpu.pci_maps_from_result(res)
-        # the bucketing is partitioned by key: rank r owns the keys with key % world == r
+        part = kvgpu.pci_maps_from_shard(res)
+        # the maps are partitioned by key: rank r owns the keys with key % world == r
         assert all(int(k, 16) % world == rank for k in part.deviceMap), "foreign device key"
         assert all(int(k) % world == rank for k in part.iommuMap), "foreign iommu group"
+        sh.scan_device_mdev_shard(mbuf.data_ptr(), mhi - mlo, types)
+        mres = sh.fetch_mdev()
+        mpart = kvgpu.mdev_maps_from_shard(mres)
+        assert all(int(k) % world == rank for k in mres.by_type.type_keys), "foreign mdev type"
+        assert all(int(k) % world == rank for k in mres.by_parent.par_keys), "foreign parent"
+        part.vGpuMap, part.gpuVgpuMap = mpart.vGpuMap, mpart.gpuVgpuMap
+        part.deviceNames.update(mpart.deviceNames)
         parts = [None] * world
-        dist.all_gather_object(parts, (part.deviceMap, part.iommuMap, part.deviceNames))
-        merged = kvgpu.Maps(bdfToIommuMap=part.bdfToIommuMap)   # survivor list is replicated
-        for dm, im, nm in parts:                                # disjoint key sets: plain union
-            assert not (set(dm) & set(merged.deviceMap)) and not (set(im) & set(merged.iommuMap))
-            merged.deviceMap.update(dm)
-            merged.iommuMap.update(im)
-            merged.deviceNames.update(nm)
-        got = kvgpu.canonical_dump(merged)
-        m = O.Maps()
-        m.create_iommu_device_map_flat(O.gen_pci(0, n, ids, 17))
-        want = m.dump(text)
+        dist.all_gather_object(parts, part)
+        got = kvgpu.canonical_dump(kvgpu.merge_parts(parts))      # raises if a key is owned twice
         assert got == want, "rank %d rep %d: sharded dump differs (%s vs %s)" % (
             rank, rep, hashlib.sha256(got).hexdigest()[:12], hashlib.sha256(want).hexdigest()[:12])
     dist.barrier()

@@ -461,13 +461,14 @@ def _gpu_count():
         return 0
 
 
-@pytest.mark.skipif(_gpu_count() < 2, reason="needs at least 2 GPUs on the box")
 @pytest.mark.parametrize("mode", ["p2p", "nccl"])
 @pytest.mark.parametrize("n", [200_003, 5])
 def test_sharded_scan_matches_oracle(n, mode):
+    """One process per GPU of the box (world 1 on a single-GPU box: the exchange kernels — multisplit by
+    owner, window stores, flags, gather, acks — still run, with one owner).  PCI and mdev records."""
     import subprocess
     import sys
-    world = min(_gpu_count(), 8)
+    world = max(1, min(_gpu_count(), 8))
     here = os.path.dirname(os.path.abspath(__file__))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(29600 + n % 300 + (0 if mode == "p2p" else 301)),

@@ -1,0 +1,75 @@
+"""The exchange step of the sharded scan (csrc/kvg_shard.cuh: k_shard_count -> k_shard_scan -> k_shard_send ->
+k_shard_gather) executed on the CPU from its real kernel source: P emulated ranks with their own windows and
+control blocks, several back-to-back steps (window parities, acks), peer-window mode and the NCCL local mode,
+16-byte (PCI) and 32-byte (mdev) records.  Every rank must end up with exactly the records whose key it owns
+(key % P == rank), in Walk order (source-rank order, then position), for both orderings."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import conftest  # noqa: F401
+
+sys.path.insert(0, os.path.join(conftest.ROOT, "tools", "emu"))
+import build as emu_build  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def emu():
+    L = C.CDLL(emu_build.build_shard())
+    L.emu_exchange.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    return L
+
+
+def keys_of(recs, units):
+    w = recs.reshape(-1, units * 4)
+    if units == 1:
+        return w[:, 2] & 0xffff, w[:, 1]
+    return w[:, 5] & 0xffff, w[:, 4]
+
+
+@pytest.mark.parametrize("units", [1, 2])
+@pytest.mark.parametrize("P,local_mode", [(1, 0), (2, 0), (3, 0), (8, 0), (3, 1)])
+def test_exchange_by_owner(emu, units, P, local_mode):
+    rng = np.random.default_rng(100 * P + units + local_mode)
+    sizes = [int(x) for x in rng.integers(0, 5000, P)]
+    sizes[0] = 4500 if P > 1 else 2300
+    if P > 2:
+        sizes[1] = 0                                   # an empty shard
+    shards = []
+    for r in range(P):
+        recs = rng.integers(0, 1 << 32, (sizes[r], units * 4), dtype=np.uint64).astype(np.uint32)
+        recs[:, 0] = (r << 24) | np.arange(sizes[r])   # a Walk-order tag
+        shards.append(np.ascontiguousarray(recs))
+    if local_mode:                                     # NCCL: every rank works on the gathered list
+        gathered = np.ascontiguousarray(np.concatenate(shards))
+        lists = [gathered] * P
+        n = np.full(P, len(gathered), dtype=np.uint32)
+        cap = max(sizes) + 1
+        while P * cap < len(gathered) + 1:
+            cap += 1
+    else:
+        lists = shards
+        n = np.array(sizes, dtype=np.uint32)
+        cap = max(sizes) + 1
+    ptrs = (C.c_void_p * P)(*[a.ctypes.data if len(a) else None for a in lists])
+    owned_cap = P * cap
+    o0 = np.zeros((P, owned_cap, units * 4), dtype=np.uint32)
+    o1 = np.zeros((P, owned_cap, units * 4), dtype=np.uint32)
+    n_own = np.zeros(2 * P, dtype=np.uint32)
+    mx = np.zeros(2 * P, dtype=np.uint32)
+    rc = emu.emu_exchange(units, ptrs, n.ctypes.data, P, 4, cap, local_mode, o0.ctypes.data, o1.ctypes.data,
+                          n_own.ctypes.data, mx.ctypes.data)
+    assert rc == 0, rc
+    allrecs = np.concatenate(shards) if P else shards[0]
+    k0, k1 = keys_of(allrecs, units)
+    for r in range(P):
+        for o, (keys, got) in enumerate(((k0, o0), (k1, o1))):
+            want = allrecs[keys % P == r]
+            cnt = int(n_own[2 * r + o])
+            assert cnt == len(want), (r, o, cnt, len(want))
+            assert np.array_equal(got[r, :cnt], want), (r, o)
+            assert int(mx[2 * r + o]) == (int(keys[keys % P == r].max()) if len(want) else 0)

@@ -1,0 +1,102 @@
+// shard_emu.cpp — the exchange step of the sharded scan (csrc/kvg_shard.cuh: k_shard_count, k_shard_scan,
+// k_shard_send, k_shard_gather) compiled for the CPU from its real source on top of warp_emu.h.  P ranks are
+// emulated in ONE process: every rank has its own window + control block, `peers` points at all of them, and the
+// kernels of a step run rank after rank (all sends, then all gathers — the order the flags allow).
+#define KVG_HOST_EMU 1
+#include "warp_emu.h"
+#include "kvgpu.h"
+static inline long long clock64() { return 0; }
+static inline void __threadfence_system() {}
+namespace kvg {
+#include "emu_order.inc"
+}
+#include "../../kubevirt-gpu-device-plugin_b200/csrc/kvg_order.cuh"
+#include "../../kubevirt-gpu-device-plugin_b200/csrc/kvg_shard.cuh"
+using namespace kvg;
+
+template <int U>
+static int run(const uint4* const* lists, const uint32_t* n, uint32_t P, uint32_t steps, uint32_t cap, int local_mode,
+               uint4* owned0_out, uint4* owned1_out, uint32_t* n_own_out, uint32_t* max_out) {
+  // local_mode: NCCL path — lists[r] is the SAME gathered list on every rank, one source region
+  const uint32_t n_src = local_mode ? 1 : P;
+  const size_t region_cap = local_mode ? (size_t)P * cap : cap;
+  const size_t win_units = 2 * 2 * (size_t)n_src * region_cap * U;
+  std::vector<std::vector<uint4>> win(P, std::vector<uint4>(win_units, uint4{0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu}));
+  std::vector<ShardCtrl> ctrl(P);
+  memset(ctrl.data(), 0, sizeof(ShardCtrl) * P);
+  ShardPeers peers;
+  memset(&peers, 0, sizeof peers);
+  for (uint32_t q = 0; q < P; q++) {
+    peers.win[q] = win[q].data();
+    peers.ctrl[q] = &ctrl[q];
+  }
+  uint32_t err = 0;
+  for (uint32_t step = 1; step <= steps; step++) {
+    std::vector<std::vector<uint32_t>> cnt(P);
+    for (uint32_t r = 0; r < P; r++) {
+      const size_t T = (n[r] + C_TILE - 1) / C_TILE + 1;
+      cnt[r].assign(64 + 2 * (size_t)P * T, 0);
+      for (size_t i = 64; i < cnt[r].size(); i++) cnt[r][i] = 0xdeadbeefu;  // tile counts: nothing relies on zero
+      uint32_t nn = n[r];
+      ShardArgs A;
+      A.list = lists[r];
+      A.n_ptr = &nn;
+      A.tile_cnt = cnt[r].data() + 64;
+      A.totals = cnt[r].data();
+      A.ticket = cnt[r].data() + 32;
+      A.T = (uint32_t)T;
+      A.P = P;
+      A.me = r;
+      A.only = local_mode ? r : SH_ALL;
+      A.n_src = n_src;
+      A.src = local_mode ? 0 : r;
+      A.region_cap = region_cap;
+      A.parity = step & 1;
+      A.step = step;
+      emu_launch(k_shard_count<U>, dim3((unsigned)T), KVG_BLOCK, A);
+      emu_launch(k_shard_scan, dim3((2 * P + KVG_WARPS - 1) / KVG_WARPS), KVG_BLOCK, A);
+      emu_launch(k_shard_send<U>, dim3((unsigned)T), KVG_BLOCK, A, peers, (const ShardCtrl*)&ctrl[r], &err);
+      if (cnt[r][32] != 0) return -3;  // the ticket resets itself
+    }
+    for (uint32_t r = 0; r < P; r++) {
+      uint32_t nn = n[r];
+      const size_t T = (n[r] + C_TILE - 1) / C_TILE + 1;
+      ShardArgs A;
+      A.list = lists[r];
+      A.n_ptr = &nn;
+      A.tile_cnt = cnt[r].data() + 64;
+      A.totals = cnt[r].data();
+      A.ticket = cnt[r].data() + 32;
+      A.T = (uint32_t)T;
+      A.P = P;
+      A.me = r;
+      A.only = local_mode ? r : SH_ALL;
+      A.n_src = n_src;
+      A.src = local_mode ? 0 : r;
+      A.region_cap = region_cap;
+      A.parity = step & 1;
+      A.step = step;
+      const size_t owned_cap = (size_t)P * cap;
+      GatherArgs G;
+      G.window = win[r].data();
+      G.owned[0] = owned0_out + (size_t)r * owned_cap * U;
+      G.owned[1] = owned1_out + (size_t)r * owned_cap * U;
+      G.n_own = n_own_out + 2 * r;
+      max_out[2 * r] = max_out[2 * r + 1] = 0;
+      G.max_key = max_out + 2 * r;
+      emu_launch(k_shard_gather<U>, dim3(3, 2), KVG_BLOCK, A, G, peers, (const ShardCtrl*)&ctrl[r], &err);
+      if (cnt[r][33] != 0) return -4;
+    }
+  }
+  return err ? -5 : 0;
+}
+
+extern "C" {
+// lists: P pointers to dense record lists (units x 16 bytes per record), n[P] their lengths.  Outputs per rank
+// r at owned{0,1}_out + r * P * cap * units: the owned lists; n_own_out[2r + o], max_out[2r + o].
+int emu_exchange(int units, const uint4* const* lists, const uint32_t* n, uint32_t P, uint32_t steps, uint32_t cap,
+                 int local_mode, uint4* owned0_out, uint4* owned1_out, uint32_t* n_own_out, uint32_t* max_out) {
+  if (units == 1) return run<1>(lists, n, P, steps, cap, local_mode, owned0_out, owned1_out, n_own_out, max_out);
+  return run<2>(lists, n, P, steps, cap, local_mode, owned0_out, owned1_out, n_own_out, max_out);
+}
+}
