@@ -107,6 +107,67 @@ def cpu_baseline(text, ids, sample, threads):
             "host_cores": os.cpu_count()}
 
 
+def _expect_survivors(recs):
+    """numpy restatement of the classification (device_plugin.go:201-244) on the oracle generator's records:
+    survivors in Walk order as (addr, iommu_group, device, numa)."""
+    alive = (recs["vendor"] == 0x10de) & ((recs["flags"] & 15) == 0) & ((recs["driver"] == 1) | (recs["driver"] == 2))
+    s = recs[alive]
+    numa = np.where(((s["flags"] & 16) != 0) | (s["numa"] < 0), 0, s["numa"]).astype(np.uint16)
+    return s["addr"], s["iommu_group"], s["device"], numa
+
+
+def _check_members(got, exp, sel, what):
+    addr, grp, dev, numa = exp
+    ok = (len(got) == int(sel.sum()) and np.array_equal(got["addr"], addr[sel]) and
+          np.array_equal(got["iommu_group"], grp[sel]) and np.array_equal(got["device"], dev[sel]) and
+          np.array_equal(got["numa"], numa[sel]))
+    if not ok:
+        raise AssertionError("parity: %s differ from the CPU restatement" % what)
+
+
+def _check_ordering(members, field, keys, off, perm, what):
+    k = members[field].astype(np.int64)
+    order = np.argsort(k, kind="stable")
+    uk, first = np.unique(k[order], return_index=True)
+    if not (np.array_equal(keys.astype(np.int64), uk) and np.array_equal(off[:-1].astype(np.int64), first) and
+            int(off[-1]) == len(k) and np.array_equal(perm.astype(np.int64), order)):
+        raise AssertionError("parity: %s ordering differs from a stable sort" % what)
+
+
+def check_parity(ctx, sharded, rank, world, n, ids, gbits, text, O):
+    """Exact check of THIS run's output before anything is timed.  N = 1: the fetched result of kvg_dev_scan_pci;
+    N > 1: this rank's part of the sharded scan — its shard's survivors, and ALL members of the device ids /
+    iommu groups it owns (key % N == rank), both orderings — against a numpy group-by of the same synthetic
+    records (oracle generator) over ALL shards.  Raises on the first difference."""
+    exp = _expect_survivors(O.gen_pci(0, n * world, ids, gbits))
+    addr, grp, dev, numa = exp
+    if sharded is None:
+        res = ctx.dev_scan_pci_fetch()
+        _check_members(res.survivors, exp, np.ones(len(addr), bool), "survivors")
+        dev_res = grp_res = res
+    else:
+        res = sharded.fetch()
+        lo = np.searchsorted(addr, rank * n), np.searchsorted(addr, (rank + 1) * n)   # addr == Walk index here
+        sel = np.zeros(len(addr), bool)
+        sel[lo[0]:lo[1]] = True
+        _check_members(res.local, exp, sel, "rank %d shard survivors" % rank)
+        _check_members(res.dev.survivors, exp, dev.astype(np.int64) % world == rank, "rank %d owned deviceMap members" % rank)
+        _check_members(res.grp.survivors, exp, grp.astype(np.int64) % world == rank, "rank %d owned iommuMap members" % rank)
+        dev_res, grp_res = res.dev, res.grp
+    _check_ordering(dev_res.survivors, "device", dev_res.dev_keys, dev_res.dev_off, dev_res.dev_perm, "deviceMap")
+    _check_ordering(grp_res.survivors, "iommu_group", grp_res.grp_keys, grp_res.grp_off, grp_res.grp_perm, "iommuMap")
+    for k in range(0, len(dev_res.dev_keys), max(1, len(dev_res.dev_keys) // 48)):   # the name join, sampled
+        key = b"%04x" % int(dev_res.dev_keys[k])
+        if dev_res.name_at(int(dev_res.dev_name_slot[k])) != O.get_device_name(text, key):
+            raise AssertionError("parity: resource name of device id %s differs from the oracle" % key.decode())
+    return {"status": "ok", "checked": ("survivor list, both orderings (keys, offsets, stable permutation) and a "
+                                        "sample of joined names" if sharded is None else
+                                        "this rank's shard survivors, all members of the keys it owns, both "
+                                        "orderings and a sample of joined names; every rank checks its own part"),
+            "against": "numpy group-by of the oracle generator's records + oracle getDeviceName",
+            "survivors_global": int(len(addr))}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU algorithm (oracle port; the Go binary cannot be
     built in this image) on the host cores, bounded sample per step."""
@@ -115,7 +176,7 @@ def run_reference(args, rank, world):
     from oracle import oracle as O
     text = load_pciids()
     ids = O.nv_ids(text)
-    sample = min(args.records, args.ref_sample)
+    sample = min(args.records, args.ref_sample) if args.ref_sample else args.records
     recs = O.gen_pci(0, sample, ids, GROUP_BITS_FOR(sample))
     for _ in range(min(args.warmup, 1)):
         O.bench_faithful(recs, text)
@@ -131,9 +192,10 @@ def run_reference(args, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/u32 (byte + integer)", "data": "synthetic",
-        "config": {"workload": "full pci.ids (1,536,458 B) name lookups + %d of %d synthetic PCI "
-                               "records per step (bounded sample)" % (sample, args.records),
-                   "records_per_step": sample},
+        "config": {"workload": "BASELINE.json configs[1]: full pci.ids (1,536,458 B) name lookups + %d synthetic PCI "
+                               "records per step%s" % (sample, "" if sample == args.records else
+                                                       " (bounded sample of %d)" % args.records),
+                   "records_per_step": sample, "same_config_as_gpu_arm": sample == args.records},
         "cpu_baseline": {"value": value, "unit": "records/s", "cores": 1, "kind": "port",
                          "sample": "%d records/step x %d steps, faithful-cost C restatement of the "
                                    "Go scan (single goroutine in the reference => 1 thread)" % (
@@ -154,13 +216,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--records", type=int, default=1_000_000, help="PCI records per rank per step")
-    ap.add_argument("--ref-sample", type=int, default=100_000)
+    ap.add_argument("--ref-sample", type=int, default=0,
+                    help="records per step of the reference arm (0 = the full --records workload: same config)")
     ap.add_argument("--cpu-sample", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the config-3 / config-5 legs")
     ap.add_argument("--big-records", type=int, default=1 << 24,
                     help="records for the HBM-bound roofline leg (N=1 only; 0 disables)")
-    ap.add_argument("--big-files", type=int, default=128,
+    ap.add_argument("--big-files", type=int, default=256,
                     help="pci.ids images for the HBM-bound parse roofline leg (0 disables)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -213,7 +276,9 @@ def main():
             dist.all_gather(outs, t)
             return [bytes(o.cpu().numpy().tobytes()) for o in outs]
         use_p2p = os.environ.get("KVG_P2P", "1") != "0"
-        sharded = kvgpu.ShardedScan(ctx, rank, world, bcast, allgather if use_p2p else None, n)
+        c4_pci, c4_mdev = (12_000_000, 500_000) if (not args.no_extra and world == 8) else (0, 0)
+        sharded = kvgpu.ShardedScan(ctx, rank, world, bcast, allgather if use_p2p else None,
+                                    max(n, c4_pci, 2 * c4_mdev) + 1)
 
     def step():
         ctx.dev_pciids_parse(d_text.data_ptr(), len(text), pad + 16, 1)
@@ -234,6 +299,12 @@ def main():
         step()
     sync_all()
     S, KD, G = ctx.dev_scan_pci_count()
+    # ---- parity of what is about to be timed (every rank checks its own part; a mismatch aborts the run)
+    parity = check_parity(ctx, sharded, rank, world, n, ids, gbits, text, O)
+    if world > 1:
+        flags = [None] * world
+        dist.all_gather_object(flags, parity["status"])
+        assert all(f == "ok" for f in flags)
 
     # ---- timed region: K steps, CUDA events on the launching stream, L2 flushed between steps
     sampler = ClockSampler(local_rank)
@@ -265,34 +336,36 @@ def main():
     # ---- per-kernel times (separate pass, events around every launch) -> roofline
     ctx.set_kernel_timing(True)
     per = {}
-    for _ in range(max(3, min(args.steps, 10))):
+    passes = max(3, min(args.steps, 10))
+    for _ in range(passes):
         ctx.dev_flush_l2()
         ctx.set_kernel_timing(True)
         step()
         for name, ms in ctx.kernel_times():
             per.setdefault(name, []).append(ms)
     ctx.set_kernel_timing(False)
-    passes = max(3, min(args.steps, 10))
     ksum = {k: sum(v) / passes for k, v in per.items()}          # ms per step per kernel name
     kavg = {k: sum(v) / len(v) for k, v in per.items()}          # ms per launch
+    nl = {k: len(v) / passes for k, v in per.items()}            # launches per step
     S, KD, G = ctx.dev_scan_pci_count()
     info = ctx.pciids_info()
-    S_local = S if not sharded else S // world   # survivors this rank classified (its shard)
-    # radix passes of the group ordering: the same plan the kernels derive on the device
+    # members each ordering sorts on this rank: all survivors (N = 1) or the members of the owned keys
+    S_ord = S if not sharded else parity["survivors_global"] // world
     import ctypes as _C
     _np, _sh, _bt = _C.c_uint32(), (_C.c_uint32 * 4)(), (_C.c_uint32 * 4)()
     kvgpu.load().kvg_debug_radix_plan((1 << int(gbits)) - 1 if gbits else max(n // 2, 1), 32,
                                       8 if n >= (8 << 20) else 11, _C.byref(_np), _sh, _bt)
     grp_passes = max(1, int(_np.value))
-    # ALGORITHMIC bytes per step of every kernel family (DESIGN.md "Kernels"): what must move.
+    # IMPLEMENTATION bytes per step of every kernel family (what this implementation moves; the CONTRACT
+    # figure of SURVEY.md 8(d), 16 N + 24 S per scan, is reported separately as whole_scan_contract)
     algo = {
-        "pciids_parse": len(text) + 8 * info["n_entries"],
-        "classify_compact": 16 * n + 16 * S_local,            # every record read, every survivor written
-        "pack_survivors": 32 * S_local,                       # ragged -> dense
-        "radix_hist": 4 * S * 2 + 8 * S * (1 + (grp_passes - 1)),     # pass 0 keys, later passes pairs
-        "radix_scatter": 16 * S * (2 + grp_passes),           # 8 B read + 8 B written per pair per pass
-        "order_count": (8 * S + 4 * S) * 2,                   # pairs read, permutation written
-        "order_emit": 8 * S * 2 + 8 * (KD + G),
+        "pciids_parse": len(text) + 16 * ((len(text) + 4095) // 4096),   # text once + one 16-byte summary per span
+        "classify_compact": 16 * n + 16 * S,                   # every record read, every survivor written
+        "order_hist": 4 * S_ord * 2 + 8 * S_ord * (1 + (grp_passes - 1)),
+        "order_scatter": 16 * S_ord * (2 + grp_passes),        # 8 B read + 8 B written per pair per pass
+        "order_final": (8 * S_ord + 4 * S_ord) * 2 + 8 * (KD + G),
+        "shard_send": 16 * S * 3,                              # survivors read, one record stored per ordering
+        "shard_gather": 2 * 32 * S_ord,                        # window regions -> dense owned lists
     }
     main_kernels = [k for k in algo if k in ksum]
     dominant = max(main_kernels, key=lambda k: ksum.get(k, 0.0))
@@ -303,11 +376,10 @@ def main():
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
                 "frac": ach / hbm_peak, "traffic": None, "algorithmic_bytes": nbytes,
                 "avg_launch_ms": ms / launches_per_step, "peak_source": peak_src}
-    nl = {k: len(v) / passes for k, v in per.items()}     # launches per step
     # DRAM traffic per launch from the committed ncu --set full captures (never measured here: a
     # number taken under a profiler is not a bench number, and ncu is not run by bench.py)
     try:
-        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")))
+        ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
     except (OSError, ValueError):
         ncu_traffic = {}
 
@@ -317,11 +389,20 @@ def main():
     roofline = roof(dominant, algo[dominant], ksum[dominant], nl[dominant])
     if n == 1_000_000:
         roofline["traffic"] = traffic_for(dominant + "@config2")
-        roofline["traffic_note"] = "per launch, from profiles/r01_ncu_traffic.json (ncu --set full capture of the same kernel and size)"
+        roofline["traffic_note"] = "per launch, from profiles/r02_ncu_traffic.json (ncu --set full capture of the same kernel and size)"
     roofline["share_of_step"] = ksum[dominant] / step_ms
-    roofline["note"] = ("bytes and time are per STEP for the whole kernel family (all its launches); "
-                        "at this 1M-record config every kernel is latency-bound — see roofline_hbm_bound")
-    kernel_rooflines = {k: {"ms_per_step": ksum[k], "share": ksum[k] / step_ms,
+    roofline["note"] = ("dominant kernel FAMILY of the step at this config (all its launches; per-kernel event timing "
+                        "adds ~5 us per launch, so shares are indicative); at 1 M records every kernel is "
+                        "latency-bound — the HBM-bound fractions are in roofline_hbm_bound")
+    # the contract figure: bytes that MUST move for one scan (every record read once, every survivor written
+    # once, two 4-byte permutation entries per survivor) over the time the whole scan takes
+    scan_ms = sum(v for k, v in ksum.items() if not k.startswith("pciids"))
+    contract = 16 * n + 24 * S
+    roofline["whole_scan_contract"] = {"bytes": contract, "scan_ms_sum_of_kernels": scan_ms,
+                                       "GBps": contract / (scan_ms * 1e-3) / 1e9 if scan_ms else None,
+                                       "frac": contract / (scan_ms * 1e-3) / 1e9 / hbm_peak if scan_ms else None,
+                                       "what": "(16 N + 24 S) / sum of the scan's kernel times at THIS config (latency-bound)"}
+    kernel_rooflines = {k: {"ms_per_step": ksum[k], "share": ksum[k] / step_ms, "launches_per_step": nl[k],
                             "GBps": algo[k] / (ksum[k] * 1e-3) / 1e9, "frac": algo[k] / (ksum[k] * 1e-3) / 1e9 / hbm_peak}
                         for k in main_kernels}
 
@@ -334,18 +415,42 @@ def main():
         ctx.dev_gen_pci(big.data_ptr(), 0, nb, ids, GROUP_BITS_FOR(nb))
         for _ in range(3):
             ctx.dev_scan_pci(big.data_ptr(), nb)
-        ts = []
+        ts, packs, offs = [], [], []
         for _ in range(5):
             ctx.set_kernel_timing(True)
             ctx.dev_scan_pci(big.data_ptr(), nb)
             kt = ctx.kernel_times()
-            ts.append(dict((k, v) for k, v in kt if k == "classify_compact")["classify_compact"])
+            d = {}
+            for k, v in kt:
+                d.setdefault(k, []).append(v)
+            ts.append(d["classify_compact"][0])
+            packs.append(d.get("pack_survivors", [0.0])[0])
+            offs.append(d.get("tile_offsets", [0.0])[0])
             tot_ms = sum(v for _, v in kt)
-        Sb = ctx.dev_scan_pci_count()[0]
+        # the same scan WITHOUT per-kernel events (programmatic dependent launch on): the honest whole-scan time
         ctx.set_kernel_timing(False)
-        r = roof("classify_compact", 16 * nb + 16 * Sb, sum(ts) / len(ts))
-        r.update({"records": nb, "survivors": Sb, "whole_scan_ms": tot_ms,
-                  "whole_scan_records_per_s": nb / (tot_ms * 1e-3)})
+        evs2 = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ext)
+            ctx.dev_scan_pci(big.data_ptr(), nb)
+            e1.record(ext)
+            evs2.append((e0, e1))
+        Sb = ctx.dev_scan_pci_count()[0]
+        whole_ms = sum(a.elapsed_time(b) for a, b in evs2) / len(evs2)
+        cl = sum(ts) / len(ts)
+        r = roof("classify_compact", 16 * nb + 16 * Sb, cl)
+        comp_ms = cl + sum(packs) / len(packs) + sum(offs) / len(offs)
+        r.update({"records": nb, "survivors": Sb, "whole_scan_ms": whole_ms,
+                  "whole_scan_ms_sum_of_event_timed_kernels": tot_ms,
+                  "whole_scan_records_per_s": nb / (whole_ms * 1e-3),
+                  "compaction": {"what": "classify + tile offsets + pack = filter + STABLE compaction (the ragged "
+                                         "classify kernel alone is the `achieved` figure above)",
+                                 "ms": comp_ms, "GBps": (16 * nb + 16 * Sb) / (comp_ms * 1e-3) / 1e9,
+                                 "frac": (16 * nb + 16 * Sb) / (comp_ms * 1e-3) / 1e9 / hbm_peak},
+                  "whole_scan_contract": {"bytes": 16 * nb + 24 * Sb,
+                                          "GBps": (16 * nb + 24 * Sb) / (whole_ms * 1e-3) / 1e9,
+                                          "frac": (16 * nb + 24 * Sb) / (whole_ms * 1e-3) / 1e9 / hbm_peak}})
         r["traffic"] = traffic_for("classify_compact@%d" % nb)
         roofline_big["classify_compact"] = r
         del big
@@ -357,17 +462,24 @@ def main():
         c2 = kvgpu.Context(local_rank)
         for _ in range(3):
             c2.dev_pciids_parse(bigt.data_ptr(), len(text), stride, nf)
-        ts = []
+        ts, fam = [], []
         for _ in range(5):
             c2.set_kernel_timing(True)
             c2.dev_pciids_parse(bigt.data_ptr(), len(text), stride, nf)
-            kt = c2.kernel_times()
-            ts.append(dict(kt)["pciids_parse"])
+            kt = dict(c2.kernel_times())
+            ts.append(kt["pciids_parse"])
+            fam.append(kt["pciids_parse"] + kt.get("pciids_resolve", 0.0))
         c2.set_kernel_timing(False)
         ent = c2.pciids_info()["n_entries"]
-        r = roof("pciids_parse", nf * (len(text) + 8 * ent), sum(ts) / len(ts))
-        r.update({"images": nf, "text_bytes": nf * len(text), "entries_per_image": ent,
-                  "parse_GBps_text_only": nf * len(text) / (sum(ts) / len(ts) * 1e-3) / 1e9})
+        spans = (len(text) + 4095) // 4096
+        r = roof("pciids_parse", nf * (len(text) + 16 * spans), sum(ts) / len(ts))
+        fam_ms = sum(fam) / len(fam)
+        r.update({"images": nf, "text_bytes": nf * len(text), "entries_image0": ent,
+                  "parse_GBps_text_only": nf * len(text) / (sum(ts) / len(ts) * 1e-3) / 1e9,
+                  "scan_plus_resolve": {"ms": fam_ms, "GBps": nf * len(text) / (fam_ms * 1e-3) / 1e9,
+                                        "frac": nf * len(text) / (fam_ms * 1e-3) / 1e9 / hbm_peak,
+                                        "what": "k_pciids_scan + k_pciids_resolve_finalize (the lines of the NVIDIA "
+                                                "block are recorded by the resolve pass)"}})
         r["traffic"] = traffic_for("pciids_parse@%d" % nf)
         roofline_big["pciids_parse"] = r
         c2.close()
@@ -407,7 +519,7 @@ def main():
         rng = np.random.default_rng(5)
         lib.kvg_health_reset(ctx.handle)
         lat = []
-        ticks = 3000
+        ticks = 10_000
         period = 1e-3
         t_next = time.perf_counter()
         for tick in range(ticks + 50):
@@ -431,6 +543,60 @@ def main():
                                           "max_us": float(lat.max()),
                                           "what": "host wall time from snapshot-in-pinned-buffer to "
                                                   "transition list on the host (H2D 160 KB + K6 + D2H)"}
+
+    # ---- BASELINE.json config 4 as stated: mixed passthrough + vGPU, 100 M records over 8 GPUs
+    if world == 8 and not args.no_extra:
+        c4_types = O.gen_type_names(256)
+        d4 = torch.empty(c4_pci * 16, dtype=torch.uint8, device="cuda")
+        m4 = torch.empty(c4_mdev * 32, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        ctx.dev_gen_pci(d4.data_ptr(), rank * c4_pci, c4_pci, ids, GROUP_BITS_FOR(c4_pci * world))
+        ctx.dev_gen_mdev(m4.data_ptr(), rank * c4_mdev, c4_mdev)
+
+        def c4_step():
+            sharded.scan_device_shard(d4.data_ptr(), c4_pci)
+            sharded.scan_device_mdev_shard(m4.data_ptr(), c4_mdev, c4_types)
+        for _ in range(2):
+            c4_step()
+        sync_all()
+        # size-independent properties of the sharded result (the exact check ran at the headline size)
+        r4, q4 = sharded.fetch(), sharded.fetch_mdev()
+        cnt = torch.tensor([len(r4.local), len(r4.dev.survivors), len(r4.grp.survivors), len(q4.local),
+                            len(q4.by_type.survivors), len(q4.by_parent.survivors)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(cnt)
+        cnt = [int(x) for x in cnt.tolist()]
+        assert cnt[0] == cnt[1] == cnt[2] and cnt[3] == cnt[4] == cnt[5], cnt   # every survivor has exactly one owner per map
+        assert np.all(r4.dev.survivors["device"].astype(np.int64) % world == rank)
+        assert np.all(r4.grp.survivors["iommu_group"].astype(np.int64) % world == rank)
+        assert np.all(np.diff(r4.local["addr"].astype(np.int64)) > 0) and np.all(np.diff(r4.dev.survivors["addr"].astype(np.int64)) > 0)
+        _check_ordering(r4.dev.survivors, "device", r4.dev.dev_keys, r4.dev.dev_off, r4.dev.dev_perm, "config 4 deviceMap")
+        _check_ordering(r4.grp.survivors, "iommu_group", r4.grp.grp_keys, r4.grp.grp_off, r4.grp.grp_perm, "config 4 iommuMap")
+        _check_ordering(q4.by_type.survivors, "type_key", q4.by_type.type_keys, q4.by_type.type_off, q4.by_type.type_perm, "config 4 vGpuMap")
+        _check_ordering(q4.by_parent.survivors, "parent", q4.by_parent.par_keys, q4.by_parent.par_off, q4.by_parent.par_perm, "config 4 gpuVgpuMap")
+        del r4, q4
+        evs4 = []
+        sync_all()
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(ext)
+            c4_step()
+            e1.record(ext)
+            evs4.append((e0, e1))
+        sync_all()
+        t4 = torch.tensor([sum(a.elapsed_time(b) for a, b in evs4) / len(evs4)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+        t4 = float(t4.item())
+        per_rank_bytes = 16 * c4_pci + 24 * (cnt[0] // world) + 32 * c4_mdev + 24 * (cnt[3] // world)
+        extra["config4_sharded_100M"] = {
+            "records_total": (c4_pci + c4_mdev) * world, "pci_per_rank": c4_pci, "mdev_per_rank": c4_mdev,
+            "pci_survivors_total": cnt[0], "mdev_survivors_total": cnt[3], "ms_per_scan_max_over_ranks": t4,
+            "records_per_s": (c4_pci + c4_mdev) * world / (t4 * 1e-3),
+            "per_rank_contract_GBps": per_rank_bytes / (t4 * 1e-3) / 1e9,
+            "per_rank_contract_frac": per_rank_bytes / (t4 * 1e-3) / 1e9 / hbm_peak,
+            "nvlink_out_bytes_per_rank": 2 * 16 * (cnt[0] // world) + 2 * 32 * (cnt[3] // world),
+            "exchange": sharded.mode, "parity": "properties: one owner per survivor and map (all-reduced counts), "
+            "key % 8 == rank, Walk order inside every list, both orderings == stable sort, on every rank"}
+        del d4, m4
 
     # ---- end to end through the reference-facing calls: pinned host in, host results out
     e2e = None
@@ -494,16 +660,16 @@ def main():
         import ctypes as C
 
         def e2e_step():
-            rc = lib.kvg_pciids_load(ctx.handle, p_text.data_ptr(), len(text))
+            rc = lib.kvg_pciids_load(ctx.handle, p_text.data_ptr(), len(text))      # pinned: copy + parse enqueued
             assert rc == 0
-            d_recs[:n * 16].copy_(p_recs[:n * 16], non_blocking=True)   # H2D of the rank's shard
-            torch.cuda.current_stream().synchronize()
+            with torch.cuda.stream(ext):                                           # the rank's shard: async, same stream
+                d_recs[:n * 16].copy_(p_recs[:n * 16], non_blocking=True)
             sharded.scan_device_shard(d_recs.data_ptr(), n)
-            res = C.POINTER(kvgpu._lib.PciResultC)()
-            rc = lib.kvg_dev_scan_pci_fetch(ctx.handle, C.byref(res))       # gathered result -> host
+            res = C.POINTER(kvgpu._lib.PciShardResultC)()
+            rc = lib.kvg_dev_scan_pci_shard_fetch(ctx.handle, C.byref(res))        # THIS rank's parts -> host
             assert rc == 0
             r = res.contents
-            out = (int(r.n_survivors), int(r.n_dev_keys), int(r.n_groups))
+            out = (int(r.n_local), int(r.n_dev_members), int(r.n_grp_members), int(r.n_dev_keys), int(r.n_groups))
             lib.kvg_result_free(res)
             return out
         for _ in range(3):
@@ -519,8 +685,8 @@ def main():
         e2e = {"value": n * world * args.steps / te, "unit": "records/s",
                "ms_per_step": 1e3 * te / args.steps,
                "h2d_bytes_per_step": len(text) + 16 * n,
-               "d2h_bytes_per_step": int(r[0] * 24 + r[1] * 10 + r[2] * 8),
-               "timing": "host wall clock, max over ranks"}
+               "d2h_bytes_per_step": int(16 * (r[0] + r[1] + r[2]) + 4 * (r[1] + r[2]) + 10 * r[3] + 8 * r[4]),
+               "timing": "host wall clock, max over ranks; per rank: pinned shard in, its parts of the result out"}
 
     if rank == 0:
         cpu = None
@@ -534,16 +700,17 @@ def main():
             "config": {"workload": "BASELINE.json configs[1]: full utils/pci.ids (%d B, %d lines) parse "
                                    "+ %d synthetic PCI records per GPU per step%s" % (
                                        len(text), info["n_lines"], n,
-                                       "" if world == 1 else ", range-sharded over %d GPUs, survivors all-gathered "
-                                       "(%s), bucketing partitioned by key" % (
-                                           world, "pack fused with peer-memory stores over NVLink"
-                                           if sharded.mode == "p2p" else "NCCL grouped broadcast")),
+                                       "" if world == 1 else ", range-sharded over %d GPUs, every survivor sent to the "
+                                       "owner of its key once per map (%s), maps partitioned by key" % (
+                                           world, "stores into the owners' peer windows over NVLink"
+                                           if sharded.mode == "p2p" else "NCCL allgatherv + local select")),
                        "exchange": None if world == 1 else sharded.mode,
                        "records_per_gpu": n, "survivors": S, "device_ids": KD, "iommu_groups": G,
                        "iommu_group_order": "bijective scramble of i>>1 (group_bits=%d)" % gbits,
                        "l2": "flushed between timed steps (192 MiB fill, outside the event bracket)",
                        "wall_s_timed_loop_incl_flush": t_wall},
             "pciids_parse_GBps": len(text) / (kavg.get("pciids_parse", 0) * 1e-3) / 1e9 if kavg.get("pciids_parse") else None,
+            "parity": parity,
             "roofline": roofline,
             "kernel_rooflines": kernel_rooflines,
             "roofline_hbm_bound": roofline_big,

@@ -1358,6 +1358,54 @@ int kvg_health_reset(kvg_ctx* ctx) {
 int kvg_health_rescan(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, kvg_health_delta** delta) {
   if (!ctx || !delta || (!recs && n) || n > 0x7fffffffull) return KVG_EINVAL;
   CK(cudaSetDevice(ctx->device));
+  if (n && n <= HEALTH_SMALL_MAX && !ctx->timing) {
+    // poll-loop sizes: one kernel reads the snapshot in place (mapped pinned memory) and writes the transition
+    // list and the counters straight into the host-visible result block; one synchronisation
+    if (ctx->health_n != n) {
+      ENSURE(ctx->alive_prev, n + 1);
+      CK(cudaMemsetAsync(ctx->alive_prev.p, 0, n + 1, ctx->stream));
+      ctx->health_n = n;
+    }
+    cudaPointerAttributes attr;
+    const void* dev_view = nullptr;
+    if (cudaPointerGetAttributes(&attr, recs) == cudaSuccess && attr.type == cudaMemoryTypeHost) dev_view = attr.devicePointer;
+    cudaGetLastError();
+    if (!dev_view) {  // pageable caller memory (cgo rule: never keep the pointer): stage it in pinned memory
+      if (ctx->h_stage_cap < n * 16) {
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr;
+        ctx->h_stage_cap = 0;
+        CK(cudaMallocHost(&ctx->h_stage, n * 16 + 4096));
+        ctx->h_stage_cap = n * 16 + 4096;
+      }
+      memcpy(ctx->h_stage, recs, n * 16);
+      dev_view = ctx->h_stage;
+    }
+    const size_t o_list = align64(sizeof(kvg_health_delta)) + 64;  // [header][2 counters, padded][list]
+    void* blk = pinned_alloc(ctx, o_list + align64(n * 4));
+    if (!blk) return KVG_ENOMEM;
+    uint8_t* b = pinned_payload(blk);
+    uint32_t* hdr = (uint32_t*)(b + align64(sizeof(kvg_health_delta)));
+    LAUNCH("health_diff", k_health_small, 1, HEALTH_SMALL_THREADS, 0, (const uint4*)dev_view, (uint32_t)n,
+           ctx->alive_prev.p, (uint32_t*)(b + o_list), hdr);
+    int rc = check_launch(ctx, "health");
+    if (rc == KVG_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      ctx->err = "health re-scan failed";
+      rc = KVG_ECUDA;
+    }
+    if (rc) {
+      ctx->pinned_free.push_back({blk, (size_t)((uint64_t*)blk)[1]});
+      return rc;
+    }
+    kvg_health_delta* d = (kvg_health_delta*)b;
+    d->n_records = (uint32_t)n;
+    d->n_alive = hdr[0];
+    d->n_changed = hdr[1];
+    d->changed = (const uint32_t*)(b + o_list);
+    *delta = d;
+    ctx->last_kind = 0;
+    return KVG_OK;
+  }
   ENSURE(ctx->recs, n + 1);
   ENSURE(ctx->changed, n + 1);
   ENSURE(ctx->classify_state, (n + C_TILE - 1) / C_TILE + 1);

@@ -39,10 +39,16 @@
 
 namespace kvg {
 
-constexpr uint32_t K1_SPAN = 4096;                 // text bytes owned by one warp iteration
+#ifndef KVG_K1_SPAN
+#define KVG_K1_SPAN 4096
+#endif
+#ifndef KVG_K1_STAGES
+#define KVG_K1_STAGES 2
+#endif
+constexpr uint32_t K1_SPAN = KVG_K1_SPAN;          // text bytes owned by one warp iteration
 constexpr uint32_t K1_HALO = 16;                   // a line starting on the span's last byte is classified
 constexpr uint32_t K1_STAGE = K1_SPAN + K1_HALO;   // one TMA transaction (multiple of 16)
-constexpr uint32_t K1_STAGES = 2;
+constexpr uint32_t K1_STAGES = KVG_K1_STAGES;
 constexpr uint32_t K1_WARPS = 4;                   // warps (independent span streams) per CTA
 constexpr uint32_t K1_ROWS = K1_SPAN / 1024;       // 4 rows; a lane owns bytes [l*16, +16) of both row halves
 constexpr uint32_t K1_SMEM = K1_WARPS * K1_STAGES * K1_STAGE;
@@ -366,7 +372,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_resolve_finalize(K1Args A)
       if (t < A.spans_per_file && sum[t].y == 0) continue;
       int u = (int)t - 1;
       while (u >= 0 && sum[u].y == 0) u--;
-      if ((int)t - u < 15) continue;  // the line that ends in span t is shorter than 15 * 4 KiB
+      if (((uint32_t)((int)t - u) + 1) * K1_SPAN < SCAN_TOKEN_MAX) continue;  // that line cannot reach 64 KiB
       uint32_t fn = A.len;            // first newline at or after span t
       if (t < A.spans_per_file) {
         fn = t * K1_SPAN;

@@ -87,6 +87,34 @@ def test_health_diff_kernel_reports_transitions_in_record_order(emu):
         prev = now
 
 
+def test_health_small_kernel_one_cta(emu):
+    """K6 at poll-loop sizes = k_health_small (one CTA, the transition list and the counters written where the
+    host reads them): same contract as the look-back form, at sizes around the row and CTA boundaries."""
+    emu.emu_health_small.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+    ids = O.nv_ids(util.pciids_text())
+    drop = 1 | 2 | 4 | 8
+    rng = np.random.default_rng(6)
+    for n in (1, 1023, 1024, 1025, 10_000, 32_768):
+        recs = O.gen_pci(0, n, ids, 0)
+        alive_prev = np.zeros(n + 1, dtype=np.uint8)
+        prev = np.zeros(n, dtype=bool)
+        for tick in range(3):
+            if tick:
+                flip = rng.integers(0, n, 10)
+                recs["driver"][flip] = rng.integers(0, 5, 10)
+            changed = np.zeros(n + 1, dtype=np.uint32)
+            hdr = np.zeros(2, dtype=np.uint32)
+            assert emu.emu_health_small(np.ascontiguousarray(recs).ctypes.data, n, alive_prev.ctypes.data,
+                                        changed.ctypes.data, hdr.ctypes.data) == 0
+            now = (recs["vendor"] == 0x10de) & ((recs["flags"] & drop) == 0) & ((recs["driver"] == 1) | (recs["driver"] == 2))
+            idx = np.nonzero(now != prev)[0]
+            want = (idx.astype(np.uint32) << 1) | now[idx].astype(np.uint32)
+            assert int(hdr[0]) == int(now.sum()) and int(hdr[1]) == len(want), (n, tick)
+            assert np.array_equal(changed[:len(want)], want)
+            assert np.array_equal(alive_prev[:n].astype(bool), now)
+            prev = now
+
+
 def test_mdev_dictionary_and_classification_from_kernel_source(emu):
     """K5: label rule (Trim "\\n", \\s+ -> "_", device_plugin.go:341-342), equal labels merge into the
     smallest raw index, drop rules :270-279, NUMA clamp, survivors in Walk order with their source index."""

@@ -83,43 +83,3 @@ def test_create_iommu_device_map_from_kernel_source(libs, parser, variant):
         m = O.Maps()
         m.create_iommu_device_map_flat(recs)
         assert got == m.dump(text), (n, gbits)
-
-
-def test_key_partitioned_bucketing_from_kernel_source(libs):
-    """Multi-GPU bucketing (kvg_dev_scan_pci_sharded): every rank selects the pairs whose key % P == rank
-    (OwnedPairOp through the classification machinery + k_pack_pairs) and orders only those; the union
-    of the per-rank buckets is the single-GPU result and no key appears on two ranks."""
-    names, cls, rdx = libs
-    cls.emu_own_select.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
-    ids = O.nv_ids(util.pciids_text())
-    recs = O.gen_pci(9, 2400, ids, 10)
-    nv_index = np.zeros(65536, dtype=np.uint32)
-    surv = np.zeros(len(recs) + 1, dtype=kvgpu.PCI_SURV)
-    ctrl = np.zeros(3, dtype=np.uint32)
-    assert cls.emu_classify_pci(np.ascontiguousarray(recs).ctypes.data, len(recs), nv_index.ctypes.data, 0,
-                                surv.ctypes.data, ctrl.ctypes.data) == 0
-    surv = surv[:int(ctrl[0])].copy()
-    raw = np.ascontiguousarray(surv).view(np.uint32).reshape(-1, 4)
-    for field, name, bits in ((0, "device", 16), (1, "iommu_group", 32)):
-        whole_keys, whole_off, whole_perm, _ = ordering(rdx, surv, name, bits)
-        whole = {int(k): list(whole_perm[whole_off[i]:whole_off[i + 1]]) for i, k in enumerate(whole_keys)}
-        for P in ((2,) if field == 0 else (3,)):
-            union = {}
-            for r in range(P):
-                pairs = np.zeros(len(surv) + 1, dtype=PAIR)
-                mk = C.c_uint32()
-                cnt = cls.emu_own_select(raw.ctypes.data, len(surv), field, P, r, pairs.ctypes.data, C.byref(mk))
-                own = pairs[:cnt]
-                assert np.all(own["key"] % P == r) and np.array_equal(own["idx"], np.nonzero(surv[name] % P == r)[0])
-                assert cnt == 0 or mk.value == int(own["key"].max())
-                # order the owned pairs exactly like a rank does (pass 0 reads the packed pairs)
-                perm = np.zeros(cnt + 1, np.uint32)
-                sk, so, sn = np.zeros(cnt + 2, np.uint32), np.zeros(cnt + 2, np.uint32), np.zeros(cnt + 2, np.uint32)
-                buf = np.zeros(cnt + 1, dtype=PAIR)
-                buf[:cnt] = own
-                k = rdx.emu_ordering(buf.ctypes.data, cnt, raw.ctypes.data, bits, 11, perm.ctypes.data, sk.ctypes.data,
-                                     so.ctypes.data, sn.ctypes.data, 0)
-                for i in range(k):
-                    assert int(sk[i]) not in union
-                    union[int(sk[i])] = list(perm[so[i]:so[i + 1]])
-            assert union == whole, (name, P)

@@ -77,6 +77,14 @@ int emu_health_rescan(const uint4* recs, uint32_t n, uint8_t* alive_prev, uint32
   return 0;
 }
 
+// K6 at poll-loop sizes (kvg_health_rescan, n <= 32,768): one CTA, transitions + counters written where the
+// host reads them.  hdr_out: {n_alive, n_changed}.
+int emu_health_small(const uint4* recs, uint32_t n, uint8_t* alive_prev, uint32_t* changed_out, uint32_t* hdr_out) {
+  if (n == 0 || n > HEALTH_SMALL_MAX) return -1;
+  emu_launch(k_health_small, dim3(1), HEALTH_SMALL_THREADS, recs, n, alive_prev, changed_out, hdr_out);
+  return 0;
+}
+
 // K5 (kvg_dev_scan_mdev up to the survivor list): type dictionary -> labels -> canonical ids, then the
 // 32-byte mdev records through k_classify_ragged<MdevClassifyOp,128,4> -> k_tile_offsets -> k_pack_survivors<2>.
 // raw / raw_off: the dictionary blob with n_types+1 offsets.  Outputs: label bytes per entry (at raw_off),
@@ -119,40 +127,6 @@ int emu_scan_mdev(const uint4* recs, uint32_t n, const uint8_t* raw, const uint3
   ctrl_out[1] = ctrl.max_group;
   ctrl_out[2] = ctrl.max_devkey;
   return 0;
-}
-
-// Sharded scan, bucketing partitioned by key (enqueue_orderings, owned_only): rank r of P selects the
-// {key, index} pairs of the gathered survivor list whose key % P == r, for one ordering
-// (field 0 = device id, 1 = iommu group).  pairs_out: room for n pairs.  Returns the owned count.
-int emu_own_select(const uint4* surv, uint32_t n, uint32_t field, uint32_t nranks, uint32_t rank, uint2* pairs_out,
-                   uint32_t* max_key_out) {
-  constexpr int T = 128, R = 8;
-  const size_t tiles = (n + (size_t)T * R - 1) / ((size_t)T * R);
-  if (!tiles) return 0;
-  ScanCtrl ctrl;
-  memset(&ctrl, 0, sizeof ctrl);
-  ctrl.n_surv = n;
-  std::vector<uint2> ragged((tiles + 1) * T * R);
-  std::vector<uint32_t> tile_count(tiles + 2), tile_off(tiles + 3);
-  std::vector<uint2> tile_max(tiles + 2);
-  std::vector<uint64_t> state(tiles + 4, 0);
-  OwnedPairOp op;
-  op.surv = surv;
-  op.n_ptr = &ctrl.n_surv;
-  op.out = ragged.data();
-  op.field = field;
-  op.nranks = nranks;
-  op.rank = rank;
-  op.local_max = 0;
-  emu_launch(k_classify_ragged<OwnedPairOp, T, R>, dim3((unsigned)tiles), T, op, tile_count.data(), tile_max.data());
-  TileOffsetsArgs2 tt;
-  tt.o[0] = {tile_count.data(), tile_max.data(), nullptr, (uint32_t)tiles, tile_off.data(), &ctrl.n_own[field], state.data()};
-  tt.o[1] = tt.o[0];
-  emu_launch(k_tile_offsets, dim3((unsigned)((tiles + C_TILE - 1) / C_TILE)), KVG_BLOCK, tt, &ctrl, 17u);
-  emu_launch(k_pack_pairs, dim3((unsigned)tiles), 128, (const uint2*)ragged.data(), (const uint32_t*)tile_off.data(),
-             (uint32_t)(T * R), pairs_out);
-  *max_key_out = field ? ctrl.max_group : ctrl.max_devkey;
-  return (int)ctrl.n_own[field];
 }
 
 }  // extern "C"

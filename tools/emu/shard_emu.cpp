@@ -5,8 +5,6 @@
 #define KVG_HOST_EMU 1
 #include "warp_emu.h"
 #include "kvgpu.h"
-static inline long long clock64() { return 0; }
-static inline void __threadfence_system() {}
 namespace kvg {
 #include "emu_order.inc"
 }

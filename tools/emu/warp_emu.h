@@ -77,6 +77,8 @@ static inline uint32_t lane_id() { return threadIdx.x & 31u; }
 static inline uint32_t warp_id() { return threadIdx.x >> 5; }
 static inline void pdl_enter() {}
 static inline void __threadfence() {}
+static inline void __threadfence_system() {}
+static inline long long clock64() { return 0; }
 static inline uint4 ld_stream(const uint4* p) { return *p; }
 static inline void st_stream(uint4* p, const uint4& v) { *p = v; }
 static inline uint64_t ld_relaxed_u64(const uint64_t* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
