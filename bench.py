@@ -221,6 +221,8 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the config-3 / config-5 legs")
+    ap.add_argument("--config4", action="store_true",
+                    help="run the config-4 leg (12 M PCI + 0.5 M mdev records per rank) at any N > 1, not only at N = 8")
     ap.add_argument("--big-records", type=int, default=1 << 24,
                     help="records for the HBM-bound roofline leg (N=1 only; 0 disables)")
     ap.add_argument("--big-files", type=int, default=256,
@@ -276,7 +278,8 @@ def main():
             dist.all_gather(outs, t)
             return [bytes(o.cpu().numpy().tobytes()) for o in outs]
         use_p2p = os.environ.get("KVG_P2P", "1") != "0"
-        c4_pci, c4_mdev = (12_000_000, 500_000) if (not args.no_extra and world == 8) else (0, 0)
+        run_c4 = not args.no_extra and (world == 8 or args.config4)
+        c4_pci, c4_mdev = (12_000_000, 500_000) if run_c4 else (0, 0)
         sharded = kvgpu.ShardedScan(ctx, rank, world, bcast, allgather if use_p2p else None,
                                     max(n, c4_pci, 2 * c4_mdev) + 1)
 
@@ -545,7 +548,7 @@ def main():
                                                   "transition list on the host (H2D 160 KB + K6 + D2H)"}
 
     # ---- BASELINE.json config 4 as stated: mixed passthrough + vGPU, 100 M records over 8 GPUs
-    if world == 8 and not args.no_extra:
+    if world > 1 and run_c4:
         c4_types = O.gen_type_names(256)
         d4 = torch.empty(c4_pci * 16, dtype=torch.uint8, device="cuda")
         m4 = torch.empty(c4_mdev * 32, dtype=torch.uint8, device="cuda")
@@ -595,7 +598,7 @@ def main():
             "per_rank_contract_frac": per_rank_bytes / (t4 * 1e-3) / 1e9 / hbm_peak,
             "nvlink_out_bytes_per_rank": 2 * 16 * (cnt[0] // world) + 2 * 32 * (cnt[3] // world),
             "exchange": sharded.mode, "parity": "properties: one owner per survivor and map (all-reduced counts), "
-            "key % 8 == rank, Walk order inside every list, both orderings == stable sort, on every rank"}
+            "key % world == rank, Walk order inside every list, both orderings == stable sort, on every rank"}
         del d4, m4
 
     # ---- end to end through the reference-facing calls: pinned host in, host results out
@@ -722,8 +725,11 @@ def main():
             "clocks": clocks,
         }
         print(json.dumps(line))
-    # free torch tensors before the context (and its stream) goes away
-    del d_recs, d_text
+    # free torch tensors before the context (and its stream) goes away — pinned ones too: the host allocator
+    # records an event on every stream a pinned block was used on when the block is freed
+    del d_recs, d_text, p_recs, p_text
+    import gc
+    gc.collect()
     torch.cuda.synchronize()
     if sharded:
         sharded.close()

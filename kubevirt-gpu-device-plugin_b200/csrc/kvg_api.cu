@@ -202,6 +202,7 @@ struct kvg_ctx {
   DevBuf<uint8_t> alive_prev;
   DevBuf<uint32_t> changed;
   size_t health_n = 0;
+  uint32_t health_seq = 0;
   // misc
   DevBuf<uint4> flush;
   DevBuf<uint16_t> nv_ids;
@@ -229,7 +230,8 @@ struct kvg_ctx {
   size_t win_cap = 0;                    // PCI records per region (an mdev record takes two)
   uint8_t* win_peer[SH_MAX_RANKS] = {};  // peer-mapped bases (own entry = win_mine)
   unsigned long long shard_step = 0;
-  DevBuf<uint32_t> shard_cnt;            // [2][P] totals, 2 tickets, 1 error word (64-word header), then [2][P][T] tile counts
+  DevBuf<uint32_t> shard_cnt;            // [2][P] totals, 2 tickets, 1 error word (64-word header)
+  DevBuf<uint64_t> shard_state;          // [2][P][T] chained-scan words of k_shard_send
   uint32_t* shard_err = nullptr;         // that error word (device)
   DevBuf<uint4> owned0, owned1;          // dense owned lists of ordering 0 / 1
   DevBuf<uint4> gathered;                // NCCL mode: the all-gathered survivor list
@@ -440,7 +442,7 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   release(ctx->changed); release(ctx->flush); release(ctx->nv_ids); release(ctx->probe_slots);
   release(ctx->keys_blob); release(ctx->keys_off); release(ctx->match_off); release(ctx->match_len);
   release(ctx->match_out); release(ctx->gather_counts); release(ctx->gathered);
-  release(ctx->shard_cnt); release(ctx->owned0); release(ctx->owned1);
+  release(ctx->shard_cnt); release(ctx->shard_state); release(ctx->owned0); release(ctx->owned1);
   for (int q = 0; q < SH_MAX_RANKS; q++)
     if (ctx->win_peer[q] && ctx->win_peer[q] != ctx->win_mine) cudaIpcCloseMemHandle(ctx->win_peer[q]);
   if (ctx->win_mine) cudaFree(ctx->win_mine);
@@ -878,13 +880,19 @@ struct OrdInput {
   uint32_t* max_key[2];    // its largest key (device): decides the digit plan
   const uint4* head_surv;  // PCI device-id ordering: records whose name slot the segment heads publish (or NULL)
 };
-static int enqueue_orderings(kvg_ctx* ctx, size_t cap, const OrdInput& in) {
+// cap: the most elements an ordering can have (buffers; the grids of the kernels that need one CTA per tile).
+// expect: how many it is expected to have — the launch shapes (digit width, grids of the tile loops, final
+// variant) are chosen for it; every kernel is correct for any count up to cap.  The two differ in the
+// sharded scan, whose owned lists can hold P shards but normally hold about one.
+static int enqueue_orderings(kvg_ctx* ctx, size_t cap, const OrdInput& in, size_t expect = 0) {
+  if (expect == 0 || expect > cap) expect = cap;
   int rc = ensure_order(ctx, ctx->ord_dev, cap);
   if (rc) return rc;
   rc = ensure_order(ctx, ctx->ord_grp, cap);
   if (rc) return rc;
   size_t T = (cap + C_TILE - 1) / C_TILE;
   if (T == 0) T = 1;
+  const size_t Te = std::max<size_t>(1, (expect + C_TILE - 1) / C_TILE);
   ENSURE(ctx->tile_hist, 2 * (size_t)RADIX_MAX_DIGITS * T);
   ENSURE(ctx->bin_total, 2 * (size_t)RADIX_MAX_DIGITS);
   ScanCtrl* c = ctx->ctrl.p;
@@ -894,7 +902,7 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, const OrdInput& in) {
   const uint32_t key_bits[2] = {16, 32};  // device id / mdev type: u16; iommu group / parent: u32
   // digit width: up to 11 bits where the scan is latency-bound (fewer passes: 19-bit groups sort in 2),
   // 8 bits for inputs large enough to be bandwidth-bound (half the shared memory, more CTAs/SM)
-  const bool big = cap >= (8u << 20);
+  const bool big = expect >= (8u << 20);
   const uint32_t max_bits = big ? 8 : RADIX_MAX_BITS;
   const int nsets[2] = {(int)((key_bits[0] + max_bits - 1) / max_bits),
                         (int)((key_bits[1] + max_bits - 1) / max_bits)};  // 2 and 3 (or 4) launch sets
@@ -923,7 +931,7 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, const OrdInput& in) {
     // sets 0/1 always have work: one CTA per tile.  Later sets exist only for wide keys and are usually
     // ruled out on the device: a small persistent grid makes a ruled-out pass nearly free.
     const bool both = p < nsets[0];
-    const unsigned gx = p < 2 ? (unsigned)T : (unsigned)std::min<size_t>(T, (size_t)ctx->sm_count * (big ? 5 : 3));
+    const unsigned gx = p < 2 ? (unsigned)Te : (unsigned)std::min<size_t>(Te, (size_t)ctx->sm_count * (big ? 5 : 3));
     dim3 grid(gx, both ? 2 : 1);
     if (both) {
       aa.o[0] = fill(0, p);
@@ -933,7 +941,7 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, const OrdInput& in) {
       aa.o[1] = aa.o[0];
     }
     LAUNCH("order_hist", k_order_hist, grid, KVG_BLOCK, 0, aa);
-    if (T > 2048) {
+    if (Te > 2048) {
       dim3 sgrid(1u << max_bits, grid.y);
       LAUNCH("order_tilescan", k_order_tilescan_long, sgrid, KVG_BLOCK, 0, aa);
     } else {
@@ -977,7 +985,7 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, const OrdInput& in) {
     t.state = ob[ord]->heads_state.p;
   }
   dim3 fgrid((unsigned)T, 2);
-  if (cap < (2u << 20)) {  // latency-bound: one launch (chained scan of the head counts)
+  if (expect < (2u << 20)) {  // latency-bound: one launch (chained scan of the head counts)
     LAUNCH("order_final", k_order_final, fgrid, KVG_BLOCK, 0, ff, next_epoch());
   } else {                 // bandwidth-bound: no CTA waits for another
     LAUNCH("order_count", k_order_heads<false>, fgrid, KVG_BLOCK, 0, ff);
@@ -1366,11 +1374,20 @@ int kvg_health_rescan(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, kvg_healt
       CK(cudaMemsetAsync(ctx->alive_prev.p, 0, n + 1, ctx->stream));
       ctx->health_n = n;
     }
+    static const bool zero_copy = [] {  // KVG_HEALTH_ZEROCOPY=1: the kernel reads the pinned snapshot in place (A/B)
+      const char* e = getenv("KVG_HEALTH_ZEROCOPY");
+      return e && e[0] == '1';
+    }();
     cudaPointerAttributes attr;
     const void* dev_view = nullptr;
     if (cudaPointerGetAttributes(&attr, recs) == cudaSuccess && attr.type == cudaMemoryTypeHost) dev_view = attr.devicePointer;
     cudaGetLastError();
-    if (!dev_view) {  // pageable caller memory (cgo rule: never keep the pointer): stage it in pinned memory
+    if (!zero_copy) {  // one DMA copy (pageable memory is staged in pinned memory first), then device-resident reads
+      ENSURE(ctx->recs, n + 1);
+      int rc_c = stage_h2d(ctx, recs, n * sizeof(kvg_pci_rec), ctx->recs.p);
+      if (rc_c) return rc_c;
+      dev_view = ctx->recs.p;
+    } else if (!dev_view) {  // pageable caller memory (cgo rule: never keep the pointer): stage it in pinned memory
       if (ctx->h_stage_cap < n * 16) {
         if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
         ctx->h_stage = nullptr;
@@ -1386,12 +1403,27 @@ int kvg_health_rescan(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, kvg_healt
     if (!blk) return KVG_ENOMEM;
     uint8_t* b = pinned_payload(blk);
     uint32_t* hdr = (uint32_t*)(b + align64(sizeof(kvg_health_delta)));
+    const uint32_t seq = ++ctx->health_seq ? ctx->health_seq : ++ctx->health_seq;  // never 0
+    ((volatile uint32_t*)hdr)[2] = 0;
     LAUNCH("health_diff", k_health_small, 1, HEALTH_SMALL_THREADS, 0, (const uint4*)dev_view, (uint32_t)n,
-           ctx->alive_prev.p, (uint32_t*)(b + o_list), hdr);
+           ctx->alive_prev.p, (uint32_t*)(b + o_list), hdr, seq);
     int rc = check_launch(ctx, "health");
-    if (rc == KVG_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
-      ctx->err = "health re-scan failed";
-      rc = KVG_ECUDA;
+    if (rc == KVG_OK) {
+      // the kernel's last store is a flag in this (mapped, pinned) block: poll it instead of paying a driver
+      // synchronisation per tick; a launch that never completes falls back to the stream after ~1 s
+      const auto t0 = std::chrono::steady_clock::now();
+      uint32_t spins = 0;
+      while (((volatile uint32_t*)hdr)[2] != seq) {
+        if ((++spins & 0xffffu) == 0 &&
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 1.0) {
+          if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || ((volatile uint32_t*)hdr)[2] != seq) {
+            ctx->err = "health re-scan failed";
+            rc = KVG_ECUDA;
+          }
+          break;
+        }
+      }
+      std::atomic_thread_fence(std::memory_order_acquire);
     }
     if (rc) {
       ctx->pinned_free.push_back({blk, (size_t)((uint64_t*)blk)[1]});
@@ -1949,9 +1981,11 @@ static int enqueue_exchange(kvg_ctx* ctx, const uint4* local, size_t n_cap, size
   ENSURE(ctx->owned0, (owned_cap + 1) * U);
   ENSURE(ctx->owned1, (owned_cap + 1) * U);
   const size_t T = (list_cap + C_TILE - 1) / C_TILE + 1;
-  // [0, 2P) totals, [32, 34) self-resetting tickets, [34] error word, [64, ...) tile counts; a fresh
-  // allocation is zero-filled, the tickets return to zero by themselves, the error word is sticky
-  ENSURE(ctx->shard_cnt, 64 + 2 * (size_t)P * T);
+  // shard_cnt: [0, 2P) totals, [32, 34) self-resetting tickets, [34] error word; a fresh allocation is
+  // zero-filled, the tickets return to zero by themselves, the error word is sticky.  shard_state: the
+  // chained-scan words of the send kernel (epoch-tagged: never cleared)
+  ENSURE(ctx->shard_cnt, 64);
+  ENSURE(ctx->shard_state, 2 * (size_t)P * T);
   uint32_t* totals = ctx->shard_cnt.p;
   uint32_t* tickets = ctx->shard_cnt.p + 32;
   uint32_t* err = ctx->shard_cnt.p + 34;
@@ -1960,7 +1994,7 @@ static int enqueue_exchange(kvg_ctx* ctx, const uint4* local, size_t n_cap, size
   ShardArgs A;
   A.list = list;
   A.n_ptr = n_ptr;
-  A.tile_cnt = ctx->shard_cnt.p + 64;
+  A.state = ctx->shard_state.p;
   A.totals = totals;
   A.ticket = tickets;
   A.T = (uint32_t)T;
@@ -1980,9 +2014,7 @@ static int enqueue_exchange(kvg_ctx* ctx, const uint4* local, size_t n_cap, size
     peers.win[q] = (uint4*)(base + SH_HDR);
   }
   const ShardCtrl* mine = (const ShardCtrl*)ctx->win_mine;
-  LAUNCH("shard_count", k_shard_count<U>, (unsigned)T, KVG_BLOCK, 0, A);
-  LAUNCH("shard_scan", k_shard_scan, (unsigned)((2 * P + KVG_WARPS - 1) / KVG_WARPS), KVG_BLOCK, 0, A);
-  LAUNCH("shard_send", k_shard_send<U>, (unsigned)T, KVG_BLOCK, 0, A, peers, mine, err);
+  LAUNCH("shard_send", k_shard_send<U>, (unsigned)T, KVG_BLOCK, 0, A, peers, mine, err, next_epoch());
   GatherArgs G;
   G.window = (const uint4*)(ctx->win_mine + SH_HDR);
   G.owned[0] = ctx->owned0.p;
@@ -1996,11 +2028,12 @@ static int enqueue_exchange(kvg_ctx* ctx, const uint4* local, size_t n_cap, size
 }
 
 // orderings of the two owned lists
-static int enqueue_owned_orderings(kvg_ctx* ctx, size_t owned_cap, int src0, int src1, bool names) {
+static int enqueue_owned_orderings(kvg_ctx* ctx, size_t owned_cap, size_t n_local, int src0, int src1, bool names) {
   ScanCtrl* c = ctx->ctrl.p;
   OrdInput in = {{ctx->owned0.p, ctx->owned1.p}, {&c->n_own[0], &c->n_own[1]}, {src0, src1},
                  {&c->own_max[0], &c->own_max[1]}, names ? ctx->owned0.p : nullptr};
-  return enqueue_orderings(ctx, owned_cap, in);
+  // keys spread over the owners evenly (key % P): an owned list is about as long as the local survivor list
+  return enqueue_orderings(ctx, owned_cap, in, std::max<size_t>(n_local, C_TILE));
 }
 
 extern "C" {
@@ -2019,7 +2052,7 @@ int kvg_dev_scan_pci_sharded(kvg_ctx* ctx, const void* d_recs, size_t n_local) {
   size_t owned_cap = 0;
   rc = enqueue_exchange<1>(ctx, ctx->surv.p, n_local, &owned_cap);
   if (rc) return rc;
-  rc = enqueue_owned_orderings(ctx, owned_cap, SRC_PCI_DEVICE, SRC_PCI_GROUP, true);
+  rc = enqueue_owned_orderings(ctx, owned_cap, n_local, SRC_PCI_DEVICE, SRC_PCI_GROUP, true);
   if (rc) return rc;
   ctx->last_n = n_local;
   ctx->last_total = owned_cap;
@@ -2185,7 +2218,7 @@ int kvg_dev_scan_mdev_sharded(kvg_ctx* ctx, const void* d_recs, size_t n_local, 
   size_t owned_cap = 0;
   rc = enqueue_exchange<2>(ctx, ctx->surv.p, n_local, &owned_cap);
   if (rc) return rc;
-  rc = enqueue_owned_orderings(ctx, owned_cap, SRC_MDEV_TYPE, SRC_MDEV_PARENT, false);
+  rc = enqueue_owned_orderings(ctx, owned_cap, n_local, SRC_MDEV_TYPE, SRC_MDEV_PARENT, false);
   if (rc) return rc;
   ctx->last_n = n_local;
   ctx->last_total = owned_cap;

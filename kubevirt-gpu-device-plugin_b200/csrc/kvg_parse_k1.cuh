@@ -43,7 +43,7 @@ namespace kvg {
 #define KVG_K1_SPAN 4096
 #endif
 #ifndef KVG_K1_STAGES
-#define KVG_K1_STAGES 2
+#define KVG_K1_STAGES 1
 #endif
 constexpr uint32_t K1_SPAN = KVG_K1_SPAN;          // text bytes owned by one warp iteration
 constexpr uint32_t K1_HALO = 16;                   // a line starting on the span's last byte is classified
@@ -210,7 +210,10 @@ __device__ __noinline__ void k1_record_lines(const uint8_t* sm, uint32_t* dev_of
   }
 }
 
-__global__ void __launch_bounds__(K1_WARPS * 32) k_pciids_scan(K1Args A) {
+#ifndef KVG_K1_MINCTAS
+#define KVG_K1_MINCTAS 1
+#endif
+__global__ void __launch_bounds__(K1_WARPS * 32, KVG_K1_MINCTAS) k_pciids_scan(K1Args A) {
   pdl_enter();
 #ifndef KVG_HOST_EMU
   extern __shared__ __align__(128) uint8_t k1_smem[];
@@ -295,21 +298,30 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_pciids_scan(K1Args A) {
       }
     }
     const uint8_t* cell = sm + lane * 16;
+    auto header_at = [&](uint32_t po) {  // a header-type line starts at cell + po
+      const uint32_t p = po + lane * 16;
+      const uint32_t k = k1_header_key(sm, p);
+      last_key = max(last_key, k);  // mask bits are not in position order: keys carry the position
+      first_hdr = min(first_hdr, p);
+      if ((k & 0x1ffffu) == K1_VALID_10DE) {
+        saw_10de = true;
+        atomicMin(&A.info[f].v_off, a + p);
+      }
+    };
 #pragma unroll
     for (uint32_t r = 0; r < K1_ROWS; r++) {
-      for (uint32_t mm = ls[r]; mm; mm &= mm - 1) {
-        const uint32_t po = r * 1024 + s_off[__ffs(mm) - 1];  // newline position + 1, relative to my cell
-        const uint32_t b0 = cell[po];
-        if (b0 != '\t' && b0 != '#') {
-          const uint32_t p = po + lane * 16;
-          const uint32_t k = k1_header_key(sm, p);
-          last_key = max(last_key, k);  // mask bits are not in position order: keys carry the position
-          first_hdr = min(first_hdr, p);
-          if ((k & 0x1ffffu) == K1_VALID_10DE) {
-            saw_10de = true;
-            atomicMin(&A.info[f].v_off, a + p);
-          }
-        }
+      // two line starts per round: their first bytes are fetched together (the loop is a chain of dependent
+      // shared-memory loads; a lane rarely owns more than two line starts of a row)
+      for (uint32_t mm = ls[r]; mm;) {
+        const uint32_t t0 = (uint32_t)__ffs(mm) - 1;
+        mm &= mm - 1;
+        const bool two = mm != 0;
+        const uint32_t t1 = two ? (uint32_t)__ffs(mm) - 1 : t0;
+        mm &= mm - 1;
+        const uint32_t po0 = r * 1024 + s_off[t0], po1 = r * 1024 + s_off[t1];
+        const uint32_t b0 = cell[po0], b1 = cell[po1];
+        if (b0 != '\t' && b0 != '#') header_at(po0);
+        if (two && b1 != '\t' && b1 != '#') header_at(po1);
       }
     }
     last_key = warp_max(last_key);

@@ -340,53 +340,53 @@ constexpr uint32_t HEALTH_SMALL_MAX = HEALTH_SMALL_THREADS * HEALTH_SMALL_ROWS; 
 __global__ void __launch_bounds__(HEALTH_SMALL_THREADS) k_health_small(const uint4* __restrict__ recs, uint32_t n,
                                                                        uint8_t* __restrict__ alive_prev,
                                                                        uint32_t* __restrict__ changed_host,
-                                                                       uint32_t* __restrict__ hdr_host) {
+                                                                       uint32_t* __restrict__ hdr_host, uint32_t seq) {
   pdl_enter();
   constexpr uint32_t NW = HEALTH_SMALL_THREADS / 32;
-  __shared__ uint32_t s_w[NW];
-  __shared__ uint32_t s_base, s_alive;
+  __shared__ uint32_t s_chg[NW], s_alv[NW];
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t rows = (n + HEALTH_SMALL_THREADS - 1) / HEALTH_SMALL_THREADS;
-  if (tid == 0) s_base = s_alive = 0;
-  unsigned long long st = 0;  // 2 bits per row: now alive | changed << 1
-  uint32_t my_alive = 0;
+  // every thread owns a CONTIGUOUS run of records, so thread order is record order and ONE block scan of the
+  // per-thread transition counts places every transition
+  const uint32_t per = (n + HEALTH_SMALL_THREADS - 1) / HEALTH_SMALL_THREADS;  // <= HEALTH_SMALL_ROWS
+  const uint32_t i0 = tid * per, i1 = min(n, i0 + per);
+  unsigned long long st = 0;  // 2 bits per record of my run: now alive | changed << 1
+  uint32_t n_alive = 0, n_chg = 0;
 #pragma unroll 4
-  for (uint32_t k = 0; k < rows; k++) {
-    const uint32_t i = k * HEALTH_SMALL_THREADS + tid;
-    uint32_t bits = 0;
-    if (i < n) {
-      const uint4 r = recs[i];
-      const uint32_t now = pci_record_alive(r) ? 1u : 0u;
-      const uint32_t was = alive_prev[i];
-      bits = now | ((now != was) ? 2u : 0u);
-      if (now != was) alive_prev[i] = (uint8_t)now;
-      my_alive += now;
-    }
-    st |= (unsigned long long)bits << (2 * k);
+  for (uint32_t i = i0; i < i1; i++) {
+    const uint4 r = recs[i];
+    const uint32_t now = pci_record_alive(r) ? 1u : 0u;
+    const uint32_t was = alive_prev[i];
+    const uint32_t chg = now != was ? 1u : 0u;
+    if (chg) alive_prev[i] = (uint8_t)now;
+    st |= (unsigned long long)(now | (chg << 1)) << (2 * (i - i0));
+    n_alive += now;
+    n_chg += chg;
   }
+  const uint32_t incl = warp_incl_sum(n_chg);
+  const uint32_t wal = warp_sum(n_alive);
+  if (lane == 31) s_chg[warp] = incl;
+  if (lane == 0) s_alv[warp] = wal;
   __syncthreads();
-  my_alive = warp_sum(my_alive);
-  if (lane == 0 && my_alive) atomicAdd(&s_alive, my_alive);
-  for (uint32_t k = 0; k < rows; k++) {  // record order == (row, thread) order
-    const uint32_t bits = (uint32_t)(st >> (2 * k)) & 3u;
-    const uint32_t bal = __ballot_sync(KVG_FULL, (bits & 2u) != 0);
-    if (lane == 0) s_w[warp] = __popc(bal);
-    __syncthreads();
-    uint32_t off = s_base;
-    for (uint32_t w = 0; w < warp; w++) off += s_w[w];
-    if (bits & 2u) changed_host[off + __popc(bal & lanemask_lt())] = ((k * HEALTH_SMALL_THREADS + tid) << 1) | (bits & 1u);
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t t = 0;
-      for (uint32_t w = 0; w < NW; w++) t += s_w[w];
-      s_base += t;
-    }
-    __syncthreads();
+  uint32_t base = 0, total = 0, alive = 0;
+#pragma unroll
+  for (uint32_t w = 0; w < NW; w++) {
+    const uint32_t c = s_chg[w];
+    if (w < warp) base += c;
+    total += c;
+    alive += s_alv[w];
   }
+  uint32_t pos = base + incl - n_chg;
+  for (uint32_t i = i0; i < i1; i++) {
+    const uint32_t bits = (uint32_t)(st >> (2 * (i - i0))) & 3u;
+    if (bits & 2u) changed_host[pos++] = (i << 1) | (bits & 1u);
+  }
+  __threadfence_system();  // the list entries of every thread are on their way before the flag
+  __syncthreads();
   if (tid == 0) {
-    hdr_host[0] = s_alive;
-    hdr_host[1] = s_base;
+    hdr_host[0] = alive;
+    hdr_host[1] = total;
     __threadfence_system();
+    *((volatile uint32_t*)&hdr_host[2]) = seq;  // the host polls this word: no driver call on the way back
   }
 }
 

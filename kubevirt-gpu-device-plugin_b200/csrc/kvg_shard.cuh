@@ -13,11 +13,12 @@
 // Transport: peer memory (CUDA IPC over NVLink / NVSwitch).  Every rank owns a receive WINDOW
 //   [parity w][ordering o][source rank s][cap records]
 // mapped by every peer.  The multisplit is stable and its stores ARE the collective:
-//   k_shard_count   per 2048-survivor tile: how many survivors go to each (ordering, owner)
-//   k_shard_scan    per (ordering, owner) row: exclusive scan over the tiles, totals
-//   k_shard_send    every survivor is stored at its final position of region `me` in its owner's window
-//                   (ballot ranks: stable), once per ordering; the last CTA to finish publishes the
+//   k_shard_send    per 2048-survivor tile: counts per (ordering, owner), 2P chained scans over the tiles, then
+//                   every survivor is stored at its final position of region `me` in its owner's window
+//                   (match.any ranks: stable), once per ordering; the last CTA to finish publishes the
 //                   region counts and a release flag (st.release.sys) in every peer's control block
+//                   (round 2 first had count / scan / send as three launches: two reads of the list and
+//                   ~15 us of launch gaps more)
 //   k_shard_gather  waits for the P flags of the step (ld.acquire.sys), concatenates the P regions of each
 //                   ordering — source-rank order == Walk order — into the dense OWNED list the orderings
 //                   read, reduces the largest owned keys (radix plan), and the last CTA acknowledges the
@@ -78,10 +79,10 @@ __device__ __forceinline__ uint2 shard_keys(const uint4* rec) {
 struct ShardArgs {
   const uint4* list;       // dense survivor list of this rank (NCCL mode: the gathered list)
   const uint32_t* n_ptr;   // its length (device)
-  uint32_t* tile_cnt;      // [2 orderings][P][T] per-tile counts -> exclusive offsets (T = tiles the launch covers)
+  uint64_t* state;         // [2 orderings * P][T] chained-scan words of the per-tile counts (epoch-tagged)
   uint32_t* totals;        // [2][P]
   uint32_t* ticket;        // self-resetting "last CTA" counters: [0] send, [1] gather
-  uint32_t T;              // row pitch of tile_cnt
+  uint32_t T;              // row pitch of state (tiles the launch covers)
   uint32_t P;              // owners (key % P)
   uint32_t me;             // this rank
   uint32_t only;           // SH_ALL: send to every owner; else keep only records owned by `only` (local mode)
@@ -92,84 +93,24 @@ struct ShardArgs {
   unsigned long long step;
 };
 
-template <int U>
-__global__ void __launch_bounds__(KVG_BLOCK) k_shard_count(ShardArgs A) {
-  pdl_enter();
-  const uint32_t n = *A.n_ptr;
-  const uint32_t tile = blockIdx.x;
-  __shared__ uint32_t s_cnt[2][SH_MAX_RANKS];
-  if (threadIdx.x < 2 * SH_MAX_RANKS) (&s_cnt[0][0])[threadIdx.x] = 0;
-  __syncthreads();
-  if ((uint64_t)tile * C_TILE < n) {
-    const uint32_t lane = lane_id();
-    const uint32_t base = tile * C_TILE + warp_id() * C_WARP_ITEMS;
-    uint32_t q0[C_ROWS], q1[C_ROWS];
-#pragma unroll
-    for (uint32_t k = 0; k < C_ROWS; k++) {  // all loads in flight first
-      const uint32_t i = base + k * 32 + lane;
-      q0[k] = q1[k] = SH_ALL;
-      if (i < n) {
-        uint4 rec[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) rec[u] = A.list[(size_t)i * U + u];
-        const uint2 key = shard_keys<U>(rec);
-        q0[k] = key.x % A.P;
-        q1[k] = key.y % A.P;
-      }
-    }
-    for (uint32_t q = 0; q < A.P; q++) {  // P <= 16 ballots per row and ordering
-      uint32_t c0 = 0, c1 = 0;
-#pragma unroll
-      for (uint32_t k = 0; k < C_ROWS; k++) {
-        c0 += __popc(__ballot_sync(KVG_FULL, q0[k] == q));
-        c1 += __popc(__ballot_sync(KVG_FULL, q1[k] == q));
-      }
-      if (lane == 0) {
-        if (c0) atomicAdd(&s_cnt[0][q], c0);
-        if (c1) atomicAdd(&s_cnt[1][q], c1);
-      }
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < 2 * A.P) {
-    const uint32_t o = threadIdx.x / A.P, q = threadIdx.x - o * A.P;
-    A.tile_cnt[((size_t)o * A.P + q) * A.T + tile] = s_cnt[o][q];
-  }
-}
-
-// one warp per (ordering, owner) row: exclusive scan over the tiles in place, row total
-__global__ void __launch_bounds__(KVG_BLOCK) k_shard_scan(ShardArgs A) {
-  pdl_enter();
-  const uint32_t n = *A.n_ptr;
-  const uint32_t Tu = (n + C_TILE - 1) / C_TILE;
-  const uint32_t lane = lane_id();
-  for (uint32_t row = blockIdx.x * KVG_WARPS + warp_id(); row < 2 * A.P; row += gridDim.x * KVG_WARPS) {
-    uint32_t* r = A.tile_cnt + (size_t)row * A.T;
-    uint32_t carry = 0;
-    for (uint32_t b = 0; b < Tu; b += 32) {
-      const uint32_t i = b + lane;
-      const uint32_t v = i < Tu ? r[i] : 0;
-      const uint32_t incl = warp_incl_sum(v);
-      if (i < Tu) r[i] = carry + incl - v;
-      carry += __shfl_sync(KVG_FULL, incl, 31);
-    }
-    if (lane == 0) A.totals[row] = carry;
-  }
-}
-
 // window addressing (16-byte units): region (parity, ordering, source) of a window
 __device__ __forceinline__ size_t shard_region(const ShardArgs& A, uint32_t o, uint32_t s, int U) {
   return (((size_t)A.parity * 2 + o) * A.n_src + s) * A.region_cap * (size_t)U;
 }
 
+// One launch: count, chained scan, send.  A CTA owns a 2048-survivor tile.  Ranks inside a warp come from
+// match.any (one instruction per row and ordering whatever P is); the 2P per-tile counts are combined over the
+// tiles by 2P chained scans (look-back), warp c of the CTA running counter c — so the survivor list is read once
+// and nothing but the stores stands between the classify kernel and the windows.
 template <int U>
 __global__ void __launch_bounds__(KVG_BLOCK) k_shard_send(ShardArgs A, ShardPeers peers, const ShardCtrl* mine,
-                                                          uint32_t* err) {
+                                                          uint32_t* err, uint32_t epoch) {
   pdl_enter();
   const uint32_t n = *A.n_ptr;
+  const uint32_t Tu = (n + C_TILE - 1) / C_TILE;
   const uint32_t tile = blockIdx.x;
-  __shared__ uint32_t s_wcnt[KVG_WARPS][2][SH_MAX_RANKS];   // per warp: survivors of every (ordering, owner)
-  __shared__ uint32_t s_wbase[KVG_WARPS][2][SH_MAX_RANKS];  // per warp: running position in the owner's region
+  __shared__ uint32_t s_wcnt[KVG_WARPS][2][SH_MAX_RANKS];  // per warp: survivors of every (ordering, owner) -> prefix over the warps
+  __shared__ uint32_t s_base[2][SH_MAX_RANKS];             // the tile's position in every (ordering, owner) region
   __shared__ uint32_t s_last;
   const uint32_t lane = lane_id(), warp = warp_id();
   // the window parity is rewritten: every owner must have consumed the step that used it two steps ago
@@ -182,12 +123,12 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_shard_send(ShardArgs A, ShardPeer
       }
     }
   }
-  if ((uint64_t)tile * C_TILE < n) {
+  if (tile < Tu) {
     const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
     uint4 rec[C_ROWS][U];
     uint32_t q0[C_ROWS], q1[C_ROWS];
 #pragma unroll
-    for (uint32_t k = 0; k < C_ROWS; k++) {
+    for (uint32_t k = 0; k < C_ROWS; k++) {  // all loads in flight first
       const uint32_t i = base + k * 32 + lane;
       q0[k] = q1[k] = SH_ALL;
       if (i < n) {
@@ -198,55 +139,55 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_shard_send(ShardArgs A, ShardPeer
         q1[k] = key.y % A.P;
       }
     }
-    // per warp: counts of every (ordering, owner) in my 256 survivors
-    for (uint32_t q = 0; q < A.P; q++) {
-      uint32_t c0 = 0, c1 = 0;
-#pragma unroll
-      for (uint32_t k = 0; k < C_ROWS; k++) {
-        c0 += __popc(__ballot_sync(KVG_FULL, q0[k] == q));
-        c1 += __popc(__ballot_sync(KVG_FULL, q1[k] == q));
-      }
-      if (lane == 0) {
-        s_wcnt[warp][0][q] = c0;
-        s_wcnt[warp][1][q] = c1;
-      }
-    }
-    __syncthreads();
-    // my warp's base = tile offset (scanned) + the warps in front of me
-    if (lane < 2 * A.P) {
-      const uint32_t o = lane / A.P, q = lane - o * A.P;
-      uint32_t b = A.tile_cnt[((size_t)o * A.P + q) * A.T + tile];
-      for (uint32_t w = 0; w < warp; w++) b += s_wcnt[w][o][q];
-      s_wbase[warp][o][q] = b;
-    }
+    static_assert(2 * SH_MAX_RANKS == 32, "one lane per counter");
+    (&s_wcnt[warp][0][0])[lane] = 0;
     __syncwarp();
+    // stable position of every survivor among those of my warp that go to the same (ordering, owner)
+    uint32_t pos[C_ROWS][2];
 #pragma unroll
     for (uint32_t k = 0; k < C_ROWS; k++) {
 #pragma unroll
       for (uint32_t o = 0; o < 2; o++) {
         const uint32_t q = o ? q1[k] : q0[k];
-        // stable rank among the lanes of this row that go to the same owner
-        uint32_t before = 0, total_q = 0;
-        for (uint32_t t = 0; t < A.P; t++) {
-          const uint32_t b = __ballot_sync(KVG_FULL, q == t);
-          if (q == t) {
-            before = __popc(b & lanemask_lt());
-            total_q = __popc(b);
-          }
-        }
-        if (q != SH_ALL) {
-          const uint32_t pos = s_wbase[warp][o][q] + before;
-          if (A.only == SH_ALL || q == A.only) {
-            uint4* dst = peers.win[q] + shard_region(A, o, A.src, U) + (size_t)pos * U;
-#pragma unroll
-            for (int u = 0; u < U; u++) dst[u] = rec[k][u];  // NVLink store (or local)
-          }
-        }
+        const uint32_t same = __match_any_sync(KVG_FULL, q);
+        const uint32_t before = __popc(same & lanemask_lt());
+        const uint32_t prior = q != SH_ALL ? s_wcnt[warp][o][q] : 0;
+        pos[k][o] = prior + before;
         __syncwarp();
-        if (q != SH_ALL && before == 0) s_wbase[warp][o][q] += total_q;  // the first lane of each owner advances the base
+        if (q != SH_ALL && before == 0) s_wcnt[warp][o][q] = prior + __popc(same);  // one lane per owner advances
         __syncwarp();
       }
     }
+    __syncthreads();
+    // warp c: counter c = (ordering, owner) — prefix over the warps in place, tile aggregate, chained scan
+    for (uint32_t c = warp; c < 2 * A.P; c += KVG_WARPS) {
+      const uint32_t o = c / A.P, q = c - o * A.P;
+      const uint32_t v = lane < KVG_WARPS ? s_wcnt[lane][o][q] : 0;
+      const uint32_t incl = warp_incl_sum(v);
+      const uint32_t agg = __shfl_sync(KVG_FULL, incl, KVG_WARPS - 1);
+      if (lane < KVG_WARPS) s_wcnt[lane][o][q] = incl - v;
+      const uint32_t excl = lookback_sum(A.state + (size_t)c * A.T, tile, agg, epoch);
+      if (lane == 0) {
+        s_base[o][q] = excl;
+        if (tile == Tu - 1) A.totals[c] = excl + agg;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (uint32_t k = 0; k < C_ROWS; k++) {
+#pragma unroll
+      for (uint32_t o = 0; o < 2; o++) {
+        const uint32_t q = o ? q1[k] : q0[k];
+        if (q != SH_ALL && (A.only == SH_ALL || q == A.only)) {
+          const uint32_t at = s_base[o][q] + s_wcnt[warp][o][q] + pos[k][o];
+          uint4* dst = peers.win[q] + shard_region(A, o, A.src, U) + (size_t)at * U;
+#pragma unroll
+          for (int u = 0; u < U; u++) dst[u] = rec[k][u];  // NVLink store (or local)
+        }
+      }
+    }
+  } else if (n == 0 && tile == 0 && threadIdx.x < 2 * A.P) {
+    A.totals[threadIdx.x] = 0;
   }
   // the last CTA to finish publishes the region counts and the release flag to every owner
   __threadfence_system();

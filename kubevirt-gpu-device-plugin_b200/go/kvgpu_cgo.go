@@ -2,7 +2,8 @@
 
 // Package device_plugin — cgo shim that routes the reference's discovery scan through libkvgpu.so.
 //
-// SOURCE ONLY: this image has no Go toolchain, so this file has never been compiled here.  It is
+// SOURCE ONLY: this image has no Go toolchain, so this file has never been compiled here (round-1 review
+// findings — cgo pointer rule for the type dictionary, locking, range checks — are addressed in source).  It is
 // the binding a maintainer of NVIDIA/kubevirt-gpu-device-plugin drops into pkg/device_plugin/
 // next to device_plugin.go (see INTEGRATION.md).  It contains marshalling only — every decision
 // (filter, join, bucketing, name sanitising) is made by the CUDA library behind include/kvgpu.h.
@@ -34,11 +35,17 @@ import (
 	"sort"
 	"strconv"
 	"strings"
+	"sync"
 	"unsafe"
 )
 
 var kvgCtx *C.kvg_ctx
 var kvgLoadedPath string
+
+// A kvg_ctx is single-threaded (include/kvgpu.h).  The scans run on the main goroutine before any server
+// starts, but getDeviceNameGPU and revalidateBatchGPU are reached from gRPC handler goroutines (grpc-go runs
+// one goroutine per stream) and from healthCheck goroutines: every entry into the library takes kvgMu.
+var kvgMu sync.Mutex
 
 // kvgEnsure creates the context once and (re)loads the pci.ids table when the path changed.
 // A CUDA failure is reported like the reference reports a failed walk: log + empty maps.
@@ -67,6 +74,12 @@ func kvgEnsure() error {
 }
 
 func getDeviceNameGPU(deviceID string) string {
+	kvgMu.Lock()
+	defer kvgMu.Unlock()
+	return getDeviceNameLocked(deviceID)
+}
+
+func getDeviceNameLocked(deviceID string) string {
 	if err := kvgEnsure(); err != nil {
 		log.Printf("Error: %v", err)
 		return ""
@@ -97,6 +110,8 @@ func parseHex4(s string) (uint16, bool) {
 // createIommuDeviceMapGPU: same walk, same readers, same short-circuit order as :192-246, but the
 // entries are only RECORDED (read failures become flag bits); the GPU filters, joins and buckets.
 func createIommuDeviceMapGPU() {
+	kvgMu.Lock()
+	defer kvgMu.Unlock()
 	iommuMap = make(map[string][]NvidiaGpuDevice)
 	deviceMap = make(map[string][]NvidiaGpuDevice)
 	bdfToIommuMap = make(map[string]string)
@@ -104,6 +119,11 @@ func createIommuDeviceMapGPU() {
 	var recs []C.kvg_pci_rec
 	groupIDs := map[string]uint32{}
 	var groupNames []string
+	// `device` strings travel in index mode: the reference keeps WHATEVER the file holds as the map key
+	// (:240, :294-302), so the record carries an interned id and the string stays here
+	deviceIDs := map[string]uint16{}
+	var deviceNames []string
+	rangeErr := ""
 	filepath.Walk(basePath, func(path string, info os.FileInfo, err error) error {
 		if err != nil {
 			log.Printf("Error accessing file path %q: %v\n", path, err)
@@ -148,16 +168,25 @@ func createIommuDeviceMapGPU() {
 					numaNode, err := readNUMANode(basePath, info.Name())
 					if err != nil {
 						r.flags |= C.KVG_PF_NUMA_ERR
+					} else if numaNode < -32768 || numaNode > 32767 {
+						// the 16-byte record carries an int16: refuse loudly (kvgpu/plugin.py: KVG_ERANGE)
+						rangeErr = fmt.Sprintf("numa_node %d of %s does not fit the wire format", numaNode, info.Name())
 					}
 					r.numa = C.int16_t(numaNode)
 					deviceID, err := readIDFromFile(basePath, info.Name(), "device")
 					if err != nil {
 						r.flags |= C.KVG_PF_DEVICE_ERR
-					} else if d, ok := parseHex4(deviceID); ok {
-						r.device = C.uint16_t(d)
 					} else {
-						log.Printf("device id %q of %s is not 4 lower-case hex digits", deviceID, info.Name())
-						r.flags |= C.KVG_PF_DEVICE_ERR
+						id, ok := deviceIDs[deviceID]
+						if !ok {
+							if len(deviceNames) > 0xffff {
+								rangeErr = "more than 65536 distinct device strings"
+							}
+							id = uint16(len(deviceNames))
+							deviceIDs[deviceID] = id
+							deviceNames = append(deviceNames, deviceID)
+						}
+						r.device = C.uint16_t(id)
 					}
 				}
 			}
@@ -166,6 +195,10 @@ func createIommuDeviceMapGPU() {
 		recs = append(recs, r)
 		return nil
 	})
+	if rangeErr != "" {
+		log.Printf("Error: %s", rangeErr) // maps stay empty, like a failed walk (:193-196)
+		return
+	}
 	if err := kvgEnsure(); err != nil {
 		log.Printf("Error: %v", err) // maps stay empty, like a failed walk (:193-196)
 		return
@@ -189,7 +222,7 @@ func createIommuDeviceMapGPU() {
 	devOff := unsafe.Slice(res.dev_off, int(res.n_dev_keys)+1)
 	devPerm := unsafe.Slice(res.dev_perm, S)
 	for k := range devKeys {
-		key := fmt.Sprintf("%04x", uint16(devKeys[k]))
+		key := deviceNames[devKeys[k]] // index mode; getDeviceName(key) is asked later with these exact bytes
 		for _, i := range devPerm[devOff[k]:devOff[k+1]] {
 			deviceMap[key] = append(deviceMap[key], dev(uint32(i)))
 		}
@@ -210,6 +243,8 @@ func createIommuDeviceMapGPU() {
 
 // createVgpuIDMapGPU: :259-290 with the label rule (:341-342) and both group-bys on the GPU.
 func createVgpuIDMapGPU() {
+	kvgMu.Lock()
+	defer kvgMu.Unlock()
 	vGpuMap = make(map[string][]NvidiaGpuDevice)
 	gpuVgpuMap = make(map[string][]string)
 	var names, parentNames []string
@@ -264,14 +299,26 @@ func createVgpuIDMapGPU() {
 		log.Printf("Error: %v", err)
 		return
 	}
-	off := make([]C.uint32_t, len(rawTypes)+1)
-	var blob []byte
-	for i, t := range rawTypes {
-		blob = append(blob, t...)
-		off[i+1] = C.uint32_t(len(blob))
+	// The dictionary struct holds two pointers: they must not be Go pointers (cgo rule: a Go pointer passed to
+	// C may not point at memory that itself holds Go pointers), so both arrays live in C memory for the call.
+	total := 0
+	for _, t := range rawTypes {
+		total += len(t)
 	}
-	blob = append(blob, 0)
-	dict := C.kvg_type_dict{n_types: C.uint32_t(len(rawTypes)), off: &off[0], bytes: (*C.uint8_t)(unsafe.Pointer(&blob[0]))}
+	cOff := (*C.uint32_t)(C.malloc(C.size_t(4 * (len(rawTypes) + 1))))
+	cBlob := (*C.uint8_t)(C.malloc(C.size_t(total + 1)))
+	defer C.free(unsafe.Pointer(cOff))
+	defer C.free(unsafe.Pointer(cBlob))
+	off := unsafe.Slice(cOff, len(rawTypes)+1)
+	blob := unsafe.Slice((*byte)(unsafe.Pointer(cBlob)), total+1)
+	off[0] = 0
+	pos := 0
+	for i, t := range rawTypes {
+		pos += copy(blob[pos:], t)
+		off[i+1] = C.uint32_t(pos)
+	}
+	blob[total] = 0
+	dict := C.kvg_type_dict{n_types: C.uint32_t(len(rawTypes)), off: cOff, bytes: cBlob}
 	var res *C.kvg_mdev_result
 	var p *C.kvg_mdev_rec
 	if len(recs) > 0 {
@@ -324,6 +371,8 @@ func revalidateBatchGPU(devs []string, want []string) (first int, err error) {
 	if len(devs) == 0 {
 		return -1, nil
 	}
+	kvgMu.Lock()
+	defer kvgMu.Unlock()
 	if err := kvgEnsure(); err != nil {
 		return 0, err
 	}

@@ -57,10 +57,9 @@ def main(argv=None) -> int:
             try:
                 p.start()
                 started.append(p)
-                if not p.vgpu:
-                    w = serve.DeviceNodeWatcher(p)
-                    w.start()
-                    watchers.append(w)
+                w = serve.DeviceNodeWatcher(p)   # device nodes (or mdev nodes) + the plugin socket
+                w.start()
+                watchers.append(w)
             except Exception as e:        # noqa: BLE001
                 print("kvgpu: error starting the %s device plugin: %s" % (p.device_name, e), file=sys.stderr)
         stop = threading.Event()

@@ -155,6 +155,7 @@ class PciSnapshot:
     names: list            # Walk-order entry names (record i <-> names[i])
     packed_addr: bool      # True: recs.addr is the packed BDF; False: the Walk index
     group_names: list | None   # None: iommu_group is the number itself; else interned strings
+    device_names: list | None = None   # None: recs.device is the id itself ("%04x"); else interned `device` strings
 
 
 def snapshot_pci_tree(base_path: str) -> PciSnapshot:
@@ -191,11 +192,8 @@ def snapshot_pci_tree(base_path: str) -> PciSnapshot:
                     dv, e = _read_id(base_path, name, "device")
                     if e:
                         flags |= L.PF_DEVICE_ERR
-                    elif len(dv) == 4 and all(c in HEXD for c in dv):
-                        device = int(dv, 16)
                     else:
-                        raise L.KvgError(L.KVG_ERANGE, "device id %r of %s is not 4 lower-case hex "
-                                         "digits; the 16-byte wire format cannot carry it" % (dv, name))
+                        device = dv   # the reference keeps WHATEVER the file holds as the map key (:240, :294-302)
         rows.append((name, vendor, device, group, driver, flags, numa))
         names.append(name)
     packed = [parse_bdf(n) for n in names]
@@ -207,8 +205,24 @@ def snapshot_pci_tree(base_path: str) -> PciSnapshot:
 
     groups_numeric = all(canon_dec(r[3]) for r in rows if r[3] != "")
     group_names, intern = (None, None) if groups_numeric else ([], {})
+    # `device`: "%04x" strings travel as the number; anything else switches the column to index mode (interned
+    # strings, like the groups): the GPU groups by the interned id, the host keeps the strings and asks
+    # getDeviceName with the exact bytes
+    devs = [r[2] for r in rows if isinstance(r[2], str)]
+    devices_numeric = all(len(d) == 4 and all(c in HEXD for c in d) for d in devs)
+    device_names, dintern = (None, None) if devices_numeric else ([], {})
     recs = np.zeros(len(rows), dtype=L.PCI_REC)
     for i, (name, vendor, device, group, driver, flags, numa) in enumerate(rows):
+        if isinstance(device, str):
+            if devices_numeric:
+                device = int(device, 16)
+            else:
+                k = dintern.setdefault(device, len(dintern))
+                if k == len(device_names):
+                    device_names.append(device)
+                if k > 0xFFFF:
+                    raise L.KvgError(L.KVG_ERANGE, "more than 65536 distinct non-canonical device strings")
+                device = k
         if group == "":
             g = 0
         elif groups_numeric:
@@ -220,7 +234,7 @@ def snapshot_pci_tree(base_path: str) -> PciSnapshot:
         if not -32768 <= numa <= 32767:
             raise L.KvgError(L.KVG_ERANGE, "numa_node %d of %s does not fit int16" % (numa, name))
         recs[i] = (packed[i] if packed_ok else i, vendor, device, g, driver, flags, numa)
-    return PciSnapshot(recs, names, packed_ok, group_names)
+    return PciSnapshot(recs, names, packed_ok, group_names, device_names)
 
 
 def _read_vgpu_raw(base, addr, prop):
@@ -326,7 +340,10 @@ class Maps:
     deviceNames: dict = field(default_factory=dict)    # key -> getDeviceName(key) ("" = miss)
 
 
-def pci_maps_from_result(res: PciResult, snap: PciSnapshot | None = None, maps: Maps | None = None) -> Maps:
+def pci_maps_from_result(res: PciResult, snap: PciSnapshot | None = None, maps: Maps | None = None,
+                         name_of=None) -> Maps:
+    """name_of(key) -> getDeviceName(key): needed (and only used) when the snapshot carries the `device`
+    strings in index mode — the GPU's per-survivor join is keyed by the numeric id and does not apply."""
     m = maps or Maps()
     m.iommuMap, m.deviceMap, m.bdfToIommuMap = {}, {}, {}  # :188-190
     s = res.survivors
@@ -339,11 +356,14 @@ def pci_maps_from_result(res: PciResult, snap: PciSnapshot | None = None, maps: 
     else:
         gname = lambda g: snap.group_names[int(g)]
     numa = s["numa"]
+    dev_index = snap is not None and snap.device_names is not None
+    if dev_index and name_of is None:
+        raise ValueError("snapshot carries device strings in index mode: pass name_of (Context.name_lookup)")
     for k in range(len(res.dev_keys)):
-        key = "%04x" % int(res.dev_keys[k])
+        key = snap.device_names[int(res.dev_keys[k])] if dev_index else "%04x" % int(res.dev_keys[k])
         idx = res.dev_perm[res.dev_off[k]:res.dev_off[k + 1]]
         m.deviceMap[key] = [NvidiaGpuDevice(addr[i], int(numa[i])) for i in idx]
-        m.deviceNames[key] = res.name_at(int(res.dev_name_slot[k]))
+        m.deviceNames[key] = name_of(key) if dev_index else res.name_at(int(res.dev_name_slot[k]))
     for k in range(len(res.grp_keys)):
         idx = res.grp_perm[res.grp_off[k]:res.grp_off[k + 1]]
         m.iommuMap[gname(res.grp_keys[k])] = [NvidiaGpuDevice(addr[i], int(numa[i])) for i in idx]
@@ -448,7 +468,7 @@ class DiscoveryScan:
         except ReferencePanic:
             raise
         res = self.ctx.scan_pci(snap.recs)
-        return pci_maps_from_result(res, snap, self.maps)
+        return pci_maps_from_result(res, snap, self.maps, name_of=self.ctx.name_lookup)
 
     def create_vgpu_id_map(self) -> Maps:
         self._ensure_table()

@@ -550,6 +550,50 @@ class HealthRescanFeed:
 
 
 # ------------------------------------------------------------------------------------------------
+# NVML XID events -> vGPU health (generic_vgpu_device_plugin.go:330-339 and watchXIDsFunc :387-433)
+# ------------------------------------------------------------------------------------------------
+XID_APPLICATION_ERRORS = (31, 43, 45)   # :413-417 "Application errors: the GPU should still be healthy"
+
+
+class XidEventRouter:
+    """The decision logic between an NVML XidCriticalError event and the `unhealthy` channel of a vGPU plugin,
+    without NVML itself (the binding stays in the Go host; out of scope here):
+
+      on_event(xid, uuid)    XIDs 31 / 43 / 45 are ignored (:415); an event without a device UUID marks EVERY GPU
+                             (:419-424); otherwise the GPU with that UUID (:427-431)
+      on_unsupported(uuid)   registration failed with "Not Supported": that GPU is marked at once (:392-397)
+      a marked GPU           -> every vGPU of returnGpuVgpuMap()[gpu.PCI.BusID] goes to plugin.unhealthy (:333-338)
+
+    `gpus`: list of (uuid, bus_id) in NVML enumeration order; `gpu_vgpu_map`: the scan's gpuVgpuMap
+    (parent BDF -> [mdev uuid]); `plugins`: the vGPU plugins (an id is routed to the plugin that advertises it;
+    the reference sends it down ITS OWN channel whether or not the id is its own — ListAndWatch then finds no
+    such device and changes nothing, :186-199)."""
+
+    def __init__(self, gpus, gpu_vgpu_map, plugins):
+        self.gpus, self.gpu_vgpu_map = list(gpus), gpu_vgpu_map
+        self.owner = {d.ID: p for p in plugins for d in p.devs}
+
+    def _mark(self, bus_id) -> int:
+        sent = 0
+        for vgpu in self.gpu_vgpu_map.get(bus_id, []):
+            plugin = self.owner.get(vgpu)
+            if plugin is not None:
+                plugin.unhealthy(vgpu)
+                sent += 1
+        return sent
+
+    def on_unsupported(self, uuid) -> int:
+        return sum(self._mark(bus) for u, bus in self.gpus if u == uuid)
+
+    def on_event(self, xid: int, uuid=None) -> int:
+        if xid in XID_APPLICATION_ERRORS:
+            return 0
+        if not uuid:
+            return sum(self._mark(bus) for _, bus in self.gpus)
+        return sum(self._mark(bus) for u, bus in self.gpus if u == uuid)
+
+
+# ------------------------------------------------------------------------------------------------
 # a mock kubelet: Registration server + DevicePlugin client (SURVEY.md 8(f) rank 1)
 # ------------------------------------------------------------------------------------------------
 @dataclass
@@ -655,8 +699,12 @@ class DeviceNodeWatcher:
 
       node created            -> healthy(id)   for every device of that group   (:659-662)
       node removed / renamed  -> unhealthy(id)                                   (:663-668)
-      plugin socket removed   -> kubelet restarted: restart() = Stop + Start + Register, then the
-                                 watcher ends, like the goroutine does            (:669-679)
+      plugin socket removed   -> kubelet restarted: restart() = Stop + Start + Register (:669-679).  The
+                                 reference's Start() spawns a fresh healthCheck goroutine and the old one
+                                 returns; here the SAME watcher keeps running (its inotify watches are on the
+                                 parent directories and survive), so every later restart is handled too.
+
+    For a vGPU plugin the watched nodes are <vgpu_base_path>/<uuid> (generic_vgpu_device_plugin.go:319-351).
 
     fsnotify watches the PARENT directories; so does this (inotify through libc, no extra package)."""
     IN_CREATE, IN_DELETE, IN_MOVED_FROM, IN_DELETE_SELF, IN_MOVE_SELF = 0x100, 0x200, 0x40, 0x400, 0x800
@@ -668,13 +716,17 @@ class DeviceNodeWatcher:
         self._fd = self._libc.inotify_init1(0o4000)          # IN_NONBLOCK
         if self._fd < 0:
             raise OSError(ctypes.get_errno(), "inotify_init1")
-        bdf_to_iommu = bdf_to_iommu if bdf_to_iommu is not None else plugin.maps.bdfToIommuMap
         self.path_devices = {}                               # node path -> [device ids]
-        for dev in plugin.devs:
-            group = bdf_to_iommu.get(dev.ID)
-            if group is None:                                # :634-637 logged and skipped
-                continue
-            self.path_devices.setdefault(os.path.join(plugin.device_path, group), []).append(dev.ID)
+        if getattr(plugin, "vgpu", False):
+            for dev in plugin.devs:                          # one node per mediated device
+                self.path_devices.setdefault(os.path.join(plugin.vgpu_base_path, dev.ID), []).append(dev.ID)
+        else:
+            bdf_to_iommu = bdf_to_iommu if bdf_to_iommu is not None else plugin.maps.bdfToIommuMap
+            for dev in plugin.devs:
+                group = bdf_to_iommu.get(dev.ID)
+                if group is None:                            # :634-637 logged and skipped
+                    continue
+                self.path_devices.setdefault(os.path.join(plugin.device_path, group), []).append(dev.ID)
         self._wd_dir = {}
         dirs = {os.path.dirname(p) for p in self.path_devices} | {os.path.dirname(plugin.socket_path)}
         mask = self.IN_CREATE | self.IN_DELETE | self.IN_MOVED_FROM
@@ -688,6 +740,7 @@ class DeviceNodeWatcher:
         self._stop = threading.Event()
         self._thread = None
         self.restarted = threading.Event()
+        self.restarts = 0
 
     def poll_once(self) -> int:
         """Drain pending inotify events; returns how many health / restart actions were taken."""
@@ -714,8 +767,8 @@ class DeviceNodeWatcher:
                     acted += len(ids)
             elif path == self.plugin.socket_path and mask & self.IN_DELETE:
                 self.plugin.restart()
+                self.restarts += 1
                 self.restarted.set()
-                self._stop.set()
                 acted += 1
         return acted
 

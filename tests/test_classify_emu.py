@@ -103,13 +103,13 @@ def test_health_small_kernel_one_cta(emu):
                 flip = rng.integers(0, n, 10)
                 recs["driver"][flip] = rng.integers(0, 5, 10)
             changed = np.zeros(n + 1, dtype=np.uint32)
-            hdr = np.zeros(2, dtype=np.uint32)
+            hdr = np.zeros(3, dtype=np.uint32)
             assert emu.emu_health_small(np.ascontiguousarray(recs).ctypes.data, n, alive_prev.ctypes.data,
                                         changed.ctypes.data, hdr.ctypes.data) == 0
             now = (recs["vendor"] == 0x10de) & ((recs["flags"] & drop) == 0) & ((recs["driver"] == 1) | (recs["driver"] == 2))
             idx = np.nonzero(now != prev)[0]
             want = (idx.astype(np.uint32) << 1) | now[idx].astype(np.uint32)
-            assert int(hdr[0]) == int(now.sum()) and int(hdr[1]) == len(want), (n, tick)
+            assert int(hdr[0]) == int(now.sum()) and int(hdr[1]) == len(want) and int(hdr[2]) == 7, (n, tick)
             assert np.array_equal(changed[:len(want)], want)
             assert np.array_equal(alive_prev[:n].astype(bool), now)
             prev = now

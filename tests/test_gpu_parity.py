@@ -373,6 +373,28 @@ def test_discovery_scan_on_trees(kv, tmp_path, pciids):
     ds.close()
 
 
+def test_non_canonical_device_strings_are_kept_as_keys(kv, tmp_path, pciids):
+    """readIDFromFile returns string(data[2:]) for ANY file content (device_plugin.go:294-302) and that string is
+    the deviceMap key (:240) and the getDeviceName argument (:124, prefix match :388-402).  The snapshotter
+    carries such strings in index mode; the dump must equal the oracle's on the same tree."""
+    ids_path = tmp_path / "pci.ids"
+    ids_path.write_bytes(pciids)
+    ent = {}
+    for i, dev in enumerate(("0x1b38\n", "0X1B38\n", "0x1b3\n", "0x1b38 \n", "garbage\n", "0x\n", "0x1b38\n", "0x2901\n\n")):
+        ent["0000:%02x:00.0" % (4 + i)] = dict(vendor="10de", device=dev, driver="vfio-pci", iommu_group=str(40 + i),
+                                              numa_node="%d\n" % (i & 1))
+    base = util.make_pci_tree(str(tmp_path / "odd"), ent)
+    ds = kv.DiscoveryScan(str(ids_path), base, str(tmp_path / "nomdev"))
+    ds.create_iommu_device_map()
+    m = O.Maps()
+    m.create_iommu_device_map_tree(base)
+    assert kv.canonical_dump(ds.maps) == m.dump(pciids)
+    assert set(ds.maps.deviceMap) == {"1b38", "0X1B38", "1b3", "1b38 ", "garbage", "", "2901"}
+    assert ds.maps.deviceNames["1b3"] == "0_GP102GL_QUADRO_P6000"       # prefix semantics (:388)
+    assert len(ds.maps.deviceMap["1b38"]) == 2
+    ds.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # device-resident path, generators, batch parse, full-size properties
 # ------------------------------------------------------------------------------------------------

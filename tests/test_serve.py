@@ -499,9 +499,41 @@ def test_device_node_watcher_like_the_reference_health_check(V):
         assert w.poll_once() == 1 and w.restarted.is_set()
         regs = kubelet.wait_for(2)
         assert [r.endpoint for r in regs] == ["kubevirt-foo.sock"] * 2 and os.path.exists(p.socket_path)
+        # a SECOND kubelet restart: the watcher is still there and re-registers again
+        os.remove(p.socket_path)
+        assert w.poll_once() == 1 and w.restarts == 2
+        regs = kubelet.wait_for(3)
+        assert len(regs) == 3 and os.path.exists(p.socket_path)
+        # ... and it still reports device nodes
+        os.remove(os.path.join(devdir, "2"))
+        assert w.poll_once() == 1
     finally:
         if w:
             w.stop()
         p.stop()
         kubelet.stop()
         shutil.rmtree(sockdir, ignore_errors=True)
+
+
+def test_xid_events_mark_every_vgpu_of_the_gpu():
+    """generic_vgpu_device_plugin.go:330-339 + watchXIDsFunc :387-433 with the reference's own fixture
+    (generic_vgpu_device_plugin_test.go:45-76: one GPU "busID", gpuVgpuMap["busID"] = ["1"], devs "1", "2")."""
+    devs = [dpapi.Device(ID="1", health=dpapi.HEALTHY), dpapi.Device(ID="2", health=dpapi.HEALTHY)]
+    p = serve.GenericVGpuDevicePlugin("vGPUId", "/nonexistent/", devs, socket_dir=tempfile.mkdtemp())
+    r = serve.XidEventRouter([("GPU-a", "busID"), ("GPU-b", "other")], {"busID": ["1"], "other": ["2", "zz"]}, [p])
+    stream = p.ListAndWatch(dpapi.Empty(), None)
+    assert [d.health for d in next(stream).devices] == ["Healthy", "Healthy"]
+    for xid in serve.XID_APPLICATION_ERRORS:                      # application errors: ignored
+        assert r.on_event(xid, "GPU-a") == 0
+    assert r.on_event(79, "GPU-a") == 1                           # fallen off the bus: its vGPU goes unhealthy
+    assert [(d.ID, d.health) for d in next(stream).devices] == [("1", "Unhealthy"), ("2", "Healthy")]
+    p.healthy("1")
+    next(stream)
+    assert r.on_event(48, None) == 2                              # no UUID: every GPU ("zz" is nobody's device)
+    assert [d.health for d in next(stream).devices] == ["Unhealthy", "Healthy"]
+    assert [d.health for d in next(stream).devices] == ["Unhealthy", "Unhealthy"]
+    assert r.on_event(48, "GPU-unknown") == 0
+    p.healthy("2")
+    next(stream)
+    assert r.on_unsupported("GPU-b") == 1                         # too old to register: marked at once
+    assert [d.health for d in next(stream).devices] == ["Unhealthy", "Unhealthy"]

@@ -32,7 +32,7 @@ def keys_of(recs, units):
 
 
 @pytest.mark.parametrize("units", [1, 2])
-@pytest.mark.parametrize("P,local_mode", [(1, 0), (2, 0), (3, 0), (8, 0), (3, 1)])
+@pytest.mark.parametrize("P,local_mode", [(1, 0), (2, 0), (3, 0), (8, 0), (16, 0), (3, 1)])
 def test_exchange_by_owner(emu, units, P, local_mode):
     rng = np.random.default_rng(100 * P + units + local_mode)
     sizes = [int(x) for x in rng.integers(0, 5000, P)]

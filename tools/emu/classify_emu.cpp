@@ -81,7 +81,7 @@ int emu_health_rescan(const uint4* recs, uint32_t n, uint8_t* alive_prev, uint32
 // host reads them.  hdr_out: {n_alive, n_changed}.
 int emu_health_small(const uint4* recs, uint32_t n, uint8_t* alive_prev, uint32_t* changed_out, uint32_t* hdr_out) {
   if (n == 0 || n > HEALTH_SMALL_MAX) return -1;
-  emu_launch(k_health_small, dim3(1), HEALTH_SMALL_THREADS, recs, n, alive_prev, changed_out, hdr_out);
+  emu_launch(k_health_small, dim3(1), HEALTH_SMALL_THREADS, recs, n, alive_prev, changed_out, hdr_out, 7u);
   return 0;
 }
 

@@ -1,5 +1,5 @@
-// shard_emu.cpp — the exchange step of the sharded scan (csrc/kvg_shard.cuh: k_shard_count, k_shard_scan,
-// k_shard_send, k_shard_gather) compiled for the CPU from its real source on top of warp_emu.h.  P ranks are
+// shard_emu.cpp — the exchange step of the sharded scan (csrc/kvg_shard.cuh: k_shard_send,
+// k_shard_gather) compiled for the CPU from its real source on top of warp_emu.h.  P ranks are
 // emulated in ONE process: every rank has its own window + control block, `peers` points at all of them, and the
 // kernels of a step run rank after rank (all sends, then all gathers — the order the flags allow).
 #define KVG_HOST_EMU 1
@@ -29,17 +29,18 @@ static int run(const uint4* const* lists, const uint32_t* n, uint32_t P, uint32_
     peers.ctrl[q] = &ctrl[q];
   }
   uint32_t err = 0;
+  std::vector<std::vector<uint64_t>> state(P);  // chained-scan words: epoch-tagged, reused by every step uncleared
   for (uint32_t step = 1; step <= steps; step++) {
     std::vector<std::vector<uint32_t>> cnt(P);
     for (uint32_t r = 0; r < P; r++) {
       const size_t T = (n[r] + C_TILE - 1) / C_TILE + 1;
-      cnt[r].assign(64 + 2 * (size_t)P * T, 0);
-      for (size_t i = 64; i < cnt[r].size(); i++) cnt[r][i] = 0xdeadbeefu;  // tile counts: nothing relies on zero
+      cnt[r].assign(64, 0);
       uint32_t nn = n[r];
       ShardArgs A;
       A.list = lists[r];
       A.n_ptr = &nn;
-      A.tile_cnt = cnt[r].data() + 64;
+      if (state[r].empty()) state[r].assign(2 * (size_t)P * T, 0);
+      A.state = state[r].data();
       A.totals = cnt[r].data();
       A.ticket = cnt[r].data() + 32;
       A.T = (uint32_t)T;
@@ -51,9 +52,7 @@ static int run(const uint4* const* lists, const uint32_t* n, uint32_t P, uint32_
       A.region_cap = region_cap;
       A.parity = step & 1;
       A.step = step;
-      emu_launch(k_shard_count<U>, dim3((unsigned)T), KVG_BLOCK, A);
-      emu_launch(k_shard_scan, dim3((2 * P + KVG_WARPS - 1) / KVG_WARPS), KVG_BLOCK, A);
-      emu_launch(k_shard_send<U>, dim3((unsigned)T), KVG_BLOCK, A, peers, (const ShardCtrl*)&ctrl[r], &err);
+      emu_launch(k_shard_send<U>, dim3((unsigned)T), KVG_BLOCK, A, peers, (const ShardCtrl*)&ctrl[r], &err, 100u + step);
       if (cnt[r][32] != 0) return -3;  // the ticket resets itself
     }
     for (uint32_t r = 0; r < P; r++) {
@@ -62,7 +61,7 @@ static int run(const uint4* const* lists, const uint32_t* n, uint32_t P, uint32_
       ShardArgs A;
       A.list = lists[r];
       A.n_ptr = &nn;
-      A.tile_cnt = cnt[r].data() + 64;
+      A.state = state[r].data();
       A.totals = cnt[r].data();
       A.ticket = cnt[r].data() + 32;
       A.T = (uint32_t)T;
