@@ -563,7 +563,10 @@ def main():
             c4_step()
         sync_all()
         # size-independent properties of the sharded result (the exact check ran at the headline size)
-        r4, q4 = sharded.fetch(), sharded.fetch_mdev()
+        sharded.scan_device_shard(d4.data_ptr(), c4_pci)          # a fetch returns the LAST scan's result
+        r4 = sharded.fetch()
+        sharded.scan_device_mdev_shard(m4.data_ptr(), c4_mdev, c4_types)
+        q4 = sharded.fetch_mdev()
         cnt = torch.tensor([len(r4.local), len(r4.dev.survivors), len(r4.grp.survivors), len(q4.local),
                             len(q4.by_type.survivors), len(q4.by_parent.survivors)], dtype=torch.int64, device="cuda")
         dist.all_reduce(cnt)

@@ -187,6 +187,10 @@ struct kvg_ctx {
   OrderBufs ord_dev, ord_grp;
   DevBuf<uint32_t> tile_hist;     // K4: [2 orderings][<= 2048 digits][T tiles]
   DevBuf<uint32_t> bin_total;     // [2 orderings][2048] digit totals
+  bool health_smem_set = false;
+  int order_all_ctas = 0;         // CTAs of k_order_all this device holds at once (its grid never exceeds it)
+  DevBuf<uint32_t> grid_bar;      // its grid barrier: arrivals, generation
+  int final_ctas_per_sm = 0;      // occupancy of k_order_final on this device (bounds its grid)
   bool scatter_smem_set = false;  // dynamic shared-memory opt-in of k_order_scatter<11> done on this device
   size_t last_n = 0;     // records of the last enqueued scan
   size_t last_total = 0; // survivors capacity used by the last scan (sharded: all ranks)
@@ -232,6 +236,9 @@ struct kvg_ctx {
   unsigned long long shard_step = 0;
   DevBuf<uint32_t> shard_cnt;            // [2][P] totals, 2 tickets, 1 error word (64-word header)
   DevBuf<uint64_t> shard_state;          // [2][P][T] chained-scan words of k_shard_send
+  DevBuf<uint32_t> send_words;           // [tiles][4 * cw4] published tile counts of k_classify_send
+  uint32_t send_epoch = 0;               // 1 .. 2^21 - 2, 0 = clear send_words first
+  int send_cw4 = 0;
   uint32_t* shard_err = nullptr;         // that error word (device)
   DevBuf<uint4> owned0, owned1;          // dense owned lists of ordering 0 / 1
   DevBuf<uint4> gathered;                // NCCL mode: the all-gathered survivor list
@@ -431,7 +438,7 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   release(ctx->text); release(ctx->dev_off); release(ctx->info); release(ctx->span_sum); release(ctx->pool); release(ctx->ctrl);
   release(ctx->nv_index); release(ctx->sec_lines); release(ctx->type_hash); release(ctx->ragged); release(ctx->tile_count); release(ctx->tile_off);
   release(ctx->tile_max); release(ctx->offs_state);
-  release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist); release(ctx->bin_total);
+  release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist); release(ctx->bin_total); release(ctx->grid_bar);
   for (OrderBufs* o : {&ctx->ord_dev, &ctx->ord_grp}) {
     release(o->p0); release(o->p1); release(o->perm); release(o->tile_heads); release(o->tile_off);
     release(o->seg_key); release(o->seg_off); release(o->seg_name); release(o->heads_state);
@@ -442,7 +449,7 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   release(ctx->changed); release(ctx->flush); release(ctx->nv_ids); release(ctx->probe_slots);
   release(ctx->keys_blob); release(ctx->keys_off); release(ctx->match_off); release(ctx->match_len);
   release(ctx->match_out); release(ctx->gather_counts); release(ctx->gathered);
-  release(ctx->shard_cnt); release(ctx->shard_state); release(ctx->owned0); release(ctx->owned1);
+  release(ctx->shard_cnt); release(ctx->shard_state); release(ctx->send_words); release(ctx->owned0); release(ctx->owned1);
   for (int q = 0; q < SH_MAX_RANKS; q++)
     if (ctx->win_peer[q] && ctx->win_peer[q] != ctx->win_mine) cudaIpcCloseMemHandle(ctx->win_peer[q]);
   if (ctx->win_mine) cudaFree(ctx->win_mine);
@@ -921,6 +928,48 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, const OrdInput& in, size_
     a.src = p == 0 ? in.src[ord] : SRC_PAIRS;
     return a;
   };
+  static const bool persist = [] {  // KVG_ORDER_PERSIST=0: the launch-per-phase form at every size (A/B)
+    const char* e = getenv("KVG_ORDER_PERSIST");
+    return !(e && e[0] == '0');
+  }();
+  if (persist && expect < (2u << 20)) {
+    // latency-bound: the whole step (all passes, permutation, heads) is ONE persistent launch
+    if (!ctx->order_all_ctas) {
+      CK(cudaFuncSetAttribute(k_order_all, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              (int)OrdScatterCfg<RADIX_MAX_BITS>::SMEM));
+      int nb = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_order_all, KVG_BLOCK, OrdScatterCfg<RADIX_MAX_BITS>::SMEM));
+      ctx->order_all_ctas = std::max(1, nb) * std::max(1, ctx->sm_count);
+      ENSURE(ctx->grid_bar, 4);  // zero-filled: arrivals, generation
+    }
+    OrdAllArgs A;
+    for (int ord = 0; ord < 2; ord++) {
+      A.o[ord] = fill(ord, 0);
+      A.p0[ord] = ob[ord]->p0.p;
+      A.p1[ord] = ob[ord]->p1.p;
+      A.nsets[ord] = (uint32_t)nsets[ord];
+      OrdFinalArgs& a = A.f[ord];
+      a.p0 = ob[ord]->p0.p;
+      a.p1 = ob[ord]->p1.p;
+      a.max_key = maxk[ord];
+      a.key_bits_max = key_bits[ord];
+      a.max_bits = max_bits;
+      a.n_ptr = cnt[ord];
+      a.perm = ob[ord]->perm.p;
+      a.state = ob[ord]->heads_state.p;
+      a.tile_heads = ob[ord]->tile_heads.p;
+      a.tile_off = ob[ord]->tile_off.p;
+      a.seg_key = ob[ord]->seg_key.p;
+      a.seg_off = ob[ord]->seg_off.p;
+      a.n_seg = ord == 0 ? &c->n_dev_keys : &c->n_groups;
+      a.head_surv = ord == 0 ? in.head_surv : nullptr;
+      a.head_name = a.head_surv ? ob[ord]->seg_name.p : nullptr;
+    }
+    A.gbar = ctx->grid_bar.p;
+    const unsigned G = (unsigned)std::min<size_t>(2 * Te, (size_t)ctx->order_all_ctas);
+    LAUNCH("order_all", k_order_all, G, KVG_BLOCK, OrdScatterCfg<RADIX_MAX_BITS>::SMEM, A);
+    return check_launch(ctx, "orderings");
+  }
   if (!ctx->scatter_smem_set) {  // a function attribute is per device: remember it per context
     CK(cudaFuncSetAttribute(k_order_scatter<RADIX_MAX_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)OrdScatterCfg<RADIX_MAX_BITS>::SMEM));
@@ -984,8 +1033,16 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, const OrdInput& in, size_
     t.total_out = nseg[ord];
     t.state = ob[ord]->heads_state.p;
   }
-  dim3 fgrid((unsigned)T, 2);
+  // the final kernels loop over the tiles: grids for the EXPECTED length (every tile of a longer list is still
+  // visited); the chained-scan form must also fit the GPU at once (half of it: two orderings share the launch)
+  dim3 fgrid((unsigned)Te, 2);
   if (expect < (2u << 20)) {  // latency-bound: one launch (chained scan of the head counts)
+    if (!ctx->final_ctas_per_sm) {
+      int nb = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_order_final, KVG_BLOCK, 0));
+      ctx->final_ctas_per_sm = std::max(1, nb);
+    }
+    fgrid.x = (unsigned)std::min<size_t>(Te, (size_t)std::max(1, ctx->sm_count) * ctx->final_ctas_per_sm / 2);
     LAUNCH("order_final", k_order_final, fgrid, KVG_BLOCK, 0, ff, next_epoch());
   } else {                 // bandwidth-bound: no CTA waits for another
     LAUNCH("order_count", k_order_heads<false>, fgrid, KVG_BLOCK, 0, ff);
@@ -1374,10 +1431,14 @@ int kvg_health_rescan(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, kvg_healt
       CK(cudaMemsetAsync(ctx->alive_prev.p, 0, n + 1, ctx->stream));
       ctx->health_n = n;
     }
-    static const bool zero_copy = [] {  // KVG_HEALTH_ZEROCOPY=1: the kernel reads the pinned snapshot in place (A/B)
+    static const bool zero_copy = [] {  // KVG_HEALTH_ZEROCOPY=0: DMA copy first, device-resident reads (A/B)
       const char* e = getenv("KVG_HEALTH_ZEROCOPY");
-      return e && e[0] == '1';
+      return !(e && e[0] == '0');
     }();
+    if (!ctx->health_smem_set) {
+      CK(cudaFuncSetAttribute(k_health_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HEALTH_SMALL_SMEM));
+      ctx->health_smem_set = true;
+    }
     cudaPointerAttributes attr;
     const void* dev_view = nullptr;
     if (cudaPointerGetAttributes(&attr, recs) == cudaSuccess && attr.type == cudaMemoryTypeHost) dev_view = attr.devicePointer;
@@ -1405,7 +1466,7 @@ int kvg_health_rescan(kvg_ctx* ctx, const kvg_pci_rec* recs, size_t n, kvg_healt
     uint32_t* hdr = (uint32_t*)(b + align64(sizeof(kvg_health_delta)));
     const uint32_t seq = ++ctx->health_seq ? ctx->health_seq : ++ctx->health_seq;  // never 0
     ((volatile uint32_t*)hdr)[2] = 0;
-    LAUNCH("health_diff", k_health_small, 1, HEALTH_SMALL_THREADS, 0, (const uint4*)dev_view, (uint32_t)n,
+    LAUNCH("health_diff", k_health_small, 1, HEALTH_SMALL_THREADS, HEALTH_SMALL_SMEM, (const uint4*)dev_view, (uint32_t)n,
            ctx->alive_prev.p, (uint32_t*)(b + o_list), hdr, seq);
     int rc = check_launch(ctx, "health");
     if (rc == KVG_OK) {
@@ -1542,7 +1603,10 @@ extern "C" {
 
 // K5 up to the dense survivor list (ctx->surv, 2 x 16 bytes per mdev): type dictionary (labels, canonical
 // ids, the resource-name join of every label) + classification + stable compaction
-static int mdev_classify(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type_dict* types) {
+// fused: fill *fused with the classify operator and stop in front of the classify kernels (the sharded scan
+// classifies and sends in one kernel)
+static int mdev_classify(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_type_dict* types,
+                         MdevClassifyOp* fused = nullptr) {
   {
     int rc_t = table_needed(ctx, "kvg_pciids_load must precede a scan (the scan joins names)");
     if (rc_t) return rc_t;
@@ -1574,6 +1638,10 @@ static int mdev_classify(kvg_ctx* ctx, const void* d_recs, size_t n, const kvg_t
   op.n_types = nt;
   op.local_max_parent = 0;
   op.local_max_type = 0;
+  if (fused) {
+    *fused = op;
+    return check_launch(ctx, "mdev dictionary");
+  }
   {
     constexpr int T = 128, R = 4;  // 512 x 32-byte records = 16 KiB per tile
     const size_t tiles = (n + (size_t)T * R - 1) / ((size_t)T * R);
@@ -1939,14 +2007,18 @@ static int nccl_allgatherv(kvg_ctx* ctx, const uint4* local, int U, size_t* tota
 // The exchange step behind a dense local survivor list of <= n_cap records (U x 16 bytes each) whose length
 // lives in ctrl->n_surv: multisplit by owner -> windows -> owned lists (ctx->owned0 / owned1, lengths in
 // ctrl->n_own[], largest keys in ctrl->max_devkey / max_group).  Returns the capacity of an owned list.
-template <int U>
-static int enqueue_exchange(kvg_ctx* ctx, const uint4* local, size_t n_cap, size_t* owned_cap_out) {
+// fused (peer transport, latency-bound shard): *fused is the classify operator of the shard — the records are
+// classified and sent by ONE kernel (k_classify_send) and `local` is the dense list it also writes.
+constexpr size_t FUSED_SEND_MAX = 2u << 20;  // records per shard up to which the T^2 prefix of k_classify_send is free
+template <int U, class Op, int ROWS>
+static int enqueue_exchange(kvg_ctx* ctx, const uint4* local, size_t n_cap, size_t* owned_cap_out, Op* fused = nullptr) {
   const int P = ctx->nranks;
   const bool peer = ctx->p2p;
   if (!peer && !ctx->comm) {
     ctx->err = "kvg_comm_init / kvg_comm_p2p_import has not been called";
     return KVG_ESTATE;
   }
+  if (fused && !peer) return KVG_ESTATE;  // callers fuse only over the peer transport
   ScanCtrl* c = ctx->ctrl.p;
   const uint4* list = local;
   size_t list_cap = n_cap;
@@ -2006,6 +2078,12 @@ static int enqueue_exchange(kvg_ctx* ctx, const uint4* local, size_t n_cap, size
   A.region_cap = peer ? ctx->win_cap / U : (size_t)P * ctx->win_cap / U;
   A.parity = (uint32_t)(step & 1);
   A.step = step;
+#ifdef KVG_EXP
+  {
+    const char* e = getenv("KVG_SHARD_EXP");
+    A.exp = e ? (uint32_t)atoi(e) : 0u;
+  }
+#endif
   ShardPeers peers;
   memset(&peers, 0, sizeof peers);
   for (int q = 0; q < P; q++) {
@@ -2014,7 +2092,28 @@ static int enqueue_exchange(kvg_ctx* ctx, const uint4* local, size_t n_cap, size
     peers.win[q] = (uint4*)(base + SH_HDR);
   }
   const ShardCtrl* mine = (const ShardCtrl*)ctx->win_mine;
-  LAUNCH("shard_send", k_shard_send<U>, (unsigned)T, KVG_BLOCK, 0, A, peers, mine, err, next_epoch());
+  if (fused) {
+    constexpr int TH = 128;
+    const size_t tiles = std::max<size_t>(1, (n_cap + (size_t)TH * ROWS - 1) / ((size_t)TH * ROWS));
+    const int C = 1 + 2 * P;
+    const int cw4 = C <= 8 ? 2 : C <= 16 ? 4 : C <= 20 ? 5 : 9;
+    ENSURE(ctx->send_words, tiles * 4 * (size_t)cw4);
+    if (ctx->send_epoch == 0 || ctx->send_cw4 != cw4) {  // the epoch field wrapped (or the row shape changed): start over
+      CK(cudaMemsetAsync(ctx->send_words.p, 0, ctx->send_words.cap * sizeof(uint32_t), ctx->stream));
+      ctx->send_epoch = 0;
+      ctx->send_cw4 = cw4;
+    }
+    const uint32_t ep = ++ctx->send_epoch;
+    if (ctx->send_epoch == (1u << (32 - CS_COUNT_BITS)) - 1) ctx->send_epoch = 0;
+    switch (cw4) {
+      case 2: LAUNCH("classify_send", (k_classify_send<Op, TH, ROWS, 2>), (unsigned)tiles, TH, 0, *fused, A, peers, mine, err, ctx->send_words.p, ep); break;
+      case 4: LAUNCH("classify_send", (k_classify_send<Op, TH, ROWS, 4>), (unsigned)tiles, TH, 0, *fused, A, peers, mine, err, ctx->send_words.p, ep); break;
+      case 5: LAUNCH("classify_send", (k_classify_send<Op, TH, ROWS, 5>), (unsigned)tiles, TH, 0, *fused, A, peers, mine, err, ctx->send_words.p, ep); break;
+      default: LAUNCH("classify_send", (k_classify_send<Op, TH, ROWS, 9>), (unsigned)tiles, TH, 0, *fused, A, peers, mine, err, ctx->send_words.p, ep); break;
+    }
+  } else {
+    LAUNCH("shard_send", k_shard_send<U>, (unsigned)T, KVG_BLOCK, 0, A, peers, mine, err, next_epoch());
+  }
   GatherArgs G;
   G.window = (const uint4*)(ctx->win_mine + SH_HDR);
   G.owned[0] = ctx->owned0.p;
@@ -2047,10 +2146,23 @@ int kvg_dev_scan_pci_sharded(kvg_ctx* ctx, const void* d_recs, size_t n_local) {
   CK(cudaSetDevice(ctx->device));
   ENSURE(ctx->surv, n_local + 1);
   CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
-  int rc = enqueue_classify(ctx, d_recs, n_local, ctx->surv.p);
-  if (rc) return rc;
   size_t owned_cap = 0;
-  rc = enqueue_exchange<1>(ctx, ctx->surv.p, n_local, &owned_cap);
+  int rc;
+  if (ctx->p2p && n_local < FUSED_SEND_MAX) {  // classify + send in one kernel
+    PciClassifyOp op;
+    op.recs = (const uint4*)d_recs;
+    op.n = (uint32_t)n_local;
+    op.out = (kvg_pci_surv*)ctx->surv.p;
+    op.ctrl = ctx->ctrl.p;
+    op.nv_index = ctx->nv_index.p;
+    op.local_max_group = 0;
+    op.local_max_dev = 0;
+    rc = enqueue_exchange<1, PciClassifyOp, 8>(ctx, ctx->surv.p, n_local, &owned_cap, &op);
+  } else {
+    rc = enqueue_classify(ctx, d_recs, n_local, ctx->surv.p);
+    if (rc) return rc;
+    rc = enqueue_exchange<1, PciClassifyOp, 8>(ctx, ctx->surv.p, n_local, &owned_cap);
+  }
   if (rc) return rc;
   rc = enqueue_owned_orderings(ctx, owned_cap, n_local, SRC_PCI_DEVICE, SRC_PCI_GROUP, true);
   if (rc) return rc;
@@ -2213,10 +2325,18 @@ int kvg_dev_scan_pci_shard_fetch(kvg_ctx* ctx, kvg_pci_shard_result** res) {
 
 int kvg_dev_scan_mdev_sharded(kvg_ctx* ctx, const void* d_recs, size_t n_local, const kvg_type_dict* types) {
   if (!ctx || !types || (!d_recs && n_local) || n_local > 0x7ffffff0ull || ((uintptr_t)d_recs & 15)) return KVG_EINVAL;
-  int rc = mdev_classify(ctx, d_recs, n_local, types);
-  if (rc) return rc;
   size_t owned_cap = 0;
-  rc = enqueue_exchange<2>(ctx, ctx->surv.p, n_local, &owned_cap);
+  int rc;
+  if (ctx->p2p && n_local < FUSED_SEND_MAX) {  // classify + send in one kernel
+    MdevClassifyOp op;
+    rc = mdev_classify(ctx, d_recs, n_local, types, &op);
+    if (rc) return rc;
+    rc = enqueue_exchange<2, MdevClassifyOp, 4>(ctx, ctx->surv.p, n_local, &owned_cap, &op);
+  } else {
+    rc = mdev_classify(ctx, d_recs, n_local, types);
+    if (rc) return rc;
+    rc = enqueue_exchange<2, MdevClassifyOp, 4>(ctx, ctx->surv.p, n_local, &owned_cap);
+  }
   if (rc) return rc;
   rc = enqueue_owned_orderings(ctx, owned_cap, n_local, SRC_MDEV_TYPE, SRC_MDEV_PARENT, false);
   if (rc) return rc;

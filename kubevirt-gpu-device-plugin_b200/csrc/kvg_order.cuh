@@ -94,20 +94,15 @@ __device__ __forceinline__ uint2 ord_load(const OrdArgs& a, uint32_t i) {
 }
 
 // ---- histogram ----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(KVG_BLOCK) k_order_hist(OrdArgs2 aa) {
-  pdl_enter();
-  const OrdArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
+// tiles tile0, tile0 + tstride, ... of one ordering; h: RADIX_MAX_DIGITS words of shared memory
+__device__ __forceinline__ void ord_hist_tiles(const OrdArgs& a, const RadixPlan pl, uint32_t tile0, uint32_t tstride,
+                                               uint32_t* h) {
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
-  const RadixPlan pl = ord_pass(a);
-  if (!pl.bits) return;
   const uint32_t dmask = (1u << pl.bits) - 1;
   const uint32_t nj = ((1u << pl.bits) + KVG_BLOCK - 1) / KVG_BLOCK;  // digit chunks in use
-  __shared__ uint32_t h[RADIX_MAX_DIGITS];
   const uint32_t lane = lane_id();
-  // tile loop: launched with one CTA per tile for the always-active passes, with a small grid for the
-  // high passes that are usually ruled out by the device-side max key (they then cost ~nothing)
-  for (uint32_t tile = blockIdx.x; tile < T; tile += gridDim.x) {
+  for (uint32_t tile = tile0; tile < T; tile += tstride) {
     for (uint32_t j = 0; j < nj; j++) h[j * KVG_BLOCK + threadIdx.x] = 0;
     __syncthreads();
     const uint32_t base = tile * C_TILE + warp_id() * C_WARP_ITEMS;
@@ -128,19 +123,27 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_order_hist(OrdArgs2 aa) {
     __syncthreads();
   }
 }
+__global__ void __launch_bounds__(KVG_BLOCK) k_order_hist(OrdArgs2 aa) {
+  pdl_enter();
+  const OrdArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
+  const RadixPlan pl = ord_pass(a);
+  if (!pl.bits) return;
+  __shared__ uint32_t h[RADIX_MAX_DIGITS];
+  // tile loop: launched with one CTA per tile for the always-active passes, with a small grid for the
+  // high passes that are usually ruled out by the device-side max key (they then cost ~nothing)
+  ord_hist_tiles(a, pl, blockIdx.x, gridDim.x, h);
+}
 
 // ---- tile scan: one warp per digit row, in place; bin_total[digit] <- the row's total -----------------
 constexpr uint32_t TS_WARPS = 8;  // digit rows per CTA
-__global__ void __launch_bounds__(TS_WARPS * 32) k_order_tilescan(OrdArgs2 aa) {
-  pdl_enter();
-  const OrdArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
+// digit rows row0, row0 + rstride, ... of one ordering, one warp per row
+__device__ __forceinline__ void ord_tilescan_rows(const OrdArgs& a, const RadixPlan pl, uint32_t row0, uint32_t rstride) {
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
-  const RadixPlan pl = ord_pass(a);
-  if (T == 0 || !pl.bits) return;
+  if (T == 0) return;
   const uint32_t digits = (((1u << pl.bits) + KVG_BLOCK - 1) / KVG_BLOCK) * KVG_BLOCK;  // rows the histogram wrote
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  for (uint32_t dg = blockIdx.x * TS_WARPS + warp; dg < digits; dg += gridDim.x * TS_WARPS) {
+  const uint32_t lane = lane_id();
+  for (uint32_t dg = row0; dg < digits; dg += rstride) {
     uint32_t* row = a.tile_hist + (size_t)dg * T;
     uint32_t carry = 0;
     for (uint32_t b = 0; b < T; b += 128) {  // four independent loads per lane and round
@@ -160,6 +163,13 @@ __global__ void __launch_bounds__(TS_WARPS * 32) k_order_tilescan(OrdArgs2 aa) {
     }
     if (lane == 0) a.bin_total[dg] = carry;
   }
+}
+__global__ void __launch_bounds__(TS_WARPS * 32) k_order_tilescan(OrdArgs2 aa) {
+  pdl_enter();
+  const OrdArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
+  const RadixPlan pl = ord_pass(a);
+  if (!pl.bits) return;
+  ord_tilescan_rows(a, pl, blockIdx.x * TS_WARPS + (threadIdx.x >> 5), gridDim.x * TS_WARPS);
 }
 
 // the same for long rows (bandwidth-bound sizes: thousands of tiles): one CTA per digit row, every thread
@@ -207,35 +217,27 @@ struct OrdScatterCfg {
   static constexpr int MIN_CTAS = MAXB <= 8 ? 5 : 3;  // 6 would cap registers at 40 and spill
 };
 
+// tiles tile0, tile0 + tstride, ... of one ordering; rs_smem: Cfg::SMEM bytes, scratch: KVG_WARPS + 1 words
 template <uint32_t MAXB>
-__global__ void __launch_bounds__(KVG_BLOCK, OrdScatterCfg<MAXB>::MIN_CTAS) k_order_scatter(OrdArgs2 aa) {
+__device__ __forceinline__ void ord_scatter_tiles(const OrdArgs& a, const RadixPlan pl, uint32_t tile0, uint32_t tstride,
+                                                  uint8_t* rs_smem, uint32_t* scratch) {
   using Cfg = OrdScatterCfg<MAXB>;
   constexpr uint32_t DPT = Cfg::DPT;
-  pdl_enter();
-  const OrdArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
-  const RadixPlan pl = ord_pass(a);
-  if (!pl.bits) return;
   const uint32_t dmask = (1u << pl.bits) - 1;
   const uint32_t digits = 1u << pl.bits;
   const uint32_t lane = lane_id(), warp = warp_id(), tid = threadIdx.x;
   const uint32_t d0 = tid * DPT;  // my digits: d0 .. d0 + DPT - 1
   const bool mine = d0 < digits;
-#ifndef KVG_HOST_EMU
-  extern __shared__ __align__(16) uint8_t rs_smem[];
-#else
-  static __attribute__((aligned(16))) uint8_t rs_smem[Cfg::SMEM];
-#endif
   uint16_t (*s_cnt)[Cfg::DIGITS] = reinterpret_cast<uint16_t (*)[Cfg::DIGITS]>(rs_smem);
   uint16_t* s_start = reinterpret_cast<uint16_t*>(rs_smem + Cfg::CNT_BYTES);
   int32_t* s_goff = reinterpret_cast<int32_t*>(rs_smem + Cfg::CNT_BYTES + Cfg::START_BYTES);
   uint2* s_stage = reinterpret_cast<uint2*>(rs_smem + Cfg::CNT_BYTES + Cfg::START_BYTES + Cfg::GOFF_BYTES);
-  __shared__ uint32_t scratch[KVG_WARPS + 1];
   uint32_t total;
   uint32_t bin_base[DPT];
   bool have_base = false;
-  for (uint32_t tile = blockIdx.x; tile < T; tile += gridDim.x) {
+  for (uint32_t tile = tile0; tile < T; tile += tstride) {
     const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
     // all global loads of the tile up front: the scanned tile counts of my digits, the pairs
     uint32_t tile_prefix[DPT];
@@ -350,6 +352,20 @@ __global__ void __launch_bounds__(KVG_BLOCK, OrdScatterCfg<MAXB>::MIN_CTAS) k_or
     }
   }  // tile loop
 }
+template <uint32_t MAXB>
+__global__ void __launch_bounds__(KVG_BLOCK, OrdScatterCfg<MAXB>::MIN_CTAS) k_order_scatter(OrdArgs2 aa) {
+  pdl_enter();
+  const OrdArgs a = blockIdx.y ? aa.o[1] : aa.o[0];  // static indices: parameters stay in the constant bank
+  const RadixPlan pl = ord_pass(a);
+  if (!pl.bits) return;
+#ifndef KVG_HOST_EMU
+  extern __shared__ __align__(16) uint8_t rs_smem[];
+#else
+  static __attribute__((aligned(16))) uint8_t rs_smem[OrdScatterCfg<MAXB>::SMEM];
+#endif
+  __shared__ uint32_t scratch[KVG_WARPS + 1];
+  ord_scatter_tiles<MAXB>(a, pl, blockIdx.x, gridDim.x, rs_smem, scratch);
+}
 
 // ---- final permutation + distinct keys of both orderings ------------------------------------------
 struct OrdFinalArgs {
@@ -417,15 +433,17 @@ __device__ __forceinline__ void ord_emit_heads(const OrdFinalArgs& a, uint32_t o
   }
 }
 
-// latency-bound sizes: one launch; the per-tile head counts are combined by a chained scan (look-back)
+// latency-bound sizes: one launch; the per-tile head counts are combined by a chained scan (look-back).
+// Tile loop: the grid may be smaller than the tile count (the sharded scan sizes it for the EXPECTED length of
+// an owned list, not for its capacity) — it must then fit the GPU at once (a CTA waits for lower tiles, which
+// must be running or done: enqueue_orderings bounds the grid by the occupancy).
 __global__ void __launch_bounds__(KVG_BLOCK) k_order_final(OrdFinalArgs2 aa, uint32_t epoch) {
   pdl_enter();
   const OrdFinalArgs a = blockIdx.y ? aa.o[1] : aa.o[0];
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
-  const uint32_t tile = blockIdx.x;
-  if (tile >= T) {
-    if (n == 0 && tile == 0 && threadIdx.x == 0) {
+  if (n == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
       a.seg_off[0] = 0;
       *a.n_seg = 0;
     }
@@ -433,32 +451,35 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_order_final(OrdFinalArgs2 aa, uin
   }
   const uint2* pairs = ord_final_buf(a);
   const uint32_t lane = lane_id(), warp = warp_id();
-  const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
   __shared__ uint32_t s_w[KVG_WARPS];
   __shared__ uint32_t s_base;
-  uint32_t bal[C_ROWS], key[C_ROWS], idx[C_ROWS];
-  const uint32_t wtot = ord_tile_heads(a, pairs, n, base, lane, true, bal, key, idx);
-  if (lane == 0) s_w[warp] = wtot;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t t = 0;
+  for (uint32_t tile = blockIdx.x; tile < T; tile += gridDim.x) {
+    const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
+    uint32_t bal[C_ROWS], key[C_ROWS], idx[C_ROWS];
+    const uint32_t wtot = ord_tile_heads(a, pairs, n, base, lane, true, bal, key, idx);
+    if (lane == 0) s_w[warp] = wtot;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t t = 0;
 #pragma unroll
-    for (uint32_t w = 0; w < KVG_WARPS; w++) t += s_w[w];
-    const uint32_t excl = lookback_sum(a.state, tile, t, epoch);
-    if (lane == 0) {
-      s_base = excl;
-      if (tile == T - 1) {
-        *a.n_seg = excl + t;
-        a.seg_off[excl + t] = n;
+      for (uint32_t w = 0; w < KVG_WARPS; w++) t += s_w[w];
+      const uint32_t excl = lookback_sum(a.state, tile, t, epoch);
+      if (lane == 0) {
+        s_base = excl;
+        if (tile == T - 1) {
+          *a.n_seg = excl + t;
+          a.seg_off[excl + t] = n;
+        }
       }
     }
-  }
-  __syncthreads();
-  uint32_t off = s_base;
+    __syncthreads();
+    uint32_t off = s_base;
 #pragma unroll
-  for (uint32_t w = 0; w < KVG_WARPS; w++)
-    if (w < warp) off += s_w[w];
-  ord_emit_heads(a, off, base, lane, bal, key, idx);
+    for (uint32_t w = 0; w < KVG_WARPS; w++)
+      if (w < warp) off += s_w[w];
+    ord_emit_heads(a, off, base, lane, bal, key, idx);
+    __syncthreads();  // s_w / s_base are rewritten by the next tile
+  }
 }
 
 // bandwidth-bound sizes: <false> writes the permutation and counts heads per tile, k_tile_offsets scans the
@@ -469,34 +490,177 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_order_heads(OrdFinalArgs2 aa) {
   const OrdFinalArgs a = blockIdx.y ? aa.o[1] : aa.o[0];
   const uint32_t n = *a.n_ptr;
   const uint32_t T = (n + C_TILE - 1) / C_TILE;
-  const uint32_t tile = blockIdx.x;
-  if (tile >= T) {
-    if (EMIT && n == 0 && tile == 0 && threadIdx.x == 0) a.seg_off[0] = 0;
+  if (n == 0) {
+    if (EMIT && blockIdx.x == 0 && threadIdx.x == 0) a.seg_off[0] = 0;
     return;
   }
   const uint2* pairs = ord_final_buf(a);
   const uint32_t lane = lane_id(), warp = warp_id();
-  const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
   __shared__ uint32_t s_w[KVG_WARPS];
-  uint32_t bal[C_ROWS], key[C_ROWS], idx[C_ROWS];
-  const uint32_t wtot = ord_tile_heads(a, pairs, n, base, lane, !EMIT, bal, key, idx);
-  if (lane == 0) s_w[warp] = wtot;
-  __syncthreads();
-  if (!EMIT) {
-    if (threadIdx.x == 0) {
-      uint32_t t = 0;
+  for (uint32_t tile = blockIdx.x; tile < T; tile += gridDim.x) {
+    const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
+    uint32_t bal[C_ROWS], key[C_ROWS], idx[C_ROWS];
+    const uint32_t wtot = ord_tile_heads(a, pairs, n, base, lane, !EMIT, bal, key, idx);
+    if (lane == 0) s_w[warp] = wtot;
+    __syncthreads();
+    if (!EMIT) {
+      if (threadIdx.x == 0) {
+        uint32_t t = 0;
 #pragma unroll
-      for (uint32_t w = 0; w < KVG_WARPS; w++) t += s_w[w];
-      a.tile_heads[tile] = t;
+        for (uint32_t w = 0; w < KVG_WARPS; w++) t += s_w[w];
+        a.tile_heads[tile] = t;
+      }
+    } else {
+      uint32_t off = a.tile_off[tile];
+#pragma unroll
+      for (uint32_t w = 0; w < KVG_WARPS; w++)
+        if (w < warp) off += s_w[w];
+      ord_emit_heads(a, off, base, lane, bal, key, idx);
+      if (tile == T - 1 && threadIdx.x == 0) a.seg_off[*a.n_seg] = n;
     }
-    return;
+    __syncthreads();  // s_w is rewritten by the next tile
   }
-  uint32_t off = a.tile_off[tile];
+}
+
+// ---- the whole ordering step as ONE persistent launch (latency-bound sizes) --------------------------------
+// Below ~2 M elements every kernel above runs for 3-15 us and the step is a chain of ten launches whose
+// boundaries (launch gap, ramp-up, tail, and the chained scan of the final kernel: ~6 us of dependent L2 round
+// trips when all tiles start together) cost as much as the work.  k_order_all runs the same phases — the same
+// device functions — in one grid that fits the GPU at once, separated by grid barriers:
+//   per pass:  histograms | tile scan | scatter        (3 barriers)
+//   final:     permutation + head counts | offsets (every CTA sums the <= 1024 tile counts in front of its
+//              tile: no chain) + heads                    (1 barrier)
+// Both orderings share every phase.  The barrier is the sense-reversing counter of cooperative groups
+// (thread 0: fence, arrive, spin on the generation word, fence; block barriers around it); enqueue_orderings
+// bounds the grid by the occupancy so that every CTA is resident.
+struct OrdAllArgs {
+  OrdArgs o[2];       // pass 0 view of each ordering (pass / buffers of later passes are derived on the device)
+  OrdFinalArgs f[2];
+  uint2* p0[2];       // ping-pong buffers
+  uint2* p1[2];
+  uint32_t nsets[2];  // launch sets of each ordering (ceil(key bits / max_bits))
+  uint32_t* gbar;     // [0] arrivals, [1] generation
+};
+__device__ __forceinline__ void grid_sync(uint32_t* bar) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t gen = *((volatile uint32_t*)&bar[1]);  // cannot advance before I arrive
+    __threadfence();
+    if (atomicAdd(&bar[0], 1u) == gridDim.x - 1) {
+      atomicExch(&bar[0], 0u);
+      __threadfence();
+      atomicAdd(&bar[1], 1u);
+    } else {
+      while (*((volatile uint32_t*)&bar[1]) == gen) {
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ OrdArgs ord_args_of_pass(const OrdArgs& base, uint2* p0, uint2* p1, uint32_t nsets, uint32_t p) {
+  OrdArgs a = base;
+  a.pairs_in = (p & 1) ? p0 : p1;  // pass 0 reads the survivor records (or, SRC_PAIRS, pairs placed in p1)
+  a.pairs_out = (p & 1) ? p1 : p0;
+  a.pass = p < nsets ? p : 0xffu;
+  a.src = p == 0 ? base.src : SRC_PAIRS;
+  return a;
+}
+__global__ void __launch_bounds__(KVG_BLOCK, OrdScatterCfg<RADIX_MAX_BITS>::MIN_CTAS) k_order_all(OrdAllArgs A) {
+  using Cfg = OrdScatterCfg<RADIX_MAX_BITS>;
+  pdl_enter();
+#ifndef KVG_HOST_EMU
+  extern __shared__ __align__(16) uint8_t rs_smem[];
+#else
+  static __attribute__((aligned(16))) uint8_t rs_smem[Cfg::SMEM];
+#endif
+  static_assert(Cfg::SMEM >= RADIX_MAX_DIGITS * 4, "the histogram aliases the scatter's shared memory");
+  __shared__ uint32_t scratch[KVG_WARPS + 1];
+  __shared__ uint32_t s_w[KVG_WARPS];
+  const uint32_t G = gridDim.x, cta = blockIdx.x;
+  const uint32_t lane = lane_id(), warp = warp_id(), tid = threadIdx.x;
+  const uint32_t n0 = *A.o[0].n_ptr, n1 = *A.o[1].n_ptr;
+  const uint32_t T0 = (n0 + C_TILE - 1) / C_TILE;
+  // ordering 1 starts where ordering 0's tiles end, so that the CTAs ordering 0 left idle work first
+  const uint32_t cta1 = (cta + G - T0 % G) % G;
+  const uint32_t max_sets = max(A.nsets[0], A.nsets[1]);
+  for (uint32_t p = 0; p < max_sets; p++) {
+    const OrdArgs a0 = ord_args_of_pass(A.o[0], A.p0[0], A.p1[0], A.nsets[0], p);
+    const OrdArgs a1 = ord_args_of_pass(A.o[1], A.p0[1], A.p1[1], A.nsets[1], p);
+    const RadixPlan pl0 = ord_pass(a0), pl1 = ord_pass(a1);
+    if (!pl0.bits && !pl1.bits) break;  // the same decision in every CTA (device-side plan)
+    if (pl0.bits) ord_hist_tiles(a0, pl0, cta, G, reinterpret_cast<uint32_t*>(rs_smem));
+    if (pl1.bits) ord_hist_tiles(a1, pl1, cta1, G, reinterpret_cast<uint32_t*>(rs_smem));
+    grid_sync(A.gbar);
+    if (pl0.bits) ord_tilescan_rows(a0, pl0, cta * KVG_WARPS + warp, G * KVG_WARPS);
+    if (pl1.bits) ord_tilescan_rows(a1, pl1, cta1 * KVG_WARPS + warp, G * KVG_WARPS);
+    grid_sync(A.gbar);
+    if (pl0.bits) ord_scatter_tiles<RADIX_MAX_BITS>(a0, pl0, cta, G, rs_smem, scratch);
+    if (pl1.bits) ord_scatter_tiles<RADIX_MAX_BITS>(a1, pl1, cta1, G, rs_smem, scratch);
+    grid_sync(A.gbar);
+  }
+  // ---- final: permutation + head counts per tile
+#pragma unroll 1
+  for (uint32_t ord = 0; ord < 2; ord++) {
+    const OrdFinalArgs f = ord ? A.f[1] : A.f[0];
+    const uint32_t n = ord ? n1 : n0;
+    const uint32_t T = (n + C_TILE - 1) / C_TILE;
+    if (n == 0) {
+      if (cta == 0 && tid == 0) {
+        f.seg_off[0] = 0;
+        *f.n_seg = 0;
+      }
+      continue;
+    }
+    const uint2* pairs = ord_final_buf(f);
+    for (uint32_t tile = ord ? cta1 : cta; tile < T; tile += G) {
+      const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
+      uint32_t bal[C_ROWS], key[C_ROWS], idx[C_ROWS];
+      const uint32_t wtot = ord_tile_heads(f, pairs, n, base, lane, true, bal, key, idx);
+      if (lane == 0) s_w[warp] = wtot;
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t t = 0;
 #pragma unroll
-  for (uint32_t w = 0; w < KVG_WARPS; w++)
-    if (w < warp) off += s_w[w];
-  ord_emit_heads(a, off, base, lane, bal, key, idx);
-  if (tile == T - 1 && threadIdx.x == 0) a.seg_off[*a.n_seg] = n;
+        for (uint32_t w = 0; w < KVG_WARPS; w++) t += s_w[w];
+        f.tile_heads[tile] = t;
+      }
+      __syncthreads();
+    }
+  }
+  grid_sync(A.gbar);
+  // ---- heads: every CTA sums the tile counts in front of its tile, then emits
+#pragma unroll 1
+  for (uint32_t ord = 0; ord < 2; ord++) {
+    const OrdFinalArgs f = ord ? A.f[1] : A.f[0];
+    const uint32_t n = ord ? n1 : n0;
+    const uint32_t T = (n + C_TILE - 1) / C_TILE;
+    if (n == 0) continue;
+    const uint2* pairs = ord_final_buf(f);
+    for (uint32_t tile = ord ? cta1 : cta; tile < T; tile += G) {
+      uint32_t part = 0;
+      for (uint32_t i = tid; i < tile; i += KVG_BLOCK) part += f.tile_heads[i];
+      uint32_t before;
+      block_excl_sum(part, scratch, &before);  // syncs inside; `before` = heads of all earlier tiles
+      const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
+      uint32_t bal[C_ROWS], key[C_ROWS], idx[C_ROWS];
+      const uint32_t wtot = ord_tile_heads(f, pairs, n, base, lane, false, bal, key, idx);
+      if (lane == 0) s_w[warp] = wtot;
+      __syncthreads();
+      uint32_t off = before, t = 0;
+#pragma unroll
+      for (uint32_t w = 0; w < KVG_WARPS; w++) {
+        if (w < warp) off += s_w[w];
+        t += s_w[w];
+      }
+      ord_emit_heads(f, off, base, lane, bal, key, idx);
+      if (tile == T - 1 && tid == 0) {
+        *f.n_seg = before + t;
+        f.seg_off[before + t] = n;
+      }
+      __syncthreads();  // scratch / s_w are rewritten by the next tile
+    }
+  }
 }
 
 }  // namespace kvg

@@ -100,18 +100,31 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_prep(K1PrepArgs P) {
     for (size_t i = tid; i < P.pool16; i += nth) P.pool[i] = make_uint4(0, 0, 0, 0);
 }
 
-// bit 7 of byte b is CLEAR iff byte b of w is '\n' (exact: no carries cross a byte)
-__device__ __forceinline__ uint32_t k1_not_nl(uint32_t w) {
-  const uint32_t x = w ^ 0x0A0A0A0Au;
-  return ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;
+// bit 7 of byte b is CLEAR iff the LOW SEVEN bits of byte b of w are those of '\n' — true for '\n' and for
+// 0x8A.  Three instructions per word ((w ^ c) & m as ONE LOP3 with a constant in a register, an add, and the
+// shift that the combine needs anyway); the exact test costs one more per word, and bytes >= 0x80 are rare in
+// pci.ids, so k1_row_mask pays for them only in the cells that have one.
+__device__ __forceinline__ uint32_t k1_lo7(uint32_t w) {
+#ifndef KVG_HOST_EMU
+  uint32_t t;
+  asm("lop3.b32 %0, %1, 0x0A0A0A0A, 0x7F7F7F7F, 0x28;" : "=r"(t) : "r"(w));  // (w ^ 0x0A..) & 0x7F..
+  return t + 0x7F7F7F7Fu;
+#else
+  return ((w ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+#endif
 }
+// bit 7 of every byte of word k -> bit position 8*b + k
+#define K1_GATHER(f, va, vb)                                                                                   \
+  ((((f(va.x)) >> 7) & 0x01010101u) | (((f(va.y)) >> 6) & 0x02020202u) | (((f(va.z)) >> 5) & 0x04040404u) |    \
+   (((f(va.w)) >> 4) & 0x08080808u) | (((f(vb.x)) >> 3) & 0x10101010u) | (((f(vb.y)) >> 2) & 0x20202020u) |    \
+   (((f(vb.z)) >> 1) & 0x40404040u) | ((f(vb.w)) & 0x80808080u))
+#define K1_IDENT(w) (w)
 // Line-start mask of one lane and row: the lane's 16 bytes of the row's first half (words k = 0..3) and of
-// its second half (words k = 4..7).  Bit t = 8*b + k is set iff byte b of word k is '\n'.
+// its second half (words k = 4..7).  Bit t = 8*b + k is set iff byte b of word k is '\n'.  Exact.
 __device__ __forceinline__ uint32_t k1_row_mask(const uint4& va, const uint4& vb) {
-  const uint32_t m = ((k1_not_nl(va.x) >> 7) & 0x01010101u) | ((k1_not_nl(va.y) >> 6) & 0x02020202u) |
-                     ((k1_not_nl(va.z) >> 5) & 0x04040404u) | ((k1_not_nl(va.w) >> 4) & 0x08080808u) |
-                     ((k1_not_nl(vb.x) >> 3) & 0x10101010u) | ((k1_not_nl(vb.y) >> 2) & 0x20202020u) |
-                     ((k1_not_nl(vb.z) >> 1) & 0x40404040u) | (k1_not_nl(vb.w) & 0x80808080u);
+  uint32_t m = K1_GATHER(k1_lo7, va, vb);  // bit set: NOT a newline (low seven bits differ)
+  const uint32_t hi = (va.x | va.y | va.z | va.w | vb.x | vb.y | vb.z | vb.w) & 0x80808080u;
+  if (hi) m |= K1_GATHER(K1_IDENT, va, vb);  // a byte >= 0x80 is not a newline whatever its low bits are
   return ~m;
 }
 // offset (inside the lane's row: + r * 1024 + lane * 16) of the byte behind mask bit t
@@ -213,6 +226,9 @@ __device__ __noinline__ void k1_record_lines(const uint8_t* sm, uint32_t* dev_of
 #ifndef KVG_K1_MINCTAS
 #define KVG_K1_MINCTAS 1
 #endif
+#ifndef KVG_K1_CELLS
+#define KVG_K1_CELLS 1
+#endif
 __global__ void __launch_bounds__(K1_WARPS * 32, KVG_K1_MINCTAS) k_pciids_scan(K1Args A) {
   pdl_enter();
 #ifndef KVG_HOST_EMU
@@ -308,10 +324,30 @@ __global__ void __launch_bounds__(K1_WARPS * 32, KVG_K1_MINCTAS) k_pciids_scan(K
         atomicMin(&A.info[f].v_off, a + p);
       }
     };
+#if KVG_K1_CELLS
+    // A lane's row is two 16-byte cells and a 16-byte cell rarely holds more than one line start (the shortest
+    // lines of the file are about that long).  The FIRST line start of each of the 8 cells is handled without a
+    // loop — eight independent chains (find bit -> offset -> first byte), all in flight together; what is left
+    // (a cell with two or more newlines) goes through the loop below.
+#pragma unroll
+    for (uint32_t r = 0; r < K1_ROWS; r++) {
+      uint32_t rest = 0;
+#pragma unroll
+      for (uint32_t h = 0; h < 2; h++) {
+        const uint32_t m = ls[r] & (h ? 0xF0F0F0F0u : 0x0F0F0F0Fu);  // mask bit 8b + k: k < 4 is the first cell
+        const uint32_t t = (uint32_t)__ffs((int)(m | 0x80000000u)) - 1;  // m == 0: any valid index
+        const uint32_t po = r * 1024 + s_off[t];
+        const uint32_t b0 = cell[po];
+        if (m != 0 && b0 != '\t' && b0 != '#') header_at(po);
+        rest |= m & (m - 1);
+      }
+      ls[r] = rest;
+    }
+#endif
 #pragma unroll
     for (uint32_t r = 0; r < K1_ROWS; r++) {
       // two line starts per round: their first bytes are fetched together (the loop is a chain of dependent
-      // shared-memory loads; a lane rarely owns more than two line starts of a row)
+      // shared-memory loads)
       for (uint32_t mm = ls[r]; mm;) {
         const uint32_t t0 = (uint32_t)__ffs(mm) - 1;
         mm &= mm - 1;

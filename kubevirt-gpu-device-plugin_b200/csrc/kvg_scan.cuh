@@ -198,19 +198,26 @@ struct PciClassifyOp {
   // device_plugin.go:203-238: any of vendor/driver/iommu/device read errors drops the entry,
   // vendor must be "10de" (:209), driver in supportedVfioDrivers (:217, :75-78)
   __device__ __forceinline__ bool pred(const Item& r, uint32_t) const { return pci_record_alive(r); }
-  __device__ __forceinline__ void emit(uint32_t pos, const Item& r, uint32_t, uint32_t name_slot) {
+  static constexpr int UNITS = 1;  // 16-byte units per survivor
+  // the survivor record (kvgpu.h kvg_pci_surv)
+  __device__ __forceinline__ void make(const Item& r, uint32_t, uint32_t name_slot, uint4* s) const {
     uint32_t device = r.y >> 16;
     uint32_t flags = (r.w >> 8) & 0xffu;
     int32_t numa = (int32_t)r.w >> 16;  // sign-extended int16
     if ((flags & KVG_PF_NUMA_ERR) || numa < 0) numa = 0;  // :227-230, :316-318
-    uint4 s;
-    s.x = r.x;
-    s.y = r.z;
-    s.z = device | ((uint32_t)numa << 16);
-    s.w = name_slot;
-    st_stream(reinterpret_cast<uint4*>(out) + pos, s);
+    s[0].x = r.x;
+    s[0].y = r.z;
+    s[0].z = device | ((uint32_t)numa << 16);
+    s[0].w = name_slot;
+  }
+  // keys of the two group-by maps: {device id (deviceMap), iommu group (iommuMap)}
+  __device__ __forceinline__ uint2 keys(const Item& r, uint32_t) const { return make_uint2(r.y >> 16, r.z); }
+  __device__ __forceinline__ void emit(uint32_t pos, const Item& r, uint32_t i, uint32_t name_slot) {
+    uint4 s[1];
+    make(r, i, name_slot, s);
+    st_stream(reinterpret_cast<uint4*>(out) + pos, s[0]);
     local_max_group = max(local_max_group, r.z);
-    local_max_dev = max(local_max_dev, device);
+    local_max_dev = max(local_max_dev, r.y >> 16);
   }
   __device__ __forceinline__ void tile_epilogue() {
     uint32_t g = warp_max(local_max_group), d = warp_max(local_max_dev);
@@ -263,17 +270,25 @@ struct MdevClassifyOp {
     uint32_t type_idx = r.hi.y & 0xffffu;
     return (flags & (KVG_MF_TYPE_ERR | KVG_MF_PARENT_ERR)) == 0 && type_idx < n_types;
   }
-  __device__ __forceinline__ void emit(uint32_t pos, const Item& r, uint32_t i, uint32_t canon) {
+  static constexpr int UNITS = 2;  // 16-byte units per survivor
+  // the survivor record (kvgpu.h kvg_mdev_surv)
+  __device__ __forceinline__ void make(const Item& r, uint32_t i, uint32_t canon, uint4* s) const {
     uint32_t flags = (r.hi.y >> 16) & 0xffu;
     int32_t numa = (int32_t)(int16_t)(r.hi.z & 0xffffu);
     if ((flags & KVG_MF_NUMA_ERR) || numa < 0) numa = 0;  // :281-284, :316-318
-    uint4 hi;
-    hi.x = r.hi.x;
-    hi.y = canon | ((uint32_t)numa << 16);
-    hi.z = i;
-    hi.w = 0;
-    st_stream(out + 2 * (size_t)pos, r.lo);
-    st_stream(out + 2 * (size_t)pos + 1, hi);
+    s[0] = r.lo;
+    s[1].x = r.hi.x;
+    s[1].y = canon | ((uint32_t)numa << 16);
+    s[1].z = i;
+    s[1].w = 0;
+  }
+  // keys of the two group-by maps: {canonical type (vGpuMap), parent GPU (gpuVgpuMap)}
+  __device__ __forceinline__ uint2 keys(const Item& r, uint32_t canon) const { return make_uint2(canon, r.hi.x); }
+  __device__ __forceinline__ void emit(uint32_t pos, const Item& r, uint32_t i, uint32_t canon) {
+    uint4 s[2];
+    make(r, i, canon, s);
+    st_stream(out + 2 * (size_t)pos, s[0]);
+    st_stream(out + 2 * (size_t)pos + 1, s[1]);
     local_max_parent = max(local_max_parent, r.hi.x);
     local_max_type = max(local_max_type, canon);
   }
@@ -335,50 +350,94 @@ struct HealthOp {
 // the host-visible result block, and the two counters follow.  No staging copy, no look-back, no second
 // device-to-host copy.
 constexpr uint32_t HEALTH_SMALL_THREADS = 1024;
-constexpr uint32_t HEALTH_SMALL_ROWS = 32;
+constexpr uint32_t HEALTH_SMALL_ROWS = 32;                                        // rows of 1024 records
 constexpr uint32_t HEALTH_SMALL_MAX = HEALTH_SMALL_THREADS * HEALTH_SMALL_ROWS;  // 32,768 records
+constexpr uint32_t HEALTH_STAGE_ROWS = 12;                                        // rows staged per round
+constexpr uint32_t HEALTH_SMALL_SMEM = HEALTH_STAGE_ROWS * HEALTH_SMALL_THREADS * 16;  // 192 KiB
 __global__ void __launch_bounds__(HEALTH_SMALL_THREADS) k_health_small(const uint4* __restrict__ recs, uint32_t n,
                                                                        uint8_t* __restrict__ alive_prev,
                                                                        uint32_t* __restrict__ changed_host,
                                                                        uint32_t* __restrict__ hdr_host, uint32_t seq) {
   pdl_enter();
   constexpr uint32_t NW = HEALTH_SMALL_THREADS / 32;
-  __shared__ uint32_t s_chg[NW], s_alv[NW];
+#ifndef KVG_HOST_EMU
+  extern __shared__ __align__(128) uint8_t hs_smem[];
+#else
+  static __attribute__((aligned(128))) uint8_t hs_smem[HEALTH_SMALL_SMEM];
+#endif
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_bal[HEALTH_SMALL_ROWS][NW];  // "changed" ballot of (row, warp) -> its position in the list
+  __shared__ uint32_t s_now[HEALTH_SMALL_ROWS][NW];  // "alive now" ballot of (row, warp)
+  __shared__ uint32_t s_scan[NW], s_alv[NW];
+  const uint4* stage = reinterpret_cast<const uint4*>(hs_smem);
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // every thread owns a CONTIGUOUS run of records, so thread order is record order and ONE block scan of the
-  // per-thread transition counts places every transition
-  const uint32_t per = (n + HEALTH_SMALL_THREADS - 1) / HEALTH_SMALL_THREADS;  // <= HEALTH_SMALL_ROWS
-  const uint32_t i0 = tid * per, i1 = min(n, i0 + per);
-  unsigned long long st = 0;  // 2 bits per record of my run: now alive | changed << 1
-  uint32_t n_alive = 0, n_chg = 0;
-#pragma unroll 4
-  for (uint32_t i = i0; i < i1; i++) {
-    const uint4 r = recs[i];
-    const uint32_t now = pci_record_alive(r) ? 1u : 0u;
-    const uint32_t was = alive_prev[i];
-    const uint32_t chg = now != was ? 1u : 0u;
-    if (chg) alive_prev[i] = (uint8_t)now;
-    st |= (unsigned long long)(now | (chg << 1)) << (2 * (i - i0));
-    n_alive += now;
-    n_chg += chg;
+  const uint32_t rows = (n + HEALTH_SMALL_THREADS - 1) / HEALTH_SMALL_THREADS;
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
   }
-  const uint32_t incl = warp_incl_sum(n_chg);
+  __syncthreads();
+  uint32_t n_alive = 0, phase = 0;
+  for (uint32_t r0 = 0; r0 < rows; r0 += HEALTH_STAGE_ROWS) {
+    // the whole round (<= 192 KiB of the snapshot) is requested at once by the TMA unit: over PCIe what counts
+    // is bytes in flight, and a bulk copy keeps them in flight without a register per load
+    const uint32_t first = r0 * HEALTH_SMALL_THREADS;
+    const uint32_t cnt = min(n - first, HEALTH_STAGE_ROWS * HEALTH_SMALL_THREADS);
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&s_bar, cnt * 16);
+      for (uint32_t off = 0; off < cnt * 16; off += 16384)
+        tma_load_1d(hs_smem + off, reinterpret_cast<const uint8_t*>(recs + first) + off, min(16384u, cnt * 16 - off), &s_bar);
+    }
+    uint32_t was[HEALTH_STAGE_ROWS];
+#pragma unroll
+    for (uint32_t k = 0; k < HEALTH_STAGE_ROWS; k++) {  // the previous state (device memory) meanwhile
+      const uint32_t i = first + k * HEALTH_SMALL_THREADS + tid;
+      was[k] = i < n ? alive_prev[i] : 0;
+    }
+    mbar_wait(&s_bar, phase);
+    phase ^= 1;
+#pragma unroll
+    for (uint32_t k = 0; k < HEALTH_STAGE_ROWS; k++) {
+      if (r0 + k < rows) {  // uniform
+        const uint32_t i = first + k * HEALTH_SMALL_THREADS + tid;
+        const bool in = i < n;
+        const bool now = in && pci_record_alive(stage[k * HEALTH_SMALL_THREADS + tid]);
+        const bool chg = in && (now ? 1u : 0u) != was[k];
+        if (chg) alive_prev[i] = now ? 1 : 0;
+        const uint32_t bc = __ballot_sync(KVG_FULL, chg), bn = __ballot_sync(KVG_FULL, now);
+        if (lane == 0) {
+          s_bal[r0 + k][warp] = bc;
+          s_now[r0 + k][warp] = bn;
+        }
+        n_alive += now ? 1u : 0u;
+      }
+    }
+    __syncthreads();  // every read of the stage is done before the next round's copy lands in it
+  }
+  // 32 rows x 32 warps = one counter per thread, in record order: ONE block scan places every transition
+  const uint32_t crow = tid >> 5, cw = tid & 31;
+  const uint32_t mybal = crow < rows ? s_bal[crow][cw] : 0;
+  const uint32_t mycnt = __popc(mybal);
+  const uint32_t incl = warp_incl_sum(mycnt);
   const uint32_t wal = warp_sum(n_alive);
-  if (lane == 31) s_chg[warp] = incl;
+  if (lane == 31) s_scan[warp] = incl;
   if (lane == 0) s_alv[warp] = wal;
   __syncthreads();
   uint32_t base = 0, total = 0, alive = 0;
 #pragma unroll
   for (uint32_t w = 0; w < NW; w++) {
-    const uint32_t c = s_chg[w];
+    const uint32_t c = s_scan[w];
     if (w < warp) base += c;
     total += c;
     alive += s_alv[w];
   }
-  uint32_t pos = base + incl - n_chg;
-  for (uint32_t i = i0; i < i1; i++) {
-    const uint32_t bits = (uint32_t)(st >> (2 * (i - i0))) & 3u;
-    if (bits & 2u) changed_host[pos++] = (i << 1) | (bits & 1u);
+  // thread (crow, cw) writes the transitions of warp cw in row crow: lane order == record order
+  uint32_t pos = base + incl - mycnt;
+  const uint32_t nowb = crow < rows ? s_now[crow][cw] : 0;
+  for (uint32_t m = mybal; m; m &= m - 1) {
+    const uint32_t l = (uint32_t)__ffs((int)m) - 1;
+    const uint32_t i = crow * HEALTH_SMALL_THREADS + cw * 32 + l;
+    changed_host[pos++] = (i << 1) | ((nowb >> l) & 1u);
   }
   __threadfence_system();  // the list entries of every thread are on their way before the flag
   __syncthreads();

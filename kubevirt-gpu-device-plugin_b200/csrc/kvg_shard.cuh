@@ -91,6 +91,9 @@ struct ShardArgs {
   uint64_t region_cap;     // records per region
   uint32_t parity;
   unsigned long long step;
+#ifdef KVG_EXP
+  uint32_t exp;            // timing experiments only (never in the shipped build)
+#endif
 };
 
 // window addressing (16-byte units): region (parity, ordering, source) of a window
@@ -113,6 +116,8 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_shard_send(ShardArgs A, ShardPeer
   __shared__ uint32_t s_base[2][SH_MAX_RANKS];             // the tile's position in every (ordering, owner) region
   __shared__ uint32_t s_last;
   const uint32_t lane = lane_id(), warp = warp_id();
+  const uint32_t active = max(Tu, 1u);  // CTAs that take part (tile 0 also stands for the empty list)
+  if (tile >= active) return;
   // the window parity is rewritten: every owner must have consumed the step that used it two steps ago
   if (threadIdx.x < A.P && A.step > 2 && A.only == SH_ALL) {
     const long long t0 = clock64();
@@ -180,7 +185,12 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_shard_send(ShardArgs A, ShardPeer
         const uint32_t q = o ? q1[k] : q0[k];
         if (q != SH_ALL && (A.only == SH_ALL || q == A.only)) {
           const uint32_t at = s_base[o][q] + s_wcnt[warp][o][q] + pos[k][o];
+#ifdef KVG_EXP
+          uint4* dst = peers.win[(A.exp & 1u) ? A.me : q] + shard_region(A, o, A.src, U) + (size_t)at * U;
+          if (!(A.exp & 4u))
+#else
           uint4* dst = peers.win[q] + shard_region(A, o, A.src, U) + (size_t)at * U;
+#endif
 #pragma unroll
           for (int u = 0; u < U; u++) dst[u] = rec[k][u];  // NVLink store (or local)
         }
@@ -189,10 +199,17 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_shard_send(ShardArgs A, ShardPeer
   } else if (n == 0 && tile == 0 && threadIdx.x < 2 * A.P) {
     A.totals[threadIdx.x] = 0;
   }
-  // the last CTA to finish publishes the region counts and the release flag to every owner
-  __threadfence_system();
+  // the last CTA to finish publishes the region counts and the release flag to every owner.  ONE fence per CTA:
+  // the block barrier orders every thread's stores before thread 0's fence, and fences are cumulative (256
+  // system-scope fences per CTA, and one in every idle CTA, were a third of this kernel's time)
   __syncthreads();
-  if (threadIdx.x == 0) s_last = atomicAdd(&A.ticket[0], 1u) == gridDim.x - 1 ? 1u : 0u;
+  if (threadIdx.x == 0) {
+#ifdef KVG_EXP
+    if (!(A.exp & 2u))
+#endif
+    __threadfence_system();
+    s_last = atomicAdd(&A.ticket[0], 1u) == active - 1 ? 1u : 0u;
+  }
   __syncthreads();
   if (!s_last) return;
   __threadfence_system();
@@ -207,6 +224,216 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_shard_send(ShardArgs A, ShardPeer
     }
   }
   if (threadIdx.x == 0) A.ticket[0] = 0;
+}
+
+// ---- classify + send in ONE kernel (latency-bound shard sizes) ------------------------------------------------
+// The classify kernel already holds every survivor in registers together with its position in the rank's dense
+// list; it now also knows its position in the owner's window and stores it there itself.  Per 1024-record tile
+// the CTA counts 1 + 2P things — survivors, and survivors per (ordering, owner) — and needs their totals over
+// all earlier tiles.  With ~1000 tiles that all start together a chained scan is a chain of dependent L2 round
+// trips per counter; instead every tile publishes its COUNTS only (one 32-bit word each: epoch << 11 | count,
+// count <= 1024) and sums the words of ALL earlier tiles itself, a thread per earlier tile, every load
+// independent: O(T^2 (1 + 2P)) loads from L2 in total — nothing at T ~ 1000 — and no chain.  (The standalone
+// k_shard_send keeps the chained scan: it serves the sizes where T^2 is not nothing.)
+// CW4 = uint4 loads per tile row: 4 * CW4 >= 1 + 2P.
+constexpr uint32_t CS_COUNT_BITS = 11;
+template <class Op, int THREADS, int ROWS, int CW4>
+__global__ void __launch_bounds__(THREADS) k_classify_send(Op op, ShardArgs A, ShardPeers peers, const ShardCtrl* mine,
+                                                           uint32_t* err, uint32_t* tile_words, uint32_t epoch) {
+  pdl_enter();
+  constexpr int U = Op::UNITS;
+  constexpr uint32_t TILE = THREADS * ROWS;
+  constexpr uint32_t NW = THREADS / 32;
+  constexpr uint32_t WARP_ITEMS = 32 * ROWS;
+  constexpr uint32_t CW = 4 * CW4;
+  static_assert(TILE < (1u << CS_COUNT_BITS), "a tile count fits the count field");
+  static_assert(ROWS <= 8 && WARP_ITEMS <= 256, "warp-local positions are packed in bytes");
+  __shared__ uint32_t s_wcnt[NW][2][SH_MAX_RANKS];  // per warp: survivors of every (ordering, owner) -> prefix over the warps
+  __shared__ uint32_t s_wtot[NW], s_woff[NW];
+  __shared__ uint32_t s_agg[CW], s_excl[CW];
+  __shared__ uint32_t s_part[NW][CW];
+  __shared__ uint32_t s_last;
+  op.begin();
+  const uint32_t n = op.count();
+  const uint32_t n_tiles = (n + TILE - 1) / TILE;
+  const uint32_t active = max(n_tiles, 1u);  // tile 0 also stands for the empty shard
+  const uint32_t tile = blockIdx.x;
+  if (tile >= active) return;
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, tid = threadIdx.x;
+  const uint32_t C = 1 + 2 * A.P;  // counters in use: [0] survivors, [1 + o*P + q] survivors of ordering o owned by q
+  const uint32_t ep = epoch << CS_COUNT_BITS;
+  // the window parity is rewritten: every owner must have consumed the step that used it two steps ago
+  if (tid < A.P && A.step > 2) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(&mine->ack[tid]) < A.step - 2) {
+      if (clock64() - t0 > SH_SPIN_LIMIT) {
+        atomicExch(err, 1u);
+        break;
+      }
+    }
+  }
+  if (n_tiles == 0) {
+    if (tid == 0) op.finish(0);
+    if (tid < 2 * A.P) A.totals[tid] = 0;
+  } else {
+    const uint32_t base = tile * TILE + warp * WARP_ITEMS;
+    typename Op::Item item[ROWS];
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) {
+      const uint32_t i = base + k * 32 + lane;
+      item[k] = op.load(i, i < n);
+    }
+    uint32_t bal[ROWS], aux[ROWS];
+    uint32_t wtot = 0;
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) {
+      const uint32_t i = base + k * 32 + lane;
+      const bool p = i < n && op.pred(item[k], i);
+      bal[k] = __ballot_sync(KVG_FULL, p);
+      wtot += __popc(bal[k]);
+      aux[k] = p ? op.prepare(item[k]) : 0u;
+    }
+    static_assert(2 * SH_MAX_RANKS == 32, "one lane per counter");
+    (&s_wcnt[warp][0][0])[lane] = 0;
+    __syncwarp();
+    // stable position of every survivor among those of my warp that go to the same (ordering, owner): a byte each
+    uint32_t pos0[2] = {0, 0}, pos1[2] = {0, 0};
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) {
+      const bool p = (bal[k] >> lane) & 1u;
+      const uint2 key = op.keys(item[k], aux[k]);
+#pragma unroll
+      for (uint32_t o = 0; o < 2; o++) {
+        const uint32_t q = p ? (o ? key.y : key.x) % A.P : SH_ALL;
+        const uint32_t same = __match_any_sync(KVG_FULL, q);
+        const uint32_t before = __popc(same & lanemask_lt());
+        const uint32_t prior = p ? s_wcnt[warp][o][q] : 0;
+        const uint32_t at = prior + before;  // < 256
+        if (o == 0)
+          pos0[k >> 2] |= at << (8 * (k & 3));
+        else
+          pos1[k >> 2] |= at << (8 * (k & 3));
+        __syncwarp();
+        if (p && before == 0) s_wcnt[warp][o][q] = prior + __popc(same);  // one lane per owner advances
+        __syncwarp();
+      }
+    }
+    if (lane == 0) s_wtot[warp] = wtot;
+    __syncthreads();
+    // counts of the tile -> published words; the warps' counts become prefixes over the warps in place
+    if (warp == 0) {
+      for (uint32_t c = lane; c < CW; c += 32) {
+        uint32_t agg = 0;
+        if (c == 0) {
+#pragma unroll
+          for (uint32_t w = 0; w < NW; w++) {
+            s_woff[w] = agg;
+            agg += s_wtot[w];
+          }
+        } else if (c < C) {
+          const uint32_t o = (c - 1) / A.P, q = (c - 1) - o * A.P;
+#pragma unroll
+          for (uint32_t w = 0; w < NW; w++) {
+            const uint32_t v = s_wcnt[w][o][q];
+            s_wcnt[w][o][q] = agg;
+            agg += v;
+          }
+        }
+        s_agg[c] = agg;
+        st_relaxed_u32(&tile_words[(size_t)tile * CW + c], ep | agg);
+      }
+    }
+    // totals of all earlier tiles: a thread per earlier tile, CW4 independent 16-byte loads each
+    uint32_t acc[CW];
+#pragma unroll
+    for (uint32_t c = 0; c < CW; c++) acc[c] = 0;
+    const uint32_t cmask = (1u << CS_COUNT_BITS) - 1;
+    for (uint32_t j = tid; j < tile; j += THREADS) {
+      const uint4* row = reinterpret_cast<const uint4*>(tile_words + (size_t)j * CW);
+      uint4 x[CW4];
+      bool ok;
+      long long t0 = 0;
+      do {
+        ok = true;
+#pragma unroll
+        for (uint32_t v = 0; v < CW4; v++) {
+          x[v] = ld_volatile_v4(row + v);
+          ok = ok && ((x[v].x & ~cmask) == ep) && ((x[v].y & ~cmask) == ep) && ((x[v].z & ~cmask) == ep) &&
+               ((x[v].w & ~cmask) == ep);
+        }
+        if (!ok) {  // tile j has not published yet
+          if (t0 == 0) t0 = clock64();
+          if (clock64() - t0 > SH_SPIN_LIMIT) {
+            atomicExch(err, 1u);
+            break;
+          }
+        }
+      } while (!ok);
+#pragma unroll
+      for (uint32_t v = 0; v < CW4; v++) {
+        acc[4 * v + 0] += x[v].x & cmask;
+        acc[4 * v + 1] += x[v].y & cmask;
+        acc[4 * v + 2] += x[v].z & cmask;
+        acc[4 * v + 3] += x[v].w & cmask;
+      }
+    }
+#pragma unroll
+    for (uint32_t c = 0; c < CW; c++) {
+      const uint32_t v = warp_sum(acc[c]);
+      if (lane == 0) s_part[warp][c] = v;
+    }
+    __syncthreads();
+    if (tid < CW) {
+      uint32_t e = 0;
+#pragma unroll
+      for (uint32_t w = 0; w < NW; w++) e += s_part[w][tid];
+      s_excl[tid] = e;
+      if (tile == n_tiles - 1) {
+        if (tid == 0) op.finish(e + s_agg[0]);
+        else if (tid < C) A.totals[tid - 1] = e + s_agg[tid];
+      }
+    }
+    __syncthreads();
+    // survivors: to the rank's dense list (Walk order) and, once per ordering, to the owner's window
+    uint32_t off = s_excl[0] + s_woff[warp];
+#pragma unroll
+    for (int k = 0; k < ROWS; k++) {
+      const uint32_t i = base + k * 32 + lane;
+      if ((bal[k] >> lane) & 1u) {
+        op.emit(off + __popc(bal[k] & lanemask_lt()), item[k], i, aux[k]);
+        uint4 rec[U];
+        op.make(item[k], i, aux[k], rec);
+        const uint2 key = op.keys(item[k], aux[k]);
+#pragma unroll
+        for (uint32_t o = 0; o < 2; o++) {
+          const uint32_t q = (o ? key.y : key.x) % A.P;
+          const uint32_t at = s_excl[1 + o * A.P + q] + s_wcnt[warp][o][q] + (((o ? pos1 : pos0)[k >> 2] >> (8 * (k & 3))) & 0xffu);
+          uint4* dst = peers.win[q] + shard_region(A, o, A.src, U) + (size_t)at * U;
+#pragma unroll
+          for (int u = 0; u < U; u++) dst[u] = rec[u];  // NVLink store (or local)
+        }
+      }
+      off += __popc(bal[k]);
+    }
+    op.tile_epilogue();
+  }
+  // the last CTA to finish publishes the region counts and the release flag to every owner (one fence per CTA)
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();
+    s_last = atomicAdd(&A.ticket[0], 1u) == active - 1 ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence_system();
+  if (tid < A.P) {
+    ShardCtrl* c = peers.ctrl[tid];
+    c->count[A.parity][0][A.src] = *((volatile uint32_t*)&A.totals[tid]);
+    c->count[A.parity][1][A.src] = *((volatile uint32_t*)&A.totals[A.P + tid]);
+    __threadfence_system();
+    st_release_sys(&c->flag[A.parity][A.src], A.step);
+  }
+  if (tid == 0) A.ticket[0] = 0;
 }
 
 struct GatherArgs {
@@ -267,9 +494,11 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_shard_gather(ShardArgs A, GatherA
   mx = warp_max(mx);
   if (lane_id() == 0 && mx) atomicMax(&G.max_key[o], mx);
   // the last CTA acknowledges the window parity to every source
-  __threadfence();
   __syncthreads();
-  if (tid == 0) s_last = atomicAdd(&A.ticket[1], 1u) == gridDim.x * gridDim.y - 1 ? 1u : 0u;
+  if (tid == 0) {
+    __threadfence();
+    s_last = atomicAdd(&A.ticket[1], 1u) == gridDim.x * gridDim.y - 1 ? 1u : 0u;
+  }
   __syncthreads();
   if (!s_last) return;
   if (tid < A.P && A.only == SH_ALL) st_release_sys(&peers.ctrl[tid]->ack[A.me], A.step);

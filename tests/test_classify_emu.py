@@ -94,7 +94,7 @@ def test_health_small_kernel_one_cta(emu):
     ids = O.nv_ids(util.pciids_text())
     drop = 1 | 2 | 4 | 8
     rng = np.random.default_rng(6)
-    for n in (1, 1023, 1024, 1025, 10_000, 32_768):
+    for n in (1, 1023, 1024, 1025, 10_000, 12_288, 12_289, 32_768):
         recs = O.gen_pci(0, n, ids, 0)
         alive_prev = np.zeros(n + 1, dtype=np.uint8)
         prev = np.zeros(n, dtype=bool)

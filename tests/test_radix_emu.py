@@ -88,12 +88,18 @@ def test_whole_ordering_permutation_segments_and_bucket_names(emu):
         pairs["key"][:n], pairs["idx"][:n] = keys, np.arange(n, dtype=np.uint32)
         perm = np.zeros(n + 1, np.uint32)
         seg_key, seg_off, seg_name = np.zeros(n + 2, np.uint32), np.zeros(n + 2, np.uint32), np.zeros(n + 2, np.uint32)
-        n_seg = emu.emu_ordering(pairs.ctypes.data, n, surv.ctypes.data, kmax, 11, perm.ctypes.data, seg_key.ctypes.data,
-                                 seg_off.ctypes.data, seg_name.ctypes.data, n % 2)
         order = np.argsort(keys, kind="stable")
         uniq, first = np.unique(keys[order], return_index=True)
-        assert n_seg == len(uniq), n_seg
-        assert np.array_equal(perm[:n], order.astype(np.uint32))
-        assert np.array_equal(seg_key[:n_seg], uniq) and np.array_equal(seg_off[:n_seg], first.astype(np.uint32))
-        assert int(seg_off[n_seg]) == n
-        assert np.array_equal(seg_name[:n_seg], (uniq * 7 + 1) & 0xffff)
+        # forms of the step: 0 = count / offsets / emit, 1 = one chained-scan launch, 2 = k_order_all (all radix
+        # passes AND the final step in one persistent launch)
+        for form in (n % 2, 2):
+            p2 = pairs.copy()
+            perm[:] = 0xdeadbeef
+            seg_key[:] = seg_off[:] = seg_name[:] = 0xdeadbeef
+            n_seg = emu.emu_ordering(p2.ctypes.data, n, surv.ctypes.data, kmax, 11, perm.ctypes.data, seg_key.ctypes.data,
+                                     seg_off.ctypes.data, seg_name.ctypes.data, form)
+            assert n_seg == len(uniq), (n_seg, form)
+            assert np.array_equal(perm[:n], order.astype(np.uint32))
+            assert np.array_equal(seg_key[:n_seg], uniq) and np.array_equal(seg_off[:n_seg], first.astype(np.uint32))
+            assert int(seg_off[n_seg]) == n
+            assert np.array_equal(seg_name[:n_seg], (uniq * 7 + 1) & 0xffff)

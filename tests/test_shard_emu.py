@@ -73,3 +73,62 @@ def test_exchange_by_owner(emu, units, P, local_mode):
             assert cnt == len(want), (r, o, cnt, len(want))
             assert np.array_equal(got[r, :cnt], want), (r, o)
             assert int(mx[2 * r + o]) == (int(keys[keys % P == r].max()) if len(want) else 0)
+
+
+@pytest.mark.parametrize("P", [1, 2, 5, 8, 16])
+def test_classify_and_send_in_one_kernel(emu, P):
+    """k_classify_send: raw PCI records in; every rank's dense survivor list (Walk order) and both owned lists
+    out — the owned lists must equal those of the separate classify + exchange path (the oracle's drop rules
+    applied with numpy, then key % P)."""
+    from oracle import oracle as O
+    import util
+    emu.emu_classify_exchange.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    ids = O.nv_ids(util.pciids_text())
+    rng = np.random.default_rng(7 * P)
+    sizes = [int(x) for x in rng.integers(0, 5000, P)]
+    sizes[0] = 4097
+    if P > 2:
+        sizes[1] = 0
+    nv_index = np.full(65536, 0xffffffff, dtype=np.uint32)
+    nv_index[ids] = np.arange(len(ids), dtype=np.uint32) * 3 + 5
+    shards, first = [], 0
+    for r in range(P):
+        shards.append(np.ascontiguousarray(O.gen_pci(first, sizes[r], ids, 9)))
+        first += sizes[r]
+    cap = max(sizes) + 1
+    ptrs = (C.c_void_p * P)(*[a.ctypes.data if len(a) else None for a in shards])
+    n = np.array(sizes, dtype=np.uint32)
+    surv = np.zeros((P, cap, 4), dtype=np.uint32)
+    n_surv = np.zeros(P, dtype=np.uint32)
+    owned_cap = P * cap
+    o0 = np.zeros((P, owned_cap, 4), dtype=np.uint32)
+    o1 = np.zeros((P, owned_cap, 4), dtype=np.uint32)
+    n_own = np.zeros(2 * P, dtype=np.uint32)
+    mx = np.zeros(2 * P, dtype=np.uint32)
+    rc = emu.emu_classify_exchange(ptrs, n.ctypes.data, P, 3, cap, nv_index.ctypes.data, surv.ctypes.data, n_surv.ctypes.data,
+                                   o0.ctypes.data, o1.ctypes.data, n_own.ctypes.data, mx.ctypes.data)
+    assert rc == 0, rc
+    drop = 1 | 2 | 4 | 8
+    want_all = []
+    for r in range(P):
+        recs = shards[r]
+        alive = (recs["vendor"] == 0x10de) & ((recs["flags"] & drop) == 0) & ((recs["driver"] == 1) | (recs["driver"] == 2))
+        a = recs[alive]
+        numa = np.where(((a["flags"] & 16) != 0) | (a["numa"] < 0), 0, a["numa"]).astype(np.uint32)
+        w = np.zeros((len(a), 4), dtype=np.uint32)
+        w[:, 0] = a["addr"]
+        w[:, 1] = a["iommu_group"]
+        w[:, 2] = a["device"].astype(np.uint32) | (numa << 16)
+        w[:, 3] = nv_index[a["device"]]
+        assert int(n_surv[r]) == len(w), (r, int(n_surv[r]), len(w))
+        assert np.array_equal(surv[r, :len(w)], w), r
+        want_all.append(w)
+    allrecs = np.concatenate(want_all)
+    k0, k1 = keys_of(allrecs, 1)
+    for r in range(P):
+        for o, (keys, got) in enumerate(((k0, o0), (k1, o1))):
+            want = allrecs[keys % P == r]
+            cnt = int(n_own[2 * r + o])
+            assert cnt == len(want), (r, o, cnt, len(want))
+            assert np.array_equal(got[r, :cnt], want), (r, o)

@@ -9,6 +9,9 @@ namespace kvg {
 #include "emu_order.inc"
 }
 #include "../../kubevirt-gpu-device-plugin_b200/csrc/kvg_order.cuh"
+namespace kvg {
+#include "emu_classify.inc"
+}
 #include "../../kubevirt-gpu-device-plugin_b200/csrc/kvg_shard.cuh"
 using namespace kvg;
 
@@ -88,7 +91,90 @@ static int run(const uint4* const* lists, const uint32_t* n, uint32_t P, uint32_
   return err ? -5 : 0;
 }
 
+// k_classify_send: raw PCI records of P shards -> each rank's dense survivor list AND the owners' windows in one
+// kernel per rank, then the gathers.  CW4 follows the host's choice for P.
+template <int CW4>
+static int run_fused(const uint4* const* recs, const uint32_t* n, uint32_t P, uint32_t steps, uint32_t cap, const uint32_t* nv_index,
+                     uint4* surv_out, uint32_t* n_surv_out, uint4* owned0_out, uint4* owned1_out, uint32_t* n_own_out,
+                     uint32_t* max_out) {
+  constexpr int TH = 128, ROWS = 8, U = 1;
+  const size_t win_units = 2 * 2 * (size_t)P * cap * U;
+  std::vector<std::vector<uint4>> win(P, std::vector<uint4>(win_units, uint4{0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu, 0xdeadbeefu}));
+  std::vector<ShardCtrl> ctrl(P);
+  memset(ctrl.data(), 0, sizeof(ShardCtrl) * P);
+  ShardPeers peers;
+  memset(&peers, 0, sizeof peers);
+  for (uint32_t q = 0; q < P; q++) {
+    peers.win[q] = win[q].data();
+    peers.ctrl[q] = &ctrl[q];
+  }
+  uint32_t err = 0;
+  std::vector<std::vector<uint32_t>> words(P);  // published tile counts: epoch-tagged, reused uncleared
+  std::vector<std::vector<uint32_t>> cnt(P, std::vector<uint32_t>(64, 0));
+  std::vector<ScanCtrl> sc(P);
+  auto args = [&](uint32_t r, uint32_t step) {
+    ShardArgs A;
+    A.list = nullptr;
+    A.n_ptr = nullptr;
+    A.state = nullptr;
+    A.totals = cnt[r].data();
+    A.ticket = cnt[r].data() + 32;
+    A.T = 0;
+    A.P = P;
+    A.me = r;
+    A.only = SH_ALL;
+    A.n_src = P;
+    A.src = r;
+    A.region_cap = cap;
+    A.parity = step & 1;
+    A.step = step;
+    return A;
+  };
+  for (uint32_t step = 1; step <= steps; step++) {
+    for (uint32_t r = 0; r < P; r++) {
+      const size_t tiles = std::max<size_t>(1, (n[r] + (size_t)TH * ROWS - 1) / ((size_t)TH * ROWS));
+      if (words[r].empty()) words[r].assign(tiles * 4 * CW4, 0);
+      memset(&sc[r], 0, sizeof(ScanCtrl));
+      PciClassifyOp op;
+      op.recs = recs[r];
+      op.n = n[r];
+      op.out = (kvg_pci_surv*)(surv_out + (size_t)r * cap);
+      op.ctrl = &sc[r];
+      op.nv_index = nv_index;
+      op.local_max_group = 0;
+      op.local_max_dev = 0;
+      emu_launch(k_classify_send<PciClassifyOp, TH, ROWS, CW4>, dim3((unsigned)tiles), TH, op, args(r, step), peers,
+                 (const ShardCtrl*)&ctrl[r], &err, words[r].data(), 40u + step);
+      if (cnt[r][32] != 0) return -3;
+      n_surv_out[r] = sc[r].n_surv;
+    }
+    for (uint32_t r = 0; r < P; r++) {
+      const size_t owned_cap = (size_t)P * cap;
+      GatherArgs G;
+      G.window = win[r].data();
+      G.owned[0] = owned0_out + (size_t)r * owned_cap * U;
+      G.owned[1] = owned1_out + (size_t)r * owned_cap * U;
+      G.n_own = n_own_out + 2 * r;
+      max_out[2 * r] = max_out[2 * r + 1] = 0;
+      G.max_key = max_out + 2 * r;
+      emu_launch(k_shard_gather<U>, dim3(3, 2), KVG_BLOCK, args(r, step), G, peers, (const ShardCtrl*)&ctrl[r], &err);
+      if (cnt[r][33] != 0) return -4;
+    }
+  }
+  return err ? -5 : 0;
+}
+
 extern "C" {
+// recs: P pointers to raw PCI records (16 bytes each), n[P].  Outputs per rank r: surv_out + r * cap (dense
+// survivor list, n_surv_out[r] long), owned lists as in emu_exchange.
+int emu_classify_exchange(const uint4* const* recs, const uint32_t* n, uint32_t P, uint32_t steps, uint32_t cap,
+                          const uint32_t* nv_index, uint4* surv_out, uint32_t* n_surv_out, uint4* owned0_out, uint4* owned1_out,
+                          uint32_t* n_own_out, uint32_t* max_out) {
+  const int C = 1 + 2 * (int)P;
+#define KVG_RUN(W) run_fused<W>(recs, n, P, steps, cap, nv_index, surv_out, n_surv_out, owned0_out, owned1_out, n_own_out, max_out)
+  return C <= 8 ? KVG_RUN(2) : C <= 16 ? KVG_RUN(4) : C <= 20 ? KVG_RUN(5) : KVG_RUN(9);
+#undef KVG_RUN
+}
 // lists: P pointers to dense record lists (units x 16 bytes per record), n[P] their lengths.  Outputs per rank
 // r at owned{0,1}_out + r * P * cap * units: the owned lists; n_own_out[2r + o], max_out[2r + o].
 int emu_exchange(int units, const uint4* const* lists, const uint32_t* n, uint32_t P, uint32_t steps, uint32_t cap,

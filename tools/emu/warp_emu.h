@@ -8,6 +8,7 @@
 //
 // Test infrastructure only (tests/test_*_emu.py); never part of the product.
 #pragma once
+#include <cassert>
 #include <ucontext.h>
 
 #include <cstdint>
@@ -83,6 +84,12 @@ static inline uint4 ld_stream(const uint4* p) { return *p; }
 static inline void st_stream(uint4* p, const uint4& v) { *p = v; }
 static inline uint64_t ld_relaxed_u64(const uint64_t* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 static inline void st_relaxed_u64(uint64_t* p, uint64_t v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+static inline void st_relaxed_u32(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+static inline uint4 ld_volatile_v4(const uint4* p) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
+  return uint4{__atomic_load_n(w, __ATOMIC_RELAXED), __atomic_load_n(w + 1, __ATOMIC_RELAXED),
+               __atomic_load_n(w + 2, __ATOMIC_RELAXED), __atomic_load_n(w + 3, __ATOMIC_RELAXED)};
+}
 template <class T>
 static inline T __ldg(const T* p) { return *p; }
 static inline int __popc(uint32_t v) { return __builtin_popcount(v); }
@@ -152,12 +159,16 @@ static inline uint32_t lanemask_lt() { return (1u << lane_id()) - 1u; }
 // mbarrier + TMA 1-D bulk copy (kvg_common.cuh) as used by the 4-stage text ring of k_pciids_parse: the
 // copy completes at issue time, the barrier word counts completed phases, a wait on parity p returns once
 // phase p has completed — the same observable protocol, minus the asynchrony
+// (barrier word here: low half = completed phases, high half = bytes still expected by the current phase;
+// one arriving thread per phase, which is how every kernel of this library uses its barriers)
 static inline void mbar_init(uint64_t* bar, uint32_t) { *bar = 0; }
 static inline void mbar_fence_init() {}
-static inline void mbar_arrive_expect_tx(uint64_t*, uint32_t) {}
+static inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) { *bar += (uint64_t)bytes << 32; }
 static inline void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
   memcpy(smem_dst, gmem_src, bytes);
-  (*bar)++;
+  assert((*bar >> 32) >= bytes && "bulk copy without a matching expect_tx");
+  *bar -= (uint64_t)bytes << 32;
+  if ((*bar >> 32) == 0) (*bar)++;  // the phase's last byte has landed
   emu_block->progressed = true;
 }
 static inline void mbar_wait(uint64_t* bar, uint32_t parity) {
