@@ -368,6 +368,7 @@ def main():
         "order_scatter": 16 * S_ord * (2 + grp_passes),        # 8 B read + 8 B written per pair per pass
         "order_final": (8 * S_ord + 4 * S_ord) * 2 + 8 * (KD + G),
         "shard_send": 16 * S * 3,                              # survivors read, one record stored per ordering
+        "classify_send": 16 * n + 16 * S * 3,                  # records read; survivor stored locally + once per ordering
         "shard_gather": 2 * 32 * S_ord,                        # window regions -> dense owned lists
     }
     main_kernels = [k for k in algo if k in ksum]

@@ -188,8 +188,6 @@ struct kvg_ctx {
   DevBuf<uint32_t> tile_hist;     // K4: [2 orderings][<= 2048 digits][T tiles]
   DevBuf<uint32_t> bin_total;     // [2 orderings][2048] digit totals
   bool health_smem_set = false;
-  int order_all_ctas = 0;         // CTAs of k_order_all this device holds at once (its grid never exceeds it)
-  DevBuf<uint32_t> grid_bar;      // its grid barrier: arrivals, generation
   int final_ctas_per_sm = 0;      // occupancy of k_order_final on this device (bounds its grid)
   bool scatter_smem_set = false;  // dynamic shared-memory opt-in of k_order_scatter<11> done on this device
   size_t last_n = 0;     // records of the last enqueued scan
@@ -438,7 +436,7 @@ void kvg_ctx_destroy(kvg_ctx* ctx) {
   release(ctx->text); release(ctx->dev_off); release(ctx->info); release(ctx->span_sum); release(ctx->pool); release(ctx->ctrl);
   release(ctx->nv_index); release(ctx->sec_lines); release(ctx->type_hash); release(ctx->ragged); release(ctx->tile_count); release(ctx->tile_off);
   release(ctx->tile_max); release(ctx->offs_state);
-  release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist); release(ctx->bin_total); release(ctx->grid_bar);
+  release(ctx->recs); release(ctx->surv); release(ctx->classify_state); release(ctx->tile_hist); release(ctx->bin_total);
   for (OrderBufs* o : {&ctx->ord_dev, &ctx->ord_grp}) {
     release(o->p0); release(o->p1); release(o->perm); release(o->tile_heads); release(o->tile_off);
     release(o->seg_key); release(o->seg_off); release(o->seg_name); release(o->heads_state);
@@ -532,8 +530,13 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
   }
   const uint32_t n_spans = (uint32_t)n_spans64;
   const size_t pool_bytes = (len + 16 + 15) & ~(size_t)15;
-  ENSURE(ctx->dev_off, (size_t)K1_IDS * n_files);
-  ENSURE(ctx->info, n_files);
+  {
+    // the table is self-cleaning (k_pciids_names resets what it reads): only a fresh allocation is filled
+    const uint32_t* before = ctx->dev_off.p;
+    ENSURE(ctx->dev_off, (size_t)K1_IDS * n_files);
+    if (ctx->dev_off.p != before) CK(cudaMemsetAsync(ctx->dev_off.p, 0xff, ctx->dev_off.cap * sizeof(uint32_t), ctx->stream));
+  }
+  ENSURE(ctx->info, n_files);  // zero-filled when fresh: the accumulators in PciIdsInfo::pad start at "nothing seen"
   ENSURE(ctx->span_sum, n_spans);
   ENSURE(ctx->nv_index, K1_IDS);
   ENSURE(ctx->pool, pool_bytes);
@@ -552,19 +555,8 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
   A.dev_off = ctx->dev_off.p;
   A.info = ctx->info.p;
   A.span_sum = ctx->span_sum.p;
-  K1PrepArgs P;
-  P.dev_off = (uint4*)ctx->dev_off.p;
-  P.dev_off16 = (uint64_t)K1_IDS * n_files / 4;
-  P.info = ctx->info.p;
-  P.n_files = n_files;
-  P.nv_index = (uint4*)ctx->nv_index.p;
-  P.pool = (uint4*)ctx->pool.p;
-  P.pool16 = (uint32_t)(pool_bytes / 16);
-  {
-    size_t work = std::max<size_t>(P.dev_off16, std::max<size_t>(P.pool16, K1_IDS / 4));
-    unsigned grid = (unsigned)std::min<size_t>((work + KVG_BLOCK - 1) / KVG_BLOCK, (size_t)ctx->sm_count * 8);
-    LAUNCH("pciids_prep", k_pciids_prep, grid ? grid : 1, KVG_BLOCK, 0, P);
-  }
+  A.pool = (uint4*)ctx->pool.p;
+  A.pool16 = (uint32_t)(pool_bytes / 16);
   {
     unsigned grid = (n_spans + K1_WARPS - 1) / K1_WARPS;
     if (grid > (unsigned)ctx->k1_grid) grid = (unsigned)ctx->k1_grid;
@@ -572,7 +564,7 @@ static int parse_enqueue(kvg_ctx* ctx, const uint8_t* d_text, size_t len, size_t
   }
   LAUNCH("pciids_resolve", k_pciids_resolve_finalize, n_files + (n_spans + K1_RWARPS - 1) / K1_RWARPS, KVG_BLOCK,
          K1_RWARPS * K1_STAGE, A);
-  LAUNCH("pciids_names", k_pciids_names, K1_IDS / 32 / KVG_WARPS, KVG_BLOCK, 0, (const uint32_t*)ctx->dev_off.p, d_text,
+  LAUNCH("pciids_names", k_pciids_names, K1_IDS / 32 / KVG_WARPS, KVG_BLOCK, 0, ctx->dev_off.p, n_files, d_text,
          (uint32_t)len, ctx->info.p, ctx->nv_index.p, ctx->pool.p);
   ctx->sec_lines_ready = false;
   return check_launch(ctx, "pciids parse");
@@ -649,19 +641,11 @@ int kvg_pciids_load(kvg_ctx* ctx, const uint8_t* text, size_t len) {
   ctx->load_pending = false;
   if (len == 0) {  // an empty file: locateVendor fails, every lookup is "" (:382-385)
     ENSURE(ctx->info, 1);
-    ENSURE(ctx->dev_off, K1_IDS);
     ENSURE(ctx->nv_index, K1_IDS);
     ENSURE(ctx->pool, 16);
     ENSURE(ctx->text, 64);
-    K1PrepArgs P;
-    P.dev_off = (uint4*)ctx->dev_off.p;
-    P.dev_off16 = K1_IDS / 4;
-    P.info = ctx->info.p;
-    P.n_files = 1;
-    P.nv_index = (uint4*)ctx->nv_index.p;
-    P.pool = (uint4*)ctx->pool.p;
-    P.pool16 = 1;
-    LAUNCH("pciids_prep", k_pciids_prep, 64, KVG_BLOCK, 0, P);
+    CK(cudaMemsetAsync(ctx->nv_index.p, 0xff, K1_IDS * sizeof(uint32_t), ctx->stream));  // no id has a name
+    CK(cudaMemsetAsync(ctx->pool.p, 0, 16, ctx->stream));
     PciIdsInfo z;
     memset(&z, 0, sizeof z);
     z.v_off = z.sec_end = P_NONE;
@@ -928,48 +912,6 @@ static int enqueue_orderings(kvg_ctx* ctx, size_t cap, const OrdInput& in, size_
     a.src = p == 0 ? in.src[ord] : SRC_PAIRS;
     return a;
   };
-  static const bool persist = [] {  // KVG_ORDER_PERSIST=0: the launch-per-phase form at every size (A/B)
-    const char* e = getenv("KVG_ORDER_PERSIST");
-    return !(e && e[0] == '0');
-  }();
-  if (persist && expect < (2u << 20)) {
-    // latency-bound: the whole step (all passes, permutation, heads) is ONE persistent launch
-    if (!ctx->order_all_ctas) {
-      CK(cudaFuncSetAttribute(k_order_all, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)OrdScatterCfg<RADIX_MAX_BITS>::SMEM));
-      int nb = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_order_all, KVG_BLOCK, OrdScatterCfg<RADIX_MAX_BITS>::SMEM));
-      ctx->order_all_ctas = std::max(1, nb) * std::max(1, ctx->sm_count);
-      ENSURE(ctx->grid_bar, 4);  // zero-filled: arrivals, generation
-    }
-    OrdAllArgs A;
-    for (int ord = 0; ord < 2; ord++) {
-      A.o[ord] = fill(ord, 0);
-      A.p0[ord] = ob[ord]->p0.p;
-      A.p1[ord] = ob[ord]->p1.p;
-      A.nsets[ord] = (uint32_t)nsets[ord];
-      OrdFinalArgs& a = A.f[ord];
-      a.p0 = ob[ord]->p0.p;
-      a.p1 = ob[ord]->p1.p;
-      a.max_key = maxk[ord];
-      a.key_bits_max = key_bits[ord];
-      a.max_bits = max_bits;
-      a.n_ptr = cnt[ord];
-      a.perm = ob[ord]->perm.p;
-      a.state = ob[ord]->heads_state.p;
-      a.tile_heads = ob[ord]->tile_heads.p;
-      a.tile_off = ob[ord]->tile_off.p;
-      a.seg_key = ob[ord]->seg_key.p;
-      a.seg_off = ob[ord]->seg_off.p;
-      a.n_seg = ord == 0 ? &c->n_dev_keys : &c->n_groups;
-      a.head_surv = ord == 0 ? in.head_surv : nullptr;
-      a.head_name = a.head_surv ? ob[ord]->seg_name.p : nullptr;
-    }
-    A.gbar = ctx->grid_bar.p;
-    const unsigned G = (unsigned)std::min<size_t>(2 * Te, (size_t)ctx->order_all_ctas);
-    LAUNCH("order_all", k_order_all, G, KVG_BLOCK, OrdScatterCfg<RADIX_MAX_BITS>::SMEM, A);
-    return check_launch(ctx, "orderings");
-  }
   if (!ctx->scatter_smem_set) {  // a function attribute is per device: remember it per context
     CK(cudaFuncSetAttribute(k_order_scatter<RADIX_MAX_BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)OrdScatterCfg<RADIX_MAX_BITS>::SMEM));
@@ -2071,6 +2013,7 @@ static int enqueue_exchange(kvg_ctx* ctx, const uint4* local, size_t n_cap, size
   A.ticket = tickets;
   A.T = (uint32_t)T;
   A.P = (uint32_t)P;
+  A.Pm = shard_magic((uint32_t)P);
   A.me = (uint32_t)ctx->rank;
   A.only = peer ? SH_ALL : (uint32_t)ctx->rank;
   A.n_src = peer ? (uint32_t)P : 1u;
@@ -2121,7 +2064,7 @@ static int enqueue_exchange(kvg_ctx* ctx, const uint4* local, size_t n_cap, size
   G.n_own = &c->n_own[0];
   G.max_key = &c->own_max[0];
   dim3 ggrid((unsigned)std::max(1, ctx->sm_count), 2);
-  LAUNCH("shard_gather", k_shard_gather<U>, ggrid, KVG_BLOCK, 0, A, G, peers, mine, err);
+  LAUNCH("shard_gather", k_shard_gather<U>, ggrid, KVG_BLOCK, 0, A, G, peers, mine, err, 3u);
   *owned_cap_out = owned_cap;
   return check_launch(ctx, "shard exchange");
 }
@@ -2148,7 +2091,11 @@ int kvg_dev_scan_pci_sharded(kvg_ctx* ctx, const void* d_recs, size_t n_local) {
   CK(cudaMemsetAsync(ctx->ctrl.p, 0, sizeof(ScanCtrl), ctx->stream));
   size_t owned_cap = 0;
   int rc;
-  if (ctx->p2p && n_local < FUSED_SEND_MAX) {  // classify + send in one kernel
+  bool fuse = ctx->p2p && n_local < FUSED_SEND_MAX;  // classify + send in one kernel
+#ifdef KVG_EXP
+  if (const char* e = getenv("KVG_SHARD_EXP")) fuse = fuse && !(atoi(e) & 8);
+#endif
+  if (fuse) {
     PciClassifyOp op;
     op.recs = (const uint4*)d_recs;
     op.n = (uint32_t)n_local;

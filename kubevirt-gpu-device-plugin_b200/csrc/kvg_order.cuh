@@ -18,6 +18,11 @@
 // from the scatter for the next pass) removes the histogram launches but costs more than they do — +13 us
 // in the 1 M-record classify, +35 us in its pass-0 scatter (hot rows), +64 us in the 16.7 M-record pack.
 //
+// Second measured dead end (round 2): the whole step as ONE persistent launch (the same device functions in a
+// grid that fits the GPU, 3 grid barriers per pass + 1 for the heads).  Correct (GPU suite green) but 7 us SLOWER
+// at 1 M records (0.121 vs 0.114 ms per step): seven barriers over ~440 CTAs cost more than the nine launch
+// boundaries they replace once those launches overlap through programmatic dependent launch.
+//
 // Digit width is decided ON THE DEVICE from the largest key of the ordering: the fewest passes of at most
 // `max_bits` bits, the key bits split evenly between them (19-bit keys: 2 passes of 10 bits; 16-bit keys:
 // 2 x 8; 23-bit: 3 x 8).  Every CTA of every kernel of a pass derives the same plan from the same word, so
@@ -519,147 +524,6 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_order_heads(OrdFinalArgs2 aa) {
       if (tile == T - 1 && threadIdx.x == 0) a.seg_off[*a.n_seg] = n;
     }
     __syncthreads();  // s_w is rewritten by the next tile
-  }
-}
-
-// ---- the whole ordering step as ONE persistent launch (latency-bound sizes) --------------------------------
-// Below ~2 M elements every kernel above runs for 3-15 us and the step is a chain of ten launches whose
-// boundaries (launch gap, ramp-up, tail, and the chained scan of the final kernel: ~6 us of dependent L2 round
-// trips when all tiles start together) cost as much as the work.  k_order_all runs the same phases — the same
-// device functions — in one grid that fits the GPU at once, separated by grid barriers:
-//   per pass:  histograms | tile scan | scatter        (3 barriers)
-//   final:     permutation + head counts | offsets (every CTA sums the <= 1024 tile counts in front of its
-//              tile: no chain) + heads                    (1 barrier)
-// Both orderings share every phase.  The barrier is the sense-reversing counter of cooperative groups
-// (thread 0: fence, arrive, spin on the generation word, fence; block barriers around it); enqueue_orderings
-// bounds the grid by the occupancy so that every CTA is resident.
-struct OrdAllArgs {
-  OrdArgs o[2];       // pass 0 view of each ordering (pass / buffers of later passes are derived on the device)
-  OrdFinalArgs f[2];
-  uint2* p0[2];       // ping-pong buffers
-  uint2* p1[2];
-  uint32_t nsets[2];  // launch sets of each ordering (ceil(key bits / max_bits))
-  uint32_t* gbar;     // [0] arrivals, [1] generation
-};
-__device__ __forceinline__ void grid_sync(uint32_t* bar) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const uint32_t gen = *((volatile uint32_t*)&bar[1]);  // cannot advance before I arrive
-    __threadfence();
-    if (atomicAdd(&bar[0], 1u) == gridDim.x - 1) {
-      atomicExch(&bar[0], 0u);
-      __threadfence();
-      atomicAdd(&bar[1], 1u);
-    } else {
-      while (*((volatile uint32_t*)&bar[1]) == gen) {
-      }
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-__device__ __forceinline__ OrdArgs ord_args_of_pass(const OrdArgs& base, uint2* p0, uint2* p1, uint32_t nsets, uint32_t p) {
-  OrdArgs a = base;
-  a.pairs_in = (p & 1) ? p0 : p1;  // pass 0 reads the survivor records (or, SRC_PAIRS, pairs placed in p1)
-  a.pairs_out = (p & 1) ? p1 : p0;
-  a.pass = p < nsets ? p : 0xffu;
-  a.src = p == 0 ? base.src : SRC_PAIRS;
-  return a;
-}
-__global__ void __launch_bounds__(KVG_BLOCK, OrdScatterCfg<RADIX_MAX_BITS>::MIN_CTAS) k_order_all(OrdAllArgs A) {
-  using Cfg = OrdScatterCfg<RADIX_MAX_BITS>;
-  pdl_enter();
-#ifndef KVG_HOST_EMU
-  extern __shared__ __align__(16) uint8_t rs_smem[];
-#else
-  static __attribute__((aligned(16))) uint8_t rs_smem[Cfg::SMEM];
-#endif
-  static_assert(Cfg::SMEM >= RADIX_MAX_DIGITS * 4, "the histogram aliases the scatter's shared memory");
-  __shared__ uint32_t scratch[KVG_WARPS + 1];
-  __shared__ uint32_t s_w[KVG_WARPS];
-  const uint32_t G = gridDim.x, cta = blockIdx.x;
-  const uint32_t lane = lane_id(), warp = warp_id(), tid = threadIdx.x;
-  const uint32_t n0 = *A.o[0].n_ptr, n1 = *A.o[1].n_ptr;
-  const uint32_t T0 = (n0 + C_TILE - 1) / C_TILE;
-  // ordering 1 starts where ordering 0's tiles end, so that the CTAs ordering 0 left idle work first
-  const uint32_t cta1 = (cta + G - T0 % G) % G;
-  const uint32_t max_sets = max(A.nsets[0], A.nsets[1]);
-  for (uint32_t p = 0; p < max_sets; p++) {
-    const OrdArgs a0 = ord_args_of_pass(A.o[0], A.p0[0], A.p1[0], A.nsets[0], p);
-    const OrdArgs a1 = ord_args_of_pass(A.o[1], A.p0[1], A.p1[1], A.nsets[1], p);
-    const RadixPlan pl0 = ord_pass(a0), pl1 = ord_pass(a1);
-    if (!pl0.bits && !pl1.bits) break;  // the same decision in every CTA (device-side plan)
-    if (pl0.bits) ord_hist_tiles(a0, pl0, cta, G, reinterpret_cast<uint32_t*>(rs_smem));
-    if (pl1.bits) ord_hist_tiles(a1, pl1, cta1, G, reinterpret_cast<uint32_t*>(rs_smem));
-    grid_sync(A.gbar);
-    if (pl0.bits) ord_tilescan_rows(a0, pl0, cta * KVG_WARPS + warp, G * KVG_WARPS);
-    if (pl1.bits) ord_tilescan_rows(a1, pl1, cta1 * KVG_WARPS + warp, G * KVG_WARPS);
-    grid_sync(A.gbar);
-    if (pl0.bits) ord_scatter_tiles<RADIX_MAX_BITS>(a0, pl0, cta, G, rs_smem, scratch);
-    if (pl1.bits) ord_scatter_tiles<RADIX_MAX_BITS>(a1, pl1, cta1, G, rs_smem, scratch);
-    grid_sync(A.gbar);
-  }
-  // ---- final: permutation + head counts per tile
-#pragma unroll 1
-  for (uint32_t ord = 0; ord < 2; ord++) {
-    const OrdFinalArgs f = ord ? A.f[1] : A.f[0];
-    const uint32_t n = ord ? n1 : n0;
-    const uint32_t T = (n + C_TILE - 1) / C_TILE;
-    if (n == 0) {
-      if (cta == 0 && tid == 0) {
-        f.seg_off[0] = 0;
-        *f.n_seg = 0;
-      }
-      continue;
-    }
-    const uint2* pairs = ord_final_buf(f);
-    for (uint32_t tile = ord ? cta1 : cta; tile < T; tile += G) {
-      const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
-      uint32_t bal[C_ROWS], key[C_ROWS], idx[C_ROWS];
-      const uint32_t wtot = ord_tile_heads(f, pairs, n, base, lane, true, bal, key, idx);
-      if (lane == 0) s_w[warp] = wtot;
-      __syncthreads();
-      if (tid == 0) {
-        uint32_t t = 0;
-#pragma unroll
-        for (uint32_t w = 0; w < KVG_WARPS; w++) t += s_w[w];
-        f.tile_heads[tile] = t;
-      }
-      __syncthreads();
-    }
-  }
-  grid_sync(A.gbar);
-  // ---- heads: every CTA sums the tile counts in front of its tile, then emits
-#pragma unroll 1
-  for (uint32_t ord = 0; ord < 2; ord++) {
-    const OrdFinalArgs f = ord ? A.f[1] : A.f[0];
-    const uint32_t n = ord ? n1 : n0;
-    const uint32_t T = (n + C_TILE - 1) / C_TILE;
-    if (n == 0) continue;
-    const uint2* pairs = ord_final_buf(f);
-    for (uint32_t tile = ord ? cta1 : cta; tile < T; tile += G) {
-      uint32_t part = 0;
-      for (uint32_t i = tid; i < tile; i += KVG_BLOCK) part += f.tile_heads[i];
-      uint32_t before;
-      block_excl_sum(part, scratch, &before);  // syncs inside; `before` = heads of all earlier tiles
-      const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
-      uint32_t bal[C_ROWS], key[C_ROWS], idx[C_ROWS];
-      const uint32_t wtot = ord_tile_heads(f, pairs, n, base, lane, false, bal, key, idx);
-      if (lane == 0) s_w[warp] = wtot;
-      __syncthreads();
-      uint32_t off = before, t = 0;
-#pragma unroll
-      for (uint32_t w = 0; w < KVG_WARPS; w++) {
-        if (w < warp) off += s_w[w];
-        t += s_w[w];
-      }
-      ord_emit_heads(f, off, base, lane, bal, key, idx);
-      if (tile == T - 1 && tid == 0) {
-        *f.n_seg = before + t;
-        f.seg_off[before + t] = n;
-      }
-      __syncthreads();  // scratch / s_w are rewritten by the next tile
-    }
   }
 }
 

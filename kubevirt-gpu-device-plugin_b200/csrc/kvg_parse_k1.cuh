@@ -3,8 +3,10 @@
 //
 // A WARP owns a 4 KiB span of text end to end and never waits for another warp or CTA:
 //
-//   k_pciids_prep      dev_off <- NONE, info <- {v_off = NONE}, nv_index <- NONE, pool <- 0   (one launch
-//                      instead of a chain of memsets)
+//   (no clearing launch: the table and the accumulators are SELF-CLEANING — k_pciids_names resets every
+//   dev_off slot it reads, the finalize CTAs consume and reset the two per-image accumulators kept in
+//   PciIdsInfo::pad, the resolve CTAs zero the name pool of the parse they belong to, and nv_index is written
+//   whole.  Fresh allocations are filled once by the host.)
 //   k_pciids_scan      persistent warps; every warp streams a contiguous run of spans through a PRIVATE two-stage ring of
 //                      TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx::bytes -> SASS UBLKCP) into
 //                      shared memory.  Per span, 4 rows of 1 KiB: two conflict-free LDS.128 per lane and
@@ -70,35 +72,12 @@ struct K1Args {
   uint32_t spans_per_file;
   uint32_t n_spans;
   uint32_t* dev_off;  // [n_files][K1_IDS] line offset of the FIRST "\t<id>" line under a 10de header, or NONE
-  PciIdsInfo* info;   // [n_files]
+  PciIdsInfo* info;   // [n_files]; pad[0] = max over ~offset of the "10de" headers seen (0: none), pad[1] = newlines:
+                      // accumulators of the scan kernel, consumed and reset by the finalize CTA of the image
   uint4* span_sum;    // [n_spans]
-};
-
-struct K1PrepArgs {
-  uint4* dev_off;       // all images, 16-byte units
-  uint64_t dev_off16;
-  PciIdsInfo* info;
-  uint32_t n_files;
-  uint4* nv_index;      // [K1_IDS / 4] or NULL
-  uint4* pool;          // name pool, pool16 x 16 bytes, or NULL
+  uint4* pool;        // name pool of image 0 (pool16 x 16 bytes): zeroed by the resolve CTAs, filled by k_pciids_names
   uint32_t pool16;
 };
-__global__ void __launch_bounds__(KVG_BLOCK) k_pciids_prep(K1PrepArgs P) {
-  pdl_enter();
-  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
-  const uint4 e = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
-  for (size_t i = tid; i < P.dev_off16; i += nth) P.dev_off[i] = e;
-  for (size_t i = tid; i < P.n_files; i += nth) {
-    PciIdsInfo z;
-    z.v_off = P_NONE;
-    z.sec_end = z.n_entries = z.n_lines = z.limit = z.overflow = z.pad[0] = z.pad[1] = 0;
-    P.info[i] = z;
-  }
-  if (P.nv_index)
-    for (size_t i = tid; i < K1_IDS / 4; i += nth) P.nv_index[i] = e;
-  if (P.pool)
-    for (size_t i = tid; i < P.pool16; i += nth) P.pool[i] = make_uint4(0, 0, 0, 0);
-}
 
 // bit 7 of byte b is CLEAR iff the LOW SEVEN bits of byte b of w are those of '\n' — true for '\n' and for
 // 0x8A.  Three instructions per word ((w ^ c) & m as ONE LOP3 with a constant in a register, an add, and the
@@ -138,6 +117,10 @@ __host__ __device__ __forceinline__ uint32_t k1_bit_off(uint32_t t) {
 __device__ __forceinline__ uint32_t k1_header_key(const uint8_t* sm, uint32_t p) {
   return ((p + 1) << 17) | parse_hex4(sm + p);
 }
+// the same, out of line: the scan kernel tests ~110 line starts per span and ~6 of them are headers — one shared
+// copy of the hex parse instead of one per unrolled call site keeps the hot loop inside the instruction cache
+// (no_inst stalls were 11 % of the kernel's samples with the parse inlined ten times)
+__device__ __noinline__ uint32_t k1_header_key_cold(const uint8_t* sm, uint32_t p) { return k1_header_key(sm, p); }
 
 // A span whose tail lies beyond EOF (the last span of an image): padding bytes become 0 in shared memory, so
 // that no mask needs an EOF case (the one remaining rule — a '\n' that is the file's LAST byte is counted but
@@ -309,19 +292,19 @@ __global__ void __launch_bounds__(K1_WARPS * 32, KVG_K1_MINCTAS) k_pciids_scan(K
         first_hdr = 0;
         if ((last_key & 0x1ffffu) == K1_VALID_10DE) {
           saw_10de = true;
-          atomicMin(&A.info[f].v_off, a);
+          atomicMax(&A.info[f].pad[0], ~a);
         }
       }
     }
     const uint8_t* cell = sm + lane * 16;
     auto header_at = [&](uint32_t po) {  // a header-type line starts at cell + po
       const uint32_t p = po + lane * 16;
-      const uint32_t k = k1_header_key(sm, p);
+      const uint32_t k = k1_header_key_cold(sm, p);
       last_key = max(last_key, k);  // mask bits are not in position order: keys carry the position
       first_hdr = min(first_hdr, p);
       if ((k & 0x1ffffu) == K1_VALID_10DE) {
         saw_10de = true;
-        atomicMin(&A.info[f].v_off, a + p);
+        atomicMax(&A.info[f].pad[0], ~(a + p));
       }
     };
 #if KVG_K1_CELLS
@@ -367,7 +350,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, KVG_K1_MINCTAS) k_pciids_scan(K
     if (__any_sync(KVG_FULL, saw_10de))
       k1_record_lines(sm, A.dev_off + (size_t)f * K1_IDS, A.len, a, lane, extra, 0u, false);
     if (lane == 0) {
-      if (n_nl) atomicAdd(&A.info[f].n_lines, n_nl);
+      if (n_nl) atomicAdd(&A.info[f].pad[1], n_nl);
       A.span_sum[s0 + i] = make_uint4(first_hdr == P_NONE ? P_NONE : a + first_hdr, has_nl ? 1u : 0u, 0u,
                                       last_key ? (0x80000000u | (last_key & 0x1ffffu)) : 0u);
     }
@@ -397,7 +380,8 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_resolve_finalize(K1Args A)
     const uint8_t* text = A.text + (uint64_t)f * A.stride;
     const uint4* sum = A.span_sum + (size_t)f * A.spans_per_file;
     PciIdsInfo* info = &A.info[f];
-    const uint32_t V = info->v_off;  // complete: the scan kernel has finished
+    const uint32_t acc_v = info->pad[0], acc_lines = info->pad[1];  // complete: the scan kernel has finished
+    const uint32_t V = acc_v ? ~acc_v : P_NONE;
     // stage the span that owns the line starting at V (the byte scan below reads neighbours)
     const uint32_t tv = (V == P_NONE || V == 0) ? 0 : (V - 1) / K1_SPAN;
     if (V != P_NONE) {
@@ -438,9 +422,13 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_resolve_finalize(K1Args A)
     const uint32_t limit = s_limit;
     if (V == P_NONE || V >= limit) {  // vendor line never reached (:382-385)
       if (threadIdx.x == 0) {
-        info->v_off = P_NONE;
-        info->sec_end = P_NONE;
-        info->limit = limit;
+        PciIdsInfo z;
+        z.v_off = z.sec_end = P_NONE;
+        z.n_entries = 0;
+        z.n_lines = acc_lines;
+        z.limit = limit;
+        z.overflow = z.pad[0] = z.pad[1] = 0;  // accumulators back to "nothing seen" for the next parse
+        *info = z;
       }
       return;
     }
@@ -459,12 +447,21 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_resolve_finalize(K1Args A)
     if (threadIdx.x == 0) {
       uint32_t e = s_end;
       if (e == A.len && s_hdr_span != P_NONE) e = sum[s_hdr_span].x;
-      info->sec_end = min(e, limit);
-      info->limit = limit;
+      PciIdsInfo z;
+      z.v_off = V;
+      z.sec_end = min(e, limit);
+      z.n_entries = 0;  // counted by k_pciids_names
+      z.n_lines = acc_lines;
+      z.limit = limit;
+      z.overflow = z.pad[0] = z.pad[1] = 0;  // accumulators back to "nothing seen" for the next parse
+      *info = z;
     }
     return;
   }
   // ------------------------------------------------------------------ resolve: one warp per span
+  // first the name pool of this parse (k_pciids_names, the next kernel, is its only writer)
+  for (uint32_t i = (blockIdx.x - A.n_files) * KVG_BLOCK + threadIdx.x; i < A.pool16; i += (gridDim.x - A.n_files) * KVG_BLOCK)
+    A.pool[i] = make_uint4(0, 0, 0, 0);
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   const uint32_t span = (blockIdx.x - A.n_files) * K1_RWARPS + warp;
   if (span >= A.n_spans) return;  // warp-uniform; no block barrier on this path
@@ -502,9 +499,10 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_resolve_finalize(K1Args A)
 // K2 for image 0: thread per device id (strided so that runs of consecutive ids — the shipped file has
 // many — spread over the warps); every id recorded inside the first "10de" section publishes
 // nv_index[id] = slot (= line offset - v_off) and, warp-cooperatively, its sanitised name at pool + slot
-// (u16 length + bytes).  nv_index and the pool were cleared by k_pciids_prep.  Also counts the ids recorded.
+// (u16 length + bytes); every other id publishes NONE, so nv_index never needs clearing.  Counts the ids
+// recorded.  Every slot read is reset (the table is self-cleaning), the tables of the other images included.
 // Launch with K1_IDS / 32 warps.
-__global__ void __launch_bounds__(KVG_BLOCK) k_pciids_names(const uint32_t* __restrict__ dev_off,
+__global__ void __launch_bounds__(KVG_BLOCK) k_pciids_names(uint32_t* __restrict__ dev_off, uint32_t n_files,
                                                             const uint8_t* __restrict__ text, uint32_t len,
                                                             PciIdsInfo* __restrict__ info,
                                                             uint32_t* __restrict__ nv_index,
@@ -516,14 +514,22 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_names(const uint32_t* __re
   const uint32_t w = blockIdx.x * KVG_WARPS + warp_id();
   const uint32_t id = lane * n_warps + w;
   const uint32_t off = id < K1_IDS ? dev_off[id] : P_NONE;
+  if (off != P_NONE) dev_off[id] = P_NONE;
   const uint32_t recorded = __ballot_sync(KVG_FULL, off != P_NONE);
   if (lane == 0 && recorded) atomicAdd(&info->n_entries, (uint32_t)__popc(recorded));
-  if (V == P_NONE) return;
-  const bool ok = off != P_NONE && off > V && off < E;
-  if (ok) nv_index[id] = off - V;
+  const bool ok = V != P_NONE && off != P_NONE && off > V && off < E;
+  if (id < K1_IDS && nv_index) nv_index[id] = ok ? off - V : P_NONE;
   for (uint32_t todo = __ballot_sync(KVG_FULL, ok); todo; todo &= todo - 1) {
     const uint32_t slot = __shfl_sync(KVG_FULL, off, (uint32_t)__ffs(todo) - 1) - V;
     sanitise_line_warp(text, len, V + slot + 5, pool + slot, lane);  // first byte after "\t" + 4 hex
+  }
+  // the tables of images 1 .. n_files - 1 (throughput runs parse many images; nothing reads their slots)
+  uint4* rest = reinterpret_cast<uint4*>(dev_off + K1_IDS);
+  const size_t rest16 = (size_t)(n_files - 1) * (K1_IDS / 4);
+  const uint4 none = make_uint4(P_NONE, P_NONE, P_NONE, P_NONE);
+  for (size_t i = (size_t)blockIdx.x * KVG_BLOCK + threadIdx.x; i < rest16; i += (size_t)gridDim.x * KVG_BLOCK) {
+    const uint4 v = rest[i];
+    if ((v.x & v.y & v.z & v.w) != P_NONE) rest[i] = none;
   }
 }
 

@@ -84,6 +84,7 @@ struct ShardArgs {
   uint32_t* ticket;        // self-resetting "last CTA" counters: [0] send, [1] gather
   uint32_t T;              // row pitch of state (tiles the launch covers)
   uint32_t P;              // owners (key % P)
+  uint32_t Pm;             // floor(2^32 / P) (P = 1: 2^32 - 1): key % P without a division (shard_owner)
   uint32_t me;             // this rank
   uint32_t only;           // SH_ALL: send to every owner; else keep only records owned by `only` (local mode)
   uint32_t n_src;          // regions per (parity, ordering): P, or 1 in local mode
@@ -95,6 +96,22 @@ struct ShardArgs {
   uint32_t exp;            // timing experiments only (never in the shipped build)
 #endif
 };
+
+// owner of a key = key % P.  A runtime 32-bit modulo is ~20 instructions and every survivor needs four of them;
+// with m = floor(2^32 / P) the estimate hi(key * m) is the quotient or one less, so one multiply-high, one
+// multiply-subtract and one conditional subtract are exact.
+__host__ __device__ __forceinline__ uint32_t shard_magic(uint32_t P) {
+  return P <= 1 ? 0xffffffffu : (uint32_t)(0x100000000ull / P);
+}
+__device__ __forceinline__ uint32_t shard_owner(uint32_t key, const ShardArgs& A) {
+#ifdef __CUDA_ARCH__
+  const uint32_t qd = __umulhi(key, A.Pm);
+#else
+  const uint32_t qd = (uint32_t)(((uint64_t)key * A.Pm) >> 32);
+#endif
+  const uint32_t r = key - qd * A.P;
+  return r >= A.P ? r - A.P : r;
+}
 
 // window addressing (16-byte units): region (parity, ordering, source) of a window
 __device__ __forceinline__ size_t shard_region(const ShardArgs& A, uint32_t o, uint32_t s, int U) {
@@ -114,7 +131,6 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_shard_send(ShardArgs A, ShardPeer
   const uint32_t tile = blockIdx.x;
   __shared__ uint32_t s_wcnt[KVG_WARPS][2][SH_MAX_RANKS];  // per warp: survivors of every (ordering, owner) -> prefix over the warps
   __shared__ uint32_t s_base[2][SH_MAX_RANKS];             // the tile's position in every (ordering, owner) region
-  __shared__ uint32_t s_last;
   const uint32_t lane = lane_id(), warp = warp_id();
   const uint32_t active = max(Tu, 1u);  // CTAs that take part (tile 0 also stands for the empty list)
   if (tile >= active) return;
@@ -140,8 +156,8 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_shard_send(ShardArgs A, ShardPeer
 #pragma unroll
         for (int u = 0; u < U; u++) rec[k][u] = A.list[(size_t)i * U + u];
         const uint2 key = shard_keys<U>(rec[k]);
-        q0[k] = key.x % A.P;
-        q1[k] = key.y % A.P;
+        q0[k] = shard_owner(key.x, A);
+        q1[k] = shard_owner(key.y, A);
       }
     }
     static_assert(2 * SH_MAX_RANKS == 32, "one lane per counter");
@@ -199,31 +215,7 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_shard_send(ShardArgs A, ShardPeer
   } else if (n == 0 && tile == 0 && threadIdx.x < 2 * A.P) {
     A.totals[threadIdx.x] = 0;
   }
-  // the last CTA to finish publishes the region counts and the release flag to every owner.  ONE fence per CTA:
-  // the block barrier orders every thread's stores before thread 0's fence, and fences are cumulative (256
-  // system-scope fences per CTA, and one in every idle CTA, were a third of this kernel's time)
-  __syncthreads();
-  if (threadIdx.x == 0) {
-#ifdef KVG_EXP
-    if (!(A.exp & 2u))
-#endif
-    __threadfence_system();
-    s_last = atomicAdd(&A.ticket[0], 1u) == active - 1 ? 1u : 0u;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence_system();
-  if (threadIdx.x < A.P) {
-    const uint32_t q = threadIdx.x;
-    if (A.only == SH_ALL || q == A.only) {
-      ShardCtrl* c = peers.ctrl[q];
-      c->count[A.parity][0][A.src] = *((volatile uint32_t*)&A.totals[q]);
-      c->count[A.parity][1][A.src] = *((volatile uint32_t*)&A.totals[A.P + q]);
-      __threadfence_system();
-      st_release_sys(&c->flag[A.parity][A.src], A.step);
-    }
-  }
-  if (threadIdx.x == 0) A.ticket[0] = 0;
+  // nothing is published here: the grid's completion is the fence (see k_shard_gather)
 }
 
 // ---- classify + send in ONE kernel (latency-bound shard sizes) ------------------------------------------------
@@ -237,8 +229,11 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_shard_send(ShardArgs A, ShardPeer
 // k_shard_send keeps the chained scan: it serves the sizes where T^2 is not nothing.)
 // CW4 = uint4 loads per tile row: 4 * CW4 >= 1 + 2P.
 constexpr uint32_t CS_COUNT_BITS = 11;
+#ifndef KVG_CS_MINB
+#define KVG_CS_MINB 7  // CTAs per SM asked of the P <= 3 instantiation: 7 x 148 >= the 977 tiles of a 1 M-record shard (one wave)
+#endif
 template <class Op, int THREADS, int ROWS, int CW4>
-__global__ void __launch_bounds__(THREADS) k_classify_send(Op op, ShardArgs A, ShardPeers peers, const ShardCtrl* mine,
+__global__ void __launch_bounds__(THREADS, CW4 <= 2 ? KVG_CS_MINB : 1) k_classify_send(Op op, ShardArgs A, ShardPeers peers, const ShardCtrl* mine,
                                                            uint32_t* err, uint32_t* tile_words, uint32_t epoch) {
   pdl_enter();
   constexpr int U = Op::UNITS;
@@ -252,7 +247,6 @@ __global__ void __launch_bounds__(THREADS) k_classify_send(Op op, ShardArgs A, S
   __shared__ uint32_t s_wtot[NW], s_woff[NW];
   __shared__ uint32_t s_agg[CW], s_excl[CW];
   __shared__ uint32_t s_part[NW][CW];
-  __shared__ uint32_t s_last;
   op.begin();
   const uint32_t n = op.count();
   const uint32_t n_tiles = (n + TILE - 1) / TILE;
@@ -304,7 +298,7 @@ __global__ void __launch_bounds__(THREADS) k_classify_send(Op op, ShardArgs A, S
       const uint2 key = op.keys(item[k], aux[k]);
 #pragma unroll
       for (uint32_t o = 0; o < 2; o++) {
-        const uint32_t q = p ? (o ? key.y : key.x) % A.P : SH_ALL;
+        const uint32_t q = p ? shard_owner(o ? key.y : key.x, A) : SH_ALL;
         const uint32_t same = __match_any_sync(KVG_FULL, q);
         const uint32_t before = __popc(same & lanemask_lt());
         const uint32_t prior = p ? s_wcnt[warp][o][q] : 0;
@@ -406,7 +400,7 @@ __global__ void __launch_bounds__(THREADS) k_classify_send(Op op, ShardArgs A, S
         const uint2 key = op.keys(item[k], aux[k]);
 #pragma unroll
         for (uint32_t o = 0; o < 2; o++) {
-          const uint32_t q = (o ? key.y : key.x) % A.P;
+          const uint32_t q = shard_owner(o ? key.y : key.x, A);
           const uint32_t at = s_excl[1 + o * A.P + q] + s_wcnt[warp][o][q] + (((o ? pos1 : pos0)[k >> 2] >> (8 * (k & 3))) & 0xffu);
           uint4* dst = peers.win[q] + shard_region(A, o, A.src, U) + (size_t)at * U;
 #pragma unroll
@@ -417,23 +411,7 @@ __global__ void __launch_bounds__(THREADS) k_classify_send(Op op, ShardArgs A, S
     }
     op.tile_epilogue();
   }
-  // the last CTA to finish publishes the region counts and the release flag to every owner (one fence per CTA)
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence_system();
-    s_last = atomicAdd(&A.ticket[0], 1u) == active - 1 ? 1u : 0u;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence_system();
-  if (tid < A.P) {
-    ShardCtrl* c = peers.ctrl[tid];
-    c->count[A.parity][0][A.src] = *((volatile uint32_t*)&A.totals[tid]);
-    c->count[A.parity][1][A.src] = *((volatile uint32_t*)&A.totals[A.P + tid]);
-    __threadfence_system();
-    st_release_sys(&c->flag[A.parity][A.src], A.step);
-  }
-  if (tid == 0) A.ticket[0] = 0;
+  // nothing is published here: the grid's completion is the fence (see k_shard_gather)
 }
 
 struct GatherArgs {
@@ -443,13 +421,28 @@ struct GatherArgs {
   uint32_t* max_key;       // [2]: {max_devkey, max_group} of ScanCtrl (pre-zeroed)
 };
 
+// phase bit 0: publish my regions, bit 1: gather.  The product launches both at once; a sequential emulation of
+// P ranks has to publish for every rank before any rank can gather.
+//
+// Publishing lives HERE, not at the end of the send kernel: a kernel boundary is a fence.  This kernel starts
+// (griddepcontrol.wait returns) when the send grid has completed and all its stores — the NVLink ones included —
+// are performed, so one CTA can publish the counts and the release flags at once.  The send kernels used to end
+// with a system-scope fence + ticket per CTA: the fence alone was 45 % of the warp time of k_classify_send.
 template <int U>
 __global__ void __launch_bounds__(KVG_BLOCK) k_shard_gather(ShardArgs A, GatherArgs G, ShardPeers peers,
-                                                            const ShardCtrl* mine, uint32_t* err) {
+                                                            const ShardCtrl* mine, uint32_t* err, uint32_t phase) {
   pdl_enter();
   __shared__ uint32_t s_cnt[2][SH_MAX_RANKS], s_off[2][SH_MAX_RANKS + 1];
   __shared__ uint32_t s_last;
   const uint32_t tid = threadIdx.x;
+  if ((phase & 1u) && blockIdx.x == 0 && blockIdx.y == 0 && tid < A.P && (A.only == SH_ALL || tid == A.only)) {
+    ShardCtrl* c = peers.ctrl[tid];
+    c->count[A.parity][0][A.src] = A.totals[tid];
+    c->count[A.parity][1][A.src] = A.totals[A.P + tid];
+    __threadfence_system();
+    st_release_sys(&c->flag[A.parity][A.src], A.step);
+  }
+  if (!(phase & 2u)) return;
   if (tid < A.n_src) {  // wait for every source's regions of this step
     const long long t0 = clock64();
     bool ok = true;

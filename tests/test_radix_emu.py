@@ -90,9 +90,8 @@ def test_whole_ordering_permutation_segments_and_bucket_names(emu):
         seg_key, seg_off, seg_name = np.zeros(n + 2, np.uint32), np.zeros(n + 2, np.uint32), np.zeros(n + 2, np.uint32)
         order = np.argsort(keys, kind="stable")
         uniq, first = np.unique(keys[order], return_index=True)
-        # forms of the step: 0 = count / offsets / emit, 1 = one chained-scan launch, 2 = k_order_all (all radix
-        # passes AND the final step in one persistent launch)
-        for form in (n % 2, 2):
+        # forms of the final step: 0 = count / offsets / emit, 1 = one chained-scan launch
+        for form in (0, 1):
             p2 = pairs.copy()
             perm[:] = 0xdeadbeef
             seg_key[:] = seg_off[:] = seg_name[:] = 0xdeadbeef

@@ -1,5 +1,5 @@
-"""The exchange step of the sharded scan (csrc/kvg_shard.cuh: k_shard_count -> k_shard_scan -> k_shard_send ->
-k_shard_gather) executed on the CPU from its real kernel source: P emulated ranks with their own windows and
+"""The exchange step of the sharded scan (csrc/kvg_shard.cuh: k_shard_send or the fused k_classify_send, then
+k_shard_gather — which also publishes) executed on the CPU from its real kernel source: P emulated ranks with their own windows and
 control blocks, several back-to-back steps (window parities, acks), peer-window mode and the NCCL local mode,
 16-byte (PCI) and 32-byte (mdev) records.  Every rank must end up with exactly the records whose key it owns
 (key % P == rank), in Walk order (source-rank order, then position), for both orderings."""
@@ -132,3 +132,19 @@ def test_classify_and_send_in_one_kernel(emu, P):
             cnt = int(n_own[2 * r + o])
             assert cnt == len(want), (r, o, cnt, len(want))
             assert np.array_equal(got[r, :cnt], want), (r, o)
+
+
+def test_owner_without_division_is_exact():
+    """shard_owner (kvg_shard.cuh): hi(key * floor(2^32 / P)) is the quotient or one less for every 32-bit key,
+    so one conditional subtract makes key % P exact.  Checked on the corners and a random sample for every P."""
+    rng = np.random.default_rng(3)
+    keys = np.concatenate([np.arange(0, 70, dtype=np.uint64), np.uint64(2 ** 32) - np.arange(1, 70, dtype=np.uint64),
+                           rng.integers(0, 2 ** 32, 200_000, dtype=np.uint64),
+                           (np.arange(1, 17, dtype=np.uint64)[:, None] * np.arange(0, 2 ** 32, 2 ** 27, dtype=np.uint64)[None, :]).ravel() % (2 ** 32)])
+    for P in range(1, 17):
+        m = np.uint64(0xffffffff if P == 1 else (2 ** 32) // P)
+        qd = (keys * m) >> np.uint64(32)
+        r = keys - qd * np.uint64(P)
+        assert np.all(r < 2 * P)
+        r = np.where(r >= P, r - np.uint64(P), r)
+        assert np.array_equal(r, keys % np.uint64(P)), P

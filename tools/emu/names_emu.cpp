@@ -12,7 +12,8 @@ namespace kvg {
 #include "../../kubevirt-gpu-device-plugin_b200/csrc/kvg_parse_k1.cuh"
 using namespace kvg;
 
-// K1 sequenced as parse_enqueue does.  scan_ctas = grid of the persistent scan kernel (0: one warp per
+// K1 sequenced as parse_enqueue does (no clearing launch: dev_off all NONE and info all zero is the state a fresh
+// allocation is given once, and the state every parse leaves behind).  scan_ctas = grid of the persistent scan kernel (0: one warp per
 // span).  nv_index / pool may be NULL (then the names kernel is skipped).
 static void run_k1(const uint8_t* text, uint64_t stride, uint32_t len, uint32_t n_files, uint32_t scan_ctas,
                    uint32_t* dev_off, PciIdsInfo* info, uint32_t* nv_index, uint8_t* pool, uint32_t pool16) {
@@ -28,21 +29,14 @@ static void run_k1(const uint8_t* text, uint64_t stride, uint32_t len, uint32_t 
   A.dev_off = dev_off;
   A.info = info;
   A.span_sum = sums.data();
-  K1PrepArgs P;
-  P.dev_off = (uint4*)dev_off;
-  P.dev_off16 = (uint64_t)K1_IDS * n_files / 4;
-  P.info = info;
-  P.n_files = n_files;
-  P.nv_index = (uint4*)nv_index;
-  P.pool = (uint4*)pool;
-  P.pool16 = pool16;
-  emu_launch(k_pciids_prep, dim3(3), KVG_BLOCK, P);
+  A.pool = (uint4*)pool;
+  A.pool16 = pool16;
   unsigned grid = (n_spans + K1_WARPS - 1) / K1_WARPS;
   if (scan_ctas && scan_ctas < grid) grid = scan_ctas;
   if (n_spans) emu_launch(k_pciids_scan, dim3(grid), K1_WARPS * 32, A);
   emu_launch(k_pciids_resolve_finalize, dim3(n_files + (n_spans + K1_RWARPS - 1) / K1_RWARPS), KVG_BLOCK, A);
   if (nv_index)
-    emu_launch(k_pciids_names, dim3(K1_IDS / 32 / KVG_WARPS), KVG_BLOCK, (const uint32_t*)dev_off, text, len, info, nv_index, pool);
+    emu_launch(k_pciids_names, dim3(K1_IDS / 32 / KVG_WARPS), KVG_BLOCK, dev_off, n_files, text, len, info, nv_index, pool);
 }
 
 static bool canonical_key(const uint8_t* k, uint32_t n, uint32_t* v) {  // kvg_api.cu: 4 lower-case hex digits
@@ -62,9 +56,9 @@ extern "C" {
 // K1 alone: n_files images (text + f*stride); outputs per image info[8 words] and the device-id table
 int emu_parse_k1(const uint8_t* text, uint64_t stride, uint32_t len, uint32_t n_files, uint32_t scan_ctas,
                  uint32_t* info_out, uint32_t* dev_off_out) {
-  std::vector<uint32_t> dev_off((size_t)K1_IDS * n_files, 0x12345678u);  // poisoned: the prep kernel clears
+  std::vector<uint32_t> dev_off((size_t)K1_IDS * n_files, P_NONE);  // the state of a fresh allocation
   std::vector<PciIdsInfo> info(n_files);
-  memset(info.data(), 0x5a, sizeof(PciIdsInfo) * n_files);
+  memset(info.data(), 0, sizeof(PciIdsInfo) * n_files);
   run_k1(text, stride, len, n_files, scan_ctas, dev_off.data(), info.data(), nullptr, nullptr, 0);
   memcpy(info_out, info.data(), sizeof(PciIdsInfo) * n_files);
   memcpy(dev_off_out, dev_off.data(), sizeof(uint32_t) * dev_off.size());
@@ -77,11 +71,30 @@ int emu_get_device_names(const uint8_t* text, uint32_t len, const uint8_t* keys,
                          uint8_t* names_out, uint32_t name_cap, uint32_t* names_len, uint32_t* info_out,
                          uint32_t* nv_index_out, uint8_t* pool_out, uint32_t pool_cap, uint32_t* pool_len) {
   PciIdsInfo info;
-  memset(&info, 0x5a, sizeof info);
+  memset(&info, 0, sizeof info);
   const uint32_t pool_bytes = (len + 16 + 15) & ~15u;
-  std::vector<uint32_t> dev_off(K1_IDS, 0x12345678u), nv_index(K1_IDS, 0x77777777u);
+  std::vector<uint32_t> dev_off(K1_IDS, P_NONE), nv_index(K1_IDS, 0x77777777u);  // nv_index / pool: poisoned, K1 writes them whole
   std::vector<uint8_t> k1_pool(pool_bytes, 0xee);
-  run_k1(text, 0, len, 1, 3, dev_off.data(), &info, nv_index.data(), k1_pool.data(), pool_bytes / 16);
+  // twice on the same buffers: the second parse starts from what the first one left behind (self-cleaning table,
+  // accumulators consumed by the finalize CTA) and must produce the same table
+  std::vector<uint32_t> nv_first;
+  std::vector<uint8_t> pool_first;
+  PciIdsInfo info_first;
+  for (int rep = 0; rep < 2; rep++) {
+    run_k1(text, 0, len, 1, 3, dev_off.data(), &info, nv_index.data(), k1_pool.data(), pool_bytes / 16);
+    for (uint32_t v : dev_off)
+      if (v != P_NONE) return 10;  // a slot survived k_pciids_names
+    if (info.pad[0] || info.pad[1]) return 11;
+    if (rep == 0) {
+      nv_first = nv_index;
+      pool_first = k1_pool;
+      info_first = info;
+      std::fill(nv_index.begin(), nv_index.end(), 0x77777777u);
+      std::fill(k1_pool.begin(), k1_pool.end(), 0xee);
+    } else if (nv_first != nv_index || pool_first != k1_pool || memcmp(&info_first, &info, sizeof info)) {
+      return 12;
+    }
+  }
   memcpy(info_out, &info, sizeof info);
   // ---- table_publish: the host mirrors sec + 16 bytes of the pool; the general lookup's candidate lines
   const size_t sec = info.v_off == P_NONE ? 0 : (size_t)info.sec_end - info.v_off;

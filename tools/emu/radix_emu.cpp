@@ -106,51 +106,6 @@ int emu_ordering(uint2* pairs_io, uint32_t n, const uint4* surv, uint32_t key_bi
   OrdFinalArgs2 ff;
   ff.o[0] = a;
   ff.o[1] = a;
-  if (fused == 2) {
-    // the persistent form: all passes + final in one launch, from the UNSORTED pairs (one CTA here: the grid
-    // barrier of a sequential emulation; the GPU parity tests cover the real grid)
-    Ordering u(pairs_io, n, key_bits_max, max_bits);
-    OrdAllArgs A;
-    for (int ord = 0; ord < 2; ord++) {
-      OrdArgs& b = A.o[ord];
-      b.n_ptr = &u.n;
-      b.max_key = &u.max_key;
-      b.src_records = nullptr;
-      b.pairs_in = nullptr;
-      b.pairs_out = nullptr;
-      b.tile_hist = u.hist.data();
-      b.bin_total = u.bins.data();
-      b.pass = 0;
-      b.key_bits_max = key_bits_max;
-      b.max_bits = max_bits;
-      b.src = SRC_PAIRS;
-      A.p0[ord] = u.p0.data();
-      A.p1[ord] = u.p1.data();
-      A.nsets[ord] = (key_bits_max + max_bits - 1) / max_bits;
-      A.f[ord] = a;
-      A.f[ord].p0 = u.p0.data();
-      A.f[ord].p1 = u.p1.data();
-      A.f[ord].max_key = &u.max_key;
-      A.f[ord].n_ptr = &u.n;
-    }
-    // ordering 1 of the launch is an empty ordering: exercises the "nothing to do" branches next to a real one
-    static uint32_t zero = 0;
-    std::vector<uint32_t> segk(2), sego(2), nseg1(1);
-    A.o[1].n_ptr = &zero;
-    A.f[1].n_ptr = &zero;
-    A.f[1].seg_key = segk.data();
-    A.f[1].seg_off = sego.data();
-    A.f[1].n_seg = nseg1.data();
-    A.f[1].head_surv = nullptr;
-    A.f[1].head_name = nullptr;
-    uint32_t gbar[4] = {0, 0, 0, 0};
-    A.gbar = gbar;
-    if (max_bits != RADIX_MAX_BITS) return -2;
-    emu_launch(k_order_all, dim3(1), KVG_BLOCK, A);
-    const uint32_t npu = radix_plan(u.max_key, key_bits_max, 0, max_bits).npass;
-    memcpy(pairs_io, (((npu - 1) & 1) ? u.p1 : u.p0).data(), sizeof(uint2) * n);
-    return (int)ctrl.n_groups;
-  }
   if (fused) {
     emu_launch(k_order_final, dim3((unsigned)T, 1), KVG_BLOCK, ff, 9u);
   } else {

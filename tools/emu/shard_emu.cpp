@@ -48,6 +48,7 @@ static int run(const uint4* const* lists, const uint32_t* n, uint32_t P, uint32_
       A.ticket = cnt[r].data() + 32;
       A.T = (uint32_t)T;
       A.P = P;
+      A.Pm = shard_magic(P);
       A.me = r;
       A.only = local_mode ? r : SH_ALL;
       A.n_src = n_src;
@@ -56,8 +57,8 @@ static int run(const uint4* const* lists, const uint32_t* n, uint32_t P, uint32_
       A.parity = step & 1;
       A.step = step;
       emu_launch(k_shard_send<U>, dim3((unsigned)T), KVG_BLOCK, A, peers, (const ShardCtrl*)&ctrl[r], &err, 100u + step);
-      if (cnt[r][32] != 0) return -3;  // the ticket resets itself
     }
+    for (int pass = 0; pass < 2; pass++)  // every rank publishes, then every rank gathers
     for (uint32_t r = 0; r < P; r++) {
       uint32_t nn = n[r];
       const size_t T = (n[r] + C_TILE - 1) / C_TILE + 1;
@@ -69,6 +70,7 @@ static int run(const uint4* const* lists, const uint32_t* n, uint32_t P, uint32_
       A.ticket = cnt[r].data() + 32;
       A.T = (uint32_t)T;
       A.P = P;
+      A.Pm = shard_magic(P);
       A.me = r;
       A.only = local_mode ? r : SH_ALL;
       A.n_src = n_src;
@@ -84,7 +86,11 @@ static int run(const uint4* const* lists, const uint32_t* n, uint32_t P, uint32_
       G.n_own = n_own_out + 2 * r;
       max_out[2 * r] = max_out[2 * r + 1] = 0;
       G.max_key = max_out + 2 * r;
-      emu_launch(k_shard_gather<U>, dim3(3, 2), KVG_BLOCK, A, G, peers, (const ShardCtrl*)&ctrl[r], &err);
+      if (pass == 0) {
+        emu_launch(k_shard_gather<U>, dim3(1, 1), KVG_BLOCK, A, G, peers, (const ShardCtrl*)&ctrl[r], &err, 1u);  // publish
+        continue;
+      }
+      emu_launch(k_shard_gather<U>, dim3(3, 2), KVG_BLOCK, A, G, peers, (const ShardCtrl*)&ctrl[r], &err, 2u);
       if (cnt[r][33] != 0) return -4;
     }
   }
@@ -121,6 +127,7 @@ static int run_fused(const uint4* const* recs, const uint32_t* n, uint32_t P, ui
     A.ticket = cnt[r].data() + 32;
     A.T = 0;
     A.P = P;
+    A.Pm = shard_magic(P);
     A.me = r;
     A.only = SH_ALL;
     A.n_src = P;
@@ -145,9 +152,9 @@ static int run_fused(const uint4* const* recs, const uint32_t* n, uint32_t P, ui
       op.local_max_dev = 0;
       emu_launch(k_classify_send<PciClassifyOp, TH, ROWS, CW4>, dim3((unsigned)tiles), TH, op, args(r, step), peers,
                  (const ShardCtrl*)&ctrl[r], &err, words[r].data(), 40u + step);
-      if (cnt[r][32] != 0) return -3;
       n_surv_out[r] = sc[r].n_surv;
     }
+    for (int pass = 0; pass < 2; pass++)
     for (uint32_t r = 0; r < P; r++) {
       const size_t owned_cap = (size_t)P * cap;
       GatherArgs G;
@@ -157,7 +164,11 @@ static int run_fused(const uint4* const* recs, const uint32_t* n, uint32_t P, ui
       G.n_own = n_own_out + 2 * r;
       max_out[2 * r] = max_out[2 * r + 1] = 0;
       G.max_key = max_out + 2 * r;
-      emu_launch(k_shard_gather<U>, dim3(3, 2), KVG_BLOCK, args(r, step), G, peers, (const ShardCtrl*)&ctrl[r], &err);
+      if (pass == 0) {
+        emu_launch(k_shard_gather<U>, dim3(1, 1), KVG_BLOCK, args(r, step), G, peers, (const ShardCtrl*)&ctrl[r], &err, 1u);
+        continue;
+      }
+      emu_launch(k_shard_gather<U>, dim3(3, 2), KVG_BLOCK, args(r, step), G, peers, (const ShardCtrl*)&ctrl[r], &err, 2u);
       if (cnt[r][33] != 0) return -4;
     }
   }
