@@ -221,6 +221,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the config-3 / config-5 legs")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: transport of the exchange by owner — stores into the owners' peer windows over NVLink "
+                         "(default), or the NCCL fallback a deployment without peer access gets")
     ap.add_argument("--config4", action="store_true",
                     help="run the config-4 leg (12 M PCI + 0.5 M mdev records per rank) at any N > 1, not only at N = 8")
     ap.add_argument("--big-records", type=int, default=1 << 24,
@@ -277,7 +280,7 @@ def main():
             outs = [torch.empty_like(t) for _ in range(world)]
             dist.all_gather(outs, t)
             return [bytes(o.cpu().numpy().tobytes()) for o in outs]
-        use_p2p = os.environ.get("KVG_P2P", "1") != "0"
+        use_p2p = args.exchange == "p2p"
         run_c4 = not args.no_extra and (world == 8 or args.config4)
         c4_pci, c4_mdev = (12_000_000, 500_000) if run_c4 else (0, 0)
         sharded = kvgpu.ShardedScan(ctx, rank, world, bcast, allgather if use_p2p else None,

@@ -117,10 +117,6 @@ __host__ __device__ __forceinline__ uint32_t k1_bit_off(uint32_t t) {
 __device__ __forceinline__ uint32_t k1_header_key(const uint8_t* sm, uint32_t p) {
   return ((p + 1) << 17) | parse_hex4(sm + p);
 }
-// the same, out of line: the scan kernel tests ~110 line starts per span and ~6 of them are headers — one shared
-// copy of the hex parse instead of one per unrolled call site keeps the hot loop inside the instruction cache
-// (no_inst stalls were 11 % of the kernel's samples with the parse inlined ten times)
-__device__ __noinline__ uint32_t k1_header_key_cold(const uint8_t* sm, uint32_t p) { return k1_header_key(sm, p); }
 
 // A span whose tail lies beyond EOF (the last span of an image): padding bytes become 0 in shared memory, so
 // that no mask needs an EOF case (the one remaining rule — a '\n' that is the file's LAST byte is counted but
@@ -209,9 +205,10 @@ __device__ __noinline__ void k1_record_lines(const uint8_t* sm, uint32_t* dev_of
 #ifndef KVG_K1_MINCTAS
 #define KVG_K1_MINCTAS 1
 #endif
-#ifndef KVG_K1_CELLS
-#define KVG_K1_CELLS 1
+#ifndef KVG_K1_UNROLL
+#define KVG_K1_UNROLL 4  // rows of a span unrolled in the scan loop (measured at 256 images: 1 -> 65.1 %, 2 -> 66.3 %, 4 -> 68.1 % of the HBM peak)
 #endif
+constexpr int K1_UNROLL = KVG_K1_UNROLL;
 __global__ void __launch_bounds__(K1_WARPS * 32, KVG_K1_MINCTAS) k_pciids_scan(K1Args A) {
   pdl_enter();
 #ifndef KVG_HOST_EMU
@@ -260,27 +257,18 @@ __global__ void __launch_bounds__(K1_WARPS * 32, KVG_K1_MINCTAS) k_pciids_scan(K
     const bool full = a + K1_SPAN < A.len;  // every byte of the span and its successor lie inside the file
     if (!full) k1_patch_eof(sm, a, A.len, lane);
 
-    uint32_t ls[K1_ROWS];
     uint32_t n_nl = 0, any = 0;
-#pragma unroll
-    for (uint32_t r = 0; r < K1_ROWS; r++) {
-      const uint4 va = *reinterpret_cast<const uint4*>(sm + r * 1024 + lane * 16);
-      const uint4 vb = *reinterpret_cast<const uint4*>(sm + r * 1024 + 512 + lane * 16);
-      ls[r] = k1_row_mask(va, vb);
-      n_nl += (uint32_t)__popc(ls[r]);
-      any |= ls[r];
-    }
-    if (!full) {  // a '\n' that is the file's last byte is counted but starts no line
+    const bool extra = j == 0 && lane == 0 && A.len > 0;  // the line at offset 0 of the image
+    // a '\n' that is the file's last byte is counted but starts no line: its row and mask bit (this lane's, else none)
+    uint32_t eof_row = K1_ROWS, eof_bit = 0;
+    if (!full) {
       const uint32_t q = A.len - 1 - a;  // span-relative position of the last byte (< K1_SPAN)
-      const uint32_t r = q >> 10, h = (q >> 9) & 1u, l = (q >> 4) & 31u, o = q & 15u;
+      const uint32_t h = (q >> 9) & 1u, l = (q >> 4) & 31u, o = q & 15u;
       if (l == lane) {
-        const uint32_t t = ((o & 3u) << 3) | (h << 2) | (o >> 2);
-#pragma unroll
-        for (uint32_t rr = 0; rr < K1_ROWS; rr++)
-          if (rr == r) ls[rr] &= ~(1u << t);
+        eof_row = q >> 10;
+        eof_bit = 1u << (((o & 3u) << 3) | (h << 2) | (o >> 2));
       }
     }
-    const bool extra = j == 0 && lane == 0 && A.len > 0;  // the line at offset 0 of the image
 
     // header-type lines: first byte of every line start
     uint32_t last_key = 0, first_hdr = P_NONE;
@@ -299,7 +287,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32, KVG_K1_MINCTAS) k_pciids_scan(K
     const uint8_t* cell = sm + lane * 16;
     auto header_at = [&](uint32_t po) {  // a header-type line starts at cell + po
       const uint32_t p = po + lane * 16;
-      const uint32_t k = k1_header_key_cold(sm, p);
+      const uint32_t k = k1_header_key(sm, p);
       last_key = max(last_key, k);  // mask bits are not in position order: keys carry the position
       first_hdr = min(first_hdr, p);
       if ((k & 0x1ffffu) == K1_VALID_10DE) {
@@ -307,40 +295,35 @@ __global__ void __launch_bounds__(K1_WARPS * 32, KVG_K1_MINCTAS) k_pciids_scan(K
         atomicMax(&A.info[f].pad[0], ~(a + p));
       }
     };
-#if KVG_K1_CELLS
-    // A lane's row is two 16-byte cells and a 16-byte cell rarely holds more than one line start (the shortest
-    // lines of the file are about that long).  The FIRST line start of each of the 8 cells is handled without a
-    // loop — eight independent chains (find bit -> offset -> first byte), all in flight together; what is left
-    // (a cell with two or more newlines) goes through the loop below.
-#pragma unroll
+    // One row (1 KiB) per iteration: the row's mask is consumed where it is made (51 registers instead of 72 when
+    // the four masks were kept for a second loop).  Fully unrolled by default: instruction-level parallelism across
+    // rows beats the smaller code (11 % of the samples are instruction-cache misses either way).
+#pragma unroll K1_UNROLL
     for (uint32_t r = 0; r < K1_ROWS; r++) {
+      const uint4 va = *reinterpret_cast<const uint4*>(sm + r * 1024 + lane * 16);
+      const uint4 vb = *reinterpret_cast<const uint4*>(sm + r * 1024 + 512 + lane * 16);
+      uint32_t ls = k1_row_mask(va, vb);
+      n_nl += (uint32_t)__popc(ls);
+      any |= ls;
+      if (r == eof_row) ls &= ~eof_bit;
+      // A lane's row is two 16-byte cells and a 16-byte cell rarely holds more than one line start (the shortest
+      // lines of the file are about that long).  The FIRST line start of each cell is handled without a loop —
+      // independent chains (find bit -> offset -> first byte) in flight together; what is left (a cell with two
+      // or more newlines) goes through the loop below.
       uint32_t rest = 0;
 #pragma unroll
       for (uint32_t h = 0; h < 2; h++) {
-        const uint32_t m = ls[r] & (h ? 0xF0F0F0F0u : 0x0F0F0F0Fu);  // mask bit 8b + k: k < 4 is the first cell
+        const uint32_t m = ls & (h ? 0xF0F0F0F0u : 0x0F0F0F0Fu);  // mask bit 8b + k: k < 4 is the first cell
         const uint32_t t = (uint32_t)__ffs((int)(m | 0x80000000u)) - 1;  // m == 0: any valid index
         const uint32_t po = r * 1024 + s_off[t];
         const uint32_t b0 = cell[po];
         if (m != 0 && b0 != '\t' && b0 != '#') header_at(po);
         rest |= m & (m - 1);
       }
-      ls[r] = rest;
-    }
-#endif
-#pragma unroll
-    for (uint32_t r = 0; r < K1_ROWS; r++) {
-      // two line starts per round: their first bytes are fetched together (the loop is a chain of dependent
-      // shared-memory loads)
-      for (uint32_t mm = ls[r]; mm;) {
-        const uint32_t t0 = (uint32_t)__ffs(mm) - 1;
-        mm &= mm - 1;
-        const bool two = mm != 0;
-        const uint32_t t1 = two ? (uint32_t)__ffs(mm) - 1 : t0;
-        mm &= mm - 1;
-        const uint32_t po0 = r * 1024 + s_off[t0], po1 = r * 1024 + s_off[t1];
-        const uint32_t b0 = cell[po0], b1 = cell[po1];
-        if (b0 != '\t' && b0 != '#') header_at(po0);
-        if (two && b1 != '\t' && b1 != '#') header_at(po1);
+      for (uint32_t mm = rest; mm; mm &= mm - 1) {
+        const uint32_t po = r * 1024 + s_off[(uint32_t)__ffs(mm) - 1];
+        const uint32_t b0 = cell[po];
+        if (b0 != '\t' && b0 != '#') header_at(po);
       }
     }
     last_key = warp_max(last_key);
@@ -501,16 +484,35 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_resolve_finalize(K1Args A)
 // nv_index[id] = slot (= line offset - v_off) and, warp-cooperatively, its sanitised name at pool + slot
 // (u16 length + bytes); every other id publishes NONE, so nv_index never needs clearing.  Counts the ids
 // recorded.  Every slot read is reset (the table is self-cleaning), the tables of the other images included.
-// Launch with K1_IDS / 32 warps.
+// Launch with K1_NAME_CTAS CTAs (image 0), plus any number of further CTAs that only reset the tables of the
+// other images.
+constexpr uint32_t K1_NAME_CTAS = K1_IDS / 32 / KVG_WARPS;
 __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_names(uint32_t* __restrict__ dev_off, uint32_t n_files,
                                                             const uint8_t* __restrict__ text, uint32_t len,
                                                             PciIdsInfo* __restrict__ info,
                                                             uint32_t* __restrict__ nv_index,
                                                             uint8_t* __restrict__ pool) {
   pdl_enter();
+  if (blockIdx.x >= K1_NAME_CTAS) {
+    // the tables of images 1 .. n_files - 1 (throughput runs parse many images; nothing reads their slots)
+    uint4* rest = reinterpret_cast<uint4*>(dev_off + K1_IDS);
+    const size_t rest16 = (size_t)(n_files - 1) * (K1_IDS / 4);
+    const size_t nth = (size_t)(gridDim.x - K1_NAME_CTAS) * KVG_BLOCK;
+    const uint4 none = make_uint4(P_NONE, P_NONE, P_NONE, P_NONE);
+    for (size_t i0 = (size_t)(blockIdx.x - K1_NAME_CTAS) * KVG_BLOCK + threadIdx.x; i0 < rest16; i0 += 4 * nth) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)  // four loads in flight per thread
+        v[u] = i0 + u * nth < rest16 ? rest[i0 + u * nth] : none;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if ((v[u].x & v[u].y & v[u].z & v[u].w) != P_NONE) rest[i0 + u * nth] = none;
+    }
+    return;
+  }
   const uint32_t V = info->v_off, E = info->sec_end;
   const uint32_t lane = lane_id();
-  const uint32_t n_warps = gridDim.x * KVG_WARPS;
+  const uint32_t n_warps = K1_NAME_CTAS * KVG_WARPS;
   const uint32_t w = blockIdx.x * KVG_WARPS + warp_id();
   const uint32_t id = lane * n_warps + w;
   const uint32_t off = id < K1_IDS ? dev_off[id] : P_NONE;
@@ -522,14 +524,6 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_pciids_names(uint32_t* __restrict
   for (uint32_t todo = __ballot_sync(KVG_FULL, ok); todo; todo &= todo - 1) {
     const uint32_t slot = __shfl_sync(KVG_FULL, off, (uint32_t)__ffs(todo) - 1) - V;
     sanitise_line_warp(text, len, V + slot + 5, pool + slot, lane);  // first byte after "\t" + 4 hex
-  }
-  // the tables of images 1 .. n_files - 1 (throughput runs parse many images; nothing reads their slots)
-  uint4* rest = reinterpret_cast<uint4*>(dev_off + K1_IDS);
-  const size_t rest16 = (size_t)(n_files - 1) * (K1_IDS / 4);
-  const uint4 none = make_uint4(P_NONE, P_NONE, P_NONE, P_NONE);
-  for (size_t i = (size_t)blockIdx.x * KVG_BLOCK + threadIdx.x; i < rest16; i += (size_t)gridDim.x * KVG_BLOCK) {
-    const uint4 v = rest[i];
-    if ((v.x & v.y & v.z & v.w) != P_NONE) rest[i] = none;
   }
 }
 

@@ -1,8 +1,8 @@
-"""csrc/kvg_parse_k1.cuh — K1, the pci.ids parse (prep -> scan with the per-warp TMA ring -> resolve +
-finalize) — executed on the CPU from its REAL kernel source under the warp emulator (tools/emu/) and
-compared with the oracle and with the Python model of the span decomposition (tools/parse_v2_model.py:
-same spans, same ownership rule, same section / scanner-limit arithmetic).  Scratch buffers are
-poisoned (the prep kernel must clear what the parse relies on) and the persistent scan kernel runs
+"""csrc/kvg_parse_k1.cuh — K1, the pci.ids parse (scan with the per-warp TMA ring -> resolve + finalize ->
+names, self-cleaning: no clearing launch) — executed on the CPU from its REAL kernel source under the warp emulator (tools/emu/) and
+compared with the oracle and with the Python model of the span decomposition (tools/span_model.py:
+same spans, same ownership rule, same section / scanner-limit arithmetic).  Output buffers are
+poisoned where the kernels write them whole, and the persistent scan kernel runs
 with several grid sizes so that the two-stage ring is exercised over many iterations per warp."""
 import ctypes as C
 import os
@@ -18,7 +18,7 @@ from oracle import oracle as O
 sys.path.insert(0, os.path.join(conftest.ROOT, "tools"))
 sys.path.insert(0, os.path.join(conftest.ROOT, "tools", "emu"))
 import build as emu_build  # noqa: E402
-import parse_v2_model as M  # noqa: E402
+import span_model as M  # noqa: E402
 from test_gpu_parity import _random_pciids  # noqa: E402
 
 NONE = 0xFFFFFFFF

@@ -1,8 +1,7 @@
-"""The decomposition of the barrier-free parse (tools/parse_v2_model.py: what a span decides alone,
-what it defers, how the deferred part resolves, section bounds from span summaries) against the
-oracle: the shipped pci.ids, the grammar fuzz and the span-boundary / scanner-limit cases the GPU
-parity tests use.  CPU-only; the CUDA twin (csrc/kvg_parse_v2.cuh, KVG_PARSE=v2) is exercised by the
-same GPU parity tests as the default kernel."""
+"""The decomposition of the barrier-free parse K1 (tools/span_model.py: what a span decides alone, what it
+defers, how the deferred part resolves, section bounds from span summaries) against the oracle: the shipped
+pci.ids, the grammar fuzz and the span-boundary / scanner-limit cases the GPU parity tests use.  CPU-only.  The
+model is what tests/test_parse_k1_emu.py compares the kernel's device-id table with, so it is pinned here."""
 import os
 import sys
 
@@ -13,7 +12,7 @@ import util
 from oracle import oracle as O
 
 sys.path.insert(0, os.path.join(conftest.ROOT, "tools"))
-import parse_v2_model as M  # noqa: E402
+import span_model as M  # noqa: E402
 
 from test_gpu_parity import _random_pciids  # noqa: E402  (a pure-Python generator)
 

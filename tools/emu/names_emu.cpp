@@ -36,7 +36,7 @@ static void run_k1(const uint8_t* text, uint64_t stride, uint32_t len, uint32_t 
   if (n_spans) emu_launch(k_pciids_scan, dim3(grid), K1_WARPS * 32, A);
   emu_launch(k_pciids_resolve_finalize, dim3(n_files + (n_spans + K1_RWARPS - 1) / K1_RWARPS), KVG_BLOCK, A);
   if (nv_index)
-    emu_launch(k_pciids_names, dim3(K1_IDS / 32 / KVG_WARPS), KVG_BLOCK, dev_off, n_files, text, len, info, nv_index, pool);
+    emu_launch(k_pciids_names, dim3(K1_NAME_CTAS + (n_files > 1 ? 3 : 0)), KVG_BLOCK, dev_off, n_files, text, len, info, nv_index, pool);
 }
 
 static bool canonical_key(const uint8_t* k, uint32_t n, uint32_t* v) {  // kvg_api.cu: 4 lower-case hex digits
@@ -62,6 +62,14 @@ int emu_parse_k1(const uint8_t* text, uint64_t stride, uint32_t len, uint32_t n_
   run_k1(text, stride, len, n_files, scan_ctas, dev_off.data(), info.data(), nullptr, nullptr, 0);
   memcpy(info_out, info.data(), sizeof(PciIdsInfo) * n_files);
   memcpy(dev_off_out, dev_off.data(), sizeof(uint32_t) * dev_off.size());
+  // the names kernel leaves EVERY image's table clean for the next parse (image 0 by the name CTAs, the others
+  // by the cleaning CTAs)
+  std::vector<uint32_t> nv_index(K1_IDS, 0x77777777u);
+  std::vector<uint8_t> pool(((size_t)len + 16 + 15) & ~(size_t)15, 0);
+  emu_launch(k_pciids_names, dim3(K1_NAME_CTAS + (n_files > 1 ? 3 : 0)), KVG_BLOCK, dev_off.data(), n_files, text, len, info.data(),
+             nv_index.data(), pool.data());
+  for (uint32_t v : dev_off)
+    if (v != P_NONE) return 10;
   return 0;
 }
 

@@ -1,10 +1,11 @@
 #!/usr/bin/env python3
-"""Executable model of the barrier-free pci.ids parse (k_pciids_scan_v2 + k_pciids_resolve_v2).
+"""Executable model of the barrier-free pci.ids parse K1 (k_pciids_scan + k_pciids_resolve_finalize).
 
-The CUDA kernels of csrc/kvg_parse_v2.cuh follow this decomposition step by step; the model exists
+The CUDA kernels of csrc/kvg_parse_k1.cuh follow this decomposition step by step; the model exists
 so that the DECOMPOSITION (what a 4 KiB span decides alone, what it defers, how the deferred part is
 resolved, how the section bounds come out of the span summaries) can be checked against the oracle
-on a CPU-only box (tests/test_parse_v2_model.py).  It is test/tool code, never on the product path.
+on a CPU-only box (tests/test_span_model.py), and so that the emulated kernel's device-id table has
+something to be compared with.  It is test/tool code, never on the product path.
 
   span        4096 text bytes owned by one warp; it owns the lines that START in (a, a + 4096]
               (line start = newline position + 1; the line at offset 0 belongs to span 0)
