@@ -85,6 +85,15 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4)
                           if r[2 + i].lower().startswith("active")})
+        csv_path = os.environ.get("KVG_CLOCKS_CSV")   # evidence: the raw samples behind the medians
+        if csv_path:
+            try:
+                with open(csv_path, "w") as f:
+                    f.write(self.Q + "\n")
+                    for r in self.rows:
+                        f.write(",".join(r) + "\n")
+            except OSError:
+                pass
         return {"sm_mhz": float(np.median(sm)) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm)}

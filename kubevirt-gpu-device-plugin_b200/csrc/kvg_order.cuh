@@ -388,6 +388,12 @@ struct OrdFinalArgs {
   uint32_t* n_seg;           // total heads (written by k_order_final / k_tile_offsets)
   const uint4* head_surv;    // optional: survivors, to publish the joined name slot of each segment
   uint32_t* head_name;       // [n_seg] name slot of the segment's first member (NULL: skip)
+  // deferred name join (the pci.ids parse ran beside the classification, on another stream): while the
+  // permutation is written every record of the list gets its name slot — join 1: nv_index[key] (the ordering's
+  // key IS the device id), join 2: nv_index[device id read from the record]; 0: names were joined at classify time
+  const uint32_t* join_index;
+  uint4* join_recs;
+  uint32_t join;
 };
 struct OrdFinalArgs2 {
   OrdFinalArgs o[2];
@@ -411,7 +417,14 @@ __device__ __forceinline__ uint32_t ord_tile_heads(const OrdFinalArgs& a, const 
       const uint2 e = pairs[i];
       key[k] = e.x;
       idx[k] = e.y;
-      if (write_perm) a.perm[i] = e.y;
+      if (write_perm) {
+        a.perm[i] = e.y;
+        if (a.join == 1)
+          reinterpret_cast<uint32_t*>(a.join_recs + e.y)[3] = __ldg(&a.join_index[e.x & 0xffffu]);
+        else if (a.join == 2)
+          reinterpret_cast<uint32_t*>(a.join_recs + e.y)[3] =
+              __ldg(&a.join_index[reinterpret_cast<const uint32_t*>(a.join_recs + e.y)[2] & 0xffffu]);
+      }
       if (lane == 0 && i) edge = pairs[i - 1].x;
     }
     const uint32_t below = __shfl_up_sync(KVG_FULL, key[k], 1);
@@ -432,7 +445,8 @@ __device__ __forceinline__ void ord_emit_heads(const OrdFinalArgs& a, uint32_t o
       a.seg_key[pos] = key[k];
       a.seg_off[pos] = i;
       // all members of a device-id bucket share the name (same id): take the first member's slot
-      if (a.head_name) a.head_name[pos] = __ldg(&a.head_surv[idx[k]].w);
+      if (a.head_name)  // deferred join: straight from the table (the record's slot may be written by another thread)
+        a.head_name[pos] = a.join ? __ldg(&a.join_index[key[k] & 0xffffu]) : __ldg(&a.head_surv[idx[k]].w);
     }
     off += __popc(bal[k]);
   }

@@ -189,7 +189,8 @@ struct PciClassifyOp {
 
   __device__ __forceinline__ void begin() {}
   // the name join: one load per survivor from the flattened table of vendor 10de
-  __device__ __forceinline__ uint32_t prepare(const Item& r) const { return __ldg(&nv_index[r.y >> 16]); }
+  // (nv_index == NULL: the parse is still running on its own stream; the final ordering kernel joins the names)
+  __device__ __forceinline__ uint32_t prepare(const Item& r) const { return nv_index ? __ldg(&nv_index[r.y >> 16]) : P_NONE; }
   __device__ __forceinline__ uint32_t count() const { return n; }
   __device__ __forceinline__ Item load(uint32_t i, bool ok) const {
     return ok ? ld_stream(recs + i) : make_uint4(0, 0, 0, 0xff00u);
@@ -235,6 +236,18 @@ struct PciClassifyOp {
     return m;
   }
 };
+// the deferred name join of a dense PCI survivor list no ordering walks (the rank's own shard of a sharded scan):
+// runs on the side stream behind the parse, beside the exchange and the orderings
+__global__ void __launch_bounds__(KVG_BLOCK) k_join_names(uint4* __restrict__ recs, const uint32_t* __restrict__ n_ptr,
+                                                          const uint32_t* __restrict__ nv_index) {
+  pdl_enter();
+  const uint32_t n = *n_ptr;
+  for (uint32_t i = blockIdx.x * KVG_BLOCK + threadIdx.x; i < n; i += gridDim.x * KVG_BLOCK) {
+    uint32_t* w = reinterpret_cast<uint32_t*>(recs + i);
+    w[3] = __ldg(&nv_index[w[2] & 0xffffu]);
+  }
+}
+
 // ---- K5: mdev classify --------------------------------------------------------------------------
 struct MdevItem {
   uint4 lo, hi;

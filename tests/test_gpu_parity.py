@@ -209,6 +209,68 @@ def test_orderings_at_key_width_boundaries(kv, loaded, pciids, bits):
     assert got == _pci_dump_oracle(recs, pciids)
 
 
+def test_speculated_pass_sets_are_verified(kv, loaded, pciids):
+    """The number of radix pass sets launched for the wide ordering is speculated from the previous scan's largest
+    key and verified when the control block comes home (ctrl_fetch): a scan whose keys are wider than the previous
+    scan's must re-run its orderings and still match the oracle, through the host entry point and through the
+    device-resident entry point + count."""
+    import torch
+    ids = O.nv_ids(pciids)
+    n = 30_000
+    for bits in (5, 30, 7, 32, 23, 22):
+        recs = O.gen_pci(0, n, ids, 0)
+        rng = np.random.default_rng(bits)
+        recs["iommu_group"] = rng.integers(0, 1 << bits, n, dtype=np.uint64).astype(np.uint32)
+        recs[0] = (0x0100, 0x10de, int(ids[0]), (1 << bits) - 1, 1, 0, 0)
+        got, _ = _pci_dump_gpu(kv, loaded, recs)
+        assert got == _pci_dump_oracle(recs, pciids), bits
+    # device-resident: narrow keys first (the hint), then wide keys; the count call is what verifies
+    for bits in (6, 31):
+        recs = O.gen_pci(0, n, ids, 0)
+        recs["iommu_group"] = np.random.default_rng(bits).integers(0, 1 << bits, n, dtype=np.uint64).astype(np.uint32)
+        recs[0] = (0x0100, 0x10de, int(ids[0]), (1 << bits) - 1, 1, 0, 0)
+        d = torch.from_numpy(np.frombuffer(recs.tobytes(), dtype=np.uint8).copy()).cuda()
+        loaded.dev_scan_pci(d.data_ptr(), n)
+        loaded.dev_scan_pci_count()
+        res = loaded.dev_scan_pci_fetch()
+        assert kv.canonical_dump(kv.pci_maps_from_result(res)) == _pci_dump_oracle(recs, pciids), bits
+        del d
+
+
+def test_scan_beside_a_reparse_on_the_side_stream(kv, pciids):
+    """A re-parse of the published image runs on the context's side stream; the PCI scan that follows classifies and
+    sorts beside it and joins the names in its final kernel.  Results must equal the oracle's, scan after scan, and
+    everything else that needs the table (name lookups, the host entry points, an mdev scan) must wait for it."""
+    import torch
+    ctx = kv.Context(0)
+    try:
+        ids = O.nv_ids(pciids)
+        pad = ctx.text_pad(len(pciids))
+        h = np.full(pad + 16, 10, dtype=np.uint8)
+        h[:len(pciids)] = np.frombuffer(pciids, dtype=np.uint8)
+        d_text = torch.from_numpy(h).cuda()
+        ctx.dev_pciids_parse(d_text.data_ptr(), len(pciids), pad + 16, 1)          # publishes (synchronous)
+        for rep, n in enumerate((50_000, 3, 200_001, 0, 2049)):
+            recs = O.gen_pci(7 * rep, n, ids, 9)
+            d = torch.from_numpy(np.frombuffer(recs.tobytes(), dtype=np.uint8).copy()).cuda() if n else torch.zeros(16, dtype=torch.uint8).cuda()
+            ctx.dev_pciids_parse(d_text.data_ptr(), len(pciids), pad + 16, 1)      # re-parse: side stream
+            ctx.dev_scan_pci(d.data_ptr(), n)
+            res = ctx.dev_scan_pci_fetch()
+            assert kv.canonical_dump(kv.pci_maps_from_result(res)) == _pci_dump_oracle(recs, pciids), (rep, n)
+            del d
+        # a consumer that is not the PCI device scan right after a re-parse
+        ctx.dev_pciids_parse(d_text.data_ptr(), len(pciids), pad + 16, 1)
+        assert ctx.name_lookup(b"1b38") == O.get_device_name(pciids, b"1b38")
+        ctx.dev_pciids_parse(d_text.data_ptr(), len(pciids), pad + 16, 1)
+        recs = O.gen_pci(0, 5000, ids, 0)
+        got, _ = _pci_dump_gpu(kv, ctx, recs)
+        assert got == _pci_dump_oracle(recs, pciids)
+        del d_text
+    finally:
+        torch.cuda.synchronize()
+        ctx.close()
+
+
 @pytest.mark.parametrize("n", [131_072, 131_077, 300_001, 1_048_576 + 1])
 def test_pipelined_host_entry_matches_oracle(kv, loaded, pciids, n):
     """kvg_scan_pci switches to the chunked copy / classify / copy-back pipeline at 128 Ki records:

@@ -76,7 +76,7 @@ def test_whole_ordering_permutation_segments_and_bucket_names(emu):
     k_order_heads<true>): the final permutation, the distinct keys with their segment offsets, and (device-id
     ordering) each bucket's joined name slot."""
     emu.emu_ordering.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_void_p, C.c_int]
+                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     rng = np.random.default_rng(23)
     for n, bits, kmax in ((1, 3, 16), (2048, 6, 16), (4500, 16, 16), (3000, 19, 32), (2500, 25, 32), (0, 1, 32)):
         keys = rng.integers(0, 1 << bits, n, dtype=np.uint64).astype(np.uint32)
@@ -96,9 +96,39 @@ def test_whole_ordering_permutation_segments_and_bucket_names(emu):
             perm[:] = 0xdeadbeef
             seg_key[:] = seg_off[:] = seg_name[:] = 0xdeadbeef
             n_seg = emu.emu_ordering(p2.ctypes.data, n, surv.ctypes.data, kmax, 11, perm.ctypes.data, seg_key.ctypes.data,
-                                     seg_off.ctypes.data, seg_name.ctypes.data, form)
+                                     seg_off.ctypes.data, seg_name.ctypes.data, form, None, 0)
             assert n_seg == len(uniq), (n_seg, form)
             assert np.array_equal(perm[:n], order.astype(np.uint32))
             assert np.array_equal(seg_key[:n_seg], uniq) and np.array_equal(seg_off[:n_seg], first.astype(np.uint32))
             assert int(seg_off[n_seg]) == n
             assert np.array_equal(seg_name[:n_seg], (uniq * 7 + 1) & 0xffff)
+
+
+def test_deferred_name_join_in_the_final_kernel(emu):
+    """The parse may still be running when the scan classifies (side stream): the records then carry no name slot
+    and the final kernel of an ordering joins it while it writes the permutation — by the ordering's key (device-id
+    ordering: join 1) or by the device id read from the record (any other ordering of such records: join 2).  The
+    segment heads take their name straight from the table."""
+    emu.emu_ordering.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(41)
+    table = rng.integers(0, 1 << 20, 65536, dtype=np.uint64).astype(np.uint32)
+    for n, mode, form in ((4500, 1, 1), (4500, 1, 0), (3000, 2, 1), (2049, 2, 0), (1, 1, 1)):
+        dev = rng.integers(0, 700, n, dtype=np.uint64).astype(np.uint32)       # device ids
+        surv = np.zeros((n, 4), dtype=np.uint32)
+        surv[:, 2] = dev | (rng.integers(0, 4, n, dtype=np.uint64).astype(np.uint32) << 16)   # device | numa << 16
+        surv[:, 3] = 0xffffffff                                               # no name yet
+        keys = dev if mode == 1 else rng.integers(0, 1 << 19, n, dtype=np.uint64).astype(np.uint32)
+        pairs = np.zeros(n + 1, dtype=PAIR)
+        pairs["key"][:n], pairs["idx"][:n] = keys, np.arange(n, dtype=np.uint32)
+        perm = np.zeros(n + 1, np.uint32)
+        seg_key, seg_off, seg_name = np.zeros(n + 2, np.uint32), np.zeros(n + 2, np.uint32), np.zeros(n + 2, np.uint32)
+        n_seg = emu.emu_ordering(pairs.ctypes.data, n, surv.ctypes.data, 16 if mode == 1 else 32, 11, perm.ctypes.data,
+                                 seg_key.ctypes.data, seg_off.ctypes.data, seg_name.ctypes.data, form, table.ctypes.data, mode)
+        order = np.argsort(keys, kind="stable")
+        uniq = np.unique(keys)
+        assert n_seg == len(uniq)
+        assert np.array_equal(perm[:n], order.astype(np.uint32))
+        assert np.array_equal(surv[:, 3], table[dev]), (n, mode, form)        # every record joined
+        if mode == 1:
+            assert np.array_equal(seg_name[:n_seg], table[uniq])

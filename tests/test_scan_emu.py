@@ -32,7 +32,7 @@ def libs():
     cls.emu_classify_pci.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     rdx = C.CDLL(emu_build.build_radix())
     rdx.emu_ordering.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
-                                 C.c_void_p, C.c_void_p, C.c_int]
+                                 C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     return names, cls, rdx
 
 
@@ -57,7 +57,7 @@ def ordering(rdx, surv, field, key_bits):
     seg_key, seg_off, seg_name = np.zeros(n + 2, np.uint32), np.zeros(n + 2, np.uint32), np.zeros(n + 2, np.uint32)
     raw = np.ascontiguousarray(surv).view(np.uint32).reshape(-1, 4) if n else np.zeros((1, 4), np.uint32)
     k = rdx.emu_ordering(pairs.ctypes.data, n, raw.ctypes.data, key_bits, 11, perm.ctypes.data, seg_key.ctypes.data,
-                         seg_off.ctypes.data, seg_name.ctypes.data, 1)
+                         seg_off.ctypes.data, seg_name.ctypes.data, 1, None, 0)
     assert k >= 0
     return seg_key[:k].copy(), seg_off[:k + 1].copy(), perm[:n].copy(), seg_name[:k].copy()
 

@@ -76,7 +76,7 @@ int emu_radix_sort(uint2* pairs_io, uint32_t n, uint32_t key_bits_max, uint32_t 
 // k_order_heads<true>.  surv: the survivor records the pairs index (head_name gathers surv[idx].w).
 // Outputs: perm[n], seg_key / seg_off / seg_name [n_seg (+1 for seg_off)]; returns n_seg.
 int emu_ordering(uint2* pairs_io, uint32_t n, const uint4* surv, uint32_t key_bits_max, uint32_t max_bits, uint32_t* perm,
-                 uint32_t* seg_key, uint32_t* seg_off, uint32_t* seg_name, int fused) {
+                 uint32_t* seg_key, uint32_t* seg_off, uint32_t* seg_name, int fused, const uint32_t* join_table, int join_mode) {
   if (max_bits != 8 && max_bits != RADIX_MAX_BITS) return -1;
   Ordering o(pairs_io, n, key_bits_max, max_bits);
   o.sort();
@@ -103,6 +103,11 @@ int emu_ordering(uint2* pairs_io, uint32_t n, const uint4* surv, uint32_t key_bi
   a.n_seg = &ctrl.n_groups;
   a.head_surv = surv;
   a.head_name = seg_name;
+  // join_mode 1 / 2: the deferred name join — `join_table` is the 65,536-entry device-id -> name-slot table and
+  // every record of `surv` gets its slot (word 3) while the permutation is written; 0: names already joined
+  a.join_index = join_table;
+  a.join_recs = const_cast<uint4*>(surv);
+  a.join = join_table ? (uint32_t)join_mode : 0u;
   OrdFinalArgs2 ff;
   ff.o[0] = a;
   ff.o[1] = a;
