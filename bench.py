@@ -560,6 +560,33 @@ def main():
                                           "what": "host wall time from snapshot-in-pinned-buffer to "
                                                   "transition list on the host (H2D 160 KB + K6 + D2H)"}
 
+    # ---- Allocate re-validation = one tiny batch through kvg_scan_pci; latency per request size
+    if world == 1 and not args.no_extra:
+        import ctypes as C
+        lib = kvgpu.load()
+        reval = {}
+        for k in (1, 2, 4, 8, 16):
+            rr = np.zeros(k, dtype=kvgpu.PCI_REC)
+            for i in range(k):
+                rr[i] = (i, 0x10de, 0, i // 2, 1, 0, 0)          # what BatchRevalidator builds: driver pinned, index mode
+            hr = torch.from_numpy(np.frombuffer(rr.tobytes(), dtype=np.uint8).copy()).pin_memory()
+            lat = []
+            for it in range(1050):
+                t0 = time.perf_counter()
+                res = C.POINTER(kvgpu._lib.PciResultC)()
+                rc = lib.kvg_scan_pci(ctx.handle, hr.data_ptr(), k, C.byref(res))
+                dt = time.perf_counter() - t0
+                assert rc == 0 and res.contents.n_survivors == k
+                lib.kvg_result_free(res)
+                if it >= 50:
+                    lat.append(dt)
+            lat = np.array(lat) * 1e6
+            reval[str(k)] = {"p50_us": float(np.percentile(lat, 50)), "p99_us": float(np.percentile(lat, 99))}
+        extra["allocate_revalidation"] = {"devices_per_request": reval, "requests_per_size": 1000,
+                                          "what": "host wall time of one kvg_scan_pci batch of the size an Allocate request "
+                                                  "re-checks (pinned records in, result block out): classify + both "
+                                                  "orderings + fetch"}
+
     # ---- BASELINE.json config 4 as stated: mixed passthrough + vGPU, 100 M records over 8 GPUs
     if world > 1 and run_c4:
         c4_types = O.gen_type_names(256)

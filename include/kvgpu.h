@@ -294,7 +294,12 @@ int kvg_health_reset(kvg_ctx *ctx);
  * kvg_text_pad(len) readable bytes from it, all padding bytes '\n'.  n_files images of `len`
  * bytes each, image f at d_text + f*stride (stride % 16 == 0, stride >= kvg_text_pad(len)+16).
  * Image 0 becomes the context's table; images >= 1 are parsed into scratch tables (batch
- * throughput measurement: every byte is split, every line start classified). */
+ * throughput measurement: every byte is split, every line start classified).
+ * The first call on an image publishes its table (synchronous).  A later call on the SAME single image
+ * re-parses it asynchronously on the context's side stream: it starts when everything enqueued before it
+ * has finished, kvg_dev_scan_pci / kvg_dev_scan_pci_sharded enqueued after it classify and sort beside
+ * it and join the names in their last kernel, every other consumer of the table waits for it first.
+ * d_text must stay valid until the next call on the context that synchronises (any fetch / count). */
 size_t kvg_text_pad(size_t len);
 int kvg_dev_pciids_parse(kvg_ctx *ctx, const void *d_text, size_t len, size_t stride,
                          uint32_t n_files);

@@ -237,35 +237,6 @@ __device__ __forceinline__ uint32_t lookback_sum(uint64_t* state, uint32_t tile,
   return excl;
 }
 
-// ---- published counts: the prefix over ALL earlier tiles without a chain ----------------------------------
-// One 32-bit word per tile: epoch << BITS | count (count < 2^BITS).  A tile publishes its count, then the
-// threads of its CTA sum the words of tiles 0 .. tile-1 themselves — one independent load per thread and tile,
-// spinning on a word until it carries this launch's epoch.  O(T^2) loads from L2 in total: nothing for the
-// ~10^3 tiles of a launch-bound scan, and unlike the chained scan above there is no sequence of dependent
-// round trips when all tiles start together (which is exactly what happens at those sizes).  Every thread of
-// the CTA calls it; `scratch` holds one word per warp.  Returns the exclusive prefix in every thread.
-template <uint32_t BITS>
-__device__ __forceinline__ uint32_t published_prefix(uint32_t* words, uint32_t tile, uint32_t count, uint32_t epoch,
-                                                     uint32_t* scratch) {
-  const uint32_t ep = epoch << BITS, mask = (1u << BITS) - 1;
-  if (threadIdx.x == 0) st_relaxed_u32(&words[tile], ep | count);
-  uint32_t acc = 0;
-  for (uint32_t j = threadIdx.x; j < tile; j += blockDim.x) {
-    uint32_t w;
-    do {
-      w = ld_relaxed_u32(&words[j]);
-    } while ((w & ~mask) != ep);
-    acc += w & mask;
-  }
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  uint32_t total = 0;
-  for (uint32_t w = 0; w < (blockDim.x >> 5); w++) total += scratch[w];
-  __syncthreads();  // scratch may be reused by the caller
-  return total;
-}
-
 // "Last writer wins" look-back (used for the pci.ids vendor context): a tile either defines a new
 // value (publishes INCLUSIVE immediately, no dependence on predecessors) or passes its
 // predecessor's value through.  Returns the value carried INTO `tile`; one full warp executes it.

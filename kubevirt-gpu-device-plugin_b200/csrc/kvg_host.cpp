@@ -249,12 +249,18 @@ int kvgh_get_device_name(kvgh_scan* h, const char* id, size_t idlen, char* out, 
 }
 
 // Snapshot only (exposed so the CPU tests can check it without a GPU): records in Walk order, names
-// as a '\0'-separated blob, interned iommu-group strings likewise.  Free the three with free().
+// as a '\0'-separated blob, interned iommu-group strings likewise.  `device` contents: when every one that was
+// read is "%04x" the records carry the number and the devices blob is empty; otherwise the whole column is in
+// index mode (readIDFromFile returns string(data[2:]) whatever it is, :294-302): the records carry interned ids
+// in first-appearance order and the blob holds the strings.  Free the blobs with free().
 int kvgh_snapshot_pci(const char* base_path, kvg_pci_rec** recs_out, size_t* n_out, char** names_out,
-                      size_t* names_len, char** groups_out, size_t* groups_len) {
+                      size_t* names_len, char** groups_out, size_t* groups_len, char** devices_out,
+                      size_t* devices_len) {
   std::string base = base_path;
   std::vector<kvg_pci_rec> recs;
   std::string names, groups;
+  std::vector<std::string> dev_str;  // per record: what the `device` file held ("" = not read / unreadable)
+  std::vector<bool> dev_read;
   std::unordered_map<std::string, uint32_t> gid;
   bool panic = false;
   walk(base, [&](const std::string& name, bool is_dir) {
@@ -264,6 +270,7 @@ int kvgh_snapshot_pci(const char* base_path, kvg_pci_rec** recs_out, size_t* n_o
     r.addr = (uint32_t)recs.size();  // index mode
     r.vendor = 0xffff;
     std::string vendor, driver, group, device;
+    bool have_dev = false;
     int vrc = read_id(base, name, "vendor", &vendor);  // :202
     if (vrc == 2) {
       panic = true;
@@ -299,23 +306,49 @@ int kvgh_snapshot_pci(const char* base_path, kvg_pci_rec** recs_out, size_t* n_o
               panic = true;
               return false;
             }
-            uint16_t hd;
-            if (drc)
-              r.flags |= KVG_PF_DEVICE_ERR;
-            else if (hex4(device, &hd))
-              r.device = hd;
-            else
-              r.flags |= KVG_PF_DEVICE_ERR;  // not representable; real sysfs prints 0x%04x
+            if (drc) r.flags |= KVG_PF_DEVICE_ERR;
+            have_dev = !drc;
           }
         }
       }
     }
+    dev_read.push_back(have_dev);
+    dev_str.push_back(have_dev ? device : std::string());
     recs.push_back(r);
     names.append(name);
     names.push_back('\0');
     return true;
   });
   if (panic) return KVGH_EPANIC;
+  std::string devices;
+  {
+    bool numeric = true;
+    uint16_t hd;
+    for (size_t i = 0; i < recs.size(); i++)
+      if (dev_read[i] && !hex4(dev_str[i], &hd)) numeric = false;
+    std::unordered_map<std::string, uint32_t> did;
+    for (size_t i = 0; i < recs.size(); i++) {
+      if (!dev_read[i]) continue;
+      if (numeric) {
+        hex4(dev_str[i], &hd);
+        recs[i].device = hd;
+      } else {
+        auto it = did.find(dev_str[i]);
+        if (it == did.end()) {
+          if (did.size() > 0xffff) return KVG_ERANGE;  // more than 65,536 distinct non-canonical strings
+          it = did.emplace(dev_str[i], (uint32_t)did.size()).first;
+          devices.append(dev_str[i]);
+          devices.push_back('\0');
+        }
+        recs[i].device = (uint16_t)it->second;
+      }
+    }
+  }
+  if (devices_out) {
+    *devices_out = (char*)malloc(devices.size() + 1);
+    memcpy(*devices_out, devices.data(), devices.size());
+    *devices_len = devices.size();
+  }
   *n_out = recs.size();
   *recs_out = (kvg_pci_rec*)malloc(std::max<size_t>(1, recs.size()) * sizeof(kvg_pci_rec));
   memcpy(*recs_out, recs.data(), recs.size() * sizeof(kvg_pci_rec));
@@ -347,11 +380,12 @@ int kvgh_create_iommu_device_map(kvgh_scan* h) {
   int rc = ensure_table(s);
   if (rc) return rc;
   kvg_pci_rec* recs = nullptr;
-  size_t n = 0, nl = 0, gl = 0;
-  char *nb = nullptr, *gb = nullptr;
-  rc = kvgh_snapshot_pci(s->base_path.c_str(), &recs, &n, &nb, &nl, &gb, &gl);
+  size_t n = 0, nl = 0, gl = 0, dl = 0;
+  char *nb = nullptr, *gb = nullptr, *db = nullptr;
+  rc = kvgh_snapshot_pci(s->base_path.c_str(), &recs, &n, &nb, &nl, &gb, &gl, &db, &dl);
   if (rc) return rc;
-  std::vector<std::string> names = split0(nb, nl), groups = split0(gb, gl);
+  std::vector<std::string> names = split0(nb, nl), groups = split0(gb, gl), devices = split0(db, dl);
+  free(db);
   kvg_pci_result* res = nullptr;
   rc = kvg_scan_pci(s->ctx, recs, n, &res);
   free(recs);
@@ -363,11 +397,24 @@ int kvgh_create_iommu_device_map(kvgh_scan* h) {
   }
   auto dev = [&](uint32_t i) { return Dev{names[res->survivors[i].addr], (long long)res->survivors[i].numa}; };
   for (uint32_t k = 0; k < res->n_dev_keys; k++) {
-    char key[8];
-    snprintf(key, sizeof key, "%04x", res->dev_keys[k]);
+    std::string key;
+    if (devices.empty()) {
+      char hex[8];
+      snprintf(hex, sizeof hex, "%04x", res->dev_keys[k]);
+      key = hex;
+    } else {
+      key = devices[res->dev_keys[k]];  // index mode: the id is a handle, the key is the string itself
+    }
     auto& v = s->deviceMap[key];
     for (uint32_t j = res->dev_off[k]; j < res->dev_off[k + 1]; j++) v.push_back(dev(res->dev_perm[j]));  // :240
-    s->deviceNames[key] = pool_name(res, res->dev_name_slot[k]);                                     // :124
+    if (devices.empty()) {
+      s->deviceNames[key] = pool_name(res, res->dev_name_slot[k]);                                   // :124
+    } else {  // getDeviceName with the exact bytes (prefix semantics and all)
+      char name[512];
+      size_t nlen = 0;
+      int lrc = kvg_name_lookup(s->ctx, key.data(), key.size(), name, sizeof name, &nlen);
+      s->deviceNames[key] = lrc == KVG_OK ? std::string(name, nlen) : std::string();
+    }
   }
   for (uint32_t k = 0; k < res->n_groups; k++) {
     auto& v = s->iommuMap[groups[res->grp_keys[k]]];

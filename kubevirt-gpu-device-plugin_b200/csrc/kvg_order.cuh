@@ -373,8 +373,6 @@ __global__ void __launch_bounds__(KVG_BLOCK, OrdScatterCfg<MAXB>::MIN_CTAS) k_or
 }
 
 // ---- final permutation + distinct keys of both orderings ------------------------------------------
-constexpr uint32_t OF_COUNT_BITS = 12;  // a tile has at most 2048 heads
-static_assert(C_TILE < (1u << OF_COUNT_BITS), "head count field");
 struct OrdFinalArgs {
   const uint2* p0;  // ping-pong buffers of the radix passes
   const uint2* p1;
@@ -382,8 +380,7 @@ struct OrdFinalArgs {
   uint32_t key_bits_max, max_bits;
   const uint32_t* n_ptr;
   uint32_t* perm;            // [n] survivor indices in key order (stable)
-  uint64_t* state;           // k_tile_offsets: chained scan of the chunk totals (epoch-tagged)
-  uint32_t* words;           // k_order_final: [tiles] published head counts (epoch << OF_COUNT_BITS | count)
+  uint64_t* state;           // k_order_final: [tiles] chained scan of the head counts (epoch-tagged)
   uint32_t* tile_heads;      // k_order_heads: [T] number of segment heads in each tile
   const uint32_t* tile_off;  // k_order_heads<true>: [T+1] exclusive scan of tile_heads
   uint32_t* seg_key;
@@ -455,8 +452,7 @@ __device__ __forceinline__ void ord_emit_heads(const OrdFinalArgs& a, uint32_t o
   }
 }
 
-// latency-bound sizes: one launch; every tile publishes its head count and sums the counts of the earlier tiles
-// itself (published_prefix: no chain of dependent round trips when all tiles start together).
+// latency-bound sizes: one launch; the per-tile head counts are combined by a chained scan (look-back).
 // Tile loop: the grid may be smaller than the tile count (the sharded scan sizes it for the EXPECTED length of
 // an owned list, not for its capacity) — it must then fit the GPU at once (a CTA waits for lower tiles, which
 // must be running or done: enqueue_orderings bounds the grid by the occupancy).
@@ -474,26 +470,34 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_order_final(OrdFinalArgs2 aa, uin
   }
   const uint2* pairs = ord_final_buf(a);
   const uint32_t lane = lane_id(), warp = warp_id();
-  __shared__ uint32_t s_w[KVG_WARPS], s_scr[KVG_WARPS];
+  __shared__ uint32_t s_w[KVG_WARPS];
+  __shared__ uint32_t s_base;
   for (uint32_t tile = blockIdx.x; tile < T; tile += gridDim.x) {
     const uint32_t base = tile * C_TILE + warp * C_WARP_ITEMS;
     uint32_t bal[C_ROWS], key[C_ROWS], idx[C_ROWS];
     const uint32_t wtot = ord_tile_heads(a, pairs, n, base, lane, true, bal, key, idx);
     if (lane == 0) s_w[warp] = wtot;
     __syncthreads();
-    uint32_t t = 0, off = 0;
+    if (warp == 0) {
+      uint32_t t = 0;
 #pragma unroll
-    for (uint32_t w = 0; w < KVG_WARPS; w++) {
+      for (uint32_t w = 0; w < KVG_WARPS; w++) t += s_w[w];
+      const uint32_t excl = lookback_sum(a.state, tile, t, epoch);
+      if (lane == 0) {
+        s_base = excl;
+        if (tile == T - 1) {
+          *a.n_seg = excl + t;
+          a.seg_off[excl + t] = n;
+        }
+      }
+    }
+    __syncthreads();
+    uint32_t off = s_base;
+#pragma unroll
+    for (uint32_t w = 0; w < KVG_WARPS; w++)
       if (w < warp) off += s_w[w];
-      t += s_w[w];
-    }
-    // heads of all earlier tiles: every tile publishes its count and sums the earlier ones itself (no chain)
-    const uint32_t excl = published_prefix<OF_COUNT_BITS>(a.words, tile, t, epoch, s_scr);
-    if (tile == T - 1 && threadIdx.x == 0) {
-      *a.n_seg = excl + t;
-      a.seg_off[excl + t] = n;
-    }
-    ord_emit_heads(a, excl + off, base, lane, bal, key, idx);  // (published_prefix ends with a block barrier: s_w is free)
+    ord_emit_heads(a, off, base, lane, bal, key, idx);
+    __syncthreads();  // s_w / s_base are rewritten by the next tile
   }
 }
 

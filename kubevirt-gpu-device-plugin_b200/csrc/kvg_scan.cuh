@@ -107,16 +107,18 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_compact(Op op, uint64_t* tile_sta
 // of them, dispatched in blockIdx order by the hardware.  Many resident CTAs per SM hide the
 // count -> look-back -> write-out latency chain of each other; predecessors were dispatched
 // earlier, so the classic decoupled look-back usually finds an inclusive prefix close by.
+// (Measured alternative, round 2: every tile publishes its count and sums ALL earlier counts itself, a thread
+// per earlier tile — no chain, but 8 dependent L2 round trips per thread for the last tiles: 20.1 vs 14.9 us,
+// config-2 step 0.108 vs 0.097 ms.  The chained scan stays.)
 // ------------------------------------------------------------------------------------------------
-constexpr uint32_t CO_COUNT_BITS = 11;  // a tile has at most 1024 survivors
 template <class Op, int THREADS, int ROWS>
-__global__ void __launch_bounds__(THREADS) k_classify_oneshot(Op op, uint32_t* tile_words, uint32_t epoch) {
+__global__ void __launch_bounds__(THREADS) k_classify_oneshot(Op op, uint64_t* tile_state, uint32_t epoch) {
   pdl_enter();
   constexpr uint32_t TILE = THREADS * ROWS;
   constexpr uint32_t NW = THREADS / 32;
   constexpr uint32_t WARP_ITEMS = 32 * ROWS;
-  static_assert(TILE < (1u << CO_COUNT_BITS), "survivor count field");
-  __shared__ uint32_t s_wtot[NW], s_scr[NW];
+  __shared__ uint32_t s_wtot[NW], s_woff[NW];
+  __shared__ uint32_t s_base;
   op.begin();
   const uint32_t n = op.count();
   const uint32_t n_tiles = (n + TILE - 1) / TILE;
@@ -146,16 +148,19 @@ __global__ void __launch_bounds__(THREADS) k_classify_oneshot(Op op, uint32_t* t
   }
   if (lane == 0) s_wtot[warp] = wtot;
   __syncthreads();
-  uint32_t tile_total = 0, woff = 0;
-#pragma unroll
-  for (uint32_t w = 0; w < NW; w++) {
-    if (w < warp) woff += s_wtot[w];
-    tile_total += s_wtot[w];
+  if (warp == 0) {
+    uint32_t w = lane < NW ? s_wtot[lane] : 0;
+    uint32_t wi = warp_incl_sum(w);
+    if (lane < NW) s_woff[lane] = wi - w;
+    uint32_t tile_total = __shfl_sync(KVG_FULL, wi, NW - 1);
+    uint32_t excl = lookback_sum(tile_state, tile, tile_total, epoch);
+    if (lane == 0) {
+      s_base = excl;
+      if (tile == n_tiles - 1) op.finish(excl + tile_total);
+    }
   }
-  // survivors of all earlier tiles: every tile publishes its count and sums the earlier ones itself (no chain)
-  const uint32_t excl = published_prefix<CO_COUNT_BITS>(tile_words, tile, tile_total, epoch, s_scr);
-  if (tile == n_tiles - 1 && threadIdx.x == 0) op.finish(excl + tile_total);
-  uint32_t off = excl + woff;
+  __syncthreads();
+  uint32_t off = s_base + s_woff[warp];
 #pragma unroll
   for (int k = 0; k < ROWS; k++) {
     uint32_t i = base + k * 32 + lane;

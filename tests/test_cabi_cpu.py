@@ -144,6 +144,7 @@ def _host_lib():
     L = C.CDLL(path)
     L.kvgh_snapshot_pci.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
+                                    C.POINTER(C.c_void_p), C.POINTER(C.c_size_t),
                                     C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.kvgh_free.argtypes = [C.c_void_p]
     L.kvgh_create.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]
@@ -156,7 +157,7 @@ def _native_snapshot(base):
     L = _host_lib()
     recs, n, names, nl, groups, gl = C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t(), C.c_void_p(), C.c_size_t()
     rc = L.kvgh_snapshot_pci(base.encode(), C.byref(recs), C.byref(n), C.byref(names), C.byref(nl),
-                             C.byref(groups), C.byref(gl))
+                             C.byref(groups), C.byref(gl), None, None)
     if rc != 0:
         return rc, None, None, None
     arr = np.frombuffer(C.string_at(recs, n.value * 16), dtype=kvgpu.PCI_REC).copy()

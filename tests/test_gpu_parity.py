@@ -455,6 +455,14 @@ def test_non_canonical_device_strings_are_kept_as_keys(kv, tmp_path, pciids):
     assert ds.maps.deviceNames["1b3"] == "0_GP102GL_QUADRO_P6000"       # prefix semantics (:388)
     assert len(ds.maps.deviceMap["1b38"]) == 2
     ds.close()
+    # the native host layer (C++ above the same C-ABI) carries them the same way
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                       "kubevirt-gpu-device-plugin_b200", "kvg-discover")
+    r = subprocess.run([exe, "--pci-ids", str(ids_path), "--sysfs-pci", base, "--sysfs-mdev", str(tmp_path / "nomdev"), "--dump"],
+                       capture_output=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == m.dump(pciids)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -38,8 +38,7 @@ int emu_classify_pci(const uint4* recs, uint32_t n, const uint32_t* nv_index, in
   const uint32_t epoch = 7;
   if (variant == 1) {
     op.out = (kvg_pci_surv*)surv_out;
-    std::vector<uint32_t> words(tiles + 2, 0);  // published tile counts: a fresh allocation is zero-filled
-    emu_launch(k_classify_oneshot<PciClassifyOp, T, R>, dim3((unsigned)(tiles ? tiles : 1)), T, op, words.data(), epoch);
+    emu_launch(k_classify_oneshot<PciClassifyOp, T, R>, dim3((unsigned)(tiles ? tiles : 1)), T, op, state.data(), epoch);
   } else if (tiles) {
     op.out = (kvg_pci_surv*)ragged.data();
     emu_launch(k_classify_ragged<PciClassifyOp, T, R>, dim3((unsigned)tiles), T, op, tile_count.data(), tile_max.data());

@@ -96,8 +96,6 @@ int emu_ordering(uint2* pairs_io, uint32_t n, const uint4* surv, uint32_t key_bi
   a.n_ptr = &o.n;
   a.perm = perm;
   a.state = state.data();
-  std::vector<uint32_t> words(T + 2, 0);  // published head counts: a fresh allocation is zero-filled
-  a.words = words.data();
   a.tile_heads = tile_heads.data();
   a.tile_off = tile_off.data();
   a.seg_key = seg_key;

@@ -85,7 +85,6 @@ static inline void st_stream(uint4* p, const uint4& v) { *p = v; }
 static inline uint64_t ld_relaxed_u64(const uint64_t* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 static inline void st_relaxed_u64(uint64_t* p, uint64_t v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
 static inline void st_relaxed_u32(uint32_t* p, uint32_t v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
-static inline uint32_t ld_relaxed_u32(const uint32_t* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 static inline uint4 ld_volatile_v4(const uint4* p) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(p);
   return uint4{__atomic_load_n(w, __ATOMIC_RELAXED), __atomic_load_n(w + 1, __ATOMIC_RELAXED),

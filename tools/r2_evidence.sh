@@ -17,6 +17,6 @@ PY
 B="python bench.py --steps 2 --warmup 3 --no-extra --no-cpu-baseline"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r02_launches.csv $B --big-files 0 --big-records 0 > $O/ncu_b.log 2>&1; tail -1 $O/ncu_b.log | cut -c1-200
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_order|k_classify|k_pciids' -s 33 -c 12 -o $O/r02_cfg2 -f $B --big-files 0 --big-records 0 > $O/ncu_c.log 2>&1; tail -1 $O/ncu_c.log | cut -c1-200
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pciids -s 9 -c 3 -o $O/r02_parse256 -f python tools/exp_parse.py > $O/ncu_p.log 2>&1; tail -1 $O/ncu_p.log | cut -c1-200
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pciids -s 9 -c 3 -o $O/r02_parse256 -f python tools/time_parse.py > $O/ncu_p.log 2>&1; tail -1 $O/ncu_p.log | cut -c1-200
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_classify_ragged|k_pack_survivors|k_order_scatter|k_order_hist|k_order_heads' -c 12 -o $O/r02_big -f python bench.py --steps 1 --warmup 3 --no-extra --no-cpu-baseline --big-files 0 --records 16 > $O/ncu_g.log 2>&1; tail -1 $O/ncu_g.log | cut -c1-200
 ls -la $O/r02_*
