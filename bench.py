@@ -6,8 +6,11 @@
 One "step" = one pass of the hot path over one batch of synthetic input:
   parse the full utils/pci.ids image (1,536,458 B) into the name table  +  classify / compact /
   bucket R synthetic PCI records (default 1,000,000 = BASELINE.json configs[1]).
-N > 1 (torchrun, one rank per GPU): every rank owns R records (weak scaling), classifies its shard
-and the survivors are all-gathered over NCCL; every rank then buckets the gathered list.
+N > 1 (torchrun, one rank per GPU): every rank owns R records (weak scaling), classifies its shard, keeps
+its survivors (its part of bdfToIommuMap) and sends every survivor once per map to the owner of its key
+(stores into the owners' peer windows over NVLink; --exchange nccl for the fallback); every rank buckets
+the keys it owns.  Before anything is timed every rank checks its part of the result against a numpy
+restatement of the oracle ("parity" in the JSON line; a mismatch aborts the run).
 
 value   records/s with inputs resident in HBM (CUDA events on the launching stream, L2 flushed
         between steps, max over ranks)

@@ -221,11 +221,14 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_shard_send(ShardArgs A, ShardPeer
 // k_shard_send keeps the chained scan: it serves the sizes where T^2 is not nothing.)
 // CW4 = uint4 loads per tile row: 4 * CW4 >= 1 + 2P.
 constexpr uint32_t CS_COUNT_BITS = 11;
+#ifndef KVG_CS_MINB_WIDE
+#define KVG_CS_MINB_WIDE 7  // the same for P >= 4 (more counters: more registers in the prefix loop)
+#endif
 #ifndef KVG_CS_MINB
 #define KVG_CS_MINB 7  // CTAs per SM asked of the P <= 3 instantiation: 7 x 148 >= the 977 tiles of a 1 M-record shard (one wave)
 #endif
 template <class Op, int THREADS, int ROWS, int CW4>
-__global__ void __launch_bounds__(THREADS, CW4 <= 2 ? KVG_CS_MINB : 1) k_classify_send(Op op, ShardArgs A, ShardPeers peers, const ShardCtrl* mine,
+__global__ void __launch_bounds__(THREADS, CW4 <= 2 ? KVG_CS_MINB : KVG_CS_MINB_WIDE) k_classify_send(Op op, ShardArgs A, ShardPeers peers, const ShardCtrl* mine,
                                                            uint32_t* err, uint32_t* tile_words, uint32_t epoch) {
   pdl_enter();
   constexpr int U = Op::UNITS;
@@ -239,6 +242,12 @@ __global__ void __launch_bounds__(THREADS, CW4 <= 2 ? KVG_CS_MINB : 1) k_classif
   __shared__ uint32_t s_wtot[NW], s_woff[NW];
   __shared__ uint32_t s_agg[CW], s_excl[CW];
   __shared__ uint32_t s_part[NW][CW];
+  // the tile's survivors, staged in tile order: the registers that held the records are free during the prefix
+  // below (the P = 8 instantiation needed 118 registers = 4 CTAs per SM = two waves of tiles without this), and
+  // the rank's own list is then written with consecutive threads on consecutive records
+  __shared__ uint4 s_rec[TILE * U];
+  __shared__ uint32_t s_meta[TILE];  // warp | position among the warp's survivors of the same (ordering, owner): 2 + 8 + 8 bits
+  static_assert(NW <= 4, "the warp index has two bits in s_meta");
   op.begin();
   const uint32_t n = op.count();
   const uint32_t n_tiles = (n + TILE - 1) / TILE;
@@ -306,6 +315,24 @@ __global__ void __launch_bounds__(THREADS, CW4 <= 2 ? KVG_CS_MINB : 1) k_classif
     }
     if (lane == 0) s_wtot[warp] = wtot;
     __syncthreads();
+    {
+      uint32_t l = 0;
+#pragma unroll
+      for (uint32_t w = 0; w < NW; w++)
+        if (w < warp) l += s_wtot[w];
+#pragma unroll
+      for (int k = 0; k < ROWS; k++) {
+        if ((bal[k] >> lane) & 1u) {
+          const uint32_t my = l + __popc(bal[k] & lanemask_lt());
+          uint4 rec[U];
+          op.make(item[k], base + k * 32 + lane, aux[k], rec);
+#pragma unroll
+          for (int u = 0; u < U; u++) s_rec[my * U + u] = rec[u];
+          s_meta[my] = warp | (((pos0[k >> 2] >> (8 * (k & 3))) & 0xffu) << 2) | (((pos1[k >> 2] >> (8 * (k & 3))) & 0xffu) << 10);
+        }
+        l += __popc(bal[k]);
+      }
+    }
     // counts of the tile -> published words; the warps' counts become prefixes over the warps in place
     if (warp == 0) {
       for (uint32_t c = lane; c < CW; c += 32) {
@@ -381,28 +408,40 @@ __global__ void __launch_bounds__(THREADS, CW4 <= 2 ? KVG_CS_MINB : 1) k_classif
       }
     }
     __syncthreads();
-    // survivors: to the rank's dense list (Walk order) and, once per ordering, to the owner's window
-    uint32_t off = s_excl[0] + s_woff[warp];
-#pragma unroll
-    for (int k = 0; k < ROWS; k++) {
-      const uint32_t i = base + k * 32 + lane;
-      if ((bal[k] >> lane) & 1u) {
-        op.emit(off + __popc(bal[k] & lanemask_lt()), item[k], i, aux[k]);
+    // survivors: to the rank's dense list (Walk order; consecutive threads, consecutive records) and, once per
+    // ordering, to the owner's window
+    {
+      const uint32_t tile_total = s_agg[0];
+      const size_t out0 = s_excl[0];
+      uint4* out = reinterpret_cast<uint4*>(op.out);
+      uint32_t mx0 = 0, mx1 = 0;
+      for (uint32_t l = tid; l < tile_total; l += THREADS) {
         uint4 rec[U];
-        op.make(item[k], i, aux[k], rec);
-        const uint2 key = op.keys(item[k], aux[k]);
+#pragma unroll
+        for (int u = 0; u < U; u++) rec[u] = s_rec[l * U + u];
+        const uint32_t meta = s_meta[l];
+#pragma unroll
+        for (int u = 0; u < U; u++) st_stream(out + (out0 + l) * U + u, rec[u]);
+        const uint2 key = shard_keys<U>(rec);
+        mx0 = max(mx0, key.x);
+        mx1 = max(mx1, key.y);
 #pragma unroll
         for (uint32_t o = 0; o < 2; o++) {
           const uint32_t q = shard_owner(o ? key.y : key.x, A);
-          const uint32_t at = s_excl[1 + o * A.P + q] + s_wcnt[warp][o][q] + (((o ? pos1 : pos0)[k >> 2] >> (8 * (k & 3))) & 0xffu);
+          const uint32_t at = s_excl[1 + o * A.P + q] + s_wcnt[meta & 3u][o][q] + ((meta >> (2 + 8 * o)) & 0xffu);
           uint4* dst = peers.win[q] + shard_region(A, o, A.src, U) + (size_t)at * U;
 #pragma unroll
           for (int u = 0; u < U; u++) dst[u] = rec[u];  // NVLink store (or local)
         }
       }
-      off += __popc(bal[k]);
+      // largest keys of the shard (the radix plans): ordering 0 -> max_devkey, ordering 1 -> max_group
+      mx0 = warp_max(mx0);
+      mx1 = warp_max(mx1);
+      if (lane == 0) {
+        if (mx0) atomicMax(&op.ctrl->max_devkey, mx0);
+        if (mx1) atomicMax(&op.ctrl->max_group, mx1);
+      }
     }
-    op.tile_epilogue();
   }
   // nothing is published here: the grid's completion is the fence (see k_shard_gather)
 }

@@ -12,7 +12,7 @@ import re
 import numpy as np
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-LIB_PATH = os.environ.get("KVG_LIB") or os.path.join(_PKG, "libkvgpu.so")   # KVG_LIB: A/B builds of the same source
+LIB_PATH = os.path.join(_PKG, "libkvgpu.so")
 HEADER_PATH = os.path.join(os.path.dirname(_PKG), "include", "kvgpu.h")
 
 KVG_OK, KVG_EINVAL, KVG_ECUDA, KVG_ENOMEM, KVG_ENCCL, KVG_ESTATE, KVG_ERANGE = 0, -1, -2, -3, -4, -5, -6

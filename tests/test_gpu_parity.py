@@ -258,6 +258,20 @@ def test_scan_beside_a_reparse_on_the_side_stream(kv, pciids):
             res = ctx.dev_scan_pci_fetch()
             assert kv.canonical_dump(kv.pci_maps_from_result(res)) == _pci_dump_oracle(recs, pciids), (rep, n)
             del d
+        # the split classify / split final path (>= 2 Mi records): the deferred result must equal the plain one
+        n = 2_200_000
+        big = torch.empty(n * 16, dtype=torch.uint8, device="cuda")
+        ctx.dev_gen_pci(big.data_ptr(), 0, n, ids, 21)
+        ctx.dev_scan_pci(big.data_ptr(), n)
+        plain = ctx.dev_scan_pci_fetch()
+        ctx.dev_pciids_parse(d_text.data_ptr(), len(pciids), pad + 16, 1)
+        ctx.dev_scan_pci(big.data_ptr(), n)
+        late = ctx.dev_scan_pci_fetch()
+        assert np.array_equal(plain.survivors, late.survivors)
+        for f in ("dev_keys", "dev_off", "dev_perm", "dev_name_slot", "grp_keys", "grp_off", "grp_perm"):
+            assert np.array_equal(getattr(plain, f), getattr(late, f)), f
+        assert int((plain.survivors["name_slot"] != 0xffffffff).sum()) > 0
+        del big, plain, late
         # a consumer that is not the PCI device scan right after a re-parse
         ctx.dev_pciids_parse(d_text.data_ptr(), len(pciids), pad + 16, 1)
         assert ctx.name_lookup(b"1b38") == O.get_device_name(pciids, b"1b38")

@@ -1,5 +1,6 @@
 #!/bin/bash
 # round-2 evidence run (one GPU): tests, bench both arms, ncu launch list + full captures -> gpurun_out/r02_*
+# (then: python tools/summarize_profiles.py r02 ... ; python tools/sass_report.py r02 ; python tools/fill_docs.py r02)
 O=gpurun_out
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -5 > $O/r02_pytest_gpu.log; cat $O/r02_pytest_gpu.log
 KVG_CLOCKS_CSV=$O/r02_clocks_n1.csv timeout 900 python bench.py --steps 20 --warmup 5 2>$O/r02_bench_n1.err > $O/r02_bench_n1.json; echo "bench exit $?"
@@ -19,4 +20,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_order|k_classify|k_pciids' -s 33 -c 12 -o $O/r02_cfg2 -f $B --big-files 0 --big-records 0 > $O/ncu_c.log 2>&1; tail -1 $O/ncu_c.log | cut -c1-200
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pciids -s 9 -c 3 -o $O/r02_parse256 -f python tools/time_parse.py > $O/ncu_p.log 2>&1; tail -1 $O/ncu_p.log | cut -c1-200
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_classify_ragged|k_pack_survivors|k_order_scatter|k_order_hist|k_order_heads' -c 12 -o $O/r02_big -f python bench.py --steps 1 --warmup 3 --no-extra --no-cpu-baseline --big-files 0 --records 16 > $O/ncu_g.log 2>&1; tail -1 $O/ncu_g.log | cut -c1-200
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k_classify_send|k_shard_gather' -s 12 -c 2 -o $O/r02_shard -f python tools/time_shard.py > $O/ncu_s.log 2>&1; tail -1 $O/ncu_s.log | cut -c1-200
 ls -la $O/r02_*
