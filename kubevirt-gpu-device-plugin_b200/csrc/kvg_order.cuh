@@ -69,7 +69,10 @@ struct OrdArgs {
   const void* src_records;  // survivors (pass 0)
   const uint2* pairs_in;    // {key, index} (passes >= 1)
   uint2* pairs_out;
-  uint32_t* tile_hist;      // [digit][T]  (T = ceil(n / C_TILE)), digit-major
+  uint32_t* tile_hist;      // tile_major = 0: [digit][T] (T = ceil(n / C_TILE)); 1: [T][D] (D = digits padded to 256)
+  uint32_t tile_major;      // 1 at latency-bound sizes: the histogram kernel writes a tile's counts as ONE contiguous
+                            // row and the scatter kernel reads its eight digits as ONE 32-byte load (digit-major,
+                            // each was 1024-2048 scattered 4-byte accesses per CTA); the tile scan then walks columns
   uint32_t* bin_total;      // [RADIX_MAX_DIGITS] digit totals of this pass
   uint32_t pass;            // 0xff: this ordering has no such launch set
   uint32_t key_bits_max;    // 16 (device id / type) or 32 (iommu group / parent)
@@ -123,7 +126,10 @@ __device__ __forceinline__ void ord_hist_tiles(const OrdArgs& a, const RadixPlan
     __syncthreads();
     for (uint32_t j = 0; j < nj; j++) {
       const uint32_t dg = j * KVG_BLOCK + threadIdx.x;
-      a.tile_hist[(size_t)dg * T + tile] = h[dg];
+      if (a.tile_major)
+        a.tile_hist[(size_t)tile * (nj * KVG_BLOCK) + dg] = h[dg];
+      else
+        a.tile_hist[(size_t)dg * T + tile] = h[dg];
     }
     __syncthreads();
   }
@@ -206,6 +212,83 @@ __global__ void __launch_bounds__(KVG_BLOCK) k_order_tilescan_long(OrdArgs2 aa) 
   }
 }
 
+// tile-major layout: one CTA per group of 32 digits (a lane per digit: coalesced rows), its 8 warps split the
+// tiles; pass 1 sums a warp's slice per digit, the slices are combined in shared memory, pass 2 rewrites the
+// slice as exclusive prefixes.  64 CTAs per ordering at 11-bit digits: one wave.
+__global__ void __launch_bounds__(KVG_BLOCK) k_order_tilescan_cols(OrdArgs2 aa) {
+  pdl_enter();
+  const OrdArgs a = blockIdx.y ? aa.o[1] : aa.o[0];
+  const RadixPlan pl = ord_pass(a);
+  if (!pl.bits) return;
+  const uint32_t n = *a.n_ptr;
+  const uint32_t T = (n + C_TILE - 1) / C_TILE;
+  if (T == 0) return;
+  const uint32_t D = (((1u << pl.bits) + KVG_BLOCK - 1) / KVG_BLOCK) * KVG_BLOCK;
+  __shared__ uint32_t s_part[KVG_WARPS][32];
+  const uint32_t lane = lane_id(), warp = warp_id();
+  const uint32_t per = (T + KVG_WARPS - 1) / KVG_WARPS;
+  const uint32_t t0 = min(T, warp * per), t1 = min(T, t0 + per);
+  for (uint32_t g = blockIdx.x; g * 32 < D; g += gridDim.x) {
+    uint32_t* col = a.tile_hist + g * 32 + lane;
+    if (per <= 32) {
+      // the whole slice of a lane fits in registers (up to 256 tiles, i.e. 512 K elements): ONE read with every
+      // load in flight, one write
+      uint32_t v[32];
+      uint32_t sum = 0;
+#pragma unroll
+      for (uint32_t k = 0; k < 32; k++) v[k] = t0 + k < t1 ? col[(size_t)(t0 + k) * D] : 0;
+#pragma unroll
+      for (uint32_t k = 0; k < 32; k++) sum += v[k];
+      s_part[warp][lane] = sum;
+      __syncthreads();
+      uint32_t run = 0, total = 0;
+#pragma unroll
+      for (uint32_t w = 0; w < KVG_WARPS; w++) {
+        const uint32_t c = s_part[w][lane];
+        if (w < warp) run += c;
+        total += c;
+      }
+      if (warp == 0) a.bin_total[g * 32 + lane] = total;
+#pragma unroll
+      for (uint32_t k = 0; k < 32; k++) {
+        if (t0 + k < t1) col[(size_t)(t0 + k) * D] = run;
+        run += v[k];
+      }
+      __syncthreads();  // s_part is rewritten by the next group
+      continue;
+    }
+    uint32_t sum = 0;
+    for (uint32_t t = t0; t < t1; t += 8) {  // eight independent loads per round
+      uint32_t v[8];
+#pragma unroll
+      for (uint32_t k = 0; k < 8; k++) v[k] = t + k < t1 ? col[(size_t)(t + k) * D] : 0;
+#pragma unroll
+      for (uint32_t k = 0; k < 8; k++) sum += v[k];
+    }
+    s_part[warp][lane] = sum;
+    __syncthreads();
+    uint32_t run = 0, total = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < KVG_WARPS; w++) {
+      const uint32_t c = s_part[w][lane];
+      if (w < warp) run += c;
+      total += c;
+    }
+    if (warp == 0) a.bin_total[g * 32 + lane] = total;
+    for (uint32_t t = t0; t < t1; t += 8) {
+      uint32_t v[8];
+#pragma unroll
+      for (uint32_t k = 0; k < 8; k++) v[k] = t + k < t1 ? col[(size_t)(t + k) * D] : 0;
+#pragma unroll
+      for (uint32_t k = 0; k < 8; k++) {
+        if (t + k < t1) col[(size_t)(t + k) * D] = run;
+        run += v[k];
+      }
+    }
+    __syncthreads();  // s_part is rewritten by the next group
+  }
+}
+
 // ---- scatter ------------------------------------------------------------------------------------
 // dynamic shared memory: per-warp digit counts (u16: a warp owns 256 items), tile-local digit starts,
 // global run offsets, the staged tile
@@ -235,6 +318,7 @@ __device__ __forceinline__ void ord_scatter_tiles(const OrdArgs& a, const RadixP
   const uint32_t lane = lane_id(), warp = warp_id(), tid = threadIdx.x;
   const uint32_t d0 = tid * DPT;  // my digits: d0 .. d0 + DPT - 1
   const bool mine = d0 < digits;
+  const uint32_t DP = ((digits + KVG_BLOCK - 1) / KVG_BLOCK) * KVG_BLOCK;  // row pitch of the tile-major layout
   uint16_t (*s_cnt)[Cfg::DIGITS] = reinterpret_cast<uint16_t (*)[Cfg::DIGITS]>(rs_smem);
   uint16_t* s_start = reinterpret_cast<uint16_t*>(rs_smem + Cfg::CNT_BYTES);
   int32_t* s_goff = reinterpret_cast<int32_t*>(rs_smem + Cfg::CNT_BYTES + Cfg::START_BYTES);
@@ -248,7 +332,9 @@ __device__ __forceinline__ void ord_scatter_tiles(const OrdArgs& a, const RadixP
     uint32_t tile_prefix[DPT];
 #pragma unroll
     for (uint32_t q = 0; q < DPT; q++)
-      tile_prefix[q] = (mine && d0 + q < digits) ? a.tile_hist[(size_t)(d0 + q) * T + tile] : 0;
+      tile_prefix[q] = (mine && d0 + q < digits)
+                           ? (a.tile_major ? a.tile_hist[(size_t)tile * DP + d0 + q] : a.tile_hist[(size_t)(d0 + q) * T + tile])
+                           : 0;
     uint2 kv[C_ROWS];
     uint32_t rank[C_ROWS];
 #pragma unroll

@@ -39,7 +39,7 @@ def expected(keys):
 
 
 CASES = [  # (n, key bits in the data, key_bits_max, max_bits)
-    (1, 1, 32, 11), (31, 5, 16, 11), (2049, 11, 32, 11), (3000, 12, 32, 11),
+    (1, 1, 32, 11), (31, 5, 16, 11), (2049, 11, 32, 11), (3000, 12, 32, 11), (40_000, 17, 32, 11),
     (5000, 19, 32, 11), (2500, 23, 32, 11), (2200, 32, 32, 11), (2300, 16, 16, 11), (2600, 24, 32, 8),
 ]
 
@@ -55,10 +55,11 @@ def test_device_radix_sort_is_a_stable_sort(emu):
         keys[rng.integers(0, n)] = (1 << bits) - 1          # the widest key is present: the plan sees it
         if n > 100:
             keys[rng.integers(0, n, n // 3)] = keys[0]       # a heavy bucket: long runs of equal keys
-        got, npass = device_sort(emu, keys, kmax, mb, 0)
         want_k, want_i = expected(keys)
-        assert npass == want_passes(bits, kmax, mb), (n, bits, mb)
-        assert np.array_equal(got["key"], want_k) and np.array_equal(got["idx"], want_i), (n, bits, kmax, mb)
+        for layout in (0, 1):   # histogram layout: digit-major (row tile scan) / tile-major (column tile scan)
+            got, npass = device_sort(emu, keys, kmax, mb, layout)
+            assert npass == want_passes(bits, kmax, mb), (n, bits, mb)
+            assert np.array_equal(got["key"], want_k) and np.array_equal(got["idx"], want_i), (n, bits, kmax, mb, layout)
 
 
 def test_skewed_input(emu):
@@ -66,9 +67,10 @@ def test_skewed_input(emu):
     keys = np.concatenate([np.full(3000, 7, np.uint32), rng.integers(0, 1 << 19, 1500, dtype=np.uint64).astype(np.uint32),
                            np.zeros(700, np.uint32)])
     rng.shuffle(keys)
-    a, _ = device_sort(emu, keys, 32, 11, 0)
     want_k, want_i = expected(keys)
-    assert np.array_equal(a["key"], want_k) and np.array_equal(a["idx"], want_i)
+    for layout in (0, 1):
+        a, _ = device_sort(emu, keys, 32, 11, layout)
+        assert np.array_equal(a["key"], want_k) and np.array_equal(a["idx"], want_i), layout
 
 
 def test_whole_ordering_permutation_segments_and_bucket_names(emu):

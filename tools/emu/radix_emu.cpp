@@ -17,6 +17,7 @@ using namespace kvg;
 namespace {
 struct Ordering {
   uint32_t n, max_key, key_bits_max, max_bits;
+  uint32_t tile_major = 0;  // histogram layout (OrdArgs::tile_major)
   size_t T;
   std::vector<uint2> p0, p1;
   std::vector<uint32_t> hist, bins;
@@ -44,11 +45,15 @@ struct Ordering {
       a.key_bits_max = key_bits_max;
       a.max_bits = max_bits;
       a.src = SRC_PAIRS;
+      a.tile_major = tile_major;
       OrdArgs2 aa;
       aa.o[0] = a;
       aa.o[1] = a;
       emu_launch(k_order_hist, dim3((unsigned)T, 1), KVG_BLOCK, aa);
-      emu_launch(k_order_tilescan, dim3((1u << max_bits) / TS_WARPS, 1), TS_WARPS * 32, aa);
+      if (tile_major)
+        emu_launch(k_order_tilescan_cols, dim3((1u << max_bits) / 32, 1), KVG_BLOCK, aa);
+      else
+        emu_launch(k_order_tilescan, dim3((1u << max_bits) / TS_WARPS, 1), TS_WARPS * 32, aa);
       if (max_bits == 8)
         emu_launch(k_order_scatter<8>, dim3((unsigned)T, 1), KVG_BLOCK, aa);
       else
@@ -63,9 +68,10 @@ extern "C" {
 
 // Stable sort of {key, index} pairs the way the device does it.  pairs_io: n x {key, index}; on return the
 // sorted pairs.  Returns the pass count the device-side plan chose, or a negative number.
-int emu_radix_sort(uint2* pairs_io, uint32_t n, uint32_t key_bits_max, uint32_t max_bits, int /*variant*/) {
+int emu_radix_sort(uint2* pairs_io, uint32_t n, uint32_t key_bits_max, uint32_t max_bits, int variant) {
   if (max_bits != 8 && max_bits != RADIX_MAX_BITS) return -1;
   Ordering o(pairs_io, n, key_bits_max, max_bits);
+  o.tile_major = variant == 1 && max_bits == RADIX_MAX_BITS ? 1u : 0u;  // variant 1: the tile-major histogram layout
   const int np = o.sort();
   memcpy(pairs_io, (((np - 1) & 1) ? o.p1 : o.p0).data(), sizeof(uint2) * n);
   return np;
@@ -79,6 +85,7 @@ int emu_ordering(uint2* pairs_io, uint32_t n, const uint4* surv, uint32_t key_bi
                  uint32_t* seg_key, uint32_t* seg_off, uint32_t* seg_name, int fused, const uint32_t* join_table, int join_mode) {
   if (max_bits != 8 && max_bits != RADIX_MAX_BITS) return -1;
   Ordering o(pairs_io, n, key_bits_max, max_bits);
+  o.tile_major = fused && max_bits == RADIX_MAX_BITS ? 1u : 0u;  // the latency-bound form uses the tile-major layout
   o.sort();
   const size_t T = o.T;
   std::vector<uint64_t> state(T + 2, 0);

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """profiles/<tag>_sass_tma.txt: what the built libkvgpu.so contains, per kernel — the SASS mnemonics that prove the
 sm_100a features the design relies on (UBLKCP = TMA bulk copy, SYNCS = mbarrier, REDUX = warp reduction,
-MATCH = match.any, RED/ATOM = fire-and-forget / returning atomics, ACQBULK/griddepcontrol = programmatic
+MATCH = match.any, REDG / ATOMG = fire-and-forget / returning global atomics, ACQBULK/griddepcontrol = programmatic
 dependent launch), with registers and shared memory.   python tools/sass_report.py r02"""
 import collections, os, re, subprocess, sys
 tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
@@ -13,7 +13,7 @@ arch = sorted(set(re.findall(r"arch = (sm_\w+)", sass)))
 usage = {}
 for m in re.finditer(r"Function (\S+):\n\s+REG:(\d+) STACK:(\d+) SHARED:(\d+)", res):
     usage[m.group(1)] = (int(m.group(2)), int(m.group(3)), int(m.group(4)))
-want = ["UBLKCP", "SYNCS", "REDUX", "MATCH", "RED", "ATOMG", "ATOMS", "MEMBAR", "ACQBULK", "CCTL", "LDS", "STS", "LDG", "STG"]
+want = ["UBLKCP", "SYNCS", "REDUX", "MATCH", "REDG", "ATOMG", "ATOMS", "MEMBAR", "ACQBULK", "CCTL", "LDS", "STS", "LDG", "STG"]
 rows, cur, cnt, n = [], None, None, 0
 def flush():
     if cur:
