@@ -1,7 +1,7 @@
 // kvg_parse.cuh — pci.ids on the GPU, shared pieces: getDeviceName / locateVendor of the reference
 // (pkg/device_plugin/device_plugin.go:371-438) turned into a build-once table.
 //
-//   (K1 lives in kvg_parse_k1.cuh: prep -> scan -> resolve + finalize -> names)
+//   (K1 lives in kvg_parse_k1.cuh: scan -> resolve + finalize -> names, self-cleaning)
 //   SWAR newline masks, lower-hex field parse
 //   the name transform of :404-414 (serial exact routine + warp-cooperative fast path)
 //   k_section_lines / k_lookup_general / k_sanitise_matches   exact prefix semantics of :388-402 for

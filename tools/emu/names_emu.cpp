@@ -1,5 +1,5 @@
 // names_emu.cpp — getDeviceName end to end from kernel source on the CPU: K1 (csrc/kvg_parse_k1.cuh:
-// prep -> scan with the per-warp TMA ring -> resolve + finalize -> names) followed by the lookup path of
+// scan with the per-warp TMA ring -> resolve + finalize -> names) followed by the lookup path of
 // csrc/kvg_parse.cuh exactly as the library sequences it (kvg_api.cu: parse_enqueue, table_publish,
 // kvg_name_lookup, lookup_general):
 //   table path     nv_index[id] -> pool[slot] = u16 length + bytes        (4-lower-hex keys)
