@@ -64,11 +64,6 @@ __device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
                : "memory");
   return r;
 }
-__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 
 // ---- mbarrier + TMA 1-D bulk copy ---------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -110,9 +105,6 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
       : "memory");
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 // named barriers (id 1..15; id 0 is __syncthreads): producer/consumer hand-off inside a CTA
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -160,27 +152,6 @@ __device__ __forceinline__ uint32_t block_excl_sum(uint32_t v, uint32_t* scratch
   *total = scratch[KVG_WARPS];
   return r;
 }
-// Block-wide exclusive max (identity 0); *total receives the block max.  Two __syncthreads().
-__device__ __forceinline__ uint32_t block_excl_max(uint32_t v, uint32_t* scratch, uint32_t* total) {
-  uint32_t incl = warp_incl_max(v);
-  uint32_t excl_in_warp = __shfl_up_sync(KVG_FULL, incl, 1);
-  if (lane_id() == 0) excl_in_warp = 0;
-  if (lane_id() == 31) scratch[warp_id()] = incl;
-  __syncthreads();
-  if (warp_id() == 0) {
-    uint32_t w = lane_id() < KVG_WARPS ? scratch[lane_id()] : 0;
-    uint32_t wi = warp_incl_max(w);
-    uint32_t we = __shfl_up_sync(KVG_FULL, wi, 1);
-    if (lane_id() == 0) we = 0;
-    if (lane_id() < KVG_WARPS) scratch[lane_id()] = we;
-    if (lane_id() == KVG_WARPS - 1) scratch[KVG_WARPS] = wi;
-  }
-  __syncthreads();
-  uint32_t r = max(scratch[warp_id()], excl_in_warp);
-  *total = scratch[KVG_WARPS];
-  return r;
-}
-
 // ---- decoupled look-back ------------------------------------------------------------------------
 // One 64-bit word per tile: [63:34] launch epoch, [33:32] status, [31:0] value.  The epoch makes a
 // stale word from an earlier launch read as "not ready", so the array never needs clearing.
@@ -235,40 +206,6 @@ __device__ __forceinline__ uint32_t lookback_sum(uint64_t* state, uint32_t tile,
   }
   if (lane == 0) st_relaxed_u64(&state[tile], lb_pack(epoch, LB_INCLUSIVE, excl + aggregate));
   return excl;
-}
-
-// "Last writer wins" look-back (used for the pci.ids vendor context): a tile either defines a new
-// value (publishes INCLUSIVE immediately, no dependence on predecessors) or passes its
-// predecessor's value through.  Returns the value carried INTO `tile`; one full warp executes it.
-__device__ __forceinline__ uint32_t lookback_last(uint64_t* state, uint32_t tile, bool first_of_chain,
-                                                  bool defines, uint32_t own_value, uint32_t epoch) {
-  const uint32_t lane = lane_id();
-  if (defines && lane == 0) st_relaxed_u64(&state[tile], lb_pack(epoch, LB_INCLUSIVE, own_value));
-  if (first_of_chain) {
-    if (!defines && lane == 0) st_relaxed_u64(&state[tile], lb_pack(epoch, LB_INCLUSIVE, 0));
-    return 0;
-  }
-  if (!defines && lane == 0) st_relaxed_u64(&state[tile], lb_pack(epoch, LB_AGGREGATE, 0));
-  uint32_t carry;
-  int look = (int)tile - 1;
-  for (;;) {
-    int idx = look - (int)lane;
-    // idx < 0 cannot be reached: the first tile of a chain always publishes INCLUSIVE
-    uint64_t w = idx >= 0 ? ld_relaxed_u64(&state[idx]) : lb_pack(epoch, LB_INCLUSIVE, 0);
-    uint32_t st = lb_status(w, epoch);
-    uint32_t incl_mask = __ballot_sync(KVG_FULL, st == LB_INCLUSIVE);
-    uint32_t inv_mask = __ballot_sync(KVG_FULL, st == LB_INVALID);
-    uint32_t first = incl_mask ? (uint32_t)__ffs(incl_mask) - 1 : 32;
-    uint32_t need = first >= 31 ? KVG_FULL : ((2u << first) - 1);
-    if (inv_mask & need) continue;
-    if (first < 32) {
-      carry = __shfl_sync(KVG_FULL, (uint32_t)w, first);
-      break;
-    }
-    look -= 32;
-  }
-  if (!defines && lane == 0) st_relaxed_u64(&state[tile], lb_pack(epoch, LB_INCLUSIVE, carry));
-  return carry;
 }
 
 }  // namespace kvg

@@ -615,12 +615,6 @@ __global__ void k_fill(uint4* __restrict__ p, size_t n16, uint32_t v) {
        i += (size_t)gridDim.x * blockDim.x)
     p[i] = make_uint4(v, v, v, v);
 }
-__global__ void k_fill64(uint64_t* __restrict__ p, size_t n, uint64_t v) {
-  pdl_enter();
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
-       i += (size_t)gridDim.x * blockDim.x)
-    p[i] = v;
-}
 __global__ void k_fill32(uint32_t* __restrict__ p, size_t n, uint32_t v) {
   pdl_enter();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
